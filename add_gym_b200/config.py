@@ -1,0 +1,140 @@
+"""Default configuration of the ADD / G1 hot path.
+
+The reference composes four Hydra YAML groups into one dict
+``{"agent", "engine", "robot", "task"}`` (reference add_gym/configs/train.yaml:2-8,
+agent/add_g1.yaml, engine/genesis.yaml, robot/g1.yaml, task/pose.yaml).  The plugins only
+ever read it with ``[]`` / ``.get`` so a plain dict is the whole interface.  The values below
+restate those defaults; `default_config()` returns a fresh deep copy a caller may edit.
+"""
+import copy
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+ASSET_DIR = os.path.join(_HERE, "assets")
+
+# File order of the 29 hinge columns of a `.motion` row (reference configs/task/pose.yaml:31-60).
+MOTION_JOINT_ORDER = [
+    "left_hip_pitch_joint", "left_hip_roll_joint", "left_hip_yaw_joint", "left_knee_joint",
+    "left_ankle_pitch_joint", "left_ankle_roll_joint",
+    "right_hip_pitch_joint", "right_hip_roll_joint", "right_hip_yaw_joint", "right_knee_joint",
+    "right_ankle_pitch_joint", "right_ankle_roll_joint",
+    "waist_yaw_joint", "waist_roll_joint", "waist_pitch_joint",
+    "left_shoulder_pitch_joint", "left_shoulder_roll_joint", "left_shoulder_yaw_joint",
+    "left_elbow_joint", "left_wrist_roll_joint", "left_wrist_pitch_joint", "left_wrist_yaw_joint",
+    "right_shoulder_pitch_joint", "right_shoulder_roll_joint", "right_shoulder_yaw_joint",
+    "right_elbow_joint", "right_wrist_roll_joint", "right_wrist_pitch_joint",
+    "right_wrist_yaw_joint",
+]
+
+_AGENT = {
+    "model": {
+        "actor_net": "fc_3layers_1024units",
+        "actor_init_output_scale": 0.01,
+        "actor_std_type": "FIXED",
+        "action_std": 0.05,
+        "critic_net": "fc_3layers_1024units",
+        "disc_net": "fc_2layers_1024units",
+        # B200 path only: arithmetic of the MLP contractions.
+        #   "fp32"  : IEEE fp32 FMA on the CUDA cores (parity reference path)
+        #   "tf32x3": tcgen05 kind::tf32, 3-pass split (fp32-class accuracy)
+        #   "tf32"  : tcgen05 kind::tf32, single pass (what the reference runs on GPU, main.py:17-18)
+        #   "bf16"  : tcgen05 kind::f16 bf16 operands, fp32 accumulate (BASELINE config 4)
+        "mlp_precision": "fp32",
+    },
+    "optimizer": {"type": "Adam", "learning_rate": 1e-4},
+    "discount": 0.99,
+    "steps_per_iter": 32,
+    "iters_per_output": 100,
+    "test_episodes": 10,
+    "normalizer_samples": 100000000,
+    "update_epochs": 5,
+    "batch_size": 4,
+    "td_lambda": 0.95,
+    "ppo_clip_ratio": 0.2,
+    "norm_adv_clip": 4.0,
+    "action_bound_weight": 10.0,
+    "action_entropy_weight": 0.0,
+    "action_reg_weight": 0.0,
+    "critic_loss_weight": 1.0,
+    # Present in the reference YAML at agent level but never read from there:
+    # MPOptimizer looks in config["optimizer"], so clipping is off by default.
+    "grad_clip": 1.0,
+    "disc_loss_weight": 0.5,
+    "disc_logit_reg": 0.01,
+    "disc_grad_penalty": 20,
+    "disc_weight_decay": 0.0001,
+    "disc_reward_scale": 2,
+    "task_reward_weight": 0.0,
+    "disc_reward_weight": 1.0,
+    "max_samples": 99999999999999,
+}
+
+_ENGINE = {
+    "_target_": "add_gym_b200.engine.SyntheticEngine",
+    "num_envs": 4,
+    "env_spacing": 2.0,
+    "ctrl_dt": 0.01,
+    "video_interval": 5000,
+    "video_length": 20,
+    "visualize_camera": False,
+    "enable_viewer": True,
+    "enable_video_recording": False,
+}
+
+_ROBOT = {
+    "urdf_path": os.path.join(ASSET_DIR, "g1_29_kinematics.json"),
+    "gain_scale": 1.2,
+}
+
+_TASK = {
+    "reward": {"scales": {"pose": 1.0}},
+    "sampler": {"num_segments": 20},
+    "max_episode_length": 20,
+    "global_obs": True,
+    "root_height_obs": True,
+    "pose_termination": True,
+    "pose_termination_dist": 1.0,
+    "enable_phase_obs": False,
+    "enable_tar_obs": True,
+    "num_phase_encoding": 4,
+    "tar_obs_steps": [1, 2, 3, 4, 5, 6],
+    "num_disc_obs_steps": 3,
+    "rand_reset": True,
+    "zero_center_action": True,
+    "log_tracking_error": True,
+    "visualize_ref_char": False,
+    "ref_char_offset": [0, -2.0, 0.0],
+    "enable_early_termination": True,
+    "termination_height": 0.3,
+    "enable_vel_obs": False,
+    "contact_bodies": [
+        "left_knee_link", "left_ankle_pitch_link", "left_ankle_roll_link",
+        "right_knee_link", "right_ankle_pitch_link", "right_ankle_roll_link",
+    ],
+    "motion_file": os.path.join(ASSET_DIR, "walk1_subject1_trimmed.npy"),
+    "motion_joint_order": MOTION_JOINT_ORDER,
+    "reward_pose_w": 0.5,
+    "reward_vel_w": 0.1,
+    "reward_root_pose_w": 0.15,
+    "reward_root_vel_w": 0.1,
+    "reward_pose_scale": 0.25,
+    "reward_vel_scale": 0.01,
+    "reward_root_pose_scale": 5.0,
+    "reward_root_vel_scale": 1.0,
+}
+
+
+def default_config(num_envs=None, motion_file=None, mlp_precision=None):
+    cfg = {
+        "agent": copy.deepcopy(_AGENT),
+        "engine": copy.deepcopy(_ENGINE),
+        "robot": copy.deepcopy(_ROBOT),
+        "task": copy.deepcopy(_TASK),
+    }
+    if num_envs is not None:
+        cfg["engine"]["num_envs"] = int(num_envs)
+    if motion_file is not None:
+        cfg["task"]["motion_file"] = motion_file
+    if mlp_precision is not None:
+        cfg["agent"]["model"]["mlp_precision"] = mlp_precision
+    return cfg

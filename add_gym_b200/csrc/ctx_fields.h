@@ -1,0 +1,104 @@
+// Field table of addk_update_ctx (X-macros).  The C++ side expands it into the struct and into the
+// loader behind addk_update_ctx_init(); add_gym_b200/_lib.py parses this very file to learn the order,
+// so the two sides cannot drift apart.
+//
+//   ADDK_PTR(name)   device pointer       ADDK_INT(name)   int64      ADDK_F64(name)   double
+// clang-format off
+#ifndef ADDK_PTR
+#define ADDK_PTR(n)
+#endif
+#ifndef ADDK_INT
+#define ADDK_INT(n)
+#endif
+#ifndef ADDK_F64
+#define ADDK_F64(n)
+#endif
+
+// ---- flat parameter vector and optimizer state (22 trainable tensors, reference order) ----------
+ADDK_PTR(params)        // [P] fp32
+ADDK_PTR(grads)         // [P] fp32, reduced gradient of the last minibatch
+ADDK_PTR(slabs)         // [2*split_k, P] split-K partial weight gradients
+ADDK_PTR(exp_avg)       // [P]
+ADDK_PTR(exp_avg_sq)    // [P]
+// ---- normalizers ----------------------------------------------------------------------------------
+ADDK_PTR(obs_mean)      // [obs_dim]
+ADDK_PTR(obs_std)
+ADDK_PTR(a_mean)        // [act_dim]
+ADDK_PTR(a_std)
+ADDK_PTR(disc_mean_abs) // [disc_dim]
+ADDK_PTR(logstd)        // [act_dim] _action_dist._logstd_net (frozen)
+// ---- flat [T*N, ...] experience buffers -------------------------------------------------------------
+ADDK_PTR(buf_obs)
+ADDK_PTR(buf_action)
+ADDK_PTR(buf_a_logp)
+ADDK_PTR(buf_adv)
+ADDK_PTR(buf_tar_val)
+ADDK_PTR(buf_mask)
+ADDK_PTR(buf_disc_obs)
+ADDK_PTR(buf_disc_demo)
+// ---- minibatch workspace (R = mb_rows + 1 rows; the extra row is the discriminator's "zero diff" sample)
+ADDK_PTR(xn)            // [R, obs_dim]     normalised obs
+ADDK_PTR(an)            // [R, act_ld]      normalised action
+ADDK_PTR(old_logp)      // [R]
+ADDK_PTR(adv)           // [R]
+ADDK_PTR(tar)           // [R]
+ADDK_PTR(mask)          // [R]
+ADDK_PTR(dn)            // [R, disc_ld]     normalised (demo - agent) difference, row mb_rows = 0
+ADDK_PTR(h1)            // [R, 1024]
+ADDK_PTR(h2)            // [R, 1024]
+ADDK_PTR(h3)            // [R, 512]
+ADDK_PTR(g1)            // [R, 1024]
+ADDK_PTR(g2)            // [R, 1024]
+ADDK_PTR(g3)            // [R, 512]
+ADDK_PTR(u1)            // [R, 1024]
+ADDK_PTR(u2)            // [R, 512]
+ADDK_PTR(gx)            // [R, disc_ld]
+ADDK_PTR(dg)            // [R, disc_ld]
+ADDK_PTR(mean)          // [R, act_ld]
+ADDK_PTR(dmean)         // [R, act_ld]
+ADDK_PTR(pred)          // [R]
+ADDK_PTR(dpred)         // [R]
+ADDK_PTR(ones)          // [R] all 1.0f
+ADDK_PTR(stats)         // [32] double accumulators of the current minibatch
+ADDK_PTR(info)          // [max_steps, 16] float diagnostics, one row per optimizer step
+ADDK_PTR(cnt)           // [1] int: rows of the minibatch with rand_action_mask == 1
+
+ADDK_INT(obs_dim)
+ADDK_INT(act_dim)
+ADDK_INT(disc_dim)
+ADDK_INT(act_ld)        // act_dim rounded up to a multiple of 4
+ADDK_INT(disc_ld)       // disc_dim rounded up to a multiple of 4
+ADDK_INT(mb_rows)       // minibatch rows M
+ADDK_INT(num_params)    // P (including alignment padding)
+ADDK_INT(split_k)
+ADDK_INT(precision)     // 0 fp32 | 1 tf32x3 | 2 tf32 | 3 bf16
+ADDK_INT(hid_a1)        // actor/critic hidden sizes (1024, 1024, 512)
+ADDK_INT(hid_a2)
+ADDK_INT(hid_a3)
+ADDK_INT(hid_d1)        // discriminator hidden sizes (1024, 512)
+ADDK_INT(hid_d2)
+// offsets (in floats) of the 22 tensors inside the flat vector
+ADDK_INT(o_a_w0) ADDK_INT(o_a_b0) ADDK_INT(o_a_w1) ADDK_INT(o_a_b1) ADDK_INT(o_a_w2) ADDK_INT(o_a_b2)
+ADDK_INT(o_a_wm) ADDK_INT(o_a_bm)
+ADDK_INT(o_c_w0) ADDK_INT(o_c_b0) ADDK_INT(o_c_w1) ADDK_INT(o_c_b1) ADDK_INT(o_c_w2) ADDK_INT(o_c_b2)
+ADDK_INT(o_c_wo) ADDK_INT(o_c_bo)
+ADDK_INT(o_d_w0) ADDK_INT(o_d_b0) ADDK_INT(o_d_w1) ADDK_INT(o_d_b1) ADDK_INT(o_d_wl) ADDK_INT(o_d_bl)
+
+ADDK_F64(ppo_clip_ratio)
+ADDK_F64(action_bound_weight)
+ADDK_F64(critic_loss_weight)
+ADDK_F64(disc_loss_weight)
+ADDK_F64(disc_logit_reg)
+ADDK_F64(disc_grad_penalty)
+ADDK_F64(disc_weight_decay)
+ADDK_F64(lr)
+ADDK_F64(beta1)
+ADDK_F64(beta2)
+ADDK_F64(adam_eps)
+ADDK_F64(weight_decay)
+ADDK_F64(grad_scale)    // 1/world_size when gradients were summed across ranks, else 1
+
+#undef ADDK_PTR
+#undef ADDK_INT
+#undef ADDK_F64
+// clang-format on

@@ -1,0 +1,244 @@
+// Returns, advantages, discriminator reward, running statistics and AdamW: the HBM-bound
+// elementwise / reduction stages of one training iteration.
+//
+// Replaces (reference add_gym/learning/):
+//   compute_td_lambda_return + next_vals masking + adv   base_agent.py:624-647, ppo_agent.py:126-146
+//   advantage std_mean / normalise / clamp                 ppo_agent.py:147-153
+//   AMPAgent._calc_disc_rewards tail, reward mix           amp_agent.py:201-205, add_agent.py:124-133
+//   Normalizer.record/update, DiffNormalizer.record/update normalizer.py:25-80, diff_normalizer.py:24-45
+//   torch.optim.AdamW (single tensor semantics)            mp_optimizer.py:38
+// Reductions accumulate in fp64 and are combined with fp64 atomics (two numbers per block), so they are
+// at least as accurate as the reference's fp32 cascade sums; elementwise formulas keep its op order.
+#include "common.cuh"
+#include "addk.h"
+
+namespace addk {
+
+// thread per env, serial over T (reverse), coalesced over N
+__global__ void td_lambda_kernel(const float* __restrict__ reward, const float* __restrict__ next_vals,
+                                 const float* __restrict__ vals, const int32_t* __restrict__ done, int T, int N,
+                                 float discount, float td_lambda, float succ_val, float fail_val,
+                                 float* __restrict__ tar_val, float* __restrict__ adv) {
+  int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float next_ret = 0.f;
+  for (int t = T - 1; t >= 0; --t) {
+    size_t i = (size_t)t * N + n;
+    float nv = next_vals[i];
+    int d = done[i];
+    if (d == 2) nv = succ_val;
+    if (d == 1) nv = fail_val;
+    float r = reward[i], ret;
+    if (t == T - 1) {
+      ret = add_rn(r, mul_rn(discount, nv));
+    } else {
+      float reset = (d != 0) ? 1.0f : 0.0f;
+      float lam = mul_rn(td_lambda, sub_rn(1.0f, reset));
+      ret = add_rn(r, mul_rn(discount, add_rn(mul_rn(sub_rn(1.0f, lam), nv), mul_rn(lam, next_ret))));
+    }
+    tar_val[i] = ret;
+    adv[i] = sub_rn(ret, vals[i]);
+    next_ret = ret;
+  }
+}
+
+__global__ void masked_moments_kernel(const float* __restrict__ x, const float* __restrict__ mask, int n,
+                                      double* __restrict__ work3) {
+  __shared__ double sm[32];
+  double s = 0.0, s2 = 0.0, c = 0.0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    if (!mask || mask[i] == 1.0f) { double v = x[i]; s += v; s2 += v * v; c += 1.0; }
+  }
+  s = block_sum(s, sm); s2 = block_sum(s2, sm); c = block_sum(c, sm);
+  if (threadIdx.x == 0) { atomicAdd(work3, s); atomicAdd(work3 + 1, s2); atomicAdd(work3 + 2, c); }
+}
+
+__device__ __forceinline__ void mean_std_unbiased(const double* w, float& mean, float& sd) {
+  double c = w[2], m = (c > 0) ? w[0] / c : 0.0;
+  double var = (c > 1) ? (w[1] - c * m * m) / (c - 1.0) : 0.0;
+  mean = (float)m;
+  sd = (float)sqrt(var > 0.0 ? var : 0.0);
+}
+
+__global__ void adv_normalize_kernel(float* __restrict__ adv, int n, float clip, const double* __restrict__ work3,
+                                     float* __restrict__ stats_out) {
+  float mean, sd;
+  mean_std_unbiased(work3, mean, sd);
+  float den = fmaxf(sd, 1e-5f);
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0 && stats_out) { stats_out[0] = mean; stats_out[1] = sd; }
+  if (i >= n) return;
+  float v = sub_rn(adv[i], mean) / den;
+  adv[i] = fminf(fmaxf(v, -clip), clip);
+}
+
+__global__ void disc_reward_kernel(const float* __restrict__ logits, float* __restrict__ reward, int n, float scale,
+                                   float w_task, float w_disc, double* __restrict__ work3) {
+  __shared__ double sm[32];
+  double s = 0.0, s2 = 0.0, c = 0.0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    float prob = 1.0f / add_rn(1.0f, expf(-logits[i]));
+    float dr = mul_rn(-logf(fmaxf(sub_rn(1.0f, prob), 0.0001f)), scale);
+    reward[i] = add_rn(mul_rn(w_task, reward[i]), mul_rn(w_disc, dr));
+    s += dr; s2 += (double)dr * dr; c += 1.0;
+  }
+  s = block_sum(s, sm); s2 = block_sum(s2, sm); c = block_sum(c, sm);
+  if (threadIdx.x == 0) { atomicAdd(work3, s); atomicAdd(work3 + 1, s2); atomicAdd(work3 + 2, c); }
+}
+
+__global__ void moments_finalize_kernel(const double* __restrict__ work3, float* __restrict__ stats_out) {
+  float mean, sd;
+  mean_std_unbiased(work3, mean, sd);
+  stats_out[0] = mean; stats_out[1] = sd;
+}
+
+// Column sums over a [n, dim] row-major matrix; block = 256 threads over columns, ROWS rows per block.
+template <int MODE>
+__global__ void column_stats_kernel(const float* __restrict__ a, const float* __restrict__ b, long long n, int dim,
+                                    int rows_per_block, double* __restrict__ out) {
+  long long r0 = (long long)blockIdx.x * rows_per_block;
+  long long r1 = r0 + rows_per_block < n ? r0 + rows_per_block : n;
+  for (int c = threadIdx.x; c < dim; c += blockDim.x) {
+    double s = 0.0, s2 = 0.0;
+    for (long long r = r0; r < r1; ++r) {
+      float v = a[r * dim + c];
+      if (MODE == 0) { s += v; s2 += (double)v * v; }
+      else { s += fabsf(sub_rn(v, b[r * dim + c])); }
+    }
+    atomicAdd(out + c, s);
+    if (MODE == 0) atomicAdd(out + dim + c, s2);
+  }
+}
+
+__global__ void normalizer_update_kernel(const double* __restrict__ sums, double new_count, int dim,
+                                         int64_t* count, float* mean, float* mean_sq, float* std_, float min_var) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  long long old = count[0];
+  long long total = old + (long long)new_count;
+  if (c < dim) {
+    float nm = (float)(sums[c] / new_count), nms = (float)(sums[dim + c] / new_count);
+    float w_old = (float)old / (float)total, w_new = (float)new_count / (float)total;
+    float m = add_rn(mul_rn(w_old, mean[c]), mul_rn(w_new, nm));
+    float ms = add_rn(mul_rn(w_old, mean_sq[c]), mul_rn(w_new, nms));
+    mean[c] = m; mean_sq[c] = ms;
+    std_[c] = sqrtf(fmaxf(sub_rn(ms, mul_rn(m, m)), min_var));
+  }
+  __syncthreads();
+  // every block needs the old count; only after all blocks read it may it change -> single block launch
+  if (c == 0) count[0] = total;
+}
+
+__global__ void diff_normalizer_update_kernel(const double* __restrict__ sum_abs, double new_count, int dim,
+                                              int64_t* count, float* mean_abs) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  long long old = count[0];
+  long long total = old + (long long)new_count;
+  if (c < dim) {
+    float nm = (float)(sum_abs[c] / new_count);
+    float w_old = (float)old / (float)total, w_new = (float)new_count / (float)total;
+    mean_abs[c] = add_rn(mul_rn(w_old, mean_abs[c]), mul_rn(w_new, nm));
+  }
+  __syncthreads();
+  if (c == 0) count[0] = total;
+}
+
+// torch.optim.AdamW, amsgrad=False, maximize=False (torch/optim/adamw.py -> adam.py _single_tensor_adam)
+__global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                             float* __restrict__ v, long long n, float lr_wd_factor, float one_minus_b1, float b2,
+                             float one_minus_b2, float step_size, float bc2_sqrt, float eps, float grad_scale) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float grad = mul_rn(g[i], grad_scale);
+  float w = mul_rn(p[i], lr_wd_factor);                                   // param.mul_(1 - lr*wd)
+  float mi = add_rn(m[i], mul_rn(one_minus_b1, sub_rn(grad, m[i])));      // exp_avg.lerp_(grad, 1-b1)
+  float vi = add_rn(mul_rn(v[i], b2), mul_rn(mul_rn(one_minus_b2, grad), grad));  // mul_(b2).addcmul_(g, g, 1-b2)
+  float denom = add_rn(sqrtf(vi) / bc2_sqrt, eps);
+  p[i] = add_rn(w, mul_rn(-step_size, mi / denom));                       // addcdiv_(exp_avg, denom, -step_size)
+  m[i] = mi; v[i] = vi;
+}
+
+}  // namespace addk
+
+using namespace addk;
+
+extern "C" int addk_td_lambda(void* stream, const float* reward, const float* next_vals, const float* vals,
+                              const int32_t* done, int T, int N, float discount, float td_lambda, float succ_val,
+                              float fail_val, float* tar_val, float* adv) {
+  if (!reward || !next_vals || !vals || !done || !tar_val || !adv || T <= 0 || N <= 0) return ADDK_ERR_ARG;
+  td_lambda_kernel<<<(N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(reward, next_vals, vals, done, T, N, discount,
+                                                                     td_lambda, succ_val, fail_val, tar_val, adv);
+  ADDK_CHECK_LAUNCH();
+  return ADDK_OK;
+}
+
+extern "C" int addk_adv_normalize(void* stream, float* adv, const float* rand_action_mask, int n, float clip,
+                                  double* work3, float* stats_out) {
+  if (!adv || !work3 || n <= 0) return ADDK_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaMemsetAsync(work3, 0, 3 * sizeof(double), st);
+  int bl = (n + 255) / 256; if (bl > 1184) bl = 1184;
+  masked_moments_kernel<<<bl, 256, 0, st>>>(adv, rand_action_mask, n, work3);
+  ADDK_CHECK_LAUNCH();
+  adv_normalize_kernel<<<(n + 255) / 256, 256, 0, st>>>(adv, n, clip, work3, stats_out);
+  ADDK_CHECK_LAUNCH();
+  return ADDK_OK;
+}
+
+extern "C" int addk_disc_reward(void* stream, const float* logits, float* reward_inout, int n, float scale,
+                                float w_task, float w_disc, double* work3, float* stats_out) {
+  if (!logits || !reward_inout || !work3 || n <= 0) return ADDK_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaMemsetAsync(work3, 0, 3 * sizeof(double), st);
+  int bl = (n + 255) / 256; if (bl > 1184) bl = 1184;
+  disc_reward_kernel<<<bl, 256, 0, st>>>(logits, reward_inout, n, scale, w_task, w_disc, work3);
+  ADDK_CHECK_LAUNCH();
+  if (stats_out) { moments_finalize_kernel<<<1, 1, 0, st>>>(work3, stats_out); ADDK_CHECK_LAUNCH(); }
+  return ADDK_OK;
+}
+
+extern "C" int addk_column_stats(void* stream, const float* a, const float* b, long long n, int dim, int mode,
+                                 double* out) {
+  if (!a || !out || n <= 0 || dim <= 0 || (mode == 1 && !b)) return ADDK_ERR_ARG;
+  const int rows = 128;
+  int bl = (int)((n + rows - 1) / rows);
+  if (mode == 0) column_stats_kernel<0><<<bl, 256, 0, (cudaStream_t)stream>>>(a, b, n, dim, rows, out);
+  else column_stats_kernel<1><<<bl, 256, 0, (cudaStream_t)stream>>>(a, b, n, dim, rows, out);
+  ADDK_CHECK_LAUNCH();
+  return ADDK_OK;
+}
+
+extern "C" int addk_normalizer_update(void* stream, const double* sums, double new_count, int dim, int64_t* count,
+                                      float* mean, float* mean_sq, float* std_, float min_var) {
+  if (!sums || !count || !mean || !mean_sq || !std_ || dim <= 0 || dim > 1024) return ADDK_ERR_ARG;
+  if (new_count <= 0) return ADDK_OK;  // normalizer.py:62-63
+  normalizer_update_kernel<<<1, ((dim + 31) / 32) * 32, 0, (cudaStream_t)stream>>>(sums, new_count, dim, count, mean,
+                                                                                    mean_sq, std_, min_var);
+  ADDK_CHECK_LAUNCH();
+  return ADDK_OK;
+}
+
+extern "C" int addk_diff_normalizer_update(void* stream, const double* sum_abs, double new_count, int dim,
+                                           int64_t* count, float* mean_abs) {
+  if (!sum_abs || !count || !mean_abs || dim <= 0 || dim > 1024) return ADDK_ERR_ARG;
+  diff_normalizer_update_kernel<<<1, ((dim + 31) / 32) * 32, 0, (cudaStream_t)stream>>>(sum_abs, new_count, dim,
+                                                                                         count, mean_abs);
+  ADDK_CHECK_LAUNCH();
+  return ADDK_OK;
+}
+
+extern "C" int addk_adamw(void* stream, float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
+                          long long n, int step, double lr, double beta1, double beta2, double eps,
+                          double weight_decay, double grad_scale) {
+  if (!param || !grad || !exp_avg || !exp_avg_sq || n <= 0 || step < 1) return ADDK_ERR_ARG;
+  // scalar prep in double exactly as torch does it on the host, then rounded once to fp32
+  double bc1 = 1.0 - pow(beta1, (double)step);
+  double bc2 = 1.0 - pow(beta2, (double)step);
+  float step_size = (float)(lr / bc1);
+  float bc2_sqrt = (float)sqrt(bc2);
+  float lr_wd = (float)(1.0 - lr * weight_decay);
+  adamw_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      param, grad, exp_avg, exp_avg_sq, n, lr_wd, (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2),
+      step_size, bc2_sqrt, (float)eps, (float)grad_scale);
+  ADDK_CHECK_LAUNCH();
+  return ADDK_OK;
+}

@@ -1,0 +1,531 @@
+// PPO actor-critic + ADD discriminator: rollout inference, batched evaluation and one full optimizer
+// step (gather -> forward -> losses -> backward incl. the gradient-penalty double backward -> AdamW),
+// issued from native host code as a fixed sequence of ~60 launches per minibatch.
+//
+// Replaces (reference add_gym/learning/):
+//   ExperienceBuffer.sample                       experience_buffer.py:74-113
+//   Normalizer.normalize / DiffNormalizer.normalize  normalizer.py:107-110, diff_normalizer.py:56-60
+//   PPOModel.eval_actor/eval_critic, ADDModel.eval_disc  ppo_model.py:13-21, add/add_model.py:12-15
+//   DistributionGaussianDiag.sample/log_prob       distribution_gaussian_diag.py:84-94
+//   PPOAgent._decide_action                        ppo_agent.py:72-104
+//   PPOAgent._compute_{critic,actor}_loss, BaseAgent._compute_action_bound_loss
+//                                                  ppo_agent.py:209-261, base_agent.py:522-546
+//   ADDAgent._compute_disc_loss, AMPAgent._disc_loss_pos/_neg/_compute_disc_acc
+//                                                  add/add_agent.py:141-202, amp_agent.py:177-192
+//   MPOptimizer.step (zero_grad, backward, AdamW)  mp_optimizer.py:14-23
+//
+// Backward is written out by hand.  For the discriminator D(x) = w3.relu(W2 relu(W1 x + b1) + b2) + b3
+// the input gradient is g = W1^T (m1 * (W2^T (m2 * w3))) with m1, m2 the ReLU masks; the penalty
+// 20*mean((|g|-1)^2) is differentiated through that chain with the masks held constant (ReLU has zero
+// second derivative), which is exactly what autograd's create_graph=True double backward computes.
+// The "zero diff" positive sample D(0) is carried as one extra row (row M) of the minibatch.
+#include "common.cuh"
+#include "addk.h"
+
+struct addk_update_ctx {
+#define ADDK_PTR(n) void* n;
+#define ADDK_INT(n) int64_t n;
+#define ADDK_F64(n) double n;
+#include "ctx_fields.h"
+};
+
+int addk_gemm_tc(cudaStream_t st, const addk_gemm_args& a, int precision);
+namespace addk { int sgemm_launch(cudaStream_t st, const addk_gemm_args& a); }
+
+namespace addk {
+
+enum { ST_SURR = 0, ST_CLIP, ST_RATIO, ST_BOUND, ST_CRITIC, ST_BCE_NEG, ST_BCE_POS, ST_PEN, ST_NEG_LOGIT,
+       ST_POS_LOGIT, ST_NEG_ACC, ST_POS_ACC, ST_WL_SQ, ST_W_SQ, ST_COUNT = 32 };
+
+// ---- ExperienceBuffer.sample + normalisation: one warp per minibatch row ---------------------------------
+__global__ void gather_minibatch_kernel(const long long* __restrict__ idx, int M, int obs_dim, int act_dim, int act_ld,
+                                        int disc_dim, int disc_ld, const float* __restrict__ buf_obs,
+                                        const float* __restrict__ buf_action, const float* __restrict__ buf_logp,
+                                        const float* __restrict__ buf_adv, const float* __restrict__ buf_tar,
+                                        const float* __restrict__ buf_mask, const float* __restrict__ buf_dobs,
+                                        const float* __restrict__ buf_demo, const float* __restrict__ obs_mean,
+                                        const float* __restrict__ obs_std, const float* __restrict__ a_mean,
+                                        const float* __restrict__ a_std, const float* __restrict__ mean_abs,
+                                        float* __restrict__ xn, float* __restrict__ an, float* __restrict__ old_logp,
+                                        float* __restrict__ adv, float* __restrict__ tar, float* __restrict__ mask,
+                                        float* __restrict__ dn, int* __restrict__ cnt) {
+  int i = blockIdx.x * (blockDim.x / 32) + (threadIdx.x / 32);
+  int lane = threadIdx.x & 31;
+  if (i >= M) return;
+  const size_t s = (size_t)idx[i];
+  for (int c = lane; c < obs_dim; c += 32) xn[(size_t)i * obs_dim + c] = sub_rn(buf_obs[s * obs_dim + c], obs_mean[c]) / obs_std[c];
+  for (int c = lane; c < act_ld; c += 32)
+    an[(size_t)i * act_ld + c] = c < act_dim ? sub_rn(buf_action[s * act_dim + c], a_mean[c]) / a_std[c] : 0.f;
+  for (int c = lane; c < disc_ld; c += 32)
+    dn[(size_t)i * disc_ld + c] =
+        c < disc_dim ? sub_rn(buf_demo[s * disc_dim + c], buf_dobs[s * disc_dim + c]) / fmaxf(mean_abs[c], 1e-4f) : 0.f;
+  if (lane == 0) {
+    old_logp[i] = buf_logp[s]; adv[i] = buf_adv[s]; tar[i] = buf_tar[s];
+    float mk = buf_mask[s];
+    mask[i] = mk;
+    if (mk == 1.0f) atomicAdd(cnt, 1);
+  }
+}
+
+__device__ __forceinline__ float gaussian_logp(float sq_sum, float logstd_sum, int dim) {
+  // -0.5*sum((x-mean)/std)^2  +  (-0.5*dim*log(2*pi) - sum(logstd))   distribution_gaussian_diag.py:90-94
+  const float c = (float)(-0.5 * (double)dim * 1.8378770664093453);
+  return add_rn(mul_rn(-0.5f, sq_sum), sub_rn(c, logstd_sum));
+}
+
+// ---- PPO surrogate + action-bound loss and d(loss)/d(mean): one warp per row ------------------------------
+__global__ void actor_loss_kernel(const float* __restrict__ mean, const float* __restrict__ an,
+                                  const float* __restrict__ logstd, const float* __restrict__ old_logp,
+                                  const float* __restrict__ adv, const float* __restrict__ mask, int M, int act_dim,
+                                  int act_ld, float clip, float bound_w, const int* __restrict__ cnt,
+                                  float* __restrict__ dmean, double* __restrict__ stats) {
+  int i = blockIdx.x * (blockDim.x / 32) + (threadIdx.x / 32);
+  int lane = threadIdx.x & 31;
+  if (i >= M) return;
+  const bool on = mask[i] == 1.0f;
+  float m = 0.f, d = 0.f, sd = 1.f, ls = 0.f;
+  if (lane < act_dim) {
+    m = mean[(size_t)i * act_ld + lane];
+    ls = logstd[lane];
+    sd = expf(ls);
+    d = sub_rn(an[(size_t)i * act_ld + lane], m);
+  }
+  float z = d / sd;
+  float sq = warp_sum(lane < act_dim ? mul_rn(z, z) : 0.f);
+  float lss = warp_sum(ls);
+  float logp = gaussian_logp(sq, lss, act_dim);
+  float ratio = expf(sub_rn(logp, old_logp[i]));
+  float a = adv[i];
+  float l0 = mul_rn(a, ratio);
+  float rc = fminf(fmaxf(ratio, 1.0f - clip), 1.0f + clip);
+  float l1 = mul_rn(a, rc);
+  float surr = fminf(l0, l1);
+  // d surr / d ratio: through l0 when l0 <= l1, through l1 only inside the clip range (ties split 1/2+1/2)
+  float dr;
+  const bool inside = ratio >= 1.0f - clip && ratio <= 1.0f + clip;
+  if (l0 < l1) dr = a;
+  else if (l0 == l1) dr = 0.5f * a + (inside ? 0.5f * a : 0.f);
+  else dr = inside ? a : 0.f;
+  const float n = (float)max(*cnt, 1);
+  float dlogp = -(dr * ratio) / n;   // actor_loss = -mean(surr)
+  float vmin = fminf(add_rn(m, 1.0f), 0.f), vmax = fmaxf(sub_rn(m, 1.0f), 0.f);
+  float viol = lane < act_dim ? add_rn(mul_rn(vmin, vmin), mul_rn(vmax, vmax)) : 0.f;
+  float viol_sum = warp_sum(viol);
+  if (lane < act_ld) {
+    float g = 0.f;
+    if (on && lane < act_dim) g = dlogp * (d / (sd * sd)) + bound_w * 2.0f * (vmin + vmax) / n;
+    dmean[(size_t)i * act_ld + lane] = g;
+  }
+  if (lane == 0 && on) {
+    atomicAdd(stats + ST_SURR, (double)surr);
+    atomicAdd(stats + ST_CLIP, fabsf(sub_rn(ratio, 1.0f)) > clip ? 1.0 : 0.0);
+    atomicAdd(stats + ST_RATIO, (double)ratio);
+    atomicAdd(stats + ST_BOUND, (double)viol_sum);
+  }
+}
+
+__global__ void critic_loss_kernel(const float* __restrict__ pred, const float* __restrict__ tar, int M, float w,
+                                   float* __restrict__ dpred, double* __restrict__ stats) {
+  __shared__ double sm[32];
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double s = 0.0;
+  if (i < M) {
+    float diff = sub_rn(tar[i], pred[i]);
+    s = (double)diff * diff;
+    dpred[i] = w * (-2.0f * diff) / (float)M;
+  }
+  s = block_sum(s, sm);
+  if (threadIdx.x == 0) atomicAdd(stats + ST_CRITIC, s);
+}
+
+// BCEWithLogits with smoothed labels 0.1 (rows < M, mean over M) and 0.9 (row M): amp_agent.py:177-185
+__global__ void disc_loss_kernel(const float* __restrict__ logit, int M, float w, float* __restrict__ dlogit,
+                                 double* __restrict__ stats) {
+  __shared__ double sm[32];
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double bce_n = 0.0, lg = 0.0, acc = 0.0;
+  if (i <= M) {
+    float x = logit[i];
+    float t = i < M ? 0.1f : 0.9f;
+    float bce = fmaxf(x, 0.f) - x * t + log1pf(expf(-fabsf(x)));
+    float sg = 1.0f / (1.0f + expf(-x));
+    float wt = i < M ? 1.0f / (float)M : 1.0f;
+    dlogit[i] = w * 0.5f * (sg - t) * wt;
+    if (i < M) { bce_n = bce; lg = x; acc = x < 0.f ? 1.0 : 0.0; }
+    else {
+      atomicAdd(stats + ST_BCE_POS, (double)bce);
+      atomicAdd(stats + ST_POS_LOGIT, (double)x);
+      atomicAdd(stats + ST_POS_ACC, x > 0.f ? 1.0 : 0.0);
+    }
+  }
+  bce_n = block_sum(bce_n, sm); lg = block_sum(lg, sm); acc = block_sum(acc, sm);
+  if (threadIdx.x == 0) {
+    atomicAdd(stats + ST_BCE_NEG, bce_n); atomicAdd(stats + ST_NEG_LOGIT, lg); atomicAdd(stats + ST_NEG_ACC, acc);
+  }
+}
+
+// u2 = relu'(h2) * w3 (gradient of the logit w.r.t. the last hidden layer) and dh2 = dlogit * u2
+__global__ void disc_head_backward_kernel(const float* __restrict__ h2, const float* __restrict__ wl,
+                                          const float* __restrict__ dlogit, int R, int H, float* __restrict__ u2,
+                                          float* __restrict__ dh2) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)R * H) return;
+  int r = (int)(i / H), k = (int)(i - (size_t)r * H);
+  float u = h2[i] > 0.f ? wl[k] : 0.f;
+  u2[i] = u;
+  dh2[i] = dlogit[r] * u;
+}
+
+// gradient penalty on the input gradient: one warp per row (add_agent.py:167-178)
+__global__ void grad_penalty_kernel(const float* __restrict__ gx, int M, int R, int dim, int ld, float coef,
+                                    float* __restrict__ dg, double* __restrict__ stats) {
+  int i = blockIdx.x * (blockDim.x / 32) + (threadIdx.x / 32);
+  int lane = threadIdx.x & 31;
+  if (i >= R) return;
+  float s = 0.f;
+  for (int c = lane; c < dim; c += 32) { float v = gx[(size_t)i * ld + c]; s += v * v; }
+  s = warp_sum(s);
+  float gn = sqrtf(s + 1e-8f);
+  float e = gn - 1.0f;
+  float sc = i < M ? coef * 2.0f * e / (gn * (float)M) : 0.f;
+  for (int c = lane; c < ld; c += 32) dg[(size_t)i * ld + c] = c < dim ? sc * gx[(size_t)i * ld + c] : 0.f;
+  if (lane == 0 && i < M) atomicAdd(stats + ST_PEN, (double)e * e);
+}
+
+__global__ void sumsq_kernel(const float* __restrict__ x, long long n, double* __restrict__ out) {
+  __shared__ double sm[32];
+  double s = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    double v = x[i]; s += v * v;
+  }
+  s = block_sum(s, sm);
+  if (threadIdx.x == 0) atomicAdd(out, s);
+}
+
+struct Seg { long long begin, end; int nslabs; float l2; };
+struct SegTable { Seg s[24]; int n; long long P; };
+
+// grads[i] = sum over the split-K slabs of segment(i) + l2 * param[i]
+__global__ void reduce_slabs_kernel(const __grid_constant__ SegTable t, const float* __restrict__ slabs,
+                                    const float* __restrict__ params, float* __restrict__ grads) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= t.P) return;
+  int ns = 0; float l2 = 0.f;
+  for (int k = 0; k < t.n; ++k) if (i >= t.s[k].begin && i < t.s[k].end) { ns = t.s[k].nslabs; l2 = t.s[k].l2; break; }
+  float g = 0.f;
+  for (int s = 0; s < ns; ++s) g += slabs[(size_t)s * t.P + i];
+  if (l2 != 0.f) g += l2 * params[i];
+  grads[i] = g;
+}
+
+__global__ void finalize_info_kernel(const double* __restrict__ st, const int* __restrict__ cnt, int M, float bound_w,
+                                     float critic_w, float disc_w, float logit_reg, float gp, float wd,
+                                     float* __restrict__ info) {
+  double n = (double)max(*cnt, 1);
+  double surr = st[ST_SURR] / n, bound = st[ST_BOUND] / n;
+  double actor = -surr + (bound_w != 0.f ? bound_w * bound : 0.0);
+  double critic = st[ST_CRITIC] / M;
+  double pen = st[ST_PEN] / M;
+  double disc = 0.5 * (st[ST_BCE_POS] + st[ST_BCE_NEG] / M) + logit_reg * st[ST_WL_SQ] + gp * pen + wd * st[ST_W_SQ];
+  info[0] = (float)(actor + critic_w * critic + disc_w * disc);
+  info[1] = (float)critic;
+  info[2] = (float)actor;
+  info[3] = (float)(st[ST_CLIP] / n);
+  info[4] = (float)(st[ST_RATIO] / n);
+  info[5] = (float)bound;
+  info[6] = (float)disc;
+  info[7] = (float)pen;
+  info[8] = (float)st[ST_WL_SQ];
+  info[9] = (float)st[ST_POS_ACC];
+  info[10] = (float)(st[ST_NEG_ACC] / M);
+  info[11] = (float)st[ST_POS_LOGIT];
+  info[12] = (float)(st[ST_NEG_LOGIT] / M);
+  info[13] = (float)n;
+  info[14] = 0.f; info[15] = 0.f;
+}
+
+// DistributionGaussianDiag.sample/log_prob + rand_action_mask select + Normalizer.unnormalize: warp per env
+__global__ void sample_action_kernel(const float* __restrict__ mean, int act_ld, const float* __restrict__ logstd,
+                                     const float* __restrict__ noise, const float* __restrict__ exp_mask,
+                                     const float* __restrict__ a_mean, const float* __restrict__ a_std, int n,
+                                     int act_dim, float* __restrict__ action, float* __restrict__ a_logp,
+                                     float* __restrict__ action_rec, float* __restrict__ logp_rec,
+                                     float* __restrict__ mask_rec) {
+  int i = blockIdx.x * (blockDim.x / 32) + (threadIdx.x / 32);
+  int lane = threadIdx.x & 31;
+  if (i >= n) return;
+  const float mk = exp_mask ? exp_mask[i] : 1.0f;
+  float m = 0.f, ls = 0.f, z = 0.f;
+  if (lane < act_dim) {
+    m = mean[(size_t)i * act_ld + lane];
+    ls = logstd[lane];
+    float sd = expf(ls);
+    float x = add_rn(m, mul_rn(sd, noise[(size_t)i * act_dim + lane]));
+    float na = (mk == 1.0f) ? x : m;
+    z = sub_rn(na, m) / sd;
+    float a = add_rn(mul_rn(na, a_std[lane]), a_mean[lane]);
+    action[(size_t)i * act_dim + lane] = a;
+    if (action_rec) action_rec[(size_t)i * act_dim + lane] = a;
+  }
+  float sq = warp_sum(lane < act_dim ? mul_rn(z, z) : 0.f);
+  float lss = warp_sum(ls);
+  if (lane == 0) {
+    float lp = gaussian_logp(sq, lss, act_dim);
+    a_logp[i] = lp;
+    if (logp_rec) logp_rec[i] = lp;
+    if (mask_rec) mask_rec[i] = mk;
+  }
+}
+
+__global__ void diff_normalize_kernel(const float* __restrict__ dobs, const float* __restrict__ demo,
+                                      const float* __restrict__ mean_abs, long long rows, int dim, int ld,
+                                      float* __restrict__ out) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * ld) return;
+  long long r = i / ld; int c = (int)(i - r * ld);
+  out[i] = c < dim ? sub_rn(demo[r * dim + c], dobs[r * dim + c]) / fmaxf(mean_abs[c], 1e-4f) : 0.f;
+}
+
+}  // namespace addk
+
+using namespace addk;
+typedef addk_update_ctx Ctx;
+#define F(p) ((float*)(p))
+
+static int gemm(cudaStream_t st, int prec, const float* A, int lda, int ta, const float* B, int ldb, int tb, float* C,
+                int ldc, int M, int N, int K, const float* bias = nullptr, int relu = 0, const float* mask = nullptr,
+                int ld_mask = 0, int split = 1, const float* nmean = nullptr, const float* nstd = nullptr) {
+  addk_gemm_args a;
+  a.A = A; a.lda = lda; a.B = B; a.ldb = ldb; a.C = C; a.ldc = ldc; a.M = M; a.N = N; a.K = K;
+  a.bias = bias; a.a_mean = nmean; a.a_std = nstd; a.relu_mask_src = mask; a.ld_mask = ld_mask;
+  a.trans_a = ta; a.trans_b = tb; a.relu = relu; a.split_k = split; a.accumulate = 0;
+  int rc = prec == 0 ? addk::sgemm_launch(st, a) : addk_gemm_tc(st, a, prec);
+  if (rc != ADDK_OK) return rc;
+  ADDK_CHECK_LAUNCH();
+  return ADDK_OK;
+}
+#define TRY(x) do { int rc__ = (x); if (rc__ != ADDK_OK) return rc__; } while (0)
+
+// weight gradient dW[N_out, K_in] = dY^T X and bias gradient db = 1^T dY, as split-K slabs
+static int wgrad(cudaStream_t st, const Ctx& c, const float* dY, int ldy, const float* X, int ldx, int rows, int n_out,
+                 int k_in, long long o_w, long long o_b, int slab0) {
+  const int S = (int)c.split_k;
+  const long long P = c.num_params;
+  TRY(gemm(st, (int)c.precision, dY, ldy, 1, X, ldx, 0, F(c.slabs) + (size_t)slab0 * P + o_w, k_in, n_out, k_in, rows,
+           nullptr, 0, nullptr, 0, S));
+  if (o_b >= 0)
+    TRY(gemm(st, 0, F(c.ones), 1, 1, dY, ldy, 0, F(c.slabs) + (size_t)slab0 * P + o_b, n_out, 1, n_out, rows, nullptr, 0,
+             nullptr, 0, S));
+  return ADDK_OK;
+}
+
+// 3-hidden-layer trunk forward: X[rows,in] -> h1,h2,h3
+static int trunk_forward(cudaStream_t st, const Ctx& c, const float* X, int ldx, int in_dim, int rows, long long o_w0,
+                         long long o_b0, long long o_w1, long long o_b1, long long o_w2, long long o_b2,
+                         const float* nmean = nullptr, const float* nstd = nullptr) {
+  const float* P = F(c.params);
+  const int H1 = (int)c.hid_a1, H2 = (int)c.hid_a2, H3 = (int)c.hid_a3, pr = (int)c.precision;
+  TRY(gemm(st, nmean ? 0 : pr, X, ldx, 0, P + o_w0, in_dim, 1, F(c.h1), H1, rows, H1, in_dim, P + o_b0, 1, nullptr, 0, 1,
+           nmean, nstd));
+  TRY(gemm(st, pr, F(c.h1), H1, 0, P + o_w1, H1, 1, F(c.h2), H2, rows, H2, H1, P + o_b1, 1));
+  TRY(gemm(st, pr, F(c.h2), H2, 0, P + o_w2, H2, 1, F(c.h3), H3, rows, H3, H2, P + o_b2, 1));
+  return ADDK_OK;
+}
+
+// trunk backward given g3 = dL/dh3 (already masked by h3 > 0)
+static int trunk_backward(cudaStream_t st, const Ctx& c, const float* X, int ldx, int in_dim, int rows, long long o_w0,
+                          long long o_b0, long long o_w1, long long o_b1, long long o_w2, long long o_b2) {
+  const float* P = F(c.params);
+  const int H1 = (int)c.hid_a1, H2 = (int)c.hid_a2, H3 = (int)c.hid_a3, pr = (int)c.precision;
+  TRY(wgrad(st, c, F(c.g3), H3, F(c.h2), H2, rows, H3, H2, o_w2, o_b2, 0));
+  TRY(gemm(st, pr, F(c.g3), H3, 0, P + o_w2, H2, 0, F(c.g2), H2, rows, H2, H3, nullptr, 0, F(c.h2), H2));
+  TRY(wgrad(st, c, F(c.g2), H2, F(c.h1), H1, rows, H2, H1, o_w1, o_b1, 0));
+  TRY(gemm(st, pr, F(c.g2), H2, 0, P + o_w1, H1, 0, F(c.g1), H1, rows, H1, H2, nullptr, 0, F(c.h1), H1));
+  TRY(wgrad(st, c, F(c.g1), H1, X, ldx, rows, H1, in_dim, o_w0, o_b0, 0));
+  return ADDK_OK;
+}
+
+extern "C" int addk_update_ctx_size(void) { return (int)sizeof(Ctx); }
+
+extern "C" int addk_update_ctx_init(void* ctx_host, const void* const* ptrs, int n_ptrs, const int64_t* ints,
+                                    int n_ints, const double* floats, int n_floats) {
+  if (!ctx_host || !ptrs || !ints || !floats) return ADDK_ERR_ARG;
+  Ctx* c = (Ctx*)ctx_host;
+  int ip = 0, ii = 0, id = 0;
+#define ADDK_PTR(n) if (ip >= n_ptrs) return ADDK_ERR_ARG; c->n = (void*)ptrs[ip++];
+#define ADDK_INT(n) if (ii >= n_ints) return ADDK_ERR_ARG; c->n = ints[ii++];
+#define ADDK_F64(n) if (id >= n_floats) return ADDK_ERR_ARG; c->n = floats[id++];
+#include "ctx_fields.h"
+  if (ip != n_ptrs || ii != n_ints || id != n_floats) return ADDK_ERR_ARG;
+  if (c->act_dim > 32 || c->split_k < 1 || c->split_k > 16) return ADDK_ERR_ARG;
+  return ADDK_OK;
+}
+
+extern "C" int addk_update_minibatch(void* stream, void* ctx_host, const long long* idx, int step_index,
+                                     int do_optim) {
+  if (!ctx_host || !idx || step_index < 0) return ADDK_ERR_ARG;
+  const Ctx& c = *(const Ctx*)ctx_host;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int M = (int)c.mb_rows, R = M + 1, OD = (int)c.obs_dim, AD = (int)c.act_dim, AL = (int)c.act_ld;
+  const int DD = (int)c.disc_dim, DL = (int)c.disc_ld, pr = (int)c.precision, S = (int)c.split_k;
+  const int H1 = (int)c.hid_a1, H3 = (int)c.hid_a3, E1 = (int)c.hid_d1, E2 = (int)c.hid_d2;
+  const long long P = c.num_params;
+  const float* W = F(c.params);
+  double* stats = (double*)c.stats;
+  int* cnt = (int*)c.cnt;
+  (void)H1;
+  cudaMemsetAsync(stats, 0, ST_COUNT * sizeof(double), st);
+  cudaMemsetAsync(cnt, 0, sizeof(int), st);
+  gather_minibatch_kernel<<<(M + 7) / 8, 256, 0, st>>>(
+      idx, M, OD, AD, AL, DD, DL, F(c.buf_obs), F(c.buf_action), F(c.buf_a_logp), F(c.buf_adv), F(c.buf_tar_val),
+      F(c.buf_mask), F(c.buf_disc_obs), F(c.buf_disc_demo), F(c.obs_mean), F(c.obs_std), F(c.a_mean), F(c.a_std),
+      F(c.disc_mean_abs), F(c.xn), F(c.an), F(c.old_logp), F(c.adv), F(c.tar), F(c.mask), F(c.dn), cnt);
+  ADDK_CHECK_LAUNCH();
+
+  // ---------------- actor ----------------
+  TRY(trunk_forward(st, c, F(c.xn), OD, OD, M, c.o_a_w0, c.o_a_b0, c.o_a_w1, c.o_a_b1, c.o_a_w2, c.o_a_b2));
+  TRY(gemm(st, pr, F(c.h3), H3, 0, W + c.o_a_wm, H3, 1, F(c.mean), AL, M, AD, H3, W + c.o_a_bm, 0));
+  actor_loss_kernel<<<(M + 7) / 8, 256, 0, st>>>(F(c.mean), F(c.an), F(c.logstd), F(c.old_logp), F(c.adv), F(c.mask), M,
+                                                 AD, AL, (float)c.ppo_clip_ratio, (float)c.action_bound_weight, cnt,
+                                                 F(c.dmean), stats);
+  ADDK_CHECK_LAUNCH();
+  TRY(wgrad(st, c, F(c.dmean), AL, F(c.h3), H3, M, AD, H3, c.o_a_wm, c.o_a_bm, 0));
+  TRY(gemm(st, pr, F(c.dmean), AL, 0, W + c.o_a_wm, H3, 0, F(c.g3), H3, M, H3, AD, nullptr, 0, F(c.h3), H3));
+  TRY(trunk_backward(st, c, F(c.xn), OD, OD, M, c.o_a_w0, c.o_a_b0, c.o_a_w1, c.o_a_b1, c.o_a_w2, c.o_a_b2));
+
+  // ---------------- critic ----------------
+  TRY(trunk_forward(st, c, F(c.xn), OD, OD, M, c.o_c_w0, c.o_c_b0, c.o_c_w1, c.o_c_b1, c.o_c_w2, c.o_c_b2));
+  TRY(gemm(st, pr, F(c.h3), H3, 0, W + c.o_c_wo, H3, 1, F(c.pred), 1, M, 1, H3, W + c.o_c_bo, 0));
+  critic_loss_kernel<<<(M + 255) / 256, 256, 0, st>>>(F(c.pred), F(c.tar), M, (float)c.critic_loss_weight, F(c.dpred),
+                                                      stats);
+  ADDK_CHECK_LAUNCH();
+  TRY(wgrad(st, c, F(c.dpred), 1, F(c.h3), H3, M, 1, H3, c.o_c_wo, c.o_c_bo, 0));
+  TRY(gemm(st, pr, F(c.dpred), 1, 0, W + c.o_c_wo, H3, 0, F(c.g3), H3, M, H3, 1, nullptr, 0, F(c.h3), H3));
+  TRY(trunk_backward(st, c, F(c.xn), OD, OD, M, c.o_c_w0, c.o_c_b0, c.o_c_w1, c.o_c_b1, c.o_c_w2, c.o_c_b2));
+
+  // ---------------- discriminator (R = M + 1 rows) ----------------
+  float *e1 = F(c.h1), *e2 = F(c.h3), *dh2 = F(c.g3), *dv1 = F(c.g1), *du2 = F(c.g2);
+  TRY(gemm(st, pr, F(c.dn), DL, 0, W + c.o_d_w0, DD, 1, e1, E1, R, E1, DD, W + c.o_d_b0, 1));
+  TRY(gemm(st, pr, e1, E1, 0, W + c.o_d_w1, E1, 1, e2, E2, R, E2, E1, W + c.o_d_b1, 1));
+  TRY(gemm(st, pr, e2, E2, 0, W + c.o_d_wl, E2, 1, F(c.pred), 1, R, 1, E2, W + c.o_d_bl, 0));
+  disc_loss_kernel<<<(R + 255) / 256, 256, 0, st>>>(F(c.pred), M, (float)c.disc_loss_weight, F(c.dpred), stats);
+  ADDK_CHECK_LAUNCH();
+  {
+    size_t tot = (size_t)R * E2;
+    disc_head_backward_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(e2, W + c.o_d_wl, F(c.dpred), R, E2, F(c.u2),
+                                                                            dh2);
+    ADDK_CHECK_LAUNCH();
+  }
+  // input-gradient chain: u1 = m1 * (u2 W2), gx = u1 W1
+  TRY(gemm(st, pr, F(c.u2), E2, 0, W + c.o_d_w1, E1, 0, F(c.u1), E1, R, E1, E2, nullptr, 0, e1, E1));
+  TRY(gemm(st, pr, F(c.u1), E1, 0, W + c.o_d_w0, DD, 0, F(c.gx), DL, R, DD, E1));
+  grad_penalty_kernel<<<(R + 7) / 8, 256, 0, st>>>(F(c.gx), M, R, DD, DL,
+                                                   (float)(c.disc_loss_weight * c.disc_grad_penalty), F(c.dg), stats);
+  ADDK_CHECK_LAUNCH();
+  // backward of the chain (second set of slabs)
+  TRY(gemm(st, pr, F(c.u1), E1, 1, F(c.dg), DL, 0, F(c.slabs) + (size_t)S * P + c.o_d_w0, DD, E1, DD, R, nullptr, 0,
+           nullptr, 0, S));
+  TRY(gemm(st, pr, F(c.dg), DL, 0, W + c.o_d_w0, DD, 1, dv1, E1, R, E1, DD, nullptr, 0, e1, E1));
+  TRY(gemm(st, pr, F(c.u2), E2, 1, dv1, E1, 0, F(c.slabs) + (size_t)S * P + c.o_d_w1, E1, E2, E1, R, nullptr, 0, nullptr, 0,
+           S));
+  TRY(gemm(st, pr, dv1, E1, 0, W + c.o_d_w1, E1, 1, du2, E2, R, E2, E1, nullptr, 0, e2, E2));
+  TRY(gemm(st, 0, F(c.ones), 1, 1, du2, E2, 0, F(c.slabs) + (size_t)S * P + c.o_d_wl, E2, 1, E2, R, nullptr, 0, nullptr, 0,
+           S));
+  // ordinary backward of the BCE terms
+  TRY(wgrad(st, c, F(c.dpred), 1, e2, E2, R, 1, E2, c.o_d_wl, c.o_d_bl, 0));
+  TRY(wgrad(st, c, dh2, E2, e1, E1, R, E2, E1, c.o_d_w1, c.o_d_b1, 0));
+  TRY(gemm(st, pr, dh2, E2, 0, W + c.o_d_w1, E1, 0, F(c.u1), E1, R, E1, E2, nullptr, 0, e1, E1));
+  TRY(wgrad(st, c, F(c.u1), E1, F(c.dn), DL, R, E1, DD, c.o_d_w0, c.o_d_b0, 0));
+  // regularisers (values for the log; their gradients are folded into the slab reduction)
+  sumsq_kernel<<<8, 256, 0, st>>>(W + c.o_d_wl, E2, stats + ST_WL_SQ);
+  ADDK_CHECK_LAUNCH();
+  sumsq_kernel<<<8, 256, 0, st>>>(W + c.o_d_wl, E2, stats + ST_W_SQ);
+  ADDK_CHECK_LAUNCH();
+  sumsq_kernel<<<148, 256, 0, st>>>(W + c.o_d_w0, (long long)E1 * DD, stats + ST_W_SQ);
+  ADDK_CHECK_LAUNCH();
+  sumsq_kernel<<<148, 256, 0, st>>>(W + c.o_d_w1, (long long)E2 * E1, stats + ST_W_SQ);
+  ADDK_CHECK_LAUNCH();
+
+  // ---------------- reduce slabs -> grads, AdamW, diagnostics ----------------
+  SegTable t;
+  t.P = P; t.n = 0;
+  const long long offs[22] = {c.o_a_w0, c.o_a_b0, c.o_a_w1, c.o_a_b1, c.o_a_w2, c.o_a_b2, c.o_a_wm, c.o_a_bm,
+                              c.o_c_w0, c.o_c_b0, c.o_c_w1, c.o_c_b1, c.o_c_w2, c.o_c_b2, c.o_c_wo, c.o_c_bo,
+                              c.o_d_w0, c.o_d_b0, c.o_d_w1, c.o_d_b1, c.o_d_wl, c.o_d_bl};
+  const float dlw = (float)c.disc_loss_weight;
+  for (int k = 0; k < 22; ++k) {
+    Seg& s = t.s[t.n++];
+    s.begin = offs[k];
+    s.end = (k + 1 < 22) ? offs[k + 1] : P;
+    s.nslabs = S; s.l2 = 0.f;
+    if (offs[k] == c.o_d_w0 || offs[k] == c.o_d_w1) { s.nslabs = 2 * S; s.l2 = dlw * 2.0f * (float)c.disc_weight_decay; }
+    if (offs[k] == c.o_d_wl) { s.nslabs = 2 * S; s.l2 = dlw * 2.0f * (float)(c.disc_weight_decay + c.disc_logit_reg); }
+  }
+  reduce_slabs_kernel<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(t, F(c.slabs), W, F(c.grads));
+  ADDK_CHECK_LAUNCH();
+  finalize_info_kernel<<<1, 1, 0, st>>>(stats, cnt, M, (float)c.action_bound_weight, (float)c.critic_loss_weight, dlw,
+                                        (float)c.disc_logit_reg, (float)c.disc_grad_penalty,
+                                        (float)c.disc_weight_decay, F(c.info) + (size_t)step_index * 16);
+  ADDK_CHECK_LAUNCH();
+  if (do_optim)
+    TRY(addk_adamw(stream, F(c.params), F(c.grads), F(c.exp_avg), F(c.exp_avg_sq), P, do_optim, c.lr, c.beta1, c.beta2,
+                   c.adam_eps, c.weight_decay, c.grad_scale));
+  return ADDK_OK;
+}
+
+extern "C" int addk_actor_step(void* stream, void* ctx_host, const float* obs, const float* noise,
+                               const float* exp_mask, int n, float* action, float* a_logp, float* obs_rec,
+                               float* action_rec, float* logp_rec, float* mask_rec) {
+  if (!ctx_host || !obs || !noise || !action || !a_logp || n <= 0) return ADDK_ERR_ARG;
+  const Ctx& c = *(const Ctx*)ctx_host;
+  if (n > c.mb_rows + 1) return ADDK_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int OD = (int)c.obs_dim, AD = (int)c.act_dim, AL = (int)c.act_ld, H3 = (int)c.hid_a3;
+  const float* W = F(c.params);
+  if (obs_rec) cudaMemcpyAsync(obs_rec, obs, (size_t)n * OD * sizeof(float), cudaMemcpyDeviceToDevice, st);
+  TRY(trunk_forward(st, c, obs, OD, OD, n, c.o_a_w0, c.o_a_b0, c.o_a_w1, c.o_a_b1, c.o_a_w2, c.o_a_b2, F(c.obs_mean),
+                    F(c.obs_std)));
+  TRY(gemm(st, (int)c.precision, F(c.h3), H3, 0, W + c.o_a_wm, H3, 1, F(c.mean), AL, n, AD, H3, W + c.o_a_bm, 0));
+  sample_action_kernel<<<(n + 7) / 8, 256, 0, st>>>(F(c.mean), AL, F(c.logstd), noise, exp_mask, F(c.a_mean), F(c.a_std),
+                                                    n, AD, action, a_logp, action_rec, logp_rec, mask_rec);
+  ADDK_CHECK_LAUNCH();
+  return ADDK_OK;
+}
+
+extern "C" int addk_critic_eval(void* stream, void* ctx_host, const float* obs, long long n, float* vals) {
+  if (!ctx_host || !obs || !vals || n <= 0) return ADDK_ERR_ARG;
+  const Ctx& c = *(const Ctx*)ctx_host;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int OD = (int)c.obs_dim, H3 = (int)c.hid_a3;
+  const long long chunk = c.mb_rows + 1;
+  const float* W = F(c.params);
+  for (long long r0 = 0; r0 < n; r0 += chunk) {
+    int rows = (int)((n - r0 < chunk) ? n - r0 : chunk);
+    TRY(trunk_forward(st, c, obs + r0 * OD, OD, OD, rows, c.o_c_w0, c.o_c_b0, c.o_c_w1, c.o_c_b1, c.o_c_w2, c.o_c_b2,
+                      F(c.obs_mean), F(c.obs_std)));
+    TRY(gemm(st, (int)c.precision, F(c.h3), H3, 0, W + c.o_c_wo, H3, 1, vals + r0, 1, rows, 1, H3, W + c.o_c_bo, 0));
+  }
+  return ADDK_OK;
+}
+
+extern "C" int addk_disc_eval(void* stream, void* ctx_host, const float* disc_obs, const float* disc_obs_demo,
+                              long long n, float* logits) {
+  if (!ctx_host || !disc_obs || !disc_obs_demo || !logits || n <= 0) return ADDK_ERR_ARG;
+  const Ctx& c = *(const Ctx*)ctx_host;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int DD = (int)c.disc_dim, DL = (int)c.disc_ld, E1 = (int)c.hid_d1, E2 = (int)c.hid_d2, pr = (int)c.precision;
+  const long long chunk = c.mb_rows;
+  const float* W = F(c.params);
+  float *e1 = F(c.h1), *e2 = F(c.h3);
+  for (long long r0 = 0; r0 < n; r0 += chunk) {
+    int rows = (int)((n - r0 < chunk) ? n - r0 : chunk);
+    long long tot = (long long)rows * DL;
+    diff_normalize_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(disc_obs + r0 * DD, disc_obs_demo + r0 * DD,
+                                                                        F(c.disc_mean_abs), rows, DD, DL, F(c.gx));
+    ADDK_CHECK_LAUNCH();
+    TRY(gemm(st, pr, F(c.gx), DL, 0, W + c.o_d_w0, DD, 1, e1, E1, rows, E1, DD, W + c.o_d_b0, 1));
+    TRY(gemm(st, pr, e1, E1, 0, W + c.o_d_w1, E1, 1, e2, E2, rows, E2, E1, W + c.o_d_b1, 1));
+    TRY(gemm(st, pr, e2, E2, 0, W + c.o_d_wl, E2, 1, logits + r0, 1, rows, 1, E2, W + c.o_d_bl, 0));
+  }
+  return ADDK_OK;
+}

@@ -1,0 +1,619 @@
+// Fused per-env work around the physics step: reference-motion window gather, history push,
+// policy observation, agent / demo discriminator observations, tracking reward, done flags,
+// episode bookkeeping and the experience-buffer row -- one kernel, one warp per environment.
+//
+// Replaces (reference add_gym/learning/add/):
+//   ADDObservation.update_motion / compute_obs      add_observation.py:163-306,356-419,422-717
+//   ADDReward.compute_reward                          add_reward.py:54-177
+//   ADDDone.compute_done + Manipulator contact bool   add_done.py:59-147, robot.py:221-231
+//   ADDAgent._record_data_post_step                   add_agent.py:93-108
+//   ReturnTracker.update                              base_agent.py:596-621
+//   ADDObservation.reset_idx / _reset_disc_hist       add_observation.py:308-344
+//   ADDMotion.sample_time, AdaptiveSegmentSampler     add_motion.py:53-61, sampler.py:20-92
+//
+// Data movement per env-step (D=29, defaults): the warp stages its 9-row window of the step table
+// (288-byte rows, float4 loads), the simulator state and the two older history rows in shared memory,
+// assembles the 264/114/114-float output rows there, and streams them out with 128-bit stores.
+// HBM-bound: ~2.0 KB read + ~3.6 KB written per env-step.
+#include "common.cuh"
+#include "addk.h"
+
+namespace addk {
+
+constexpr int WPB = 8;  // warps (= envs) per block
+
+enum { F_ADVANCE = 1, F_UPDATE_MOTION = 2, F_REWARD_DONE = 4, F_MASKED = 8 };
+
+struct StepParams {
+  addk_task task;
+  addk_motion_lib lib;
+  addk_sim_state sim;
+  addk_env_buffers env;
+  addk_exp_row exp;
+  const float* dof_err_w;
+  const uint8_t* env_mask;
+  int n, newest_slot, flags, has_exp;
+};
+
+__device__ __forceinline__ long long table_row(const addk_motion_lib& lib, float time, float dt_inv, long long start) {
+  long long fr = (long long)mul_rn(time, dt_inv);
+  fr = fr < 0 ? 0 : (fr > lib.s_total - 1 ? lib.s_total - 1 : fr);
+  long long idx = fr + start;
+  return idx < 0 ? 0 : (idx > lib.s_total - 1 ? lib.s_total - 1 : idx);
+}
+
+__device__ __forceinline__ Quat ldq(const float* p) { return {p[0], p[1], p[2], p[3]}; }
+
+// pose-obs of one history / demo step into dst: [pos3 | tan_norm 6 | dof D | (vel3 ang3 dofvel D)]
+// src is a staged row: pose half at src[0..], velocity half at src[half..]   (add_observation.py:462-554)
+__device__ __forceinline__ void disc_step_small(const float* src, int half, float* dst, int D, bool global_obs,
+                                                bool vel_obs) {
+  dst[0] = global_obs ? src[0] : 0.0f;
+  dst[1] = global_obs ? src[1] : 0.0f;
+  dst[2] = src[2];
+  Quat q = ldq(src + 3);
+  quat_to_tan_norm(q, dst + 3);
+  if (vel_obs) {
+    float* v = dst + 9 + D;
+    Vec3 lv = {src[half], src[half + 1], src[half + 2]}, av = {src[half + 3], src[half + 4], src[half + 5]};
+    if (!global_obs) {
+      Quat h = calc_heading_quat_inv(q);
+      lv = quat_rotate(h, lv);
+      av = quat_rotate(h, av);
+    }
+    v[0] = lv.x; v[1] = lv.y; v[2] = lv.z; v[3] = av.x; v[4] = av.y; v[5] = av.z;
+  }
+}
+
+__global__ void __launch_bounds__(WPB * 32) env_step_kernel(const __grid_constant__ StepParams p) {
+  extern __shared__ __align__(16) float smem[];
+  const addk_task& tk = p.task;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int e = blockIdx.x * WPB + warp;
+  if (e >= p.n) return;
+  if ((p.flags & F_MASKED) && !p.env_mask[e]) return;
+
+  const int D = tk.num_dofs;
+  const int half = (7 + D + 3) & ~3;
+  const int RS = p.lib.row_stride;
+  const int nT = tk.enable_tar_obs ? tk.num_tar_steps : 0;
+  const int nH = tk.num_disc_steps;
+  const bool vel = tk.enable_vel_obs != 0, glob = tk.global_obs != 0;
+  const int obs_pad = (tk.obs_dim + 3) & ~3, disc_pad = (tk.disc_obs_dim + 3) & ~3;
+  // per-warp shared layout
+  const int per_warp = RS /*ref*/ + nT * half + nH * RS /*demo*/ + RS /*sim*/ + nH * RS /*hist*/ + obs_pad + 2 * disc_pad;
+  float* s_ref = smem + (size_t)warp * per_warp;
+  float* s_tar = s_ref + RS;
+  float* s_demo = s_tar + nT * half;
+  float* s_sim = s_demo + nH * RS;
+  float* s_hist = s_sim + RS;
+  float* s_obs = s_hist + nH * RS;
+  float* s_disc = s_obs + obs_pad;
+  float* s_dobs = s_disc + disc_pad;
+
+  // ---- time and table rows ---------------------------------------------------------------------
+  // lane 0 owns the read-modify-write of time_buf; everyone else gets the value by shuffle
+  float t = 0.f;
+  if (lane == 0) {
+    t = p.env.time_buf[e];
+    if (p.flags & F_ADVANCE) {
+      t = add_rn(t, tk.ctrl_dt);
+      p.env.time_buf[e] = t;
+    }
+  }
+  t = __shfl_sync(0xffffffffu, t, 0);
+  const long long mid = p.env.motion_ids[e];
+  const float mt = add_rn(t, p.env.motion_time_offsets[e]);
+  const long long start = p.lib.start_idx[mid];
+
+  {  // reference row at mt: full row
+    const float* src = p.lib.table + (size_t)table_row(p.lib, mt, tk.dt_inv, start) * RS;
+    for (int i = lane; i < RS / 4; i += 32) stg4(s_ref + 4 * i, ldg4(src + 4 * i));
+  }
+  {  // target rows at mt + dt*k : pose half only
+    const int h4 = half / 4;
+    for (int i = lane; i < nT * h4; i += 32) {
+      int k = i / h4, c = i - k * h4;
+      const float* src = p.lib.table + (size_t)table_row(p.lib, add_rn(mt, tk.tar_offsets[k]), tk.dt_inv, start) * RS;
+      stg4(s_tar + k * half + 4 * c, ldg4(src + 4 * c));
+    }
+  }
+  {  // demo rows at mt + disc_offsets[j] (oldest -> newest)
+    const int w4 = (vel ? RS : half) / 4;
+    for (int i = lane; i < nH * w4; i += 32) {
+      int j = i / w4, c = i - j * w4;
+      const float* src = p.lib.table + (size_t)table_row(p.lib, add_rn(mt, tk.disc_offsets[j]), tk.dt_inv, start) * RS;
+      stg4(s_demo + j * RS + 4 * c, ldg4(src + 4 * c));
+    }
+  }
+  // ---- simulator state -> packed row ---------------------------------------------------------
+  if (lane < D) {
+    s_sim[7 + lane] = p.sim.dof_pos[(size_t)e * p.sim.ld_dof_pos + lane];
+    s_sim[half + 6 + lane] = p.sim.dof_vel[(size_t)e * p.sim.ld_dof_vel + lane];
+  }
+  if (lane < 3) {
+    s_sim[lane] = p.sim.root_pos[(size_t)e * p.sim.ld_root_pos + lane];
+    s_sim[half + lane] = p.sim.root_vel[(size_t)e * p.sim.ld_root_vel + lane];
+    s_sim[half + 3 + lane] = p.sim.root_ang[(size_t)e * p.sim.ld_root_ang + lane];
+  }
+  if (lane < 4) s_sim[3 + lane] = p.sim.root_rot[(size_t)e * p.sim.ld_root_rot + lane];
+  if (lane == 31) {
+    for (int i = 7 + D; i < half; ++i) s_sim[i] = 0.0f;
+    for (int i = half + 6 + D; i < RS; ++i) s_sim[i] = 0.0f;
+  }
+  // ---- history ring: logical j (oldest..newest) lives in slot (newest_slot + 1 + j) % nH -------------
+  float* g_hist = p.env.hist + (size_t)e * nH * p.env.hist_stride;
+  const bool push = (p.flags & F_UPDATE_MOTION) != 0;
+  {
+    const int r4 = RS / 4;
+    for (int i = lane; i < nH * r4; i += 32) {
+      int j = i / r4, c = i - j * r4;
+      if (push && j == nH - 1) continue;  // newest entry is the state being pushed
+      int slot = (p.newest_slot + 1 + j) % nH;
+      stg4(s_hist + j * RS + 4 * c, *reinterpret_cast<const float4*>(g_hist + (size_t)slot * p.env.hist_stride + 4 * c));
+    }
+  }
+  __syncwarp();
+  if (push) {
+    float* dst = g_hist + (size_t)p.newest_slot * p.env.hist_stride;
+    for (int i = lane; i < RS / 4; i += 32) {
+      float4 v = *reinterpret_cast<const float4*>(s_sim + 4 * i);
+      stg4(dst + 4 * i, v);
+      stg4(s_hist + (nH - 1) * RS + 4 * i, v);
+    }
+    // _update_ref_motion: ref_* <- table row (add_observation.py:163-175)
+    if (lane < 3) {
+      p.env.ref_root_pos[(size_t)e * 3 + lane] = s_ref[lane];
+      p.env.ref_root_vel[(size_t)e * 3 + lane] = s_ref[half + lane];
+      p.env.ref_root_ang_vel[(size_t)e * 3 + lane] = s_ref[half + 3 + lane];
+    }
+    if (lane < 4) p.env.ref_root_rot[(size_t)e * 4 + lane] = s_ref[3 + lane];
+    if (lane < D) {
+      p.env.ref_dof_pos[(size_t)e * D + lane] = s_ref[7 + lane];
+      p.env.ref_dof_vel[(size_t)e * D + lane] = s_ref[half + 6 + lane];
+    }
+  }
+  __syncwarp();
+
+  // ---- policy observation (add_observation.py:422-459,578-717) ----------------------------------
+  const Quat root_q = ldq(s_sim + 3);
+  int o = 0;
+  const int o_h = o;            o += tk.root_height_obs ? 1 : 0;
+  const int o_rot = o;          o += 6;
+  const int o_dof = o;          o += D;
+  const int o_vel = o;          o += vel ? 6 + D : 0;
+  const int o_phase = o;        o += tk.enable_phase_obs ? 1 + 2 * tk.num_phase_encoding : 0;
+  const int o_tar = o;
+  const int tar_pos_dim = tk.root_height_obs ? 3 : 2;
+  const int tar_dim = tar_pos_dim + 6 + D;
+  if (lane == 31) {
+    if (tk.root_height_obs) s_obs[o_h] = s_sim[2];
+    Quat hinv = {1.f, 0.f, 0.f, 0.f};
+    if (!glob) hinv = calc_heading_quat_inv(root_q);
+    Quat q = glob ? root_q : quat_mul(hinv, root_q);
+    quat_to_tan_norm(q, s_obs + o_rot);
+    if (vel) {
+      Vec3 lv = {s_sim[half], s_sim[half + 1], s_sim[half + 2]}, av = {s_sim[half + 3], s_sim[half + 4], s_sim[half + 5]};
+      if (!glob) { lv = quat_rotate(hinv, lv); av = quat_rotate(hinv, av); }
+      float* v = s_obs + o_vel;
+      v[0] = lv.x; v[1] = lv.y; v[2] = lv.z; v[3] = av.x; v[4] = av.y; v[5] = av.z;
+    }
+    if (tk.enable_phase_obs) {  // calc_phase + compute_phase_obs (motion_lib.py:361-372; add_observation.py:557-575)
+      float ph = mt / p.lib.lengths[mid];
+      if (p.lib.loop_modes[mid] == 1) ph = sub_rn(ph, floorf(ph));
+      ph = fminf(fmaxf(ph, 0.0f), 1.0f);
+      s_obs[o_phase] = ph;
+      for (int k = 0; k < tk.num_phase_encoding; ++k) {
+        float sc = mul_rn(mul_rn(2.0f, 3.14159274101257324f), exp2f((float)k));
+        float v = mul_rn(ph, sc);
+        s_obs[o_phase + 1 + k] = sinf(v);
+        s_obs[o_phase + 1 + tk.num_phase_encoding + k] = cosf(v);
+      }
+    }
+  }
+  if (lane < D) {
+    s_obs[o_dof + lane] = s_sim[7 + lane];
+    if (vel) s_obs[o_vel + 6 + lane] = s_sim[half + 6 + lane];
+  }
+  if (lane < nT) {  // compute_tar_obs, one target step per lane
+    const float* tr = s_tar + lane * half;
+    float* dst = s_obs + o_tar + lane * tar_dim;
+    Vec3 ref_pos = glob ? Vec3{s_sim[0], s_sim[1], s_sim[2]} : Vec3{s_tar[0], s_tar[1], s_tar[2]};
+    Vec3 dp = {sub_rn(tr[0], ref_pos.x), sub_rn(tr[1], ref_pos.y), sub_rn(tr[2], ref_pos.z)};
+    Quat q = ldq(tr + 3);
+    if (!glob) {
+      Quat hinv = calc_heading_quat_inv(ldq(s_tar + 3));
+      dp = quat_rotate(hinv, dp);
+      q = quat_mul(hinv, q);
+    }
+    dst[0] = dp.x; dst[1] = dp.y;
+    if (tk.root_height_obs) dst[2] = tr[2];
+    quat_to_tan_norm(q, dst + tar_pos_dim);
+  }
+  for (int k = 0; k < nT; ++k)
+    if (lane < D) s_obs[o_tar + k * tar_dim + tar_pos_dim + 6 + lane] = s_tar[k * half + 7 + lane];
+
+  // ---- discriminator observations: agent history and demo rows (add_observation.py:276-294,356-419)
+  const int step_dim = 9 + D + (vel ? 6 + D : 0);
+  if (lane < nH) disc_step_small(s_hist + lane * RS, half, s_disc + lane * step_dim, D, glob, vel);
+  else if (lane >= 16 && lane < 16 + nH)
+    disc_step_small(s_demo + (lane - 16) * RS, half, s_dobs + (lane - 16) * step_dim, D, glob, vel);
+  for (int j = 0; j < nH; ++j) {
+    if (lane < D) {
+      s_disc[j * step_dim + 9 + lane] = s_hist[j * RS + 7 + lane];
+      s_dobs[j * step_dim + 9 + lane] = s_demo[j * RS + 7 + lane];
+      if (vel) {
+        s_disc[j * step_dim + 15 + D + lane] = s_hist[j * RS + half + 6 + lane];
+        s_dobs[j * step_dim + 15 + D + lane] = s_demo[j * RS + half + 6 + lane];
+      }
+    }
+  }
+  __syncwarp();
+
+  // ---- stream the rows out ----------------------------------------------------------------------
+  {
+    float* g = p.env.obs_buf + (size_t)e * tk.obs_dim;
+    float* gx = p.has_exp ? p.exp.next_obs + (size_t)e * tk.obs_dim : nullptr;
+    if ((tk.obs_dim & 3) == 0) {
+      for (int i = lane; i < tk.obs_dim / 4; i += 32) {
+        float4 v = *reinterpret_cast<const float4*>(s_obs + 4 * i);
+        stg4(g + 4 * i, v);
+        if (gx) stg4_cs(gx + 4 * i, v);
+      }
+    } else {
+      for (int i = lane; i < tk.obs_dim; i += 32) { g[i] = s_obs[i]; if (gx) gx[i] = s_obs[i]; }
+    }
+    float* gd = p.env.disc_obs + (size_t)e * tk.disc_obs_dim;
+    float* gm = p.env.disc_obs_demo + (size_t)e * tk.disc_obs_dim;
+    float* xd = p.has_exp ? p.exp.disc_obs + (size_t)e * tk.disc_obs_dim : nullptr;
+    float* xm = p.has_exp ? p.exp.disc_obs_demo + (size_t)e * tk.disc_obs_dim : nullptr;
+    if ((tk.disc_obs_dim & 1) == 0) {  // rows are 8-byte aligned: 64-bit stores
+      for (int i = lane; i < tk.disc_obs_dim / 2; i += 32) {
+        float2 a = *reinterpret_cast<const float2*>(s_disc + 2 * i);
+        float2 b = *reinterpret_cast<const float2*>(s_dobs + 2 * i);
+        *reinterpret_cast<float2*>(gd + 2 * i) = a;
+        *reinterpret_cast<float2*>(gm + 2 * i) = b;
+        if (xd) { __stcs(reinterpret_cast<float2*>(xd + 2 * i), a); __stcs(reinterpret_cast<float2*>(xm + 2 * i), b); }
+      }
+    } else {
+      for (int i = lane; i < tk.disc_obs_dim; i += 32) {
+        gd[i] = s_disc[i]; gm[i] = s_dobs[i];
+        if (xd) { xd[i] = s_disc[i]; xm[i] = s_dobs[i]; }
+      }
+    }
+  }
+  if (p.has_exp && lane == 0) {
+    p.exp.motion_ids[e] = mid;
+    p.exp.motion_times[e] = mt;
+  }
+  if (!(p.flags & F_REWARD_DONE)) return;
+
+  // ---- tracking reward (add_reward.py:104-177) --------------------------------------------------
+  float pe = 0.f, ve = 0.f, de = 0.f;
+  if (lane < D) {
+    float w = p.dof_err_w[lane];
+    float pd = sub_rn(s_ref[7 + lane], s_sim[7 + lane]);
+    float vd = sub_rn(s_ref[half + 6 + lane], s_sim[half + 6 + lane]);
+    pe = mul_rn(mul_rn(w, pd), pd);
+    ve = mul_rn(mul_rn(w, vd), vd);
+    de = mul_rn(pd, pd);
+  }
+  pe = warp_sum(pe); ve = warp_sum(ve); de = warp_sum(de);
+  int contact = 0;
+  if (lane < tk.contact_slots && p.sim.valid) {
+    size_t ci = (size_t)e * tk.contact_slots + lane;
+    if (p.sim.valid[ci]) {
+      int la = p.sim.link_a[ci], lb = p.sim.link_b[ci];
+      bool ha = la >= 0 && la < 64 && ((tk.noncontact_link_mask >> la) & 1ull);
+      bool hb = lb >= 0 && lb < 64 && ((tk.noncontact_link_mask >> lb) & 1ull);
+      contact = (ha || hb) ? 1 : 0;
+    }
+  }
+  contact = __any_sync(0xffffffffu, contact);
+  if (lane == 0) {
+    Vec3 rp = {s_sim[0], s_sim[1], s_sim[2]}, tp = {s_ref[0], s_ref[1], s_ref[2]};
+    Vec3 dpos = {sub_rn(tp.x, rp.x), sub_rn(tp.y, rp.y), sub_rn(tp.z, rp.z)};
+    Vec3 dpos_r = dpos;
+    if (!tk.track_root) { dpos_r.x = 0.f; dpos_r.y = 0.f; }
+    if (!tk.track_root_h) dpos_r.z = 0.f;
+    float root_pos_err = add_rn(add_rn(mul_rn(dpos_r.x, dpos_r.x), mul_rn(dpos_r.y, dpos_r.y)), mul_rn(dpos_r.z, dpos_r.z));
+    Quat rq = root_q, tq = ldq(s_ref + 3);
+    Vec3 rv = {s_sim[half], s_sim[half + 1], s_sim[half + 2]}, ra = {s_sim[half + 3], s_sim[half + 4], s_sim[half + 5]};
+    Vec3 tv = {s_ref[half], s_ref[half + 1], s_ref[half + 2]}, ta = {s_ref[half + 3], s_ref[half + 4], s_ref[half + 5]};
+    if (!tk.track_root) {  // convert_to_local_root (add_reward.py:91-102)
+      Quat h0 = calc_heading_quat_inv(rq), h1 = calc_heading_quat_inv(tq);
+      rv = quat_rotate(h0, rv); ra = quat_rotate(h0, ra); rq = quat_mul(h0, rq);
+      tv = quat_rotate(h1, tv); ta = quat_rotate(h1, ta); tq = quat_mul(h1, tq);
+    }
+    float rot_err = quat_diff_angle(rq, tq);
+    rot_err = mul_rn(rot_err, rot_err);
+    Vec3 dv = {sub_rn(tv.x, rv.x), sub_rn(tv.y, rv.y), sub_rn(tv.z, rv.z)};
+    Vec3 da = {sub_rn(ta.x, ra.x), sub_rn(ta.y, ra.y), sub_rn(ta.z, ra.z)};
+    float vel_err = add_rn(add_rn(mul_rn(dv.x, dv.x), mul_rn(dv.y, dv.y)), mul_rn(dv.z, dv.z));
+    float ang_err = add_rn(add_rn(mul_rn(da.x, da.x), mul_rn(da.y, da.y)), mul_rn(da.z, da.z));
+    float pose_r = expf(mul_rn(-tk.pose_scale, pe));
+    float vel_r = expf(mul_rn(-tk.vel_scale, ve));
+    float root_pose_r = expf(mul_rn(-tk.root_pose_scale, add_rn(root_pos_err, mul_rn(0.1f, rot_err))));
+    float root_vel_r = expf(mul_rn(-tk.root_vel_scale, add_rn(vel_err, mul_rn(0.1f, ang_err))));
+    float r = add_rn(add_rn(add_rn(mul_rn(tk.pose_w, pose_r), mul_rn(tk.vel_w, vel_r)), mul_rn(tk.root_pose_w, root_pose_r)),
+                     mul_rn(tk.root_vel_w, root_vel_r));
+    // ---- done flags (add_done.py:97-147): later writes win -------------------------------------
+    int done = 0;
+    if (t >= tk.ep_len) done = 3;
+    if (mt >= p.lib.lengths[mid] && p.lib.loop_modes[mid] != 1) done = 2;
+    if (tk.enable_early_termination) {
+      bool failed = contact != 0;
+      if (tk.pose_termination) {
+        bool pf = (de / (float)D) > tk.pose_termination_dist;
+        if (tk.track_root) {
+          float re = add_rn(add_rn(mul_rn(dpos.x, dpos.x), mul_rn(dpos.y, dpos.y)), mul_rn(dpos.z, dpos.z));
+          pf = pf || (re > tk.pose_termination_dist);
+        }
+        failed = failed || pf;
+      }
+      if (failed && t > 0.0f) done = 1;
+    }
+    p.env.reward[e] = r;
+    p.env.done[e] = done;
+    if (p.has_exp) { p.exp.reward[e] = r; p.exp.done[e] = done; }
+    // ---- ReturnTracker.update ---------------------------------------------------------------------
+    if (p.env.return_buf) {
+      float ret = add_rn(p.env.return_buf[e], r);
+      long long len = p.env.ep_len_buf[e] + 1;
+      if (done != 0) {
+        atomicAdd(p.env.tracker_sums, (double)ret);
+        atomicAdd(p.env.tracker_sums + 1, (double)len);
+        atomicAdd(reinterpret_cast<unsigned long long*>(p.env.tracker_count), 1ull);
+        p.env.eps_per_env[e] += 1;
+        ret = 0.f; len = 0;
+      }
+      p.env.return_buf[e] = ret;
+      p.env.ep_len_buf[e] = len;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+struct ResetParams {
+  addk_task task;
+  addk_motion_lib lib;
+  addk_env_buffers env;
+  const long long* new_ids;
+  const float* new_times;
+  int n, head, reset_all;
+  float* qpos_out;
+  float* qvel_out;
+  uint8_t* reset_mask_out;
+};
+
+__global__ void __launch_bounds__(WPB * 32) reset_done_kernel(const __grid_constant__ ResetParams p) {
+  const addk_task& tk = p.task;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int e = blockIdx.x * WPB + warp;
+  if (e >= p.n) return;
+  int dn = (lane == 0) ? p.env.done[e] : 0;   // lane 0 also clears the flag below
+  dn = __shfl_sync(0xffffffffu, dn, 0);
+  const bool doit = p.reset_all || dn != 0;
+  if (lane == 0 && p.reset_mask_out) p.reset_mask_out[e] = doit ? 1 : 0;
+  if (!doit) return;
+  const int D = tk.num_dofs, half = (7 + D + 3) & ~3, RS = p.lib.row_stride, nH = tk.num_disc_steps;
+  const long long mid = p.new_ids[e];
+  const float off = p.new_times[e];
+  if (lane == 0) {
+    p.env.motion_ids[e] = mid;
+    p.env.motion_time_offsets[e] = off;
+    p.env.time_buf[e] = 0.0f;   // Environment.reset_idx (env.py:157-163)
+    p.env.done[e] = 0;          // ADDDone.reset_idx (add_done.py:92-93)
+  }
+  const float mt = add_rn(0.0f, off);
+  const long long start = p.lib.start_idx[mid];
+  const float* row = p.lib.table + (size_t)table_row(p.lib, mt, tk.dt_inv, start) * RS;
+  // ref_* and the pose written into the simulator (add_observation.py:308-331)
+  for (int c = lane; c < 7 + D; c += 32) {
+    float v = row[c];
+    if (p.qpos_out) p.qpos_out[(size_t)e * (7 + D) + c] = v;
+    if (c < 3) p.env.ref_root_pos[(size_t)e * 3 + c] = v;
+    else if (c < 7) p.env.ref_root_rot[(size_t)e * 4 + (c - 3)] = v;
+    else p.env.ref_dof_pos[(size_t)e * D + (c - 7)] = v;
+  }
+  for (int c = lane; c < 6 + D; c += 32) {
+    float v = row[half + c];
+    if (p.qvel_out) p.qvel_out[(size_t)e * (6 + D) + c] = v;
+    if (c < 3) p.env.ref_root_vel[(size_t)e * 3 + c] = v;
+    else if (c < 6) p.env.ref_root_ang_vel[(size_t)e * 3 + (c - 3)] = v;
+    else p.env.ref_dof_vel[(size_t)e * D + (c - 6)] = v;
+  }
+  // _reset_disc_hist + CircularBuffer.fill: logical j -> slot (head + j) % nH (circular_buffer.py:22-29)
+  float* g_hist = p.env.hist + (size_t)e * nH * p.env.hist_stride;
+  const int r4 = RS / 4;
+  for (int i = lane; i < nH * r4; i += 32) {
+    int j = i / r4, c = i - j * r4;
+    const float* src = p.lib.table + (size_t)table_row(p.lib, add_rn(mt, tk.disc_offsets[j]), tk.dt_inv, start) * RS;
+    int slot = (p.head + j) % nH;
+    stg4(g_hist + (size_t)slot * p.env.hist_stride + 4 * c, ldg4(src + 4 * c));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// c10::div_floor_floating, the arithmetic behind `time // dt` on fp32 tensors (sampler.py:88).
+__device__ __forceinline__ float floor_div(float a, float b) {
+  float mod = fmodf(a, b);
+  float div = sub_rn(a, mod) / b;
+  if (mod != 0.0f && ((b < 0.0f) != (mod < 0.0f))) div = sub_rn(div, 1.0f);
+  float fl;
+  if (div != 0.0f) {
+    fl = floorf(div);
+    if (sub_rn(div, fl) > 0.5f) fl = add_rn(fl, 1.0f);
+  } else {
+    fl = copysignf(0.0f, a / b);
+  }
+  return fl;
+}
+
+__global__ void sample_clip_kernel(const float* __restrict__ weights, int C, const float* __restrict__ errors, int S,
+                                   const int32_t* __restrict__ done, const float* __restrict__ u, int n,
+                                   unsigned int* temp_bits, long long* ids_out) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  if (done && done[e] == 0) return;
+  // inverse CDF over the (normalised) clip weights -- torch.multinomial with replacement (motion_lib.py:35-39)
+  float u0 = u[3 * (size_t)e], cum = 0.f;
+  int c = C - 1;
+  for (int k = 0; k < C; ++k) { cum = add_rn(cum, weights[k]); if (u0 < cum) { c = k; break; } }
+  ids_out[e] = c;
+  if (temp_bits) {  // temperature None: max error over the clips drawn in this batch (sampler.py:66-69)
+    float m = 0.f;
+    for (int s = 0; s < S; ++s) m = fmaxf(m, errors[c * S + s]);
+    atomicMax(temp_bits, __float_as_uint(m));
+  }
+}
+
+__global__ void sample_time_kernel(const float* __restrict__ errors, int S, const float* __restrict__ seg_sizes,
+                                   float dt, float min_start, float temperature, int rand_reset,
+                                   const int32_t* __restrict__ done, const float* __restrict__ u, int n,
+                                   const unsigned int* temp_bits, const long long* __restrict__ ids, float* times_out) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  if (done && done[e] == 0) return;
+  if (!rand_reset) { times_out[e] = 0.f; return; }
+  int c = (int)ids[e];
+  float temp = temp_bits ? add_rn(__uint_as_float(*temp_bits), 1e-6f) : temperature;
+  const float* er = errors + (size_t)c * S;
+  float mx = -INFINITY;
+  for (int s = 0; s < S; ++s) mx = fmaxf(mx, er[s] / temp);
+  float z = 0.f;
+  for (int s = 0; s < S; ++s) z = add_rn(z, expf(sub_rn(er[s] / temp, mx)));
+  float u1 = u[3 * (size_t)e + 1], cum = 0.f;
+  int seg = S - 1;
+  for (int s = 0; s < S; ++s) { cum = add_rn(cum, expf(sub_rn(er[s] / temp, mx)) / z); if (u1 < cum) { seg = s; break; } }
+  float sz = seg_sizes[c];
+  float tm = add_rn(mul_rn((float)seg, sz), mul_rn(u[3 * (size_t)e + 2], sz));
+  tm = mul_rn(floor_div(tm, dt), dt);
+  times_out[e] = fmaxf(tm, min_start);
+}
+
+__global__ void sampler_accum_kernel(const long long* __restrict__ clip_ids, const float* __restrict__ timesteps,
+                                     const float* __restrict__ a, const float* __restrict__ b, int dim, int n,
+                                     const float* __restrict__ seg_sizes, int S, double* sums, int* counts) {
+  int i = blockIdx.x * (blockDim.x / 32) + (threadIdx.x / 32);
+  int lane = threadIdx.x & 31;
+  if (i >= n) return;
+  float acc = 0.f;
+  for (int c = lane; c < dim; c += 32) {
+    float d = sub_rn(a[(size_t)i * dim + c], b[(size_t)i * dim + c]);
+    acc += d * d;
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) {
+    long long c = clip_ids[i];
+    float sz = fmaxf(seg_sizes[c], 1e-6f);
+    long long seg = (long long)(timesteps[i] / sz);
+    seg = seg < 0 ? 0 : (seg > S - 1 ? S - 1 : seg);
+    atomicAdd(sums + c * S + seg, (double)acc);
+    atomicAdd(counts + c * S + seg, 1);
+  }
+}
+
+__global__ void sampler_ema_kernel(double* sums, int* counts, int bins, float* errors) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= bins) return;
+  if (counts[i] > 0) {
+    float mean = (float)(sums[i] / (double)counts[i]);
+    errors[i] = add_rn(mul_rn(0.9f, errors[i]), mul_rn(0.1f, mean));
+  }
+  sums[i] = 0.0;
+  counts[i] = 0;
+}
+
+}  // namespace addk
+
+using namespace addk;
+
+static int step_smem_bytes(const addk_task& tk, int RS) {
+  const int D = tk.num_dofs, half = (7 + D + 3) & ~3;
+  const int nT = tk.enable_tar_obs ? tk.num_tar_steps : 0, nH = tk.num_disc_steps;
+  const int per_warp = RS + nT * half + nH * RS + RS + nH * RS + ((tk.obs_dim + 3) & ~3) + 2 * ((tk.disc_obs_dim + 3) & ~3);
+  return per_warp * WPB * (int)sizeof(float);
+}
+
+extern "C" int addk_env_step(void* stream, const addk_task* task, const addk_motion_lib* lib,
+                             const addk_sim_state* sim, const addk_env_buffers* env, const addk_exp_row* exp,
+                             const float* dof_err_w, const uint8_t* env_mask, int num_envs, int hist_head, int flags) {
+  if (!task || !lib || !sim || !env || num_envs <= 0) return ADDK_ERR_ARG;
+  const int D = task->num_dofs, half = (7 + D + 3) & ~3;
+  if (D < 1 || D > 31 || lib->row_stride < 2 * half || (lib->row_stride & 3) || env->hist_stride < lib->row_stride ||
+      (env->hist_stride & 3) || task->num_tar_steps > ADDK_MAX_TAR_STEPS || task->num_tar_steps > 16 ||
+      task->num_disc_steps > ADDK_MAX_DISC_STEPS || task->num_disc_steps < 1 || task->contact_slots > 32)
+    return ADDK_ERR_ARG;
+  if ((flags & F_MASKED) && !env_mask) return ADDK_ERR_ARG;
+  if ((flags & F_REWARD_DONE) && !dof_err_w) return ADDK_ERR_ARG;
+  StepParams p;
+  p.task = *task; p.lib = *lib; p.sim = *sim; p.env = *env;
+  p.has_exp = exp != nullptr;
+  if (exp) p.exp = *exp; else p.exp = addk_exp_row{};
+  p.dof_err_w = dof_err_w; p.env_mask = env_mask; p.n = num_envs; p.flags = flags;
+  const int nH = task->num_disc_steps;
+  // with a push the newest entry lands in slot `hist_head`; without, the newest is the slot before the head
+  p.newest_slot = (flags & F_UPDATE_MOTION) ? hist_head % nH : (hist_head + nH - 1) % nH;
+  int smem = step_smem_bytes(*task, lib->row_stride);
+  if (smem > 200 * 1024) return ADDK_ERR_UNSUPPORTED;
+  static int configured = 0;
+  if (smem > 48 * 1024 && configured < smem) {
+    cudaFuncSetAttribute(env_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    configured = smem;
+  }
+  env_step_kernel<<<(num_envs + WPB - 1) / WPB, WPB * 32, smem, (cudaStream_t)stream>>>(p);
+  ADDK_CHECK_LAUNCH();
+  return ADDK_OK;
+}
+
+extern "C" int addk_reset_done(void* stream, const addk_task* task, const addk_motion_lib* lib,
+                               const addk_env_buffers* env, const long long* new_ids, const float* new_times,
+                               int num_envs, int hist_head, int reset_all, float* qpos_out, float* qvel_out,
+                               uint8_t* reset_mask_out) {
+  if (!task || !lib || !env || !new_ids || !new_times || num_envs <= 0) return ADDK_ERR_ARG;
+  ResetParams p;
+  p.task = *task; p.lib = *lib; p.env = *env; p.new_ids = new_ids; p.new_times = new_times;
+  p.n = num_envs; p.head = hist_head % task->num_disc_steps; p.reset_all = reset_all;
+  p.qpos_out = qpos_out; p.qvel_out = qvel_out; p.reset_mask_out = reset_mask_out;
+  reset_done_kernel<<<(num_envs + WPB - 1) / WPB, WPB * 32, 0, (cudaStream_t)stream>>>(p);
+  ADDK_CHECK_LAUNCH();
+  return ADDK_OK;
+}
+
+extern "C" int addk_sample_motion_time(void* stream, const float* motion_weights, int num_motions,
+                                       const float* errors, int num_segments, const float* seg_sizes, float dt,
+                                       float min_start_time, float temperature, int rand_reset,
+                                       const int32_t* done, const float* uniforms, int num_envs,
+                                       unsigned int* temp_bits_work, long long* ids_out, float* times_out) {
+  if (!motion_weights || !errors || !seg_sizes || !uniforms || !ids_out || !times_out || num_envs <= 0)
+    return ADDK_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned int* tb = (temperature < 0.f) ? temp_bits_work : nullptr;
+  if (temperature < 0.f && !temp_bits_work) return ADDK_ERR_ARG;
+  if (tb) cudaMemsetAsync(tb, 0, sizeof(unsigned int), st);
+  int th = 128, bl = (num_envs + th - 1) / th;
+  sample_clip_kernel<<<bl, th, 0, st>>>(motion_weights, num_motions, errors, num_segments, done, uniforms, num_envs,
+                                        tb, ids_out);
+  ADDK_CHECK_LAUNCH();
+  sample_time_kernel<<<bl, th, 0, st>>>(errors, num_segments, seg_sizes, dt, min_start_time, temperature, rand_reset,
+                                        done, uniforms, num_envs, tb, ids_out, times_out);
+  ADDK_CHECK_LAUNCH();
+  return ADDK_OK;
+}
+
+extern "C" int addk_sampler_update_errors(void* stream, const long long* clip_ids, const float* timesteps,
+                                          const float* disc_obs, const float* disc_obs_demo, int disc_dim, int n,
+                                          const float* seg_sizes, int num_motions, int num_segments,
+                                          double* sums_work, int* counts_work, float* errors) {
+  if (!clip_ids || !timesteps || !disc_obs || !disc_obs_demo || !sums_work || !counts_work || !errors || n <= 0)
+    return ADDK_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  sampler_accum_kernel<<<(n + 7) / 8, 256, 0, st>>>(clip_ids, timesteps, disc_obs, disc_obs_demo, disc_dim, n,
+                                                    seg_sizes, num_segments, sums_work, counts_work);
+  ADDK_CHECK_LAUNCH();
+  int bins = num_motions * num_segments;
+  sampler_ema_kernel<<<(bins + 127) / 128, 128, 0, st>>>(sums_work, counts_work, bins, errors);
+  ADDK_CHECK_LAUNCH();
+  return ADDK_OK;
+}

@@ -1,0 +1,214 @@
+/* addk -- C ABI of the B200-native add-gym hot path (libaddk.so).
+ *
+ * The reference (rsamf/add-gym) has no FFI: its boundary for this path is a set of Python classes the
+ * agent constructs by name (add_gym/learning/add/add_agent.py:30-60).  The drop-in classes in
+ * add_gym_b200/ keep those names and put this library underneath them.  Every entry point below cites
+ * the reference interface it replaces; INTEGRATION.md shows the ctypes stub a maintainer would add to
+ * the reference itself.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in `_host`; the caller owns all memory,
+ *     nothing is allocated and nothing synchronises with the host inside a call;
+ *   - `stream` is a cudaStream_t (pass torch.cuda.current_stream().cuda_stream);
+ *   - return value 0 = ok, non-zero = ADDK_ERR_* ; addk_last_error() gives the text;
+ *   - quaternions are wxyz, all floating data fp32, ids int64 (torch.long), done flags int32.
+ */
+#ifndef ADDK_H_
+#define ADDK_H_
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ADDK_MAX_TAR_STEPS 16
+#define ADDK_MAX_DISC_STEPS 8
+
+const char* addk_last_error(void);
+int addk_version(void);
+/* number of kernel launches issued through this library since the last reset (bench.py "gpu_launches") */
+long long addk_launch_count(int reset);
+
+/* ---------------------------------------------------------------------------------------------
+ * Task description shared by the per-step kernels.  Plain data, filled once by the host from the
+ * task YAML keys the reference plugins read (configs/task/pose.yaml).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct addk_task {
+  int32_t num_dofs;            /* D = 29 */
+  int32_t num_tar_steps;       /* len(tar_obs_steps); 0 when enable_tar_obs is false */
+  int32_t num_disc_steps;      /* num_disc_obs_steps */
+  int32_t global_obs, root_height_obs, enable_vel_obs, enable_phase_obs, enable_tar_obs;
+  int32_t num_phase_encoding;
+  int32_t obs_dim, disc_obs_dim;
+  int32_t track_root, track_root_h;                 /* add_obs._track_global_root(), root_height_obs */
+  int32_t enable_early_termination, pose_termination;
+  int32_t contact_slots;                            /* C of get_contacts()[...] [N,C] */
+  float tar_offsets[ADDK_MAX_TAR_STEPS];            /* fl32(dt * k)  (add_observation.py:214-215) */
+  float disc_offsets[ADDK_MAX_DISC_STEPS];          /* oldest -> newest (add_observation.py:362-370) */
+  float ctrl_dt;                                    /* env.time_buf += ctrl_dt (env.py:155) */
+  float dt_inv;                                     /* MotionLib._dt_inv = round(1/dt) (motion_lib.py:23) */
+  float pose_w, vel_w, root_pose_w, root_vel_w;     /* add_reward.py:12-21 */
+  float pose_scale, vel_scale, root_pose_scale, root_vel_scale;
+  float ep_len, pose_termination_dist;              /* add_done.py:21-25 */
+  uint64_t noncontact_link_mask;                    /* bit l set: link idx l is not allowed to touch the plane */
+} addk_task;
+
+/* Motion library metadata living on the device (MotionLib, motion_lib.py:236-283). */
+typedef struct addk_motion_lib {
+  const float* table;          /* [S_total, row_stride] step table, layout in csrc/motion.cu */
+  int32_t row_stride;          /* floats per row (72 for D = 29) */
+  int32_t num_motions;
+  int64_t s_total;             /* rows in the table = _step_root_pos.shape[-2] */
+  const int64_t* start_idx;    /* [C]  MotionLib._motion_start_idx (30 fps cumsum, quirk Q2) */
+  const float* lengths;        /* [C]  seconds */
+  const int32_t* loop_modes;   /* [C]  0 CLAMP / 1 WRAP */
+} addk_motion_lib;
+
+/* Simulator state as the engine getters return it (robot.py:271-293): AoS rows with a leading dim. */
+typedef struct addk_sim_state {
+  const float* root_pos;  int32_t ld_root_pos;     /* [N,3]   */
+  const float* root_rot;  int32_t ld_root_rot;     /* [N,4]   */
+  const float* root_vel;  int32_t ld_root_vel;     /* [N,3]   */
+  const float* root_ang;  int32_t ld_root_ang;     /* [N,3]   */
+  const float* dof_pos;   int32_t ld_dof_pos;      /* [N,D] = get_dofs_position()[:,6:] */
+  const float* dof_vel;   int32_t ld_dof_vel;      /* [N,D] */
+  const int32_t* link_a;  const int32_t* link_b;   /* [N,C] contact pairs vs the ground plane */
+  const uint8_t* valid;                            /* [N,C] */
+} addk_sim_state;
+
+/* Persistent per-env tensors owned by ADDObservation / ADDDone / Environment and mutated in place. */
+typedef struct addk_env_buffers {
+  float* time_buf;              /* [N]  env.time_buf */
+  int64_t* motion_ids;          /* [N]  add_obs._motion_ids */
+  float* motion_time_offsets;   /* [N]  add_obs._motion_time_offsets */
+  float* ref_root_pos; float* ref_root_rot; float* ref_root_vel; float* ref_root_ang_vel; /* [N,3|4|3|3] */
+  float* ref_dof_pos;  float* ref_dof_vel;  /* [N,D] */
+  float* hist;                  /* [N, num_disc_steps, hist_stride] ring of sim states: pose half | vel half */
+  int32_t hist_stride;
+  float* obs_buf;               /* [N, obs_dim] */
+  float* disc_obs;              /* [N, disc_obs_dim]   info["disc_obs"] */
+  float* disc_obs_demo;         /* [N, disc_obs_dim]   info["disc_obs_demo"] */
+  float* reward;                /* [N] */
+  int32_t* done;                /* [N] add_done.done_buf */
+  /* ReturnTracker (base_agent.py:564-621) */
+  float* return_buf; int64_t* ep_len_buf; int64_t* eps_per_env;
+  double* tracker_sums;         /* [2] sum of returns / of lengths over finished episodes */
+  int64_t* tracker_count;       /* [1] finished episodes */
+} addk_env_buffers;
+
+/* Row `t` of the [T,N,...] experience buffers (ExperienceBuffer.record, experience_buffer.py:50-53). */
+typedef struct addk_exp_row {
+  float* next_obs; float* reward; int32_t* done; float* disc_obs; float* disc_obs_demo;
+  int64_t* motion_ids; float* motion_times;
+} addk_exp_row;
+
+/* ----- motion table (csrc/motion.cu) --------------------------------------------------------- */
+/* MotionLib._load_motion_pkl + _precompute_motion_steps for ONE clip (motion_lib.py:164-320).
+ * frames [F,7+D] fp32 in file layout; writes rows [row0, row0+n_steps) of `table`. */
+int addk_motion_table_build(void* stream, const float* frames, int num_frames, int num_dofs,
+                            const int* col_of_dof, const float* dof_axis, float fps, float frame_dt,
+                            int n_steps, double dt, float motion_len, int loop_wrap, float* jrot_work,
+                            float* fvel_work, float* table, int row_stride, long long row0,
+                            float* joint_rot_out, long long* frame_idx_out);
+/* MotionLib.get_precomputed_motion_step (motion_lib.py:322-335); any output may be NULL. */
+int addk_motion_gather(void* stream, const float* table, int row_stride, int num_dofs, long long s_total,
+                       const long long* start_idx, float dt_inv, const long long* ids, const float* times,
+                       int n, float* root_pos, float* root_rot, float* root_vel, float* root_ang_vel,
+                       float* dof_pos, float* dof_vel, long long* idx_out);
+
+/* ----- fused per-step work around the physics step (csrc/step.cu) ---------------------------- */
+/* ADDAgent._step_env after scene.step() + _record_data_post_step + ReturnTracker.update
+ * (add_agent.py:93-108,204-219; add_observation.py:163-207,296-306; add_reward.py:54-89;
+ *  add_done.py:59-90; base_agent.py:596-621).  flags: bit0 advance time_buf by ctrl_dt,
+ *  bit1 update ref motion + push history (update_motion), bit2 compute reward/done + tracker,
+ *  bit3 only touch envs whose `env_mask` byte is non-zero.  `hist_head` is the ring slot written
+ *  by this push (CircularBuffer._head before the push). `exp` may be NULL. */
+int addk_env_step(void* stream, const addk_task* task_host, const addk_motion_lib* lib_host,
+                  const addk_sim_state* sim_host, const addk_env_buffers* env_host,
+                  const addk_exp_row* exp_host, const float* dof_err_w, const uint8_t* env_mask,
+                  int num_envs, int hist_head, int flags);
+/* ADDObservation.reset_idx for the envs with done != 0 (add_observation.py:308-344; env.py:157-163;
+ * add_done.py:92-93): adopts (new_ids,new_times), zeroes time/done, refreshes ref_*, refills the
+ * history from the table and emits the pose to write into the simulator.  reset_mask_out[N] = 1 for
+ * the envs that were reset. `hist_head` is CircularBuffer._head. */
+int addk_reset_done(void* stream, const addk_task* task_host, const addk_motion_lib* lib_host,
+                    const addk_env_buffers* env_host, const long long* new_ids, const float* new_times,
+                    int num_envs, int hist_head, int reset_all, float* qpos_out, float* qvel_out,
+                    uint8_t* reset_mask_out);
+/* ADDMotion.sample_time for every env (add_motion.py:53-61; motion_lib.py:35-39; sampler.py:57-92)
+ * from three uniforms per env.  Candidates are only consumed where done != 0. */
+int addk_sample_motion_time(void* stream, const float* motion_weights, int num_motions, const float* errors,
+                            int num_segments, const float* seg_sizes, float dt, float min_start_time,
+                            float temperature, int rand_reset, const int32_t* done, const float* uniforms,
+                            int num_envs, unsigned int* temp_bits_work, long long* ids_out, float* times_out);
+/* AdaptiveSegmentSampler.update_errors (sampler.py:20-55). sums/counts are [C*S] work buffers. */
+int addk_sampler_update_errors(void* stream, const long long* clip_ids, const float* timesteps,
+                               const float* disc_obs, const float* disc_obs_demo, int disc_dim, int n,
+                               const float* seg_sizes, int num_motions, int num_segments, double* sums_work,
+                               int* counts_work, float* errors);
+
+/* ----- returns / advantages / statistics (csrc/gae.cu) --------------------------------------- */
+/* compute_td_lambda_return + next_vals masking + adv (base_agent.py:624-647; ppo_agent.py:126-146). */
+int addk_td_lambda(void* stream, const float* reward, const float* next_vals, const float* vals,
+                   const int32_t* done, int T, int N, float discount, float td_lambda, float succ_val,
+                   float fail_val, float* tar_val, float* adv);
+/* std_mean over rand_action_mask == 1 (unbiased) then clamp((adv-mean)/max(std,1e-5), +-clip)
+ * (ppo_agent.py:147-153).  stats_out: [mean, std]. */
+int addk_adv_normalize(void* stream, float* adv, const float* rand_action_mask, int n, float clip,
+                       double* work3, float* stats_out);
+/* _calc_disc_rewards tail + reward mix (amp_agent.py:194-206; add_agent.py:124):
+ * r = w_task*task_r + w_disc * scale * -log(max(1 - sigmoid(logit), 1e-4)); stats_out [mean,std] of disc_r */
+int addk_disc_reward(void* stream, const float* logits, float* reward_inout, int n, float scale, float w_task,
+                     float w_disc, double* work3, float* stats_out);
+/* Column sums over rows of X[n, dim] in fp64: mode 0 -> (sum, sum of squares), mode 1 -> sum |a - b|.
+ * Replaces Normalizer.record / DiffNormalizer.record accumulated over one iteration
+ * (normalizer.py:25-35; diff_normalizer.py:24-31). out is [2*dim] or [dim] doubles, pre-zeroed. */
+int addk_column_stats(void* stream, const float* a, const float* b, long long n, int dim, int mode, double* out);
+/* Normalizer.update / DiffNormalizer.update (normalizer.py:37-80; diff_normalizer.py:33-45). */
+int addk_normalizer_update(void* stream, const double* sums, double new_count, int dim, int64_t* count,
+                           float* mean, float* mean_sq, float* std, float min_var);
+int addk_diff_normalizer_update(void* stream, const double* sum_abs, double new_count, int dim, int64_t* count,
+                                float* mean_abs);
+
+/* ----- dense layers on the CUDA cores / tensor cores (csrc/gemm.cu, csrc/gemm_tc.cu) ---------- */
+/* C[M,N] = act( normA(A)[M,K] . op(B) + bias ) ; see csrc/gemm.cu for the flag bits. */
+typedef struct addk_gemm_args {
+  const float* A; int32_t lda;       /* A_T=0: [M,K] row-major ; A_T=1: [K,M] row-major */
+  const float* B; int32_t ldb;       /* B_T=1: [N,K] row-major (nn.Linear weight) ; B_T=0: [K,N] */
+  float* C; int32_t ldc;
+  int32_t M, N, K;
+  const float* bias;                 /* [N] or NULL */
+  const float* a_mean; const float* a_std;  /* optional (A-mean)/std on load, per K column */
+  const float* relu_mask_src; int32_t ld_mask;  /* optional: C *= (mask_src > 0), [M,N] */
+  int32_t trans_a, trans_b, relu, split_k;  /* split_k > 1: C is [split_k, M, N] partial slabs */
+  int32_t accumulate;                /* C += result (single-slab only) */
+} addk_gemm_args;
+int addk_gemm(void* stream, const addk_gemm_args* args_host, int precision);
+
+/* ----- PPO / ADD minibatch (csrc/mlp.cu) ------------------------------------------------------ */
+struct addk_update_ctx;  /* opaque; plain host struct of device pointers, see csrc/mlp.cu */
+int addk_update_ctx_size(void);
+/* fills in the context from a flat pointer table; layout documented in add_gym_b200/_lib.py */
+int addk_update_ctx_init(void* ctx_host, const void* const* ptrs, int n_ptrs, const int64_t* ints, int n_ints,
+                         const double* floats, int n_floats);
+/* one optimizer step: ExperienceBuffer.sample gather + AMPAgent._compute_loss + backward + AdamW
+ * (experience_buffer.py:74-113; amp_agent.py:98-114; ppo_agent.py:194-275; add_agent.py:141-202;
+ *  mp_optimizer.py:14-23).  idx: the int64 minibatch permutation slice. */
+int addk_update_minibatch(void* stream, void* ctx_host, const long long* idx, int step_index, int do_optim);
+/* actor inference for one env step (ppo_agent.py:72-104) */
+int addk_actor_step(void* stream, void* ctx_host, const float* obs, const float* noise, const float* exp_mask,
+                    int n, float* action, float* a_logp, float* obs_rec, float* action_rec, float* logp_rec,
+                    float* mask_rec);
+/* critic over rows (ppo_agent.py:120-144) and discriminator logits (amp_agent.py:194-200) */
+int addk_critic_eval(void* stream, void* ctx_host, const float* obs, long long n, float* vals);
+int addk_disc_eval(void* stream, void* ctx_host, const float* disc_obs, const float* disc_obs_demo, long long n,
+                   float* logits);
+/* AdamW on a flat fp32 parameter vector (torch.optim.AdamW, mp_optimizer.py:38; lr,betas,eps,wd). */
+int addk_adamw(void* stream, float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n,
+               int step, double lr, double beta1, double beta2, double eps, double weight_decay,
+               double grad_scale);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ADDK_H_ */
