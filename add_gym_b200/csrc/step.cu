@@ -380,7 +380,7 @@ struct ResetParams {
   addk_env_buffers env;
   const long long* new_ids;
   const float* new_times;
-  int n, head, reset_all;
+  int n, head, reset_all, zero_time_done;
   float* qpos_out;
   float* qvel_out;
   uint8_t* reset_mask_out;
@@ -402,10 +402,12 @@ __global__ void __launch_bounds__(WPB * 32) reset_done_kernel(const __grid_const
   if (lane == 0) {
     p.env.motion_ids[e] = mid;
     p.env.motion_time_offsets[e] = off;
-    p.env.time_buf[e] = 0.0f;   // Environment.reset_idx (env.py:157-163)
-    p.env.done[e] = 0;          // ADDDone.reset_idx (add_done.py:92-93)
+    if (p.zero_time_done) {
+      p.env.time_buf[e] = 0.0f;   // Environment.reset_idx (env.py:157-163)
+      p.env.done[e] = 0;          // ADDDone.reset_idx (add_done.py:92-93)
+    }
   }
-  const float mt = add_rn(0.0f, off);
+  const float mt = add_rn(p.zero_time_done ? 0.0f : p.env.time_buf[e], off);
   const long long start = p.lib.start_idx[mid];
   const float* row = p.lib.table + (size_t)table_row(p.lib, mt, tk.dt_inv, start) * RS;
   // ref_* and the pose written into the simulator (add_observation.py:308-331)
@@ -499,11 +501,15 @@ __global__ void sampler_accum_kernel(const long long* __restrict__ clip_ids, con
   int lane = threadIdx.x & 31;
   if (i >= n) return;
   float acc = 0.f;
-  for (int c = lane; c < dim; c += 32) {
-    float d = sub_rn(a[(size_t)i * dim + c], b[(size_t)i * dim + c]);
-    acc += d * d;
+  if (b) {  // tracking error = sum((disc_obs - disc_obs_demo)^2)  (add_agent.py:120-122)
+    for (int c = lane; c < dim; c += 32) {
+      float d = sub_rn(a[(size_t)i * dim + c], b[(size_t)i * dim + c]);
+      acc += d * d;
+    }
+    acc = warp_sum(acc);
+  } else {  // `a` already holds one tracking error per sample
+    acc = a[i];
   }
-  acc = warp_sum(acc);
   if (lane == 0) {
     long long c = clip_ids[i];
     float sz = fmaxf(seg_sizes[c], 1e-6f);
@@ -569,12 +575,12 @@ extern "C" int addk_env_step(void* stream, const addk_task* task, const addk_mot
 
 extern "C" int addk_reset_done(void* stream, const addk_task* task, const addk_motion_lib* lib,
                                const addk_env_buffers* env, const long long* new_ids, const float* new_times,
-                               int num_envs, int hist_head, int reset_all, float* qpos_out, float* qvel_out,
+                               int num_envs, int hist_head, int reset_all, int zero_time_done, float* qpos_out, float* qvel_out,
                                uint8_t* reset_mask_out) {
   if (!task || !lib || !env || !new_ids || !new_times || num_envs <= 0) return ADDK_ERR_ARG;
   ResetParams p;
   p.task = *task; p.lib = *lib; p.env = *env; p.new_ids = new_ids; p.new_times = new_times;
-  p.n = num_envs; p.head = hist_head % task->num_disc_steps; p.reset_all = reset_all;
+  p.n = num_envs; p.head = hist_head % task->num_disc_steps; p.reset_all = reset_all; p.zero_time_done = zero_time_done;
   p.qpos_out = qpos_out; p.qvel_out = qvel_out; p.reset_mask_out = reset_mask_out;
   reset_done_kernel<<<(num_envs + WPB - 1) / WPB, WPB * 32, 0, (cudaStream_t)stream>>>(p);
   ADDK_CHECK_LAUNCH();
@@ -602,12 +608,23 @@ extern "C" int addk_sample_motion_time(void* stream, const float* motion_weights
   return ADDK_OK;
 }
 
+extern "C" int addk_sample_start_time(void* stream, const float* errors, int num_segments, const float* seg_sizes,
+                                      float dt, float min_start_time, float temperature, const float* uniforms, int n,
+                                      const long long* clip_ids, float* times_out) {
+  if (!errors || !seg_sizes || !uniforms || !clip_ids || !times_out || n <= 0 || temperature <= 0.f) return ADDK_ERR_ARG;
+  sample_time_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(errors, num_segments, seg_sizes, dt,
+                                                                        min_start_time, temperature, 1, nullptr, uniforms,
+                                                                        n, nullptr, clip_ids, times_out);
+  ADDK_CHECK_LAUNCH();
+  return ADDK_OK;
+}
+
 extern "C" int addk_sampler_update_errors(void* stream, const long long* clip_ids, const float* timesteps,
                                           const float* disc_obs, const float* disc_obs_demo, int disc_dim, int n,
                                           const float* seg_sizes, int num_motions, int num_segments,
                                           double* sums_work, int* counts_work, float* errors) {
-  if (!clip_ids || !timesteps || !disc_obs || !disc_obs_demo || !sums_work || !counts_work || !errors || n <= 0)
-    return ADDK_ERR_ARG;
+  // disc_obs_demo == NULL: `disc_obs` is a ready-made [n] vector of tracking errors (sampler.py:21 signature)
+  if (!clip_ids || !timesteps || !disc_obs || !sums_work || !counts_work || !errors || n <= 0) return ADDK_ERR_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   sampler_accum_kernel<<<(n + 7) / 8, 256, 0, st>>>(clip_ids, timesteps, disc_obs, disc_obs_demo, disc_dim, n,
                                                     seg_sizes, num_segments, sums_work, counts_work);

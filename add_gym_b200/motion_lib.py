@@ -1,0 +1,189 @@
+"""MotionLib: the reference-motion step table in HBM and its lookups.
+
+Drop-in for the reference's ``add_gym.anim.motion_lib.MotionLib`` as far as the hot path uses it
+(motion_lib.py:18-59,285-335): same constructor, same query methods, same index arithmetic -- but the
+30 fps -> 100 Hz resampling (root lerp, root / joint slerp, twist-angle extraction, finite-difference
+velocities) runs as CUDA kernels (csrc/motion.cu) and the result is ONE packed table
+``[S_total, 72]`` instead of seven tensors.
+
+Reference quirk Q2 is reproduced by default: the start row of clip ``m`` is the cumulative sum of the
+30 fps *frame* counts (motion_lib.py:280-282) although the table is sampled at 100 Hz, so for every
+clip but the first the lookup lands in an earlier clip's rows.  ``fix_start_idx=True`` uses the true row
+offsets instead (opt-in; changes results versus the reference).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import torch
+import yaml
+
+from . import _lib, motion_io
+
+ROW_STRIDE_ALIGN = 4
+
+
+def arange_count(length_f32, dt):
+    """Number of elements of torch.arange(0, tensor(length, float32), dt): ceil((end-start)/step) in double."""
+    return int(np.ceil(float(np.float32(length_f32)) / dt))
+
+
+class MotionLib:
+    def __init__(self, motion_file, motion_order, kin_char_model, dt, device, fix_start_idx=False):
+        self._device = torch.device(device)
+        self._kin_char_model = kin_char_model
+        self._dt = dt
+        self._dt_inv = round(1 / dt)
+        self._fix_start_idx = fix_start_idx
+        self._load_motions(motion_file, list(motion_order))
+
+    # ---- loading ----------------------------------------------------------------------------------------
+    def _fetch_motion_files(self, motion_file):
+        if os.path.splitext(motion_file)[1] == ".yaml":
+            with open(motion_file, "r") as f:
+                cfg = yaml.load(f, Loader=yaml.SafeLoader)
+            files, weights = [], []
+            base = os.path.dirname(os.path.abspath(motion_file))
+            for entry in cfg["motions"]:
+                w = entry["weight"]
+                assert w >= 0
+                path = entry["file"]
+                if not os.path.isabs(path) and not os.path.exists(path):
+                    path = os.path.join(base, path)
+                files.append(path)
+                weights.append(w)
+            return files, weights
+        return [motion_file], [1.0]
+
+    def _load_motions(self, motion_file, motion_order):
+        L = _lib.lib()
+        kin = self._kin_char_model
+        D = kin.get_dof_size()
+        self._num_dofs = D
+        half = (7 + D + 3) & ~3
+        self._row_stride = 2 * half
+        files, weights = self._fetch_motion_files(motion_file)
+        clips = [motion_io.load_motion(f) for f in files]
+        fps = [c.fps for c in clips]
+        nframes = [c.frames.shape[0] for c in clips]
+        lengths = [1.0 / c.fps * (c.frames.shape[0] - 1) for c in clips]
+        dev = self._device
+        self._motion_files = files
+        self._motion_weights = torch.tensor(weights, dtype=torch.float32)
+        self._motion_weights /= self._motion_weights.sum()
+        self._motion_weights = self._motion_weights.to(dev)
+        self._motion_fps = torch.tensor(fps, dtype=torch.float32, device=dev)
+        self._motion_num_frames = torch.tensor(nframes, dtype=torch.long, device=dev)
+        lengths_f32 = torch.tensor(lengths, dtype=torch.float32)
+        self._motion_lengths_host = lengths_f32.clone()
+        self._motion_lengths = lengths_f32.to(dev)
+        self._motion_loop_modes = torch.tensor([c.loop_mode.value for c in clips], dtype=torch.int, device=dev)
+        n_steps = [arange_count(l, self._dt) for l in lengths_f32.tolist()]
+        self._motion_num_steps = n_steps
+        true_start = np.concatenate([[0], np.cumsum(n_steps)[:-1]]).astype(np.int64)
+        quirk_start = np.concatenate([[0], np.cumsum(nframes)[:-1]]).astype(np.int64)
+        self._true_start_idx = torch.tensor(true_start, dtype=torch.long, device=dev)
+        self._motion_start_idx = self._true_start_idx if self._fix_start_idx else torch.tensor(
+            quirk_start, dtype=torch.long, device=dev)
+        s_total = int(np.sum(n_steps))
+        self._s_total = s_total
+        self._table = torch.zeros(s_total, self._row_stride, dtype=torch.float32, device=dev)
+        # kinematic constants for the kernels
+        self._dof_axis = torch.tensor(kin.dof_axes(), dtype=torch.float32, device=dev).contiguous()
+        self._col_of_dof = torch.tensor(kin.motion_column_of_dof(motion_order), dtype=torch.int32, device=dev)
+        self._frame_idx = torch.zeros(s_total, 2, dtype=torch.long, device=dev)
+        for m, clip in enumerate(clips):
+            frames = torch.tensor(clip.frames, dtype=torch.float32).to(dev).contiguous()   # fp64 -> fp32 rounding
+            F = frames.shape[0]
+            assert frames.shape[1] == 7 + D
+            jrot = torch.empty(F, D, 4, dtype=torch.float32, device=dev)
+            fvel = torch.empty(F, 6 + D, dtype=torch.float32, device=dev)
+            rc = L.addk_motion_table_build(
+                _lib.stream(), _lib.ptr(frames), C.c_int(F), C.c_int(D), _lib.ptr(self._col_of_dof),
+                _lib.ptr(self._dof_axis), C.c_float(float(clip.fps)), C.c_float(float(np.float32(1.0 / clip.fps))),
+                C.c_int(n_steps[m]), C.c_double(self._dt), C.c_float(float(lengths_f32[m])),
+                C.c_int(1 if clip.loop_mode == motion_io.LoopMode.WRAP else 0), _lib.ptr(jrot), _lib.ptr(fvel),
+                _lib.ptr(self._table), C.c_int(self._row_stride), C.c_longlong(int(true_start[m])), C.c_void_p(0),
+                _lib.ptr(self._frame_idx))
+            _lib.check(rc, "addk_motion_table_build")
+        torch.cuda.synchronize(dev)
+        self._c_lib = _lib.AddkMotionLib(
+            table=self._table.data_ptr(), row_stride=self._row_stride, num_motions=len(clips), s_total=s_total,
+            start_idx=self._motion_start_idx.data_ptr(), lengths=self._motion_lengths.data_ptr(),
+            loop_modes=self._motion_loop_modes.data_ptr())
+
+    # ---- queries (reference names) ----------------------------------------------------------------------
+    def get_num_motions(self):
+        return self._motion_lengths.shape[0]
+
+    def get_total_length(self):
+        return torch.sum(self._motion_lengths).item()
+
+    def get_motion_length(self, motion_ids):
+        return self._motion_lengths[motion_ids]
+
+    def get_motion_lengths(self):
+        return self._motion_lengths
+
+    def get_motion_weights(self):
+        return self._motion_weights
+
+    def get_motion_loop_mode(self, motion_ids):
+        return self._motion_loop_modes[motion_ids]
+
+    def sample_motions(self, n):
+        return torch.multinomial(self._motion_weights, num_samples=n, replacement=True)
+
+    def calc_motion_phase(self, motion_ids, times):
+        length = self._motion_lengths[motion_ids]
+        phase = times / length
+        wrap = self._motion_loop_modes[motion_ids] == motion_io.LoopMode.WRAP.value
+        phase = torch.where(wrap, phase - torch.floor(phase), phase)
+        return torch.clip(phase, 0.0, 1.0)
+
+    def get_precomputed_motion_step(self, motion_ids, motion_times, return_index=False):
+        """(root_pos, root_rot, root_vel, root_ang_vel, dof_pos, dof_vel) rows of the step table."""
+        n = motion_ids.shape[0]
+        dev, D = self._device, self._num_dofs
+        ids = motion_ids.to(torch.long).contiguous()
+        times = motion_times.to(torch.float32).contiguous()
+        out = [torch.empty(n, w, dtype=torch.float32, device=dev) for w in (3, 4, 3, 3, D, D)]
+        idx = torch.empty(n, dtype=torch.long, device=dev) if return_index else None
+        rc = _lib.lib().addk_motion_gather(
+            _lib.stream(), _lib.ptr(self._table), C.c_int(self._row_stride), C.c_int(D), C.c_longlong(self._s_total),
+            _lib.ptr(self._motion_start_idx), C.c_float(float(self._dt_inv)), _lib.ptr(ids), _lib.ptr(times), C.c_int(n),
+            *[_lib.ptr(o) for o in out], _lib.ptr(idx))
+        _lib.check(rc, "addk_motion_gather")
+        return tuple(out) + ((idx,) if return_index else ())
+
+    # ---- views of the packed table under the reference attribute names -----------------------------------
+    @property
+    def step_table(self):
+        return self._table
+
+    @property
+    def _step_root_pos(self):
+        return self._table[:, 0:3]
+
+    @property
+    def _step_root_rot(self):
+        return self._table[:, 3:7]
+
+    @property
+    def _step_dof_pos(self):
+        return self._table[:, 7:7 + self._num_dofs]
+
+    @property
+    def _step_root_vel(self):
+        h = self._row_stride // 2
+        return self._table[:, h:h + 3]
+
+    @property
+    def _step_root_ang_vel(self):
+        h = self._row_stride // 2
+        return self._table[:, h + 3:h + 6]
+
+    @property
+    def _step_dof_vel(self):
+        h = self._row_stride // 2
+        return self._table[:, h + 6:h + 6 + self._num_dofs]

@@ -133,7 +133,7 @@ int addk_env_step(void* stream, const addk_task* task_host, const addk_motion_li
  * the envs that were reset. `hist_head` is CircularBuffer._head. */
 int addk_reset_done(void* stream, const addk_task* task_host, const addk_motion_lib* lib_host,
                     const addk_env_buffers* env_host, const long long* new_ids, const float* new_times,
-                    int num_envs, int hist_head, int reset_all, float* qpos_out, float* qvel_out,
+                    int num_envs, int hist_head, int reset_all, int zero_time_done, float* qpos_out, float* qvel_out,
                     uint8_t* reset_mask_out);
 /* ADDMotion.sample_time for every env (add_motion.py:53-61; motion_lib.py:35-39; sampler.py:57-92)
  * from three uniforms per env.  Candidates are only consumed where done != 0. */
@@ -141,7 +141,13 @@ int addk_sample_motion_time(void* stream, const float* motion_weights, int num_m
                             int num_segments, const float* seg_sizes, float dt, float min_start_time,
                             float temperature, int rand_reset, const int32_t* done, const float* uniforms,
                             int num_envs, unsigned int* temp_bits_work, long long* ids_out, float* times_out);
-/* AdaptiveSegmentSampler.update_errors (sampler.py:20-55). sums/counts are [C*S] work buffers. */
+/* AdaptiveSegmentSampler.sample_start_frame for given clip ids and an explicit temperature (sampler.py:75-92);
+ * uniforms [n,3], columns 1 and 2 are consumed. */
+int addk_sample_start_time(void* stream, const float* errors, int num_segments, const float* seg_sizes, float dt,
+                           float min_start_time, float temperature, const float* uniforms, int n,
+                           const long long* clip_ids, float* times_out);
+/* AdaptiveSegmentSampler.update_errors (sampler.py:20-55). sums/counts are [C*S] work buffers.
+ * disc_obs_demo == NULL: disc_obs is a ready [n] vector of tracking errors. */
 int addk_sampler_update_errors(void* stream, const long long* clip_ids, const float* timesteps,
                                const float* disc_obs, const float* disc_obs_demo, int disc_dim, int n,
                                const float* seg_sizes, int num_motions, int num_segments, double* sums_work,

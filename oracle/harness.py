@@ -1,0 +1,67 @@
+"""Builders shared by the tests and bench.py's CPU-baseline leg.  TEST / BASELINE INFRASTRUCTURE.
+
+`make_oracle_agent` assembles the CPU oracle (oracle/add_oracle.py) over a CPU SyntheticEngine using only
+files that ship in this repository, so it also runs on the GPU box (where /root/reference is absent).
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import yaml
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+from add_gym_b200 import config as b200_config  # noqa: E402
+from add_gym_b200 import kinematics, motion_io  # noqa: E402
+from add_gym_b200.env import ImitationEnvironment  # noqa: E402
+from oracle import add_oracle  # noqa: E402
+
+
+def load_clips(motion_file):
+    if motion_file.endswith(".yaml"):
+        with open(motion_file, "r") as f:
+            cfg = yaml.safe_load(f)
+        base = os.path.dirname(os.path.abspath(motion_file))
+        files, weights = [], []
+        for e in cfg["motions"]:
+            p = e["file"]
+            if not os.path.isabs(p) and not os.path.exists(p):
+                p = os.path.join(base, p)
+            files.append(p)
+            weights.append(e["weight"])
+    else:
+        files, weights = [motion_file], [1.0]
+    clips = []
+    for f in files:
+        m = motion_io.load_motion(f)
+        clips.append((m.frames, m.fps, m.loop_mode.value))
+    return clips, weights
+
+
+def make_oracle_lib(cfg, fix_start_idx=False):
+    kin = kinematics.KinCharModel()
+    kin.load_char_file(cfg["robot"]["urdf_path"])
+    clips, weights = load_clips(cfg["task"]["motion_file"])
+    return add_oracle.OracleMotionLib(clips, weights, kin.dof_axes(),
+                                      kin.motion_column_of_dof(list(cfg["task"]["motion_joint_order"])),
+                                      cfg["engine"]["ctrl_dt"], fix_start_idx=fix_start_idx)
+
+
+def make_cpu_env(cfg, engine_seed=1234, fall_prob=0.002):
+    c = {**cfg, "engine": {**cfg["engine"], "seed": engine_seed, "noise_device": "cpu", "fall_prob": fall_prob,
+                           "_target_": "add_gym_b200.engine.SyntheticEngine"}}
+    return ImitationEnvironment(c, "cpu")
+
+
+def make_oracle_agent(num_envs, seed=0, engine_seed=1234, cfg=None, rng=None, mimic_reference_rng=True,
+                      fall_prob=0.002, lib=None):
+    cfg = cfg or b200_config.default_config(num_envs=num_envs)
+    cfg["engine"]["num_envs"] = num_envs
+    env = make_cpu_env(cfg, engine_seed, fall_prob)
+    lib = lib or make_oracle_lib(cfg, cfg["task"].get("fix_start_idx", False))
+    torch.manual_seed(seed)
+    agent = add_oracle.OracleAgent(cfg, env, lib, rng=rng, mimic_reference_rng=mimic_reference_rng)
+    return agent

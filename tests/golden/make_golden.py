@@ -1,0 +1,81 @@
+"""Generate tests/golden/*.npz by EXECUTING the unmodified reference (needs /root/reference).
+
+    python tests/golden/make_golden.py
+
+For each case the real `ADDAgent` (reference add_gym/learning/add/add_agent.py) is constructed on CPU over
+a SyntheticEngine with `torch.manual_seed(0)`, all envs are reset, `_init_train()`'s buffer clear is applied
+and one `_train_iter()` (32-step rollout + build_train_data + 40 optimizer steps + normalizer update) runs.
+Stored: a strided sample of the motion step table, the initial observation, every experience buffer, the
+per-iteration diagnostics, post-update parameter digests, normalizer and sampler state.  These are the
+pins for oracle/add_oracle.py (tests/test_oracle_golden.py) and, through it, for the CUDA path.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, REPO)
+from oracle import ref_harness  # noqa: E402
+
+CASES = {
+    "walk_n12": dict(num_envs=12, motion_file=None, fall_prob=0.01),
+    "three_clips_n10": dict(num_envs=10, fall_prob=0.01,
+                            motion_file=[("walk1_subject1_trimmed.motion", 1.0, None),
+                                         ("run2_subject4_trimmed.motion", 0.5, 700),
+                                         ("fallAndGetUp3_subject1.motion", 0.25, 450)]),
+}
+BUF_KEYS = ["obs", "next_obs", "action", "reward", "done", "a_logp", "tar_val", "adv", "rand_action_mask", "disc_obs",
+            "disc_obs_demo", "motion_ids", "motion_times"]
+
+
+def run_case(name, num_envs, motion_file, fall_prob):
+    agent, cfg = ref_harness.make_reference_agent(num_envs, seed=0, engine_seed=1234, motion_file=motion_file,
+                                                  fall_prob=fall_prob)
+    out = {}
+    ml = agent._add_motion.motion_lib
+    S = ml._step_root_pos.shape[0]
+    rows = np.arange(0, S, 97)
+    tab = torch.cat([ml._step_root_pos, ml._step_root_rot, ml._step_dof_pos, ml._step_root_vel, ml._step_root_ang_vel,
+                     ml._step_dof_vel], dim=-1)
+    out["table_rows"] = rows
+    out["table_sample"] = tab[rows].numpy()
+    out["table_shape"] = np.array(tab.shape)
+    out["table_colsum"] = tab.double().sum(0).numpy()
+    out["start_idx"] = ml._motion_start_idx.numpy()
+    out["lengths"] = ml._motion_lengths.numpy()
+    names = [k for k, p in agent._model.named_parameters() if p.requires_grad]
+    for k, p in agent._model.named_parameters():
+        if p.requires_grad:
+            out["p0/" + k] = p.detach().flatten()[:64].numpy().copy()
+            out["p0sum/" + k] = np.array(p.detach().double().sum().item())
+    agent._curr_obs, agent._curr_info = agent._reset_envs()
+    agent._init_train_done = True
+    agent._exp_buffer.clear()
+    agent._train_return_tracker.reset()
+    out["obs0"] = agent._curr_obs.numpy().copy()
+    out["ids0"] = agent._add_obs._motion_ids.numpy().copy()
+    out["off0"] = agent._add_obs._motion_time_offsets.numpy().copy()
+    info = agent._train_iter()
+    for k in BUF_KEYS:
+        out["buf/" + k] = agent._exp_buffer.get_data(k).numpy().copy()
+    for k, v in info.items():
+        out["info/" + k] = np.array(float(v))
+    for k, p in agent._model.named_parameters():
+        if p.requires_grad:
+            out["p1/" + k] = p.detach().flatten()[:64].numpy().copy()
+            out["p1sum/" + k] = np.array(p.detach().double().sum().item())
+    out["obs_mean"] = agent._obs_norm._mean.numpy().copy()
+    out["obs_std"] = agent._obs_norm._std.numpy().copy()
+    out["diff_mean_abs"] = agent._disc_obs_norm._mean_abs.numpy().copy()
+    out["sampler_errors"] = agent._add_motion.sampler.errors.numpy().copy()
+    out["param_names"] = np.array(names)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(name, "written;", {k: float(v) for k, v in info.items() if k in ("loss", "mean_return", "num_eps")})
+
+
+if __name__ == "__main__":
+    for name, kw in CASES.items():
+        run_case(name, **kw)
