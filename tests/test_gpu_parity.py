@@ -1,0 +1,314 @@
+"""GPU parity: the CUDA path (through the C-ABI, via the drop-in classes) against the CPU oracle and against
+the golden vectors produced by the executed reference.
+
+Bars (BASELINE.json north_star): bit-exact motion-frame indices, done / reset masks, motion ids and minibatch
+permutations; norm-wise relative error <= 1e-5 (fp32 MLPs) on observations, rewards, advantages, the loss and
+the gradients.  Tolerances are spelled out at each assert.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from add_gym_b200 import config as b200_config
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+FP32_TOL = 1e-5
+THREE_CLIPS = os.path.join(b200_config.ASSET_DIR, "three_clips.yaml")
+FLOAT_KEYS = ["obs", "next_obs", "action", "reward", "a_logp", "disc_obs", "disc_obs_demo", "motion_times"]
+EXACT_KEYS = ["done", "rand_action_mask", "motion_ids"]
+
+
+def _pair(num_envs, motion=None, fall_prob=0.01, precision="fp32", task_overrides=None):
+    """(oracle agent with recorded randomness, CUDA agent replaying it) over the same synthetic physics stream."""
+    from add_gym_b200.add_agent import ADDAgent
+    from oracle import harness
+    from tests import helpers
+    torch.set_num_threads(max(1, min(8, os.cpu_count() or 1)))
+    cfg = b200_config.default_config(num_envs=num_envs, motion_file=motion, mlp_precision=precision)
+    cfg["task"].update(task_overrides or {})
+    rec = helpers.RecordRandom()
+    oracle = harness.make_oracle_agent(num_envs, seed=0, engine_seed=1234, cfg=cfg, rng=rec, fall_prob=fall_prob)
+    gcfg = b200_config.default_config(num_envs=num_envs, motion_file=motion, mlp_precision=precision)
+    gcfg["task"].update(task_overrides or {})
+    gcfg["engine"].update(seed=1234, noise_device="cpu", fall_prob=fall_prob)
+    torch.manual_seed(0)
+    agent = ADDAgent(gcfg, device="cuda:0")
+    helpers.load_oracle_weights(agent, oracle)
+    replay = helpers.ReplayRandom(rec, oracle.trace, "cuda:0", first_reset=0, first_noise=0, first_perm=2)
+    helpers.install_replay(agent, replay)
+    return oracle, agent, rec
+
+
+def _start(oracle, agent):
+    oracle.start()
+    agent._curr_obs, agent._curr_info = agent._reset_envs()
+    agent._exp_buffer.clear()
+    agent._reset_tracker()
+
+
+def _check_buffers(agent, ref, keys_float=FLOAT_KEYS, keys_exact=EXACT_KEYS):
+    from tests.helpers import rel_err
+    for k in keys_exact:
+        got = agent._exp_buffer.get_data(k).cpu()
+        assert torch.equal(got.to(ref[k].dtype), ref[k]), "%s must be bit-exact" % k
+    for k in keys_float:
+        e = rel_err(agent._exp_buffer.get_data(k), ref[k])
+        assert e <= FP32_TOL, "%s: rel err %.3e > %.0e" % (k, e, FP32_TOL)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# motion table + gather
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("motion", [None, THREE_CLIPS])
+def test_motion_table_matches_oracle_and_golden(motion):
+    from add_gym_b200.env import ImitationEnvironment
+    from add_gym_b200.add_motion import ADDMotion
+    from oracle import harness
+    from tests.helpers import rel_err
+    cfg = b200_config.default_config(num_envs=4, motion_file=motion)
+    env = ImitationEnvironment(cfg, "cuda:0")
+    lib = ADDMotion(cfg["task"], env, "cuda:0").motion_lib
+    olib = harness.make_oracle_lib(cfg)
+    D, h = lib._num_dofs, lib._row_stride // 2
+    tab = lib.step_table.cpu()
+    got = torch.cat([tab[:, :7 + D], tab[:, h:h + 6 + D]], dim=1)
+    assert got.shape == olib.table.shape
+    # source-frame indices of every 100 Hz step: bit-exact (phase * (F-1) truncation, fp32 op order)
+    assert torch.equal(lib._frame_idx.cpu(), olib.frame_idx)
+    assert torch.equal(lib._motion_start_idx.cpu(), olib.start_idx)            # quirk Q2 (30 fps cumsum)
+    assert torch.equal(lib._motion_lengths.cpu(), olib.lengths)
+    # values: slerp / twist-angle use device sinf/acosf/atan2f instead of the host libm -> 1e-5 norm-wise, and no
+    # single entry off by more than 2e-5 absolute (angles in rad, positions in m)
+    assert rel_err(got, olib.table) <= FP32_TOL
+    assert float((got - olib.table).abs().max()) <= 2e-5
+    case = "walk_n12" if motion is None else "three_clips_n10"
+    g = np.load(os.path.join(GOLD, case + ".npz"))
+    assert list(g["table_shape"]) == list(got.shape)
+    assert rel_err(got[torch.from_numpy(g["table_rows"])], torch.from_numpy(g["table_sample"])) <= FP32_TOL
+    np.testing.assert_allclose(got.double().sum(0).numpy(), g["table_colsum"], rtol=1e-4, atol=1e-2)
+
+
+def test_motion_gather_indices_bit_exact():
+    """get_precomputed_motion_step: trunc(t*100) with fp32 rounding, global clip, Q2 start offsets; edge times."""
+    from add_gym_b200.env import ImitationEnvironment
+    from add_gym_b200.add_motion import ADDMotion
+    from oracle import harness
+    cfg = b200_config.default_config(num_envs=4, motion_file=THREE_CLIPS)
+    env = ImitationEnvironment(cfg, "cuda:0")
+    motion = ADDMotion(cfg["task"], env, "cuda:0")
+    lib = motion.motion_lib
+    olib = harness.make_oracle_lib(cfg)
+    g = torch.Generator().manual_seed(5)
+    n = 20000
+    ids = torch.randint(0, 3, (n,), generator=g)
+    times = torch.rand(n, generator=g) * 130.0
+    # iterated fp32 accumulation, like env.time_buf (quirk Q3)
+    acc = torch.zeros(2000)
+    cur = torch.zeros(1)
+    for i in range(2000):
+        cur = cur + 0.01
+        acc[i] = cur[0]
+    times[:2000] = acc
+    ids[:2000] = 0
+    times[2000:2010] = torch.tensor([0.0, -1.0, 1e9, 0.00999, 0.01, 0.019999, 124.16, 124.17, 200.0, 1e-30])
+    ids[2000:2010] = 0
+    out = lib.get_precomputed_motion_step(ids.cuda(), times.cuda(), return_index=True)
+    oidx = olib.rows(ids, times)
+    assert torch.equal(out[6].cpu(), oidx)
+    D, h = lib._num_dofs, lib._row_stride // 2
+    tab = lib.step_table.cpu()
+    safe = oidx.clamp(0, tab.shape[0] - 1)
+    for k, (a, b) in enumerate(zip(out[:6], [tab[safe, 0:3], tab[safe, 3:7], tab[safe, h:h + 3], tab[safe, h + 3:h + 6],
+                                             tab[safe, 7:7 + D], tab[safe, h + 6:h + 6 + D]])):
+        assert torch.equal(a.cpu(), b), "gather output %d is a pure copy of the table row" % k
+    # empty request
+    e = lib.get_precomputed_motion_step(torch.zeros(0, dtype=torch.long, device="cuda"), torch.zeros(0, device="cuda"))
+    assert e[0].shape == (0, 3)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# one full iteration: rollout -> train data -> 40 optimizer steps -> normalizers
+# ---------------------------------------------------------------------------------------------------------
+def _iteration_parity(num_envs, motion, gold_case=None, task_overrides=None, steps_synced=None):
+    from tests.helpers import rel_err
+    from add_gym_b200 import _lib
+    oracle, agent, rec = _pair(num_envs, motion, task_overrides=task_overrides)
+    _start(oracle, agent)
+    assert rel_err(agent._curr_obs, oracle.curr_obs) <= FP32_TOL
+    assert torch.equal(agent._add_obs._motion_ids.cpu(), oracle.motion_ids)
+    assert torch.equal(agent._add_obs._motion_time_offsets.cpu(), oracle.offsets)
+    # ---- rollout
+    oracle.rollout()
+    agent._rollout_train(agent._steps_per_iter)
+    _check_buffers(agent, oracle.buf)
+    assert torch.equal(agent._env.time_buf.cpu(), oracle.time_buf), "time_buf is an iterated fp32 sum: bit-exact"
+    assert int(agent._core.tracker_count.item()) == oracle.episodes
+    if oracle.episodes:
+        assert abs(agent._core.tracker_sums[0].item() - oracle.ep_sum) <= 1e-4 * max(1.0, abs(oracle.ep_sum))
+        assert agent._core.tracker_sums[1].item() == oracle.len_sum
+    if gold_case is not None:
+        g = np.load(os.path.join(GOLD, gold_case + ".npz"))
+        gold = {k: torch.from_numpy(g["buf/" + k]) for k in FLOAT_KEYS + EXACT_KEYS}
+        _check_buffers(agent, gold)
+    # ---- train data
+    od = oracle.build_train_data()
+    info = agent._build_train_data()
+    assert rel_err(agent._logits, od["logits"]) <= FP32_TOL
+    keep = (oracle.buf["done"] != 1) & (oracle.buf["done"] != 2)       # SUCC / FAIL rows are overwritten by 0 later
+    nv = agent._next_vals.view(oracle.T, -1).cpu()
+    assert rel_err(nv[keep], od["next_vals"][keep]) <= FP32_TOL
+    assert rel_err(agent._vals.view(oracle.T, -1), od["vals"]) <= FP32_TOL
+    _check_buffers(agent, oracle.buf, keys_float=["reward", "tar_val", "adv"], keys_exact=[])
+    for k in ("adv_mean", "adv_std", "disc_reward_mean", "disc_reward_std"):
+        assert abs(float(info[k]) - float(od[k])) <= FP32_TOL * max(1.0, abs(float(od[k]))), k
+    assert rel_err(agent._add_motion.sampler.errors, oracle.errors) <= FP32_TOL
+    # ---- optimizer steps, parameter-synchronised: same weights in, compare loss / gradient / weights out
+    L = _lib.lib()
+    names = oracle.names
+    gparams = dict(agent._model.named_parameters())
+    snap = {}
+
+    def grad_hook(grads):
+        snap["pre"] = {k: oracle.params[k].detach().clone() for k in names}
+
+    worst = {"loss": 0.0, "grad": 0.0, "param": 0.0}
+    INFO = ["loss", "critic_loss", "actor_loss", "clip_frac", "imp_ratio", "action_bound_loss", "disc_loss",
+            "disc_grad_penalty", "disc_logit_loss", "disc_pos_acc", "disc_neg_acc", "disc_pos_logit", "disc_neg_logit"]
+
+    def on_step(step, idx, oinfo, o):
+        for k in names:
+            gparams[k].data.copy_(snap["pre"][k])
+        opt = agent._optimizer
+        gidx = idx.cuda().contiguous()
+        _lib.check(L.addk_update_minibatch(_lib.stream(), agent._ctx.buf, _lib.ptr(gidx), C.c_int(step),
+                                           C.c_int(opt.steps + 1)), "addk_update_minibatch")
+        opt.steps += 1
+        row = agent._ws["info"][step].cpu()
+        for i, k in enumerate(INFO):
+            ref = float(oinfo[k])
+            tol = FP32_TOL * max(1.0, abs(ref))
+            assert abs(float(row[i]) - ref) <= tol, "step %d %s: %.8g vs %.8g" % (step, k, float(row[i]), ref)
+        worst["loss"] = max(worst["loss"], abs(float(row[0]) - float(oinfo["loss"])) / max(1.0, abs(float(oinfo["loss"]))))
+        for k in names:
+            e = rel_err(gparams[k].grad, o.params[k].grad)
+            worst["grad"] = max(worst["grad"], e)
+            assert e <= FP32_TOL, "step %d grad %s: rel err %.3e" % (step, k, e)
+            # AdamW normalises the gradient (update ~ lr * sign(g) in the first steps), so an entry whose gradient is
+            # rounding noise may move by up to 2*lr in either direction: bound the norm-wise error, not each entry.
+            pe = rel_err(gparams[k], o.params[k])
+            worst["param"] = max(worst["param"], pe)
+            assert pe <= FP32_TOL, "step %d param %s: rel err %.3e" % (step, k, pe)
+
+    oinfo = oracle.update_model(on_step=on_step, grad_hook=grad_hook, max_steps=steps_synced)
+    print("worst rel errors over the update:", worst)
+    # ---- normalizers
+    if steps_synced is None:
+        oracle.update_normalizers()
+        agent._update_normalizers()
+        assert rel_err(agent._obs_norm._mean, oracle.obs_mean) <= FP32_TOL
+        assert rel_err(agent._obs_norm._std, oracle.obs_std) <= FP32_TOL
+        assert rel_err(agent._disc_obs_norm._mean_abs, oracle.diff_mean_abs) <= FP32_TOL
+        assert int(agent._obs_norm._count.item()) == oracle.obs_count
+    return oracle, agent, oinfo
+
+
+def test_iteration_parity_walk_n12_and_golden():
+    """The golden case of the executed reference (tests/golden/walk_n12.npz), full 40 optimizer steps."""
+    _iteration_parity(12, None, gold_case="walk_n12")
+
+
+def test_iteration_parity_three_clips_golden():
+    """Multi-clip library with the Q2 start-index quirk, WRAP and CLAMP clips, SUCC terminations."""
+    _iteration_parity(10, THREE_CLIPS, gold_case="three_clips_n10", steps_synced=8)
+
+
+def test_iteration_parity_config0_n64():
+    """BASELINE configs[0] shape: 64 envs, one rollout + one ADD/PPO update."""
+    _iteration_parity(64, None, steps_synced=16)
+
+
+def test_iteration_parity_local_obs_with_velocity_and_phase():
+    """Non-default observation switches the reference keeps (local frame, velocity obs, phase encoding)."""
+    _iteration_parity(9, THREE_CLIPS, steps_synced=2,
+                      task_overrides={"global_obs": False, "enable_vel_obs": True, "enable_phase_obs": True})
+
+
+def test_free_running_iteration_matches_oracle():
+    """No parameter re-synchronisation: the CUDA agent runs the reference's whole `_train_iter` on its own and the
+    per-iteration diagnostics must agree.  Tolerance 1e-4 relative: 40 AdamW steps amplify rounding-level gradient
+    differences by lr*sign(g) per step (see the synchronised test for the 1e-5 per-step bar)."""
+    oracle, agent, rec = _pair(16, None)
+    _start(oracle, agent)
+    oi = oracle.train_iter()
+    gi = agent._train_iter()
+    _check_buffers(agent, oracle.buf)
+    for k in ("loss", "critic_loss", "actor_loss", "disc_loss", "disc_grad_penalty", "imp_ratio", "adv_mean", "adv_std",
+              "disc_reward_mean", "disc_reward_std"):
+        assert abs(float(gi[k]) - float(oi[k])) <= 1e-4 * max(1.0, abs(float(oi[k]))), (k, float(gi[k]), float(oi[k]))
+    # minibatch permutations were replayed from the oracle's randperm draws: same consumption count
+    assert agent.rng.i_perm == len(rec.perms)
+    # second iteration keeps tracking (normalizers updated, sampler errors updated, permutation wrap)
+    oi = oracle.train_iter()
+    gi = agent._train_iter()
+    _check_buffers(agent, oracle.buf, keys_float=["obs", "next_obs", "disc_obs", "disc_obs_demo", "motion_times"])
+    assert abs(float(gi["loss"]) - float(oi["loss"])) <= 1e-3 * max(1.0, abs(float(oi["loss"])))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# plugin-by-plugin API (how the unmodified reference agent would drive the drop-in classes)
+# ---------------------------------------------------------------------------------------------------------
+def test_plugin_api_step_by_step():
+    from tests.helpers import rel_err
+    oracle, agent, rec = _pair(8, None)
+    _start(oracle, agent)
+    obs_p, rew_p, done_p = agent._add_obs, agent._add_reward, agent._add_done
+    for _ in range(5):
+        a = torch.zeros(8, 29)
+        o_obs, o_r, o_done = oracle.step_env(a)
+        agent._env.step(a.cuda())                       # apply_action + scene.step + time_buf += dt (env.py:150-155)
+        obs_p.update_motion()
+        obs = obs_p.compute_obs()
+        r = rew_p.compute_reward()
+        d = done_p.compute_done()
+        assert rel_err(obs, o_obs) <= FP32_TOL
+        assert rel_err(r, o_r) <= FP32_TOL
+        assert torch.equal(d.cpu(), o_done)
+        assert rel_err(obs_p.info["disc_obs"], oracle.disc_obs) <= FP32_TOL
+        assert rel_err(obs_p.info["disc_obs_demo"], oracle.disc_obs_demo) <= FP32_TOL
+        assert rel_err(obs_p.ref_dof_pos, oracle.ref[4]) <= FP32_TOL
+    # model API: eval_actor / eval_critic / eval_disc against the oracle's forward
+    x = torch.randn(33, agent._model.obs_dim)
+    dx = torch.randn(17, agent._model.disc_dim)
+    with torch.no_grad():
+        assert rel_err(agent._model.eval_actor(x.cuda()).mode, oracle.actor_mean(x)) <= FP32_TOL
+        assert rel_err(agent._model.eval_critic(x.cuda()), oracle.critic(x)) <= FP32_TOL
+        assert rel_err(agent._model.eval_disc(dx.cuda()), oracle.disc(dx)) <= FP32_TOL
+
+
+def test_no_cpu_path():
+    """The product refuses host tensors instead of falling back."""
+    from add_gym_b200 import _lib
+    with pytest.raises(_lib.AddkError):
+        _lib.ptr(torch.zeros(4))
+
+
+def test_checkpoint_roundtrip_and_reference_key_names(tmp_path):
+    from add_gym_b200.add_agent import ADDAgent
+    cfg = b200_config.default_config(num_envs=4)
+    a = ADDAgent(cfg, device="cuda:0")
+    keys = set(a.state_dict().keys())
+    for k in ("_obs_norm._count", "_obs_norm._mean", "_obs_norm._std", "_a_norm._mean", "_disc_obs_norm._mean_abs",
+              "_model._actor_layers.0.weight", "_model._actor_layers.4.bias", "_model._action_dist._mean_net.weight",
+              "_model._action_dist._logstd_net", "_model._critic_out.weight", "_model._disc_layers.2.weight",
+              "_model._disc_logits.bias"):
+        assert k in keys, k
+    p = str(tmp_path / "model.pt")
+    a.save(p)
+    b = ADDAgent(cfg, device="cuda:0")
+    b.load(p)
+    assert torch.equal(a._model.flat, b._model.flat)
