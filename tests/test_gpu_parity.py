@@ -27,7 +27,7 @@ def _pair(num_envs, motion=None, fall_prob=0.01, precision="fp32", task_override
     """(oracle agent with recorded randomness, CUDA agent replaying it) over the same synthetic physics stream."""
     from add_gym_b200.add_agent import ADDAgent
     from oracle import harness
-    from tests import helpers
+    import parity_helpers as helpers
     torch.set_num_threads(max(1, min(8, os.cpu_count() or 1)))
     cfg = b200_config.default_config(num_envs=num_envs, motion_file=motion, mlp_precision=precision)
     cfg["task"].update(task_overrides or {})
@@ -52,7 +52,7 @@ def _start(oracle, agent):
 
 
 def _check_buffers(agent, ref, keys_float=FLOAT_KEYS, keys_exact=EXACT_KEYS):
-    from tests.helpers import rel_err
+    from parity_helpers import rel_err
     for k in keys_exact:
         got = agent._exp_buffer.get_data(k).cpu()
         assert torch.equal(got.to(ref[k].dtype), ref[k]), "%s must be bit-exact" % k
@@ -69,7 +69,7 @@ def test_motion_table_matches_oracle_and_golden(motion):
     from add_gym_b200.env import ImitationEnvironment
     from add_gym_b200.add_motion import ADDMotion
     from oracle import harness
-    from tests.helpers import rel_err
+    from parity_helpers import rel_err
     cfg = b200_config.default_config(num_envs=4, motion_file=motion)
     env = ImitationEnvironment(cfg, "cuda:0")
     lib = ADDMotion(cfg["task"], env, "cuda:0").motion_lib
@@ -135,7 +135,7 @@ def test_motion_gather_indices_bit_exact():
 # one full iteration: rollout -> train data -> 40 optimizer steps -> normalizers
 # ---------------------------------------------------------------------------------------------------------
 def _iteration_parity(num_envs, motion, gold_case=None, task_overrides=None, steps_synced=None):
-    from tests.helpers import rel_err
+    from parity_helpers import rel_err
     from add_gym_b200 import _lib
     oracle, agent, rec = _pair(num_envs, motion, task_overrides=task_overrides)
     _start(oracle, agent)
@@ -263,7 +263,7 @@ def test_free_running_iteration_matches_oracle():
 # plugin-by-plugin API (how the unmodified reference agent would drive the drop-in classes)
 # ---------------------------------------------------------------------------------------------------------
 def test_plugin_api_step_by_step():
-    from tests.helpers import rel_err
+    from parity_helpers import rel_err
     oracle, agent, rec = _pair(8, None)
     _start(oracle, agent)
     obs_p, rew_p, done_p = agent._add_obs, agent._add_reward, agent._add_done
