@@ -1,9 +1,393 @@
-// Tensor-core (tcgen05) dense layer modes; see gemm.cu for the shared argument struct.
+// Dense layer contraction on the 5th-generation tensor cores: TMA-fed tcgen05.mma tiles with the
+// accumulator in TMEM ("tf32" and "tf32x3" precision modes of addk_gemm; argument struct shared with gemm.cu).
+//
+//   C[M,N] = epilogue( op_a(A)[M,K] . op_b(B)[K,N] ),  fp32 operands in HBM, fp32 accumulate, fp32 out
+//
+// One CTA = one 128 x BN output tile (BN = 256 / 128 / 64), 192 threads, warp-specialised:
+//   warp 0      TMA producer: cp.async.bulk.tensor.2d of the A / B k-blocks (32 fp32 = 128 B wide,
+//               SWIZZLE_128B) into a ring of shared-memory stages, completion on mbarriers;
+//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (kind::tf32, M=128, N=BN, K=8 per
+//               instruction), tcgen05.commit releases the stage / publishes the accumulator;
+//   warps 2..5  "tf32x3" only: split each landed fp32 tile in place into hi = tf32(x) and lo = x - hi
+//               (3 MMAs per k-step: lo.hi + hi.lo + hi.hi -> fp32-class accuracy, the reference's fp32
+//               MLP parity mode); then the epilogue: tcgen05.ld the accumulator (each warp its own 32
+//               TMEM lanes), bias / ReLU / ReLU-mask / accumulate, 128-bit stores.
+// Operands may be K-major (row = M or N index, contraction contiguous: forward layers) or MN-major
+// (row = contraction index: input-gradient and weight-gradient GEMMs); both are described to the tensor
+// core through shared-memory matrix descriptors, no transposed copies are made.  Split-K (weight
+// gradients, contraction over the minibatch rows) writes one partial slab per blockIdx.z.
+//
+// Every mbarrier wait is bounded by a clock watchdog that traps instead of hanging the GPU.
 #include "common.cuh"
 #include "addk.h"
+#include <cuda.h>
+#include <cudaTypedefs.h>
 
+namespace addk { int sgemm_launch(cudaStream_t st, const addk_gemm_args& a); }
+
+namespace addk_tc {
+
+constexpr int BM = 128;        // UMMA M
+constexpr int BK = 32;         // fp32 elements per k-block = one 128-byte swizzle row
+constexpr int UMMA_K = 8;      // kind::tf32
+constexpr int NTHREADS = 192;
+
+struct Params {
+  float* C; int ldc; int M, N, K;
+  const float* bias; const float* mask; int ld_mask;
+  int relu, accumulate;
+  int kb_per_split;            // k-blocks per blockIdx.z
+  int a_mn, b_mn;              // operand is MN-major (memory rows = contraction index)
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+// bounded wait: ~2 s at 2 GHz, then trap (a launch error instead of a hung device)
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+// Shared-memory matrix descriptor (SWIZZLE_128B, descriptor version 1 = Blackwell).
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// One stage of the ring.  A: 128 rows/columns x 32 k  (16 KB);  B: BN x 32 k.  X3 adds the "lo" halves.
+template <int BN, bool X3>
+struct Cfg {
+  static constexpr int A_BYTES = BM * BK * 4;
+  static constexpr int B_BYTES = BN * BK * 4;
+  static constexpr int STAGE_BYTES = (A_BYTES + B_BYTES) * (X3 ? 2 : 1);
+  static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 6 ? 6 : (200 * 1024) / STAGE_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+  static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+};
+
+template <int BN, bool X3>
+__global__ void __launch_bounds__(NTHREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
+  using C = Cfg<BN, X3>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bars = base + C::STAGES * C::STAGE_BYTES;      // full[S] | empty[S] | ready[S] | tmem_full | tmem_ptr
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (C::STAGES + s); };
+  auto ready_bar = [&](int s) { return bars + 8u * (2 * C::STAGES + s); };
+  const uint32_t tmem_full_bar = bars + 8u * (3 * C::STAGES);
+  const uint32_t tmem_ptr_addr = bars + 8u * (3 * C::STAGES + 1);
+  auto a_hi = [&](int s) { return base + (uint32_t)s * C::STAGE_BYTES; };
+  auto b_hi = [&](int s) { return a_hi(s) + C::A_BYTES; };
+  auto a_lo = [&](int s) { return b_hi(s) + C::B_BYTES; };
+  auto b_lo = [&](int s) { return a_lo(s) + C::A_BYTES; };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int kb_total = (p.K + BK - 1) / BK;
+  const int kb_begin = blockIdx.z * p.kb_per_split;
+  const int kb_end = min(kb_total, kb_begin + p.kb_per_split);
+  const int num_kb = kb_end - kb_begin;          // host guarantees >= 1
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+      mbar_init(ready_bar(s), 128);
+    }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "r"((uint32_t)C::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr) : "memory");
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      for (int i = 0; i < num_kb; ++i) {
+        const int s = i % C::STAGES;
+        const uint32_t ph = (uint32_t)(i / C::STAGES) & 1u;
+        mbar_wait(empty_bar(s), ph ^ 1u);
+        mbar_expect_tx(full_bar(s), C::A_BYTES + C::B_BYTES);
+        const int k0 = (kb_begin + i) * BK;
+        if (!p.a_mn) {
+          tma_load_2d(a_hi(s), &tmA, full_bar(s), k0, m0);                      // box {32 k, 128 rows}
+        } else {
+#pragma unroll
+          for (int j = 0; j < BM / 32; ++j) tma_load_2d(a_hi(s) + j * 4096, &tmA, full_bar(s), m0 + 32 * j, k0);   // box {32 m, 32 k}
+        }
+        if (!p.b_mn) {
+          tma_load_2d(b_hi(s), &tmB, full_bar(s), k0, n0);                      // box {32 k, BN rows}
+        } else {
+#pragma unroll
+          for (int j = 0; j < BN / 32; ++j) tma_load_2d(b_hi(s) + j * 4096, &tmB, full_bar(s), n0 + 32 * j, k0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      // instruction descriptor: D fp32, A/B tf32, majors, N>>3, M>>4
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.a_mn ? 1 : 0) << 15) |
+                             ((uint32_t)(p.b_mn ? 1 : 0) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      // K-major: 8-row groups 1024 B apart, k-step = 32 B inside the swizzled row.
+      // MN-major: 32-wide MN atoms 4096 B apart (LBO), 8-k groups 1024 B apart (SBO), k-step = 1024 B.
+      const uint32_t a_lbo = p.a_mn ? 4096u : 16u, b_lbo = p.b_mn ? 4096u : 16u;
+      const uint32_t a_kstep = p.a_mn ? 1024u : 32u, b_kstep = p.b_mn ? 1024u : 32u;
+      uint32_t acc = 0;
+      for (int i = 0; i < num_kb; ++i) {
+        const int s = i % C::STAGES;
+        const uint32_t ph = (uint32_t)(i / C::STAGES) & 1u;
+        mbar_wait(X3 ? ready_bar(s) : full_bar(s), ph);
+        tc_fence_after();
+#pragma unroll
+        for (int ks = 0; ks < BK / UMMA_K; ++ks) {
+          const uint64_t dah = smem_desc(a_hi(s) + ks * a_kstep, a_lbo, 1024u);
+          const uint64_t dbh = smem_desc(b_hi(s) + ks * b_kstep, b_lbo, 1024u);
+          if (X3) {
+            const uint64_t dal = smem_desc(a_lo(s) + ks * a_kstep, a_lbo, 1024u);
+            const uint64_t dbl = smem_desc(b_lo(s) + ks * b_kstep, b_lbo, 1024u);
+            umma_tf32(tmem_base, dal, dbh, idesc, acc);
+            acc = 1;
+            umma_tf32(tmem_base, dah, dbl, idesc, acc);
+          }
+          umma_tf32(tmem_base, dah, dbh, idesc, acc);
+          acc = 1;
+        }
+        umma_commit(empty_bar(s));          // stage reusable once these MMAs have read it
+      }
+      umma_commit(tmem_full_bar);           // accumulator complete
+    }
+  } else {
+    // ===================== splitter (tf32x3) + epilogue: warps 2..5 =====================
+    const int t = threadIdx.x - 64;          // 0..127
+    if (X3) {
+      for (int i = 0; i < num_kb; ++i) {
+        const int s = i % C::STAGES;
+        const uint32_t ph = (uint32_t)(i / C::STAGES) & 1u;
+        mbar_wait(full_bar(s), ph);
+        // elementwise, so the swizzled placement does not matter: A and B are contiguous in the stage
+        constexpr int N4 = (C::A_BYTES + C::B_BYTES) / 16;
+        const uint32_t src = a_hi(s), dst = a_lo(s);
+#pragma unroll 4
+        for (int j = t; j < N4; j += 128) {
+          float4 x;
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(src + 16u * j) : "memory");
+          float4 h, l;
+          h.x = __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u); l.x = x.x - h.x;
+          h.y = __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u); l.y = x.y - h.y;
+          h.z = __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u); l.z = x.z - h.z;
+          h.w = __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u); l.w = x.w - h.w;
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(src + 16u * j), "f"(h.x), "f"(h.y), "f"(h.z), "f"(h.w) : "memory");
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + 16u * j), "f"(l.x), "f"(l.y), "f"(l.z), "f"(l.w) : "memory");
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
+        mbar_arrive(ready_bar(s));
+      }
+    }
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const int q = warp & 3;                  // TMEM lane quarter this warp may access
+    const int row = m0 + 32 * q + lane;
+    float* Cz = p.C + (size_t)blockIdx.z * p.M * p.ldc;
+    const bool vec = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(Cz) & 15) == 0) &&
+                     (!p.mask || (((p.ld_mask & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.mask) & 15) == 0)));
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      if (n0 + c0 >= p.N) break;             // warp-uniform
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)c0, v);
+      if (row < p.M) {
+        float* dst = Cz + (size_t)row * p.ldc + n0 + c0;
+        const float* mk = p.mask ? p.mask + (size_t)row * p.ld_mask + n0 + c0 : nullptr;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const int col = n0 + c0 + j;
+          if (col >= p.N) break;
+          float o[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float x = __uint_as_float(v[j + e]);
+            if (p.bias && col + e < p.N) x += p.bias[col + e];
+            if (p.relu) x = fmaxf(x, 0.f);
+            o[e] = x;
+          }
+          if (vec && col + 3 < p.N) {
+            if (mk) {
+              const float4 m4 = *reinterpret_cast<const float4*>(mk + j);
+              o[0] = m4.x > 0.f ? o[0] : 0.f; o[1] = m4.y > 0.f ? o[1] : 0.f;
+              o[2] = m4.z > 0.f ? o[2] : 0.f; o[3] = m4.w > 0.f ? o[3] : 0.f;
+            }
+            if (p.accumulate) {
+              const float4 c4 = *reinterpret_cast<const float4*>(dst + j);
+              o[0] += c4.x; o[1] += c4.y; o[2] += c4.z; o[3] += c4.w;
+            }
+            *reinterpret_cast<float4*>(dst + j) = make_float4(o[0], o[1], o[2], o[3]);
+          } else {
+            for (int e = 0; e < 4 && col + e < p.N; ++e) {
+              float x = o[e];
+              if (mk) x = mk[j + e] > 0.f ? x : 0.f;
+              if (p.accumulate) x += dst[j + e];
+              dst[j + e] = x;
+            }
+          }
+        }
+      }
+    }
+  }
+  // ===================== teardown =====================
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
+
+static bool resolve_encode() {
+  if (g_encode) return true;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) return false;
+  g_encode = (PFN_cuTensorMapEncodeTiled_v12000)fn;
+  return true;
+}
+
+// 2-D fp32 tensor map: memory [outer, inner] with `ld` floats between rows; box {32, box_rows}, 128-byte swizzle.
+static bool make_map(CUtensorMap* map, const float* ptr, long long inner, long long outer, long long ld, int box_rows) {
+  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+template <int BN, bool X3>
+static int launch(cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, dim3 grid) {
+  using C = Cfg<BN, X3>;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(gemm_tc_kernel<BN, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES) != cudaSuccess) {
+      addk_set_error("gemm_tc: cannot raise the dynamic shared memory limit");
+      return ADDK_ERR_LAUNCH;
+    }
+    configured = true;
+  }
+  gemm_tc_kernel<BN, X3><<<grid, NTHREADS, C::SMEM_BYTES, st>>>(ta, tb, p);
+  return ADDK_OK;
+}
+
+}  // namespace addk_tc
+
+// precision: 1 = tf32x3, 2 = tf32.  Shapes the tensor-core tiles do not cover (heads with 1 or 29 outputs,
+// contraction shorter than one k-block, misaligned leading dimensions, fused input normalisation) run on the
+// exact-fp32 CUDA-core kernel, which is at least as accurate.
 int addk_gemm_tc(cudaStream_t st, const addk_gemm_args& a, int precision) {
-  (void)st; (void)a; (void)precision;
-  addk_set_error("tensor-core GEMM mode not built");
-  return ADDK_ERR_UNSUPPORTED;
+  using namespace addk_tc;
+  if (precision != 1 && precision != 2) {
+    addk_set_error("gemm: unsupported precision mode (bf16 tensor-core tiles are not built yet)");
+    return ADDK_ERR_UNSUPPORTED;
+  }
+  const bool aligned = ((a.lda & 3) == 0) && ((a.ldb & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.A) & 15) == 0) &&
+                       ((reinterpret_cast<uintptr_t>(a.B) & 15) == 0);
+  if (!aligned || a.a_mean || a.M < 64 || a.N < 48 || a.K < 32 || !resolve_encode()) return addk::sgemm_launch(st, a);
+  int split = a.split_k > 1 ? a.split_k : 1;
+  if (split > 1 && (a.bias || a.relu || a.relu_mask_src || a.accumulate)) return ADDK_ERR_ARG;
+  const int kb_total = (a.K + BK - 1) / BK;
+  int kb_per = (kb_total + split - 1) / split;
+  // every slab must own at least one k-block: idle slabs would leave stale data behind
+  if ((long long)kb_per * (split - 1) >= kb_total) return addk::sgemm_launch(st, a);
+  Params p;
+  p.C = a.C; p.ldc = a.ldc; p.M = a.M; p.N = a.N; p.K = a.K; p.bias = a.bias; p.mask = a.relu_mask_src;
+  p.ld_mask = a.ld_mask; p.relu = a.relu; p.accumulate = a.accumulate; p.kb_per_split = kb_per;
+  p.a_mn = a.trans_a ? 1 : 0;          // A given as [K,M]: rows are the contraction index
+  p.b_mn = a.trans_b ? 0 : 1;          // B given as [K,N]
+  const int BN = a.N > 128 ? 256 : (a.N > 64 ? 128 : 64);
+  CUtensorMap ta, tb;
+  bool ok = p.a_mn ? make_map(&ta, a.A, a.M, a.K, a.lda, 32) : make_map(&ta, a.A, a.K, a.M, a.lda, BM);
+  ok = ok && (p.b_mn ? make_map(&tb, a.B, a.N, a.K, a.ldb, 32) : make_map(&tb, a.B, a.K, a.N, a.ldb, BN));
+  if (!ok) return addk::sgemm_launch(st, a);
+  dim3 grid((a.N + BN - 1) / BN, (a.M + BM - 1) / BM, split);
+  const bool x3 = precision == 1;
+  if (BN == 256) return x3 ? launch<256, true>(st, ta, tb, p, grid) : launch<256, false>(st, ta, tb, p, grid);
+  if (BN == 128) return x3 ? launch<128, true>(st, ta, tb, p, grid) : launch<128, false>(st, ta, tb, p, grid);
+  return x3 ? launch<64, true>(st, ta, tb, p, grid) : launch<64, false>(st, ta, tb, p, grid);
 }

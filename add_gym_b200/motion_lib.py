@@ -92,6 +92,8 @@ class MotionLib:
         self._dof_axis = torch.tensor(kin.dof_axes(), dtype=torch.float32, device=dev).contiguous()
         self._col_of_dof = torch.tensor(kin.motion_column_of_dof(motion_order), dtype=torch.int32, device=dev)
         self._frame_idx = torch.zeros(s_total, 2, dtype=torch.long, device=dev)
+        self._frame_joint_rot = []      # per clip [F, D, 4]: 30 fps joint rotations (reference `_frame_joint_rot`)
+        self._frame_vel = []            # per clip [F, 6 + D]: root_vel, root_ang_vel, dof_vel of the source frames
         for m, clip in enumerate(clips):
             frames = torch.tensor(clip.frames, dtype=torch.float32).to(dev).contiguous()   # fp64 -> fp32 rounding
             F = frames.shape[0]
@@ -106,6 +108,8 @@ class MotionLib:
                 _lib.ptr(self._table), C.c_int(self._row_stride), C.c_longlong(int(true_start[m])), C.c_void_p(0),
                 _lib.ptr(self._frame_idx))
             _lib.check(rc, "addk_motion_table_build")
+            self._frame_joint_rot.append(jrot)
+            self._frame_vel.append(fvel)
         torch.cuda.synchronize(dev)
         self._c_lib = _lib.AddkMotionLib(
             table=self._table.data_ptr(), row_stride=self._row_stride, num_motions=len(clips), s_total=s_total,

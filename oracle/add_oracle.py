@@ -136,8 +136,10 @@ def arange_times(n, dt):
 class OracleMotionLib:
     """Frames -> 100 Hz step table, and the truncated-index lookup (motion_lib.py:18-335)."""
 
-    def __init__(self, clips, weights, dof_axis, col_of_dof, dt, fix_start_idx=False):
-        """clips: list of (frames[F,36] float64 ndarray, fps, loop_mode); dof_axis [D,3]; col_of_dof [D]."""
+    def __init__(self, clips, weights, dof_axis, col_of_dof, dt, fix_start_idx=False, jrot_override=None):
+        """clips: list of (frames[F,36] float64 ndarray, fps, loop_mode); dof_axis [D,3]; col_of_dof [D].
+        jrot_override: optional per-clip [F,D,4] joint rotations to use instead of cos/sin of the hinge angles
+        (tests feed the device-computed ones so that the branchy resampling is compared on identical inputs)."""
         self.dt, self.dt_inv = dt, round(1 / dt)
         self.axis = torch.as_tensor(dof_axis, dtype=torch.float32)
         D = self.axis.shape[0]
@@ -157,6 +159,9 @@ class OracleMotionLib:
             F = fr.shape[0]
             ax = self.axis.unsqueeze(0).expand(F, D, 3)
             jrot = q_pos(axis_angle_q(ax, dof))                             # kin_char_model.py:595-639, :113-114
+            self.frame_joint_rot = getattr(self, "frame_joint_rot", []) + [jrot]
+            if jrot_override is not None:
+                jrot = torch.as_tensor(jrot_override[m], dtype=torch.float32).cpu()
             vel = torch.zeros_like(pos)                                     # motion_lib.py:203-205
             vel[:-1] = fps * (pos[1:] - pos[:-1]); vel[-1] = vel[-2]
             ang = torch.zeros_like(pos)                                     # motion_lib.py:207-212

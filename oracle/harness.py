@@ -41,13 +41,13 @@ def load_clips(motion_file):
     return clips, weights
 
 
-def make_oracle_lib(cfg, fix_start_idx=False):
+def make_oracle_lib(cfg, fix_start_idx=False, jrot_override=None):
     kin = kinematics.KinCharModel()
     kin.load_char_file(cfg["robot"]["urdf_path"])
     clips, weights = load_clips(cfg["task"]["motion_file"])
     return add_oracle.OracleMotionLib(clips, weights, kin.dof_axes(),
                                       kin.motion_column_of_dof(list(cfg["task"]["motion_joint_order"])),
-                                      cfg["engine"]["ctrl_dt"], fix_start_idx=fix_start_idx)
+                                      cfg["engine"]["ctrl_dt"], fix_start_idx=fix_start_idx, jrot_override=jrot_override)
 
 
 def make_cpu_env(cfg, engine_seed=1234, fall_prob=0.002):
