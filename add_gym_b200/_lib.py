@@ -69,7 +69,7 @@ class AddkGemmArgs(C.Structure):
                 ("ldc", C.c_int32), ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32), ("bias", C.c_void_p),
                 ("a_mean", C.c_void_p), ("a_std", C.c_void_p), ("relu_mask_src", C.c_void_p), ("ld_mask", C.c_int32),
                 ("trans_a", C.c_int32), ("trans_b", C.c_int32), ("relu", C.c_int32), ("split_k", C.c_int32),
-                ("accumulate", C.c_int32)]
+                ("accumulate", C.c_int32), ("slab_stride", C.c_int64)]
 
 
 class AddkError(RuntimeError):

@@ -24,6 +24,7 @@ struct GemmParams {
   int lda, ldb, ldc, M, N, K;
   const float* bias; const float* a_mean; const float* a_std; const float* mask; int ld_mask;
   int relu, accumulate, k_chunk;
+  long long slab_stride;
 };
 
 // Load one BKxBM (or BKxBN) operand tile into registers.
@@ -98,7 +99,7 @@ __global__ void __launch_bounds__(NT, 2) sgemm_kernel(const GemmParams p) {
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
   const int kb = blockIdx.z * p.k_chunk;
   const int ke = min(p.K, kb + p.k_chunk);
-  float* C = p.C + (size_t)blockIdx.z * p.M * p.ldc;
+  float* C = p.C + (size_t)blockIdx.z * p.slab_stride;
   const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
   float acc[8][8];
 #pragma unroll
@@ -206,6 +207,7 @@ int sgemm_launch(cudaStream_t st, const addk_gemm_args& a) {
   int chunk = (a.K + split - 1) / split;
   chunk = ((chunk + BK - 1) / BK) * BK;
   p.k_chunk = chunk;
+  p.slab_stride = a.slab_stride > 0 ? a.slab_stride : (long long)a.M * a.ldc;
   if (a.a_mean && a.trans_a) return ADDK_ERR_UNSUPPORTED;
   if (split > 1 && (a.bias || a.relu || a.relu_mask_src || a.accumulate)) return ADDK_ERR_ARG;
   dim3 grid((a.N + BN - 1) / BN, (a.M + BM - 1) / BM, split);

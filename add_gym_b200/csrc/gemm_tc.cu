@@ -38,6 +38,7 @@ struct Params {
   int relu, accumulate;
   int kb_per_split;            // k-blocks per blockIdx.z
   int a_mn, b_mn;              // operand is MN-major (memory rows = contraction index)
+  long long slab_stride;       // floats between split-K slabs
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -78,14 +79,15 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
 
-// Shared-memory matrix descriptor (SWIZZLE_128B, descriptor version 1 = Blackwell).
-__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// Shared-memory matrix descriptor (descriptor version 1 = Blackwell).  layout: 2 = SWIZZLE_128B (K-major tiles),
+// 1 = SWIZZLE_128B with 32-byte atoms -- the only swizzle the tensor core accepts for MN-major 32-bit operands.
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)layout << 61;
   return d;
 }
 
@@ -123,7 +125,10 @@ struct Cfg {
   static constexpr int STAGE_BYTES = (A_BYTES + B_BYTES) * (X3 ? 2 : 1);
   static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 6 ? 6 : (200 * 1024) / STAGE_BYTES;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
-  static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+  // tf32x3 keeps the small cross terms (lo.hi + hi.lo) in a second accumulator: the tensor core truncates its
+  // fp32 accumulator after every instruction, so three accumulations per k-step into ONE accumulator would
+  // triple that bias; the cross-term accumulator is 2^-11 smaller and its truncation is negligible.
+  static constexpr int TMEM_COLS = (X3 ? 2 : 1) * (BN < 32 ? 32 : BN);
 };
 
 template <int BN, bool X3>
@@ -200,11 +205,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // instruction descriptor: D fp32, A/B tf32, majors, N>>3, M>>4
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.a_mn ? 1 : 0) << 15) |
                              ((uint32_t)(p.b_mn ? 1 : 0) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-      // K-major: 8-row groups 1024 B apart, k-step = 32 B inside the swizzled row.
-      // MN-major: 32-wide MN atoms 4096 B apart (LBO), 8-k groups 1024 B apart (SBO), k-step = 1024 B.
+      // K-major  (SWIZZLE_128B): 8-row groups 1024 B apart (SBO), k-step = 32 B inside the swizzled row.
+      // MN-major (SWIZZLE_128B, 32 B atoms): one TMA box = 32 MN x 32 k = 4096 B; MN atoms 4096 B apart (LBO),
+      //          4-k groups 512 B apart (SBO), k-step (8 k) = 1024 B.
       const uint32_t a_lbo = p.a_mn ? 4096u : 16u, b_lbo = p.b_mn ? 4096u : 16u;
+      const uint32_t a_sbo = p.a_mn ? 512u : 1024u, b_sbo = p.b_mn ? 512u : 1024u;
+      const uint32_t a_lay = p.a_mn ? 1u : 2u, b_lay = p.b_mn ? 1u : 2u;
       const uint32_t a_kstep = p.a_mn ? 1024u : 32u, b_kstep = p.b_mn ? 1024u : 32u;
-      uint32_t acc = 0;
+      uint32_t acc = 0, acc_x = 0;
       for (int i = 0; i < num_kb; ++i) {
         const int s = i % C::STAGES;
         const uint32_t ph = (uint32_t)(i / C::STAGES) & 1u;
@@ -212,14 +220,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tc_fence_after();
 #pragma unroll
         for (int ks = 0; ks < BK / UMMA_K; ++ks) {
-          const uint64_t dah = smem_desc(a_hi(s) + ks * a_kstep, a_lbo, 1024u);
-          const uint64_t dbh = smem_desc(b_hi(s) + ks * b_kstep, b_lbo, 1024u);
+          const uint64_t dah = smem_desc(a_hi(s) + ks * a_kstep, a_lbo, a_sbo, a_lay);
+          const uint64_t dbh = smem_desc(b_hi(s) + ks * b_kstep, b_lbo, b_sbo, b_lay);
           if (X3) {
-            const uint64_t dal = smem_desc(a_lo(s) + ks * a_kstep, a_lbo, 1024u);
-            const uint64_t dbl = smem_desc(b_lo(s) + ks * b_kstep, b_lbo, 1024u);
-            umma_tf32(tmem_base, dal, dbh, idesc, acc);
-            acc = 1;
-            umma_tf32(tmem_base, dah, dbl, idesc, acc);
+            const uint64_t dal = smem_desc(a_lo(s) + ks * a_kstep, a_lbo, a_sbo, a_lay);
+            const uint64_t dbl = smem_desc(b_lo(s) + ks * b_kstep, b_lbo, b_sbo, b_lay);
+            umma_tf32(tmem_base + BN, dal, dbh, idesc, acc_x);
+            acc_x = 1;
+            umma_tf32(tmem_base + BN, dah, dbl, idesc, acc_x);
           }
           umma_tf32(tmem_base, dah, dbh, idesc, acc);
           acc = 1;
@@ -259,7 +267,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tc_fence_after();
     const int q = warp & 3;                  // TMEM lane quarter this warp may access
     const int row = m0 + 32 * q + lane;
-    float* Cz = p.C + (size_t)blockIdx.z * p.M * p.ldc;
+    float* Cz = p.C + (size_t)blockIdx.z * p.slab_stride;
     const bool vec = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(Cz) & 15) == 0) &&
                      (!p.mask || (((p.ld_mask & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.mask) & 15) == 0)));
 #pragma unroll 1
@@ -267,6 +275,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (n0 + c0 >= p.N) break;             // warp-uniform
       uint32_t v[32];
       tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)c0, v);
+      if (X3) {
+        uint32_t w[32];
+        tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(BN + c0), w);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w[j]));
+      }
       if (row < p.M) {
         float* dst = Cz + (size_t)row * p.ldc + n0 + c0;
         const float* mk = p.mask ? p.mask + (size_t)row * p.ld_mask + n0 + c0 : nullptr;
@@ -329,13 +343,16 @@ static bool resolve_encode() {
 }
 
 // 2-D fp32 tensor map: memory [outer, inner] with `ld` floats between rows; box {32, box_rows}, 128-byte swizzle.
-static bool make_map(CUtensorMap* map, const float* ptr, long long inner, long long outer, long long ld, int box_rows) {
+static bool make_map(CUtensorMap* map, const float* ptr, long long inner, long long outer, long long ld, int box_rows,
+                     bool mn_major) {
   cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
   cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
   cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1u, 1u};
   CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
@@ -378,12 +395,13 @@ int addk_gemm_tc(cudaStream_t st, const addk_gemm_args& a, int precision) {
   Params p;
   p.C = a.C; p.ldc = a.ldc; p.M = a.M; p.N = a.N; p.K = a.K; p.bias = a.bias; p.mask = a.relu_mask_src;
   p.ld_mask = a.ld_mask; p.relu = a.relu; p.accumulate = a.accumulate; p.kb_per_split = kb_per;
+  p.slab_stride = a.slab_stride > 0 ? a.slab_stride : (long long)a.M * a.ldc;
   p.a_mn = a.trans_a ? 1 : 0;          // A given as [K,M]: rows are the contraction index
   p.b_mn = a.trans_b ? 0 : 1;          // B given as [K,N]
   const int BN = a.N > 128 ? 256 : (a.N > 64 ? 128 : 64);
   CUtensorMap ta, tb;
-  bool ok = p.a_mn ? make_map(&ta, a.A, a.M, a.K, a.lda, 32) : make_map(&ta, a.A, a.K, a.M, a.lda, BM);
-  ok = ok && (p.b_mn ? make_map(&tb, a.B, a.N, a.K, a.ldb, 32) : make_map(&tb, a.B, a.K, a.N, a.ldb, BN));
+  bool ok = p.a_mn ? make_map(&ta, a.A, a.M, a.K, a.lda, 32, true) : make_map(&ta, a.A, a.K, a.M, a.lda, BM, false);
+  ok = ok && (p.b_mn ? make_map(&tb, a.B, a.N, a.K, a.ldb, 32, true) : make_map(&tb, a.B, a.K, a.N, a.ldb, BN, false));
   if (!ok) return addk::sgemm_launch(st, a);
   dim3 grid((a.N + BN - 1) / BN, (a.M + BM - 1) / BM, split);
   const bool x3 = precision == 1;

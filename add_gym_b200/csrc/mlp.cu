@@ -294,11 +294,12 @@ typedef addk_update_ctx Ctx;
 
 static int gemm(cudaStream_t st, int prec, const float* A, int lda, int ta, const float* B, int ldb, int tb, float* C,
                 int ldc, int M, int N, int K, const float* bias = nullptr, int relu = 0, const float* mask = nullptr,
-                int ld_mask = 0, int split = 1, const float* nmean = nullptr, const float* nstd = nullptr) {
+                int ld_mask = 0, int split = 1, const float* nmean = nullptr, const float* nstd = nullptr,
+                long long slab_stride = 0) {
   addk_gemm_args a;
   a.A = A; a.lda = lda; a.B = B; a.ldb = ldb; a.C = C; a.ldc = ldc; a.M = M; a.N = N; a.K = K;
   a.bias = bias; a.a_mean = nmean; a.a_std = nstd; a.relu_mask_src = mask; a.ld_mask = ld_mask;
-  a.trans_a = ta; a.trans_b = tb; a.relu = relu; a.split_k = split; a.accumulate = 0;
+  a.trans_a = ta; a.trans_b = tb; a.relu = relu; a.split_k = split; a.accumulate = 0; a.slab_stride = slab_stride;
   int rc = prec == 0 ? addk::sgemm_launch(st, a) : addk_gemm_tc(st, a, prec);
   if (rc != ADDK_OK) return rc;
   ADDK_CHECK_LAUNCH();
@@ -312,10 +313,10 @@ static int wgrad(cudaStream_t st, const Ctx& c, const float* dY, int ldy, const 
   const int S = (int)c.split_k;
   const long long P = c.num_params;
   TRY(gemm(st, (int)c.precision, dY, ldy, 1, X, ldx, 0, F(c.slabs) + (size_t)slab0 * P + o_w, k_in, n_out, k_in, rows,
-           nullptr, 0, nullptr, 0, S));
+           nullptr, 0, nullptr, 0, S, nullptr, nullptr, P));
   if (o_b >= 0)
     TRY(gemm(st, 0, F(c.ones), 1, 1, dY, ldy, 0, F(c.slabs) + (size_t)slab0 * P + o_b, n_out, 1, n_out, rows, nullptr, 0,
-             nullptr, 0, S));
+             nullptr, 0, S, nullptr, nullptr, P));
   return ADDK_OK;
 }
 
@@ -424,13 +425,13 @@ extern "C" int addk_update_minibatch(void* stream, void* ctx_host, const long lo
   ADDK_CHECK_LAUNCH();
   // backward of the chain (second set of slabs)
   TRY(gemm(st, pr, F(c.u1), E1, 1, F(c.dg), DL, 0, F(c.slabs) + (size_t)S * P + c.o_d_w0, DD, E1, DD, R, nullptr, 0,
-           nullptr, 0, S));
+           nullptr, 0, S, nullptr, nullptr, P));
   TRY(gemm(st, pr, F(c.dg), DL, 0, W + c.o_d_w0, DD, 1, dv1, E1, R, E1, DD, nullptr, 0, e1, E1));
   TRY(gemm(st, pr, F(c.u2), E2, 1, dv1, E1, 0, F(c.slabs) + (size_t)S * P + c.o_d_w1, E1, E2, E1, R, nullptr, 0, nullptr, 0,
-           S));
+           S, nullptr, nullptr, P));
   TRY(gemm(st, pr, dv1, E1, 0, W + c.o_d_w1, E1, 1, du2, E2, R, E2, E1, nullptr, 0, e2, E2));
   TRY(gemm(st, 0, F(c.ones), 1, 1, du2, E2, 0, F(c.slabs) + (size_t)S * P + c.o_d_wl, E2, 1, E2, R, nullptr, 0, nullptr, 0,
-           S));
+           S, nullptr, nullptr, P));
   // ordinary backward of the BCE terms
   TRY(wgrad(st, c, F(c.dpred), 1, e2, E2, R, 1, E2, c.o_d_wl, c.o_d_bl, 0));
   TRY(wgrad(st, c, dh2, E2, e1, E1, R, E2, E1, c.o_d_w1, c.o_d_b1, 0));

@@ -186,8 +186,9 @@ typedef struct addk_gemm_args {
   const float* bias;                 /* [N] or NULL */
   const float* a_mean; const float* a_std;  /* optional (A-mean)/std on load, per K column */
   const float* relu_mask_src; int32_t ld_mask;  /* optional: C *= (mask_src > 0), [M,N] */
-  int32_t trans_a, trans_b, relu, split_k;  /* split_k > 1: C is [split_k, M, N] partial slabs */
+  int32_t trans_a, trans_b, relu, split_k;  /* split_k > 1: slab z is written at C + z * slab_stride */
   int32_t accumulate;                /* C += result (single-slab only) */
+  int64_t slab_stride;               /* floats between consecutive split-K slabs; 0 = M * ldc */
 } addk_gemm_args;
 int addk_gemm(void* stream, const addk_gemm_args* args_host, int precision);
 

@@ -21,7 +21,7 @@ def _gemm(A, B, Cout, M, N, K, ta, tb, prec, bias=None, relu=0, mask=None, split
                           bias=bias.data_ptr() if bias is not None else None, a_mean=None, a_std=None,
                           relu_mask_src=mask.data_ptr() if mask is not None else None,
                           ld_mask=mask.stride(0) if mask is not None else 0, trans_a=ta, trans_b=tb, relu=relu,
-                          split_k=split, accumulate=accumulate)
+                          split_k=split, accumulate=accumulate, slab_stride=0)
     _lib.check(_lib.lib().addk_gemm(_lib.stream(), C.byref(a), C.c_int(_lib.PRECISIONS[prec])), "addk_gemm")
 
 
