@@ -277,6 +277,18 @@ __global__ void sample_action_kernel(const float* __restrict__ mean, int act_ld,
   }
 }
 
+// Normalizer.normalize for a block of rows (normalizer.py:107-110): out = (x - mean) / std, 128-bit when dim % 4 == 0
+__global__ void obs_normalize_kernel(const float* __restrict__ x, const float* __restrict__ mean,
+                                     const float* __restrict__ sd, long long rows, int dim, float* __restrict__ out) {
+  const long long n4 = rows * dim / 4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)((i * 4) % dim);
+    const float4 v = ldg4(x + 4 * i);
+    const float4 m = ldg4(mean + c), s = ldg4(sd + c);
+    stg4(out + 4 * i, make_float4(sub_rn(v.x, m.x) / s.x, sub_rn(v.y, m.y) / s.y, sub_rn(v.z, m.z) / s.z, sub_rn(v.w, m.w) / s.w));
+  }
+}
+
 __global__ void diff_normalize_kernel(const float* __restrict__ dobs, const float* __restrict__ demo,
                                       const float* __restrict__ mean_abs, long long rows, int dim, int ld,
                                       float* __restrict__ out) {
@@ -326,6 +338,14 @@ static int trunk_forward(cudaStream_t st, const Ctx& c, const float* X, int ldx,
                          const float* nmean = nullptr, const float* nstd = nullptr) {
   const float* P = F(c.params);
   const int H1 = (int)c.hid_a1, H2 = (int)c.hid_a2, H3 = (int)c.hid_a3, pr = (int)c.precision;
+  if (nmean && pr != 0 && (in_dim & 3) == 0 && ldx == in_dim && rows <= c.mb_rows + 1) {
+    // tensor-core modes: normalise into the minibatch scratch first (TMA cannot apply it on load), then the TC tile
+    const long long n4 = (long long)rows * in_dim / 4;
+    int bl = (int)((n4 + 255) / 256); if (bl > 148 * 8) bl = 148 * 8;
+    obs_normalize_kernel<<<bl, 256, 0, st>>>(X, nmean, nstd, rows, in_dim, F(c.xn));
+    ADDK_CHECK_LAUNCH();
+    X = F(c.xn); nmean = nullptr; nstd = nullptr;
+  }
   TRY(gemm(st, nmean ? 0 : pr, X, ldx, 0, P + o_w0, in_dim, 1, F(c.h1), H1, rows, H1, in_dim, P + o_b0, 1, nullptr, 0, 1,
            nmean, nstd));
   TRY(gemm(st, pr, F(c.h1), H1, 0, P + o_w1, H1, 1, F(c.h2), H2, rows, H2, H1, P + o_b1, 1));
