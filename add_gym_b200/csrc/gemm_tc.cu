@@ -28,7 +28,6 @@ namespace addk { int sgemm_launch(cudaStream_t st, const addk_gemm_args& a); }
 namespace addk_tc {
 
 constexpr int BM = 128;        // UMMA M
-constexpr int BK = 32;         // fp32 elements per k-block = one 128-byte swizzle row
 constexpr int UMMA_K = 8;      // kind::tf32
 constexpr int NTHREADS = 192;
 
@@ -117,9 +116,11 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// One stage of the ring.  A: 128 rows/columns x 32 k  (16 KB);  B: BN x 32 k.  X3 adds the "lo" halves.
+// One stage of the ring.  A: 128 (rows | columns) x BK k;  B: BN x BK k.  tf32x3 adds the "lo" halves and uses
+// BK = 16 (64-byte rows) so that four stages still fit; the single-pass mode uses BK = 32 (128-byte rows).
 template <int BN, bool X3>
 struct Cfg {
+  static constexpr int BK = X3 ? 16 : 32;
   static constexpr int A_BYTES = BM * BK * 4;
   static constexpr int B_BYTES = BN * BK * 4;
   static constexpr int STAGE_BYTES = (A_BYTES + B_BYTES) * (X3 ? 2 : 1);
@@ -129,14 +130,23 @@ struct Cfg {
   // fp32 accumulator after every instruction, so three accumulations per k-step into ONE accumulator would
   // triple that bias; the cross-term accumulator is 2^-11 smaller and its truncation is negligible.
   static constexpr int TMEM_COLS = (X3 ? 2 : 1) * (BN < 32 ? 32 : BN);
+  // K-major tiles: 128-byte rows -> SWIZZLE_128B (UMMA layout 2), 64-byte rows -> SWIZZLE_64B (layout 4);
+  // 8-row groups are 8 * row bytes apart (SBO).  MN-major tiles: one TMA box = 32 MN x BK k (BK * 128 bytes),
+  // 128B swizzle with 32-byte atoms (layout 1), MN atoms one box apart (LBO), 4-k groups 512 B apart (SBO).
+  static constexpr uint32_t K_LAYOUT = BK == 32 ? 2u : 4u;
+  static constexpr uint32_t K_SBO = 8u * BK * 4u;
+  static constexpr uint32_t MN_BOX_BYTES = BK * 128u;
 };
 
 template <int BN, bool X3>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
   using C = Cfg<BN, X3>;
+  constexpr int BK = C::BK;
   extern __shared__ uint8_t smem_raw[];
-  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t raw_u32 = smem_u32(smem_raw);
+  const uint32_t base = (raw_u32 + 1023u) & ~1023u;
+  uint8_t* const base_ptr = smem_raw + (base - raw_u32);
   const uint32_t bars = base + C::STAGES * C::STAGE_BYTES;      // full[S] | empty[S] | ready[S] | tmem_full | tmem_ptr
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (C::STAGES + s); };
@@ -186,16 +196,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_expect_tx(full_bar(s), C::A_BYTES + C::B_BYTES);
         const int k0 = (kb_begin + i) * BK;
         if (!p.a_mn) {
-          tma_load_2d(a_hi(s), &tmA, full_bar(s), k0, m0);                      // box {32 k, 128 rows}
+          tma_load_2d(a_hi(s), &tmA, full_bar(s), k0, m0);                      // box {BK k, 128 rows}
         } else {
 #pragma unroll
-          for (int j = 0; j < BM / 32; ++j) tma_load_2d(a_hi(s) + j * 4096, &tmA, full_bar(s), m0 + 32 * j, k0);   // box {32 m, 32 k}
+          for (int j = 0; j < BM / 32; ++j)                                      // box {32 m, BK k}
+            tma_load_2d(a_hi(s) + j * C::MN_BOX_BYTES, &tmA, full_bar(s), m0 + 32 * j, k0);
         }
         if (!p.b_mn) {
-          tma_load_2d(b_hi(s), &tmB, full_bar(s), k0, n0);                      // box {32 k, BN rows}
+          tma_load_2d(b_hi(s), &tmB, full_bar(s), k0, n0);                      // box {BK k, BN rows}
         } else {
 #pragma unroll
-          for (int j = 0; j < BN / 32; ++j) tma_load_2d(b_hi(s) + j * 4096, &tmB, full_bar(s), n0 + 32 * j, k0);
+          for (int j = 0; j < BN / 32; ++j)
+            tma_load_2d(b_hi(s) + j * C::MN_BOX_BYTES, &tmB, full_bar(s), n0 + 32 * j, k0);
         }
       }
     }
@@ -205,59 +217,72 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // instruction descriptor: D fp32, A/B tf32, majors, N>>3, M>>4
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.a_mn ? 1 : 0) << 15) |
                              ((uint32_t)(p.b_mn ? 1 : 0) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-      // K-major  (SWIZZLE_128B): 8-row groups 1024 B apart (SBO), k-step = 32 B inside the swizzled row.
-      // MN-major (SWIZZLE_128B, 32 B atoms): one TMA box = 32 MN x 32 k = 4096 B; MN atoms 4096 B apart (LBO),
-      //          4-k groups 512 B apart (SBO), k-step (8 k) = 1024 B.
-      const uint32_t a_lbo = p.a_mn ? 4096u : 16u, b_lbo = p.b_mn ? 4096u : 16u;
-      const uint32_t a_sbo = p.a_mn ? 512u : 1024u, b_sbo = p.b_mn ? 512u : 1024u;
-      const uint32_t a_lay = p.a_mn ? 1u : 2u, b_lay = p.b_mn ? 1u : 2u;
-      const uint32_t a_kstep = p.a_mn ? 1024u : 32u, b_kstep = p.b_mn ? 1024u : 32u;
+      const uint32_t a_lbo = p.a_mn ? C::MN_BOX_BYTES : 16u, b_lbo = p.b_mn ? C::MN_BOX_BYTES : 16u;
+      const uint32_t a_sbo = p.a_mn ? 512u : C::K_SBO, b_sbo = p.b_mn ? 512u : C::K_SBO;
+      const uint32_t a_lay = p.a_mn ? 1u : C::K_LAYOUT, b_lay = p.b_mn ? 1u : C::K_LAYOUT;
+      const uint32_t a_kstep = p.a_mn ? 1024u : 32u, b_kstep = p.b_mn ? 1024u : 32u;   // 8 k per MMA
       uint32_t acc = 0, acc_x = 0;
       for (int i = 0; i < num_kb; ++i) {
         const int s = i % C::STAGES;
         const uint32_t ph = (uint32_t)(i / C::STAGES) & 1u;
-        mbar_wait(X3 ? ready_bar(s) : full_bar(s), ph);
+        mbar_wait(full_bar(s), ph);
         tc_fence_after();
+        // main term: the tensor core truncates the fp32 operands to tf32 itself, so hi(x) is the landed tile as is
 #pragma unroll
         for (int ks = 0; ks < BK / UMMA_K; ++ks) {
-          const uint64_t dah = smem_desc(a_hi(s) + ks * a_kstep, a_lbo, a_sbo, a_lay);
-          const uint64_t dbh = smem_desc(b_hi(s) + ks * b_kstep, b_lbo, b_sbo, b_lay);
-          if (X3) {
+          umma_tf32(tmem_base, smem_desc(a_hi(s) + ks * a_kstep, a_lbo, a_sbo, a_lay),
+                    smem_desc(b_hi(s) + ks * b_kstep, b_lbo, b_sbo, b_lay), idesc, acc);
+          acc = 1;
+        }
+        if (X3) {
+          mbar_wait(ready_bar(s), ph);         // lo tiles written by the splitter warps
+          tc_fence_after();
+#pragma unroll
+          for (int ks = 0; ks < BK / UMMA_K; ++ks) {
+            const uint64_t dah = smem_desc(a_hi(s) + ks * a_kstep, a_lbo, a_sbo, a_lay);
+            const uint64_t dbh = smem_desc(b_hi(s) + ks * b_kstep, b_lbo, b_sbo, b_lay);
             const uint64_t dal = smem_desc(a_lo(s) + ks * a_kstep, a_lbo, a_sbo, a_lay);
             const uint64_t dbl = smem_desc(b_lo(s) + ks * b_kstep, b_lbo, b_sbo, b_lay);
             umma_tf32(tmem_base + BN, dal, dbh, idesc, acc_x);
             acc_x = 1;
             umma_tf32(tmem_base + BN, dah, dbl, idesc, acc_x);
           }
-          umma_tf32(tmem_base, dah, dbh, idesc, acc);
-          acc = 1;
         }
         umma_commit(empty_bar(s));          // stage reusable once these MMAs have read it
       }
-      umma_commit(tmem_full_bar);           // accumulator complete
+      umma_commit(tmem_full_bar);           // accumulators complete
     }
   } else {
     // ===================== splitter (tf32x3) + epilogue: warps 2..5 =====================
     const int t = threadIdx.x - 64;          // 0..127
     if (X3) {
+      // lo = x - tf32_trunc(x), elementwise (so the swizzled placement does not matter; A and B are contiguous
+      // in the stage and so are their lo twins).  The hi tile is left untouched: the MMA reads it concurrently.
+      constexpr int N4 = (C::A_BYTES + C::B_BYTES) / 16;
+      constexpr int PER = N4 / 128;
+      static_assert(N4 % 128 == 0, "tile size");
       for (int i = 0; i < num_kb; ++i) {
         const int s = i % C::STAGES;
         const uint32_t ph = (uint32_t)(i / C::STAGES) & 1u;
         mbar_wait(full_bar(s), ph);
-        // elementwise, so the swizzled placement does not matter: A and B are contiguous in the stage
-        constexpr int N4 = (C::A_BYTES + C::B_BYTES) / 16;
-        const uint32_t src = a_hi(s), dst = a_lo(s);
-#pragma unroll 4
-        for (int j = t; j < N4; j += 128) {
-          float4 x;
-          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(src + 16u * j) : "memory");
-          float4 h, l;
-          h.x = __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u); l.x = x.x - h.x;
-          h.y = __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u); l.y = x.y - h.y;
-          h.z = __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u); l.z = x.z - h.z;
-          h.w = __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u); l.w = x.w - h.w;
-          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(src + 16u * j), "f"(h.x), "f"(h.y), "f"(h.z), "f"(h.w) : "memory");
-          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + 16u * j), "f"(l.x), "f"(l.y), "f"(l.z), "f"(l.w) : "memory");
+        const float4* src = reinterpret_cast<const float4*>(base_ptr + (size_t)s * C::STAGE_BYTES);
+        float4* dst = reinterpret_cast<float4*>(base_ptr + (size_t)s * C::STAGE_BYTES + C::A_BYTES + C::B_BYTES);
+#pragma unroll
+        for (int j0 = 0; j0 < PER; j0 += 4) {
+          float4 x[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) if (j0 + u < PER) x[u] = src[t + 128 * (j0 + u)];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if (j0 + u < PER) {
+              float4 l;
+              l.x = x[u].x - __uint_as_float(__float_as_uint(x[u].x) & 0xFFFFE000u);
+              l.y = x[u].y - __uint_as_float(__float_as_uint(x[u].y) & 0xFFFFE000u);
+              l.z = x[u].z - __uint_as_float(__float_as_uint(x[u].z) & 0xFFFFE000u);
+              l.w = x[u].w - __uint_as_float(__float_as_uint(x[u].w) & 0xFFFFE000u);
+              dst[t + 128 * (j0 + u)] = l;
+            }
+          }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
         mbar_arrive(ready_bar(s));
@@ -343,15 +368,16 @@ static bool resolve_encode() {
 }
 
 // 2-D fp32 tensor map: memory [outer, inner] with `ld` floats between rows; box {32, box_rows}, 128-byte swizzle.
-static bool make_map(CUtensorMap* map, const float* ptr, long long inner, long long outer, long long ld, int box_rows,
-                     bool mn_major) {
+static bool make_map(CUtensorMap* map, const float* ptr, long long inner, long long outer, long long ld, int box_inner,
+                     int box_rows, bool mn_major) {
   cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
   cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
-  cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
+  cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1u, 1u};
   CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                        mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B
+                                 : (box_inner == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B),
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
@@ -385,9 +411,11 @@ int addk_gemm_tc(cudaStream_t st, const addk_gemm_args& a, int precision) {
   }
   const bool aligned = ((a.lda & 3) == 0) && ((a.ldb & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.A) & 15) == 0) &&
                        ((reinterpret_cast<uintptr_t>(a.B) & 15) == 0);
-  if (!aligned || a.a_mean || a.M < 64 || a.N < 48 || a.K < 32 || !resolve_encode()) return addk::sgemm_launch(st, a);
+  if (!aligned || a.a_mean || a.M < 16 || a.N < 16 || a.K < 16 || !resolve_encode()) return addk::sgemm_launch(st, a);
   int split = a.split_k > 1 ? a.split_k : 1;
   if (split > 1 && (a.bias || a.relu || a.relu_mask_src || a.accumulate)) return ADDK_ERR_ARG;
+  const bool x3 = precision == 1;
+  const int BK = x3 ? 16 : 32;
   const int kb_total = (a.K + BK - 1) / BK;
   int kb_per = (kb_total + split - 1) / split;
   // every slab must own at least one k-block: idle slabs would leave stale data behind
@@ -400,11 +428,10 @@ int addk_gemm_tc(cudaStream_t st, const addk_gemm_args& a, int precision) {
   p.b_mn = a.trans_b ? 0 : 1;          // B given as [K,N]
   const int BN = a.N > 128 ? 256 : (a.N > 64 ? 128 : 64);
   CUtensorMap ta, tb;
-  bool ok = p.a_mn ? make_map(&ta, a.A, a.M, a.K, a.lda, 32, true) : make_map(&ta, a.A, a.K, a.M, a.lda, BM, false);
-  ok = ok && (p.b_mn ? make_map(&tb, a.B, a.N, a.K, a.ldb, 32, true) : make_map(&tb, a.B, a.K, a.N, a.ldb, BN, false));
+  bool ok = p.a_mn ? make_map(&ta, a.A, a.M, a.K, a.lda, 32, BK, true) : make_map(&ta, a.A, a.K, a.M, a.lda, BK, BM, false);
+  ok = ok && (p.b_mn ? make_map(&tb, a.B, a.N, a.K, a.ldb, 32, BK, true) : make_map(&tb, a.B, a.K, a.N, a.ldb, BK, BN, false));
   if (!ok) return addk::sgemm_launch(st, a);
   dim3 grid((a.N + BN - 1) / BN, (a.M + BM - 1) / BM, split);
-  const bool x3 = precision == 1;
   if (BN == 256) return x3 ? launch<256, true>(st, ta, tb, p, grid) : launch<256, false>(st, ta, tb, p, grid);
   if (BN == 128) return x3 ? launch<128, true>(st, ta, tb, p, grid) : launch<128, false>(st, ta, tb, p, grid);
   return x3 ? launch<64, true>(st, ta, tb, p, grid) : launch<64, false>(st, ta, tb, p, grid);

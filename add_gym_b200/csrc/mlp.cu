@@ -202,6 +202,82 @@ __global__ void sumsq_kernel(const float* __restrict__ x, long long n, double* _
   if (threadIdx.x == 0) atomicAdd(out, s);
 }
 
+// Bias gradient db[n] = sum over rows of dY[row, n], as `nsplit` partial slabs (slab z at out + z * slab_stride).
+// Block = 256 threads: 32 column-quads x 8 row lanes; 128-bit loads, rows strided by 8 within the block's chunk.
+// With `rw` given, rows are weighted: out[n] = sum_r rw[r] * dY[r, n] -- the weight gradient of a 1-output head.
+__global__ void colsum_slabs_kernel(const float* __restrict__ dY, int ld, int rows, int n, int rows_per_split,
+                                    float* __restrict__ out, long long slab_stride, const float* __restrict__ rw) {
+  __shared__ float4 sm[8][32];
+  const int cq = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int col = (blockIdx.x * 32 + cq) * 4;
+  const int r0 = blockIdx.y * rows_per_split, r1 = min(rows, r0 + rows_per_split);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (col < n) {
+    if (col + 3 < n && (ld & 3) == 0) {
+      for (int r = r0 + rl; r < r1; r += 8) {
+        const float4 v = ldg4(dY + (size_t)r * ld + col);
+        const float w = rw ? rw[r] : 1.0f;
+        acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y); acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
+      }
+    } else {
+      for (int r = r0 + rl; r < r1; r += 8) {
+        const float* q = dY + (size_t)r * ld + col;
+        const float w = rw ? rw[r] : 1.0f;
+        acc.x = fmaf(w, q[0], acc.x);
+        if (col + 1 < n) acc.y = fmaf(w, q[1], acc.y);
+        if (col + 2 < n) acc.z = fmaf(w, q[2], acc.z);
+        if (col + 3 < n) acc.w = fmaf(w, q[3], acc.w);
+      }
+    }
+  }
+  sm[rl][cq] = acc;
+  __syncthreads();
+  if (rl == 0 && col < n) {
+    float4 t = sm[0][cq];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) { t.x += sm[i][cq].x; t.y += sm[i][cq].y; t.z += sm[i][cq].z; t.w += sm[i][cq].w; }
+    float* o = out + (size_t)blockIdx.y * slab_stride + col;
+    o[0] = t.x;
+    if (col + 1 < n) o[1] = t.y;
+    if (col + 2 < n) o[2] = t.z;
+    if (col + 3 < n) o[3] = t.w;
+  }
+}
+
+// 1-output head forward: out[r] = dot(X[r, :], w) + b   (critic value, discriminator logit); warp per row
+__global__ void rowdot_kernel(const float* __restrict__ X, int ld, long long rows, int K, const float* __restrict__ w,
+                              const float* __restrict__ b, float* __restrict__ out) {
+  const long long r = (long long)blockIdx.x * (blockDim.x / 32) + (threadIdx.x / 32);
+  const int lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  const float* x = X + r * ld;
+  float acc = 0.f;
+  if ((K & 3) == 0 && (ld & 3) == 0) {
+    for (int k = lane * 4; k < K; k += 128) {
+      const float4 v = ldg4(x + k), u = ldg4(w + k);
+      acc = fmaf(v.x, u.x, acc); acc = fmaf(v.y, u.y, acc); acc = fmaf(v.z, u.z, acc); acc = fmaf(v.w, u.w, acc);
+    }
+  } else {
+    for (int k = lane; k < K; k += 32) acc = fmaf(x[k], w[k], acc);
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) out[r] = acc + (b ? b[0] : 0.f);
+}
+
+// 1-output head input gradient through the ReLU: g[r, k] = (h[r, k] > 0) ? d[r] * w[k] : 0
+__global__ void outer_mask_kernel(const float* __restrict__ d, const float* __restrict__ w, const float* __restrict__ h,
+                                  long long rows, int K, float* __restrict__ g) {
+  const long long n4 = rows * K / 4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = (i * 4) / K;
+    const int k = (int)((i * 4) % K);
+    const float dv = d[r];
+    const float4 u = ldg4(w + k), m = ldg4(h + 4 * i);
+    stg4(g + 4 * i, make_float4(m.x > 0.f ? dv * u.x : 0.f, m.y > 0.f ? dv * u.y : 0.f, m.z > 0.f ? dv * u.z : 0.f,
+                                m.w > 0.f ? dv * u.w : 0.f));
+  }
+}
+
 struct Seg { long long begin, end; int nslabs; float l2; };
 struct SegTable { Seg s[24]; int n; long long P; };
 
@@ -324,11 +400,34 @@ static int wgrad(cudaStream_t st, const Ctx& c, const float* dY, int ldy, const 
                  int k_in, long long o_w, long long o_b, int slab0) {
   const int S = (int)c.split_k;
   const long long P = c.num_params;
-  TRY(gemm(st, (int)c.precision, dY, ldy, 1, X, ldx, 0, F(c.slabs) + (size_t)slab0 * P + o_w, k_in, n_out, k_in, rows,
-           nullptr, 0, nullptr, 0, S, nullptr, nullptr, P));
-  if (o_b >= 0)
-    TRY(gemm(st, 0, F(c.ones), 1, 1, dY, ldy, 0, F(c.slabs) + (size_t)slab0 * P + o_b, n_out, 1, n_out, rows, nullptr, 0,
-             nullptr, 0, S, nullptr, nullptr, P));
+  if (n_out == 1 && ldy == 1) {
+    colsum_slabs_kernel<<<dim3((k_in + 127) / 128, S), 256, 0, st>>>(X, ldx, rows, k_in, (rows + S - 1) / S,
+                                                                   F(c.slabs) + (size_t)slab0 * P + o_w, P, dY);
+    ADDK_CHECK_LAUNCH();
+  } else {
+    TRY(gemm(st, (int)c.precision, dY, ldy, 1, X, ldx, 0, F(c.slabs) + (size_t)slab0 * P + o_w, k_in, n_out, k_in, rows,
+             nullptr, 0, nullptr, 0, S, nullptr, nullptr, P));
+  }
+  if (o_b >= 0) {
+    const int rps = (rows + S - 1) / S;
+    colsum_slabs_kernel<<<dim3((n_out + 127) / 128, S), 256, 0, st>>>(dY, ldy, rows, n_out, rps,
+                                                                    F(c.slabs) + (size_t)slab0 * P + o_b, P, nullptr);
+    ADDK_CHECK_LAUNCH();
+  }
+  return ADDK_OK;
+}
+
+static int head1_forward(cudaStream_t st, const float* X, int ld, long long rows, int K, const float* w, const float* b,
+                         float* out) {
+  rowdot_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(X, ld, rows, K, w, b, out);
+  ADDK_CHECK_LAUNCH();
+  return ADDK_OK;
+}
+static int head1_dgrad(cudaStream_t st, const float* d, const float* w, const float* h, long long rows, int K, float* g) {
+  const long long n4 = rows * K / 4;
+  long long bl = (n4 + 255) / 256; if (bl > 148 * 16) bl = 148 * 16;
+  outer_mask_kernel<<<(unsigned)bl, 256, 0, st>>>(d, w, h, rows, K, g);
+  ADDK_CHECK_LAUNCH();
   return ADDK_OK;
 }
 
@@ -416,19 +515,19 @@ extern "C" int addk_update_minibatch(void* stream, void* ctx_host, const long lo
 
   // ---------------- critic ----------------
   TRY(trunk_forward(st, c, F(c.xn), OD, OD, M, c.o_c_w0, c.o_c_b0, c.o_c_w1, c.o_c_b1, c.o_c_w2, c.o_c_b2));
-  TRY(gemm(st, pr, F(c.h3), H3, 0, W + c.o_c_wo, H3, 1, F(c.pred), 1, M, 1, H3, W + c.o_c_bo, 0));
+  TRY(head1_forward(st, F(c.h3), H3, M, H3, W + c.o_c_wo, W + c.o_c_bo, F(c.pred)));
   critic_loss_kernel<<<(M + 255) / 256, 256, 0, st>>>(F(c.pred), F(c.tar), M, (float)c.critic_loss_weight, F(c.dpred),
                                                       stats);
   ADDK_CHECK_LAUNCH();
   TRY(wgrad(st, c, F(c.dpred), 1, F(c.h3), H3, M, 1, H3, c.o_c_wo, c.o_c_bo, 0));
-  TRY(gemm(st, pr, F(c.dpred), 1, 0, W + c.o_c_wo, H3, 0, F(c.g3), H3, M, H3, 1, nullptr, 0, F(c.h3), H3));
+  TRY(head1_dgrad(st, F(c.dpred), W + c.o_c_wo, F(c.h3), M, H3, F(c.g3)));
   TRY(trunk_backward(st, c, F(c.xn), OD, OD, M, c.o_c_w0, c.o_c_b0, c.o_c_w1, c.o_c_b1, c.o_c_w2, c.o_c_b2));
 
   // ---------------- discriminator (R = M + 1 rows) ----------------
   float *e1 = F(c.h1), *e2 = F(c.h3), *dh2 = F(c.g3), *dv1 = F(c.g1), *du2 = F(c.g2);
   TRY(gemm(st, pr, F(c.dn), DL, 0, W + c.o_d_w0, DD, 1, e1, E1, R, E1, DD, W + c.o_d_b0, 1));
   TRY(gemm(st, pr, e1, E1, 0, W + c.o_d_w1, E1, 1, e2, E2, R, E2, E1, W + c.o_d_b1, 1));
-  TRY(gemm(st, pr, e2, E2, 0, W + c.o_d_wl, E2, 1, F(c.pred), 1, R, 1, E2, W + c.o_d_bl, 0));
+  TRY(head1_forward(st, e2, E2, R, E2, W + c.o_d_wl, W + c.o_d_bl, F(c.pred)));
   disc_loss_kernel<<<(R + 255) / 256, 256, 0, st>>>(F(c.pred), M, (float)c.disc_loss_weight, F(c.dpred), stats);
   ADDK_CHECK_LAUNCH();
   {
@@ -450,8 +549,9 @@ extern "C" int addk_update_minibatch(void* stream, void* ctx_host, const long lo
   TRY(gemm(st, pr, F(c.u2), E2, 1, dv1, E1, 0, F(c.slabs) + (size_t)S * P + c.o_d_w1, E1, E2, E1, R, nullptr, 0, nullptr, 0,
            S, nullptr, nullptr, P));
   TRY(gemm(st, pr, dv1, E1, 0, W + c.o_d_w1, E1, 1, du2, E2, R, E2, E1, nullptr, 0, e2, E2));
-  TRY(gemm(st, 0, F(c.ones), 1, 1, du2, E2, 0, F(c.slabs) + (size_t)S * P + c.o_d_wl, E2, 1, E2, R, nullptr, 0, nullptr, 0,
-           S, nullptr, nullptr, P));
+  colsum_slabs_kernel<<<dim3((E2 + 127) / 128, S), 256, 0, st>>>(du2, E2, R, E2, (R + S - 1) / S,
+                                                                 F(c.slabs) + (size_t)S * P + c.o_d_wl, P, nullptr);
+  ADDK_CHECK_LAUNCH();
   // ordinary backward of the BCE terms
   TRY(wgrad(st, c, F(c.dpred), 1, e2, E2, R, 1, E2, c.o_d_wl, c.o_d_bl, 0));
   TRY(wgrad(st, c, dh2, E2, e1, E1, R, E2, E1, c.o_d_w1, c.o_d_b1, 0));
@@ -524,7 +624,7 @@ extern "C" int addk_critic_eval(void* stream, void* ctx_host, const float* obs, 
     int rows = (int)((n - r0 < chunk) ? n - r0 : chunk);
     TRY(trunk_forward(st, c, obs + r0 * OD, OD, OD, rows, c.o_c_w0, c.o_c_b0, c.o_c_w1, c.o_c_b1, c.o_c_w2, c.o_c_b2,
                       F(c.obs_mean), F(c.obs_std)));
-    TRY(gemm(st, (int)c.precision, F(c.h3), H3, 0, W + c.o_c_wo, H3, 1, vals + r0, 1, rows, 1, H3, W + c.o_c_bo, 0));
+    TRY(head1_forward(st, F(c.h3), H3, rows, H3, W + c.o_c_wo, W + c.o_c_bo, vals + r0));
   }
   return ADDK_OK;
 }
@@ -546,7 +646,7 @@ extern "C" int addk_disc_eval(void* stream, void* ctx_host, const float* disc_ob
     ADDK_CHECK_LAUNCH();
     TRY(gemm(st, pr, F(c.gx), DL, 0, W + c.o_d_w0, DD, 1, e1, E1, rows, E1, DD, W + c.o_d_b0, 1));
     TRY(gemm(st, pr, e1, E1, 0, W + c.o_d_w1, E1, 1, e2, E2, rows, E2, E1, W + c.o_d_b1, 1));
-    TRY(gemm(st, pr, e2, E2, 0, W + c.o_d_wl, E2, 1, logits + r0, 1, rows, 1, E2, W + c.o_d_bl, 0));
+    TRY(head1_forward(st, e2, E2, rows, E2, W + c.o_d_wl, W + c.o_d_bl, logits + r0));
   }
   return ADDK_OK;
 }

@@ -35,6 +35,7 @@ SHAPES = [
     # M, N, K   (forward / dgrad / wgrad shapes of the three MLPs, plus ragged edges)
     (512, 1024, 264), (300, 512, 1024), (129, 1024, 1024), (1024, 264, 2048), (1024, 114, 1500), (256, 256, 32),
     (128, 64, 40), (16385 // 8, 512, 1024),
+    (29, 512, 2048), (2048, 29, 512), (2048, 512, 29), (1024, 114, 1000), (40, 24, 20),   # heads: tiles mostly out of bounds
 ]
 
 
