@@ -294,7 +294,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int row = m0 + 32 * q + lane;
     float* Cz = p.C + (size_t)blockIdx.z * p.slab_stride;
     const bool vec = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(Cz) & 15) == 0) &&
+                     (!p.bias || ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0)) &&
                      (!p.mask || (((p.ld_mask & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.mask) & 15) == 0)));
+    // Each warp owns rows [32q, 32q+32) of the tile.  Accumulator columns come out of TMEM one row per lane, which
+    // would scatter every store over 32 rows; so each 32 x 32 chunk is transposed through a 4 KB swizzled shared
+    // buffer (the operand stages are idle by now) and leaves as four full 128-byte row segments per instruction,
+    // with bias / mask / accumulate applied on the coalesced side (one float4 of bias per lane per chunk).
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    float4* stg = reinterpret_cast<float4*>(base_ptr + 4096 * q);
+    const int l_row = lane >> 3, l_c4 = lane & 7;
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
       if (n0 + c0 >= p.N) break;             // warp-uniform
@@ -306,40 +314,62 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w[j]));
       }
-      if (row < p.M) {
+      if (vec) {
+#pragma unroll
+        for (int c4 = 0; c4 < 8; ++c4)
+          stg[lane * 8 + (c4 ^ (lane & 7))] = make_float4(__uint_as_float(v[4 * c4]), __uint_as_float(v[4 * c4 + 1]),
+                                                          __uint_as_float(v[4 * c4 + 2]), __uint_as_float(v[4 * c4 + 3]));
+        __syncwarp();
+        const int col = n0 + c0 + 4 * l_c4;
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.bias) {
+          if (col + 3 < p.N) b4 = *reinterpret_cast<const float4*>(p.bias + col);   // bias is 16-byte aligned (flat vector)
+          else { if (col < p.N) b4.x = p.bias[col]; if (col + 1 < p.N) b4.y = p.bias[col + 1]; if (col + 2 < p.N) b4.z = p.bias[col + 2]; }
+        }
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int r = it * 4 + l_row;
+          const int grow = m0 + 32 * q + r;
+          float4 o = stg[r * 8 + (l_c4 ^ (r & 7))];
+          if (grow < p.M && col < p.N) {
+            o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
+            if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+            float* dst = Cz + (size_t)grow * p.ldc + col;
+            if (col + 3 < p.N) {
+              if (p.mask) {
+                const float4 m4 = *reinterpret_cast<const float4*>(p.mask + (size_t)grow * p.ld_mask + col);
+                o.x = m4.x > 0.f ? o.x : 0.f; o.y = m4.y > 0.f ? o.y : 0.f;
+                o.z = m4.z > 0.f ? o.z : 0.f; o.w = m4.w > 0.f ? o.w : 0.f;
+              }
+              if (p.accumulate) {
+                const float4 c4 = *reinterpret_cast<const float4*>(dst);
+                o.x += c4.x; o.y += c4.y; o.z += c4.z; o.w += c4.w;
+              }
+              *reinterpret_cast<float4*>(dst) = o;
+            } else {
+              const float oo[4] = {o.x, o.y, o.z, o.w};
+              for (int e = 0; e < 4 && col + e < p.N; ++e) {
+                float x = oo[e];
+                if (p.mask) x = p.mask[(size_t)grow * p.ld_mask + col + e] > 0.f ? x : 0.f;
+                if (p.accumulate) x += dst[e];
+                dst[e] = x;
+              }
+            }
+          }
+        }
+        __syncwarp();
+      } else if (row < p.M) {                // unaligned output (ldc % 4 != 0): row-per-lane scalar stores
         float* dst = Cz + (size_t)row * p.ldc + n0 + c0;
         const float* mk = p.mask ? p.mask + (size_t)row * p.ld_mask + n0 + c0 : nullptr;
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
+        for (int j = 0; j < 32; ++j) {
           const int col = n0 + c0 + j;
           if (col >= p.N) break;
-          float o[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            float x = __uint_as_float(v[j + e]);
-            if (p.bias && col + e < p.N) x += p.bias[col + e];
-            if (p.relu) x = fmaxf(x, 0.f);
-            o[e] = x;
-          }
-          if (vec && col + 3 < p.N) {
-            if (mk) {
-              const float4 m4 = *reinterpret_cast<const float4*>(mk + j);
-              o[0] = m4.x > 0.f ? o[0] : 0.f; o[1] = m4.y > 0.f ? o[1] : 0.f;
-              o[2] = m4.z > 0.f ? o[2] : 0.f; o[3] = m4.w > 0.f ? o[3] : 0.f;
-            }
-            if (p.accumulate) {
-              const float4 c4 = *reinterpret_cast<const float4*>(dst + j);
-              o[0] += c4.x; o[1] += c4.y; o[2] += c4.z; o[3] += c4.w;
-            }
-            *reinterpret_cast<float4*>(dst + j) = make_float4(o[0], o[1], o[2], o[3]);
-          } else {
-            for (int e = 0; e < 4 && col + e < p.N; ++e) {
-              float x = o[e];
-              if (mk) x = mk[j + e] > 0.f ? x : 0.f;
-              if (p.accumulate) x += dst[j + e];
-              dst[j + e] = x;
-            }
-          }
+          float x = __uint_as_float(v[j]);
+          if (p.bias) x += p.bias[col];
+          if (p.relu) x = fmaxf(x, 0.f);
+          if (mk) x = mk[j] > 0.f ? x : 0.f;
+          if (p.accumulate) x += dst[j];
+          dst[j] = x;
         }
       }
     }

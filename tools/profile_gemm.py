@@ -1,0 +1,42 @@
+"""Profiling driver (GPU box): the dominant dense layer (M x 1024 x 1024, bias + ReLU) a few times, nothing else.
+    python tools/profile_gemm.py [precision] [M] [reps] [layout: fwd|dgrad|wgrad]"""
+import ctypes as C, os, sys
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO)
+import torch
+from add_gym_b200 import _lib
+prec = sys.argv[1] if len(sys.argv) > 1 else "tf32x3"
+M = int(sys.argv[2]) if len(sys.argv) > 2 else 16384
+reps = int(sys.argv[3]) if len(sys.argv) > 3 else 5
+layout = sys.argv[4] if len(sys.argv) > 4 else "fwd"
+K = N = 1024
+dev = "cuda:0"
+A = [torch.randn(M, K, device=dev) for _ in range(3)]
+W = torch.randn(N, K, device=dev) * 0.03
+bias = torch.zeros(N, device=dev)
+Cc = [torch.empty(M, N, device=dev) for _ in range(2)]
+slabs = torch.empty(8, N, K, device=dev)
+L = _lib.lib()
+def launch(i):
+    if layout == "fwd":
+        a = _lib.AddkGemmArgs(A=A[i % 3].data_ptr(), lda=K, B=W.data_ptr(), ldb=K, C=Cc[i % 2].data_ptr(), ldc=N, M=M, N=N, K=K,
+                              bias=bias.data_ptr(), a_mean=None, a_std=None, relu_mask_src=None, ld_mask=0, trans_a=0, trans_b=1,
+                              relu=1, split_k=1, accumulate=0, slab_stride=0)
+    elif layout == "dgrad":
+        a = _lib.AddkGemmArgs(A=A[i % 3].data_ptr(), lda=K, B=W.data_ptr(), ldb=K, C=Cc[i % 2].data_ptr(), ldc=N, M=M, N=K, K=N,
+                              bias=None, a_mean=None, a_std=None, relu_mask_src=A[(i + 1) % 3].data_ptr(), ld_mask=K, trans_a=0,
+                              trans_b=0, relu=0, split_k=1, accumulate=0, slab_stride=0)
+    else:
+        a = _lib.AddkGemmArgs(A=A[i % 3].data_ptr(), lda=K, B=A[(i + 1) % 3].data_ptr(), ldb=K, C=slabs.data_ptr(), ldc=K, M=N, N=K,
+                              K=M, bias=None, a_mean=None, a_std=None, relu_mask_src=None, ld_mask=0, trans_a=1, trans_b=0,
+                              relu=0, split_k=8, accumulate=0, slab_stride=0)
+    _lib.check(L.addk_gemm(_lib.stream(), C.byref(a), C.c_int(_lib.PRECISIONS[prec])), "addk_gemm")
+for i in range(2):
+    launch(i)
+torch.cuda.synchronize()
+ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+for i, (a, b) in enumerate(ev):
+    a.record(); launch(i); b.record()
+torch.cuda.synchronize()
+ms = sorted(a.elapsed_time(b) for a, b in ev)[len(ev) // 2]
+print("%s %s M=%d: %.1f us  %.1f TFLOP/s" % (prec, layout, M, ms * 1e3, 2.0 * M * N * K / ms / 1e9))
