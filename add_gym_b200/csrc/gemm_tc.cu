@@ -306,6 +306,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
       if (n0 + c0 >= p.N) break;             // warp-uniform
+      // ReLU-mask / accumulate operands of this chunk: issue the global loads first so they fly during the TMEM read
+      float4 m4[8], a4[8];
+      const int colv = n0 + c0 + 4 * l_c4;
+      const bool full4 = vec && (colv + 3 < p.N);
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int grow = m0 + 32 * q + it * 4 + l_row;
+        m4[it] = make_float4(1.f, 1.f, 1.f, 1.f);
+        a4[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (full4 && grow < p.M) {
+          if (p.mask) m4[it] = *reinterpret_cast<const float4*>(p.mask + (size_t)grow * p.ld_mask + colv);
+          if (p.accumulate) a4[it] = *reinterpret_cast<const float4*>(Cz + (size_t)grow * p.ldc + colv);
+        }
+      }
       uint32_t v[32];
       tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)c0, v);
       if (X3) {
@@ -336,15 +350,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
             float* dst = Cz + (size_t)grow * p.ldc + col;
             if (col + 3 < p.N) {
-              if (p.mask) {
-                const float4 m4 = *reinterpret_cast<const float4*>(p.mask + (size_t)grow * p.ld_mask + col);
-                o.x = m4.x > 0.f ? o.x : 0.f; o.y = m4.y > 0.f ? o.y : 0.f;
-                o.z = m4.z > 0.f ? o.z : 0.f; o.w = m4.w > 0.f ? o.w : 0.f;
-              }
-              if (p.accumulate) {
-                const float4 c4 = *reinterpret_cast<const float4*>(dst);
-                o.x += c4.x; o.y += c4.y; o.z += c4.z; o.w += c4.w;
-              }
+              o.x = m4[it].x > 0.f ? o.x : 0.f; o.y = m4[it].y > 0.f ? o.y : 0.f;
+              o.z = m4[it].z > 0.f ? o.z : 0.f; o.w = m4[it].w > 0.f ? o.w : 0.f;
+              o.x += a4[it].x; o.y += a4[it].y; o.z += a4[it].z; o.w += a4[it].w;
               *reinterpret_cast<float4*>(dst) = o;
             } else {
               const float oo[4] = {o.x, o.y, o.z, o.w};
