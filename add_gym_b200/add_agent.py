@@ -225,7 +225,8 @@ class ADDAgent(torch.nn.Module):
             h1=z(R, w1), h2=z(R, w1), h3=z(R, max(H[2], E[1])), g1=z(R, w1), g2=z(R, w1), g3=z(R, max(H[2], E[1])),
             u1=z(R, E[0]), u2=z(R, E[1]), gx=z(R, dl), dg=z(R, dl), mean=z(R, al), dmean=z(R, al), pred=z(R),
             dpred=z(R), ones=torch.ones(R, device=dev), stats=z(32, dt=torch.float64), info=z(self._max_steps, 16),
-            cnt=z(1, dt=torch.int32), slabs=z(2 * S, m.num_params))
+            cnt=z(1, dt=torch.int32), slabs=z(2 * S, m.num_params), colsum_work=z(64 * 1024 + 64),
+            wd0_pad=z(E[0], dl))
         ptrs = dict(self._ws)
         ptrs.update(params=m.flat, grads=m.flat_grad, exp_avg=self._optimizer.exp_avg,
                     exp_avg_sq=self._optimizer.exp_avg_sq, obs_mean=self._obs_norm._mean, obs_std=self._obs_norm._std,

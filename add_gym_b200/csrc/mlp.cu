@@ -79,48 +79,56 @@ __global__ void actor_loss_kernel(const float* __restrict__ mean, const float* _
                                   const float* __restrict__ adv, const float* __restrict__ mask, int M, int act_dim,
                                   int act_ld, float clip, float bound_w, const int* __restrict__ cnt,
                                   float* __restrict__ dmean, double* __restrict__ stats) {
-  int i = blockIdx.x * (blockDim.x / 32) + (threadIdx.x / 32);
-  int lane = threadIdx.x & 31;
-  if (i >= M) return;
-  const bool on = mask[i] == 1.0f;
-  float m = 0.f, d = 0.f, sd = 1.f, ls = 0.f;
-  if (lane < act_dim) {
-    m = mean[(size_t)i * act_ld + lane];
-    ls = logstd[lane];
-    sd = expf(ls);
-    d = sub_rn(an[(size_t)i * act_ld + lane], m);
+  __shared__ double s_acc[8][4];
+  const int warp = threadIdx.x / 32, lane = threadIdx.x & 31;
+  const int i = blockIdx.x * (blockDim.x / 32) + warp;
+  double a_surr = 0.0, a_clip = 0.0, a_ratio = 0.0, a_bound = 0.0;
+  if (i < M) {
+    const bool on = mask[i] == 1.0f;
+    float m = 0.f, d = 0.f, sd = 1.f, ls = 0.f;
+    if (lane < act_dim) {
+      m = mean[(size_t)i * act_ld + lane];
+      ls = logstd[lane];
+      sd = expf(ls);
+      d = sub_rn(an[(size_t)i * act_ld + lane], m);
+    }
+    float z = d / sd;
+    float sq = warp_sum(lane < act_dim ? mul_rn(z, z) : 0.f);
+    float lss = warp_sum(ls);
+    float logp = gaussian_logp(sq, lss, act_dim);
+    float ratio = expf(sub_rn(logp, old_logp[i]));
+    float a = adv[i];
+    float l0 = mul_rn(a, ratio);
+    float rc = fminf(fmaxf(ratio, 1.0f - clip), 1.0f + clip);
+    float l1 = mul_rn(a, rc);
+    float surr = fminf(l0, l1);
+    // d surr / d ratio: through l0 when l0 <= l1, through l1 only inside the clip range (ties split 1/2+1/2)
+    float dr;
+    const bool inside = ratio >= 1.0f - clip && ratio <= 1.0f + clip;
+    if (l0 < l1) dr = a;
+    else if (l0 == l1) dr = 0.5f * a + (inside ? 0.5f * a : 0.f);
+    else dr = inside ? a : 0.f;
+    const float n = (float)max(*cnt, 1);
+    float dlogp = -(dr * ratio) / n;   // actor_loss = -mean(surr)
+    float vmin = fminf(add_rn(m, 1.0f), 0.f), vmax = fmaxf(sub_rn(m, 1.0f), 0.f);
+    float viol = lane < act_dim ? add_rn(mul_rn(vmin, vmin), mul_rn(vmax, vmax)) : 0.f;
+    float viol_sum = warp_sum(viol);
+    if (lane < act_ld) {
+      float g = 0.f;
+      if (on && lane < act_dim) g = dlogp * (d / (sd * sd)) + bound_w * 2.0f * (vmin + vmax) / n;
+      dmean[(size_t)i * act_ld + lane] = g;
+    }
+    if (on) {
+      a_surr = surr; a_clip = fabsf(sub_rn(ratio, 1.0f)) > clip ? 1.0 : 0.0; a_ratio = ratio; a_bound = viol_sum;
+    }
   }
-  float z = d / sd;
-  float sq = warp_sum(lane < act_dim ? mul_rn(z, z) : 0.f);
-  float lss = warp_sum(ls);
-  float logp = gaussian_logp(sq, lss, act_dim);
-  float ratio = expf(sub_rn(logp, old_logp[i]));
-  float a = adv[i];
-  float l0 = mul_rn(a, ratio);
-  float rc = fminf(fmaxf(ratio, 1.0f - clip), 1.0f + clip);
-  float l1 = mul_rn(a, rc);
-  float surr = fminf(l0, l1);
-  // d surr / d ratio: through l0 when l0 <= l1, through l1 only inside the clip range (ties split 1/2+1/2)
-  float dr;
-  const bool inside = ratio >= 1.0f - clip && ratio <= 1.0f + clip;
-  if (l0 < l1) dr = a;
-  else if (l0 == l1) dr = 0.5f * a + (inside ? 0.5f * a : 0.f);
-  else dr = inside ? a : 0.f;
-  const float n = (float)max(*cnt, 1);
-  float dlogp = -(dr * ratio) / n;   // actor_loss = -mean(surr)
-  float vmin = fminf(add_rn(m, 1.0f), 0.f), vmax = fmaxf(sub_rn(m, 1.0f), 0.f);
-  float viol = lane < act_dim ? add_rn(mul_rn(vmin, vmin), mul_rn(vmax, vmax)) : 0.f;
-  float viol_sum = warp_sum(viol);
-  if (lane < act_ld) {
-    float g = 0.f;
-    if (on && lane < act_dim) g = dlogp * (d / (sd * sd)) + bound_w * 2.0f * (vmin + vmax) / n;
-    dmean[(size_t)i * act_ld + lane] = g;
-  }
-  if (lane == 0 && on) {
-    atomicAdd(stats + ST_SURR, (double)surr);
-    atomicAdd(stats + ST_CLIP, fabsf(sub_rn(ratio, 1.0f)) > clip ? 1.0 : 0.0);
-    atomicAdd(stats + ST_RATIO, (double)ratio);
-    atomicAdd(stats + ST_BOUND, (double)viol_sum);
+  if (lane == 0) { s_acc[warp][0] = a_surr; s_acc[warp][1] = a_clip; s_acc[warp][2] = a_ratio; s_acc[warp][3] = a_bound; }
+  __syncthreads();
+  if (threadIdx.x < 4) {          // one atomic per statistic per block instead of one per row
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x / 32); ++w) t += s_acc[w][threadIdx.x];
+    const int slot = threadIdx.x == 0 ? ST_SURR : threadIdx.x == 1 ? ST_CLIP : threadIdx.x == 2 ? ST_RATIO : ST_BOUND;
+    atomicAdd(stats + slot, t);
   }
 }
 
@@ -202,27 +210,45 @@ __global__ void sumsq_kernel(const float* __restrict__ x, long long n, double* _
   if (threadIdx.x == 0) atomicAdd(out, s);
 }
 
-// Bias gradient db[n] = sum over rows of dY[row, n], as `nsplit` partial slabs (slab z at out + z * slab_stride).
-// Block = 256 threads: 32 column-quads x 8 row lanes; 128-bit loads, rows strided by 8 within the block's chunk.
-// With `rw` given, rows are weighted: out[n] = sum_r rw[r] * dY[r, n] -- the weight gradient of a 1-output head.
-__global__ void colsum_slabs_kernel(const float* __restrict__ dY, int ld, int rows, int n, int rows_per_split,
-                                    float* __restrict__ out, long long slab_stride, const float* __restrict__ rw) {
+// Column sums over the minibatch rows: out[n] = sum_r (rw ? rw[r] : 1) * dY[r, n]  -- bias gradients (rw = NULL) and
+// the weight gradient of a 1-output head (rw = d loss / d output).  HBM-bound (reads rows x n floats once).
+// grid = (ceil(n/128), COLSUM_CHUNKS): every block reduces a 128-column x rows/64 patch into `work`; the last block of
+// a column group to finish (ticket counter, self-resetting) adds the 64 partials in a fixed order, writes the total
+// to slab 0 and zeroes slabs 1..nsplit-1 so the common slab reduction stays valid.  Deterministic, no float atomics.
+constexpr int COLSUM_CHUNKS = 64;
+constexpr int COLSUM_MAX_N = 1024;
+__global__ void __launch_bounds__(256) colsum_slabs_kernel(const float* __restrict__ dY, int ld, int rows, int n,
+                                                           float* __restrict__ out, long long slab_stride, int nsplit,
+                                                           const float* __restrict__ rw, float* __restrict__ work,
+                                                           unsigned int* __restrict__ tickets) {
   __shared__ float4 sm[8][32];
+  __shared__ unsigned int s_last;
   const int cq = threadIdx.x & 31, rl = threadIdx.x >> 5;
   const int col = (blockIdx.x * 32 + cq) * 4;
-  const int r0 = blockIdx.y * rows_per_split, r1 = min(rows, r0 + rows_per_split);
+  const int per = (rows + COLSUM_CHUNKS - 1) / COLSUM_CHUNKS;
+  const int r0 = blockIdx.y * per, r1 = min(rows, r0 + per);
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   if (col < n) {
     if (col + 3 < n && (ld & 3) == 0) {
-      for (int r = r0 + rl; r < r1; r += 8) {
+      int r = r0 + rl;
+      for (; r + 24 < r1; r += 32) {          // 4 independent 128-bit loads in flight per thread
+        const float4 v0 = ldg4(dY + (size_t)r * ld + col), v1 = ldg4(dY + (size_t)(r + 8) * ld + col);
+        const float4 v2 = ldg4(dY + (size_t)(r + 16) * ld + col), v3 = ldg4(dY + (size_t)(r + 24) * ld + col);
+        const float w0 = rw ? rw[r] : 1.f, w1 = rw ? rw[r + 8] : 1.f, w2 = rw ? rw[r + 16] : 1.f, w3 = rw ? rw[r + 24] : 1.f;
+        acc.x = fmaf(w0, v0.x, acc.x); acc.y = fmaf(w0, v0.y, acc.y); acc.z = fmaf(w0, v0.z, acc.z); acc.w = fmaf(w0, v0.w, acc.w);
+        acc.x = fmaf(w1, v1.x, acc.x); acc.y = fmaf(w1, v1.y, acc.y); acc.z = fmaf(w1, v1.z, acc.z); acc.w = fmaf(w1, v1.w, acc.w);
+        acc.x = fmaf(w2, v2.x, acc.x); acc.y = fmaf(w2, v2.y, acc.y); acc.z = fmaf(w2, v2.z, acc.z); acc.w = fmaf(w2, v2.w, acc.w);
+        acc.x = fmaf(w3, v3.x, acc.x); acc.y = fmaf(w3, v3.y, acc.y); acc.z = fmaf(w3, v3.z, acc.z); acc.w = fmaf(w3, v3.w, acc.w);
+      }
+      for (; r < r1; r += 8) {
         const float4 v = ldg4(dY + (size_t)r * ld + col);
-        const float w = rw ? rw[r] : 1.0f;
+        const float w = rw ? rw[r] : 1.f;
         acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y); acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
       }
     } else {
       for (int r = r0 + rl; r < r1; r += 8) {
         const float* q = dY + (size_t)r * ld + col;
-        const float w = rw ? rw[r] : 1.0f;
+        const float w = rw ? rw[r] : 1.f;
         acc.x = fmaf(w, q[0], acc.x);
         if (col + 1 < n) acc.y = fmaf(w, q[1], acc.y);
         if (col + 2 < n) acc.z = fmaf(w, q[2], acc.z);
@@ -232,16 +258,36 @@ __global__ void colsum_slabs_kernel(const float* __restrict__ dY, int ld, int ro
   }
   sm[rl][cq] = acc;
   __syncthreads();
-  if (rl == 0 && col < n) {
+  if (rl == 0) {
     float4 t = sm[0][cq];
 #pragma unroll
     for (int i = 1; i < 8; ++i) { t.x += sm[i][cq].x; t.y += sm[i][cq].y; t.z += sm[i][cq].z; t.w += sm[i][cq].w; }
-    float* o = out + (size_t)blockIdx.y * slab_stride + col;
-    o[0] = t.x;
-    if (col + 1 < n) o[1] = t.y;
-    if (col + 2 < n) o[2] = t.z;
-    if (col + 3 < n) o[3] = t.w;
+    *reinterpret_cast<float4*>(work + ((size_t)blockIdx.y * COLSUM_MAX_N + blockIdx.x * 128 + cq * 4)) = t;
   }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(tickets + blockIdx.x, 1u) == COLSUM_CHUNKS - 1) ? 1u : 0u;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int ch = rl; ch < COLSUM_CHUNKS; ch += 8) {
+    const float4 v = __ldcg(reinterpret_cast<const float4*>(work + ((size_t)ch * COLSUM_MAX_N + blockIdx.x * 128 + cq * 4)));
+    t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+  }
+  sm[rl][cq] = t;
+  __syncthreads();
+  if (rl == 0 && col < n) {
+    t = sm[0][cq];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) { t.x += sm[i][cq].x; t.y += sm[i][cq].y; t.z += sm[i][cq].z; t.w += sm[i][cq].w; }
+    const float tv[4] = {t.x, t.y, t.z, t.w};
+    for (int e = 0; e < 4 && col + e < n; ++e) {
+      out[col + e] = tv[e];
+      for (int z = 1; z < nsplit; ++z) out[(size_t)z * slab_stride + col + e] = 0.f;
+    }
+  }
+  if (threadIdx.x == 0) tickets[blockIdx.x] = 0u;
 }
 
 // 1-output head forward: out[r] = dot(X[r, :], w) + b   (critic value, discriminator logit); warp per row
@@ -365,6 +411,15 @@ __global__ void obs_normalize_kernel(const float* __restrict__ x, const float* _
   }
 }
 
+// wd0_pad[r, c] = c < dim ? W[r, c] : 0 : the discriminator's first-layer weight with 16-byte aligned rows, so that
+// TMA can address it (disc_obs_dim = 114 floats = 456 bytes per row is not a legal tensor-map stride)
+__global__ void pad_rows_kernel(const float* __restrict__ w, int rows, int dim, int ld, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * ld) return;
+  const int r = i / ld, c = i - r * ld;
+  out[i] = c < dim ? w[(size_t)r * dim + c] : 0.f;
+}
+
 __global__ void diff_normalize_kernel(const float* __restrict__ dobs, const float* __restrict__ demo,
                                       const float* __restrict__ mean_abs, long long rows, int dim, int ld,
                                       float* __restrict__ out) {
@@ -379,6 +434,18 @@ __global__ void diff_normalize_kernel(const float* __restrict__ dobs, const floa
 using namespace addk;
 typedef addk_update_ctx Ctx;
 #define F(p) ((float*)(p))
+
+static int colsum(cudaStream_t st, const addk_update_ctx& c, const float* dY, int ld, int rows, int n, float* out,
+                  const float* rw) {
+  using addk::COLSUM_MAX_N; using addk::COLSUM_CHUNKS;
+  if (n > COLSUM_MAX_N) { addk_set_error("colsum: more than 1024 columns"); return ADDK_ERR_UNSUPPORTED; }
+  float* work = (float*)c.colsum_work;
+  unsigned int* tickets = (unsigned int*)(work + (size_t)COLSUM_CHUNKS * COLSUM_MAX_N);
+  addk::colsum_slabs_kernel<<<dim3((n + 127) / 128, COLSUM_CHUNKS), 256, 0, st>>>(dY, ld, rows, n, out, c.num_params,
+                                                                         (int)c.split_k, rw, work, tickets);
+  ADDK_CHECK_LAUNCH();
+  return ADDK_OK;
+}
 
 static int gemm(cudaStream_t st, int prec, const float* A, int lda, int ta, const float* B, int ldb, int tb, float* C,
                 int ldc, int M, int N, int K, const float* bias = nullptr, int relu = 0, const float* mask = nullptr,
@@ -401,18 +468,13 @@ static int wgrad(cudaStream_t st, const Ctx& c, const float* dY, int ldy, const 
   const int S = (int)c.split_k;
   const long long P = c.num_params;
   if (n_out == 1 && ldy == 1) {
-    colsum_slabs_kernel<<<dim3((k_in + 127) / 128, S), 256, 0, st>>>(X, ldx, rows, k_in, (rows + S - 1) / S,
-                                                                   F(c.slabs) + (size_t)slab0 * P + o_w, P, dY);
-    ADDK_CHECK_LAUNCH();
+    TRY(colsum(st, c, X, ldx, rows, k_in, F(c.slabs) + (size_t)slab0 * P + o_w, dY));
   } else {
     TRY(gemm(st, (int)c.precision, dY, ldy, 1, X, ldx, 0, F(c.slabs) + (size_t)slab0 * P + o_w, k_in, n_out, k_in, rows,
              nullptr, 0, nullptr, 0, S, nullptr, nullptr, P));
   }
   if (o_b >= 0) {
-    const int rps = (rows + S - 1) / S;
-    colsum_slabs_kernel<<<dim3((n_out + 127) / 128, S), 256, 0, st>>>(dY, ldy, rows, n_out, rps,
-                                                                    F(c.slabs) + (size_t)slab0 * P + o_b, P, nullptr);
-    ADDK_CHECK_LAUNCH();
+    TRY(colsum(st, c, dY, ldy, rows, n_out, F(c.slabs) + (size_t)slab0 * P + o_b, nullptr));
   }
   return ADDK_OK;
 }
@@ -525,7 +587,10 @@ extern "C" int addk_update_minibatch(void* stream, void* ctx_host, const long lo
 
   // ---------------- discriminator (R = M + 1 rows) ----------------
   float *e1 = F(c.h1), *e2 = F(c.h3), *dh2 = F(c.g3), *dv1 = F(c.g1), *du2 = F(c.g2);
-  TRY(gemm(st, pr, F(c.dn), DL, 0, W + c.o_d_w0, DD, 1, e1, E1, R, E1, DD, W + c.o_d_b0, 1));
+  const float* Wd0 = F(c.wd0_pad);
+  pad_rows_kernel<<<(E1 * DL + 255) / 256, 256, 0, st>>>(W + c.o_d_w0, E1, DD, DL, F(c.wd0_pad));
+  ADDK_CHECK_LAUNCH();
+  TRY(gemm(st, pr, F(c.dn), DL, 0, Wd0, DL, 1, e1, E1, R, E1, DL, W + c.o_d_b0, 1));
   TRY(gemm(st, pr, e1, E1, 0, W + c.o_d_w1, E1, 1, e2, E2, R, E2, E1, W + c.o_d_b1, 1));
   TRY(head1_forward(st, e2, E2, R, E2, W + c.o_d_wl, W + c.o_d_bl, F(c.pred)));
   disc_loss_kernel<<<(R + 255) / 256, 256, 0, st>>>(F(c.pred), M, (float)c.disc_loss_weight, F(c.dpred), stats);
@@ -538,20 +603,18 @@ extern "C" int addk_update_minibatch(void* stream, void* ctx_host, const long lo
   }
   // input-gradient chain: u1 = m1 * (u2 W2), gx = u1 W1
   TRY(gemm(st, pr, F(c.u2), E2, 0, W + c.o_d_w1, E1, 0, F(c.u1), E1, R, E1, E2, nullptr, 0, e1, E1));
-  TRY(gemm(st, pr, F(c.u1), E1, 0, W + c.o_d_w0, DD, 0, F(c.gx), DL, R, DD, E1));
+  TRY(gemm(st, pr, F(c.u1), E1, 0, Wd0, DL, 0, F(c.gx), DL, R, DL, E1));
   grad_penalty_kernel<<<(R + 7) / 8, 256, 0, st>>>(F(c.gx), M, R, DD, DL,
                                                    (float)(c.disc_loss_weight * c.disc_grad_penalty), F(c.dg), stats);
   ADDK_CHECK_LAUNCH();
   // backward of the chain (second set of slabs)
   TRY(gemm(st, pr, F(c.u1), E1, 1, F(c.dg), DL, 0, F(c.slabs) + (size_t)S * P + c.o_d_w0, DD, E1, DD, R, nullptr, 0,
            nullptr, 0, S, nullptr, nullptr, P));
-  TRY(gemm(st, pr, F(c.dg), DL, 0, W + c.o_d_w0, DD, 1, dv1, E1, R, E1, DD, nullptr, 0, e1, E1));
+  TRY(gemm(st, pr, F(c.dg), DL, 0, Wd0, DL, 1, dv1, E1, R, E1, DL, nullptr, 0, e1, E1));
   TRY(gemm(st, pr, F(c.u2), E2, 1, dv1, E1, 0, F(c.slabs) + (size_t)S * P + c.o_d_w1, E1, E2, E1, R, nullptr, 0, nullptr, 0,
            S, nullptr, nullptr, P));
   TRY(gemm(st, pr, dv1, E1, 0, W + c.o_d_w1, E1, 1, du2, E2, R, E2, E1, nullptr, 0, e2, E2));
-  colsum_slabs_kernel<<<dim3((E2 + 127) / 128, S), 256, 0, st>>>(du2, E2, R, E2, (R + S - 1) / S,
-                                                                 F(c.slabs) + (size_t)S * P + c.o_d_wl, P, nullptr);
-  ADDK_CHECK_LAUNCH();
+  TRY(colsum(st, c, du2, E2, R, E2, F(c.slabs) + (size_t)S * P + c.o_d_wl, nullptr));
   // ordinary backward of the BCE terms
   TRY(wgrad(st, c, F(c.dpred), 1, e2, E2, R, 1, E2, c.o_d_wl, c.o_d_bl, 0));
   TRY(wgrad(st, c, dh2, E2, e1, E1, R, E2, E1, c.o_d_w1, c.o_d_b1, 0));
@@ -638,13 +701,15 @@ extern "C" int addk_disc_eval(void* stream, void* ctx_host, const float* disc_ob
   const long long chunk = c.mb_rows;
   const float* W = F(c.params);
   float *e1 = F(c.h1), *e2 = F(c.h3);
+  pad_rows_kernel<<<(E1 * DL + 255) / 256, 256, 0, st>>>(W + c.o_d_w0, E1, DD, DL, F(c.wd0_pad));
+  ADDK_CHECK_LAUNCH();
   for (long long r0 = 0; r0 < n; r0 += chunk) {
     int rows = (int)((n - r0 < chunk) ? n - r0 : chunk);
     long long tot = (long long)rows * DL;
     diff_normalize_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(disc_obs + r0 * DD, disc_obs_demo + r0 * DD,
                                                                         F(c.disc_mean_abs), rows, DD, DL, F(c.gx));
     ADDK_CHECK_LAUNCH();
-    TRY(gemm(st, pr, F(c.gx), DL, 0, W + c.o_d_w0, DD, 1, e1, E1, rows, E1, DD, W + c.o_d_b0, 1));
+    TRY(gemm(st, pr, F(c.gx), DL, 0, F(c.wd0_pad), DL, 1, e1, E1, rows, E1, DL, W + c.o_d_b0, 1));
     TRY(gemm(st, pr, e1, E1, 0, W + c.o_d_w1, E1, 1, e2, E2, rows, E2, E1, W + c.o_d_b1, 1));
     TRY(head1_forward(st, e2, E2, rows, E2, W + c.o_d_wl, W + c.o_d_bl, logits + r0));
   }
