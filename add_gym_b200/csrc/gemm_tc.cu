@@ -421,6 +421,300 @@ static bool make_map(CUtensorMap* map, const float* ptr, long long inner, long l
   return r == CUDA_SUCCESS;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// tf32x3 ("fp32-parity") kernel.  Same TMA / tcgen05 pipeline as above plus two things the accuracy bar needs:
+//  * the cross terms lo.hi + hi.lo go to a second TMEM accumulator;
+//  * the main accumulator is DRAINED into fp32 registers every X3_CHUNK_KB k-blocks (K = 256): the tensor core
+//    truncates its accumulator after every instruction (measured bias -1.64e-8 per accumulated MMA, i.e. -2.1e-6 at
+//    K = 1024), so the tensor core only ever sums 32 instructions and the CUDA cores add the chunks with
+//    round-to-nearest -> 5e-7, the level of an fp32 FMA loop.
+// 10 warps: 0 = TMA producer, 1 = MMA issuer / TMEM allocator, 2..9 = workers (hi/lo split of every landed tile,
+// chunk drains, epilogue).  Worker w owns TMEM lanes 32*(w%4).. and column half (w-2)/4, BN/2 running sums per thread.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int X3_THREADS = 320;
+constexpr int X3_CHUNK_KB = 16;
+
+template <int BN>
+__global__ void __launch_bounds__(X3_THREADS, 1)
+gemm_tc_x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
+  using C = Cfg<BN, true>;
+  constexpr int BK = C::BK;
+  constexpr int CPW = BN / 2;                     // accumulator columns per worker thread
+  constexpr int NCH = CPW / 32;                   // 32-column chunks per worker
+  static_assert(CPW % 32 == 0, "BN must be a multiple of 64");
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_u32 = smem_u32(smem_raw);
+  const uint32_t base = (raw_u32 + 1023u) & ~1023u;
+  uint8_t* const base_ptr = smem_raw + (base - raw_u32);
+  const uint32_t bars = base + C::STAGES * C::STAGE_BYTES;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (C::STAGES + s); };
+  auto ready_bar = [&](int s) { return bars + 8u * (2 * C::STAGES + s); };
+  const uint32_t tmem_full_bar = bars + 8u * (3 * C::STAGES);
+  const uint32_t chunk_full_bar = bars + 8u * (3 * C::STAGES + 1);
+  const uint32_t chunk_empty_bar = bars + 8u * (3 * C::STAGES + 2);
+  const uint32_t tmem_ptr_addr = bars + 8u * (3 * C::STAGES + 3);
+  auto a_hi = [&](int s) { return base + (uint32_t)s * C::STAGE_BYTES; };
+  auto b_hi = [&](int s) { return a_hi(s) + C::A_BYTES; };
+  auto a_lo = [&](int s) { return b_hi(s) + C::B_BYTES; };
+  auto b_lo = [&](int s) { return a_lo(s) + C::A_BYTES; };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int kb_total = (p.K + BK - 1) / BK;
+  const int kb_begin = blockIdx.z * p.kb_per_split;
+  const int kb_end = min(kb_total, kb_begin + p.kb_per_split);
+  const int num_kb = kb_end - kb_begin;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+      mbar_init(ready_bar(s), 256);
+    }
+    mbar_init(tmem_full_bar, 1);
+    mbar_init(chunk_full_bar, 1);
+    mbar_init(chunk_empty_bar, 256);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "r"((uint32_t)C::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr) : "memory");
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int i = 0; i < num_kb; ++i) {
+        const int s = i % C::STAGES;
+        const uint32_t ph = (uint32_t)(i / C::STAGES) & 1u;
+        mbar_wait(empty_bar(s), ph ^ 1u);
+        mbar_expect_tx(full_bar(s), C::A_BYTES + C::B_BYTES);
+        const int k0 = (kb_begin + i) * BK;
+        if (!p.a_mn) {
+          tma_load_2d(a_hi(s), &tmA, full_bar(s), k0, m0);
+        } else {
+#pragma unroll
+          for (int j = 0; j < BM / 32; ++j) tma_load_2d(a_hi(s) + j * C::MN_BOX_BYTES, &tmA, full_bar(s), m0 + 32 * j, k0);
+        }
+        if (!p.b_mn) {
+          tma_load_2d(b_hi(s), &tmB, full_bar(s), k0, n0);
+        } else {
+#pragma unroll
+          for (int j = 0; j < BN / 32; ++j) tma_load_2d(b_hi(s) + j * C::MN_BOX_BYTES, &tmB, full_bar(s), n0 + 32 * j, k0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.a_mn ? 1 : 0) << 15) |
+                             ((uint32_t)(p.b_mn ? 1 : 0) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      const uint32_t a_lbo = p.a_mn ? C::MN_BOX_BYTES : 16u, b_lbo = p.b_mn ? C::MN_BOX_BYTES : 16u;
+      const uint32_t a_sbo = p.a_mn ? 512u : C::K_SBO, b_sbo = p.b_mn ? 512u : C::K_SBO;
+      const uint32_t a_lay = p.a_mn ? 1u : C::K_LAYOUT, b_lay = p.b_mn ? 1u : C::K_LAYOUT;
+      const uint32_t a_kstep = p.a_mn ? 1024u : 32u, b_kstep = p.b_mn ? 1024u : 32u;
+      uint32_t acc = 0, acc_x = 0;
+      for (int i = 0; i < num_kb; ++i) {
+        const int s = i % C::STAGES;
+        const uint32_t ph = (uint32_t)(i / C::STAGES) & 1u;
+        const bool new_chunk = (i % X3_CHUNK_KB == 0) && i > 0;
+        // cross terms first at a chunk boundary: they go to the other accumulator and overlap the drain
+        mbar_wait(ready_bar(s), ph);
+        tc_fence_after();
+#pragma unroll
+        for (int ks = 0; ks < BK / UMMA_K; ++ks) {
+          const uint64_t dah = smem_desc(a_hi(s) + ks * a_kstep, a_lbo, a_sbo, a_lay);
+          const uint64_t dbh = smem_desc(b_hi(s) + ks * b_kstep, b_lbo, b_sbo, b_lay);
+          const uint64_t dal = smem_desc(a_lo(s) + ks * a_kstep, a_lbo, a_sbo, a_lay);
+          const uint64_t dbl = smem_desc(b_lo(s) + ks * b_kstep, b_lbo, b_sbo, b_lay);
+          umma_tf32(tmem_base + BN, dal, dbh, idesc, acc_x);
+          acc_x = 1;
+          umma_tf32(tmem_base + BN, dah, dbl, idesc, acc_x);
+        }
+        if (new_chunk) {                       // the workers have copied the previous chunk out of the main accumulator
+          mbar_wait(chunk_empty_bar, (uint32_t)(i / X3_CHUNK_KB - 1) & 1u);
+          tc_fence_after();
+          acc = 0;
+        }
+#pragma unroll
+        for (int ks = 0; ks < BK / UMMA_K; ++ks) {
+          umma_tf32(tmem_base, smem_desc(a_hi(s) + ks * a_kstep, a_lbo, a_sbo, a_lay),
+                    smem_desc(b_hi(s) + ks * b_kstep, b_lbo, b_sbo, b_lay), idesc, acc);
+          acc = 1;
+        }
+        umma_commit(empty_bar(s));
+        if (((i + 1) % X3_CHUNK_KB == 0) && (i + 1 < num_kb)) umma_commit(chunk_full_bar);
+      }
+      umma_commit(tmem_full_bar);
+    }
+  } else {
+    // ===================== workers: warps 2..9 =====================
+    const int t = threadIdx.x - 64;          // 0..255
+    const int q = warp & 3;                  // TMEM lane quarter
+    const int half = (warp - 2) >> 2;        // column half
+    const uint32_t t_main = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(half * CPW);
+    float acc[CPW];
+#pragma unroll
+    for (int j = 0; j < CPW; ++j) acc[j] = 0.f;
+    constexpr int N4 = (C::A_BYTES + C::B_BYTES) / 16;
+    constexpr int PER = N4 / 256;
+    static_assert(N4 % 256 == 0, "tile size");
+    for (int i = 0; i < num_kb; ++i) {
+      const int s = i % C::STAGES;
+      const uint32_t ph = (uint32_t)(i / C::STAGES) & 1u;
+      mbar_wait(full_bar(s), ph);
+      const float4* src = reinterpret_cast<const float4*>(base_ptr + (size_t)s * C::STAGE_BYTES);
+      float4* dst = reinterpret_cast<float4*>(base_ptr + (size_t)s * C::STAGE_BYTES + C::A_BYTES + C::B_BYTES);
+      float4 x[PER];
+#pragma unroll
+      for (int u = 0; u < PER; ++u) x[u] = src[t + 256 * u];
+#pragma unroll
+      for (int u = 0; u < PER; ++u) {
+        float4 l;
+        l.x = x[u].x - __uint_as_float(__float_as_uint(x[u].x) & 0xFFFFE000u);
+        l.y = x[u].y - __uint_as_float(__float_as_uint(x[u].y) & 0xFFFFE000u);
+        l.z = x[u].z - __uint_as_float(__float_as_uint(x[u].z) & 0xFFFFE000u);
+        l.w = x[u].w - __uint_as_float(__float_as_uint(x[u].w) & 0xFFFFE000u);
+        dst[t + 256 * u] = l;
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_arrive(ready_bar(s));
+      if ((i % X3_CHUNK_KB == 0) && i > 0) {   // drain the chunk that ended with k-block i-1
+        mbar_wait(chunk_full_bar, (uint32_t)(i / X3_CHUNK_KB - 1) & 1u);
+        tc_fence_after();
+#pragma unroll
+        for (int cc = 0; cc < NCH; ++cc) {
+          uint32_t v[32];
+          tmem_ld32(t_main + (uint32_t)(cc * 32), v);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[cc * 32 + j] += __uint_as_float(v[j]);
+        }
+        tc_fence_before();
+        mbar_arrive(chunk_empty_bar);
+      }
+    }
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+#pragma unroll
+    for (int cc = 0; cc < NCH; ++cc) {         // last chunk of the main accumulator + the cross-term accumulator
+      uint32_t v[32];
+      tmem_ld32(t_main + (uint32_t)(cc * 32), v);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) acc[cc * 32 + j] += __uint_as_float(v[j]);
+      tmem_ld32(t_main + (uint32_t)(BN + cc * 32), v);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) acc[cc * 32 + j] += __uint_as_float(v[j]);
+    }
+    // ---- epilogue: 32 x 32 chunks transposed through a 4 KB swizzled buffer per warp, coalesced 128-bit stores
+    float* Cz = p.C + (size_t)blockIdx.z * p.slab_stride;
+    const bool vec = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(Cz) & 15) == 0) &&
+                     (!p.bias || ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0)) &&
+                     (!p.mask || (((p.ld_mask & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.mask) & 15) == 0)));
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    float4* stg = reinterpret_cast<float4*>(base_ptr + 4096 * (warp - 2));
+    const int l_row = lane >> 3, l_c4 = lane & 7;
+    const int row = m0 + 32 * q + lane;
+#pragma unroll
+    for (int cc = 0; cc < NCH; ++cc) {
+      const int cbase = n0 + half * CPW + cc * 32;
+      if (cbase < p.N) {                       // warp-uniform
+        if (vec) {
+          const int col = cbase + 4 * l_c4;
+          const bool full4 = col + 3 < p.N;
+          float4 m4[8];
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int grow = m0 + 32 * q + it * 4 + l_row;
+            m4[it] = make_float4(1.f, 1.f, 1.f, 1.f);
+            if (p.mask && full4 && grow < p.M) m4[it] = *reinterpret_cast<const float4*>(p.mask + (size_t)grow * p.ld_mask + col);
+          }
+#pragma unroll
+          for (int c4 = 0; c4 < 8; ++c4)
+            stg[lane * 8 + (c4 ^ (lane & 7))] = make_float4(acc[cc * 32 + 4 * c4], acc[cc * 32 + 4 * c4 + 1],
+                                                            acc[cc * 32 + 4 * c4 + 2], acc[cc * 32 + 4 * c4 + 3]);
+          __syncwarp();
+          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.bias) {
+            if (full4) b4 = *reinterpret_cast<const float4*>(p.bias + col);
+            else { if (col < p.N) b4.x = p.bias[col]; if (col + 1 < p.N) b4.y = p.bias[col + 1]; if (col + 2 < p.N) b4.z = p.bias[col + 2]; }
+          }
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int r = it * 4 + l_row;
+            const int grow = m0 + 32 * q + r;
+            float4 o = stg[r * 8 + (l_c4 ^ (r & 7))];
+            if (grow < p.M && col < p.N) {
+              o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
+              if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+              float* dstp = Cz + (size_t)grow * p.ldc + col;
+              if (full4) {
+                o.x = m4[it].x > 0.f ? o.x : 0.f; o.y = m4[it].y > 0.f ? o.y : 0.f;
+                o.z = m4[it].z > 0.f ? o.z : 0.f; o.w = m4[it].w > 0.f ? o.w : 0.f;
+                if (p.accumulate) {
+                  const float4 c4 = *reinterpret_cast<const float4*>(dstp);
+                  o.x += c4.x; o.y += c4.y; o.z += c4.z; o.w += c4.w;
+                }
+                *reinterpret_cast<float4*>(dstp) = o;
+              } else {
+                const float oo[4] = {o.x, o.y, o.z, o.w};
+                for (int e = 0; e < 4 && col + e < p.N; ++e) {
+                  float xv = oo[e];
+                  if (p.mask) xv = p.mask[(size_t)grow * p.ld_mask + col + e] > 0.f ? xv : 0.f;
+                  if (p.accumulate) xv += dstp[e];
+                  dstp[e] = xv;
+                }
+              }
+            }
+          }
+          __syncwarp();
+        } else if (row < p.M) {
+          float* dstp = Cz + (size_t)row * p.ldc + cbase;
+          const float* mk = p.mask ? p.mask + (size_t)row * p.ld_mask + cbase : nullptr;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int col = cbase + j;
+            if (col < p.N) {
+              float xv = acc[cc * 32 + j];
+              if (p.bias) xv += p.bias[col];
+              if (p.relu) xv = fmaxf(xv, 0.f);
+              if (mk) xv = mk[j] > 0.f ? xv : 0.f;
+              if (p.accumulate) xv += dstp[j];
+              dstp[j] = xv;
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS) : "memory");
+  }
+}
+
+template <int BN>
+static int launch_x3(cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, dim3 grid) {
+  using C = Cfg<BN, true>;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(gemm_tc_x3_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES) != cudaSuccess) {
+      addk_set_error("gemm_tc: cannot raise the dynamic shared memory limit");
+      return ADDK_ERR_LAUNCH;
+    }
+    configured = true;
+  }
+  gemm_tc_x3_kernel<BN><<<grid, X3_THREADS, C::SMEM_BYTES, st>>>(ta, tb, p);
+  return ADDK_OK;
+}
+
 template <int BN, bool X3>
 static int launch(cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, dim3 grid) {
   using C = Cfg<BN, X3>;
@@ -470,7 +764,7 @@ int addk_gemm_tc(cudaStream_t st, const addk_gemm_args& a, int precision) {
   ok = ok && (p.b_mn ? make_map(&tb, a.B, a.N, a.K, a.ldb, 32, BK, true) : make_map(&tb, a.B, a.K, a.N, a.ldb, BK, BN, false));
   if (!ok) return addk::sgemm_launch(st, a);
   dim3 grid((a.N + BN - 1) / BN, (a.M + BM - 1) / BM, split);
-  if (BN == 256) return x3 ? launch<256, true>(st, ta, tb, p, grid) : launch<256, false>(st, ta, tb, p, grid);
-  if (BN == 128) return x3 ? launch<128, true>(st, ta, tb, p, grid) : launch<128, false>(st, ta, tb, p, grid);
-  return x3 ? launch<64, true>(st, ta, tb, p, grid) : launch<64, false>(st, ta, tb, p, grid);
+  if (BN == 256) return x3 ? launch_x3<256>(st, ta, tb, p, grid) : launch<256, false>(st, ta, tb, p, grid);
+  if (BN == 128) return x3 ? launch_x3<128>(st, ta, tb, p, grid) : launch<128, false>(st, ta, tb, p, grid);
+  return x3 ? launch_x3<64>(st, ta, tb, p, grid) : launch<64, false>(st, ta, tb, p, grid);
 }
