@@ -433,6 +433,11 @@ static bool make_map(CUtensorMap* map, const float* ptr, long long inner, long l
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int X3_THREADS = 320;
 constexpr int X3_CHUNK_KB = 16;
+// Expected truncation loss of the tensor core's accumulator per accumulated instruction, relative to the chunk sum
+// (measured on B200 with tf32-exact operands: -1.68e-8 .. -2.1e-8 per instruction for 4..2048 instructions,
+// tools/tc_accuracy.py).  The drain adds it back, which removes the systematic part of the bias (-5.4e-7 per
+// 32-instruction chunk) and leaves the random part (~3e-7).
+constexpr float X3_TRUNC_LOSS_PER_MMA = 1.7e-8f;
 
 template <int BN>
 __global__ void __launch_bounds__(X3_THREADS, 1)
@@ -588,12 +593,13 @@ gemm_tc_x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       if ((i % X3_CHUNK_KB == 0) && i > 0) {   // drain the chunk that ended with k-block i-1
         mbar_wait(chunk_full_bar, (uint32_t)(i / X3_CHUNK_KB - 1) & 1u);
         tc_fence_after();
+        const float comp = X3_TRUNC_LOSS_PER_MMA * (float)(X3_CHUNK_KB * (BK / UMMA_K));
 #pragma unroll
         for (int cc = 0; cc < NCH; ++cc) {
           uint32_t v[32];
           tmem_ld32(t_main + (uint32_t)(cc * 32), v);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) acc[cc * 32 + j] += __uint_as_float(v[j]);
+          for (int j = 0; j < 32; ++j) acc[cc * 32 + j] += fmaf(__uint_as_float(v[j]), comp, __uint_as_float(v[j]));
         }
         tc_fence_before();
         mbar_arrive(chunk_empty_bar);
@@ -601,12 +607,13 @@ gemm_tc_x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
+    const float comp_last = X3_TRUNC_LOSS_PER_MMA * (float)((((num_kb - 1) % X3_CHUNK_KB) + 1) * (BK / UMMA_K));
 #pragma unroll
     for (int cc = 0; cc < NCH; ++cc) {         // last chunk of the main accumulator + the cross-term accumulator
       uint32_t v[32];
       tmem_ld32(t_main + (uint32_t)(cc * 32), v);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) acc[cc * 32 + j] += __uint_as_float(v[j]);
+      for (int j = 0; j < 32; ++j) acc[cc * 32 + j] += fmaf(__uint_as_float(v[j]), comp_last, __uint_as_float(v[j]));
       tmem_ld32(t_main + (uint32_t)(BN + cc * 32), v);
 #pragma unroll
       for (int j = 0; j < 32; ++j) acc[cc * 32 + j] += __uint_as_float(v[j]);
