@@ -260,6 +260,7 @@ def run_b200(args):
 
     # ---- dominant kernel: the dense-layer contraction of the update, timed launch by launch --------------------
     roof = dominant_kernel_roofline(agent, args, hbm_peak, tc_peak, peak_src) if rank == 0 else None
+    hbm_roof = step_kernel_roofline(agent, hbm_peak) if rank == 0 else None
     del agent
     torch.cuda.empty_cache()
 
@@ -308,7 +309,7 @@ def run_b200(args):
     try:
         os.makedirs(os.path.dirname(args.stages_out), exist_ok=True)
         with open(args.stages_out, "w") as f:
-            json.dump({"stages": stages, "roofline": roof, "clocks": clk}, f, indent=1)
+            json.dump({"stages": stages, "roofline": roof, "roofline_hbm_stage": hbm_roof, "clocks": clk}, f, indent=1)
     except OSError:
         pass
     print("stages: " + json.dumps(stages), file=sys.stderr, flush=True)
@@ -326,12 +327,41 @@ def run_b200(args):
                          (T * N * (264 * 2 + 114 * 2 + 29 + 8) * 4 / 1e6),
                    "ppo_update_samples_per_s": stages["ppo_update_samples_per_s"],
                    "physics_ms_per_step_excluded": phys / K * 1e3},
-        "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
+        "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "roofline_hbm_stage": hbm_roof,
+        "cpu_baseline": cpu,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def step_kernel_roofline(agent, hbm_peak):
+    """The HBM-bound stage: the fused per-env step kernel (csrc/step.cu), 5,624 algorithmic bytes per env-step
+    (SURVEY 8d), timed launch by launch with CUDA events while it writes successive experience rows."""
+    import torch
+    from add_gym_b200 import _lib
+    core, N, T = agent._core, agent.get_num_envs(), agent._steps_per_iter
+    flags = _lib.F_ADVANCE | _lib.F_UPDATE_MOTION | _lib.F_REWARD_DONE
+    for t in range(3):
+        core.step(flags, exp_row=agent._exp_row(t % T))
+    torch.cuda.synchronize()
+    reps = 20
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    for i, (a, b) in enumerate(evs):
+        row = agent._exp_row(i % T)
+        sim = core.sim_struct()          # noqa: F841  (struct assembly is host work, outside the events)
+        a.record()
+        core.step(flags, exp_row=row)
+        b.record()
+    torch.cuda.synchronize()
+    ms = sorted(a.elapsed_time(b) for a, b in evs)[reps // 2]
+    nbytes = 5624.0 * N
+    achieved = nbytes / (ms * 1e-3) / 1e9
+    return {"bound": "hbm", "kernel": "env_step_kernel (fused obs/disc-obs/reward/done/record)", "achieved": achieved,
+            "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None, "median_launch_ms": ms,
+            "algorithmic_bytes_per_launch": nbytes, "envs": N,
+            "note": "event pair around one ctypes call: includes ~5 us of launch latency; meaningful at N >= 32768"}
 
 
 def dominant_kernel_roofline(agent, args, hbm_peak, tc_peak, peak_src):

@@ -1,9 +1,9 @@
 """GPU: the dense-layer contraction (addk_gemm) in every operand layout the MLP forward / backward uses, for the
 exact-fp32 CUDA-core kernel and the tcgen05 tensor-core modes, against a float64 torch reference.
 
-Tolerances (norm-wise relative error vs float64): fp32 2e-6; tf32x3 (3-pass split, the fp32-parity tensor-core mode)
-1e-5 -- its error is the tensor core's truncating fp32 accumulator, measured at -2.05e-9 x K (K <= 2048 here); tf32
-(single pass, operands truncated to 10 mantissa bits) 2e-3.
+Tolerances (norm-wise relative error vs float64): fp32 2e-6; tf32x3 (3-pass split with the main accumulator drained
+into fp32 registers every 256 k, the fp32-parity tensor-core mode) 2e-6 as well -- measured 3.3e-7 at any K; tf32
+(single pass, operands truncated to 10 mantissa bits, accumulator truncation -2.05e-9 x K) 2e-3.
 """
 import ctypes as C
 
@@ -12,7 +12,7 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
-TOL = {"fp32": 2e-6, "tf32x3": 1e-5, "tf32": 2e-3}
+TOL = {"fp32": 2e-6, "tf32x3": 2e-6, "tf32": 2e-3}
 
 
 def _gemm(A, B, Cout, M, N, K, ta, tb, prec, bias=None, relu=0, mask=None, split=1, accumulate=0, lda=None, ldb=None):
@@ -92,7 +92,7 @@ def test_gemm_epilogues_and_split_k(prec):
 
 def test_tensor_core_split_is_fp32_class_on_mlp_scale_data():
     """tf32x3 on data shaped like the MLP activations (non-negative post-ReLU inputs, 1/sqrt(K) weights): the error
-    must stay inside the 1e-5 parity bar with margin (K = 1024: accumulator truncation ~2.5e-6)."""
+    must stay an order of magnitude inside the 1e-5 parity bar so the stacked layers still meet it."""
     g = torch.Generator(device="cuda").manual_seed(3)
     M, N, K = 4096, 1024, 1024
     A = torch.relu(torch.randn(M, K, device="cuda", generator=g))
@@ -100,4 +100,4 @@ def test_tensor_core_split_is_fp32_class_on_mlp_scale_data():
     out = torch.empty(M, N, device="cuda")
     _gemm(A, W, out, M, N, K, 0, 1, "tf32x3")
     e = _rel(out, A.double() @ W.double().t())
-    assert e <= 4e-6, e
+    assert e <= 1e-6, e
