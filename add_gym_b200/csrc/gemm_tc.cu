@@ -22,6 +22,7 @@
 #include "addk.h"
 #include <cuda.h>
 #include <cudaTypedefs.h>
+#include <stdlib.h>
 
 namespace addk { int sgemm_launch(cudaStream_t st, const addk_gemm_args& a); }
 
@@ -722,6 +723,365 @@ static int launch_x3(cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& 
   return ADDK_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// tf32x3, CTA-pair version (tcgen05 cta_group::2): a cluster of two CTAs on one TPC computes a 256 x 256 tile.
+// Each CTA stages its own 128 rows of A and its own 128-row half of B; the leader CTA's single thread issues
+// M = 256 MMAs that read both CTAs' shared memory, so per CTA the operand traffic per k-block drops from
+// (128 + 256) to (128 + 128) rows -- less L2->smem traffic, less splitting work, 1/3 fewer operand bytes per MMA.
+// Everything else (hi/lo split, second accumulator for the cross terms, chunked drain, coalesced epilogue) is the
+// 1-CTA kernel above; each CTA drains / stores its own 128 accumulator rows.
+// Barriers: full/empty are CTA-local (local TMA; multicast tcgen05.commit frees the stage in both CTAs);
+// ready / chunk_empty live in the leader and collect one arrival per worker warp of BOTH CTAs (remote arrive).
+// ---------------------------------------------------------------------------------------------------------------
+struct Cfg2 {
+  static constexpr int BN = 256;                  // tile N; each CTA stages BN/2 rows of B
+  static constexpr int BK = 16;
+  static constexpr int A_BYTES = BM * BK * 4;     // 8 KB
+  static constexpr int B_BYTES = (BN / 2) * BK * 4;
+  static constexpr int STAGE_BYTES = 2 * (A_BYTES + B_BYTES);
+  static constexpr int STAGES = 6;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+  static constexpr int TMEM_COLS = 512;
+  static constexpr uint32_t K_LAYOUT = 4u;
+  static constexpr uint32_t K_SBO = 8u * BK * 4u;
+  static constexpr uint32_t MN_BOX_BYTES = BK * 128u;
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_rank0(uint32_t addr) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(r) : "r"(addr));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait_cluster(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+__device__ __forceinline__ void umma_tf32_2cta(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_commit_2cta(uint32_t bar) {   // arrives on `bar` (same offset) in both CTAs
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(X3_THREADS, 1)
+gemm_tc_x3_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
+  using C = Cfg2;
+  constexpr int BK = C::BK, BN = C::BN;
+  constexpr int CPW = BN / 2, NCH = CPW / 32;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_u32 = smem_u32(smem_raw);
+  const uint32_t base = (raw_u32 + 1023u) & ~1023u;
+  uint8_t* const base_ptr = smem_raw + (base - raw_u32);
+  const uint32_t bars = base + C::STAGES * C::STAGE_BYTES;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (C::STAGES + s); };
+  auto ready_bar = [&](int s) { return bars + 8u * (2 * C::STAGES + s); };
+  const uint32_t tmem_full_bar = bars + 8u * (3 * C::STAGES);
+  const uint32_t chunk_full_bar = bars + 8u * (3 * C::STAGES + 1);
+  const uint32_t chunk_empty_bar = bars + 8u * (3 * C::STAGES + 2);
+  const uint32_t tmem_ptr_addr = bars + 8u * (3 * C::STAGES + 3);
+  auto a_hi = [&](int s) { return base + (uint32_t)s * C::STAGE_BYTES; };
+  auto b_hi = [&](int s) { return a_hi(s) + C::A_BYTES; };
+  auto a_lo = [&](int s) { return b_hi(s) + C::B_BYTES; };
+  auto b_lo = [&](int s) { return a_lo(s) + C::A_BYTES; };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int m0 = (blockIdx.y * 2 + (int)rank) * BM;          // this CTA's 128 accumulator rows
+  const int n0 = (blockIdx.x >> 1) * BN;                      // tile columns
+  const int nb0 = n0 + (int)rank * (BN / 2);                  // this CTA's half of B
+  const int kb_total = (p.K + BK - 1) / BK;
+  const int kb_begin = blockIdx.z * p.kb_per_split;
+  const int kb_end = min(kb_total, kb_begin + p.kb_per_split);
+  const int num_kb = kb_end - kb_begin;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+      mbar_init(ready_bar(s), 16);            // 8 worker warps x 2 CTAs (only the leader's copy is used)
+    }
+    mbar_init(tmem_full_bar, 1);
+    mbar_init(chunk_full_bar, 1);
+    mbar_init(chunk_empty_bar, 16);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "r"((uint32_t)C::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr) : "memory");
+
+  if (warp == 0) {
+    // ---- TMA producer (each CTA loads its own tiles)
+    if (lane == 0) {
+      for (int i = 0; i < num_kb; ++i) {
+        const int s = i % C::STAGES;
+        const uint32_t ph = (uint32_t)(i / C::STAGES) & 1u;
+        mbar_wait(empty_bar(s), ph ^ 1u);
+        mbar_expect_tx(full_bar(s), C::A_BYTES + C::B_BYTES);
+        const int k0 = (kb_begin + i) * BK;
+        if (!p.a_mn) {
+          tma_load_2d(a_hi(s), &tmA, full_bar(s), k0, m0);
+        } else {
+#pragma unroll
+          for (int j = 0; j < BM / 32; ++j) tma_load_2d(a_hi(s) + j * C::MN_BOX_BYTES, &tmA, full_bar(s), m0 + 32 * j, k0);
+        }
+        if (!p.b_mn) {
+          tma_load_2d(b_hi(s), &tmB, full_bar(s), k0, nb0);
+        } else {
+#pragma unroll
+          for (int j = 0; j < BN / 64; ++j) tma_load_2d(b_hi(s) + j * C::MN_BOX_BYTES, &tmB, full_bar(s), nb0 + 32 * j, k0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---- MMA issuer: leader CTA only
+    if (leader && lane == 0) {
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.a_mn ? 1 : 0) << 15) |
+                             ((uint32_t)(p.b_mn ? 1 : 0) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
+      const uint32_t a_lbo = p.a_mn ? C::MN_BOX_BYTES : 16u, b_lbo = p.b_mn ? C::MN_BOX_BYTES : 16u;
+      const uint32_t a_sbo = p.a_mn ? 512u : C::K_SBO, b_sbo = p.b_mn ? 512u : C::K_SBO;
+      const uint32_t a_lay = p.a_mn ? 1u : C::K_LAYOUT, b_lay = p.b_mn ? 1u : C::K_LAYOUT;
+      const uint32_t a_kstep = p.a_mn ? 1024u : 32u, b_kstep = p.b_mn ? 1024u : 32u;
+      uint32_t acc = 0, acc_x = 0;
+      for (int i = 0; i < num_kb; ++i) {
+        const int s = i % C::STAGES;
+        const uint32_t ph = (uint32_t)(i / C::STAGES) & 1u;
+        const bool new_chunk = (i % X3_CHUNK_KB == 0) && i > 0;
+        mbar_wait_cluster(ready_bar(s), ph);      // both CTAs: tiles landed and lo halves written
+        tc_fence_after();
+#pragma unroll
+        for (int ks = 0; ks < BK / UMMA_K; ++ks) {
+          const uint64_t dah = smem_desc(a_hi(s) + ks * a_kstep, a_lbo, a_sbo, a_lay);
+          const uint64_t dbh = smem_desc(b_hi(s) + ks * b_kstep, b_lbo, b_sbo, b_lay);
+          const uint64_t dal = smem_desc(a_lo(s) + ks * a_kstep, a_lbo, a_sbo, a_lay);
+          const uint64_t dbl = smem_desc(b_lo(s) + ks * b_kstep, b_lbo, b_sbo, b_lay);
+          umma_tf32_2cta(tmem_base + BN, dal, dbh, idesc, acc_x);
+          acc_x = 1;
+          umma_tf32_2cta(tmem_base + BN, dah, dbl, idesc, acc_x);
+        }
+        if (new_chunk) {
+          mbar_wait_cluster(chunk_empty_bar, (uint32_t)(i / X3_CHUNK_KB - 1) & 1u);
+          tc_fence_after();
+          acc = 0;
+        }
+#pragma unroll
+        for (int ks = 0; ks < BK / UMMA_K; ++ks) {
+          umma_tf32_2cta(tmem_base, smem_desc(a_hi(s) + ks * a_kstep, a_lbo, a_sbo, a_lay),
+                         smem_desc(b_hi(s) + ks * b_kstep, b_lbo, b_sbo, b_lay), idesc, acc);
+          acc = 1;
+        }
+        umma_commit_2cta(empty_bar(s));
+        if (((i + 1) % X3_CHUNK_KB == 0) && (i + 1 < num_kb)) umma_commit_2cta(chunk_full_bar);
+      }
+      umma_commit_2cta(tmem_full_bar);
+    }
+  } else {
+    // ---- workers: warps 2..9
+    const int t = threadIdx.x - 64;
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const uint32_t t_main = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(half * CPW);
+    float acc[CPW];
+#pragma unroll
+    for (int j = 0; j < CPW; ++j) acc[j] = 0.f;
+    constexpr int N4 = (C::A_BYTES + C::B_BYTES) / 16;
+    constexpr int PER = N4 / 256;
+    static_assert(N4 % 256 == 0, "tile size");
+    uint32_t ready_remote[C::STAGES];
+#pragma unroll
+    for (int s = 0; s < C::STAGES; ++s) ready_remote[s] = mapa_rank0(ready_bar(s));
+    const uint32_t chunk_empty_remote = mapa_rank0(chunk_empty_bar);
+    for (int i = 0; i < num_kb; ++i) {
+      const int s = i % C::STAGES;
+      const uint32_t ph = (uint32_t)(i / C::STAGES) & 1u;
+      mbar_wait(full_bar(s), ph);
+      const float4* src = reinterpret_cast<const float4*>(base_ptr + (size_t)s * C::STAGE_BYTES);
+      float4* dst = reinterpret_cast<float4*>(base_ptr + (size_t)s * C::STAGE_BYTES + C::A_BYTES + C::B_BYTES);
+      float4 x[PER];
+#pragma unroll
+      for (int u = 0; u < PER; ++u) x[u] = src[t + 256 * u];
+#pragma unroll
+      for (int u = 0; u < PER; ++u) {
+        float4 l;
+        l.x = x[u].x - __uint_as_float(__float_as_uint(x[u].x) & 0xFFFFE000u);
+        l.y = x[u].y - __uint_as_float(__float_as_uint(x[u].y) & 0xFFFFE000u);
+        l.z = x[u].z - __uint_as_float(__float_as_uint(x[u].z) & 0xFFFFE000u);
+        l.w = x[u].w - __uint_as_float(__float_as_uint(x[u].w) & 0xFFFFE000u);
+        dst[t + 256 * u] = l;
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) {
+        uint32_t ra = ready_remote[0];
+#pragma unroll
+        for (int ss = 1; ss < C::STAGES; ++ss) if (s == ss) ra = ready_remote[ss];
+        mbar_arrive_cluster(ra);
+      }
+      if ((i % X3_CHUNK_KB == 0) && i > 0) {
+        mbar_wait(chunk_full_bar, (uint32_t)(i / X3_CHUNK_KB - 1) & 1u);
+        tc_fence_after();
+        const float comp = X3_TRUNC_LOSS_PER_MMA * (float)(X3_CHUNK_KB * (BK / UMMA_K));
+#pragma unroll
+        for (int cc = 0; cc < NCH; ++cc) {
+          uint32_t v[32];
+          tmem_ld32(t_main + (uint32_t)(cc * 32), v);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[cc * 32 + j] += fmaf(__uint_as_float(v[j]), comp, __uint_as_float(v[j]));
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(chunk_empty_remote);
+      }
+    }
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const float comp_last = X3_TRUNC_LOSS_PER_MMA * (float)((((num_kb - 1) % X3_CHUNK_KB) + 1) * (BK / UMMA_K));
+#pragma unroll
+    for (int cc = 0; cc < NCH; ++cc) {
+      uint32_t v[32];
+      tmem_ld32(t_main + (uint32_t)(cc * 32), v);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) acc[cc * 32 + j] += fmaf(__uint_as_float(v[j]), comp_last, __uint_as_float(v[j]));
+      tmem_ld32(t_main + (uint32_t)(BN + cc * 32), v);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) acc[cc * 32 + j] += __uint_as_float(v[j]);
+    }
+    float* Cz = p.C + (size_t)blockIdx.z * p.slab_stride;
+    const bool vec = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(Cz) & 15) == 0) &&
+                     (!p.bias || ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0)) &&
+                     (!p.mask || (((p.ld_mask & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.mask) & 15) == 0)));
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    float4* stg = reinterpret_cast<float4*>(base_ptr + 4096 * (warp - 2));
+    const int l_row = lane >> 3, l_c4 = lane & 7;
+    const int row = m0 + 32 * q + lane;
+#pragma unroll
+    for (int cc = 0; cc < NCH; ++cc) {
+      const int cbase = n0 + half * CPW + cc * 32;
+      if (cbase < p.N) {
+        if (vec) {
+          const int col = cbase + 4 * l_c4;
+          const bool full4 = col + 3 < p.N;
+          float4 m4[8];
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int grow = m0 + 32 * q + it * 4 + l_row;
+            m4[it] = make_float4(1.f, 1.f, 1.f, 1.f);
+            if (p.mask && full4 && grow < p.M) m4[it] = *reinterpret_cast<const float4*>(p.mask + (size_t)grow * p.ld_mask + col);
+          }
+#pragma unroll
+          for (int c4 = 0; c4 < 8; ++c4)
+            stg[lane * 8 + (c4 ^ (lane & 7))] = make_float4(acc[cc * 32 + 4 * c4], acc[cc * 32 + 4 * c4 + 1],
+                                                            acc[cc * 32 + 4 * c4 + 2], acc[cc * 32 + 4 * c4 + 3]);
+          __syncwarp();
+          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.bias) {
+            if (full4) b4 = *reinterpret_cast<const float4*>(p.bias + col);
+            else { if (col < p.N) b4.x = p.bias[col]; if (col + 1 < p.N) b4.y = p.bias[col + 1]; if (col + 2 < p.N) b4.z = p.bias[col + 2]; }
+          }
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int r = it * 4 + l_row;
+            const int grow = m0 + 32 * q + r;
+            float4 o = stg[r * 8 + (l_c4 ^ (r & 7))];
+            if (grow < p.M && col < p.N) {
+              o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
+              if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+              float* dstp = Cz + (size_t)grow * p.ldc + col;
+              if (full4) {
+                o.x = m4[it].x > 0.f ? o.x : 0.f; o.y = m4[it].y > 0.f ? o.y : 0.f;
+                o.z = m4[it].z > 0.f ? o.z : 0.f; o.w = m4[it].w > 0.f ? o.w : 0.f;
+                if (p.accumulate) {
+                  const float4 c4 = *reinterpret_cast<const float4*>(dstp);
+                  o.x += c4.x; o.y += c4.y; o.z += c4.z; o.w += c4.w;
+                }
+                *reinterpret_cast<float4*>(dstp) = o;
+              } else {
+                const float oo[4] = {o.x, o.y, o.z, o.w};
+                for (int e = 0; e < 4 && col + e < p.N; ++e) {
+                  float xv = oo[e];
+                  if (p.mask) xv = p.mask[(size_t)grow * p.ld_mask + col + e] > 0.f ? xv : 0.f;
+                  if (p.accumulate) xv += dstp[e];
+                  dstp[e] = xv;
+                }
+              }
+            }
+          }
+          __syncwarp();
+        } else if (row < p.M) {
+          float* dstp = Cz + (size_t)row * p.ldc + cbase;
+          const float* mk = p.mask ? p.mask + (size_t)row * p.ld_mask + cbase : nullptr;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int col = cbase + j;
+            if (col < p.N) {
+              float xv = acc[cc * 32 + j];
+              if (p.bias) xv += p.bias[col];
+              if (p.relu) xv = fmaxf(xv, 0.f);
+              if (mk) xv = mk[j] > 0.f ? xv : 0.f;
+              if (p.accumulate) xv += dstp[j];
+              dstp[j] = xv;
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS) : "memory");
+  }
+}
+
+static int launch_x3_pair(cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, int M, int N, int split) {
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(gemm_tc_x3_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2::SMEM_BYTES) != cudaSuccess) {
+      addk_set_error("gemm_tc: cannot raise the dynamic shared memory limit");
+      return ADDK_ERR_LAUNCH;
+    }
+    configured = true;
+  }
+  dim3 grid(2 * ((N + Cfg2::BN - 1) / Cfg2::BN), (M + 2 * BM - 1) / (2 * BM), split);
+  gemm_tc_x3_pair_kernel<<<grid, X3_THREADS, Cfg2::SMEM_BYTES, st>>>(ta, tb, p);
+  return ADDK_OK;
+}
+
 template <int BN, bool X3>
 static int launch(cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, dim3 grid) {
   using C = Cfg<BN, X3>;
@@ -738,6 +1098,12 @@ static int launch(cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& tb,
 }
 
 }  // namespace addk_tc
+
+static bool addk_tc_pair_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("ADDK_TC_PAIR"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
+}
 
 // precision: 1 = tf32x3, 2 = tf32.  Shapes the tensor-core tiles do not cover (heads with 1 or 29 outputs,
 // contraction shorter than one k-block, misaligned leading dimensions, fused input normalisation) run on the
@@ -771,6 +1137,11 @@ int addk_gemm_tc(cudaStream_t st, const addk_gemm_args& a, int precision) {
   ok = ok && (p.b_mn ? make_map(&tb, a.B, a.N, a.K, a.ldb, 32, BK, true) : make_map(&tb, a.B, a.K, a.N, a.ldb, BK, BN, false));
   if (!ok) return addk::sgemm_launch(st, a);
   dim3 grid((a.N + BN - 1) / BN, (a.M + BM - 1) / BM, split);
+  if (x3 && BN == 256 && a.M > BM && addk_tc_pair_enabled()) {
+    // CTA-pair kernel: each CTA of the pair stages 128 rows of B -> its tensor-map box has 128 rows
+    if (!p.b_mn && !make_map(&tb, a.B, a.K, a.N, a.ldb, BK, Cfg2::BN / 2, false)) return addk::sgemm_launch(st, a);
+    return launch_x3_pair(st, ta, tb, p, a.M, a.N, split);
+  }
   if (BN == 256) return x3 ? launch_x3<256>(st, ta, tb, p, grid) : launch<256, false>(st, ta, tb, p, grid);
   if (BN == 128) return x3 ? launch_x3<128>(st, ta, tb, p, grid) : launch<128, false>(st, ta, tb, p, grid);
   return x3 ? launch_x3<64>(st, ta, tb, p, grid) : launch<64, false>(st, ta, tb, p, grid);
