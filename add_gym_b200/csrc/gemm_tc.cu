@@ -39,6 +39,7 @@ struct Params {
   int kb_per_split;            // k-blocks per blockIdx.z
   int a_mn, b_mn;              // operand is MN-major (memory rows = contraction index)
   long long slab_stride;       // floats between split-K slabs
+  int pair_flags;              // CTA-pair kernel experiments: bit0 cluster-scope waits, bit1 relaxed remote arrives
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -760,6 +761,14 @@ __device__ __forceinline__ uint32_t mapa_rank0(uint32_t addr) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// Remote arrive without the cluster-scope release: measured, `arrive.release.cluster` stalls the issuing warp for
+// ~1.5k cycles, which made the worker warps the bottleneck (301 us vs 199 us per 16384x1024x1024 layer).  What the
+// leader's MMAs must see is this CTA's OWN shared memory; every writer has already executed fence.proxy.async
+// (generic -> async proxy) and the warp has re-converged, so a CTA-scope fence followed by a relaxed arrive is enough.
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
+  __threadfence_block();
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -877,11 +886,12 @@ gemm_tc_x3_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       const uint32_t a_lay = p.a_mn ? 1u : C::K_LAYOUT, b_lay = p.b_mn ? 1u : C::K_LAYOUT;
       const uint32_t a_kstep = p.a_mn ? 1024u : 32u, b_kstep = p.b_mn ? 1024u : 32u;
       uint32_t acc = 0, acc_x = 0;
+      const bool pair_wait_cluster = (p.pair_flags & 1) != 0;
       for (int i = 0; i < num_kb; ++i) {
         const int s = i % C::STAGES;
         const uint32_t ph = (uint32_t)(i / C::STAGES) & 1u;
         const bool new_chunk = (i % X3_CHUNK_KB == 0) && i > 0;
-        mbar_wait_cluster(ready_bar(s), ph);      // both CTAs: tiles landed and lo halves written
+        if (pair_wait_cluster) mbar_wait_cluster(ready_bar(s), ph); else mbar_wait(ready_bar(s), ph);   // both CTAs: tiles landed, lo halves written
         tc_fence_after();
 #pragma unroll
         for (int ks = 0; ks < BK / UMMA_K; ++ks) {
@@ -894,7 +904,8 @@ gemm_tc_x3_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           umma_tf32_2cta(tmem_base + BN, dah, dbl, idesc, acc_x);
         }
         if (new_chunk) {
-          mbar_wait_cluster(chunk_empty_bar, (uint32_t)(i / X3_CHUNK_KB - 1) & 1u);
+          if (pair_wait_cluster) mbar_wait_cluster(chunk_empty_bar, (uint32_t)(i / X3_CHUNK_KB - 1) & 1u);
+          else mbar_wait(chunk_empty_bar, (uint32_t)(i / X3_CHUNK_KB - 1) & 1u);
           tc_fence_after();
           acc = 0;
         }
@@ -949,7 +960,7 @@ gemm_tc_x3_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         uint32_t ra = ready_remote[0];
 #pragma unroll
         for (int ss = 1; ss < C::STAGES; ++ss) if (s == ss) ra = ready_remote[ss];
-        mbar_arrive_cluster(ra);
+        if (p.pair_flags & 2) mbar_arrive_cluster_relaxed(ra); else mbar_arrive_cluster(ra);
       }
       if ((i % X3_CHUNK_KB == 0) && i > 0) {
         mbar_wait(chunk_full_bar, (uint32_t)(i / X3_CHUNK_KB - 1) & 1u);
@@ -964,7 +975,7 @@ gemm_tc_x3_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(chunk_empty_remote);
+        if (lane == 0) { if (p.pair_flags & 2) mbar_arrive_cluster_relaxed(chunk_empty_remote); else mbar_arrive_cluster(chunk_empty_remote); }
       }
     }
     mbar_wait(tmem_full_bar, 0);
@@ -1129,6 +1140,7 @@ int addk_gemm_tc(cudaStream_t st, const addk_gemm_args& a, int precision) {
   p.C = a.C; p.ldc = a.ldc; p.M = a.M; p.N = a.N; p.K = a.K; p.bias = a.bias; p.mask = a.relu_mask_src;
   p.ld_mask = a.ld_mask; p.relu = a.relu; p.accumulate = a.accumulate; p.kb_per_split = kb_per;
   p.slab_stride = a.slab_stride > 0 ? a.slab_stride : (long long)a.M * a.ldc;
+  { const char* e = getenv("ADDK_TC_PAIR_FLAGS"); p.pair_flags = e ? atoi(e) : 2; }
   p.a_mn = a.trans_a ? 1 : 0;          // A given as [K,M]: rows are the contraction index
   p.b_mn = a.trans_b ? 0 : 1;          // B given as [K,N]
   const int BN = a.N > 128 ? 256 : (a.N > 64 ? 128 : 64);
