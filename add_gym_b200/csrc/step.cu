@@ -65,6 +65,11 @@ __device__ __forceinline__ void disc_step_small(const float* src, int half, floa
   }
 }
 
+// FAST = true is the instance for the reference's default task (configs/task/pose.yaml: 29 dofs, 6 target steps,
+// 3 discriminator steps, global obs with root height, no velocity / phase obs): every loop bound and row size is a
+// compile-time constant, which removes ~half of the kernel's instructions (index arithmetic; the kernel is
+// issue-bound, not HBM-bound, see profiles/).  FAST = false reads the same quantities from the task struct.
+template <bool FAST>
 __global__ void __launch_bounds__(WPB * 32) env_step_kernel(const __grid_constant__ StepParams p) {
   extern __shared__ __align__(16) float smem[];
   const addk_task& tk = p.task;
@@ -73,13 +78,16 @@ __global__ void __launch_bounds__(WPB * 32) env_step_kernel(const __grid_constan
   if (e >= p.n) return;
   if ((p.flags & F_MASKED) && !p.env_mask[e]) return;
 
-  const int D = tk.num_dofs;
+  const int D = FAST ? 29 : tk.num_dofs;
   const int half = (7 + D + 3) & ~3;
-  const int RS = p.lib.row_stride;
-  const int nT = tk.enable_tar_obs ? tk.num_tar_steps : 0;
-  const int nH = tk.num_disc_steps;
-  const bool vel = tk.enable_vel_obs != 0, glob = tk.global_obs != 0;
-  const int obs_pad = (tk.obs_dim + 3) & ~3, disc_pad = (tk.disc_obs_dim + 3) & ~3;
+  const int RS = FAST ? 72 : p.lib.row_stride;
+  const int nT = FAST ? 6 : (tk.enable_tar_obs ? tk.num_tar_steps : 0);
+  const int nH = FAST ? 3 : tk.num_disc_steps;
+  const bool vel = FAST ? false : (tk.enable_vel_obs != 0), glob = FAST ? true : (tk.global_obs != 0);
+  const bool root_h = FAST ? true : (tk.root_height_obs != 0);
+  const bool phase_obs = FAST ? false : (tk.enable_phase_obs != 0);
+  const int obs_dim = FAST ? 264 : tk.obs_dim, disc_dim = FAST ? 114 : tk.disc_obs_dim;
+  const int obs_pad = (obs_dim + 3) & ~3, disc_pad = (disc_dim + 3) & ~3;
   // per-warp shared layout
   const int per_warp = RS /*ref*/ + nT * half + nH * RS /*demo*/ + RS /*sim*/ + nH * RS /*hist*/ + obs_pad + 2 * disc_pad;
   float* s_ref = smem + (size_t)warp * per_warp;
@@ -178,16 +186,16 @@ __global__ void __launch_bounds__(WPB * 32) env_step_kernel(const __grid_constan
   // ---- policy observation (add_observation.py:422-459,578-717) ----------------------------------
   const Quat root_q = ldq(s_sim + 3);
   int o = 0;
-  const int o_h = o;            o += tk.root_height_obs ? 1 : 0;
+  const int o_h = o;            o += root_h ? 1 : 0;
   const int o_rot = o;          o += 6;
   const int o_dof = o;          o += D;
   const int o_vel = o;          o += vel ? 6 + D : 0;
-  const int o_phase = o;        o += tk.enable_phase_obs ? 1 + 2 * tk.num_phase_encoding : 0;
+  const int o_phase = o;        o += phase_obs ? 1 + 2 * tk.num_phase_encoding : 0;
   const int o_tar = o;
-  const int tar_pos_dim = tk.root_height_obs ? 3 : 2;
+  const int tar_pos_dim = root_h ? 3 : 2;
   const int tar_dim = tar_pos_dim + 6 + D;
   if (lane == 31) {
-    if (tk.root_height_obs) s_obs[o_h] = s_sim[2];
+    if (root_h) s_obs[o_h] = s_sim[2];
     Quat hinv = {1.f, 0.f, 0.f, 0.f};
     if (!glob) hinv = calc_heading_quat_inv(root_q);
     Quat q = glob ? root_q : quat_mul(hinv, root_q);
@@ -198,7 +206,7 @@ __global__ void __launch_bounds__(WPB * 32) env_step_kernel(const __grid_constan
       float* v = s_obs + o_vel;
       v[0] = lv.x; v[1] = lv.y; v[2] = lv.z; v[3] = av.x; v[4] = av.y; v[5] = av.z;
     }
-    if (tk.enable_phase_obs) {  // calc_phase + compute_phase_obs (motion_lib.py:361-372; add_observation.py:557-575)
+    if (phase_obs) {  // calc_phase + compute_phase_obs (motion_lib.py:361-372; add_observation.py:557-575)
       float ph = mt / p.lib.lengths[mid];
       if (p.lib.loop_modes[mid] == 1) ph = sub_rn(ph, floorf(ph));
       ph = fminf(fmaxf(ph, 0.0f), 1.0f);
@@ -227,7 +235,7 @@ __global__ void __launch_bounds__(WPB * 32) env_step_kernel(const __grid_constan
       q = quat_mul(hinv, q);
     }
     dst[0] = dp.x; dst[1] = dp.y;
-    if (tk.root_height_obs) dst[2] = tr[2];
+    if (root_h) dst[2] = tr[2];
     quat_to_tan_norm(q, dst + tar_pos_dim);
   }
   for (int k = 0; k < nT; ++k)
@@ -252,23 +260,23 @@ __global__ void __launch_bounds__(WPB * 32) env_step_kernel(const __grid_constan
 
   // ---- stream the rows out ----------------------------------------------------------------------
   {
-    float* g = p.env.obs_buf + (size_t)e * tk.obs_dim;
-    float* gx = p.has_exp ? p.exp.next_obs + (size_t)e * tk.obs_dim : nullptr;
-    if ((tk.obs_dim & 3) == 0) {
-      for (int i = lane; i < tk.obs_dim / 4; i += 32) {
+    float* g = p.env.obs_buf + (size_t)e * obs_dim;
+    float* gx = p.has_exp ? p.exp.next_obs + (size_t)e * obs_dim : nullptr;
+    if ((obs_dim & 3) == 0) {
+      for (int i = lane; i < obs_dim / 4; i += 32) {
         float4 v = *reinterpret_cast<const float4*>(s_obs + 4 * i);
         stg4(g + 4 * i, v);
         if (gx) stg4_cs(gx + 4 * i, v);
       }
     } else {
-      for (int i = lane; i < tk.obs_dim; i += 32) { g[i] = s_obs[i]; if (gx) gx[i] = s_obs[i]; }
+      for (int i = lane; i < obs_dim; i += 32) { g[i] = s_obs[i]; if (gx) gx[i] = s_obs[i]; }
     }
-    float* gd = p.env.disc_obs + (size_t)e * tk.disc_obs_dim;
-    float* gm = p.env.disc_obs_demo + (size_t)e * tk.disc_obs_dim;
-    float* xd = p.has_exp ? p.exp.disc_obs + (size_t)e * tk.disc_obs_dim : nullptr;
-    float* xm = p.has_exp ? p.exp.disc_obs_demo + (size_t)e * tk.disc_obs_dim : nullptr;
-    if ((tk.disc_obs_dim & 1) == 0) {  // rows are 8-byte aligned: 64-bit stores
-      for (int i = lane; i < tk.disc_obs_dim / 2; i += 32) {
+    float* gd = p.env.disc_obs + (size_t)e * disc_dim;
+    float* gm = p.env.disc_obs_demo + (size_t)e * disc_dim;
+    float* xd = p.has_exp ? p.exp.disc_obs + (size_t)e * disc_dim : nullptr;
+    float* xm = p.has_exp ? p.exp.disc_obs_demo + (size_t)e * disc_dim : nullptr;
+    if ((disc_dim & 1) == 0) {  // rows are 8-byte aligned: 64-bit stores
+      for (int i = lane; i < disc_dim / 2; i += 32) {
         float2 a = *reinterpret_cast<const float2*>(s_disc + 2 * i);
         float2 b = *reinterpret_cast<const float2*>(s_dobs + 2 * i);
         *reinterpret_cast<float2*>(gd + 2 * i) = a;
@@ -276,7 +284,7 @@ __global__ void __launch_bounds__(WPB * 32) env_step_kernel(const __grid_constan
         if (xd) { __stcs(reinterpret_cast<float2*>(xd + 2 * i), a); __stcs(reinterpret_cast<float2*>(xm + 2 * i), b); }
       }
     } else {
-      for (int i = lane; i < tk.disc_obs_dim; i += 32) {
+      for (int i = lane; i < disc_dim; i += 32) {
         gd[i] = s_disc[i]; gm[i] = s_dobs[i];
         if (xd) { xd[i] = s_disc[i]; xm[i] = s_dobs[i]; }
       }
@@ -563,12 +571,17 @@ extern "C" int addk_env_step(void* stream, const addk_task* task, const addk_mot
   p.newest_slot = (flags & F_UPDATE_MOTION) ? hist_head % nH : (hist_head + nH - 1) % nH;
   int smem = step_smem_bytes(*task, lib->row_stride);
   if (smem > 200 * 1024) return ADDK_ERR_UNSUPPORTED;
+  const bool fast = D == 29 && lib->row_stride == 72 && task->enable_tar_obs && task->num_tar_steps == 6 &&
+                    task->num_disc_steps == 3 && task->global_obs && task->root_height_obs && !task->enable_vel_obs &&
+                    !task->enable_phase_obs && task->obs_dim == 264 && task->disc_obs_dim == 114;
   static int configured = 0;
   if (smem > 48 * 1024 && configured < smem) {
-    cudaFuncSetAttribute(env_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(env_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(env_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     configured = smem;
   }
-  env_step_kernel<<<(num_envs + WPB - 1) / WPB, WPB * 32, smem, (cudaStream_t)stream>>>(p);
+  if (fast) env_step_kernel<true><<<(num_envs + WPB - 1) / WPB, WPB * 32, smem, (cudaStream_t)stream>>>(p);
+  else env_step_kernel<false><<<(num_envs + WPB - 1) / WPB, WPB * 32, smem, (cudaStream_t)stream>>>(p);
   ADDK_CHECK_LAUNCH();
   return ADDK_OK;
 }
