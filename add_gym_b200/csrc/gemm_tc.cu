@@ -502,6 +502,7 @@ gemm_tc_x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int s = i % C::STAGES;
         const uint32_t ph = (uint32_t)(i / C::STAGES) & 1u;
         mbar_wait(empty_bar(s), ph ^ 1u);
+        if ((p.pair_flags & 8) && i >= C::STAGES) { mbar_arrive(full_bar(s)); continue; }   // experiment: no TMA traffic
         mbar_expect_tx(full_bar(s), C::A_BYTES + C::B_BYTES);
         const int k0 = (kb_begin + i) * BK;
         if (!p.a_mn) {
@@ -544,7 +545,7 @@ gemm_tc_x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           acc_x = 1;
           umma_tf32(tmem_base + BN, dah, dbl, idesc, acc_x);
         }
-        if (new_chunk) {                       // the workers have copied the previous chunk out of the main accumulator
+        if (new_chunk && !(p.pair_flags & 4)) {   // the workers have copied the previous chunk out of the main accumulator
           mbar_wait(chunk_empty_bar, (uint32_t)(i / X3_CHUNK_KB - 1) & 1u);
           tc_fence_after();
           acc = 0;
@@ -578,6 +579,7 @@ gemm_tc_x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_wait(full_bar(s), ph);
       const float4* src = reinterpret_cast<const float4*>(base_ptr + (size_t)s * C::STAGE_BYTES);
       float4* dst = reinterpret_cast<float4*>(base_ptr + (size_t)s * C::STAGE_BYTES + C::A_BYTES + C::B_BYTES);
+      if (p.pair_flags & 4) { mbar_arrive(ready_bar(s)); continue; }   // experiment: no split work (and no drain)
       float4 x[PER];
 #pragma unroll
       for (int u = 0; u < PER; ++u) x[u] = src[t + 256 * u];
@@ -860,6 +862,7 @@ gemm_tc_x3_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         const int s = i % C::STAGES;
         const uint32_t ph = (uint32_t)(i / C::STAGES) & 1u;
         mbar_wait(empty_bar(s), ph ^ 1u);
+        if ((p.pair_flags & 8) && i >= C::STAGES) { mbar_arrive(full_bar(s)); continue; }   // experiment: no TMA traffic
         mbar_expect_tx(full_bar(s), C::A_BYTES + C::B_BYTES);
         const int k0 = (kb_begin + i) * BK;
         if (!p.a_mn) {
@@ -903,7 +906,7 @@ gemm_tc_x3_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           acc_x = 1;
           umma_tf32_2cta(tmem_base + BN, dah, dbl, idesc, acc_x);
         }
-        if (new_chunk) {
+        if (new_chunk && !(p.pair_flags & 4)) {
           if (pair_wait_cluster) mbar_wait_cluster(chunk_empty_bar, (uint32_t)(i / X3_CHUNK_KB - 1) & 1u);
           else mbar_wait(chunk_empty_bar, (uint32_t)(i / X3_CHUNK_KB - 1) & 1u);
           tc_fence_after();
@@ -942,6 +945,16 @@ gemm_tc_x3_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       mbar_wait(full_bar(s), ph);
       const float4* src = reinterpret_cast<const float4*>(base_ptr + (size_t)s * C::STAGE_BYTES);
       float4* dst = reinterpret_cast<float4*>(base_ptr + (size_t)s * C::STAGE_BYTES + C::A_BYTES + C::B_BYTES);
+      if (p.pair_flags & 4) {   // experiment: no split work (and no drain)
+        __syncwarp();
+        if (lane == 0) {
+          uint32_t ra = ready_remote[0];
+#pragma unroll
+          for (int ss = 1; ss < C::STAGES; ++ss) if (s == ss) ra = ready_remote[ss];
+          mbar_arrive_cluster_relaxed(ra);
+        }
+        continue;
+      }
       float4 x[PER];
 #pragma unroll
       for (int u = 0; u < PER; ++u) x[u] = src[t + 256 * u];
