@@ -147,6 +147,11 @@ class ADDAgent(torch.nn.Module):
         ent = self._env.robot.entity
         self._masked_engine = hasattr(ent, "set_state_masked")
         self.engine_time_events = None   # bench.py installs a list to time scene.step() separately
+        # CUDA graphs for the launch-bound rollout step (two segments around the physics step), see _rollout_train
+        self._use_graphs = bool(config.get("cuda_graphs", True))
+        self._graphs_pre, self._graphs_post = {}, {}
+        self._graph_pool = None
+        self._rollouts_done = 0
 
     model = property(lambda s: s._model)
 
@@ -361,13 +366,67 @@ class ADDAgent(torch.nn.Module):
         core.step(_lib.F_MASKED, env_mask=core.reset_mask, track_returns=False)
         return core.obs_buf, self._add_obs.info
 
+    def _graphs_ok(self):
+        """The rollout step is ~30 small launches and launch-bound at 4096 envs; it is replayed from CUDA graphs when
+        everything it touches has a fixed address: device RNG, an engine whose getters hand out persistent tensors and
+        that takes masked state writes, a constant exploration probability.  The first rollout always runs eagerly
+        (lazy one-time initialisation inside the library must not happen during stream capture)."""
+        ent = self._env.robot.entity
+        return (self._use_graphs and self._rollouts_done >= 1 and isinstance(self.rng, DeviceRandom) and self._masked_engine
+                and getattr(ent, "persistent_state_tensors", False) and self._mode == AgentMode.TRAIN
+                and not np.isfinite(self._exp_anneal_samples))
+
+    def _capture(self, fn):
+        if self._graph_pool is None:
+            self._graph_pool = torch.cuda.graph_pool_handle()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, pool=self._graph_pool):
+            fn()
+        return g
+
+    def _rollout_step_graphed(self, t):
+        core, env = self._core, self._env
+        nH = core.hist.shape[1]
+        g = self._graphs_pre.get(t)
+        if g is None:      # segment 1: action noise + actor forward + sample / log-prob + record row t
+            g = self._graphs_pre[t] = self._capture(lambda: self._decide_action(self._curr_obs, self._curr_info, record_t=t))
+        g.replay()
+        ev = self.engine_time_events
+        env.robot.apply_action(self._action)
+        if ev is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        env.scene.step()                                   # physics: never captured
+        if ev is not None:
+            e1.record()
+            ev.append((e0, e1))
+        key = (t, core.hist_head)
+        g = self._graphs_post.get(key)
+        if g is None:      # segment 2: fused post-step kernel + reset candidates + masked reset + masked recompute
+            head = core.hist_head
+
+            def post():
+                flags = _lib.F_ADVANCE | _lib.F_UPDATE_MOTION | _lib.F_REWARD_DONE
+                core.step(flags, exp_row=self._exp_row(t))
+                self._reset_done_envs(core.done_buf)
+            g = self._graphs_post[key] = self._capture(post)
+            core.hist_head = head                          # capture ran the Python bookkeeping once; undo, replay, redo
+        g.replay()
+        core.hist_head = (core.hist_head + 1) % nH
+        self._curr_obs, self._curr_info = core.obs_buf, self._add_obs.info
+
     def _rollout_train(self, num_steps):
+        graphed = self._graphs_ok()
         for _ in range(num_steps):
             t = self._exp_buffer.get_buffer_head()
-            action, _ = self._decide_action(self._curr_obs, self._curr_info, record_t=t)
-            _, _, done, _ = self._step_env(action, record_t=t)
-            self._curr_obs, self._curr_info = self._reset_done_envs(done)
+            if graphed:
+                self._rollout_step_graphed(t)
+            else:
+                action, _ = self._decide_action(self._curr_obs, self._curr_info, record_t=t)
+                _, _, done, _ = self._step_env(action, record_t=t)
+                self._curr_obs, self._curr_info = self._reset_done_envs(done)
             self._exp_buffer.inc()
+        self._rollouts_done += 1
 
     # ---- training data ------------------------------------------------------------------------------------------
     def _build_train_data(self):

@@ -173,6 +173,7 @@ class SyntheticPlane:
 
 class SyntheticEntity(BaseEntity):
     N_CONTACT_SLOTS = 4
+    persistent_state_tensors = True     # getters return the same tensors every step (CUDA-graph friendly)
 
     def __init__(self, scene, char_file, link_offset):
         self._scene = scene

@@ -380,3 +380,49 @@ def test_checkpoint_roundtrip_and_reference_key_names(tmp_path):
     b = ADDAgent(cfg, device="cuda:0")
     b.load(p)
     assert torch.equal(a._model.flat, b._model.flat)
+
+
+def test_cuda_graph_rollout_is_bit_identical_to_eager():
+    """The rollout step replayed from CUDA graphs (two segments around the physics step) must write exactly what the
+    eager launch sequence writes: same kernels, same order, fixed addresses.  Deterministic draws make the two runs
+    comparable (torch's generator advances differently under capture)."""
+    from add_gym_b200.add_agent import ADDAgent, DeviceRandom
+
+    class FixedRandom(DeviceRandom):
+        def __init__(self, device):
+            super().__init__(device)
+            self.k = 0
+
+        def action_noise(self, n, dim):
+            return torch.full((n, dim), 0.25, device=self.device)
+
+        def reset_uniforms(self, n):
+            return torch.full((n, 3), 0.37, device=self.device)
+
+    def run(graphs):
+        cfg = b200_config.default_config(num_envs=96)
+        cfg["agent"]["cuda_graphs"] = graphs
+        cfg["engine"].update(seed=77, noise_device="device", fall_prob=0.02)
+        torch.manual_seed(0)
+        a = ADDAgent(cfg, device="cuda:0")
+        a.rng = FixedRandom("cuda:0")
+        a._curr_obs, a._curr_info = a._reset_envs()
+        a._exp_buffer.clear()
+        a._reset_tracker()
+        snaps = []
+        for _ in range(3):                       # first rollout eager in both; then graphs are captured and replayed
+            a._rollout_train(a._steps_per_iter)
+            snaps.append({k: a._exp_buffer.get_data(k).clone() for k in FLOAT_KEYS + EXACT_KEYS})
+        torch.cuda.synchronize()
+        return a, snaps
+
+    eager, s0 = run(False)
+    graphed, s1 = run(True)
+    assert len(graphed._graphs_pre) == graphed._steps_per_iter and len(graphed._graphs_post) >= graphed._steps_per_iter
+    assert len(eager._graphs_pre) == 0
+    for it, (x, y) in enumerate(zip(s0, s1)):
+        for k in x:
+            assert torch.equal(x[k], y[k]), (it, k)
+    assert torch.equal(eager._env.time_buf, graphed._env.time_buf)
+    assert torch.equal(eager._core.hist, graphed._core.hist) and eager._core.hist_head == graphed._core.hist_head
+    assert int(eager._core.tracker_count.item()) == int(graphed._core.tracker_count.item())
