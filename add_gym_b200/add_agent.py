@@ -152,6 +152,7 @@ class ADDAgent(torch.nn.Module):
         self._graphs_pre, self._graphs_post = {}, {}
         self._graph_pool = None
         self._rollouts_done = 0
+        self._host_fetch = getattr(ent, "fetch_from_host", None)
 
     model = property(lambda s: s._model)
 
@@ -400,6 +401,8 @@ class ADDAgent(torch.nn.Module):
         if ev is not None:
             e1.record()
             ev.append((e0, e1))
+        if self._host_fetch is not None:                   # host-resident simulator: its H2D staging copy stays eager
+            self._host_fetch()                             # (pinned-memory bookkeeping is not capturable)
         key = (t, core.hist_head)
         g = self._graphs_post.get(key)
         if g is None:      # segment 2: fused post-step kernel + reset candidates + masked reset + masked recompute

@@ -442,6 +442,10 @@ class HostBoundaryEntity(SyntheticEntity):
             self._stage_v.copy_(self._host_v, non_blocking=True)
             self._dirty = False
 
+    def fetch_from_host(self):
+        """Explicit form of the lazy fetch (the agent calls it before replaying a captured step)."""
+        self._fetch()
+
     def get_pos(self):
         self._fetch()
         return self._stage_f[:, 0:3]
