@@ -381,7 +381,8 @@ class ADDAgent(torch.nn.Module):
         if self._graph_pool is None:
             self._graph_pool = torch.cuda.graph_pool_handle()
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g, pool=self._graph_pool):
+        # thread_local: other threads (NCCL watchdog, pinned-memory allocator) keep querying events during capture
+        with torch.cuda.graph(g, pool=self._graph_pool, capture_error_mode="thread_local"):
             fn()
         return g
 
