@@ -16,6 +16,7 @@ diagnostics stay on the device until the end of the iteration.  Gradients ARE al
 """
 import ctypes as C
 import enum
+import gc
 import os
 import time
 
@@ -381,10 +382,25 @@ class ADDAgent(torch.nn.Module):
         if self._graph_pool is None:
             self._graph_pool = torch.cuda.graph_pool_handle()
         g = torch.cuda.CUDAGraph()
-        # thread_local: other threads (NCCL watchdog, pinned-memory allocator) keep querying events during capture
-        with torch.cuda.graph(g, pool=self._graph_pool, capture_error_mode="thread_local"):
-            fn()
+        # thread_local: other threads (NCCL watchdog, pinned-memory allocator) keep querying events during capture.
+        # The cyclic GC is paused: collecting an older agent's graphs mid-capture frees device memory, which invalidates
+        # the capture (observed when a second agent was built after a first one had captured its graphs).
+        was_enabled = gc.isenabled()
+        gc.collect()
+        gc.disable()
+        try:
+            with torch.cuda.graph(g, pool=self._graph_pool, capture_error_mode="thread_local"):
+                fn()
+        finally:
+            if was_enabled:
+                gc.enable()
         return g
+
+    def release_graphs(self):
+        """Drop the captured rollout graphs (and their private memory pool) deterministically."""
+        self._graphs_pre.clear()
+        self._graphs_post.clear()
+        self._graph_pool = None
 
     def _rollout_step_graphed(self, t):
         core, env = self._core, self._env

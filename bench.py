@@ -11,6 +11,7 @@ normalizer update -- T*N = 131,072 env-steps at N = 4096.  Physics is excluded: 
 `scene.step()` is timed with its own CUDA events and subtracted.  metric = env-steps/s = T*N*R / t.
 """
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -261,7 +262,9 @@ def run_b200(args):
     # ---- dominant kernel: the dense-layer contraction of the update, timed launch by launch --------------------
     roof = dominant_kernel_roofline(agent, args, hbm_peak, tc_peak, peak_src) if rank == 0 else None
     hbm_roof = step_kernel_roofline(agent, hbm_peak) if rank == 0 else None
+    agent.release_graphs()
     del agent
+    gc.collect()
     torch.cuda.empty_cache()
 
     # ---- end to end: simulator state arrives from pinned host memory every env step --------------------------
@@ -277,7 +280,9 @@ def run_b200(args):
                "what": "ADDAgent._train_iter with the simulator state copied from pinned host memory before every env "
                        "step, the action copied back to pinned host memory after every actor forward and the "
                        "iteration diagnostics read back as Python floats"}
+        agent.release_graphs()
         del agent
+        gc.collect()
         torch.cuda.empty_cache()
 
     if rank != 0:

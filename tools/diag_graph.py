@@ -7,6 +7,11 @@ from add_gym_b200.add_agent import ADDAgent
 envs = int(sys.argv[1]); mode = sys.argv[2]
 cfg = b200_config.default_config(num_envs=envs, mlp_precision="tf32x3")
 cfg["engine"].update(seed=1234, noise_device="device", fall_prob=0.002)
+if len(sys.argv) > 3:
+    cfg["engine"]["_target_"] = "add_gym_b200.engine." + sys.argv[3]
+if len(sys.argv) > 4:
+    import add_gym_b200.engine as E
+    exec(sys.argv[4])
 a = ADDAgent(cfg, device="cuda:0")
 a._curr_obs, a._curr_info = a._reset_envs()
 a._exp_buffer.clear()
