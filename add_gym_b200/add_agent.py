@@ -378,23 +378,36 @@ class ADDAgent(torch.nn.Module):
                 and getattr(ent, "persistent_state_tensors", False) and self._mode == AgentMode.TRAIN
                 and not np.isfinite(self._exp_anneal_samples))
 
-    def _capture(self, fn):
-        if self._graph_pool is None:
-            self._graph_pool = torch.cuda.graph_pool_handle()
-        g = torch.cuda.CUDAGraph()
-        # thread_local: other threads (NCCL watchdog, pinned-memory allocator) keep querying events during capture.
-        # The cyclic GC is paused: collecting an older agent's graphs mid-capture frees device memory, which invalidates
-        # the capture (observed when a second agent was built after a first one had captured its graphs).
+    def _capture_all(self):
+        """Capture every rollout-step graph up front: segment 1 per buffer row t, segment 2 per (t, history head).
+        Capturing does not execute anything, so the Python-side bookkeeping it runs (history head) is restored.
+        thread_local error mode: other threads (NCCL watchdog, pinned-memory allocator) keep querying events during
+        capture.  The cyclic GC is paused: collecting an older agent's graphs mid-capture frees device memory, which
+        invalidates the capture (seen when a second agent was built after a first one had captured its graphs)."""
+        core, T, nH = self._core, self._steps_per_iter, self._core.hist.shape[1]
+        self._graph_pool = torch.cuda.graph_pool_handle()
+        head0 = core.hist_head
+        flags = _lib.F_ADVANCE | _lib.F_UPDATE_MOTION | _lib.F_REWARD_DONE
         was_enabled = gc.isenabled()
         gc.collect()
         gc.disable()
         try:
-            with torch.cuda.graph(g, pool=self._graph_pool, capture_error_mode="thread_local"):
-                fn()
+            for t in range(T):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, pool=self._graph_pool, capture_error_mode="thread_local"):
+                    self._decide_action(self._curr_obs, self._curr_info, record_t=t)
+                self._graphs_pre[t] = g
+                for head in range(nH):
+                    core.hist_head = head
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, pool=self._graph_pool, capture_error_mode="thread_local"):
+                        core.step(flags, exp_row=self._exp_row(t))
+                        self._reset_done_envs(core.done_buf)
+                    self._graphs_post[(t, head)] = g
         finally:
+            core.hist_head = head0
             if was_enabled:
                 gc.enable()
-        return g
 
     def release_graphs(self):
         """Drop the captured rollout graphs (and their private memory pool) deterministically."""
@@ -405,10 +418,7 @@ class ADDAgent(torch.nn.Module):
     def _rollout_step_graphed(self, t):
         core, env = self._core, self._env
         nH = core.hist.shape[1]
-        g = self._graphs_pre.get(t)
-        if g is None:      # segment 1: action noise + actor forward + sample / log-prob + record row t
-            g = self._graphs_pre[t] = self._capture(lambda: self._decide_action(self._curr_obs, self._curr_info, record_t=t))
-        g.replay()
+        self._graphs_pre[t].replay()       # segment 1: action noise + actor forward + sample / log-prob + record row t
         ev = self.engine_time_events
         env.robot.apply_action(self._action)
         if ev is not None:
@@ -420,23 +430,15 @@ class ADDAgent(torch.nn.Module):
             ev.append((e0, e1))
         if self._host_fetch is not None:                   # host-resident simulator: its H2D staging copy stays eager
             self._host_fetch()                             # (pinned-memory bookkeeping is not capturable)
-        key = (t, core.hist_head)
-        g = self._graphs_post.get(key)
-        if g is None:      # segment 2: fused post-step kernel + reset candidates + masked reset + masked recompute
-            head = core.hist_head
-
-            def post():
-                flags = _lib.F_ADVANCE | _lib.F_UPDATE_MOTION | _lib.F_REWARD_DONE
-                core.step(flags, exp_row=self._exp_row(t))
-                self._reset_done_envs(core.done_buf)
-            g = self._graphs_post[key] = self._capture(post)
-            core.hist_head = head                          # capture ran the Python bookkeeping once; undo, replay, redo
-        g.replay()
+        # segment 2: fused post-step kernel + reset candidates + masked reset + masked recompute
+        self._graphs_post[(t, core.hist_head)].replay()
         core.hist_head = (core.hist_head + 1) % nH
         self._curr_obs, self._curr_info = core.obs_buf, self._add_obs.info
 
     def _rollout_train(self, num_steps):
         graphed = self._graphs_ok()
+        if graphed and not self._graphs_pre:
+            self._capture_all()
         for _ in range(num_steps):
             t = self._exp_buffer.get_buffer_head()
             if graphed:

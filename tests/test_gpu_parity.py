@@ -418,7 +418,7 @@ def test_cuda_graph_rollout_is_bit_identical_to_eager():
 
     eager, s0 = run(False)
     graphed, s1 = run(True)
-    assert len(graphed._graphs_pre) == graphed._steps_per_iter and len(graphed._graphs_post) >= graphed._steps_per_iter
+    assert len(graphed._graphs_pre) == graphed._steps_per_iter and len(graphed._graphs_post) == 3 * graphed._steps_per_iter
     assert len(eager._graphs_pre) == 0
     for it, (x, y) in enumerate(zip(s0, s1)):
         for k in x:
