@@ -341,9 +341,22 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+def _ncu_traffic(key):
+    """dram bytes read + written per launch from the committed `ncu --set full` capture (profiles/r01_ncu_metrics.json)."""
+    try:
+        with open(os.path.join(REPO, "profiles", "r01_ncu_metrics.json")) as f:
+            m = json.load(f)[key]
+        return int(m["dram_bytes_read"]) + int(m["dram_bytes_write"])
+    except (OSError, KeyError, ValueError):
+        return None
+
+
 def step_kernel_roofline(agent, hbm_peak):
     """The HBM-bound stage: the fused per-env step kernel (csrc/step.cu), 5,624 algorithmic bytes per env-step
-    (SURVEY 8d), timed launch by launch with CUDA events while it writes successive experience rows."""
+    (SURVEY 8d).  `reps` back-to-back launches through the C-ABI (structs prepared beforehand, successive experience
+    rows) between one CUDA-event pair on the launch stream -> average launch duration."""
+    import ctypes as C
+
     import torch
     from add_gym_b200 import _lib
     core, N, T = agent._core, agent.get_num_envs(), agent._steps_per_iter
@@ -352,21 +365,25 @@ def step_kernel_roofline(agent, hbm_peak):
         core.step(flags, exp_row=agent._exp_row(t % T))
     torch.cuda.synchronize()
     reps = 20
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
-    for i, (a, b) in enumerate(evs):
-        row = agent._exp_row(i % T)
-        sim = core.sim_struct()          # noqa: F841  (struct assembly is host work, outside the events)
-        a.record()
-        core.step(flags, exp_row=row)
-        b.record()
+    rows = [agent._exp_row(i % T) for i in range(reps)]
+    sim = core.sim_struct()
+    L = _lib.lib()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(reps):
+        L.addk_env_step(_lib.stream(), C.byref(core.task), C.byref(core.c_lib), C.byref(sim), C.byref(core.c_env),
+                        C.byref(rows[i]), _lib.ptr(core.dof_err_w), None, C.c_int(N), C.c_int(i % 3), C.c_int(flags))
+    e1.record()
     torch.cuda.synchronize()
-    ms = sorted(a.elapsed_time(b) for a, b in evs)[reps // 2]
+    ms = e0.elapsed_time(e1) / reps
     nbytes = 5624.0 * N
     achieved = nbytes / (ms * 1e-3) / 1e9
     return {"bound": "hbm", "kernel": "env_step_kernel (fused obs/disc-obs/reward/done/record)", "achieved": achieved,
-            "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None, "median_launch_ms": ms,
+            "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+            "traffic": _ncu_traffic("env_step_kernel_32768") if N == 32768 else None, "avg_launch_ms": ms,
             "algorithmic_bytes_per_launch": nbytes, "envs": N,
-            "note": "event pair around one ctypes call: includes ~5 us of launch latency; meaningful at N >= 32768"}
+            "note": "issue-bound, not HBM-bound (ncu: 65 % issue slots busy, 15 % DRAM); one launch is shorter than "
+                    "the DRAM pipeline fill at 4096 envs -- the fraction is meaningful at 32768 envs (config 5)"}
 
 
 def dominant_kernel_roofline(agent, args, hbm_peak, tc_peak, peak_src):
@@ -405,8 +422,9 @@ def dominant_kernel_roofline(agent, args, hbm_peak, tc_peak, peak_src):
     ms = sum(a.elapsed_time(b) for a, b in evs) / reps
     flops = 2.0 * M * Nd * Kd
     achieved = flops / (ms * 1e-3) / 1e12
+    traffic = _ncu_traffic("dense_layer_16384x1024x1024_tf32x3") if (args.precision == "tf32x3" and M == 16384) else None
     return {"bound": "tensor", "kernel": "dense layer %dx%dx%d (%s)" % (M, Nd, Kd, args.precision), "achieved": achieved,
-            "peak": tc_peak, "unit": "TFLOP/s", "frac": achieved / tc_peak, "traffic": None, "peak_source": peak_src,
+            "peak": tc_peak, "unit": "TFLOP/s", "frac": achieved / tc_peak, "traffic": traffic, "peak_source": peak_src,
             "avg_launch_ms": ms, "algorithmic_flops_per_launch": flops}
 
 
