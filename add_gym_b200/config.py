@@ -35,11 +35,11 @@ _AGENT = {
         "critic_net": "fc_3layers_1024units",
         "disc_net": "fc_2layers_1024units",
         # B200 path only: arithmetic of the MLP contractions.
-        #   "fp32"  : IEEE fp32 FMA on the CUDA cores (parity reference path)
-        #   "tf32x3": tcgen05 kind::tf32, 3-pass split (fp32-class accuracy)
-        #   "tf32"  : tcgen05 kind::tf32, single pass (what the reference runs on GPU, main.py:17-18)
-        #   "bf16"  : tcgen05 kind::f16 bf16 operands, fp32 accumulate (BASELINE config 4)
-        "mlp_precision": "fp32",
+        #   "tf32x3": tcgen05 kind::tf32, 3-pass hi/lo split with a drained accumulator: fp32-class accuracy
+        #             (3.3e-7 per layer), the default -- meets the same 1e-5 parity bar as "fp32"
+        #   "fp32"  : IEEE fp32 FMA on the CUDA cores (first parity path, ~4x slower)
+        #   "tf32"  : tcgen05 kind::tf32, single pass (what the reference runs on a GPU, main.py:17-18)
+        "mlp_precision": "tf32x3",
     },
     "optimizer": {"type": "Adam", "learning_rate": 1e-4},
     "discount": 0.99,
