@@ -382,6 +382,276 @@ __global__ void __launch_bounds__(WPB * 32) env_step_kernel(const __grid_constan
 }
 
 // ------------------------------------------------------------------------------------------------
+// Lean instance of the step kernel for the reference's default task (configs/task/pose.yaml: 29 dofs, 6 target steps,
+// 3 discriminator steps, global obs with root height, no velocity / phase obs).  Same arithmetic, op for op, as
+// env_step_kernel above; what changes is the bookkeeping: every offset is a compile-time constant, the 13 quaternion
+// -> tangent/normal conversions run in 13 lanes at once, the row assembly is a handful of unrolled shared-memory copies.
+// The generic kernel is issue-bound (2,220 warp-instructions per env); this one is sized to let HBM be the limit.
+//
+// Shared memory per warp (floats): rows[9][36] pose halves of the table rows (0 = ref at t, 1..6 = targets, 7..8 =
+// demo t-0.02 / t-0.01), refv[36] velocity half of the ref row, sim[72], hist[3][36] (oldest..newest), obs[264],
+// disc[116], demo[116].
+// ------------------------------------------------------------------------------------------------
+namespace fast {
+constexpr int D = 29, HALF = 36, RS = 72, NT = 6, NH = 3, OBS = 264, DISC = 114, STEP = 38;
+constexpr int O_ROWS = 0, O_REFV = 9 * HALF, O_SIM = O_REFV + HALF, O_HIST = O_SIM + RS, O_OBS = O_HIST + NH * HALF,
+              O_DISC = O_OBS + OBS, O_DEMO = O_DISC + 116, PER_WARP = O_DEMO + 116;
+}  // namespace fast
+
+__global__ void __launch_bounds__(WPB * 32) env_step_fast_kernel(const __grid_constant__ StepParams p) {
+  using namespace fast;
+  extern __shared__ __align__(16) float smem[];
+  const addk_task& tk = p.task;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int e = blockIdx.x * WPB + warp;
+  if (e >= p.n) return;
+  if ((p.flags & F_MASKED) && !p.env_mask[e]) return;
+  float* const sw = smem + (size_t)warp * PER_WARP;
+  float* const s_rows = sw + O_ROWS;
+  float* const s_refv = sw + O_REFV;
+  float* const s_sim = sw + O_SIM;
+  float* const s_hist = sw + O_HIST;
+  float* const s_obs = sw + O_OBS;
+  float* const s_disc = sw + O_DISC;
+  float* const s_demo = sw + O_DEMO;
+  const bool push = (p.flags & F_UPDATE_MOTION) != 0;
+
+  // ---- time, clip, table rows ---------------------------------------------------------------------
+  float t = 0.f;
+  if (lane == 0) {
+    t = p.env.time_buf[e];
+    if (p.flags & F_ADVANCE) {
+      t = add_rn(t, tk.ctrl_dt);
+      p.env.time_buf[e] = t;
+    }
+  }
+  t = __shfl_sync(0xffffffffu, t, 0);
+  const long long mid = p.env.motion_ids[e];
+  const float mt = add_rn(t, p.env.motion_time_offsets[e]);
+  const long long start = p.lib.start_idx[mid];
+  // lane b < 9 owns the row index of pose block b
+  long long my_row = 0;
+  if (lane < 9) {
+    float tt = mt;
+    if (lane >= 1 && lane <= 6) tt = add_rn(mt, tk.tar_offsets[lane - 1]);
+    if (lane >= 7) tt = add_rn(mt, tk.disc_offsets[lane - 7]);
+    my_row = table_row(p.lib, tt, tk.dt_inv, start);
+  }
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {        // 81 float4 of pose halves + 9 float4 of the ref row's velocity half
+    const int i = lane + 32 * r;
+    const int b = i < 81 ? i / 9 : 0;
+    const int c = i < 81 ? i - 9 * b : i - 81;
+    const long long row = __shfl_sync(0xffffffffu, my_row, b);
+    if (i < 90) {
+      const float* src = p.lib.table + (size_t)row * RS + (i < 81 ? 0 : HALF) + 4 * c;
+      float* dst = (i < 81 ? s_rows + HALF * b : s_refv) + 4 * c;
+      stg4(dst, ldg4(src));
+    }
+  }
+  // ---- simulator state -> packed row (pose half | velocity half) ---------------------------------------
+  if (lane < D) {
+    s_sim[7 + lane] = p.sim.dof_pos[(size_t)e * p.sim.ld_dof_pos + lane];
+    s_sim[HALF + 6 + lane] = p.sim.dof_vel[(size_t)e * p.sim.ld_dof_vel + lane];
+  }
+  if (lane < 3) {
+    s_sim[lane] = p.sim.root_pos[(size_t)e * p.sim.ld_root_pos + lane];
+    s_sim[HALF + lane] = p.sim.root_vel[(size_t)e * p.sim.ld_root_vel + lane];
+    s_sim[HALF + 3 + lane] = p.sim.root_ang[(size_t)e * p.sim.ld_root_ang + lane];
+  }
+  if (lane < 4) s_sim[3 + lane] = p.sim.root_rot[(size_t)e * p.sim.ld_root_rot + lane];
+  if (lane == 31) { s_sim[HALF + 6 + D] = 0.0f; }          // the one pad float of the velocity half (7 + D == HALF)
+  // ---- history ring: logical j (oldest..newest) lives in slot (newest_slot + 1 + j) % NH; pose halves only --------
+  float* const g_hist = p.env.hist + (size_t)e * NH * p.env.hist_stride;
+  {
+    const int nload = push ? 2 * 9 : 3 * 9;      // with a push the newest entry is the simulator state itself
+    if (lane < nload) {
+      const int j = lane / 9, c = lane - 9 * j;
+      const int slot = (p.newest_slot + 1 + j) % NH;
+      stg4(s_hist + HALF * j + 4 * c, *reinterpret_cast<const float4*>(g_hist + (size_t)slot * p.env.hist_stride + 4 * c));
+    }
+  }
+  __syncwarp();
+  if (push) {
+    if (lane < RS / 4) {
+      const float4 v = *reinterpret_cast<const float4*>(s_sim + 4 * lane);
+      stg4(g_hist + (size_t)p.newest_slot * p.env.hist_stride + 4 * lane, v);
+      if (lane < HALF / 4) stg4(s_hist + 2 * HALF + 4 * lane, v);
+    }
+    // _update_ref_motion: ref_* <- table row (add_observation.py:163-175)
+    if (lane < D) {
+      p.env.ref_dof_pos[(size_t)e * D + lane] = s_rows[7 + lane];
+      p.env.ref_dof_vel[(size_t)e * D + lane] = s_refv[6 + lane];
+    }
+    if (lane < 3) {
+      p.env.ref_root_pos[(size_t)e * 3 + lane] = s_rows[lane];
+      p.env.ref_root_vel[(size_t)e * 3 + lane] = s_refv[lane];
+      p.env.ref_root_ang_vel[(size_t)e * 3 + lane] = s_refv[3 + lane];
+    }
+    if (lane < 4) p.env.ref_root_rot[(size_t)e * 4 + lane] = s_rows[3 + lane];
+  }
+  __syncwarp();
+
+  // ---- 13 quaternions -> tangent / normal, one per lane ----------------------------------------------
+  //   lane 0      simulator root            -> obs[1..6]
+  //   lanes 1..6  target k = lane-1         -> obs[36 + 38k + 3 ..]
+  //   lanes 7..9  history j = lane-7        -> disc[38j + 3 ..]
+  //   lanes 10..12 demo j = lane-10         -> demo[38j + 3 ..]   (j = 2 is the ref row itself)
+  if (lane < 13) {
+    const float* src;
+    float* dst;
+    if (lane == 0) { src = s_sim + 3; dst = s_obs + 1; }
+    else if (lane <= 6) { src = s_rows + HALF * lane + 3; dst = s_obs + 36 + STEP * (lane - 1) + 3; }
+    else if (lane <= 9) { src = s_hist + HALF * (lane - 7) + 3; dst = s_disc + STEP * (lane - 7) + 3; }
+    else { const int j = lane - 10; src = s_rows + HALF * (j < 2 ? 7 + j : 0) + 3; dst = s_demo + STEP * j + 3; }
+    float o6[6];
+    quat_to_tan_norm(ldq(src), o6);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) dst[i] = o6[i];
+  }
+  // ---- copies ---------------------------------------------------------------------------------------------
+  if (lane == 31) s_obs[0] = s_sim[2];                                  // root height
+  if (lane < D) s_obs[7 + lane] = s_sim[7 + lane];                      // dof_pos
+  if (lane < 3 * NT) {                                                  // target position: xy relative to the root, z absolute
+    const int k = lane / 3, c = lane - 3 * k;
+    const float v = s_rows[HALF * (1 + k) + c];
+    s_obs[36 + STEP * k + c] = c < 2 ? sub_rn(v, s_sim[c]) : v;
+  }
+  if (lane < 3 * NH) {                                                  // discriminator positions (global obs: xyz kept)
+    const int j = lane / 3, c = lane - 3 * j;
+    s_disc[STEP * j + c] = s_hist[HALF * j + c];
+    s_demo[STEP * j + c] = s_rows[HALF * (j < 2 ? 7 + j : 0) + c];
+  }
+  if (lane < D) {
+#pragma unroll
+    for (int k = 0; k < NT; ++k) s_obs[36 + STEP * k + 9 + lane] = s_rows[HALF * (1 + k) + 7 + lane];
+#pragma unroll
+    for (int j = 0; j < NH; ++j) {
+      s_disc[STEP * j + 9 + lane] = s_hist[HALF * j + 7 + lane];
+      s_demo[STEP * j + 9 + lane] = s_rows[HALF * (j < 2 ? 7 + j : 0) + 7 + lane];
+    }
+  }
+  __syncwarp();
+
+  // ---- stream the rows out ----------------------------------------------------------------------------
+  {
+    float* g = p.env.obs_buf + (size_t)e * OBS;
+    float* gx = p.has_exp ? p.exp.next_obs + (size_t)e * OBS : nullptr;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int i = lane + 32 * r;
+      if (i < OBS / 4) {
+        const float4 v = *reinterpret_cast<const float4*>(s_obs + 4 * i);
+        stg4(g + 4 * i, v);
+        if (gx) stg4_cs(gx + 4 * i, v);
+      }
+    }
+    float* gd = p.env.disc_obs + (size_t)e * DISC;
+    float* gm = p.env.disc_obs_demo + (size_t)e * DISC;
+    float* xd = p.has_exp ? p.exp.disc_obs + (size_t)e * DISC : nullptr;
+    float* xm = p.has_exp ? p.exp.disc_obs_demo + (size_t)e * DISC : nullptr;
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int i = lane + 32 * r;
+      if (i < DISC / 2) {
+        const float2 a = *reinterpret_cast<const float2*>(s_disc + 2 * i);
+        const float2 b = *reinterpret_cast<const float2*>(s_demo + 2 * i);
+        *reinterpret_cast<float2*>(gd + 2 * i) = a;
+        *reinterpret_cast<float2*>(gm + 2 * i) = b;
+        if (xd) { __stcs(reinterpret_cast<float2*>(xd + 2 * i), a); __stcs(reinterpret_cast<float2*>(xm + 2 * i), b); }
+      }
+    }
+  }
+  if (p.has_exp && lane == 0) {
+    p.exp.motion_ids[e] = mid;
+    p.exp.motion_times[e] = mt;
+  }
+  if (!(p.flags & F_REWARD_DONE)) return;
+
+  // ---- tracking reward (add_reward.py:104-177) and done flags (add_done.py:97-147) --------------------------
+  float pe = 0.f, ve = 0.f, de = 0.f;
+  if (lane < D) {
+    const float w = p.dof_err_w[lane];
+    const float pd = sub_rn(s_rows[7 + lane], s_sim[7 + lane]);
+    const float vd = sub_rn(s_refv[6 + lane], s_sim[HALF + 6 + lane]);
+    pe = mul_rn(mul_rn(w, pd), pd);
+    ve = mul_rn(mul_rn(w, vd), vd);
+    de = mul_rn(pd, pd);
+  }
+  pe = warp_sum(pe); ve = warp_sum(ve); de = warp_sum(de);
+  int contact = 0;
+  if (lane < tk.contact_slots && p.sim.valid) {
+    const size_t ci = (size_t)e * tk.contact_slots + lane;
+    if (p.sim.valid[ci]) {
+      const int la = p.sim.link_a[ci], lb = p.sim.link_b[ci];
+      const bool ha = la >= 0 && la < 64 && ((tk.noncontact_link_mask >> la) & 1ull);
+      const bool hb = lb >= 0 && lb < 64 && ((tk.noncontact_link_mask >> lb) & 1ull);
+      contact = (ha || hb) ? 1 : 0;
+    }
+  }
+  contact = __any_sync(0xffffffffu, contact);
+  if (lane == 0) {
+    const Vec3 rp = {s_sim[0], s_sim[1], s_sim[2]}, tp = {s_rows[0], s_rows[1], s_rows[2]};
+    const Vec3 dpos = {sub_rn(tp.x, rp.x), sub_rn(tp.y, rp.y), sub_rn(tp.z, rp.z)};
+    Vec3 dpos_r = dpos;
+    if (!tk.track_root) { dpos_r.x = 0.f; dpos_r.y = 0.f; }
+    if (!tk.track_root_h) dpos_r.z = 0.f;
+    const float root_pos_err = add_rn(add_rn(mul_rn(dpos_r.x, dpos_r.x), mul_rn(dpos_r.y, dpos_r.y)), mul_rn(dpos_r.z, dpos_r.z));
+    Quat rq = ldq(s_sim + 3), tq = ldq(s_rows + 3);
+    Vec3 rv = {s_sim[HALF], s_sim[HALF + 1], s_sim[HALF + 2]}, ra = {s_sim[HALF + 3], s_sim[HALF + 4], s_sim[HALF + 5]};
+    Vec3 tv = {s_refv[0], s_refv[1], s_refv[2]}, ta = {s_refv[3], s_refv[4], s_refv[5]};
+    if (!tk.track_root) {  // convert_to_local_root (add_reward.py:91-102)
+      const Quat h0 = calc_heading_quat_inv(rq), h1 = calc_heading_quat_inv(tq);
+      rv = quat_rotate(h0, rv); ra = quat_rotate(h0, ra); rq = quat_mul(h0, rq);
+      tv = quat_rotate(h1, tv); ta = quat_rotate(h1, ta); tq = quat_mul(h1, tq);
+    }
+    float rot_err = quat_diff_angle(rq, tq);
+    rot_err = mul_rn(rot_err, rot_err);
+    const Vec3 dv = {sub_rn(tv.x, rv.x), sub_rn(tv.y, rv.y), sub_rn(tv.z, rv.z)};
+    const Vec3 da = {sub_rn(ta.x, ra.x), sub_rn(ta.y, ra.y), sub_rn(ta.z, ra.z)};
+    const float vel_err = add_rn(add_rn(mul_rn(dv.x, dv.x), mul_rn(dv.y, dv.y)), mul_rn(dv.z, dv.z));
+    const float ang_err = add_rn(add_rn(mul_rn(da.x, da.x), mul_rn(da.y, da.y)), mul_rn(da.z, da.z));
+    const float pose_r = expf(mul_rn(-tk.pose_scale, pe));
+    const float vel_r = expf(mul_rn(-tk.vel_scale, ve));
+    const float root_pose_r = expf(mul_rn(-tk.root_pose_scale, add_rn(root_pos_err, mul_rn(0.1f, rot_err))));
+    const float root_vel_r = expf(mul_rn(-tk.root_vel_scale, add_rn(vel_err, mul_rn(0.1f, ang_err))));
+    const float r = add_rn(add_rn(add_rn(mul_rn(tk.pose_w, pose_r), mul_rn(tk.vel_w, vel_r)), mul_rn(tk.root_pose_w, root_pose_r)),
+                           mul_rn(tk.root_vel_w, root_vel_r));
+    int done = 0;
+    if (t >= tk.ep_len) done = 3;
+    if (mt >= p.lib.lengths[mid] && p.lib.loop_modes[mid] != 1) done = 2;
+    if (tk.enable_early_termination) {
+      bool failed = contact != 0;
+      if (tk.pose_termination) {
+        bool pf = (de / (float)D) > tk.pose_termination_dist;
+        if (tk.track_root) {
+          const float re = add_rn(add_rn(mul_rn(dpos.x, dpos.x), mul_rn(dpos.y, dpos.y)), mul_rn(dpos.z, dpos.z));
+          pf = pf || (re > tk.pose_termination_dist);
+        }
+        failed = failed || pf;
+      }
+      if (failed && t > 0.0f) done = 1;
+    }
+    p.env.reward[e] = r;
+    p.env.done[e] = done;
+    if (p.has_exp) { p.exp.reward[e] = r; p.exp.done[e] = done; }
+    if (p.env.return_buf) {        // ReturnTracker.update (base_agent.py:596-621)
+      float ret = add_rn(p.env.return_buf[e], r);
+      long long len = p.env.ep_len_buf[e] + 1;
+      if (done != 0) {
+        atomicAdd(p.env.tracker_sums, (double)ret);
+        atomicAdd(p.env.tracker_sums + 1, (double)len);
+        atomicAdd(reinterpret_cast<unsigned long long*>(p.env.tracker_count), 1ull);
+        p.env.eps_per_env[e] += 1;
+        ret = 0.f; len = 0;
+      }
+      p.env.return_buf[e] = ret;
+      p.env.ep_len_buf[e] = len;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 struct ResetParams {
   addk_task task;
   addk_motion_lib lib;
@@ -573,15 +843,19 @@ extern "C" int addk_env_step(void* stream, const addk_task* task, const addk_mot
   if (smem > 200 * 1024) return ADDK_ERR_UNSUPPORTED;
   const bool fast = D == 29 && lib->row_stride == 72 && task->enable_tar_obs && task->num_tar_steps == 6 &&
                     task->num_disc_steps == 3 && task->global_obs && task->root_height_obs && !task->enable_vel_obs &&
-                    !task->enable_phase_obs && task->obs_dim == 264 && task->disc_obs_dim == 114;
+                    !task->enable_phase_obs && task->obs_dim == 264 && task->disc_obs_dim == 114 &&
+                    task->disc_offsets[2] == 0.0f;   // the newest demo row is the reference row itself
   static int configured = 0;
   if (smem > 48 * 1024 && configured < smem) {
-    cudaFuncSetAttribute(env_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     cudaFuncSetAttribute(env_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     configured = smem;
   }
-  if (fast) env_step_kernel<true><<<(num_envs + WPB - 1) / WPB, WPB * 32, smem, (cudaStream_t)stream>>>(p);
-  else env_step_kernel<false><<<(num_envs + WPB - 1) / WPB, WPB * 32, smem, (cudaStream_t)stream>>>(p);
+  if (fast && env->hist_stride == 72) {
+    const int fsm = fast::PER_WARP * WPB * (int)sizeof(float);
+    env_step_fast_kernel<<<(num_envs + WPB - 1) / WPB, WPB * 32, fsm, (cudaStream_t)stream>>>(p);
+  } else {
+    env_step_kernel<false><<<(num_envs + WPB - 1) / WPB, WPB * 32, smem, (cudaStream_t)stream>>>(p);
+  }
   ADDK_CHECK_LAUNCH();
   return ADDK_OK;
 }
