@@ -416,19 +416,49 @@ __global__ void __launch_bounds__(WPB * 32) env_step_fast_kernel(const __grid_co
   float* const s_demo = sw + O_DEMO;
   const bool push = (p.flags & F_UPDATE_MOTION) != 0;
 
-  // ---- time, clip, table rows ---------------------------------------------------------------------
+  // ---- issue every independent global load first (the kernel is latency-bound: in-order issue would otherwise
+  //      serialise the round trips behind the first shared-memory store that waits for its data) -----------------
   float t = 0.f;
-  if (lane == 0) {
-    t = p.env.time_buf[e];
-    if (p.flags & F_ADVANCE) {
-      t = add_rn(t, tk.ctrl_dt);
-      p.env.time_buf[e] = t;
-    }
+  if (lane == 0) t = p.env.time_buf[e];
+  const long long mid = p.env.motion_ids[e];
+  const float off = p.env.motion_time_offsets[e];
+  float sim_dp = 0.f, sim_dv = 0.f, sim_p = 0.f, sim_v = 0.f, sim_a = 0.f, sim_q = 0.f, w_dof = 0.f;
+  if (lane < D) {
+    sim_dp = p.sim.dof_pos[(size_t)e * p.sim.ld_dof_pos + lane];
+    sim_dv = p.sim.dof_vel[(size_t)e * p.sim.ld_dof_vel + lane];
+    if (p.flags & F_REWARD_DONE) w_dof = p.dof_err_w[lane];
+  }
+  if (lane < 3) {
+    sim_p = p.sim.root_pos[(size_t)e * p.sim.ld_root_pos + lane];
+    sim_v = p.sim.root_vel[(size_t)e * p.sim.ld_root_vel + lane];
+    sim_a = p.sim.root_ang[(size_t)e * p.sim.ld_root_ang + lane];
+  }
+  if (lane < 4) sim_q = p.sim.root_rot[(size_t)e * p.sim.ld_root_rot + lane];
+  float* const g_hist = p.env.hist + (size_t)e * NH * p.env.hist_stride;
+  const int nload = push ? 2 * 9 : 3 * 9;        // with a push the newest history entry is the simulator state itself
+  float4 hv = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int hj = lane / 9, hc = lane - 9 * hj;
+  if (lane < nload) {
+    const int slot = (p.newest_slot + 1 + hj) % NH;   // logical j (oldest..newest) lives in slot (newest_slot+1+j) % NH
+    hv = *reinterpret_cast<const float4*>(g_hist + (size_t)slot * p.env.hist_stride + 4 * hc);
+  }
+  int c_valid = 0, c_la = -1, c_lb = -1;
+  if ((p.flags & F_REWARD_DONE) && lane < tk.contact_slots && p.sim.valid) {
+    const size_t ci = (size_t)e * tk.contact_slots + lane;
+    c_valid = p.sim.valid[ci]; c_la = p.sim.link_a[ci]; c_lb = p.sim.link_b[ci];
+  }
+  float ret0 = 0.f; long long len0 = 0;
+  if ((p.flags & F_REWARD_DONE) && lane == 0 && p.env.return_buf) { ret0 = p.env.return_buf[e]; len0 = p.env.ep_len_buf[e]; }
+  // ---- dependent chain: clip -> start row / length; time -> table rows -----------------------------------
+  const long long start = p.lib.start_idx[mid];
+  float m_len = 0.f; int m_loop = 0;
+  if (lane == 0) { m_len = p.lib.lengths[mid]; m_loop = p.lib.loop_modes[mid]; }
+  if (lane == 0 && (p.flags & F_ADVANCE)) {
+    t = add_rn(t, tk.ctrl_dt);
+    p.env.time_buf[e] = t;
   }
   t = __shfl_sync(0xffffffffu, t, 0);
-  const long long mid = p.env.motion_ids[e];
-  const float mt = add_rn(t, p.env.motion_time_offsets[e]);
-  const long long start = p.lib.start_idx[mid];
+  const float mt = add_rn(t, off);
   // lane b < 9 owns the row index of pose block b
   long long my_row = 0;
   if (lane < 9) {
@@ -437,39 +467,28 @@ __global__ void __launch_bounds__(WPB * 32) env_step_fast_kernel(const __grid_co
     if (lane >= 7) tt = add_rn(mt, tk.disc_offsets[lane - 7]);
     my_row = table_row(p.lib, tt, tk.dt_inv, start);
   }
+  float4 tv4[3];
 #pragma unroll
   for (int r = 0; r < 3; ++r) {        // 81 float4 of pose halves + 9 float4 of the ref row's velocity half
     const int i = lane + 32 * r;
     const int b = i < 81 ? i / 9 : 0;
     const int c = i < 81 ? i - 9 * b : i - 81;
     const long long row = __shfl_sync(0xffffffffu, my_row, b);
-    if (i < 90) {
-      const float* src = p.lib.table + (size_t)row * RS + (i < 81 ? 0 : HALF) + 4 * c;
-      float* dst = (i < 81 ? s_rows + HALF * b : s_refv) + 4 * c;
-      stg4(dst, ldg4(src));
-    }
+    tv4[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < 90) tv4[r] = ldg4(p.lib.table + (size_t)row * RS + (i < 81 ? 0 : HALF) + 4 * c);
   }
-  // ---- simulator state -> packed row (pose half | velocity half) ---------------------------------------
-  if (lane < D) {
-    s_sim[7 + lane] = p.sim.dof_pos[(size_t)e * p.sim.ld_dof_pos + lane];
-    s_sim[HALF + 6 + lane] = p.sim.dof_vel[(size_t)e * p.sim.ld_dof_vel + lane];
-  }
-  if (lane < 3) {
-    s_sim[lane] = p.sim.root_pos[(size_t)e * p.sim.ld_root_pos + lane];
-    s_sim[HALF + lane] = p.sim.root_vel[(size_t)e * p.sim.ld_root_vel + lane];
-    s_sim[HALF + 3 + lane] = p.sim.root_ang[(size_t)e * p.sim.ld_root_ang + lane];
-  }
-  if (lane < 4) s_sim[3 + lane] = p.sim.root_rot[(size_t)e * p.sim.ld_root_rot + lane];
+  // ---- everything into shared memory -------------------------------------------------------------------------
+  if (lane < D) { s_sim[7 + lane] = sim_dp; s_sim[HALF + 6 + lane] = sim_dv; }
+  if (lane < 3) { s_sim[lane] = sim_p; s_sim[HALF + lane] = sim_v; s_sim[HALF + 3 + lane] = sim_a; }
+  if (lane < 4) s_sim[3 + lane] = sim_q;
   if (lane == 31) { s_sim[HALF + 6 + D] = 0.0f; }          // the one pad float of the velocity half (7 + D == HALF)
-  // ---- history ring: logical j (oldest..newest) lives in slot (newest_slot + 1 + j) % NH; pose halves only --------
-  float* const g_hist = p.env.hist + (size_t)e * NH * p.env.hist_stride;
-  {
-    const int nload = push ? 2 * 9 : 3 * 9;      // with a push the newest entry is the simulator state itself
-    if (lane < nload) {
-      const int j = lane / 9, c = lane - 9 * j;
-      const int slot = (p.newest_slot + 1 + j) % NH;
-      stg4(s_hist + HALF * j + 4 * c, *reinterpret_cast<const float4*>(g_hist + (size_t)slot * p.env.hist_stride + 4 * c));
-    }
+  if (lane < nload) stg4(s_hist + HALF * hj + 4 * hc, hv);
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const int i = lane + 32 * r;
+    const int b = i < 81 ? i / 9 : 0;
+    const int c = i < 81 ? i - 9 * b : i - 81;
+    if (i < 90) stg4((i < 81 ? s_rows + HALF * b : s_refv) + 4 * c, tv4[r]);
   }
   __syncwarp();
   if (push) {
@@ -571,23 +590,18 @@ __global__ void __launch_bounds__(WPB * 32) env_step_fast_kernel(const __grid_co
   // ---- tracking reward (add_reward.py:104-177) and done flags (add_done.py:97-147) --------------------------
   float pe = 0.f, ve = 0.f, de = 0.f;
   if (lane < D) {
-    const float w = p.dof_err_w[lane];
-    const float pd = sub_rn(s_rows[7 + lane], s_sim[7 + lane]);
-    const float vd = sub_rn(s_refv[6 + lane], s_sim[HALF + 6 + lane]);
-    pe = mul_rn(mul_rn(w, pd), pd);
-    ve = mul_rn(mul_rn(w, vd), vd);
+    const float pd = sub_rn(s_rows[7 + lane], sim_dp);
+    const float vd = sub_rn(s_refv[6 + lane], sim_dv);
+    pe = mul_rn(mul_rn(w_dof, pd), pd);
+    ve = mul_rn(mul_rn(w_dof, vd), vd);
     de = mul_rn(pd, pd);
   }
   pe = warp_sum(pe); ve = warp_sum(ve); de = warp_sum(de);
   int contact = 0;
-  if (lane < tk.contact_slots && p.sim.valid) {
-    const size_t ci = (size_t)e * tk.contact_slots + lane;
-    if (p.sim.valid[ci]) {
-      const int la = p.sim.link_a[ci], lb = p.sim.link_b[ci];
-      const bool ha = la >= 0 && la < 64 && ((tk.noncontact_link_mask >> la) & 1ull);
-      const bool hb = lb >= 0 && lb < 64 && ((tk.noncontact_link_mask >> lb) & 1ull);
-      contact = (ha || hb) ? 1 : 0;
-    }
+  if (c_valid) {
+    const bool ha = c_la >= 0 && c_la < 64 && ((tk.noncontact_link_mask >> c_la) & 1ull);
+    const bool hb = c_lb >= 0 && c_lb < 64 && ((tk.noncontact_link_mask >> c_lb) & 1ull);
+    contact = (ha || hb) ? 1 : 0;
   }
   contact = __any_sync(0xffffffffu, contact);
   if (lane == 0) {
@@ -619,7 +633,7 @@ __global__ void __launch_bounds__(WPB * 32) env_step_fast_kernel(const __grid_co
                            mul_rn(tk.root_vel_w, root_vel_r));
     int done = 0;
     if (t >= tk.ep_len) done = 3;
-    if (mt >= p.lib.lengths[mid] && p.lib.loop_modes[mid] != 1) done = 2;
+    if (mt >= m_len && m_loop != 1) done = 2;
     if (tk.enable_early_termination) {
       bool failed = contact != 0;
       if (tk.pose_termination) {
@@ -636,8 +650,8 @@ __global__ void __launch_bounds__(WPB * 32) env_step_fast_kernel(const __grid_co
     p.env.done[e] = done;
     if (p.has_exp) { p.exp.reward[e] = r; p.exp.done[e] = done; }
     if (p.env.return_buf) {        // ReturnTracker.update (base_agent.py:596-621)
-      float ret = add_rn(p.env.return_buf[e], r);
-      long long len = p.env.ep_len_buf[e] + 1;
+      float ret = add_rn(ret0, r);
+      long long len = len0 + 1;
       if (done != 0) {
         atomicAdd(p.env.tracker_sums, (double)ret);
         atomicAdd(p.env.tracker_sums + 1, (double)len);
