@@ -69,7 +69,8 @@ class AddkGemmArgs(C.Structure):
                 ("ldc", C.c_int32), ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32), ("bias", C.c_void_p),
                 ("a_mean", C.c_void_p), ("a_std", C.c_void_p), ("relu_mask_src", C.c_void_p), ("ld_mask", C.c_int32),
                 ("trans_a", C.c_int32), ("trans_b", C.c_int32), ("relu", C.c_int32), ("split_k", C.c_int32),
-                ("accumulate", C.c_int32), ("slab_stride", C.c_int64)]
+                ("accumulate", C.c_int32), ("slab_stride", C.c_int64),
+                ("A16", C.c_void_p), ("B16", C.c_void_p), ("C16", C.c_void_p)]
 
 
 class AddkError(RuntimeError):

@@ -146,7 +146,7 @@ class ADDModel(torch.nn.Module):
                               C=y.data_ptr(), ldc=lin.out_features, M=x.shape[0], N=lin.out_features,
                               K=lin.in_features, bias=lin.bias.data_ptr(), a_mean=None, a_std=None,
                               relu_mask_src=None, ld_mask=0, trans_a=0, trans_b=1, relu=int(relu), split_k=1,
-                              accumulate=0, slab_stride=0)
+                              accumulate=0, slab_stride=0, A16=None, B16=None, C16=None)
         _lib.ptr(x)
         _lib.check(_lib.lib().addk_gemm(_lib.stream(), C.byref(a), C.c_int(self.precision)), "addk_gemm")
         return y

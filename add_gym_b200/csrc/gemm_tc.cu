@@ -28,6 +28,8 @@ namespace addk { int sgemm_launch(cudaStream_t st, const addk_gemm_args& a); }
 
 namespace addk_tc {
 
+static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
+
 constexpr int BM = 128;        // UMMA M
 constexpr int UMMA_K = 8;      // kind::tf32
 constexpr int NTHREADS = 192;
@@ -39,6 +41,7 @@ struct Params {
   int kb_per_split;            // k-blocks per blockIdx.z
   int a_mn, b_mn;              // operand is MN-major (memory rows = contraction index)
   long long slab_stride;       // floats between split-K slabs
+  void* C16;                   // bf16 kernel: optional bf16 copy of the output (same leading dimension)
   int pair_flags;              // CTA-pair kernel experiments: bit0 cluster-scope waits, bit1 relaxed remote arrives
 };
 
@@ -396,8 +399,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // ---------------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------------
-static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
-
 static bool resolve_encode() {
   if (g_encode) return true;
   void* fn = nullptr;
@@ -1106,6 +1107,238 @@ static int launch_x3_pair(cudaStream_t st, const CUtensorMap& ta, const CUtensor
   return ADDK_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// bf16 kernel (precision "bf16", BASELINE config 4): bf16 operands in HBM (the producers write a bf16 twin of every
+// activation / gradient / weight), tcgen05.mma.kind::f16 (M=128, N=BN, K=16), fp32 accumulation in TMEM, fp32 and/or
+// bf16 output.  64-element (128-byte) k-blocks; K-major tiles use SWIZZLE_128B, MN-major tiles the standard 16-bit
+// MN-major SWIZZLE_128B atoms (64 MN x 8 k), one TMA box = 64 MN x 64 k = 8 KB.  6 warps: TMA producer, MMA issuer,
+// 4 epilogue warps.
+// ---------------------------------------------------------------------------------------------------------------
+template <int BN>
+struct CfgH {
+  static constexpr int BK = 64;
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 6 ? 6 : (200 * 1024) / STAGE_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+  static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+  static constexpr uint32_t MN_BOX_BYTES = BK * 128u;     // 64 k-rows x 128 bytes (64 bf16 along MN)
+};
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(NTHREADS, 1)
+gemm_tc_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
+  using C = CfgH<BN>;
+  constexpr int BK = C::BK, UK = 16;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_u32 = smem_u32(smem_raw);
+  const uint32_t base = (raw_u32 + 1023u) & ~1023u;
+  uint8_t* const base_ptr = smem_raw + (base - raw_u32);
+  const uint32_t bars = base + C::STAGES * C::STAGE_BYTES;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (C::STAGES + s); };
+  const uint32_t tmem_full_bar = bars + 8u * (2 * C::STAGES);
+  const uint32_t tmem_ptr_addr = bars + 8u * (2 * C::STAGES + 1);
+  auto a_t = [&](int s) { return base + (uint32_t)s * C::STAGE_BYTES; };
+  auto b_t = [&](int s) { return a_t(s) + C::A_BYTES; };
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int kb_total = (p.K + BK - 1) / BK;
+  const int kb_begin = blockIdx.z * p.kb_per_split;
+  const int kb_end = min(kb_total, kb_begin + p.kb_per_split);
+  const int num_kb = kb_end - kb_begin;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < C::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "r"((uint32_t)C::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr) : "memory");
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int i = 0; i < num_kb; ++i) {
+        const int s = i % C::STAGES;
+        const uint32_t ph = (uint32_t)(i / C::STAGES) & 1u;
+        mbar_wait(empty_bar(s), ph ^ 1u);
+        mbar_expect_tx(full_bar(s), C::A_BYTES + C::B_BYTES);
+        const int k0 = (kb_begin + i) * BK;
+        if (!p.a_mn) {
+          tma_load_2d(a_t(s), &tmA, full_bar(s), k0, m0);                       // box {64 k, 128 rows}
+        } else {
+#pragma unroll
+          for (int j = 0; j < BM / 64; ++j) tma_load_2d(a_t(s) + j * C::MN_BOX_BYTES, &tmA, full_bar(s), m0 + 64 * j, k0);  // box {64 m, 64 k}
+        }
+        if (!p.b_mn) {
+          tma_load_2d(b_t(s), &tmB, full_bar(s), k0, n0);
+        } else {
+#pragma unroll
+          for (int j = 0; j < BN / 64; ++j) tma_load_2d(b_t(s) + j * C::MN_BOX_BYTES, &tmB, full_bar(s), n0 + 64 * j, k0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // instruction descriptor: D fp32, A/B bf16
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.a_mn ? 1 : 0) << 15) |
+                             ((uint32_t)(p.b_mn ? 1 : 0) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      // K-major: 128-byte rows, 8-row groups 1024 B apart, 16 k = 32 B.  MN-major: 64-MN atoms one box (8 KB) apart (LBO),
+      // 8-k groups 1024 B apart (SBO), 16 k = 2048 B.
+      const uint32_t a_lbo = p.a_mn ? C::MN_BOX_BYTES : 16u, b_lbo = p.b_mn ? C::MN_BOX_BYTES : 16u;
+      const uint32_t a_kstep = p.a_mn ? 2048u : 32u, b_kstep = p.b_mn ? 2048u : 32u;
+      uint32_t acc = 0;
+      for (int i = 0; i < num_kb; ++i) {
+        const int s = i % C::STAGES;
+        const uint32_t ph = (uint32_t)(i / C::STAGES) & 1u;
+        mbar_wait(full_bar(s), ph);
+        tc_fence_after();
+#pragma unroll
+        for (int ks = 0; ks < BK / UK; ++ks) {
+          umma_bf16(tmem_base, smem_desc(a_t(s) + ks * a_kstep, a_lbo, 1024u, 2u), smem_desc(b_t(s) + ks * b_kstep, b_lbo, 1024u, 2u),
+                    idesc, acc);
+          acc = 1;
+        }
+        umma_commit(empty_bar(s));
+      }
+      umma_commit(tmem_full_bar);
+    }
+  } else {
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const int q = warp & 3;
+    float* Cz = p.C ? p.C + (size_t)blockIdx.z * p.slab_stride : nullptr;
+    uint16_t* C16 = reinterpret_cast<uint16_t*>(p.C16);
+    const bool vec = ((p.ldc & 3) == 0) && (!Cz || (reinterpret_cast<uintptr_t>(Cz) & 15) == 0) &&
+                     (!C16 || (reinterpret_cast<uintptr_t>(C16) & 7) == 0) &&
+                     (!p.bias || ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0)) &&
+                     (!p.mask || (((p.ld_mask & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.mask) & 15) == 0)));
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    float4* stg = reinterpret_cast<float4*>(base_ptr + 4096 * q);
+    const int l_row = lane >> 3, l_c4 = lane & 7;
+    const int row = m0 + 32 * q + lane;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      if (n0 + c0 >= p.N) break;
+      float4 m4[8];
+      const int colv = n0 + c0 + 4 * l_c4;
+      const bool full4 = vec && (colv + 3 < p.N);
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int grow = m0 + 32 * q + it * 4 + l_row;
+        m4[it] = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (p.mask && full4 && grow < p.M) m4[it] = *reinterpret_cast<const float4*>(p.mask + (size_t)grow * p.ld_mask + colv);
+      }
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)c0, v);
+      if (vec) {
+#pragma unroll
+        for (int c4 = 0; c4 < 8; ++c4)
+          stg[lane * 8 + (c4 ^ (lane & 7))] = make_float4(__uint_as_float(v[4 * c4]), __uint_as_float(v[4 * c4 + 1]),
+                                                          __uint_as_float(v[4 * c4 + 2]), __uint_as_float(v[4 * c4 + 3]));
+        __syncwarp();
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.bias) {
+          if (full4) b4 = *reinterpret_cast<const float4*>(p.bias + colv);
+          else { if (colv < p.N) b4.x = p.bias[colv]; if (colv + 1 < p.N) b4.y = p.bias[colv + 1]; if (colv + 2 < p.N) b4.z = p.bias[colv + 2]; }
+        }
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int r = it * 4 + l_row;
+          const int grow = m0 + 32 * q + r;
+          float4 o = stg[r * 8 + (l_c4 ^ (r & 7))];
+          if (grow < p.M && colv < p.N) {
+            o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
+            if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+            if (full4) {
+              o.x = m4[it].x > 0.f ? o.x : 0.f; o.y = m4[it].y > 0.f ? o.y : 0.f;
+              o.z = m4[it].z > 0.f ? o.z : 0.f; o.w = m4[it].w > 0.f ? o.w : 0.f;
+              if (Cz) *reinterpret_cast<float4*>(Cz + (size_t)grow * p.ldc + colv) = o;
+              if (C16) *reinterpret_cast<uint2*>(C16 + (size_t)grow * p.ldc + colv) = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+            } else {
+              const float oo[4] = {o.x, o.y, o.z, o.w};
+              for (int e = 0; e < 4 && colv + e < p.N; ++e) {
+                float xv = oo[e];
+                if (p.mask) xv = p.mask[(size_t)grow * p.ld_mask + colv + e] > 0.f ? xv : 0.f;
+                if (Cz) Cz[(size_t)grow * p.ldc + colv + e] = xv;
+                if (C16) C16[(size_t)grow * p.ldc + colv + e] = (uint16_t)(pack_bf16x2(xv, 0.f) & 0xFFFFu);
+              }
+            }
+          }
+        }
+        __syncwarp();
+      } else if (row < p.M) {
+        for (int j = 0; j < 32; ++j) {
+          const int col = n0 + c0 + j;
+          if (col >= p.N) break;
+          float xv = __uint_as_float(v[j]);
+          if (p.bias) xv += p.bias[col];
+          if (p.relu) xv = fmaxf(xv, 0.f);
+          if (p.mask) xv = p.mask[(size_t)row * p.ld_mask + col] > 0.f ? xv : 0.f;
+          if (Cz) Cz[(size_t)row * p.ldc + col] = xv;
+          if (C16) C16[(size_t)row * p.ldc + col] = (uint16_t)(pack_bf16x2(xv, 0.f) & 0xFFFFu);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS) : "memory");
+  }
+}
+
+// 2-D bf16 tensor map: memory [outer, inner] with `ld` elements between rows; box {64, box_rows}, 128-byte swizzle.
+static bool make_map_bf16(CUtensorMap* map, const void* ptr, long long inner, long long outer, long long ld, int box_rows) {
+  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+template <int BN>
+static int launch_bf16(cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, dim3 grid) {
+  using C = CfgH<BN>;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(gemm_tc_bf16_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES) != cudaSuccess) {
+      addk_set_error("gemm_tc: cannot raise the dynamic shared memory limit");
+      return ADDK_ERR_LAUNCH;
+    }
+    configured = true;
+  }
+  gemm_tc_bf16_kernel<BN><<<grid, NTHREADS, C::SMEM_BYTES, st>>>(ta, tb, p);
+  return ADDK_OK;
+}
+
 template <int BN, bool X3>
 static int launch(cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, dim3 grid) {
   using C = Cfg<BN, X3>;
@@ -1132,10 +1365,61 @@ static bool addk_tc_pair_enabled() {
 // precision: 1 = tf32x3, 2 = tf32.  Shapes the tensor-core tiles do not cover (heads with 1 or 29 outputs,
 // contraction shorter than one k-block, misaligned leading dimensions, fused input normalisation) run on the
 // exact-fp32 CUDA-core kernel, which is at least as accurate.
+__global__ void f32_to_bf16_rows_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst, int M, int N, int ld) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)M * N) return;
+  const int r = (int)(i / N), c = (int)(i - (long long)r * N);
+  dst[(size_t)r * ld + c] = (uint16_t)(addk_tc::pack_bf16x2(src[(size_t)r * ld + c], 0.f) & 0xFFFFu);
+}
+
+static int gemm_bf16(cudaStream_t st, const addk_gemm_args& a) {
+  using namespace addk_tc;
+  const int BKh = 64;
+  int split = a.split_k > 1 ? a.split_k : 1;
+  const int kb_total = (a.K + BKh - 1) / BKh;
+  const int kb_per = (kb_total + split - 1) / split;
+  if ((long long)kb_per * (split - 1) >= kb_total) return -1;
+  Params p;
+  p.C = a.C; p.ldc = a.ldc; p.M = a.M; p.N = a.N; p.K = a.K; p.bias = a.bias; p.mask = a.relu_mask_src;
+  p.ld_mask = a.ld_mask; p.relu = a.relu; p.accumulate = 0; p.kb_per_split = kb_per;
+  p.slab_stride = a.slab_stride > 0 ? a.slab_stride : (long long)a.M * a.ldc;
+  p.pair_flags = 0; p.C16 = a.C16;
+  p.a_mn = a.trans_a ? 1 : 0;
+  p.b_mn = a.trans_b ? 0 : 1;
+  const int BN = a.N > 128 ? 256 : (a.N > 64 ? 128 : 64);
+  CUtensorMap ta, tb;
+  bool ok = p.a_mn ? make_map_bf16(&ta, a.A16, a.M, a.K, a.lda, 64) : make_map_bf16(&ta, a.A16, a.K, a.M, a.lda, BM);
+  ok = ok && (p.b_mn ? make_map_bf16(&tb, a.B16, a.N, a.K, a.ldb, 64) : make_map_bf16(&tb, a.B16, a.K, a.N, a.ldb, BN));
+  if (!ok) return -1;
+  dim3 grid((a.N + BN - 1) / BN, (a.M + BM - 1) / BM, split);
+  if (BN == 256) return launch_bf16<256>(st, ta, tb, p, grid);
+  if (BN == 128) return launch_bf16<128>(st, ta, tb, p, grid);
+  return launch_bf16<64>(st, ta, tb, p, grid);
+}
+
 int addk_gemm_tc(cudaStream_t st, const addk_gemm_args& a, int precision) {
+  if (precision == 3) {
+    // bf16 tensor-core tiles when the call carries bf16 twins that TMA can address (16-byte row pitch = 8 elements);
+    // otherwise tf32x3 on the fp32 operands, followed by the bf16 copy of the output the caller asked for
+    const bool ok16 = a.A16 && a.B16 && ((a.lda & 7) == 0) && ((a.ldb & 7) == 0) && ((reinterpret_cast<uintptr_t>(a.A16) & 15) == 0) &&
+                      ((reinterpret_cast<uintptr_t>(a.B16) & 15) == 0) && !a.a_mean && !a.accumulate && a.M >= 16 && a.N >= 16 &&
+                      a.K >= 16 && (a.split_k <= 1 || !(a.bias || a.relu || a.relu_mask_src)) && addk_tc::resolve_encode();
+    if (ok16) {
+      const int rc = gemm_bf16(st, a);
+      if (rc >= 0) return rc;
+    }
+    if (!a.C) { addk_set_error("gemm: bf16 call without an fp32 output cannot fall back"); return ADDK_ERR_ARG; }
+    const int rc = addk_gemm_tc(st, a, 1);
+    if (rc != ADDK_OK) return rc;
+    if (a.C16 && a.split_k <= 1) {
+      const long long n = (long long)a.M * a.N;
+      f32_to_bf16_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a.C, reinterpret_cast<uint16_t*>(a.C16), a.M, a.N, a.ldc);
+    }
+    return ADDK_OK;
+  }
   using namespace addk_tc;
   if (precision != 1 && precision != 2) {
-    addk_set_error("gemm: unsupported precision mode (bf16 tensor-core tiles are not built yet)");
+    addk_set_error("gemm: unknown precision mode");
     return ADDK_ERR_UNSUPPORTED;
   }
   const bool aligned = ((a.lda & 3) == 0) && ((a.ldb & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.A) & 15) == 0) &&
@@ -1154,6 +1438,7 @@ int addk_gemm_tc(cudaStream_t st, const addk_gemm_args& a, int precision) {
   p.ld_mask = a.ld_mask; p.relu = a.relu; p.accumulate = a.accumulate; p.kb_per_split = kb_per;
   p.slab_stride = a.slab_stride > 0 ? a.slab_stride : (long long)a.M * a.ldc;
   { const char* e = getenv("ADDK_TC_PAIR_FLAGS"); p.pair_flags = e ? atoi(e) : 2; }
+  p.C16 = nullptr;
   p.a_mn = a.trans_a ? 1 : 0;          // A given as [K,M]: rows are the contraction index
   p.b_mn = a.trans_b ? 0 : 1;          // B given as [K,N]
   const int BN = a.N > 128 ? 256 : (a.N > 64 ? 128 : 64);

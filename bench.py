@@ -407,7 +407,7 @@ def dominant_kernel_roofline(agent, args, hbm_peak, tc_peak, peak_src):
     def launch(i):
         a = _lib.AddkGemmArgs(A=A[i % nbuf].data_ptr(), lda=Kd, B=Wt.data_ptr(), ldb=Kd, C=Cc[i % 2].data_ptr(), ldc=Nd,
                               M=M, N=Nd, K=Kd, bias=bias.data_ptr(), a_mean=None, a_std=None, relu_mask_src=None,
-                              ld_mask=0, trans_a=0, trans_b=1, relu=1, split_k=1, accumulate=0, slab_stride=0)
+                              ld_mask=0, trans_a=0, trans_b=1, relu=1, split_k=1, accumulate=0, slab_stride=0, A16=None, B16=None, C16=None)
         _lib.check(L.addk_gemm(_lib.stream(), C.byref(a), C.c_int(m.precision)), "addk_gemm")
     for i in range(3):
         launch(i)

@@ -189,6 +189,9 @@ typedef struct addk_gemm_args {
   int32_t trans_a, trans_b, relu, split_k;  /* split_k > 1: slab z is written at C + z * slab_stride */
   int32_t accumulate;                /* C += result (single-slab only) */
   int64_t slab_stride;               /* floats between consecutive split-K slabs; 0 = M * ldc */
+  /* precision "bf16" only: bf16 twins of the operands (same shapes / leading dimensions, in elements) and an
+   * optional bf16 copy of the output.  NULL twins -> the call runs in tf32x3 on the fp32 operands. */
+  const void* A16; const void* B16; void* C16;
 } addk_gemm_args;
 int addk_gemm(void* stream, const addk_gemm_args* args_host, int precision);
 

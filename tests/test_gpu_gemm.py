@@ -22,7 +22,7 @@ def _gemm(A, B, Cout, M, N, K, ta, tb, prec, bias=None, relu=0, mask=None, split
                           bias=bias.data_ptr() if bias is not None else None, a_mean=None, a_std=None,
                           relu_mask_src=mask.data_ptr() if mask is not None else None,
                           ld_mask=mask.stride(0) if mask is not None else 0, trans_a=ta, trans_b=tb, relu=relu,
-                          split_k=split, accumulate=accumulate, slab_stride=0)
+                          split_k=split, accumulate=accumulate, slab_stride=0, A16=None, B16=None, C16=None)
     _lib.check(_lib.lib().addk_gemm(_lib.stream(), C.byref(a), C.c_int(_lib.PRECISIONS[prec])), "addk_gemm")
 
 
@@ -101,3 +101,32 @@ def test_tensor_core_split_is_fp32_class_on_mlp_scale_data():
     _gemm(A, W, out, M, N, K, 0, 1, "tf32x3")
     e = _rel(out, A.double() @ W.double().t())
     assert e <= 1e-6, e
+
+
+@pytest.mark.parametrize("ta,tb", [(0, 1), (0, 0), (1, 0), (1, 1)])
+def test_gemm_bf16_layouts(ta, tb):
+    """precision "bf16": bf16 twins of the operands through TMA + tcgen05 kind::f16, fp32 accumulate.  Checked against
+    the float64 product of the SAME bf16 values (so only the accumulation differs): 1e-5; and the fp32 + bf16 outputs
+    must agree to bf16 rounding."""
+    from add_gym_b200 import _lib
+    g = torch.Generator(device="cuda").manual_seed(4)
+    pad = lambda n: (n + 7) & ~7
+    for (M, N, K) in [(512, 1024, 264), (300, 512, 1024), (1024, 264, 2048), (256, 256, 64), (129, 200, 72), (29, 512, 2048),
+                      (2048, 29, 512)]:
+        A = torch.randn((K, pad(M)) if ta else (M, pad(K)), device="cuda", generator=g)
+        B = torch.randn((N, pad(K)) if tb else (K, pad(N)), device="cuda", generator=g)
+        A16, B16 = A.to(torch.bfloat16), B.to(torch.bfloat16)
+        Aop = (A16[:, :M].t() if ta else A16[:, :K]).double()
+        Bop = (B16[:, :K].t() if tb else B16[:, :N]).double()
+        ref = Aop @ Bop
+        out = torch.full((M, pad(N)), float("nan"), device="cuda")
+        out16 = torch.zeros((M, pad(N)), device="cuda", dtype=torch.bfloat16)
+        a = _lib.AddkGemmArgs(A=A.data_ptr(), lda=A.stride(0), B=B.data_ptr(), ldb=B.stride(0), C=out.data_ptr(), ldc=out.stride(0),
+                              M=M, N=N, K=K, bias=None, a_mean=None, a_std=None, relu_mask_src=None, ld_mask=0, trans_a=ta,
+                              trans_b=tb, relu=0, split_k=1, accumulate=0, slab_stride=0, A16=A16.data_ptr(),
+                              B16=B16.data_ptr(), C16=out16.data_ptr())
+        _lib.check(_lib.lib().addk_gemm(_lib.stream(), C.byref(a), C.c_int(_lib.PRECISIONS["bf16"])), "addk_gemm")
+        torch.cuda.synchronize()
+        e = _rel(out[:, :N], ref)
+        assert e <= 1e-5, "bf16 ta=%d tb=%d %s: rel err %.3e" % (ta, tb, (M, N, K), e)
+        assert torch.equal(out16[:, :N], out[:, :N].to(torch.bfloat16)), "bf16 copy of the output"

@@ -21,15 +21,15 @@ def launch(i):
     if layout == "fwd":
         a = _lib.AddkGemmArgs(A=A[i % 3].data_ptr(), lda=K, B=W.data_ptr(), ldb=K, C=Cc[i % 2].data_ptr(), ldc=N, M=M, N=N, K=K,
                               bias=bias.data_ptr(), a_mean=None, a_std=None, relu_mask_src=None, ld_mask=0, trans_a=0, trans_b=1,
-                              relu=1, split_k=1, accumulate=0, slab_stride=0)
+                              relu=1, split_k=1, accumulate=0, slab_stride=0, A16=None, B16=None, C16=None)
     elif layout == "dgrad":
         a = _lib.AddkGemmArgs(A=A[i % 3].data_ptr(), lda=K, B=W.data_ptr(), ldb=K, C=Cc[i % 2].data_ptr(), ldc=N, M=M, N=K, K=N,
                               bias=None, a_mean=None, a_std=None, relu_mask_src=A[(i + 1) % 3].data_ptr(), ld_mask=K, trans_a=0,
-                              trans_b=0, relu=0, split_k=1, accumulate=0, slab_stride=0)
+                              trans_b=0, relu=0, split_k=1, accumulate=0, slab_stride=0, A16=None, B16=None, C16=None)
     else:
         a = _lib.AddkGemmArgs(A=A[i % 3].data_ptr(), lda=K, B=A[(i + 1) % 3].data_ptr(), ldb=K, C=slabs.data_ptr(), ldc=K, M=N, N=K,
                               K=M, bias=None, a_mean=None, a_std=None, relu_mask_src=None, ld_mask=0, trans_a=1, trans_b=0,
-                              relu=0, split_k=8, accumulate=0, slab_stride=0)
+                              relu=0, split_k=8, accumulate=0, slab_stride=0, A16=None, B16=None, C16=None)
     _lib.check(L.addk_gemm(_lib.stream(), C.byref(a), C.c_int(_lib.PRECISIONS[prec])), "addk_gemm")
 for i in range(2):
     launch(i)
