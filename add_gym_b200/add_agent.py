@@ -227,13 +227,25 @@ class ADDAgent(torch.nn.Module):
         fb = self._exp_buffer.get_data_flat
         self._max_steps = int(self._update_epochs * int(np.ceil(float(T * N) / M)))
         w1 = max(H[0], H[1], E[0])
+        # every fp32 tensor a dense layer reads or writes is carved out of ONE arena (32-byte aligned pieces), so that in
+        # the "bf16" mode the library finds the bf16 twin of any operand at arena16 + (ptr - arena)
+        shapes = dict(xn=(R, od), an=(R, al), dn=(R, dl), h1=(R, w1), h2=(R, w1), h3=(R, max(H[2], E[1])), g1=(R, w1),
+                      g2=(R, w1), g3=(R, max(H[2], E[1])), u1=(R, E[0]), u2=(R, E[1]), gx=(R, dl), dg=(R, dl), mean=(R, al),
+                      dmean=(R, al), wd0_pad=(E[0], dl))
+        offs, total = {}, 0
+        for k, shp in shapes.items():
+            offs[k] = total
+            total += (int(np.prod(shp)) + 7) & ~7
+        self._arena = z(total)
+        bf16 = m.precision == _lib.PRECISIONS["bf16"]
+        self._arena16 = torch.zeros(total if bf16 else 8, device=dev, dtype=torch.bfloat16)
+        self._params16 = torch.zeros(m.num_params if bf16 else 8, device=dev, dtype=torch.bfloat16)
+        carve = {k: self._arena[offs[k]:offs[k] + int(np.prod(shp))].view(shp) for k, shp in shapes.items()}
         self._ws = dict(
-            xn=z(R, od), an=z(R, al), old_logp=z(R), adv=z(R), tar=z(R), mask=z(R), dn=z(R, dl),
-            h1=z(R, w1), h2=z(R, w1), h3=z(R, max(H[2], E[1])), g1=z(R, w1), g2=z(R, w1), g3=z(R, max(H[2], E[1])),
-            u1=z(R, E[0]), u2=z(R, E[1]), gx=z(R, dl), dg=z(R, dl), mean=z(R, al), dmean=z(R, al), pred=z(R),
-            dpred=z(R), ones=torch.ones(R, device=dev), stats=z(32, dt=torch.float64), info=z(self._max_steps, 16),
-            cnt=z(1, dt=torch.int32), slabs=z(2 * S, m.num_params), colsum_work=z(64 * 1024 + 64),
-            wd0_pad=z(E[0], dl))
+            carve, old_logp=z(R), adv=z(R), tar=z(R), mask=z(R), pred=z(R), dpred=z(R), ones=torch.ones(R, device=dev),
+            stats=z(32, dt=torch.float64), info=z(self._max_steps, 16), cnt=z(1, dt=torch.int32),
+            slabs=z(2 * S, m.num_params), colsum_work=z(64 * 1024 + 64), arena=self._arena, arena16=self._arena16,
+            params16=self._params16)
         ptrs = dict(self._ws)
         ptrs.update(params=m.flat, grads=m.flat_grad, exp_avg=self._optimizer.exp_avg,
                     exp_avg_sq=self._optimizer.exp_avg_sq, obs_mean=self._obs_norm._mean, obs_std=self._obs_norm._std,
@@ -242,7 +254,7 @@ class ADDAgent(torch.nn.Module):
                     buf_a_logp=fb("a_logp"), buf_adv=fb("adv"), buf_tar_val=fb("tar_val"),
                     buf_mask=fb("rand_action_mask"), buf_disc_obs=fb("disc_obs"), buf_disc_demo=fb("disc_obs_demo"))
         ints = dict(obs_dim=od, act_dim=ad, disc_dim=dd, act_ld=al, disc_ld=dl, mb_rows=M, num_params=m.num_params,
-                    split_k=S, precision=m.precision, hid_a1=H[0], hid_a2=H[1], hid_a3=H[2], hid_d1=E[0], hid_d2=E[1])
+                    split_k=S, arena_elems=total, precision=m.precision, hid_a1=H[0], hid_a2=H[1], hid_a3=H[2], hid_d1=E[0], hid_d2=E[1])
         ints.update(m.offsets)
         opt = self._optimizer
         f64 = dict(ppo_clip_ratio=self._ppo_clip_ratio, action_bound_weight=self._action_bound_weight,

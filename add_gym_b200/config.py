@@ -39,6 +39,8 @@ _AGENT = {
         #             (3.3e-7 per layer), the default -- meets the same 1e-5 parity bar as "fp32"
         #   "fp32"  : IEEE fp32 FMA on the CUDA cores (first parity path, ~4x slower)
         #   "tf32"  : tcgen05 kind::tf32, single pass (what the reference runs on a GPU, main.py:17-18)
+        #   "bf16"  : tcgen05 kind::f16 on bf16 twins of every activation / gradient / weight, fp32 accumulate, fp32
+        #             master weights and AdamW (BASELINE config 4; parity bar 2e-2)
         "mlp_precision": "tf32x3",
     },
     "optimizer": {"type": "Adam", "learning_rate": 1e-4},

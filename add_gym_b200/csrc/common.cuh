@@ -208,6 +208,13 @@ __device__ __forceinline__ double block_sum(double v, double* smem32) {
   return r;
 }
 
+// fp32 -> bf16, round to nearest even
+__device__ __forceinline__ uint16_t to_bf16(float x) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(0.f), "f"(x));
+  return (uint16_t)(r & 0xFFFFu);
+}
+
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ void stg4(float* p, const float4& v) { *reinterpret_cast<float4*>(p) = v; }
 // streaming (evict-first) 128-bit store for write-once experience rows

@@ -64,6 +64,11 @@ ADDK_PTR(info)          // [max_steps, 16] float diagnostics, one row per optimi
 ADDK_PTR(cnt)           // [1] int: rows of the minibatch with rand_action_mask == 1
 ADDK_PTR(colsum_work)   // [64*1024 + 64] floats: column-sum partials + ticket counters (zero-initialised)
 ADDK_PTR(wd0_pad)       // [hid_d1, disc_ld] discriminator first-layer weight with rows padded to 16 bytes
+// ---- precision "bf16": every fp32 workspace tensor above is carved out of ONE arena, so the bf16 twin of any
+//      operand is arena16 + (ptr - arena); params16 is the bf16 shadow of the flat parameter vector
+ADDK_PTR(arena)         // fp32 arena base (may be NULL when precision != bf16)
+ADDK_PTR(arena16)       // bf16 arena, same element offsets
+ADDK_PTR(params16)      // [P] bf16
 
 ADDK_INT(obs_dim)
 ADDK_INT(act_dim)
@@ -73,6 +78,7 @@ ADDK_INT(disc_ld)       // disc_dim rounded up to a multiple of 4
 ADDK_INT(mb_rows)       // minibatch rows M
 ADDK_INT(num_params)    // P (including alignment padding)
 ADDK_INT(split_k)
+ADDK_INT(arena_elems)   // elements in the arena
 ADDK_INT(precision)     // 0 fp32 | 1 tf32x3 | 2 tf32 | 3 bf16
 ADDK_INT(hid_a1)        // actor/critic hidden sizes (1024, 1024, 512)
 ADDK_INT(hid_a2)

@@ -48,12 +48,16 @@ __global__ void gather_minibatch_kernel(const long long* __restrict__ idx, int M
                                         const float* __restrict__ a_std, const float* __restrict__ mean_abs,
                                         float* __restrict__ xn, float* __restrict__ an, float* __restrict__ old_logp,
                                         float* __restrict__ adv, float* __restrict__ tar, float* __restrict__ mask,
-                                        float* __restrict__ dn, int* __restrict__ cnt) {
+                                        float* __restrict__ dn, int* __restrict__ cnt, uint16_t* __restrict__ xn16) {
   int i = blockIdx.x * (blockDim.x / 32) + (threadIdx.x / 32);
   int lane = threadIdx.x & 31;
   if (i >= M) return;
   const size_t s = (size_t)idx[i];
-  for (int c = lane; c < obs_dim; c += 32) xn[(size_t)i * obs_dim + c] = sub_rn(buf_obs[s * obs_dim + c], obs_mean[c]) / obs_std[c];
+  for (int c = lane; c < obs_dim; c += 32) {
+    const float v = sub_rn(buf_obs[s * obs_dim + c], obs_mean[c]) / obs_std[c];
+    xn[(size_t)i * obs_dim + c] = v;
+    if (xn16) xn16[(size_t)i * obs_dim + c] = to_bf16(v);
+  }
   for (int c = lane; c < act_ld; c += 32)
     an[(size_t)i * act_ld + c] = c < act_dim ? sub_rn(buf_action[s * act_dim + c], a_mean[c]) / a_std[c] : 0.f;
   for (int c = lane; c < disc_ld; c += 32)
@@ -78,7 +82,7 @@ __global__ void actor_loss_kernel(const float* __restrict__ mean, const float* _
                                   const float* __restrict__ logstd, const float* __restrict__ old_logp,
                                   const float* __restrict__ adv, const float* __restrict__ mask, int M, int act_dim,
                                   int act_ld, float clip, float bound_w, const int* __restrict__ cnt,
-                                  float* __restrict__ dmean, double* __restrict__ stats) {
+                                  float* __restrict__ dmean, double* __restrict__ stats, uint16_t* __restrict__ dmean16) {
   __shared__ double s_acc[8][4];
   const int warp = threadIdx.x / 32, lane = threadIdx.x & 31;
   const int i = blockIdx.x * (blockDim.x / 32) + warp;
@@ -117,6 +121,7 @@ __global__ void actor_loss_kernel(const float* __restrict__ mean, const float* _
       float g = 0.f;
       if (on && lane < act_dim) g = dlogp * (d / (sd * sd)) + bound_w * 2.0f * (vmin + vmax) / n;
       dmean[(size_t)i * act_ld + lane] = g;
+      if (dmean16) dmean16[(size_t)i * act_ld + lane] = to_bf16(g);
     }
     if (on) {
       a_surr = surr; a_clip = fabsf(sub_rn(ratio, 1.0f)) > clip ? 1.0 : 0.0; a_ratio = ratio; a_bound = viol_sum;
@@ -175,13 +180,16 @@ __global__ void disc_loss_kernel(const float* __restrict__ logit, int M, float w
 // u2 = relu'(h2) * w3 (gradient of the logit w.r.t. the last hidden layer) and dh2 = dlogit * u2
 __global__ void disc_head_backward_kernel(const float* __restrict__ h2, const float* __restrict__ wl,
                                           const float* __restrict__ dlogit, int R, int H, float* __restrict__ u2,
-                                          float* __restrict__ dh2) {
+                                          float* __restrict__ dh2, uint16_t* __restrict__ u2_16, uint16_t* __restrict__ dh2_16) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (size_t)R * H) return;
   int r = (int)(i / H), k = (int)(i - (size_t)r * H);
   float u = h2[i] > 0.f ? wl[k] : 0.f;
   u2[i] = u;
-  dh2[i] = dlogit[r] * u;
+  const float dh = dlogit[r] * u;
+  dh2[i] = dh;
+  if (u2_16) u2_16[i] = to_bf16(u);
+  if (dh2_16) dh2_16[i] = to_bf16(dh);
 }
 
 // gradient penalty on the input gradient: one warp per row (add_agent.py:167-178)
@@ -312,15 +320,17 @@ __global__ void rowdot_kernel(const float* __restrict__ X, int ld, long long row
 
 // 1-output head input gradient through the ReLU: g[r, k] = (h[r, k] > 0) ? d[r] * w[k] : 0
 __global__ void outer_mask_kernel(const float* __restrict__ d, const float* __restrict__ w, const float* __restrict__ h,
-                                  long long rows, int K, float* __restrict__ g) {
+                                  long long rows, int K, float* __restrict__ g, uint16_t* __restrict__ g16) {
   const long long n4 = rows * K / 4;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     const long long r = (i * 4) / K;
     const int k = (int)((i * 4) % K);
     const float dv = d[r];
     const float4 u = ldg4(w + k), m = ldg4(h + 4 * i);
-    stg4(g + 4 * i, make_float4(m.x > 0.f ? dv * u.x : 0.f, m.y > 0.f ? dv * u.y : 0.f, m.z > 0.f ? dv * u.z : 0.f,
-                                m.w > 0.f ? dv * u.w : 0.f));
+    const float4 o = make_float4(m.x > 0.f ? dv * u.x : 0.f, m.y > 0.f ? dv * u.y : 0.f, m.z > 0.f ? dv * u.z : 0.f,
+                                 m.w > 0.f ? dv * u.w : 0.f);
+    stg4(g + 4 * i, o);
+    if (g16) { g16[4 * i] = to_bf16(o.x); g16[4 * i + 1] = to_bf16(o.y); g16[4 * i + 2] = to_bf16(o.z); g16[4 * i + 3] = to_bf16(o.w); }
   }
 }
 
@@ -401,13 +411,16 @@ __global__ void sample_action_kernel(const float* __restrict__ mean, int act_ld,
 
 // Normalizer.normalize for a block of rows (normalizer.py:107-110): out = (x - mean) / std, 128-bit when dim % 4 == 0
 __global__ void obs_normalize_kernel(const float* __restrict__ x, const float* __restrict__ mean,
-                                     const float* __restrict__ sd, long long rows, int dim, float* __restrict__ out) {
+                                     const float* __restrict__ sd, long long rows, int dim, float* __restrict__ out,
+                                     uint16_t* __restrict__ out16) {
   const long long n4 = rows * dim / 4;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)((i * 4) % dim);
     const float4 v = ldg4(x + 4 * i);
     const float4 m = ldg4(mean + c), s = ldg4(sd + c);
-    stg4(out + 4 * i, make_float4(sub_rn(v.x, m.x) / s.x, sub_rn(v.y, m.y) / s.y, sub_rn(v.z, m.z) / s.z, sub_rn(v.w, m.w) / s.w));
+    const float4 o = make_float4(sub_rn(v.x, m.x) / s.x, sub_rn(v.y, m.y) / s.y, sub_rn(v.z, m.z) / s.z, sub_rn(v.w, m.w) / s.w);
+    stg4(out + 4 * i, o);
+    if (out16) { out16[4 * i] = to_bf16(o.x); out16[4 * i + 1] = to_bf16(o.y); out16[4 * i + 2] = to_bf16(o.z); out16[4 * i + 3] = to_bf16(o.w); }
   }
 }
 
@@ -418,6 +431,11 @@ __global__ void pad_rows_kernel(const float* __restrict__ w, int rows, int dim, 
   if (i >= rows * ld) return;
   const int r = i / ld, c = i - r * ld;
   out[i] = c < dim ? w[(size_t)r * dim + c] : 0.f;
+}
+
+__global__ void f32_to_bf16_flat_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    dst[i] = to_bf16(src[i]);
 }
 
 __global__ void diff_normalize_kernel(const float* __restrict__ dobs, const float* __restrict__ demo,
@@ -447,11 +465,25 @@ static int colsum(cudaStream_t st, const addk_update_ctx& c, const float* dY, in
   return ADDK_OK;
 }
 
+// precision "bf16": the bf16 twin of an fp32 operand (NULL when the pointer is not one of the twinned tensors)
+static thread_local const addk_update_ctx* g_twin_ctx = nullptr;
+static uint16_t* twin16(const void* p) {
+  const addk_update_ctx* c = g_twin_ctx;
+  if (!c || c->precision != 3 || !p) return nullptr;
+  const float* f = (const float*)p;
+  const float* a0 = (const float*)c->arena;
+  if (a0 && f >= a0 && f < a0 + c->arena_elems) return (uint16_t*)c->arena16 + (f - a0);
+  const float* p0 = (const float*)c->params;
+  if (c->params16 && f >= p0 && f < p0 + c->num_params) return (uint16_t*)c->params16 + (f - p0);
+  return nullptr;
+}
+
 static int gemm(cudaStream_t st, int prec, const float* A, int lda, int ta, const float* B, int ldb, int tb, float* C,
                 int ldc, int M, int N, int K, const float* bias = nullptr, int relu = 0, const float* mask = nullptr,
                 int ld_mask = 0, int split = 1, const float* nmean = nullptr, const float* nstd = nullptr,
                 long long slab_stride = 0) {
   addk_gemm_args a;
+  a.A16 = prec == 3 ? twin16(A) : nullptr; a.B16 = prec == 3 ? twin16(B) : nullptr; a.C16 = prec == 3 ? twin16(C) : nullptr;
   a.A = A; a.lda = lda; a.B = B; a.ldb = ldb; a.C = C; a.ldc = ldc; a.M = M; a.N = N; a.K = K;
   a.bias = bias; a.a_mean = nmean; a.a_std = nstd; a.relu_mask_src = mask; a.ld_mask = ld_mask;
   a.trans_a = ta; a.trans_b = tb; a.relu = relu; a.split_k = split; a.accumulate = 0; a.slab_stride = slab_stride;
@@ -488,7 +520,7 @@ static int head1_forward(cudaStream_t st, const float* X, int ld, long long rows
 static int head1_dgrad(cudaStream_t st, const float* d, const float* w, const float* h, long long rows, int K, float* g) {
   const long long n4 = rows * K / 4;
   long long bl = (n4 + 255) / 256; if (bl > 148 * 16) bl = 148 * 16;
-  outer_mask_kernel<<<(unsigned)bl, 256, 0, st>>>(d, w, h, rows, K, g);
+  outer_mask_kernel<<<(unsigned)bl, 256, 0, st>>>(d, w, h, rows, K, g, twin16(g));
   ADDK_CHECK_LAUNCH();
   return ADDK_OK;
 }
@@ -503,7 +535,7 @@ static int trunk_forward(cudaStream_t st, const Ctx& c, const float* X, int ldx,
     // tensor-core modes: normalise into the minibatch scratch first (TMA cannot apply it on load), then the TC tile
     const long long n4 = (long long)rows * in_dim / 4;
     int bl = (int)((n4 + 255) / 256); if (bl > 148 * 8) bl = 148 * 8;
-    obs_normalize_kernel<<<bl, 256, 0, st>>>(X, nmean, nstd, rows, in_dim, F(c.xn));
+    obs_normalize_kernel<<<bl, 256, 0, st>>>(X, nmean, nstd, rows, in_dim, F(c.xn), twin16(c.xn));
     ADDK_CHECK_LAUNCH();
     X = F(c.xn); nmean = nullptr; nstd = nullptr;
   }
@@ -558,10 +590,16 @@ extern "C" int addk_update_minibatch(void* stream, void* ctx_host, const long lo
   (void)H1;
   cudaMemsetAsync(stats, 0, ST_COUNT * sizeof(double), st);
   cudaMemsetAsync(cnt, 0, sizeof(int), st);
+  g_twin_ctx = &c;
+  if (c.precision == 3 && c.params16) {
+    f32_to_bf16_flat_kernel<<<148 * 4, 256, 0, st>>>(F(c.params), (uint16_t*)c.params16, c.num_params);
+    ADDK_CHECK_LAUNCH();
+  }
+
   gather_minibatch_kernel<<<(M + 7) / 8, 256, 0, st>>>(
       idx, M, OD, AD, AL, DD, DL, F(c.buf_obs), F(c.buf_action), F(c.buf_a_logp), F(c.buf_adv), F(c.buf_tar_val),
       F(c.buf_mask), F(c.buf_disc_obs), F(c.buf_disc_demo), F(c.obs_mean), F(c.obs_std), F(c.a_mean), F(c.a_std),
-      F(c.disc_mean_abs), F(c.xn), F(c.an), F(c.old_logp), F(c.adv), F(c.tar), F(c.mask), F(c.dn), cnt);
+      F(c.disc_mean_abs), F(c.xn), F(c.an), F(c.old_logp), F(c.adv), F(c.tar), F(c.mask), F(c.dn), cnt, twin16(c.xn));
   ADDK_CHECK_LAUNCH();
 
   // ---------------- actor ----------------
@@ -569,7 +607,7 @@ extern "C" int addk_update_minibatch(void* stream, void* ctx_host, const long lo
   TRY(gemm(st, pr, F(c.h3), H3, 0, W + c.o_a_wm, H3, 1, F(c.mean), AL, M, AD, H3, W + c.o_a_bm, 0));
   actor_loss_kernel<<<(M + 7) / 8, 256, 0, st>>>(F(c.mean), F(c.an), F(c.logstd), F(c.old_logp), F(c.adv), F(c.mask), M,
                                                  AD, AL, (float)c.ppo_clip_ratio, (float)c.action_bound_weight, cnt,
-                                                 F(c.dmean), stats);
+                                                 F(c.dmean), stats, twin16(c.dmean));
   ADDK_CHECK_LAUNCH();
   TRY(wgrad(st, c, F(c.dmean), AL, F(c.h3), H3, M, AD, H3, c.o_a_wm, c.o_a_bm, 0));
   TRY(gemm(st, pr, F(c.dmean), AL, 0, W + c.o_a_wm, H3, 0, F(c.g3), H3, M, H3, AD, nullptr, 0, F(c.h3), H3));
@@ -598,7 +636,7 @@ extern "C" int addk_update_minibatch(void* stream, void* ctx_host, const long lo
   {
     size_t tot = (size_t)R * E2;
     disc_head_backward_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(e2, W + c.o_d_wl, F(c.dpred), R, E2, F(c.u2),
-                                                                            dh2);
+                                                                            dh2, twin16(c.u2), twin16(dh2));
     ADDK_CHECK_LAUNCH();
   }
   // input-gradient chain: u1 = m1 * (u2 W2), gx = u1 W1
@@ -666,6 +704,11 @@ extern "C" int addk_actor_step(void* stream, void* ctx_host, const float* obs, c
   cudaStream_t st = (cudaStream_t)stream;
   const int OD = (int)c.obs_dim, AD = (int)c.act_dim, AL = (int)c.act_ld, H3 = (int)c.hid_a3;
   const float* W = F(c.params);
+  g_twin_ctx = &c;
+  if (c.precision == 3 && c.params16) {
+    f32_to_bf16_flat_kernel<<<148 * 4, 256, 0, st>>>(F(c.params), (uint16_t*)c.params16, c.num_params);
+    ADDK_CHECK_LAUNCH();
+  }
   if (obs_rec) cudaMemcpyAsync(obs_rec, obs, (size_t)n * OD * sizeof(float), cudaMemcpyDeviceToDevice, st);
   TRY(trunk_forward(st, c, obs, OD, OD, n, c.o_a_w0, c.o_a_b0, c.o_a_w1, c.o_a_b1, c.o_a_w2, c.o_a_b2, F(c.obs_mean),
                     F(c.obs_std)));
@@ -683,6 +726,11 @@ extern "C" int addk_critic_eval(void* stream, void* ctx_host, const float* obs, 
   const int OD = (int)c.obs_dim, H3 = (int)c.hid_a3;
   const long long chunk = c.mb_rows + 1;
   const float* W = F(c.params);
+  g_twin_ctx = &c;
+  if (c.precision == 3 && c.params16) {
+    f32_to_bf16_flat_kernel<<<148 * 4, 256, 0, st>>>(F(c.params), (uint16_t*)c.params16, c.num_params);
+    ADDK_CHECK_LAUNCH();
+  }
   for (long long r0 = 0; r0 < n; r0 += chunk) {
     int rows = (int)((n - r0 < chunk) ? n - r0 : chunk);
     TRY(trunk_forward(st, c, obs + r0 * OD, OD, OD, rows, c.o_c_w0, c.o_c_b0, c.o_c_w1, c.o_c_b1, c.o_c_w2, c.o_c_b2,
@@ -701,6 +749,11 @@ extern "C" int addk_disc_eval(void* stream, void* ctx_host, const float* disc_ob
   const long long chunk = c.mb_rows;
   const float* W = F(c.params);
   float *e1 = F(c.h1), *e2 = F(c.h3);
+  g_twin_ctx = &c;
+  if (c.precision == 3 && c.params16) {
+    f32_to_bf16_flat_kernel<<<148 * 4, 256, 0, st>>>(F(c.params), (uint16_t*)c.params16, c.num_params);
+    ADDK_CHECK_LAUNCH();
+  }
   pad_rows_kernel<<<(E1 * DL + 255) / 256, 256, 0, st>>>(W + c.o_d_w0, E1, DD, DL, F(c.wd0_pad));
   ADDK_CHECK_LAUNCH();
   for (long long r0 = 0; r0 < n; r0 += chunk) {

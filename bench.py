@@ -33,7 +33,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--envs", type=int, default=4096, help="envs per GPU (BASELINE configs[1]: 4096)")
-    ap.add_argument("--precision", default="tf32x3", choices=["fp32", "tf32x3", "tf32"],
+    ap.add_argument("--precision", default="tf32x3", choices=["fp32", "tf32x3", "tf32", "bf16"],
                     help="MLP arithmetic: tf32x3 = tcgen05 3-pass split (fp32-parity mode, default); fp32 = CUDA cores; tf32 = single pass")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-envs", type=int, default=512, help="envs of the bounded CPU-baseline sample")
