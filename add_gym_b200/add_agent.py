@@ -220,7 +220,7 @@ class ADDAgent(torch.nn.Module):
         assert M <= T * N, "minibatch larger than the rollout"
         R = M + 1
         od, dd, ad = m.obs_dim, m.disc_dim, m.act_dim
-        al, dl = (ad + 3) & ~3, (dd + 3) & ~3
+        al, dl = (ad + 7) & ~7, (dd + 7) & ~7      # leading dimensions: 8 elements = 16 bytes in the bf16 twins too
         H, E = m.hidden
         S = 8
         z = lambda *s, dt=torch.float32: torch.zeros(list(s), device=dev, dtype=dt)

@@ -2,7 +2,7 @@
 (add/add_model.py:7-50, ppo_model.py:8-67, nets/fc_3layers_1024units.py, nets/fc_2layers_1024units.py,
 distribution_gaussian_diag.py:13-58).
 
-* The 22 trainable tensors live in ONE flat fp32 device vector (16-byte aligned segments, reference
+* The 22 trainable tensors live in ONE flat fp32 device vector (32-byte aligned segments, reference
   registration order); the ``torch.nn.Linear`` modules only provide the reference's state-dict key names
   (``_actor_layers.{0,2,4}``, ``_action_dist._mean_net``, ``_action_dist._logstd_net``, ``_critic_layers.*``,
   ``_critic_out``, ``_disc_layers.{0,2}``, ``_disc_logits``) and are re-pointed at views of that vector.
@@ -78,8 +78,9 @@ class _ActionDist(torch.nn.Module):
         torch.nn.init.constant_(self._logstd_net, np.log(init_std))
 
 
-def _round4(n):
-    return (n + 3) & ~3
+def _round8(n):
+    # segments start on 8-element boundaries: 32 bytes in fp32, 16 bytes in the bf16 shadow (TMA needs 16)
+    return (n + 7) & ~7
 
 
 class ADDModel(torch.nn.Module):
@@ -123,7 +124,7 @@ class ADDModel(torch.nn.Module):
         self.offsets, off = {}, 0
         for n, t in zip(names, tensors):
             self.offsets["o_" + n] = off
-            off += _round4(t.numel())
+            off += _round8(t.numel())
         self.num_params = off
         self.flat = torch.zeros(off, dtype=torch.float32, device=device)
         self.flat_grad = torch.zeros(off, dtype=torch.float32, device=device)

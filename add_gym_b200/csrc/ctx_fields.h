@@ -73,8 +73,8 @@ ADDK_PTR(params16)      // [P] bf16
 ADDK_INT(obs_dim)
 ADDK_INT(act_dim)
 ADDK_INT(disc_dim)
-ADDK_INT(act_ld)        // act_dim rounded up to a multiple of 4
-ADDK_INT(disc_ld)       // disc_dim rounded up to a multiple of 4
+ADDK_INT(act_ld)        // act_dim rounded up to a multiple of 8
+ADDK_INT(disc_ld)       // disc_dim rounded up to a multiple of 8
 ADDK_INT(mb_rows)       // minibatch rows M
 ADDK_INT(num_params)    // P (including alignment padding)
 ADDK_INT(split_k)

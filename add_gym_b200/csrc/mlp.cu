@@ -48,7 +48,8 @@ __global__ void gather_minibatch_kernel(const long long* __restrict__ idx, int M
                                         const float* __restrict__ a_std, const float* __restrict__ mean_abs,
                                         float* __restrict__ xn, float* __restrict__ an, float* __restrict__ old_logp,
                                         float* __restrict__ adv, float* __restrict__ tar, float* __restrict__ mask,
-                                        float* __restrict__ dn, int* __restrict__ cnt, uint16_t* __restrict__ xn16) {
+                                        float* __restrict__ dn, int* __restrict__ cnt, uint16_t* __restrict__ xn16,
+                                        uint16_t* __restrict__ dn16) {
   int i = blockIdx.x * (blockDim.x / 32) + (threadIdx.x / 32);
   int lane = threadIdx.x & 31;
   if (i >= M) return;
@@ -60,9 +61,11 @@ __global__ void gather_minibatch_kernel(const long long* __restrict__ idx, int M
   }
   for (int c = lane; c < act_ld; c += 32)
     an[(size_t)i * act_ld + c] = c < act_dim ? sub_rn(buf_action[s * act_dim + c], a_mean[c]) / a_std[c] : 0.f;
-  for (int c = lane; c < disc_ld; c += 32)
-    dn[(size_t)i * disc_ld + c] =
-        c < disc_dim ? sub_rn(buf_demo[s * disc_dim + c], buf_dobs[s * disc_dim + c]) / fmaxf(mean_abs[c], 1e-4f) : 0.f;
+  for (int c = lane; c < disc_ld; c += 32) {
+    const float v = c < disc_dim ? sub_rn(buf_demo[s * disc_dim + c], buf_dobs[s * disc_dim + c]) / fmaxf(mean_abs[c], 1e-4f) : 0.f;
+    dn[(size_t)i * disc_ld + c] = v;
+    if (dn16) dn16[(size_t)i * disc_ld + c] = to_bf16(v);
+  }
   if (lane == 0) {
     old_logp[i] = buf_logp[s]; adv[i] = buf_adv[s]; tar[i] = buf_tar[s];
     float mk = buf_mask[s];
@@ -194,7 +197,7 @@ __global__ void disc_head_backward_kernel(const float* __restrict__ h2, const fl
 
 // gradient penalty on the input gradient: one warp per row (add_agent.py:167-178)
 __global__ void grad_penalty_kernel(const float* __restrict__ gx, int M, int R, int dim, int ld, float coef,
-                                    float* __restrict__ dg, double* __restrict__ stats) {
+                                    float* __restrict__ dg, double* __restrict__ stats, uint16_t* __restrict__ dg16) {
   int i = blockIdx.x * (blockDim.x / 32) + (threadIdx.x / 32);
   int lane = threadIdx.x & 31;
   if (i >= R) return;
@@ -204,7 +207,11 @@ __global__ void grad_penalty_kernel(const float* __restrict__ gx, int M, int R, 
   float gn = sqrtf(s + 1e-8f);
   float e = gn - 1.0f;
   float sc = i < M ? coef * 2.0f * e / (gn * (float)M) : 0.f;
-  for (int c = lane; c < ld; c += 32) dg[(size_t)i * ld + c] = c < dim ? sc * gx[(size_t)i * ld + c] : 0.f;
+  for (int c = lane; c < ld; c += 32) {
+    const float v = c < dim ? sc * gx[(size_t)i * ld + c] : 0.f;
+    dg[(size_t)i * ld + c] = v;
+    if (dg16) dg16[(size_t)i * ld + c] = to_bf16(v);
+  }
   if (lane == 0 && i < M) atomicAdd(stats + ST_PEN, (double)e * e);
 }
 
@@ -426,11 +433,14 @@ __global__ void obs_normalize_kernel(const float* __restrict__ x, const float* _
 
 // wd0_pad[r, c] = c < dim ? W[r, c] : 0 : the discriminator's first-layer weight with 16-byte aligned rows, so that
 // TMA can address it (disc_obs_dim = 114 floats = 456 bytes per row is not a legal tensor-map stride)
-__global__ void pad_rows_kernel(const float* __restrict__ w, int rows, int dim, int ld, float* __restrict__ out) {
+__global__ void pad_rows_kernel(const float* __restrict__ w, int rows, int dim, int ld, float* __restrict__ out,
+                                uint16_t* __restrict__ out16) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * ld) return;
   const int r = i / ld, c = i - r * ld;
-  out[i] = c < dim ? w[(size_t)r * dim + c] : 0.f;
+  const float v = c < dim ? w[(size_t)r * dim + c] : 0.f;
+  out[i] = v;
+  if (out16) out16[i] = to_bf16(v);
 }
 
 __global__ void f32_to_bf16_flat_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst, long long n) {
@@ -440,11 +450,13 @@ __global__ void f32_to_bf16_flat_kernel(const float* __restrict__ src, uint16_t*
 
 __global__ void diff_normalize_kernel(const float* __restrict__ dobs, const float* __restrict__ demo,
                                       const float* __restrict__ mean_abs, long long rows, int dim, int ld,
-                                      float* __restrict__ out) {
+                                      float* __restrict__ out, uint16_t* __restrict__ out16) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * ld) return;
   long long r = i / ld; int c = (int)(i - r * ld);
-  out[i] = c < dim ? sub_rn(demo[r * dim + c], dobs[r * dim + c]) / fmaxf(mean_abs[c], 1e-4f) : 0.f;
+  const float v = c < dim ? sub_rn(demo[r * dim + c], dobs[r * dim + c]) / fmaxf(mean_abs[c], 1e-4f) : 0.f;
+  out[i] = v;
+  if (out16) out16[i] = to_bf16(v);
 }
 
 }  // namespace addk
@@ -599,7 +611,7 @@ extern "C" int addk_update_minibatch(void* stream, void* ctx_host, const long lo
   gather_minibatch_kernel<<<(M + 7) / 8, 256, 0, st>>>(
       idx, M, OD, AD, AL, DD, DL, F(c.buf_obs), F(c.buf_action), F(c.buf_a_logp), F(c.buf_adv), F(c.buf_tar_val),
       F(c.buf_mask), F(c.buf_disc_obs), F(c.buf_disc_demo), F(c.obs_mean), F(c.obs_std), F(c.a_mean), F(c.a_std),
-      F(c.disc_mean_abs), F(c.xn), F(c.an), F(c.old_logp), F(c.adv), F(c.tar), F(c.mask), F(c.dn), cnt, twin16(c.xn));
+      F(c.disc_mean_abs), F(c.xn), F(c.an), F(c.old_logp), F(c.adv), F(c.tar), F(c.mask), F(c.dn), cnt, twin16(c.xn), twin16(c.dn));
   ADDK_CHECK_LAUNCH();
 
   // ---------------- actor ----------------
@@ -626,7 +638,7 @@ extern "C" int addk_update_minibatch(void* stream, void* ctx_host, const long lo
   // ---------------- discriminator (R = M + 1 rows) ----------------
   float *e1 = F(c.h1), *e2 = F(c.h3), *dh2 = F(c.g3), *dv1 = F(c.g1), *du2 = F(c.g2);
   const float* Wd0 = F(c.wd0_pad);
-  pad_rows_kernel<<<(E1 * DL + 255) / 256, 256, 0, st>>>(W + c.o_d_w0, E1, DD, DL, F(c.wd0_pad));
+  pad_rows_kernel<<<(E1 * DL + 255) / 256, 256, 0, st>>>(W + c.o_d_w0, E1, DD, DL, F(c.wd0_pad), twin16(c.wd0_pad));
   ADDK_CHECK_LAUNCH();
   TRY(gemm(st, pr, F(c.dn), DL, 0, Wd0, DL, 1, e1, E1, R, E1, DL, W + c.o_d_b0, 1));
   TRY(gemm(st, pr, e1, E1, 0, W + c.o_d_w1, E1, 1, e2, E2, R, E2, E1, W + c.o_d_b1, 1));
@@ -643,7 +655,7 @@ extern "C" int addk_update_minibatch(void* stream, void* ctx_host, const long lo
   TRY(gemm(st, pr, F(c.u2), E2, 0, W + c.o_d_w1, E1, 0, F(c.u1), E1, R, E1, E2, nullptr, 0, e1, E1));
   TRY(gemm(st, pr, F(c.u1), E1, 0, Wd0, DL, 0, F(c.gx), DL, R, DL, E1));
   grad_penalty_kernel<<<(R + 7) / 8, 256, 0, st>>>(F(c.gx), M, R, DD, DL,
-                                                   (float)(c.disc_loss_weight * c.disc_grad_penalty), F(c.dg), stats);
+                                                   (float)(c.disc_loss_weight * c.disc_grad_penalty), F(c.dg), stats, twin16(c.dg));
   ADDK_CHECK_LAUNCH();
   // backward of the chain (second set of slabs)
   TRY(gemm(st, pr, F(c.u1), E1, 1, F(c.dg), DL, 0, F(c.slabs) + (size_t)S * P + c.o_d_w0, DD, E1, DD, R, nullptr, 0,
@@ -754,13 +766,13 @@ extern "C" int addk_disc_eval(void* stream, void* ctx_host, const float* disc_ob
     f32_to_bf16_flat_kernel<<<148 * 4, 256, 0, st>>>(F(c.params), (uint16_t*)c.params16, c.num_params);
     ADDK_CHECK_LAUNCH();
   }
-  pad_rows_kernel<<<(E1 * DL + 255) / 256, 256, 0, st>>>(W + c.o_d_w0, E1, DD, DL, F(c.wd0_pad));
+  pad_rows_kernel<<<(E1 * DL + 255) / 256, 256, 0, st>>>(W + c.o_d_w0, E1, DD, DL, F(c.wd0_pad), twin16(c.wd0_pad));
   ADDK_CHECK_LAUNCH();
   for (long long r0 = 0; r0 < n; r0 += chunk) {
     int rows = (int)((n - r0 < chunk) ? n - r0 : chunk);
     long long tot = (long long)rows * DL;
     diff_normalize_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(disc_obs + r0 * DD, disc_obs_demo + r0 * DD,
-                                                                        F(c.disc_mean_abs), rows, DD, DL, F(c.gx));
+                                                                        F(c.disc_mean_abs), rows, DD, DL, F(c.gx), twin16(c.gx));
     ADDK_CHECK_LAUNCH();
     TRY(gemm(st, pr, F(c.gx), DL, 0, F(c.wd0_pad), DL, 1, e1, E1, rows, E1, DL, W + c.o_d_b0, 1));
     TRY(gemm(st, pr, e1, E1, 0, W + c.o_d_w1, E1, 1, e2, E2, rows, E2, E1, W + c.o_d_b1, 1));

@@ -321,7 +321,8 @@ def run_b200(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": sec / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": {"fp32": "f32", "tf32x3": "f32 (3xTF32 tensor-core split)", "tf32": "tf32", "bf16": "bf16"}[args.precision],
+        "dtype": {"fp32": "f32", "tf32x3": "f32 (3xTF32 tensor-core split)", "tf32": "tf32",
+                  "bf16": "bf16 (fp32 accumulate, fp32 master weights)"}[args.precision],
         "data": "synthetic",
         "config": {"workload": "BASELINE configs[1]: G1 walk1_subject1_trimmed, %d envs/GPU, %s MLPs, one iteration = "
                                "32-step rollout + build_train_data + 5x8 ADD/PPO minibatches; synthetic engine stands in "
@@ -404,10 +405,17 @@ def dominant_kernel_roofline(agent, args, hbm_peak, tc_peak, peak_src):
     bias = torch.zeros(Nd, device=m.flat.device)
     L = _lib.lib()
 
+    bf16 = args.precision == "bf16"
+    A16 = [a.to(torch.bfloat16) for a in A] if bf16 else None
+    W16 = Wt.to(torch.bfloat16) if bf16 else None
+    C16 = [torch.empty(M, Nd, device=m.flat.device, dtype=torch.bfloat16) for _ in range(2)] if bf16 else None
+
     def launch(i):
         a = _lib.AddkGemmArgs(A=A[i % nbuf].data_ptr(), lda=Kd, B=Wt.data_ptr(), ldb=Kd, C=Cc[i % 2].data_ptr(), ldc=Nd,
                               M=M, N=Nd, K=Kd, bias=bias.data_ptr(), a_mean=None, a_std=None, relu_mask_src=None,
-                              ld_mask=0, trans_a=0, trans_b=1, relu=1, split_k=1, accumulate=0, slab_stride=0, A16=None, B16=None, C16=None)
+                              ld_mask=0, trans_a=0, trans_b=1, relu=1, split_k=1, accumulate=0, slab_stride=0,
+                              A16=A16[i % nbuf].data_ptr() if bf16 else None, B16=W16.data_ptr() if bf16 else None,
+                              C16=C16[i % 2].data_ptr() if bf16 else None)
         _lib.check(L.addk_gemm(_lib.stream(), C.byref(a), C.c_int(m.precision)), "addk_gemm")
     for i in range(3):
         launch(i)
