@@ -186,6 +186,7 @@ class ADDAgent(torch.nn.Module):
         self._disc_reward_scale = config["disc_reward_scale"]
         self._task_reward_weight = config["task_reward_weight"]
         self._disc_reward_weight = config["disc_reward_weight"]
+        self._update_streams = int(g("update_streams", 3))   # 3: actor / critic / discriminator chains overlap
 
     def _build_normalizers(self):
         dev = self._device
@@ -232,6 +233,13 @@ class ADDAgent(torch.nn.Module):
         shapes = dict(xn=(R, od), an=(R, al), dn=(R, dl), h1=(R, w1), h2=(R, w1), h3=(R, max(H[2], E[1])), g1=(R, w1),
                       g2=(R, w1), g3=(R, max(H[2], E[1])), u1=(R, E[0]), u2=(R, E[1]), gx=(R, dl), dg=(R, dl), mean=(R, al),
                       dmean=(R, al), wd0_pad=(E[0], dl))
+        # the critic and the discriminator chains of an optimizer step get workspaces of their own, so the library can
+        # run the three chains on three streams (csrc/mlp.cu: addk_update_minibatch)
+        n_streams = int(self._update_streams)
+        assert n_streams in (1, 3)
+        if n_streams == 3:
+            shapes.update(c_h1=(R, H[0]), c_h2=(R, H[1]), c_h3=(R, H[2]), c_g1=(R, H[0]), c_g2=(R, H[1]), c_g3=(R, H[2]),
+                          d_e1=(R, E[0]), d_e2=(R, E[1]), d_dh2=(R, E[1]), d_dv1=(R, E[0]), d_du2=(R, E[1]))
         offs, total = {}, 0
         for k, shp in shapes.items():
             offs[k] = total
@@ -246,6 +254,12 @@ class ADDAgent(torch.nn.Module):
             stats=z(32, dt=torch.float64), info=z(self._max_steps, 16), cnt=z(1, dt=torch.int32),
             slabs=z(2 * S, m.num_params), colsum_work=z(64 * 1024 + 64), arena=self._arena, arena16=self._arena16,
             params16=self._params16)
+        if n_streams == 3:
+            self._ws.update(d_pred=z(R), d_dpred=z(R), colsum_work_c=z(64 * 1024 + 64), colsum_work_d=z(64 * 1024 + 64))
+        else:
+            for k in ("c_h1", "c_h2", "c_h3", "c_g1", "c_g2", "c_g3", "d_e1", "d_e2", "d_dh2", "d_dv1", "d_du2", "d_pred",
+                      "d_dpred", "colsum_work_c", "colsum_work_d"):
+                self._ws[k] = None
         ptrs = dict(self._ws)
         ptrs.update(params=m.flat, grads=m.flat_grad, exp_avg=self._optimizer.exp_avg,
                     exp_avg_sq=self._optimizer.exp_avg_sq, obs_mean=self._obs_norm._mean, obs_std=self._obs_norm._std,
@@ -254,7 +268,7 @@ class ADDAgent(torch.nn.Module):
                     buf_a_logp=fb("a_logp"), buf_adv=fb("adv"), buf_tar_val=fb("tar_val"),
                     buf_mask=fb("rand_action_mask"), buf_disc_obs=fb("disc_obs"), buf_disc_demo=fb("disc_obs_demo"))
         ints = dict(obs_dim=od, act_dim=ad, disc_dim=dd, act_ld=al, disc_ld=dl, mb_rows=M, num_params=m.num_params,
-                    split_k=S, arena_elems=total, precision=m.precision, hid_a1=H[0], hid_a2=H[1], hid_a3=H[2], hid_d1=E[0], hid_d2=E[1])
+                    split_k=S, arena_elems=total, precision=m.precision, n_streams=n_streams, hid_a1=H[0], hid_a2=H[1], hid_a3=H[2], hid_d1=E[0], hid_d2=E[1])
         ints.update(m.offsets)
         opt = self._optimizer
         f64 = dict(ppo_clip_ratio=self._ppo_clip_ratio, action_bound_weight=self._action_bound_weight,

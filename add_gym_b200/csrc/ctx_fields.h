@@ -69,6 +69,19 @@ ADDK_PTR(wd0_pad)       // [hid_d1, disc_ld] discriminator first-layer weight wi
 ADDK_PTR(arena)         // fp32 arena base (may be NULL when precision != bf16)
 ADDK_PTR(arena16)       // bf16 arena, same element offsets
 ADDK_PTR(params16)      // [P] bf16
+// ---- second and third workspace sets: the critic and the discriminator chains of one optimizer step run on their
+//      own streams next to the actor's (n_streams == 3), so the tail wave of one chain's dense layer overlaps the
+//      next chain's tiles; all NULL / n_streams == 1 = the three chains run back to back on the caller's stream
+ADDK_PTR(c_h1) ADDK_PTR(c_h2) ADDK_PTR(c_h3) ADDK_PTR(c_g1) ADDK_PTR(c_g2) ADDK_PTR(c_g3)
+ADDK_PTR(d_e1)          // [R, hid_d1]
+ADDK_PTR(d_e2)          // [R, hid_d2]
+ADDK_PTR(d_dh2)         // [R, hid_d2]
+ADDK_PTR(d_dv1)         // [R, hid_d1]
+ADDK_PTR(d_du2)         // [R, hid_d2]
+ADDK_PTR(d_pred)        // [R]
+ADDK_PTR(d_dpred)       // [R]
+ADDK_PTR(colsum_work_c) // like colsum_work, for the critic's stream
+ADDK_PTR(colsum_work_d) // like colsum_work, for the discriminator's stream
 
 ADDK_INT(obs_dim)
 ADDK_INT(act_dim)
@@ -80,6 +93,7 @@ ADDK_INT(num_params)    // P (including alignment padding)
 ADDK_INT(split_k)
 ADDK_INT(arena_elems)   // elements in the arena
 ADDK_INT(precision)     // 0 fp32 | 1 tf32x3 | 2 tf32 | 3 bf16
+ADDK_INT(n_streams)     // 1 | 3
 ADDK_INT(hid_a1)        // actor/critic hidden sizes (1024, 1024, 512)
 ADDK_INT(hid_a2)
 ADDK_INT(hid_a3)

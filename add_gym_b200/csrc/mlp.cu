@@ -465,11 +465,18 @@ using namespace addk;
 typedef addk_update_ctx Ctx;
 #define F(p) ((float*)(p))
 
-static int colsum(cudaStream_t st, const addk_update_ctx& c, const float* dY, int ld, int rows, int n, float* out,
-                  const float* rw) {
+// One chain's activations / gradients and its column-sum scratch.  The actor, the critic and the discriminator
+// chains of an optimizer step each own one when they run on separate streams.
+struct ChainWs {
+  float *h1, *h2, *h3, *g1, *g2, *g3;
+  float* colsum_work;
+};
+
+static int colsum(cudaStream_t st, const addk_update_ctx& c, const ChainWs& ws, const float* dY, int ld, int rows, int n,
+                  float* out, const float* rw) {
   using addk::COLSUM_MAX_N; using addk::COLSUM_CHUNKS;
   if (n > COLSUM_MAX_N) { addk_set_error("colsum: more than 1024 columns"); return ADDK_ERR_UNSUPPORTED; }
-  float* work = (float*)c.colsum_work;
+  float* work = ws.colsum_work;
   unsigned int* tickets = (unsigned int*)(work + (size_t)COLSUM_CHUNKS * COLSUM_MAX_N);
   addk::colsum_slabs_kernel<<<dim3((n + 127) / 128, COLSUM_CHUNKS), 256, 0, st>>>(dY, ld, rows, n, out, c.num_params,
                                                                          (int)c.split_k, rw, work, tickets);
@@ -507,18 +514,18 @@ static int gemm(cudaStream_t st, int prec, const float* A, int lda, int ta, cons
 #define TRY(x) do { int rc__ = (x); if (rc__ != ADDK_OK) return rc__; } while (0)
 
 // weight gradient dW[N_out, K_in] = dY^T X and bias gradient db = 1^T dY, as split-K slabs
-static int wgrad(cudaStream_t st, const Ctx& c, const float* dY, int ldy, const float* X, int ldx, int rows, int n_out,
-                 int k_in, long long o_w, long long o_b, int slab0) {
+static int wgrad(cudaStream_t st, const Ctx& c, const ChainWs& ws, const float* dY, int ldy, const float* X, int ldx,
+                 int rows, int n_out, int k_in, long long o_w, long long o_b, int slab0) {
   const int S = (int)c.split_k;
   const long long P = c.num_params;
   if (n_out == 1 && ldy == 1) {
-    TRY(colsum(st, c, X, ldx, rows, k_in, F(c.slabs) + (size_t)slab0 * P + o_w, dY));
+    TRY(colsum(st, c, ws, X, ldx, rows, k_in, F(c.slabs) + (size_t)slab0 * P + o_w, dY));
   } else {
     TRY(gemm(st, (int)c.precision, dY, ldy, 1, X, ldx, 0, F(c.slabs) + (size_t)slab0 * P + o_w, k_in, n_out, k_in, rows,
              nullptr, 0, nullptr, 0, S, nullptr, nullptr, P));
   }
   if (o_b >= 0) {
-    TRY(colsum(st, c, dY, ldy, rows, n_out, F(c.slabs) + (size_t)slab0 * P + o_b, nullptr));
+    TRY(colsum(st, c, ws, dY, ldy, rows, n_out, F(c.slabs) + (size_t)slab0 * P + o_b, nullptr));
   }
   return ADDK_OK;
 }
@@ -538,7 +545,7 @@ static int head1_dgrad(cudaStream_t st, const float* d, const float* w, const fl
 }
 
 // 3-hidden-layer trunk forward: X[rows,in] -> h1,h2,h3
-static int trunk_forward(cudaStream_t st, const Ctx& c, const float* X, int ldx, int in_dim, int rows, long long o_w0,
+static int trunk_forward(cudaStream_t st, const Ctx& c, const ChainWs& ws, const float* X, int ldx, int in_dim, int rows, long long o_w0,
                          long long o_b0, long long o_w1, long long o_b1, long long o_w2, long long o_b2,
                          const float* nmean = nullptr, const float* nstd = nullptr) {
   const float* P = F(c.params);
@@ -551,23 +558,53 @@ static int trunk_forward(cudaStream_t st, const Ctx& c, const float* X, int ldx,
     ADDK_CHECK_LAUNCH();
     X = F(c.xn); nmean = nullptr; nstd = nullptr;
   }
-  TRY(gemm(st, nmean ? 0 : pr, X, ldx, 0, P + o_w0, in_dim, 1, F(c.h1), H1, rows, H1, in_dim, P + o_b0, 1, nullptr, 0, 1,
+  TRY(gemm(st, nmean ? 0 : pr, X, ldx, 0, P + o_w0, in_dim, 1, ws.h1, H1, rows, H1, in_dim, P + o_b0, 1, nullptr, 0, 1,
            nmean, nstd));
-  TRY(gemm(st, pr, F(c.h1), H1, 0, P + o_w1, H1, 1, F(c.h2), H2, rows, H2, H1, P + o_b1, 1));
-  TRY(gemm(st, pr, F(c.h2), H2, 0, P + o_w2, H2, 1, F(c.h3), H3, rows, H3, H2, P + o_b2, 1));
+  TRY(gemm(st, pr, ws.h1, H1, 0, P + o_w1, H1, 1, ws.h2, H2, rows, H2, H1, P + o_b1, 1));
+  TRY(gemm(st, pr, ws.h2, H2, 0, P + o_w2, H2, 1, ws.h3, H3, rows, H3, H2, P + o_b2, 1));
   return ADDK_OK;
 }
 
 // trunk backward given g3 = dL/dh3 (already masked by h3 > 0)
-static int trunk_backward(cudaStream_t st, const Ctx& c, const float* X, int ldx, int in_dim, int rows, long long o_w0,
+static int trunk_backward(cudaStream_t st, const Ctx& c, const ChainWs& ws, const float* X, int ldx, int in_dim, int rows, long long o_w0,
                           long long o_b0, long long o_w1, long long o_b1, long long o_w2, long long o_b2) {
   const float* P = F(c.params);
   const int H1 = (int)c.hid_a1, H2 = (int)c.hid_a2, H3 = (int)c.hid_a3, pr = (int)c.precision;
-  TRY(wgrad(st, c, F(c.g3), H3, F(c.h2), H2, rows, H3, H2, o_w2, o_b2, 0));
-  TRY(gemm(st, pr, F(c.g3), H3, 0, P + o_w2, H2, 0, F(c.g2), H2, rows, H2, H3, nullptr, 0, F(c.h2), H2));
-  TRY(wgrad(st, c, F(c.g2), H2, F(c.h1), H1, rows, H2, H1, o_w1, o_b1, 0));
-  TRY(gemm(st, pr, F(c.g2), H2, 0, P + o_w1, H1, 0, F(c.g1), H1, rows, H1, H2, nullptr, 0, F(c.h1), H1));
-  TRY(wgrad(st, c, F(c.g1), H1, X, ldx, rows, H1, in_dim, o_w0, o_b0, 0));
+  TRY(wgrad(st, c, ws, ws.g3, H3, ws.h2, H2, rows, H3, H2, o_w2, o_b2, 0));
+  TRY(gemm(st, pr, ws.g3, H3, 0, P + o_w2, H2, 0, ws.g2, H2, rows, H2, H3, nullptr, 0, ws.h2, H2));
+  TRY(wgrad(st, c, ws, ws.g2, H2, ws.h1, H1, rows, H2, H1, o_w1, o_b1, 0));
+  TRY(gemm(st, pr, ws.g2, H2, 0, P + o_w1, H1, 0, ws.g1, H1, rows, H1, H2, nullptr, 0, ws.h1, H1));
+  TRY(wgrad(st, c, ws, ws.g1, H1, X, ldx, rows, H1, in_dim, o_w0, o_b0, 0));
+  return ADDK_OK;
+}
+
+static ChainWs main_ws(const Ctx& c) {
+  return ChainWs{F(c.h1), F(c.h2), F(c.h3), F(c.g1), F(c.g2), F(c.g3), F(c.colsum_work)};
+}
+
+// Two helper streams (+ fork / join events) per device for the critic and the discriminator chains, created on first use.
+struct AuxStreams {
+  int device = -1;
+  cudaStream_t s[2] = {nullptr, nullptr};
+  cudaEvent_t fork = nullptr, join[2] = {nullptr, nullptr};
+};
+static int aux_streams(AuxStreams** out) {
+  static AuxStreams a;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { addk_set_error("cudaGetDevice failed"); return ADDK_ERR_LAUNCH; }
+  if (a.device != dev) {
+    if (a.device >= 0) {   // the process moved to another device: drop the old helpers
+      for (int i = 0; i < 2; ++i) { cudaStreamDestroy(a.s[i]); cudaEventDestroy(a.join[i]); }
+      cudaEventDestroy(a.fork);
+    }
+    bool ok = cudaEventCreateWithFlags(&a.fork, cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; i < 2 && ok; ++i)
+      ok = cudaStreamCreateWithFlags(&a.s[i], cudaStreamNonBlocking) == cudaSuccess &&
+           cudaEventCreateWithFlags(&a.join[i], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) { a.device = -1; addk_set_error("could not create the helper streams of the update"); return ADDK_ERR_LAUNCH; }
+    a.device = dev;
+  }
+  *out = &a;
   return ADDK_OK;
 }
 
@@ -614,62 +651,87 @@ extern "C" int addk_update_minibatch(void* stream, void* ctx_host, const long lo
       F(c.disc_mean_abs), F(c.xn), F(c.an), F(c.old_logp), F(c.adv), F(c.tar), F(c.mask), F(c.dn), cnt, twin16(c.xn), twin16(c.dn));
   ADDK_CHECK_LAUNCH();
 
-  // ---------------- actor ----------------
-  TRY(trunk_forward(st, c, F(c.xn), OD, OD, M, c.o_a_w0, c.o_a_b0, c.o_a_w1, c.o_a_b1, c.o_a_w2, c.o_a_b2));
-  TRY(gemm(st, pr, F(c.h3), H3, 0, W + c.o_a_wm, H3, 1, F(c.mean), AL, M, AD, H3, W + c.o_a_bm, 0));
-  actor_loss_kernel<<<(M + 7) / 8, 256, 0, st>>>(F(c.mean), F(c.an), F(c.logstd), F(c.old_logp), F(c.adv), F(c.mask), M,
+  // The three chains share only read-only inputs (xn, dn, the parameters) and write disjoint slab segments and
+  // statistics slots.  With n_streams == 3 each has its own workspace and stream: the tail wave of one chain's dense
+  // layer (3.46 waves of tiles at M = 16384) is filled by the other chains' tiles.
+  const bool multi = c.n_streams == 3 && c.c_h1 && c.d_e1 && c.colsum_work_c && c.colsum_work_d;
+  cudaStream_t sa = st, sc = st, sd = st;
+  AuxStreams* aux = nullptr;
+  if (multi) {
+    TRY(aux_streams(&aux));
+    sc = aux->s[0]; sd = aux->s[1];
+    cudaEventRecord(aux->fork, st);
+    cudaStreamWaitEvent(sc, aux->fork, 0);
+    cudaStreamWaitEvent(sd, aux->fork, 0);
+  }
+  const ChainWs wa = main_ws(c);
+  const ChainWs wc = multi ? ChainWs{F(c.c_h1), F(c.c_h2), F(c.c_h3), F(c.c_g1), F(c.c_g2), F(c.c_g3), F(c.colsum_work_c)} : wa;
+  const ChainWs wd = multi ? ChainWs{F(c.d_e1), nullptr, F(c.d_e2), F(c.d_dv1), F(c.d_du2), F(c.d_dh2), F(c.colsum_work_d)} : wa;
+  float* pred_d = multi ? F(c.d_pred) : F(c.pred);
+  float* dpred_d = multi ? F(c.d_dpred) : F(c.dpred);
+
+  // ---------------- actor (stream sa) ----------------
+  TRY(trunk_forward(sa, c, wa, F(c.xn), OD, OD, M, c.o_a_w0, c.o_a_b0, c.o_a_w1, c.o_a_b1, c.o_a_w2, c.o_a_b2));
+  TRY(gemm(sa, pr, wa.h3, H3, 0, W + c.o_a_wm, H3, 1, F(c.mean), AL, M, AD, H3, W + c.o_a_bm, 0));
+  actor_loss_kernel<<<(M + 7) / 8, 256, 0, sa>>>(F(c.mean), F(c.an), F(c.logstd), F(c.old_logp), F(c.adv), F(c.mask), M,
                                                  AD, AL, (float)c.ppo_clip_ratio, (float)c.action_bound_weight, cnt,
                                                  F(c.dmean), stats, twin16(c.dmean));
   ADDK_CHECK_LAUNCH();
-  TRY(wgrad(st, c, F(c.dmean), AL, F(c.h3), H3, M, AD, H3, c.o_a_wm, c.o_a_bm, 0));
-  TRY(gemm(st, pr, F(c.dmean), AL, 0, W + c.o_a_wm, H3, 0, F(c.g3), H3, M, H3, AD, nullptr, 0, F(c.h3), H3));
-  TRY(trunk_backward(st, c, F(c.xn), OD, OD, M, c.o_a_w0, c.o_a_b0, c.o_a_w1, c.o_a_b1, c.o_a_w2, c.o_a_b2));
+  TRY(wgrad(sa, c, wa, F(c.dmean), AL, wa.h3, H3, M, AD, H3, c.o_a_wm, c.o_a_bm, 0));
+  TRY(gemm(sa, pr, F(c.dmean), AL, 0, W + c.o_a_wm, H3, 0, wa.g3, H3, M, H3, AD, nullptr, 0, wa.h3, H3));
+  TRY(trunk_backward(sa, c, wa, F(c.xn), OD, OD, M, c.o_a_w0, c.o_a_b0, c.o_a_w1, c.o_a_b1, c.o_a_w2, c.o_a_b2));
 
-  // ---------------- critic ----------------
-  TRY(trunk_forward(st, c, F(c.xn), OD, OD, M, c.o_c_w0, c.o_c_b0, c.o_c_w1, c.o_c_b1, c.o_c_w2, c.o_c_b2));
-  TRY(head1_forward(st, F(c.h3), H3, M, H3, W + c.o_c_wo, W + c.o_c_bo, F(c.pred)));
-  critic_loss_kernel<<<(M + 255) / 256, 256, 0, st>>>(F(c.pred), F(c.tar), M, (float)c.critic_loss_weight, F(c.dpred),
+  // ---------------- critic (stream sc) ----------------
+  TRY(trunk_forward(sc, c, wc, F(c.xn), OD, OD, M, c.o_c_w0, c.o_c_b0, c.o_c_w1, c.o_c_b1, c.o_c_w2, c.o_c_b2));
+  TRY(head1_forward(sc, wc.h3, H3, M, H3, W + c.o_c_wo, W + c.o_c_bo, F(c.pred)));
+  critic_loss_kernel<<<(M + 255) / 256, 256, 0, sc>>>(F(c.pred), F(c.tar), M, (float)c.critic_loss_weight, F(c.dpred),
                                                       stats);
   ADDK_CHECK_LAUNCH();
-  TRY(wgrad(st, c, F(c.dpred), 1, F(c.h3), H3, M, 1, H3, c.o_c_wo, c.o_c_bo, 0));
-  TRY(head1_dgrad(st, F(c.dpred), W + c.o_c_wo, F(c.h3), M, H3, F(c.g3)));
-  TRY(trunk_backward(st, c, F(c.xn), OD, OD, M, c.o_c_w0, c.o_c_b0, c.o_c_w1, c.o_c_b1, c.o_c_w2, c.o_c_b2));
+  TRY(wgrad(sc, c, wc, F(c.dpred), 1, wc.h3, H3, M, 1, H3, c.o_c_wo, c.o_c_bo, 0));
+  TRY(head1_dgrad(sc, F(c.dpred), W + c.o_c_wo, wc.h3, M, H3, wc.g3));
+  TRY(trunk_backward(sc, c, wc, F(c.xn), OD, OD, M, c.o_c_w0, c.o_c_b0, c.o_c_w1, c.o_c_b1, c.o_c_w2, c.o_c_b2));
 
-  // ---------------- discriminator (R = M + 1 rows) ----------------
-  float *e1 = F(c.h1), *e2 = F(c.h3), *dh2 = F(c.g3), *dv1 = F(c.g1), *du2 = F(c.g2);
+  // ---------------- discriminator (stream sd; R = M + 1 rows) ----------------
+  float *e1 = wd.h1, *e2 = wd.h3, *dh2 = wd.g3, *dv1 = wd.g1, *du2 = wd.g2;
   const float* Wd0 = F(c.wd0_pad);
-  pad_rows_kernel<<<(E1 * DL + 255) / 256, 256, 0, st>>>(W + c.o_d_w0, E1, DD, DL, F(c.wd0_pad), twin16(c.wd0_pad));
+  pad_rows_kernel<<<(E1 * DL + 255) / 256, 256, 0, sd>>>(W + c.o_d_w0, E1, DD, DL, F(c.wd0_pad), twin16(c.wd0_pad));
   ADDK_CHECK_LAUNCH();
-  TRY(gemm(st, pr, F(c.dn), DL, 0, Wd0, DL, 1, e1, E1, R, E1, DL, W + c.o_d_b0, 1));
-  TRY(gemm(st, pr, e1, E1, 0, W + c.o_d_w1, E1, 1, e2, E2, R, E2, E1, W + c.o_d_b1, 1));
-  TRY(head1_forward(st, e2, E2, R, E2, W + c.o_d_wl, W + c.o_d_bl, F(c.pred)));
-  disc_loss_kernel<<<(R + 255) / 256, 256, 0, st>>>(F(c.pred), M, (float)c.disc_loss_weight, F(c.dpred), stats);
+  TRY(gemm(sd, pr, F(c.dn), DL, 0, Wd0, DL, 1, e1, E1, R, E1, DL, W + c.o_d_b0, 1));
+  TRY(gemm(sd, pr, e1, E1, 0, W + c.o_d_w1, E1, 1, e2, E2, R, E2, E1, W + c.o_d_b1, 1));
+  TRY(head1_forward(sd, e2, E2, R, E2, W + c.o_d_wl, W + c.o_d_bl, pred_d));
+  disc_loss_kernel<<<(R + 255) / 256, 256, 0, sd>>>(pred_d, M, (float)c.disc_loss_weight, dpred_d, stats);
   ADDK_CHECK_LAUNCH();
   {
     size_t tot = (size_t)R * E2;
-    disc_head_backward_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(e2, W + c.o_d_wl, F(c.dpred), R, E2, F(c.u2),
+    disc_head_backward_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, sd>>>(e2, W + c.o_d_wl, dpred_d, R, E2, F(c.u2),
                                                                             dh2, twin16(c.u2), twin16(dh2));
     ADDK_CHECK_LAUNCH();
   }
   // input-gradient chain: u1 = m1 * (u2 W2), gx = u1 W1
-  TRY(gemm(st, pr, F(c.u2), E2, 0, W + c.o_d_w1, E1, 0, F(c.u1), E1, R, E1, E2, nullptr, 0, e1, E1));
-  TRY(gemm(st, pr, F(c.u1), E1, 0, Wd0, DL, 0, F(c.gx), DL, R, DL, E1));
-  grad_penalty_kernel<<<(R + 7) / 8, 256, 0, st>>>(F(c.gx), M, R, DD, DL,
+  TRY(gemm(sd, pr, F(c.u2), E2, 0, W + c.o_d_w1, E1, 0, F(c.u1), E1, R, E1, E2, nullptr, 0, e1, E1));
+  TRY(gemm(sd, pr, F(c.u1), E1, 0, Wd0, DL, 0, F(c.gx), DL, R, DL, E1));
+  grad_penalty_kernel<<<(R + 7) / 8, 256, 0, sd>>>(F(c.gx), M, R, DD, DL,
                                                    (float)(c.disc_loss_weight * c.disc_grad_penalty), F(c.dg), stats, twin16(c.dg));
   ADDK_CHECK_LAUNCH();
   // backward of the chain (second set of slabs)
-  TRY(gemm(st, pr, F(c.u1), E1, 1, F(c.dg), DL, 0, F(c.slabs) + (size_t)S * P + c.o_d_w0, DD, E1, DD, R, nullptr, 0,
+  TRY(gemm(sd, pr, F(c.u1), E1, 1, F(c.dg), DL, 0, F(c.slabs) + (size_t)S * P + c.o_d_w0, DD, E1, DD, R, nullptr, 0,
            nullptr, 0, S, nullptr, nullptr, P));
-  TRY(gemm(st, pr, F(c.dg), DL, 0, Wd0, DL, 1, dv1, E1, R, E1, DL, nullptr, 0, e1, E1));
-  TRY(gemm(st, pr, F(c.u2), E2, 1, dv1, E1, 0, F(c.slabs) + (size_t)S * P + c.o_d_w1, E1, E2, E1, R, nullptr, 0, nullptr, 0,
+  TRY(gemm(sd, pr, F(c.dg), DL, 0, Wd0, DL, 1, dv1, E1, R, E1, DL, nullptr, 0, e1, E1));
+  TRY(gemm(sd, pr, F(c.u2), E2, 1, dv1, E1, 0, F(c.slabs) + (size_t)S * P + c.o_d_w1, E1, E2, E1, R, nullptr, 0, nullptr, 0,
            S, nullptr, nullptr, P));
-  TRY(gemm(st, pr, dv1, E1, 0, W + c.o_d_w1, E1, 1, du2, E2, R, E2, E1, nullptr, 0, e2, E2));
-  TRY(colsum(st, c, du2, E2, R, E2, F(c.slabs) + (size_t)S * P + c.o_d_wl, nullptr));
+  TRY(gemm(sd, pr, dv1, E1, 0, W + c.o_d_w1, E1, 1, du2, E2, R, E2, E1, nullptr, 0, e2, E2));
+  TRY(colsum(sd, c, wd, du2, E2, R, E2, F(c.slabs) + (size_t)S * P + c.o_d_wl, nullptr));
   // ordinary backward of the BCE terms
-  TRY(wgrad(st, c, F(c.dpred), 1, e2, E2, R, 1, E2, c.o_d_wl, c.o_d_bl, 0));
-  TRY(wgrad(st, c, dh2, E2, e1, E1, R, E2, E1, c.o_d_w1, c.o_d_b1, 0));
-  TRY(gemm(st, pr, dh2, E2, 0, W + c.o_d_w1, E1, 0, F(c.u1), E1, R, E1, E2, nullptr, 0, e1, E1));
-  TRY(wgrad(st, c, F(c.u1), E1, F(c.dn), DL, R, E1, DD, c.o_d_w0, c.o_d_b0, 0));
+  TRY(wgrad(sd, c, wd, dpred_d, 1, e2, E2, R, 1, E2, c.o_d_wl, c.o_d_bl, 0));
+  TRY(wgrad(sd, c, wd, dh2, E2, e1, E1, R, E2, E1, c.o_d_w1, c.o_d_b1, 0));
+  TRY(gemm(sd, pr, dh2, E2, 0, W + c.o_d_w1, E1, 0, F(c.u1), E1, R, E1, E2, nullptr, 0, e1, E1));
+  TRY(wgrad(sd, c, wd, F(c.u1), E1, F(c.dn), DL, R, E1, DD, c.o_d_w0, c.o_d_b0, 0));
+  if (multi) {
+    cudaEventRecord(aux->join[0], sc);
+    cudaEventRecord(aux->join[1], sd);
+    cudaStreamWaitEvent(st, aux->join[0], 0);
+    cudaStreamWaitEvent(st, aux->join[1], 0);
+  }
   // regularisers (values for the log; their gradients are folded into the slab reduction)
   sumsq_kernel<<<8, 256, 0, st>>>(W + c.o_d_wl, E2, stats + ST_WL_SQ);
   ADDK_CHECK_LAUNCH();
@@ -722,7 +784,7 @@ extern "C" int addk_actor_step(void* stream, void* ctx_host, const float* obs, c
     ADDK_CHECK_LAUNCH();
   }
   if (obs_rec) cudaMemcpyAsync(obs_rec, obs, (size_t)n * OD * sizeof(float), cudaMemcpyDeviceToDevice, st);
-  TRY(trunk_forward(st, c, obs, OD, OD, n, c.o_a_w0, c.o_a_b0, c.o_a_w1, c.o_a_b1, c.o_a_w2, c.o_a_b2, F(c.obs_mean),
+  TRY(trunk_forward(st, c, main_ws(c), obs, OD, OD, n, c.o_a_w0, c.o_a_b0, c.o_a_w1, c.o_a_b1, c.o_a_w2, c.o_a_b2, F(c.obs_mean),
                     F(c.obs_std)));
   TRY(gemm(st, (int)c.precision, F(c.h3), H3, 0, W + c.o_a_wm, H3, 1, F(c.mean), AL, n, AD, H3, W + c.o_a_bm, 0));
   sample_action_kernel<<<(n + 7) / 8, 256, 0, st>>>(F(c.mean), AL, F(c.logstd), noise, exp_mask, F(c.a_mean), F(c.a_std),
@@ -745,7 +807,7 @@ extern "C" int addk_critic_eval(void* stream, void* ctx_host, const float* obs, 
   }
   for (long long r0 = 0; r0 < n; r0 += chunk) {
     int rows = (int)((n - r0 < chunk) ? n - r0 : chunk);
-    TRY(trunk_forward(st, c, obs + r0 * OD, OD, OD, rows, c.o_c_w0, c.o_c_b0, c.o_c_w1, c.o_c_b1, c.o_c_w2, c.o_c_b2,
+    TRY(trunk_forward(st, c, main_ws(c), obs + r0 * OD, OD, OD, rows, c.o_c_w0, c.o_c_b0, c.o_c_w1, c.o_c_b1, c.o_c_w2, c.o_c_b2,
                       F(c.obs_mean), F(c.obs_std)));
     TRY(head1_forward(st, F(c.h3), H3, rows, H3, W + c.o_c_wo, W + c.o_c_bo, vals + r0));
   }

@@ -432,3 +432,36 @@ def test_cuda_graph_rollout_is_bit_identical_to_eager():
     assert torch.equal(eager._env.time_buf, graphed._env.time_buf)
     assert torch.equal(eager._core.hist, graphed._core.hist) and eager._core.hist_head == graphed._core.hist_head
     assert int(eager._core.tracker_count.item()) == int(graphed._core.tracker_count.item())
+
+
+@pytest.mark.parametrize("precision", ["tf32x3", "bf16"])
+def test_three_stream_update_is_bit_identical_to_one_stream(precision):
+    """The actor / critic / discriminator chains of an optimizer step on three streams (separate workspaces, tail waves
+    overlapping) must produce exactly the parameters the back-to-back single-stream order produces: every kernel is
+    deterministic and the chains write disjoint slab segments and statistics slots."""
+    from add_gym_b200.add_agent import ADDAgent
+
+    def run(streams):
+        cfg = b200_config.default_config(num_envs=96, mlp_precision=precision)
+        cfg["agent"]["update_streams"] = streams
+        cfg["engine"].update(seed=5, noise_device="device", fall_prob=0.02)
+        torch.manual_seed(1)
+        a = ADDAgent(cfg, device="cuda:0")
+        a._curr_obs, a._curr_info = a._reset_envs()
+        infos = []
+        for _ in range(2):
+            a._exp_buffer.clear()
+            a._rollout_train(a._steps_per_iter)
+            a._build_train_data()
+            infos.append(dict(a._update_model()))
+        torch.cuda.synchronize()
+        return a, infos
+
+    one, i1 = run(1)
+    three, i3 = run(3)
+    assert one._ctx.ints["n_streams"] == 1 and three._ctx.ints["n_streams"] == 3
+    assert torch.equal(one._model.flat, three._model.flat)
+    assert torch.equal(one._optimizer.exp_avg_sq, three._optimizer.exp_avg_sq)
+    for x, y in zip(i1, i3):
+        for k in x:
+            assert float(x[k]) == float(y[k]), k
