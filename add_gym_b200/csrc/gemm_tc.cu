@@ -42,6 +42,7 @@ struct Params {
   int a_mn, b_mn;              // operand is MN-major (memory rows = contraction index)
   long long slab_stride;       // floats between split-K slabs
   void* C16;                   // bf16 kernel: optional bf16 copy of the output (same leading dimension)
+  long long* dbg;              // experiment: clock64 stamps of CTA (0,0,0) of the pair kernel (env ADDK_TC_DBG = address)
   int pair_flags;              // CTA-pair kernel experiments: bit0 cluster-scope waits, bit1 relaxed remote arrives
 };
 
@@ -107,6 +108,16 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// one lane of a converged warp (always the same one for a full mask)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
@@ -119,6 +130,108 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
       : "r"(taddr) : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Epilogue helpers shared by the fp32-output kernels.  A warp owns 32 accumulator rows (one per lane, the TMEM view) x CW
+// columns.  It first writes them into a swizzled staging tile in shared memory (stage_put: slot = float4 index inside
+// the row, XOR-ed with row & 7 -> conflict-free both ways), then store_staged() walks the tile ROW by row so that one
+// store instruction covers min(CW, 128) consecutive floats of one output row (512 contiguous bytes), with bias / ReLU /
+// ReLU-mask / accumulate applied on that coalesced side.  Measured with clock stamps on the 16384x1024x1024 layer: the
+// earlier shape (4 rows x 128 B per instruction, every warp of every CTA on the same 128-byte column phase at the same
+// time) kept address bits 7-8 constant GPU-wide and drained at 2.7 B/clk/SM (38k of a CTA's 108k cycles); full rows
+// take 11k.
+template <int CW>
+__device__ __forceinline__ void stage_put(float4* stg, int lane, int slot, float a, float b, float c, float d) {
+  stg[lane * (CW / 4) + (slot ^ (lane & 7))] = make_float4(a, b, c, d);
+}
+
+template <int CW>
+__device__ __forceinline__ void store_staged(const Params& p, float* Cz, const float4* stg, int lane, int grow0, int col0) {
+  constexpr int S = CW / 4;                        // float4 slots per row
+  constexpr int RPI = S >= 32 ? 1 : 32 / S;        // rows per store instruction
+  constexpr int PPR = S > 32 ? S / 32 : 1;         // instructions per row
+  constexpr int NIT = (32 / RPI) * PPR;
+  static_assert(S % 8 == 0 && NIT % 8 == 0, "tile shape");
+  const int sub_r = S >= 32 ? 0 : lane / S;
+  const int sl0 = S >= 32 ? lane : lane % S;
+  float4 b4[PPR];
+#pragma unroll
+  for (int ps = 0; ps < PPR; ++ps) {
+    const int col = col0 + 4 * (sl0 + 32 * ps);
+    b4[ps] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p.bias) {
+      if (col + 3 < p.N) b4[ps] = *reinterpret_cast<const float4*>(p.bias + col);
+      else { if (col < p.N) b4[ps].x = p.bias[col]; if (col + 1 < p.N) b4[ps].y = p.bias[col + 1]; if (col + 2 < p.N) b4[ps].z = p.bias[col + 2]; }
+    }
+  }
+#pragma unroll 1
+  for (int i0 = 0; i0 < NIT; i0 += 8) {
+    float4 m4[8], a4[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {                  // operand loads of eight instructions first
+      const int it = i0 + u;
+      const int grow = grow0 + (it / PPR) * RPI + sub_r;
+      const int col = col0 + 4 * (sl0 + 32 * (it % PPR));
+      m4[u] = make_float4(1.f, 1.f, 1.f, 1.f);
+      a4[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (grow < p.M && col + 3 < p.N) {
+        if (p.mask) m4[u] = *reinterpret_cast<const float4*>(p.mask + (size_t)grow * p.ld_mask + col);
+        if (p.accumulate) a4[u] = *reinterpret_cast<const float4*>(Cz + (size_t)grow * p.ldc + col);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int it = i0 + u;
+      const int r = (it / PPR) * RPI + sub_r;
+      const int sl = sl0 + 32 * (it % PPR);
+      const int grow = grow0 + r, col = col0 + 4 * sl;
+      float4 o = stg[r * S + (sl ^ (r & 7))];
+      if (grow < p.M && col < p.N) {
+        const float4 bb = b4[it % PPR];
+        o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+        if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+        float* dstp = Cz + (size_t)grow * p.ldc + col;
+        if (col + 3 < p.N) {
+          o.x = m4[u].x > 0.f ? o.x : 0.f; o.y = m4[u].y > 0.f ? o.y : 0.f;
+          o.z = m4[u].z > 0.f ? o.z : 0.f; o.w = m4[u].w > 0.f ? o.w : 0.f;
+          o.x += a4[u].x; o.y += a4[u].y; o.z += a4[u].z; o.w += a4[u].w;
+          *reinterpret_cast<float4*>(dstp) = o;
+        } else {
+          const float oo[4] = {o.x, o.y, o.z, o.w};
+          for (int e = 0; e < 4 && col + e < p.N; ++e) {
+            float xv = oo[e];
+            if (p.mask) xv = p.mask[(size_t)grow * p.ld_mask + col + e] > 0.f ? xv : 0.f;
+            if (p.accumulate) xv += dstp[e];
+            dstp[e] = xv;
+          }
+        }
+      }
+    }
+  }
+}
+
+// row-per-lane scalar fallback for outputs that are not 16-byte aligned (ldc % 4 != 0)
+__device__ __forceinline__ void store_row_scalar(const Params& p, float* Cz, int row, int cbase, const float* acc32) {
+  float* dstp = Cz + (size_t)row * p.ldc + cbase;
+  const float* mk = p.mask ? p.mask + (size_t)row * p.ld_mask + cbase : nullptr;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const int col = cbase + j;
+    if (col < p.N) {
+      float xv = acc32[j];
+      if (p.bias) xv += p.bias[col];
+      if (p.relu) xv = fmaxf(xv, 0.f);
+      if (mk) xv = mk[j] > 0.f ? xv : 0.f;
+      if (p.accumulate) xv += dstp[j];
+      dstp[j] = xv;
+    }
+  }
+}
+__device__ __forceinline__ bool epilogue_vec_ok(const Params& p, const float* Cz) {
+  return ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(Cz) & 15) == 0) &&
+         (!p.bias || ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0)) &&
+         (!p.mask || (((p.ld_mask & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.mask) & 15) == 0)));
 }
 
 // One stage of the ring.  A: 128 (rows | columns) x BK k;  B: BN x BK k.  tf32x3 adds the "lo" halves and uses
@@ -298,92 +411,41 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int q = warp & 3;                  // TMEM lane quarter this warp may access
     const int row = m0 + 32 * q + lane;
     float* Cz = p.C + (size_t)blockIdx.z * p.slab_stride;
-    const bool vec = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(Cz) & 15) == 0) &&
-                     (!p.bias || ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0)) &&
-                     (!p.mask || (((p.ld_mask & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.mask) & 15) == 0)));
-    // Each warp owns rows [32q, 32q+32) of the tile.  Accumulator columns come out of TMEM one row per lane, which
-    // would scatter every store over 32 rows; so each 32 x 32 chunk is transposed through a 4 KB swizzled shared
-    // buffer (the operand stages are idle by now) and leaves as four full 128-byte row segments per instruction,
-    // with bias / mask / accumulate applied on the coalesced side (one float4 of bias per lane per chunk).
+    const bool vec = epilogue_vec_ok(p, Cz);
+    // Each warp owns rows [32q, 32q+32) of the tile: blocks of up to 128 columns go TMEM -> registers -> a 16 KB
+    // staging tile per warp (the operand stages are idle by now) -> full-row stores (store_staged).
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    float4* stg = reinterpret_cast<float4*>(base_ptr + 4096 * q);
-    const int l_row = lane >> 3, l_c4 = lane & 7;
+    constexpr int CWB = BN < 128 ? BN : 128;
+    float4* stg = reinterpret_cast<float4*>(base_ptr + (32 * CWB * 4) * q);
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
+    for (int c0 = 0; c0 < BN; c0 += CWB) {
       if (n0 + c0 >= p.N) break;             // warp-uniform
-      // ReLU-mask / accumulate operands of this chunk: issue the global loads first so they fly during the TMEM read
-      float4 m4[8], a4[8];
-      const int colv = n0 + c0 + 4 * l_c4;
-      const bool full4 = vec && (colv + 3 < p.N);
 #pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const int grow = m0 + 32 * q + it * 4 + l_row;
-        m4[it] = make_float4(1.f, 1.f, 1.f, 1.f);
-        a4[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (full4 && grow < p.M) {
-          if (p.mask) m4[it] = *reinterpret_cast<const float4*>(p.mask + (size_t)grow * p.ld_mask + colv);
-          if (p.accumulate) a4[it] = *reinterpret_cast<const float4*>(Cz + (size_t)grow * p.ldc + colv);
+      for (int cc = 0; cc < CWB / 32; ++cc) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(c0 + cc * 32), v);
+        if (X3) {
+          uint32_t w[32];
+          tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(BN + c0 + cc * 32), w);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w[j]));
         }
-      }
-      uint32_t v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)c0, v);
-      if (X3) {
-        uint32_t w[32];
-        tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(BN + c0), w);
+        if (vec) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w[j]));
+          for (int c4 = 0; c4 < 8; ++c4)
+            stage_put<CWB>(stg, lane, cc * 8 + c4, __uint_as_float(v[4 * c4]), __uint_as_float(v[4 * c4 + 1]),
+                           __uint_as_float(v[4 * c4 + 2]), __uint_as_float(v[4 * c4 + 3]));
+        } else if (row < p.M) {
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          store_row_scalar(p, Cz, row, n0 + c0 + cc * 32, f);
+        }
       }
       if (vec) {
-#pragma unroll
-        for (int c4 = 0; c4 < 8; ++c4)
-          stg[lane * 8 + (c4 ^ (lane & 7))] = make_float4(__uint_as_float(v[4 * c4]), __uint_as_float(v[4 * c4 + 1]),
-                                                          __uint_as_float(v[4 * c4 + 2]), __uint_as_float(v[4 * c4 + 3]));
         __syncwarp();
-        const int col = n0 + c0 + 4 * l_c4;
-        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p.bias) {
-          if (col + 3 < p.N) b4 = *reinterpret_cast<const float4*>(p.bias + col);   // bias is 16-byte aligned (flat vector)
-          else { if (col < p.N) b4.x = p.bias[col]; if (col + 1 < p.N) b4.y = p.bias[col + 1]; if (col + 2 < p.N) b4.z = p.bias[col + 2]; }
-        }
-#pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          const int r = it * 4 + l_row;
-          const int grow = m0 + 32 * q + r;
-          float4 o = stg[r * 8 + (l_c4 ^ (r & 7))];
-          if (grow < p.M && col < p.N) {
-            o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
-            if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-            float* dst = Cz + (size_t)grow * p.ldc + col;
-            if (col + 3 < p.N) {
-              o.x = m4[it].x > 0.f ? o.x : 0.f; o.y = m4[it].y > 0.f ? o.y : 0.f;
-              o.z = m4[it].z > 0.f ? o.z : 0.f; o.w = m4[it].w > 0.f ? o.w : 0.f;
-              o.x += a4[it].x; o.y += a4[it].y; o.z += a4[it].z; o.w += a4[it].w;
-              *reinterpret_cast<float4*>(dst) = o;
-            } else {
-              const float oo[4] = {o.x, o.y, o.z, o.w};
-              for (int e = 0; e < 4 && col + e < p.N; ++e) {
-                float x = oo[e];
-                if (p.mask) x = p.mask[(size_t)grow * p.ld_mask + col + e] > 0.f ? x : 0.f;
-                if (p.accumulate) x += dst[e];
-                dst[e] = x;
-              }
-            }
-          }
-        }
+        store_staged<CWB>(p, Cz, stg, lane, m0 + 32 * q, n0 + c0);
         __syncwarp();
-      } else if (row < p.M) {                // unaligned output (ldc % 4 != 0): row-per-lane scalar stores
-        float* dst = Cz + (size_t)row * p.ldc + n0 + c0;
-        const float* mk = p.mask ? p.mask + (size_t)row * p.ld_mask + n0 + c0 : nullptr;
-        for (int j = 0; j < 32; ++j) {
-          const int col = n0 + c0 + j;
-          if (col >= p.N) break;
-          float x = __uint_as_float(v[j]);
-          if (p.bias) x += p.bias[col];
-          if (p.relu) x = fmaxf(x, 0.f);
-          if (mk) x = mk[j] > 0.f ? x : 0.f;
-          if (p.accumulate) x += dst[j];
-          dst[j] = x;
-        }
       }
     }
   }
@@ -623,84 +685,22 @@ gemm_tc_x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
       for (int j = 0; j < 32; ++j) acc[cc * 32 + j] += __uint_as_float(v[j]);
     }
-    // ---- epilogue: 32 x 32 chunks transposed through a 4 KB swizzled buffer per warp, coalesced 128-bit stores
+    // ---- epilogue: this warp's 32 x CPW accumulators -> staging tile -> full-row stores (store_staged)
     float* Cz = p.C + (size_t)blockIdx.z * p.slab_stride;
-    const bool vec = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(Cz) & 15) == 0) &&
-                     (!p.bias || ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0)) &&
-                     (!p.mask || (((p.ld_mask & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.mask) & 15) == 0)));
+    const bool vec = epilogue_vec_ok(p, Cz);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    float4* stg = reinterpret_cast<float4*>(base_ptr + 4096 * (warp - 2));
-    const int l_row = lane >> 3, l_c4 = lane & 7;
+    float4* stg = reinterpret_cast<float4*>(base_ptr + (32 * CPW * 4) * (warp - 2));
     const int row = m0 + 32 * q + lane;
+    const int cw0 = n0 + half * CPW;
+    if (cw0 < p.N) {                           // warp-uniform
+      if (vec) {
 #pragma unroll
-    for (int cc = 0; cc < NCH; ++cc) {
-      const int cbase = n0 + half * CPW + cc * 32;
-      if (cbase < p.N) {                       // warp-uniform
-        if (vec) {
-          const int col = cbase + 4 * l_c4;
-          const bool full4 = col + 3 < p.N;
-          float4 m4[8];
+        for (int sl = 0; sl < CPW / 4; ++sl) stage_put<CPW>(stg, lane, sl, acc[4 * sl], acc[4 * sl + 1], acc[4 * sl + 2], acc[4 * sl + 3]);
+        __syncwarp();
+        store_staged<CPW>(p, Cz, stg, lane, m0 + 32 * q, cw0);
+      } else if (row < p.M) {
 #pragma unroll
-          for (int it = 0; it < 8; ++it) {
-            const int grow = m0 + 32 * q + it * 4 + l_row;
-            m4[it] = make_float4(1.f, 1.f, 1.f, 1.f);
-            if (p.mask && full4 && grow < p.M) m4[it] = *reinterpret_cast<const float4*>(p.mask + (size_t)grow * p.ld_mask + col);
-          }
-#pragma unroll
-          for (int c4 = 0; c4 < 8; ++c4)
-            stg[lane * 8 + (c4 ^ (lane & 7))] = make_float4(acc[cc * 32 + 4 * c4], acc[cc * 32 + 4 * c4 + 1],
-                                                            acc[cc * 32 + 4 * c4 + 2], acc[cc * 32 + 4 * c4 + 3]);
-          __syncwarp();
-          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (p.bias) {
-            if (full4) b4 = *reinterpret_cast<const float4*>(p.bias + col);
-            else { if (col < p.N) b4.x = p.bias[col]; if (col + 1 < p.N) b4.y = p.bias[col + 1]; if (col + 2 < p.N) b4.z = p.bias[col + 2]; }
-          }
-#pragma unroll
-          for (int it = 0; it < 8; ++it) {
-            const int r = it * 4 + l_row;
-            const int grow = m0 + 32 * q + r;
-            float4 o = stg[r * 8 + (l_c4 ^ (r & 7))];
-            if (grow < p.M && col < p.N) {
-              o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
-              if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-              float* dstp = Cz + (size_t)grow * p.ldc + col;
-              if (full4) {
-                o.x = m4[it].x > 0.f ? o.x : 0.f; o.y = m4[it].y > 0.f ? o.y : 0.f;
-                o.z = m4[it].z > 0.f ? o.z : 0.f; o.w = m4[it].w > 0.f ? o.w : 0.f;
-                if (p.accumulate) {
-                  const float4 c4 = *reinterpret_cast<const float4*>(dstp);
-                  o.x += c4.x; o.y += c4.y; o.z += c4.z; o.w += c4.w;
-                }
-                *reinterpret_cast<float4*>(dstp) = o;
-              } else {
-                const float oo[4] = {o.x, o.y, o.z, o.w};
-                for (int e = 0; e < 4 && col + e < p.N; ++e) {
-                  float xv = oo[e];
-                  if (p.mask) xv = p.mask[(size_t)grow * p.ld_mask + col + e] > 0.f ? xv : 0.f;
-                  if (p.accumulate) xv += dstp[e];
-                  dstp[e] = xv;
-                }
-              }
-            }
-          }
-          __syncwarp();
-        } else if (row < p.M) {
-          float* dstp = Cz + (size_t)row * p.ldc + cbase;
-          const float* mk = p.mask ? p.mask + (size_t)row * p.ld_mask + cbase : nullptr;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int col = cbase + j;
-            if (col < p.N) {
-              float xv = acc[cc * 32 + j];
-              if (p.bias) xv += p.bias[col];
-              if (p.relu) xv = fmaxf(xv, 0.f);
-              if (mk) xv = mk[j] > 0.f ? xv : 0.f;
-              if (p.accumulate) xv += dstp[j];
-              dstp[j] = xv;
-            }
-          }
-        }
+        for (int cc = 0; cc < NCH; ++cc) store_row_scalar(p, Cz, row, cw0 + cc * 32, acc + cc * 32);
       }
     }
   }
@@ -820,7 +820,6 @@ gemm_tc_x3_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   auto a_hi = [&](int s) { return base + (uint32_t)s * C::STAGE_BYTES; };
   auto b_hi = [&](int s) { return a_hi(s) + C::A_BYTES; };
   auto a_lo = [&](int s) { return b_hi(s) + C::B_BYTES; };
-  auto b_lo = [&](int s) { return a_lo(s) + C::A_BYTES; };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -832,6 +831,8 @@ gemm_tc_x3_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   const int kb_begin = blockIdx.z * p.kb_per_split;
   const int kb_end = min(kb_total, kb_begin + p.kb_per_split);
   const int num_kb = kb_end - kb_begin;
+  long long* const dbg = (p.dbg && leader && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) ? p.dbg : nullptr;
+  if (dbg && threadIdx.x == 32) dbg[0] = clock64();
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
@@ -855,6 +856,7 @@ gemm_tc_x3_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr) : "memory");
+  if (dbg && threadIdx.x == 32) dbg[1] = clock64();
 
   if (warp == 0) {
     // ---- TMA producer (each CTA loads its own tiles)
@@ -881,48 +883,68 @@ gemm_tc_x3_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       }
     }
   } else if (warp == 1) {
-    // ---- MMA issuer: leader CTA only
-    if (leader && lane == 0) {
+    // ---- MMA issuer: leader CTA only.  The WHOLE warp runs the loop so that the descriptors stay warp-uniform
+    // (uniform registers, no per-MMA R2UR / address arithmetic); one elected lane issues.  Measured: with a single
+    // divergent thread computing descriptors the issue thread, not the tensor pipe, paced the kernel (230 cycles per
+    // 128x256x8 MMA against a floor of 128).
+    if (leader) {
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.a_mn ? 1 : 0) << 15) |
                              ((uint32_t)(p.b_mn ? 1 : 0) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
       const uint32_t a_lbo = p.a_mn ? C::MN_BOX_BYTES : 16u, b_lbo = p.b_mn ? C::MN_BOX_BYTES : 16u;
       const uint32_t a_sbo = p.a_mn ? 512u : C::K_SBO, b_sbo = p.b_mn ? 512u : C::K_SBO;
       const uint32_t a_lay = p.a_mn ? 1u : C::K_LAYOUT, b_lay = p.b_mn ? 1u : C::K_LAYOUT;
-      const uint32_t a_kstep = p.a_mn ? 1024u : 32u, b_kstep = p.b_mn ? 1024u : 32u;
-      uint32_t acc = 0, acc_x = 0;
+      // descriptors of stage 0, k-step 0; everything else is a constant added to the 14-bit start-address field
+      const uint64_t dA0 = smem_desc(a_hi(0), a_lbo, a_sbo, a_lay);
+      const uint64_t dB0 = smem_desc(b_hi(0), b_lbo, b_sbo, b_lay);
+      const uint64_t a_k16 = p.a_mn ? (1024u >> 4) : (32u >> 4), b_k16 = p.b_mn ? (1024u >> 4) : (32u >> 4);
+      constexpr uint64_t LO16 = (C::A_BYTES + C::B_BYTES) >> 4, STAGE16 = C::STAGE_BYTES >> 4;
+      const bool issuer = elect_one();
+      const bool no_drain = (p.pair_flags & 4) != 0;
       const bool pair_wait_cluster = (p.pair_flags & 1) != 0;
-      for (int i = 0; i < num_kb; ++i) {
-        const int s = i % C::STAGES;
-        const uint32_t ph = (uint32_t)(i / C::STAGES) & 1u;
-        const bool new_chunk = (i % X3_CHUNK_KB == 0) && i > 0;
-        if (pair_wait_cluster) mbar_wait_cluster(ready_bar(s), ph); else mbar_wait(ready_bar(s), ph);   // both CTAs: tiles landed, lo halves written
-        tc_fence_after();
+      uint32_t acc = 0, acc_x = 0, ph = 0, chunk_par = 0;
+      int chunk_left = X3_CHUNK_KB;       // k-blocks left in the current drain chunk
+      for (int i = 0; i < num_kb; ph ^= 1u) {
 #pragma unroll
-        for (int ks = 0; ks < BK / UMMA_K; ++ks) {
-          const uint64_t dah = smem_desc(a_hi(s) + ks * a_kstep, a_lbo, a_sbo, a_lay);
-          const uint64_t dbh = smem_desc(b_hi(s) + ks * b_kstep, b_lbo, b_sbo, b_lay);
-          const uint64_t dal = smem_desc(a_lo(s) + ks * a_kstep, a_lbo, a_sbo, a_lay);
-          const uint64_t dbl = smem_desc(b_lo(s) + ks * b_kstep, b_lbo, b_sbo, b_lay);
-          umma_tf32_2cta(tmem_base + BN, dal, dbh, idesc, acc_x);
-          acc_x = 1;
-          umma_tf32_2cta(tmem_base + BN, dah, dbl, idesc, acc_x);
-        }
-        if (new_chunk && !(p.pair_flags & 4)) {
-          if (pair_wait_cluster) mbar_wait_cluster(chunk_empty_bar, (uint32_t)(i / X3_CHUNK_KB - 1) & 1u);
-          else mbar_wait(chunk_empty_bar, (uint32_t)(i / X3_CHUNK_KB - 1) & 1u);
+        for (int s = 0; s < C::STAGES; ++s) {
+          if (i >= num_kb) break;
+          if (pair_wait_cluster) mbar_wait_cluster(ready_bar(s), ph); else mbar_wait(ready_bar(s), ph);   // both CTAs: tiles landed, lo halves written
           tc_fence_after();
-          acc = 0;
-        }
+          if (dbg && i == 0 && lane == 0) dbg[2] = clock64();
+          const uint64_t dah = dA0 + s * STAGE16, dbh = dB0 + s * STAGE16;
+          if (issuer) {
 #pragma unroll
-        for (int ks = 0; ks < BK / UMMA_K; ++ks) {
-          umma_tf32_2cta(tmem_base, smem_desc(a_hi(s) + ks * a_kstep, a_lbo, a_sbo, a_lay),
-                         smem_desc(b_hi(s) + ks * b_kstep, b_lbo, b_sbo, b_lay), idesc, acc);
-          acc = 1;
+            for (int ks = 0; ks < BK / UMMA_K; ++ks) {
+              umma_tf32_2cta(tmem_base + BN, dah + LO16 + ks * a_k16, dbh + ks * b_k16, idesc, acc_x);
+              acc_x = 1;
+              umma_tf32_2cta(tmem_base + BN, dah + ks * a_k16, dbh + LO16 + ks * b_k16, idesc, acc_x);
+            }
+          }
+          if (chunk_left == 0) {          // the workers have copied the previous chunk out of the main accumulator
+            if (!no_drain) {
+              if (pair_wait_cluster) mbar_wait_cluster(chunk_empty_bar, chunk_par); else mbar_wait(chunk_empty_bar, chunk_par);
+              tc_fence_after();
+              acc = 0;
+            }
+            chunk_par ^= 1u;
+            chunk_left = X3_CHUNK_KB;
+          }
+          --chunk_left;
+          ++i;
+          if (issuer) {
+#pragma unroll
+            for (int ks = 0; ks < BK / UMMA_K; ++ks) {
+              umma_tf32_2cta(tmem_base, dah + ks * a_k16, dbh + ks * b_k16, idesc, acc);
+              acc = 1;
+            }
+            umma_commit_2cta(empty_bar(s));
+            if (chunk_left == 0 && i < num_kb) umma_commit_2cta(chunk_full_bar);
+          }
+          __syncwarp();
         }
-        umma_commit_2cta(empty_bar(s));
-        if (((i + 1) % X3_CHUNK_KB == 0) && (i + 1 < num_kb)) umma_commit_2cta(chunk_full_bar);
       }
-      umma_commit_2cta(tmem_full_bar);
+      if (issuer) umma_commit_2cta(tmem_full_bar);
+      __syncwarp();
+      if (dbg && lane == 0) dbg[3] = clock64();
     }
   } else {
     // ---- workers: warps 2..9
@@ -994,6 +1016,7 @@ gemm_tc_x3_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     }
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
+    if (dbg && threadIdx.x == 64) dbg[4] = clock64();
     const float comp_last = X3_TRUNC_LOSS_PER_MMA * (float)((((num_kb - 1) % X3_CHUNK_KB) + 1) * (BK / UMMA_K));
 #pragma unroll
     for (int cc = 0; cc < NCH; ++cc) {
@@ -1005,88 +1028,29 @@ gemm_tc_x3_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
 #pragma unroll
       for (int j = 0; j < 32; ++j) acc[cc * 32 + j] += __uint_as_float(v[j]);
     }
+    // ---- epilogue: this warp's 32 x 128 accumulators -> 16 KB staging tile -> full-row stores (store_staged)
     float* Cz = p.C + (size_t)blockIdx.z * p.slab_stride;
-    const bool vec = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(Cz) & 15) == 0) &&
-                     (!p.bias || ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0)) &&
-                     (!p.mask || (((p.ld_mask & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.mask) & 15) == 0)));
+    const bool vec = epilogue_vec_ok(p, Cz);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    float4* stg = reinterpret_cast<float4*>(base_ptr + 4096 * (warp - 2));
-    const int l_row = lane >> 3, l_c4 = lane & 7;
+    float4* stg = reinterpret_cast<float4*>(base_ptr + (32 * CPW * 4) * (warp - 2));
     const int row = m0 + 32 * q + lane;
+    const int cw0 = n0 + half * CPW;                 // first column of this warp
+    if (cw0 < p.N) {
+      if (vec) {
 #pragma unroll
-    for (int cc = 0; cc < NCH; ++cc) {
-      const int cbase = n0 + half * CPW + cc * 32;
-      if (cbase < p.N) {
-        if (vec) {
-          const int col = cbase + 4 * l_c4;
-          const bool full4 = col + 3 < p.N;
-          float4 m4[8];
+        for (int sl = 0; sl < CPW / 4; ++sl) stage_put<CPW>(stg, lane, sl, acc[4 * sl], acc[4 * sl + 1], acc[4 * sl + 2], acc[4 * sl + 3]);
+        __syncwarp();
+        store_staged<CPW>(p, Cz, stg, lane, m0 + 32 * q, cw0);
+      } else if (row < p.M) {
 #pragma unroll
-          for (int it = 0; it < 8; ++it) {
-            const int grow = m0 + 32 * q + it * 4 + l_row;
-            m4[it] = make_float4(1.f, 1.f, 1.f, 1.f);
-            if (p.mask && full4 && grow < p.M) m4[it] = *reinterpret_cast<const float4*>(p.mask + (size_t)grow * p.ld_mask + col);
-          }
-#pragma unroll
-          for (int c4 = 0; c4 < 8; ++c4)
-            stg[lane * 8 + (c4 ^ (lane & 7))] = make_float4(acc[cc * 32 + 4 * c4], acc[cc * 32 + 4 * c4 + 1],
-                                                            acc[cc * 32 + 4 * c4 + 2], acc[cc * 32 + 4 * c4 + 3]);
-          __syncwarp();
-          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (p.bias) {
-            if (full4) b4 = *reinterpret_cast<const float4*>(p.bias + col);
-            else { if (col < p.N) b4.x = p.bias[col]; if (col + 1 < p.N) b4.y = p.bias[col + 1]; if (col + 2 < p.N) b4.z = p.bias[col + 2]; }
-          }
-#pragma unroll
-          for (int it = 0; it < 8; ++it) {
-            const int r = it * 4 + l_row;
-            const int grow = m0 + 32 * q + r;
-            float4 o = stg[r * 8 + (l_c4 ^ (r & 7))];
-            if (grow < p.M && col < p.N) {
-              o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
-              if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-              float* dstp = Cz + (size_t)grow * p.ldc + col;
-              if (full4) {
-                o.x = m4[it].x > 0.f ? o.x : 0.f; o.y = m4[it].y > 0.f ? o.y : 0.f;
-                o.z = m4[it].z > 0.f ? o.z : 0.f; o.w = m4[it].w > 0.f ? o.w : 0.f;
-                if (p.accumulate) {
-                  const float4 c4 = *reinterpret_cast<const float4*>(dstp);
-                  o.x += c4.x; o.y += c4.y; o.z += c4.z; o.w += c4.w;
-                }
-                *reinterpret_cast<float4*>(dstp) = o;
-              } else {
-                const float oo[4] = {o.x, o.y, o.z, o.w};
-                for (int e = 0; e < 4 && col + e < p.N; ++e) {
-                  float xv = oo[e];
-                  if (p.mask) xv = p.mask[(size_t)grow * p.ld_mask + col + e] > 0.f ? xv : 0.f;
-                  if (p.accumulate) xv += dstp[e];
-                  dstp[e] = xv;
-                }
-              }
-            }
-          }
-          __syncwarp();
-        } else if (row < p.M) {
-          float* dstp = Cz + (size_t)row * p.ldc + cbase;
-          const float* mk = p.mask ? p.mask + (size_t)row * p.ld_mask + cbase : nullptr;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int col = cbase + j;
-            if (col < p.N) {
-              float xv = acc[cc * 32 + j];
-              if (p.bias) xv += p.bias[col];
-              if (p.relu) xv = fmaxf(xv, 0.f);
-              if (mk) xv = mk[j] > 0.f ? xv : 0.f;
-              if (p.accumulate) xv += dstp[j];
-              dstp[j] = xv;
-            }
-          }
-        }
+        for (int cc = 0; cc < NCH; ++cc) store_row_scalar(p, Cz, row, cw0 + cc * 32, acc + cc * 32);
       }
     }
   }
+  if (dbg && threadIdx.x == 64) dbg[5] = clock64();
   tc_fence_before();
   cluster_sync_all();
+  if (dbg && threadIdx.x == 32) dbg[6] = clock64();
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS) : "memory");
@@ -1383,7 +1347,7 @@ static int gemm_bf16(cudaStream_t st, const addk_gemm_args& a) {
   p.C = a.C; p.ldc = a.ldc; p.M = a.M; p.N = a.N; p.K = a.K; p.bias = a.bias; p.mask = a.relu_mask_src;
   p.ld_mask = a.ld_mask; p.relu = a.relu; p.accumulate = 0; p.kb_per_split = kb_per;
   p.slab_stride = a.slab_stride > 0 ? a.slab_stride : (long long)a.M * a.ldc;
-  p.pair_flags = 0; p.C16 = a.C16;
+  p.pair_flags = 0; p.dbg = nullptr; p.C16 = a.C16;
   p.a_mn = a.trans_a ? 1 : 0;
   p.b_mn = a.trans_b ? 0 : 1;
   const int BN = a.N > 128 ? 256 : (a.N > 64 ? 128 : 64);
@@ -1438,6 +1402,7 @@ int addk_gemm_tc(cudaStream_t st, const addk_gemm_args& a, int precision) {
   p.ld_mask = a.ld_mask; p.relu = a.relu; p.accumulate = a.accumulate; p.kb_per_split = kb_per;
   p.slab_stride = a.slab_stride > 0 ? a.slab_stride : (long long)a.M * a.ldc;
   { const char* e = getenv("ADDK_TC_PAIR_FLAGS"); p.pair_flags = e ? atoi(e) : 2; }
+  { const char* e = getenv("ADDK_TC_DBG"); p.dbg = e ? (long long*)strtoull(e, nullptr, 0) : nullptr; }
   p.C16 = nullptr;
   p.a_mn = a.trans_a ? 1 : 0;          // A given as [K,M]: rows are the contraction index
   p.b_mn = a.trans_b ? 0 : 1;          // B given as [K,N]

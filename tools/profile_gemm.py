@@ -40,3 +40,13 @@ for i, (a, b) in enumerate(ev):
 torch.cuda.synchronize()
 ms = sorted(a.elapsed_time(b) for a, b in ev)[len(ev) // 2]
 print("%s %s M=%d: %.1f us  %.1f TFLOP/s" % (prec, layout, M, ms * 1e3, 2.0 * M * N * K / ms / 1e9))
+if os.environ.get("ADDK_TC_STAMPS"):
+    # phase stamps (clock64) of CTA (0,0,0) of the CTA-pair kernel: see gemm_tc.cu (Params::dbg)
+    dbg = torch.zeros(16, dtype=torch.int64, device=dev)
+    os.environ["ADDK_TC_DBG"] = str(dbg.data_ptr())
+    launch(0)
+    torch.cuda.synchronize()
+    del os.environ["ADDK_TC_DBG"]
+    t = dbg.tolist()
+    names = ["entry", "setup done", "first stage ready", "all MMAs issued", "accumulator complete", "epilogue done", "cluster exit"]
+    print("stamps (cycles since entry): " + ", ".join("%s %d" % (n, t[i] - t[0]) for i, n in enumerate(names)))
