@@ -18,7 +18,7 @@ ADDK_MAX_TAR_STEPS = 16
 ADDK_MAX_DISC_STEPS = 8
 
 F_ADVANCE, F_UPDATE_MOTION, F_REWARD_DONE, F_MASKED = 1, 2, 4, 8
-PRECISIONS = {"fp32": 0, "tf32x3": 1, "tf32": 2, "bf16": 3}
+PRECISIONS = {"fp32": 0, "tf32x3": 1, "tf32": 2, "bf16": 3, "f16x3": 4}
 
 
 class AddkTask(C.Structure):
@@ -70,7 +70,9 @@ class AddkGemmArgs(C.Structure):
                 ("a_mean", C.c_void_p), ("a_std", C.c_void_p), ("relu_mask_src", C.c_void_p), ("ld_mask", C.c_int32),
                 ("trans_a", C.c_int32), ("trans_b", C.c_int32), ("relu", C.c_int32), ("split_k", C.c_int32),
                 ("accumulate", C.c_int32), ("slab_stride", C.c_int64),
-                ("A16", C.c_void_p), ("B16", C.c_void_p), ("C16", C.c_void_p)]
+                ("A16", C.c_void_p), ("B16", C.c_void_p), ("C16", C.c_void_p),
+                ("a16_plane", C.c_int64), ("b16_plane", C.c_int64), ("a_amax", C.c_void_p), ("b_amax", C.c_void_p),
+                ("a16_ready", C.c_int32), ("b16_ready", C.c_int32)]
 
 
 class AddkError(RuntimeError):

@@ -246,14 +246,16 @@ class ADDAgent(torch.nn.Module):
             total += (int(np.prod(shp)) + 7) & ~7
         self._arena = z(total)
         bf16 = m.precision == _lib.PRECISIONS["bf16"]
-        self._arena16 = torch.zeros(total if bf16 else 8, device=dev, dtype=torch.bfloat16)
-        self._params16 = torch.zeros(m.num_params if bf16 else 8, device=dev, dtype=torch.bfloat16)
+        h3 = m.precision == _lib.PRECISIONS["f16x3"]      # two fp16 planes (hi, lo) per twin + one max|x| word per tensor
+        self._arena16 = torch.zeros(2 * total if h3 else (total if bf16 else 8), device=dev, dtype=torch.bfloat16)
+        self._params16 = torch.zeros(2 * m.num_params if h3 else (m.num_params if bf16 else 8), device=dev, dtype=torch.bfloat16)
+        self._amax_slots = torch.zeros(64, device=dev, dtype=torch.int32) if h3 else None
         carve = {k: self._arena[offs[k]:offs[k] + int(np.prod(shp))].view(shp) for k, shp in shapes.items()}
         self._ws = dict(
             carve, old_logp=z(R), adv=z(R), tar=z(R), mask=z(R), pred=z(R), dpred=z(R), ones=torch.ones(R, device=dev),
             stats=z(32, dt=torch.float64), info=z(self._max_steps, 16), cnt=z(1, dt=torch.int32),
             slabs=z(2 * S, m.num_params), colsum_work=z(64 * 1024 + 64), arena=self._arena, arena16=self._arena16,
-            params16=self._params16)
+            params16=self._params16, amax_slots=self._amax_slots)
         if n_streams == 3:
             self._ws.update(d_pred=z(R), d_dpred=z(R), colsum_work_c=z(64 * 1024 + 64), colsum_work_d=z(64 * 1024 + 64))
         else:

@@ -69,6 +69,9 @@ ADDK_PTR(wd0_pad)       // [hid_d1, disc_ld] discriminator first-layer weight wi
 ADDK_PTR(arena)         // fp32 arena base (may be NULL when precision != bf16)
 ADDK_PTR(arena16)       // bf16 arena, same element offsets
 ADDK_PTR(params16)      // [P] bf16
+// ---- precision "f16x3": arena16 / params16 hold TWO fp16 planes each (hi, then lo arena_elems / num_params elements
+//      later) and amax_slots the max|x| words of the twins (slot 0 = the parameter vector); see csrc/gemm_tc.cu
+ADDK_PTR(amax_slots)    // [64] uint32 (NULL unless precision == f16x3)
 // ---- second and third workspace sets: the critic and the discriminator chains of one optimizer step run on their
 //      own streams next to the actor's (n_streams == 3), so the tail wave of one chain's dense layer overlaps the
 //      next chain's tiles; all NULL / n_streams == 1 = the three chains run back to back on the caller's stream
@@ -92,7 +95,7 @@ ADDK_INT(mb_rows)       // minibatch rows M
 ADDK_INT(num_params)    // P (including alignment padding)
 ADDK_INT(split_k)
 ADDK_INT(arena_elems)   // elements in the arena
-ADDK_INT(precision)     // 0 fp32 | 1 tf32x3 | 2 tf32 | 3 bf16
+ADDK_INT(precision)     // 0 fp32 | 1 tf32x3 | 2 tf32 | 3 bf16 | 4 f16x3
 ADDK_INT(n_streams)     // 1 | 3
 ADDK_INT(hid_a1)        // actor/critic hidden sizes (1024, 1024, 512)
 ADDK_INT(hid_a2)

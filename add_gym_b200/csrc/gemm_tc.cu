@@ -23,6 +23,7 @@
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #include <stdlib.h>
+#include <cuda_fp16.h>
 
 namespace addk { int sgemm_launch(cudaStream_t st, const addk_gemm_args& a); }
 
@@ -236,13 +237,13 @@ __device__ __forceinline__ bool epilogue_vec_ok(const Params& p, const float* Cz
 
 // One stage of the ring.  A: 128 (rows | columns) x BK k;  B: BN x BK k.  tf32x3 adds the "lo" halves and uses
 // BK = 16 (64-byte rows) so that four stages still fit; the single-pass mode uses BK = 32 (128-byte rows).
-template <int BN, bool X3>
+template <int BN, bool X3, int CAP_KB = 200>
 struct Cfg {
   static constexpr int BK = X3 ? 16 : 32;
   static constexpr int A_BYTES = BM * BK * 4;
   static constexpr int B_BYTES = BN * BK * 4;
   static constexpr int STAGE_BYTES = (A_BYTES + B_BYTES) * (X3 ? 2 : 1);
-  static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 6 ? 6 : (200 * 1024) / STAGE_BYTES;
+  static constexpr int STAGES = (CAP_KB * 1024) / STAGE_BYTES > 6 ? 6 : (CAP_KB * 1024) / STAGE_BYTES;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
   // tf32x3 keeps the small cross terms (lo.hi + hi.lo) in a second accumulator: the tensor core truncates its
   // fp32 accumulator after every instruction, so three accumulations per k-step into ONE accumulator would
@@ -504,10 +505,10 @@ constexpr int X3_CHUNK_KB = 16;
 // 32-instruction chunk) and leaves the random part (~3e-7).
 constexpr float X3_TRUNC_LOSS_PER_MMA = 1.7e-8f;
 
-template <int BN>
-__global__ void __launch_bounds__(X3_THREADS, 1)
+template <int BN, int CAP_KB = 200, int MINB = 1>
+__global__ void __launch_bounds__(X3_THREADS, MINB)
 gemm_tc_x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
-  using C = Cfg<BN, true>;
+  using C = Cfg<BN, true, CAP_KB>;
   constexpr int BK = C::BK;
   constexpr int CPW = BN / 2;                     // accumulator columns per worker thread
   constexpr int NCH = CPW / 32;                   // 32-column chunks per worker
@@ -712,18 +713,18 @@ gemm_tc_x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   }
 }
 
-template <int BN>
+template <int BN, int CAP_KB = 200, int MINB = 1>
 static int launch_x3(cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, dim3 grid) {
-  using C = Cfg<BN, true>;
+  using C = Cfg<BN, true, CAP_KB>;
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(gemm_tc_x3_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES) != cudaSuccess) {
+    if (cudaFuncSetAttribute(gemm_tc_x3_kernel<BN, CAP_KB, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES) != cudaSuccess) {
       addk_set_error("gemm_tc: cannot raise the dynamic shared memory limit");
       return ADDK_ERR_LAUNCH;
     }
     configured = true;
   }
-  gemm_tc_x3_kernel<BN><<<grid, X3_THREADS, C::SMEM_BYTES, st>>>(ta, tb, p);
+  gemm_tc_x3_kernel<BN, CAP_KB, MINB><<<grid, X3_THREADS, C::SMEM_BYTES, st>>>(ta, tb, p);
   return ADDK_OK;
 }
 
@@ -1303,6 +1304,379 @@ static int launch_bf16(cudaStream_t st, const CUtensorMap& ta, const CUtensorMap
   return ADDK_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// f16x3 kernel (precision "f16x3"): the fp32-parity mode on the fp16 tensor pipe.
+//
+// Why: in tf32x3 the tensor core reads 4-byte operands -- per 16 k of a 128x256 tile the six kind::tf32 MMAs read
+// 72 KB of shared memory and the hi/lo split moves another 48 KB, 120 KB against the SM's 128 B/clk: the main loop is
+// shared-memory-bandwidth bound at ~200 cycles per MMA (nominal 134).  Here every operand is split ONCE, outside the
+// GEMM, into two fp16 planes
+//     hi = fp16_rn(x * s),   lo = fp16_rn((x * s - hi) * 2^11),   s = 2^(14 - floor(log2(max|x|)))
+// (22+ mantissa bits, i.e. the whole fp32 value; s keeps every significant element inside fp16's normal range; the
+// residual is exact in fp32 before its rounding), and the GEMM is pure TMA -> tcgen05.mma.kind::f16 (M=128, N=BN,
+// K=16, twice the tf32 rate, half the shared-memory bytes per k):
+//     main  += hi_a . hi_b            (TMEM columns [0, BN))
+//     cross += lo_a . hi_b + hi_a . lo_b   (TMEM columns [BN, 2 BN), scaled by 2^11)
+//     C = (main + cross * 2^-11) / (s_a * s_b)            lo.lo (2^-24 relative) is dropped
+// The main accumulator is drained into fp32 registers every H3_CHUNK_KB k-blocks like in the tf32x3 kernel (the
+// tensor core truncates its accumulator after every instruction).  10 warps: 0 = TMA producer, 1 = MMA issuer (whole
+// warp runs the loop, one elected lane issues), 2..9 = chunk drains + epilogue.
+// ---------------------------------------------------------------------------------------------------------------
+template <int BN>
+struct CfgH3 {
+  static constexpr int BK = 32;                                // fp16 elements per k-block: 64-byte rows
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = 2 * (A_BYTES + B_BYTES);  // [A_hi | B_hi | A_lo | B_lo]
+  static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 6 ? 6 : (200 * 1024) / STAGE_BYTES;
+  static constexpr int EPI_BYTES = 8 * 32 * (BN / 2) * 4;      // epilogue staging: 8 warps x 32 rows x BN/2 floats
+  static constexpr int RING_BYTES = STAGES * STAGE_BYTES > EPI_BYTES ? STAGES * STAGE_BYTES : EPI_BYTES;
+  static constexpr int SMEM_BYTES = RING_BYTES + 1024 + 256;
+  static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+  static constexpr uint32_t K_SBO = 8u * BK * 2u;              // K-major: 8-row groups 512 B apart, SWIZZLE_64B
+  static constexpr uint32_t MN_BOX_BYTES = BK * 128u;          // MN-major: one TMA box = 64 MN (128 B) x BK k
+};
+constexpr int H3_CHUNK_KB = 8;                                 // drain every 256 k = 16 main-accumulator instructions
+
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+}
+
+// the power-of-two scale of a tensor whose max|x| has the bit pattern `amax_bits`: s = 2^(14 - e), returns s and 1/s
+__device__ __forceinline__ void h3_scale(uint32_t amax_bits, float& s, float& inv_s) {
+  int E = (int)((amax_bits >> 23) & 0xFFu);
+  E = E < 16 ? 16 : (E > 250 ? 250 : E);                       // zero / denormal / huge: any finite scale will do
+  s = __uint_as_float((uint32_t)(268 - E) << 23);              // 2^(14 - (E - 127))
+  inv_s = __uint_as_float((uint32_t)(E - 14) << 23);
+}
+
+struct ParamsH3 {
+  Params p;
+  const uint32_t* a_amax; const uint32_t* b_amax;
+  float comp_per_mma;          // expected truncation loss of the accumulator per accumulated instruction
+};
+
+template <int BN>
+__global__ void __launch_bounds__(X3_THREADS, 1)
+gemm_tc_h3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
+                  const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl, const ParamsH3 ph) {
+  using C = CfgH3<BN>;
+  const Params& p = ph.p;
+  constexpr int BK = C::BK, UK = 16;
+  constexpr int CPW = BN / 2, NCH = CPW / 32;
+  static_assert(CPW % 32 == 0, "BN must be a multiple of 64");
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_u32 = smem_u32(smem_raw);
+  const uint32_t base = (raw_u32 + 1023u) & ~1023u;
+  uint8_t* const base_ptr = smem_raw + (base - raw_u32);
+  const uint32_t bars = base + C::RING_BYTES;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (C::STAGES + s); };
+  const uint32_t tmem_full_bar = bars + 8u * (2 * C::STAGES);
+  const uint32_t chunk_full_bar = bars + 8u * (2 * C::STAGES + 1);
+  const uint32_t chunk_empty_bar = bars + 8u * (2 * C::STAGES + 2);
+  const uint32_t tmem_ptr_addr = bars + 8u * (2 * C::STAGES + 3);
+  auto a_hi = [&](int s) { return base + (uint32_t)s * C::STAGE_BYTES; };
+  auto b_hi = [&](int s) { return a_hi(s) + C::A_BYTES; };
+  auto a_lo = [&](int s) { return b_hi(s) + C::B_BYTES; };
+  auto b_lo = [&](int s) { return a_lo(s) + C::A_BYTES; };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int kb_total = (p.K + BK - 1) / BK;
+  const int kb_begin = blockIdx.z * p.kb_per_split;
+  const int kb_end = min(kb_total, kb_begin + p.kb_per_split);
+  const int num_kb = kb_end - kb_begin;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmAh); tma_prefetch_desc(&tmAl); tma_prefetch_desc(&tmBh); tma_prefetch_desc(&tmBl);
+    for (int s = 0; s < C::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    mbar_init(tmem_full_bar, 1);
+    mbar_init(chunk_full_bar, 1);
+    mbar_init(chunk_empty_bar, 8);                // one arrival per worker warp
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "r"((uint32_t)C::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr) : "memory");
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      for (int i = 0; i < num_kb; ++i) {
+        const int s = i % C::STAGES;
+        const uint32_t phs = (uint32_t)(i / C::STAGES) & 1u;
+        mbar_wait(empty_bar(s), phs ^ 1u);
+        mbar_expect_tx(full_bar(s), C::STAGE_BYTES);
+        const int k0 = (kb_begin + i) * BK;
+        if (!p.a_mn) {
+          tma_load_2d(a_hi(s), &tmAh, full_bar(s), k0, m0);                      // box {32 k, 128 rows}
+          tma_load_2d(a_lo(s), &tmAl, full_bar(s), k0, m0);
+        } else {
+#pragma unroll
+          for (int j = 0; j < BM / 64; ++j) {                                    // box {64 m, 32 k}
+            tma_load_2d(a_hi(s) + j * C::MN_BOX_BYTES, &tmAh, full_bar(s), m0 + 64 * j, k0);
+            tma_load_2d(a_lo(s) + j * C::MN_BOX_BYTES, &tmAl, full_bar(s), m0 + 64 * j, k0);
+          }
+        }
+        if (!p.b_mn) {
+          tma_load_2d(b_hi(s), &tmBh, full_bar(s), k0, n0);
+          tma_load_2d(b_lo(s), &tmBl, full_bar(s), k0, n0);
+        } else {
+#pragma unroll
+          for (int j = 0; j < BN / 64; ++j) {
+            tma_load_2d(b_hi(s) + j * C::MN_BOX_BYTES, &tmBh, full_bar(s), n0 + 64 * j, k0);
+            tma_load_2d(b_lo(s) + j * C::MN_BOX_BYTES, &tmBl, full_bar(s), n0 + 64 * j, k0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
+    // instruction descriptor: D fp32, A/B fp16 (format 0), majors, N>>3, M>>4
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(p.a_mn ? 1 : 0) << 15) | ((uint32_t)(p.b_mn ? 1 : 0) << 16) |
+                           ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    // K-major: 64-byte rows, SWIZZLE_64B (layout 4), 8-row groups 512 B apart, 16 k = 32 B.
+    // MN-major: SWIZZLE_128B (layout 2), 64-MN atoms one box apart (LBO), 8-k groups 1024 B apart (SBO), 16 k = 2048 B.
+    const uint32_t a_lbo = p.a_mn ? C::MN_BOX_BYTES : 16u, b_lbo = p.b_mn ? C::MN_BOX_BYTES : 16u;
+    const uint32_t a_sbo = p.a_mn ? 1024u : C::K_SBO, b_sbo = p.b_mn ? 1024u : C::K_SBO;
+    const uint32_t a_lay = p.a_mn ? 2u : 4u, b_lay = p.b_mn ? 2u : 4u;
+    const uint64_t dA0 = smem_desc(a_hi(0), a_lbo, a_sbo, a_lay);
+    const uint64_t dB0 = smem_desc(b_hi(0), b_lbo, b_sbo, b_lay);
+    const uint64_t a_k16 = p.a_mn ? (2048u >> 4) : (32u >> 4), b_k16 = p.b_mn ? (2048u >> 4) : (32u >> 4);
+    constexpr uint64_t LO16 = (C::A_BYTES + C::B_BYTES) >> 4, STAGE16 = C::STAGE_BYTES >> 4;
+    const bool issuer = elect_one();
+    uint32_t acc = 0, acc_x = 0, phs = 0, chunk_par = 0;
+    int chunk_left = H3_CHUNK_KB;
+    for (int i = 0; i < num_kb; phs ^= 1u) {
+#pragma unroll
+      for (int s = 0; s < C::STAGES; ++s) {
+        if (i >= num_kb) break;
+        mbar_wait(full_bar(s), phs);
+        tc_fence_after();
+        const uint64_t dah = dA0 + s * STAGE16, dbh = dB0 + s * STAGE16;
+        if (issuer) {
+#pragma unroll
+          for (int ks = 0; ks < BK / UK; ++ks) {     // cross terms first: they overlap the drain at a chunk boundary
+            umma_f16(tmem_base + BN, dah + LO16 + ks * a_k16, dbh + ks * b_k16, idesc, acc_x);
+            acc_x = 1;
+            umma_f16(tmem_base + BN, dah + ks * a_k16, dbh + LO16 + ks * b_k16, idesc, acc_x);
+          }
+        }
+        if (chunk_left == 0) {                       // the workers have copied the previous chunk out of the main accumulator
+          mbar_wait(chunk_empty_bar, chunk_par);
+          tc_fence_after();
+          acc = 0;
+          chunk_par ^= 1u;
+          chunk_left = H3_CHUNK_KB;
+        }
+        --chunk_left;
+        ++i;
+        if (issuer) {
+#pragma unroll
+          for (int ks = 0; ks < BK / UK; ++ks) {
+            umma_f16(tmem_base, dah + ks * a_k16, dbh + ks * b_k16, idesc, acc);
+            acc = 1;
+          }
+          umma_commit(empty_bar(s));
+          if (chunk_left == 0 && i < num_kb) umma_commit(chunk_full_bar);
+        }
+        __syncwarp();
+      }
+    }
+    if (issuer) umma_commit(tmem_full_bar);
+    __syncwarp();
+  } else {
+    // ===================== workers: warps 2..9 =====================
+    const int q = warp & 3;                  // TMEM lane quarter
+    const int half = (warp - 2) >> 2;        // column half
+    const uint32_t t_main = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(half * CPW);
+    float acc[CPW];
+#pragma unroll
+    for (int j = 0; j < CPW; ++j) acc[j] = 0.f;
+    const int n_mid = (num_kb - 1) / H3_CHUNK_KB;           // chunks that end before the last k-block
+    const float comp = ph.comp_per_mma * (float)(H3_CHUNK_KB * (BK / UK));
+    for (int c = 0; c < n_mid; ++c) {
+      mbar_wait(chunk_full_bar, (uint32_t)c & 1u);
+      tc_fence_after();
+#pragma unroll
+      for (int cc = 0; cc < NCH; ++cc) {
+        uint32_t v[32];
+        tmem_ld32(t_main + (uint32_t)(cc * 32), v);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[cc * 32 + j] += fmaf(__uint_as_float(v[j]), comp, __uint_as_float(v[j]));
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(chunk_empty_bar);
+    }
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    float sa, sb, ia, ib;
+    h3_scale(ph.a_amax ? *ph.a_amax : 0x3F800000u, sa, ia);
+    h3_scale(ph.b_amax ? *ph.b_amax : 0x3F800000u, sb, ib);
+    const float inv = ia * ib;
+    const float comp_last = ph.comp_per_mma * (float)((num_kb - n_mid * H3_CHUNK_KB) * (BK / UK));
+#pragma unroll
+    for (int cc = 0; cc < NCH; ++cc) {         // last chunk of the main accumulator + the cross-term accumulator
+      uint32_t v[32];
+      tmem_ld32(t_main + (uint32_t)(cc * 32), v);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) acc[cc * 32 + j] += fmaf(__uint_as_float(v[j]), comp_last, __uint_as_float(v[j]));
+      tmem_ld32(t_main + (uint32_t)(BN + cc * 32), v);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) acc[cc * 32 + j] = fmaf(__uint_as_float(v[j]), 4.8828125e-4f, acc[cc * 32 + j]) * inv;
+    }
+    // ---- epilogue: this warp's 32 x CPW accumulators -> staging tile -> full-row stores (store_staged)
+    float* Cz = p.C + (size_t)blockIdx.z * p.slab_stride;
+    const bool vec = epilogue_vec_ok(p, Cz);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    float4* stg = reinterpret_cast<float4*>(base_ptr + (32 * CPW * 4) * (warp - 2));
+    const int row = m0 + 32 * q + lane;
+    const int cw0 = n0 + half * CPW;
+    if (cw0 < p.N) {                           // warp-uniform
+      if (vec) {
+#pragma unroll
+        for (int sl = 0; sl < CPW / 4; ++sl) stage_put<CPW>(stg, lane, sl, acc[4 * sl], acc[4 * sl + 1], acc[4 * sl + 2], acc[4 * sl + 3]);
+        __syncwarp();
+        store_staged<CPW>(p, Cz, stg, lane, m0 + 32 * q, cw0);
+      } else if (row < p.M) {
+#pragma unroll
+        for (int cc = 0; cc < NCH; ++cc) store_row_scalar(p, Cz, row, cw0 + cc * 32, acc + cc * 32);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS) : "memory");
+  }
+}
+
+// 2-D fp16 tensor map: memory [outer, inner] with `ld` elements between rows; K-major: box {32 k, box_rows}, 64-byte
+// swizzle; MN-major: box {64 mn, 32 k}, 128-byte swizzle.
+static bool make_map_f16(CUtensorMap* map, const void* ptr, long long inner, long long outer, long long ld, int box_inner,
+                         int box_rows) {
+  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, box_inner == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+template <int BN>
+static int launch_h3(cudaStream_t st, const CUtensorMap& tah, const CUtensorMap& tal, const CUtensorMap& tbh,
+                     const CUtensorMap& tbl, const ParamsH3& p, dim3 grid) {
+  using C = CfgH3<BN>;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(gemm_tc_h3_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES) != cudaSuccess) {
+      addk_set_error("gemm_tc: cannot raise the dynamic shared memory limit");
+      return ADDK_ERR_LAUNCH;
+    }
+    configured = true;
+  }
+  gemm_tc_h3_kernel<BN><<<grid, X3_THREADS, C::SMEM_BYTES, st>>>(tah, tal, tbh, tbl, p);
+  return ADDK_OK;
+}
+
+// ---- the split pre-pass: max|x| of a [rows, cols] fp32 tensor (pitch ld), then the two fp16 planes ----------------
+__global__ void h3_amax_kernel(const float* __restrict__ x, long long rows, int cols, int ld, uint32_t* __restrict__ slot) {
+  uint32_t m = 0;
+  const bool flat = ld == cols;
+  const bool vec = ((cols & 3) == 0) && ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+  if (vec) {
+    const int c4 = cols >> 2;
+    if (flat) {
+      const long long n4 = rows * c4;
+      for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const float4 v = reinterpret_cast<const float4*>(x)[i];
+        m = max(max(m, __float_as_uint(fabsf(v.x))), max(__float_as_uint(fabsf(v.y)), max(__float_as_uint(fabsf(v.z)), __float_as_uint(fabsf(v.w)))));
+      }
+    } else {
+      for (long long r = blockIdx.x; r < rows; r += gridDim.x)
+        for (int c = threadIdx.x; c < c4; c += blockDim.x) {
+          const float4 v = *reinterpret_cast<const float4*>(x + r * ld + 4 * c);
+          m = max(max(m, __float_as_uint(fabsf(v.x))), max(__float_as_uint(fabsf(v.y)), max(__float_as_uint(fabsf(v.z)), __float_as_uint(fabsf(v.w)))));
+        }
+    }
+  } else {
+    for (long long r = blockIdx.x; r < rows; r += gridDim.x)
+      for (int c = threadIdx.x; c < cols; c += blockDim.x) m = max(m, __float_as_uint(fabsf(x[r * ld + c])));
+  }
+  m = __reduce_max_sync(0xffffffffu, m);
+  __shared__ uint32_t sm[32];
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    m = threadIdx.x < (blockDim.x >> 5) ? sm[threadIdx.x] : 0u;
+    m = __reduce_max_sync(0xffffffffu, m);
+    if (threadIdx.x == 0 && m) atomicMax(slot, m);
+  }
+}
+
+__device__ __forceinline__ void h3_split1(float x, float s, uint16_t& hi, uint16_t& lo) {
+  const float xs = x * s;                                   // exact (power of two)
+  const __half h = __float2half_rn(xs);
+  const float r = (xs - __half2float(h)) * 2048.0f;         // exact difference, exact scaling
+  hi = __half_as_ushort(h);
+  lo = __half_as_ushort(__float2half_rn(r));
+}
+
+__global__ void h3_split_kernel(const float* __restrict__ x, long long rows, int cols, int ld, const uint32_t* __restrict__ slot,
+                                uint16_t* __restrict__ hi, uint16_t* __restrict__ lo) {
+  float s, inv;
+  h3_scale(*slot, s, inv);
+  const bool flat = ld == cols;
+  const bool vec = ((cols & 3) == 0) && ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(hi) & 7) == 0) && ((reinterpret_cast<uintptr_t>(lo) & 7) == 0);
+  if (vec) {
+    const int c4 = cols >> 2;
+    const long long nrow = flat ? 1 : rows;
+    const long long per = flat ? rows * c4 : c4;
+    for (long long r = flat ? 0 : blockIdx.x; r < nrow; r += gridDim.x) {
+      const long long start = flat ? (long long)blockIdx.x * blockDim.x + threadIdx.x : threadIdx.x;
+      const long long step = flat ? (long long)gridDim.x * blockDim.x : blockDim.x;
+      for (long long c = start; c < per; c += step) {
+        const long long off = r * ld + 4 * c;
+        const float4 v = *reinterpret_cast<const float4*>(x + off);
+        uint16_t h[4], l[4];
+        h3_split1(v.x, s, h[0], l[0]); h3_split1(v.y, s, h[1], l[1]); h3_split1(v.z, s, h[2], l[2]); h3_split1(v.w, s, h[3], l[3]);
+        *reinterpret_cast<uint2*>(hi + off) = make_uint2((uint32_t)h[0] | ((uint32_t)h[1] << 16), (uint32_t)h[2] | ((uint32_t)h[3] << 16));
+        *reinterpret_cast<uint2*>(lo + off) = make_uint2((uint32_t)l[0] | ((uint32_t)l[1] << 16), (uint32_t)l[2] | ((uint32_t)l[3] << 16));
+      }
+    }
+  } else {
+    for (long long r = blockIdx.x; r < rows; r += gridDim.x)
+      for (int c = threadIdx.x; c < cols; c += blockDim.x) h3_split1(x[r * ld + c], s, hi[r * ld + c], lo[r * ld + c]);
+  }
+}
+
+static int h3_convert(cudaStream_t st, const float* x, long long rows, int cols, int ld, void* hi, long long plane, uint32_t* slot) {
+  if (!x || !hi || !slot || rows <= 0 || cols <= 0 || ld < cols || plane <= 0) { addk_set_error("f16x3 convert: bad arguments"); return ADDK_ERR_ARG; }
+  if (cudaMemsetAsync(slot, 0, sizeof(uint32_t), st) != cudaSuccess) { addk_set_error("f16x3 convert: memset failed"); return ADDK_ERR_LAUNCH; }
+  const long long work = ld == cols ? (rows * cols / 4 + 255) / 256 : rows;
+  const unsigned blocks = (unsigned)(work < 1 ? 1 : (work > 148 * 8 ? 148 * 8 : work));
+  h3_amax_kernel<<<blocks, 256, 0, st>>>(x, rows, cols, ld, slot);
+  h3_split_kernel<<<blocks, 256, 0, st>>>(x, rows, cols, ld, slot, reinterpret_cast<uint16_t*>(hi), reinterpret_cast<uint16_t*>(hi) + plane);
+  return ADDK_OK;
+}
+
 template <int BN, bool X3>
 static int launch(cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, dim3 grid) {
   using C = Cfg<BN, X3>;
@@ -1361,7 +1735,77 @@ static int gemm_bf16(cudaStream_t st, const addk_gemm_args& a) {
   return launch_bf16<64>(st, ta, tb, p, grid);
 }
 
+extern "C" int addk_f16x3_convert(void* stream, const float* x, long long rows, int cols, int ld, void* hi16, long long plane,
+                                  uint32_t* amax_slot) {
+  const int rc = addk_tc::h3_convert((cudaStream_t)stream, x, rows, cols, ld, hi16, plane, amax_slot);
+  if (rc != ADDK_OK) return rc;
+  ADDK_CHECK_LAUNCH();
+  return ADDK_OK;
+}
+
+static float addk_h3_comp() {
+  static float v = -1.f;
+  if (v < 0.f) { const char* e = getenv("ADDK_H3_COMP"); v = e ? (float)atof(e) : addk_tc::X3_TRUNC_LOSS_PER_MMA; }
+  return v;
+}
+
+// precision "f16x3": can this shape run on the fp16 planes (given 16-byte aligned twins)?  Shared with csrc/mlp.cu, whose
+// twin bookkeeping must know whether a call is going to convert its operands.
+bool addk_gemm_h3_usable(const addk_gemm_args& a) {
+  const int split = a.split_k > 1 ? a.split_k : 1;
+  const int kb_total = (a.K + 31) / 32;
+  const int kb_per = (kb_total + split - 1) / split;
+  return ((a.lda & 7) == 0) && ((a.ldb & 7) == 0) && !a.a_mean && a.M >= 16 && a.N >= 16 && a.K >= 16 &&
+         (split == 1 || !(a.bias || a.relu || a.relu_mask_src || a.accumulate)) &&
+         (long long)kb_per * (split - 1) < kb_total && addk_tc::resolve_encode();
+}
+
+static int gemm_h3(cudaStream_t st, const addk_gemm_args& a) {
+  using namespace addk_tc;
+  const int BKh = 32;
+  int split = a.split_k > 1 ? a.split_k : 1;
+  const int kb_total = (a.K + BKh - 1) / BKh;
+  const int kb_per = (kb_total + split - 1) / split;
+  // operand geometry as stored: A is [M,K] (trans_a = 0) or [K,M]; B is [N,K] (trans_b = 1) or [K,N]
+  const long long a_rows = a.trans_a ? a.K : a.M, b_rows = a.trans_b ? a.N : a.K;
+  const int a_cols = a.trans_a ? a.M : a.K, b_cols = a.trans_b ? a.K : a.N;
+  if (!a.a16_ready) { const int rc = h3_convert(st, a.A, a_rows, a_cols, a.lda, const_cast<void*>(a.A16), a.a16_plane, a.a_amax); if (rc != ADDK_OK) return rc; }
+  if (!a.b16_ready) { const int rc = h3_convert(st, a.B, b_rows, b_cols, a.ldb, const_cast<void*>(a.B16), a.b16_plane, a.b_amax); if (rc != ADDK_OK) return rc; }
+  ParamsH3 ph;
+  Params& p = ph.p;
+  p.C = a.C; p.ldc = a.ldc; p.M = a.M; p.N = a.N; p.K = a.K; p.bias = a.bias; p.mask = a.relu_mask_src;
+  p.ld_mask = a.ld_mask; p.relu = a.relu; p.accumulate = a.accumulate; p.kb_per_split = kb_per;
+  p.slab_stride = a.slab_stride > 0 ? a.slab_stride : (long long)a.M * a.ldc;
+  p.pair_flags = 0; p.dbg = nullptr; p.C16 = nullptr;
+  p.a_mn = a.trans_a ? 1 : 0;
+  p.b_mn = a.trans_b ? 0 : 1;
+  ph.a_amax = a.a_amax; ph.b_amax = a.b_amax; ph.comp_per_mma = addk_h3_comp();
+  const int BN = a.N > 128 ? 256 : (a.N > 64 ? 128 : 64);
+  const uint16_t* Ah = reinterpret_cast<const uint16_t*>(a.A16); const uint16_t* Al = Ah + a.a16_plane;
+  const uint16_t* Bh = reinterpret_cast<const uint16_t*>(a.B16); const uint16_t* Bl = Bh + a.b16_plane;
+  CUtensorMap tah, tal, tbh, tbl;
+  bool ok = p.a_mn ? (make_map_f16(&tah, Ah, a.M, a.K, a.lda, 64, BKh) && make_map_f16(&tal, Al, a.M, a.K, a.lda, 64, BKh))
+                   : (make_map_f16(&tah, Ah, a.K, a.M, a.lda, BKh, BM) && make_map_f16(&tal, Al, a.K, a.M, a.lda, BKh, BM));
+  ok = ok && (p.b_mn ? (make_map_f16(&tbh, Bh, a.N, a.K, a.ldb, 64, BKh) && make_map_f16(&tbl, Bl, a.N, a.K, a.ldb, 64, BKh))
+                     : (make_map_f16(&tbh, Bh, a.K, a.N, a.ldb, BKh, BN) && make_map_f16(&tbl, Bl, a.K, a.N, a.ldb, BKh, BN)));
+  if (!ok) { addk_set_error("gemm f16x3: cuTensorMapEncodeTiled rejected an operand"); return ADDK_ERR_ARG; }
+  dim3 grid((a.N + BN - 1) / BN, (a.M + BM - 1) / BM, split);
+  if (BN == 256) return launch_h3<256>(st, tah, tal, tbh, tbl, ph, grid);
+  if (BN == 128) return launch_h3<128>(st, tah, tal, tbh, tbl, ph, grid);
+  return launch_h3<64>(st, tah, tal, tbh, tbl, ph, grid);
+}
+
 int addk_gemm_tc(cudaStream_t st, const addk_gemm_args& a, int precision) {
+  if (precision == 4) {
+    // fp16 hi/lo planes when the call carries twins that TMA can address (16-byte row pitch = 8 elements, 16-byte
+    // aligned planes); otherwise tf32x3 on the fp32 operands
+    const bool ok16 = a.A16 && a.B16 && a.a_amax && a.b_amax &&
+                      ((reinterpret_cast<uintptr_t>(a.A16) & 15) == 0) && ((reinterpret_cast<uintptr_t>(a.B16) & 15) == 0) &&
+                      ((a.a16_plane & 7) == 0) && ((a.b16_plane & 7) == 0) && a.a16_plane > 0 && a.b16_plane > 0 &&
+                      addk_gemm_h3_usable(a);
+    if (ok16) return gemm_h3(st, a);
+    return addk_gemm_tc(st, a, 1);
+  }
   if (precision == 3) {
     // bf16 tensor-core tiles when the call carries bf16 twins that TMA can address (16-byte row pitch = 8 elements);
     // otherwise tf32x3 on the fp32 operands, followed by the bf16 copy of the output the caller asked for
@@ -1412,6 +1856,15 @@ int addk_gemm_tc(cudaStream_t st, const addk_gemm_args& a, int precision) {
   ok = ok && (p.b_mn ? make_map(&tb, a.B, a.N, a.K, a.ldb, 32, BK, true) : make_map(&tb, a.B, a.K, a.N, a.ldb, BK, BN, false));
   if (!ok) return addk::sgemm_launch(st, a);
   dim3 grid((a.N + BN - 1) / BN, (a.M + BM - 1) / BM, split);
+  {
+    static int small = -1;
+    if (small < 0) { const char* e = getenv("ADDK_TC_X3_SMALL"); small = e ? atoi(e) : 0; }
+    if (x3 && BN == 256 && small) {        // experiment: 128x128 tiles, two CTAs per SM (one's epilogue overlaps the other's main loop)
+      if (!p.b_mn && !make_map(&tb, a.B, a.K, a.N, a.ldb, BK, 128, false)) return addk::sgemm_launch(st, a);
+      dim3 g2((a.N + 127) / 128, (a.M + BM - 1) / BM, split);
+      return launch_x3<128, 100, 2>(st, ta, tb, p, g2);
+    }
+  }
   if (x3 && BN == 256 && a.M > BM && addk_tc_pair_enabled()) {
     // CTA-pair kernel: each CTA of the pair stages 128 rows of B -> its tensor-map box has 128 rows
     if (!p.b_mn && !make_map(&tb, a.B, a.K, a.N, a.ldb, BK, Cfg2::BN / 2, false)) return addk::sgemm_launch(st, a);

@@ -30,6 +30,7 @@ struct addk_update_ctx {
 };
 
 int addk_gemm_tc(cudaStream_t st, const addk_gemm_args& a, int precision);
+bool addk_gemm_h3_usable(const addk_gemm_args& a);
 namespace addk { int sgemm_launch(cudaStream_t st, const addk_gemm_args& a); }
 
 namespace addk {
@@ -486,9 +487,74 @@ static int colsum(cudaStream_t st, const addk_update_ctx& c, const ChainWs& ws, 
 
 // precision "bf16": the bf16 twin of an fp32 operand (NULL when the pointer is not one of the twinned tensors)
 static thread_local const addk_update_ctx* g_twin_ctx = nullptr;
+
+// precision "f16x3": every arena tensor has an fp16 hi/lo twin (arena16: hi plane, then the lo plane arena_elems later)
+// and a max|x| word; a twin is (re)written by the first dense layer that reads the tensor after it was produced and
+// reused by the later ones (an activation feeds the next layer AND its weight gradient, a gradient feeds the input
+// gradient AND the weight gradient).  This table is host-side bookkeeping in ISSUE order; the kernels themselves are
+// stream-ordered, so a twin may only be shared by calls on one stream -- tensors read by several chains (xn, dn, the
+// parameters) are converted before the streams fork.  Slot 0 belongs to the flat parameter vector.
+struct TwinEnt { const float* p; long long rows; int cols, ld; cudaStream_t st; bool valid, shared; };
+static thread_local TwinEnt g_tw[63];
+static thread_local int g_ntw = 0;
+static void twin_reset() { g_ntw = 0; }
+static void twin_invalidate(const void* p, size_t bytes) {
+  const char* b = (const char*)p;
+  for (int i = 0; i < g_ntw; ++i) {
+    const char* q = (const char*)g_tw[i].p;
+    if (q >= b && q < b + (bytes ? bytes : 1)) g_tw[i].valid = false;
+  }
+}
+struct H3Op { const void* hi; long long plane; uint32_t* amax; int ready; };
+// looks the operand up; on a miss the entry is created / refreshed and ready = 0 tells the library to convert first
+static H3Op h3_operand(const addk_update_ctx& c, cudaStream_t st, const float* p, long long rows, int cols, int ld) {
+  H3Op o{nullptr, 0, nullptr, 0};
+  uint32_t* slots = (uint32_t*)c.amax_slots;
+  if (!slots || !p) return o;
+  const float* p0 = (const float*)c.params;
+  if (c.params16 && p >= p0 && p < p0 + c.num_params) {
+    o.hi = (const uint16_t*)c.params16 + (p - p0); o.plane = c.num_params; o.amax = slots; o.ready = 1;
+    return o;
+  }
+  const float* a0 = (const float*)c.arena;
+  if (!a0 || !c.arena16 || p < a0 || p >= a0 + c.arena_elems) return o;
+  int e = -1;
+  for (int i = 0; i < g_ntw; ++i) if (g_tw[i].p == p) { e = i; break; }
+  if (e < 0) {
+    if (g_ntw >= 63) return o;
+    e = g_ntw++;
+    g_tw[e] = TwinEnt{p, 0, 0, 0, nullptr, false, false};
+  }
+  TwinEnt& t = g_tw[e];
+  o.hi = (const uint16_t*)c.arena16 + (p - a0); o.plane = c.arena_elems; o.amax = slots + 1 + e;
+  if (t.valid && t.cols == cols && t.ld == ld && rows <= t.rows && (t.st == st || t.shared)) { o.ready = 1; return o; }
+  t.rows = rows; t.cols = cols; t.ld = ld; t.st = st; t.valid = true; t.shared = false;   // the call about to be issued converts it
+  return o;
+}
+extern "C" int addk_f16x3_convert(void* stream, const float* x, long long rows, int cols, int ld, void* hi16, long long plane,
+                                  uint32_t* amax_slot);
+// convert now (used for tensors several streams read: must happen before the fork)
+static int h3_prepare(const addk_update_ctx& c, cudaStream_t st, const float* p, long long rows, int cols, int ld) {
+  H3Op o = h3_operand(c, st, p, rows, cols, ld);
+  if (!o.hi) { addk_set_error("f16x3: tensor has no twin"); return ADDK_ERR_ARG; }
+  for (int i = 0; i < g_ntw; ++i) if (g_tw[i].p == p) g_tw[i].shared = true;     // converted before the fork: any stream may read it
+  if (o.ready) return ADDK_OK;
+  return addk_f16x3_convert(st, p, rows, cols, ld, const_cast<void*>(o.hi), o.plane, o.amax);
+}
+// the fp16 planes of the whole flat parameter vector (one scale: slot 0)
+static int h3_params(const addk_update_ctx& c, cudaStream_t st) {
+  if (c.precision != 4) return ADDK_OK;
+  twin_reset();
+  if (!c.params16 || !c.amax_slots) { addk_set_error("f16x3: the context has no parameter twin / max|x| slots"); return ADDK_ERR_ARG; }
+  return addk_f16x3_convert(st, (const float*)c.params, 1, (int)c.num_params, (int)c.num_params, c.params16, c.num_params,
+                            (uint32_t*)c.amax_slots);
+}
+
 static uint16_t* twin16(const void* p) {
   const addk_update_ctx* c = g_twin_ctx;
-  if (!c || c->precision != 3 || !p) return nullptr;
+  if (!c || !p) return nullptr;
+  if (c->precision == 4) { twin_invalidate(p, 0); return nullptr; }   // an elementwise producer is about to rewrite p
+  if (c->precision != 3) return nullptr;
   const float* f = (const float*)p;
   const float* a0 = (const float*)c->arena;
   if (a0 && f >= a0 && f < a0 + c->arena_elems) return (uint16_t*)c->arena16 + (f - a0);
@@ -503,9 +569,24 @@ static int gemm(cudaStream_t st, int prec, const float* A, int lda, int ta, cons
                 long long slab_stride = 0) {
   addk_gemm_args a;
   a.A16 = prec == 3 ? twin16(A) : nullptr; a.B16 = prec == 3 ? twin16(B) : nullptr; a.C16 = prec == 3 ? twin16(C) : nullptr;
+  a.a16_plane = a.b16_plane = 0; a.a_amax = a.b_amax = nullptr; a.a16_ready = a.b16_ready = 0;
   a.A = A; a.lda = lda; a.B = B; a.ldb = ldb; a.C = C; a.ldc = ldc; a.M = M; a.N = N; a.K = K;
   a.bias = bias; a.a_mean = nmean; a.a_std = nstd; a.relu_mask_src = mask; a.ld_mask = ld_mask;
   a.trans_a = ta; a.trans_b = tb; a.relu = relu; a.split_k = split; a.accumulate = 0; a.slab_stride = slab_stride;
+  if (prec == 4 && g_twin_ctx) {
+    if (addk_gemm_h3_usable(a)) {
+      const H3Op oa = h3_operand(*g_twin_ctx, st, A, ta ? K : M, ta ? M : K, lda);
+      const H3Op ob = h3_operand(*g_twin_ctx, st, B, tb ? N : K, tb ? K : N, ldb);
+      if (oa.hi && ob.hi) {
+        a.A16 = oa.hi; a.a16_plane = oa.plane; a.a_amax = oa.amax; a.a16_ready = oa.ready;
+        a.B16 = ob.hi; a.b16_plane = ob.plane; a.b_amax = ob.amax; a.b16_ready = ob.ready;
+      } else {                      // the call runs in tf32x3 and converts nothing: forget what h3_operand assumed
+        if (oa.hi && !oa.ready) twin_invalidate(A, 0);
+        if (ob.hi && !ob.ready) twin_invalidate(B, 0);
+      }
+    }
+    twin_invalidate(C, (size_t)(split > 1 ? 1 : M) * ldc * sizeof(float));
+  }
   int rc = prec == 0 ? addk::sgemm_launch(st, a) : addk_gemm_tc(st, a, prec);
   if (rc != ADDK_OK) return rc;
   ADDK_CHECK_LAUNCH();
@@ -644,12 +725,18 @@ extern "C" int addk_update_minibatch(void* stream, void* ctx_host, const long lo
     f32_to_bf16_flat_kernel<<<148 * 4, 256, 0, st>>>(F(c.params), (uint16_t*)c.params16, c.num_params);
     ADDK_CHECK_LAUNCH();
   }
+  TRY(h3_params(c, st));
 
   gather_minibatch_kernel<<<(M + 7) / 8, 256, 0, st>>>(
       idx, M, OD, AD, AL, DD, DL, F(c.buf_obs), F(c.buf_action), F(c.buf_a_logp), F(c.buf_adv), F(c.buf_tar_val),
       F(c.buf_mask), F(c.buf_disc_obs), F(c.buf_disc_demo), F(c.obs_mean), F(c.obs_std), F(c.a_mean), F(c.a_std),
       F(c.disc_mean_abs), F(c.xn), F(c.an), F(c.old_logp), F(c.adv), F(c.tar), F(c.mask), F(c.dn), cnt, twin16(c.xn), twin16(c.dn));
   ADDK_CHECK_LAUNCH();
+
+  if (pr == 4) {      // twins of the inputs the chains share, before the streams fork
+    TRY(h3_prepare(c, st, F(c.xn), M, OD, OD));
+    TRY(h3_prepare(c, st, F(c.dn), R, DL, DL));
+  }
 
   // The three chains share only read-only inputs (xn, dn, the parameters) and write disjoint slab segments and
   // statistics slots.  With n_streams == 3 each has its own workspace and stream: the tail wave of one chain's dense
@@ -783,6 +870,7 @@ extern "C" int addk_actor_step(void* stream, void* ctx_host, const float* obs, c
     f32_to_bf16_flat_kernel<<<148 * 4, 256, 0, st>>>(F(c.params), (uint16_t*)c.params16, c.num_params);
     ADDK_CHECK_LAUNCH();
   }
+  TRY(h3_params(c, st));
   if (obs_rec) cudaMemcpyAsync(obs_rec, obs, (size_t)n * OD * sizeof(float), cudaMemcpyDeviceToDevice, st);
   TRY(trunk_forward(st, c, main_ws(c), obs, OD, OD, n, c.o_a_w0, c.o_a_b0, c.o_a_w1, c.o_a_b1, c.o_a_w2, c.o_a_b2, F(c.obs_mean),
                     F(c.obs_std)));
@@ -805,6 +893,7 @@ extern "C" int addk_critic_eval(void* stream, void* ctx_host, const float* obs, 
     f32_to_bf16_flat_kernel<<<148 * 4, 256, 0, st>>>(F(c.params), (uint16_t*)c.params16, c.num_params);
     ADDK_CHECK_LAUNCH();
   }
+  TRY(h3_params(c, st));
   for (long long r0 = 0; r0 < n; r0 += chunk) {
     int rows = (int)((n - r0 < chunk) ? n - r0 : chunk);
     TRY(trunk_forward(st, c, main_ws(c), obs + r0 * OD, OD, OD, rows, c.o_c_w0, c.o_c_b0, c.o_c_w1, c.o_c_b1, c.o_c_w2, c.o_c_b2,
@@ -828,6 +917,7 @@ extern "C" int addk_disc_eval(void* stream, void* ctx_host, const float* disc_ob
     f32_to_bf16_flat_kernel<<<148 * 4, 256, 0, st>>>(F(c.params), (uint16_t*)c.params16, c.num_params);
     ADDK_CHECK_LAUNCH();
   }
+  TRY(h3_params(c, st));
   pad_rows_kernel<<<(E1 * DL + 255) / 256, 256, 0, st>>>(W + c.o_d_w0, E1, DD, DL, F(c.wd0_pad), twin16(c.wd0_pad));
   ADDK_CHECK_LAUNCH();
   for (long long r0 = 0; r0 < n; r0 += chunk) {

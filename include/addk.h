@@ -192,8 +192,21 @@ typedef struct addk_gemm_args {
   /* precision "bf16" only: bf16 twins of the operands (same shapes / leading dimensions, in elements) and an
    * optional bf16 copy of the output.  NULL twins -> the call runs in tf32x3 on the fp32 operands. */
   const void* A16; const void* B16; void* C16;
+  /* precision "f16x3" only (fp32-parity mode on the fp16 tensor pipe): A16 / B16 point at the fp16 "hi" plane of the
+   * operand's twin (same shape / leading dimension as the fp32 operand, x*s rounded to fp16, s = the power of two that
+   * puts max|x| into [2^14, 2^15)); the "lo" plane ((x*s - hi) * 2^11 rounded to fp16) starts a16_plane / b16_plane
+   * ELEMENTS after it; a_amax / b_amax are device words holding the bit pattern of max|x|.  a16_ready / b16_ready = 0:
+   * the call computes max|x| and writes both planes first (two extra launches per operand); != 0: the twin already
+   * holds this operand (converted by an earlier call).  NULL twins -> the call runs in tf32x3. */
+  int64_t a16_plane, b16_plane;
+  uint32_t* a_amax; uint32_t* b_amax;
+  int32_t a16_ready, b16_ready;
 } addk_gemm_args;
 int addk_gemm(void* stream, const addk_gemm_args* args_host, int precision);
+/* precision "f16x3": max|x| of the [rows, cols] fp32 tensor x (pitch ld) -> *amax_slot (bit pattern), then the two
+ * fp16 planes hi16[0 .. rows*ld) and hi16[plane .. plane + rows*ld) described above.  Three stream-ordered operations. */
+int addk_f16x3_convert(void* stream, const float* x, long long rows, int cols, int ld, void* hi16, long long plane,
+                       uint32_t* amax_slot);
 
 /* ----- PPO / ADD minibatch (csrc/mlp.cu) ------------------------------------------------------ */
 struct addk_update_ctx;  /* opaque; plain host struct of device pointers, see csrc/mlp.cu */

@@ -12,7 +12,7 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
-TOL = {"fp32": 2e-6, "tf32x3": 2e-6, "tf32": 2e-3}
+TOL = {"fp32": 2e-6, "tf32x3": 2e-6, "tf32": 2e-3, "f16x3": 2e-6}
 
 
 def _gemm(A, B, Cout, M, N, K, ta, tb, prec, bias=None, relu=0, mask=None, split=1, accumulate=0, lda=None, ldb=None):
@@ -130,3 +130,107 @@ def test_gemm_bf16_layouts(ta, tb):
         e = _rel(out[:, :N], ref)
         assert e <= 1e-5, "bf16 ta=%d tb=%d %s: rel err %.3e" % (ta, tb, (M, N, K), e)
         assert torch.equal(out16[:, :N], out[:, :N].to(torch.bfloat16)), "bf16 copy of the output"
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# precision "f16x3": fp16 hi/lo planes (scaled by the tensor's max|x|) on the fp16 tensor pipe, fp32-class accuracy
+# ---------------------------------------------------------------------------------------------------------------------
+class _Twin:
+    """fp16 hi/lo planes + the max|x| word of one fp32 operand, as the C-ABI expects them."""
+
+    def __init__(self, t):
+        self.n = (t.numel() + 7) & ~7
+        self.planes = torch.zeros(2 * self.n, device=t.device, dtype=torch.float16)
+        self.amax = torch.zeros(1, device=t.device, dtype=torch.int32)
+
+
+def _gemm_h3(A, B, Cout, M, N, K, ta, tb, tw_a, tw_b, ready=(0, 0), bias=None, relu=0, mask=None, split=1, accumulate=0):
+    from add_gym_b200 import _lib
+    a = _lib.AddkGemmArgs(A=A.data_ptr(), lda=A.stride(0), B=B.data_ptr(), ldb=B.stride(0), C=Cout.data_ptr(),
+                          ldc=Cout.stride(-2), M=M, N=N, K=K, bias=bias.data_ptr() if bias is not None else None,
+                          a_mean=None, a_std=None, relu_mask_src=mask.data_ptr() if mask is not None else None,
+                          ld_mask=mask.stride(0) if mask is not None else 0, trans_a=ta, trans_b=tb, relu=relu,
+                          split_k=split, accumulate=accumulate, slab_stride=0, A16=tw_a.planes.data_ptr(),
+                          B16=tw_b.planes.data_ptr(), C16=None, a16_plane=tw_a.n, b16_plane=tw_b.n,
+                          a_amax=tw_a.amax.data_ptr(), b_amax=tw_b.amax.data_ptr(), a16_ready=ready[0], b16_ready=ready[1])
+    _lib.check(_lib.lib().addk_gemm(_lib.stream(), C.byref(a), C.c_int(_lib.PRECISIONS["f16x3"])), "addk_gemm")
+
+
+@pytest.mark.parametrize("ta,tb", [(0, 1), (0, 0), (1, 0), (1, 1)])
+def test_gemm_f16x3_layouts(ta, tb):
+    g = torch.Generator(device="cuda").manual_seed(5)
+    pad = lambda n: (n + 7) & ~7
+    for (M, N, K) in SHAPES:
+        A = torch.randn((K, pad(M)) if ta else (M, pad(K)), device="cuda", generator=g)
+        B = torch.randn((N, pad(K)) if tb else (K, pad(N)), device="cuda", generator=g)
+        Aop = (A[:, :M].t() if ta else A[:, :K]).double()
+        Bop = (B[:, :K].t() if tb else B[:, :N]).double()
+        ref = Aop @ Bop
+        out = torch.full((M, pad(N)), float("nan"), device="cuda")
+        tw_a, tw_b = _Twin(A), _Twin(B)
+        _gemm_h3(A, B, out, M, N, K, ta, tb, tw_a, tw_b)
+        torch.cuda.synchronize()
+        if min(M, N, K) >= 16:   # smaller shapes run the tf32x3 fallback and leave the twins untouched
+            used = A[:, :M] if ta else A[:, :K]
+            assert int(tw_a.amax.item()) == int(used.abs().max().view(torch.int32).item()), "max|A| word"
+            assert bool((tw_a.planes != 0).any()), "the fp16 planes were not written: the call fell back"
+        e = _rel(out[:, :N], ref)
+        assert e <= TOL["f16x3"], "f16x3 ta=%d tb=%d %s: rel err %.3e" % (ta, tb, (M, N, K), e)
+        if pad(N) != N:
+            assert torch.isnan(out[:, N:]).all(), "columns beyond N must not be written"
+
+
+def test_gemm_f16x3_epilogues_split_k_and_reuse():
+    g = torch.Generator(device="cuda").manual_seed(6)
+    M, N, K = 1000, 512, 1024
+    A = torch.randn(M, K, device="cuda", generator=g)
+    W = torch.randn(N, K, device="cuda", generator=g) * 0.05
+    bias = torch.randn(N, device="cuda", generator=g)
+    out = torch.empty(M, N, device="cuda")
+    tA, tW = _Twin(A), _Twin(W)
+    _gemm_h3(A, W, out, M, N, K, 0, 1, tA, tW, bias=bias, relu=1)
+    ref = torch.relu(A.double() @ W.double().t() + bias.double())
+    assert _rel(out, ref) <= TOL["f16x3"]
+    # the twins now hold A and W: a second call may skip the conversion and must give the same bits
+    out2 = torch.empty(M, N, device="cuda")
+    _gemm_h3(A, W, out2, M, N, K, 0, 1, tA, tW, ready=(1, 1), bias=bias, relu=1)
+    assert torch.equal(out, out2)
+    h = torch.randn(M, K, device="cuda", generator=g)
+    dY = torch.randn(M, N, device="cuda", generator=g) * 1e-6          # gradient-sized values: far below fp16's range unscaled
+    dX = torch.empty(M, K, device="cuda")
+    tdY = _Twin(dY)
+    _gemm_h3(dY, W, dX, M, K, N, 0, 0, tdY, tW, ready=(0, 1), mask=h)   # W's twin is layout-independent
+    ref = (dY.double() @ W.double()) * (h > 0).double()
+    assert _rel(dX, ref) <= TOL["f16x3"]
+    base = torch.randn(M, K, device="cuda", generator=g) * 1e-6
+    acc = base.clone()
+    _gemm_h3(dY, W, acc, M, K, N, 0, 0, tdY, tW, ready=(1, 1), accumulate=1)
+    assert _rel(acc, base.double() + dY.double() @ W.double()) <= TOL["f16x3"]
+    S = 8
+    slabs = torch.full((S, N, K), float("nan"), device="cuda")
+    _gemm_h3(dY, A, slabs, N, K, M, 1, 0, tdY, tA, ready=(1, 1), split=S)
+    torch.cuda.synchronize()
+    ref = dY.double().t() @ A.double()
+    assert _rel(slabs.sum(0), ref) <= TOL["f16x3"]
+
+
+def test_gemm_f16x3_dynamic_range_and_mlp_scale():
+    """Operands whose elements span 12 orders of magnitude (one scale per tensor): the norm-wise error stays fp32-class;
+    and the MLP-shaped case must stay an order of magnitude inside the 1e-5 parity bar."""
+    g = torch.Generator(device="cuda").manual_seed(7)
+    M, N, K = 2048, 1024, 1024
+    A = torch.randn(M, K, device="cuda", generator=g) * torch.exp(torch.randn(M, K, device="cuda", generator=g) * 4.0) * 1e-5
+    W = torch.randn(N, K, device="cuda", generator=g) * torch.exp(torch.randn(N, K, device="cuda", generator=g) * 4.0)
+    out = torch.empty(M, N, device="cuda")
+    _gemm_h3(A, W, out, M, N, K, 0, 1, _Twin(A), _Twin(W))
+    assert _rel(out, A.double() @ W.double().t()) <= TOL["f16x3"]
+    A = torch.relu(torch.randn(4096, K, device="cuda", generator=g))
+    W = (torch.rand(N, K, device="cuda", generator=g) * 2 - 1) / 32.0
+    out = torch.empty(4096, N, device="cuda")
+    _gemm_h3(A, W, out, 4096, N, K, 0, 1, _Twin(A), _Twin(W))
+    e = _rel(out, A.double() @ W.double().t())
+    assert e <= 1e-6, e
+    Z = torch.zeros(256, K, device="cuda")                              # all-zero operand: finite scale, zero output
+    out = torch.full((256, N), float("nan"), device="cuda")
+    _gemm_h3(Z, W, out, 256, N, K, 0, 1, _Twin(Z), _Twin(W))
+    assert torch.equal(out, torch.zeros_like(out))

@@ -294,6 +294,12 @@ def test_iteration_parity_tensor_core_tf32x3_n64():
     _iteration_parity(64, None, steps_synced=12, precision="tf32x3")
 
 
+def test_iteration_parity_tensor_core_f16x3_n64():
+    """The fp16-pipe fp32-parity mode (tcgen05 kind::f16 on hi/lo fp16 planes scaled by the tensor's max|x|, twins
+    cached across the dense layers that share an operand) must meet the same 1e-5 bar."""
+    _iteration_parity(64, None, steps_synced=12, precision="f16x3")
+
+
 def test_iteration_parity_tensor_core_tf32_n64():
     """Single-pass TF32 -- what the reference itself runs on a GPU (`allow_tf32 = True`, main.py:17-18).  10-bit
     operand mantissas: judged against the north star's reduced-precision bar (2e-2); median step within 1e-2."""
@@ -434,7 +440,7 @@ def test_cuda_graph_rollout_is_bit_identical_to_eager():
     assert int(eager._core.tracker_count.item()) == int(graphed._core.tracker_count.item())
 
 
-@pytest.mark.parametrize("precision", ["tf32x3", "bf16"])
+@pytest.mark.parametrize("precision", ["tf32x3", "bf16", "f16x3"])
 def test_three_stream_update_is_bit_identical_to_one_stream(precision):
     """The actor / critic / discriminator chains of an optimizer step on three streams (separate workspaces, tail waves
     overlapping) must produce exactly the parameters the back-to-back single-stream order produces: every kernel is
