@@ -223,7 +223,9 @@ class ADDAgent(torch.nn.Module):
         od, dd, ad = m.obs_dim, m.disc_dim, m.act_dim
         al, dl = (ad + 7) & ~7, (dd + 7) & ~7      # leading dimensions: 8 elements = 16 bytes in the bf16 twins too
         H, E = m.hidden
-        S = 8
+        # split-K slabs of the weight gradients: 9 x (16 | 32 | 16) output tiles = 144 | 288 | 144 fill the 148 SMs of the
+        # persistent f16x3 kernel; 8 suits the CTA-pair tf32x3 kernel
+        S = 9 if m.precision == _lib.PRECISIONS["f16x3"] else 8
         z = lambda *s, dt=torch.float32: torch.zeros(list(s), device=dev, dtype=dt)
         fb = self._exp_buffer.get_data_flat
         self._max_steps = int(self._update_epochs * int(np.ceil(float(T * N) / M)))

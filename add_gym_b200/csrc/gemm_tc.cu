@@ -45,6 +45,7 @@ struct Params {
   void* C16;                   // bf16 kernel: optional bf16 copy of the output (same leading dimension)
   long long* dbg;              // experiment: clock64 stamps of CTA (0,0,0) of the pair kernel (env ADDK_TC_DBG = address)
   int pair_flags;              // CTA-pair kernel experiments: bit0 cluster-scope waits, bit1 relaxed remote arrives
+  uint32_t* c_amax;            // f16x3 kernels: atomicMax of the bit patterns of |C| as stored (NULL: not wanted)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -148,7 +149,8 @@ __device__ __forceinline__ void stage_put(float4* stg, int lane, int slot, float
 }
 
 template <int CW>
-__device__ __forceinline__ void store_staged(const Params& p, float* Cz, const float4* stg, int lane, int grow0, int col0) {
+__device__ __forceinline__ void store_staged(const Params& p, float* Cz, const float4* stg, int lane, int grow0, int col0,
+                                             float* vmax = nullptr) {
   constexpr int S = CW / 4;                        // float4 slots per row
   constexpr int RPI = S >= 32 ? 1 : 32 / S;        // rows per store instruction
   constexpr int PPR = S > 32 ? S / 32 : 1;         // instructions per row
@@ -198,6 +200,7 @@ __device__ __forceinline__ void store_staged(const Params& p, float* Cz, const f
           o.z = m4[u].z > 0.f ? o.z : 0.f; o.w = m4[u].w > 0.f ? o.w : 0.f;
           o.x += a4[u].x; o.y += a4[u].y; o.z += a4[u].z; o.w += a4[u].w;
           *reinterpret_cast<float4*>(dstp) = o;
+          if (vmax) *vmax = fmaxf(fmaxf(*vmax, fmaxf(fabsf(o.x), fabsf(o.y))), fmaxf(fabsf(o.z), fabsf(o.w)));
         } else {
           const float oo[4] = {o.x, o.y, o.z, o.w};
           for (int e = 0; e < 4 && col + e < p.N; ++e) {
@@ -205,6 +208,7 @@ __device__ __forceinline__ void store_staged(const Params& p, float* Cz, const f
             if (p.mask) xv = p.mask[(size_t)grow * p.ld_mask + col + e] > 0.f ? xv : 0.f;
             if (p.accumulate) xv += dstp[e];
             dstp[e] = xv;
+            if (vmax) *vmax = fmaxf(*vmax, fabsf(xv));
           }
         }
       }
@@ -213,7 +217,8 @@ __device__ __forceinline__ void store_staged(const Params& p, float* Cz, const f
 }
 
 // row-per-lane scalar fallback for outputs that are not 16-byte aligned (ldc % 4 != 0)
-__device__ __forceinline__ void store_row_scalar(const Params& p, float* Cz, int row, int cbase, const float* acc32) {
+__device__ __forceinline__ void store_row_scalar(const Params& p, float* Cz, int row, int cbase, const float* acc32,
+                                                 float* vmax = nullptr) {
   float* dstp = Cz + (size_t)row * p.ldc + cbase;
   const float* mk = p.mask ? p.mask + (size_t)row * p.ld_mask + cbase : nullptr;
 #pragma unroll
@@ -226,6 +231,7 @@ __device__ __forceinline__ void store_row_scalar(const Params& p, float* Cz, int
       if (mk) xv = mk[j] > 0.f ? xv : 0.f;
       if (p.accumulate) xv += dstp[j];
       dstp[j] = xv;
+      if (vmax) *vmax = fmaxf(*vmax, fabsf(xv));
     }
   }
 }
@@ -1312,13 +1318,13 @@ static int launch_bf16(cudaStream_t st, const CUtensorMap& ta, const CUtensorMap
 // 72 KB of shared memory and the hi/lo split moves another 48 KB, 120 KB against the SM's 128 B/clk: the main loop is
 // shared-memory-bandwidth bound at ~200 cycles per MMA (nominal 134).  Here every operand is split ONCE, outside the
 // GEMM, into two fp16 planes
-//     hi = fp16_rn(x * s),   lo = fp16_rn((x * s - hi) * 2^11),   s = 2^(14 - floor(log2(max|x|)))
-// (22+ mantissa bits, i.e. the whole fp32 value; s keeps every significant element inside fp16's normal range; the
+//     hi = fp16_rn(x * s),   lo = fp16_rn(x * s - hi),   s = 2^(14 - floor(log2(max|x|)))
+// (22+ mantissa bits for every element within 2^-17 of max|x|, an absolute error below 2^-39 max|x| for the rest; the
 // residual is exact in fp32 before its rounding), and the GEMM is pure TMA -> tcgen05.mma.kind::f16 (M=128, N=BN,
 // K=16, twice the tf32 rate, half the shared-memory bytes per k):
 //     main  += hi_a . hi_b            (TMEM columns [0, BN))
-//     cross += lo_a . hi_b + hi_a . lo_b   (TMEM columns [BN, 2 BN), scaled by 2^11)
-//     C = (main + cross * 2^-11) / (s_a * s_b)            lo.lo (2^-24 relative) is dropped
+//     cross += lo_a . hi_b + hi_a . lo_b   (TMEM columns [BN, 2 BN))
+//     C = (main + cross) / (s_a * s_b)            lo.lo (2^-22 relative) is dropped
 // The main accumulator is drained into fp32 registers every H3_CHUNK_KB k-blocks like in the tf32x3 kernel (the
 // tensor core truncates its accumulator after every instruction).  10 warps: 0 = TMA producer, 1 = MMA issuer (whole
 // warp runs the loop, one elected lane issues), 2..9 = chunk drains + epilogue.
@@ -1329,7 +1335,10 @@ struct CfgH3 {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = 2 * (A_BYTES + B_BYTES);  // [A_hi | B_hi | A_lo | B_lo]
-  static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 6 ? 6 : (200 * 1024) / STAGE_BYTES;
+#ifndef ADDK_H3_CAP_KB
+#define ADDK_H3_CAP_KB 200
+#endif
+  static constexpr int STAGES = (ADDK_H3_CAP_KB * 1024) / STAGE_BYTES > 6 ? 6 : (ADDK_H3_CAP_KB * 1024) / STAGE_BYTES;
   static constexpr int EPI_BYTES = 8 * 32 * (BN / 2) * 4;      // epilogue staging: 8 warps x 32 rows x BN/2 floats
   static constexpr int RING_BYTES = STAGES * STAGE_BYTES > EPI_BYTES ? STAGES * STAGE_BYTES : EPI_BYTES;
   static constexpr int SMEM_BYTES = RING_BYTES + 1024 + 256;
@@ -1536,7 +1545,7 @@ gemm_tc_h3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
       for (int j = 0; j < 32; ++j) acc[cc * 32 + j] += fmaf(__uint_as_float(v[j]), comp_last, __uint_as_float(v[j]));
       tmem_ld32(t_main + (uint32_t)(BN + cc * 32), v);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) acc[cc * 32 + j] = fmaf(__uint_as_float(v[j]), 4.8828125e-4f, acc[cc * 32 + j]) * inv;
+      for (int j = 0; j < 32; ++j) acc[cc * 32 + j] = (acc[cc * 32 + j] + __uint_as_float(v[j])) * inv;
     }
     // ---- epilogue: this warp's 32 x CPW accumulators -> staging tile -> full-row stores (store_staged)
     float* Cz = p.C + (size_t)blockIdx.z * p.slab_stride;
@@ -1545,16 +1554,271 @@ gemm_tc_h3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
     float4* stg = reinterpret_cast<float4*>(base_ptr + (32 * CPW * 4) * (warp - 2));
     const int row = m0 + 32 * q + lane;
     const int cw0 = n0 + half * CPW;
+    float vmax = 0.f;
+    float* const vm = p.c_amax ? &vmax : nullptr;
     if (cw0 < p.N) {                           // warp-uniform
       if (vec) {
 #pragma unroll
         for (int sl = 0; sl < CPW / 4; ++sl) stage_put<CPW>(stg, lane, sl, acc[4 * sl], acc[4 * sl + 1], acc[4 * sl + 2], acc[4 * sl + 3]);
         __syncwarp();
-        store_staged<CPW>(p, Cz, stg, lane, m0 + 32 * q, cw0);
+        store_staged<CPW>(p, Cz, stg, lane, m0 + 32 * q, cw0, vm);
       } else if (row < p.M) {
 #pragma unroll
-        for (int cc = 0; cc < NCH; ++cc) store_row_scalar(p, Cz, row, cw0 + cc * 32, acc + cc * 32);
+        for (int cc = 0; cc < NCH; ++cc) store_row_scalar(p, Cz, row, cw0 + cc * 32, acc + cc * 32, vm);
       }
+    }
+    if (p.c_amax) {
+      const uint32_t mx = __reduce_max_sync(0xffffffffu, __float_as_uint(vmax));
+      if (lane == 0 && mx) atomicMax(p.c_amax, mx);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// f16x3, persistent version (the one the big layers run).  ncu on the kernel above (16384 x 1024 x 1024): the tensor
+// pipe is busy 57 % of a CTA's life -- the main loop runs at the nominal MMA rate, the rest is the prologue and an
+// epilogue nothing overlaps.  Here one CTA per SM walks over tiles (tile = blockIdx.x + j * gridDim.x, n fastest so
+// neighbouring SMs share A rows in L2) and the accumulator is double-buffered in TMEM per 256-k CHUNK:
+//   * main and cross terms share ONE accumulator of BN columns (3 MMAs per 16 k; the cross terms are 2^-11 of the sum,
+//     the drain into fp32 registers every 48 instructions keeps the truncation loss where the kernel above has it);
+//   * chunk g lives in buffer g & 1: the MMA warp fills one buffer while the workers drain the other, and the last
+//     drain of a tile is followed by its global stores while the tensor core is already on the next tile.
+// Warps as above (0 TMA, 1 MMA, 2..9 workers); barriers: full/empty per stage, acc_full/acc_empty per buffer.
+// ---------------------------------------------------------------------------------------------------------------
+template <int BN>
+struct CfgP {
+  static constexpr int BK = 32;
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = 2 * (A_BYTES + B_BYTES);
+#ifndef ADDK_H3P_EPI_COLS
+#define ADDK_H3P_EPI_COLS 64
+#endif
+  static constexpr int EPI_COLS = ADDK_H3P_EPI_COLS;                // columns per staging pass
+  static constexpr int EPI_BYTES = 8 * 32 * EPI_COLS * 4;           // 8 worker warps x 32 rows x 64 floats
+  static constexpr int STAGES = (226 * 1024 - EPI_BYTES) / STAGE_BYTES > 6 ? 6 : (226 * 1024 - EPI_BYTES) / STAGE_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 + 256;
+  static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+  static constexpr uint32_t K_SBO = 8u * BK * 2u;
+  static constexpr uint32_t MN_BOX_BYTES = BK * 128u;
+};
+constexpr int H3P_CHUNK_KB = 8;                                     // 256 k = 48 instructions per drain (measured: rel 5e-7)
+
+struct ParamsP {
+  Params p;
+  const uint32_t* a_amax; const uint32_t* b_amax;
+  float comp_per_mma;
+  int tiles_m, tiles_n, total_tiles;
+  int chunk_kb;                 // k-blocks per accumulator chunk (drain period)
+};
+
+template <int BN>
+__global__ void __launch_bounds__(X3_THREADS, 1)
+gemm_tc_h3p_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
+                   const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl, const ParamsP pp) {
+  using C = CfgP<BN>;
+  const Params& p = pp.p;
+  constexpr int BK = C::BK, UK = 16;
+  constexpr int CPW = BN / 2, NCH = CPW / 32;
+  static_assert(CPW % C::EPI_COLS == 0, "BN must be a multiple of 128");
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_u32 = smem_u32(smem_raw);
+  const uint32_t base = (raw_u32 + 1023u) & ~1023u;
+  uint8_t* const base_ptr = smem_raw + (base - raw_u32);
+  const uint32_t bars = base + C::STAGES * C::STAGE_BYTES + C::EPI_BYTES;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (C::STAGES + s); };
+  auto acc_full_bar = [&](int b) { return bars + 8u * (2 * C::STAGES + b); };
+  auto acc_empty_bar = [&](int b) { return bars + 8u * (2 * C::STAGES + 2 + b); };
+  const uint32_t tmem_ptr_addr = bars + 8u * (2 * C::STAGES + 4);
+  auto a_hi = [&](int s) { return base + (uint32_t)s * C::STAGE_BYTES; };
+  auto b_hi = [&](int s) { return a_hi(s) + C::A_BYTES; };
+  auto a_lo = [&](int s) { return b_hi(s) + C::B_BYTES; };
+  auto b_lo = [&](int s) { return a_lo(s) + C::A_BYTES; };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kb_total = (p.K + BK - 1) / BK;
+  const int tiles_mn = pp.tiles_m * pp.tiles_n;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmAh); tma_prefetch_desc(&tmAl); tma_prefetch_desc(&tmBh); tma_prefetch_desc(&tmBl);
+    for (int s = 0; s < C::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(acc_full_bar(b), 1); mbar_init(acc_empty_bar(b), 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "r"((uint32_t)C::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr) : "memory");
+
+  if (warp == 0) {
+    // ===================== TMA producer: runs ahead across tile boundaries =====================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int t = blockIdx.x; t < pp.total_tiles; t += gridDim.x) {
+        const int z = t / tiles_mn, r = t - z * tiles_mn;
+        const int m0 = (r / pp.tiles_n) * BM, n0 = (r % pp.tiles_n) * BN;
+        const int kb_begin = z * p.kb_per_split;
+        const int num_kb = min(kb_total, kb_begin + p.kb_per_split) - kb_begin;
+        for (int i = 0; i < num_kb; ++i, ++it) {
+          const int s = (int)(it % C::STAGES);
+          const uint32_t phs = (it / C::STAGES) & 1u;
+          mbar_wait(empty_bar(s), phs ^ 1u);
+          mbar_expect_tx(full_bar(s), C::STAGE_BYTES);
+          const int k0 = (kb_begin + i) * BK;
+          if (!p.a_mn) {
+            tma_load_2d(a_hi(s), &tmAh, full_bar(s), k0, m0);
+            tma_load_2d(a_lo(s), &tmAl, full_bar(s), k0, m0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BM / 64; ++j) {
+              tma_load_2d(a_hi(s) + j * C::MN_BOX_BYTES, &tmAh, full_bar(s), m0 + 64 * j, k0);
+              tma_load_2d(a_lo(s) + j * C::MN_BOX_BYTES, &tmAl, full_bar(s), m0 + 64 * j, k0);
+            }
+          }
+          if (!p.b_mn) {
+            tma_load_2d(b_hi(s), &tmBh, full_bar(s), k0, n0);
+            tma_load_2d(b_lo(s), &tmBl, full_bar(s), k0, n0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j) {
+              tma_load_2d(b_hi(s) + j * C::MN_BOX_BYTES, &tmBh, full_bar(s), n0 + 64 * j, k0);
+              tma_load_2d(b_lo(s) + j * C::MN_BOX_BYTES, &tmBl, full_bar(s), n0 + 64 * j, k0);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(p.a_mn ? 1 : 0) << 15) | ((uint32_t)(p.b_mn ? 1 : 0) << 16) |
+                           ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    const uint32_t a_lbo = p.a_mn ? C::MN_BOX_BYTES : 16u, b_lbo = p.b_mn ? C::MN_BOX_BYTES : 16u;
+    const uint32_t a_sbo = p.a_mn ? 1024u : C::K_SBO, b_sbo = p.b_mn ? 1024u : C::K_SBO;
+    const uint32_t a_lay = p.a_mn ? 2u : 4u, b_lay = p.b_mn ? 2u : 4u;
+    const uint64_t dA0 = smem_desc(a_hi(0), a_lbo, a_sbo, a_lay);
+    const uint64_t dB0 = smem_desc(b_hi(0), b_lbo, b_sbo, b_lay);
+    const uint64_t a_k16 = p.a_mn ? (2048u >> 4) : (32u >> 4), b_k16 = p.b_mn ? (2048u >> 4) : (32u >> 4);
+    constexpr uint64_t LO16 = (C::A_BYTES + C::B_BYTES) >> 4, STAGE16 = C::STAGE_BYTES >> 4;
+    const bool issuer = elect_one();
+    uint32_t it = 0, g = 0;
+    for (int t = blockIdx.x; t < pp.total_tiles; t += gridDim.x) {
+      const int z = t / tiles_mn;
+      const int kb_begin = z * p.kb_per_split;
+      const int num_kb = min(kb_total, kb_begin + p.kb_per_split) - kb_begin;
+      for (int kb = 0; kb < num_kb; ++g) {
+        const uint32_t b = g & 1u;
+        mbar_wait(acc_empty_bar(b), ((g >> 1) & 1u) ^ 1u);      // the workers have copied chunk g-2 out of this buffer
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + b * BN;
+        const int n = min(pp.chunk_kb, num_kb - kb);
+        uint32_t acc = 0;
+        for (int j = 0; j < n; ++j, ++it) {
+          const int s = (int)(it % C::STAGES);
+          mbar_wait(full_bar(s), (it / C::STAGES) & 1u);
+          tc_fence_after();
+          if (issuer) {
+            const uint64_t dah = dA0 + (uint64_t)s * STAGE16, dbh = dB0 + (uint64_t)s * STAGE16;
+#pragma unroll
+            for (int ks = 0; ks < BK / UK; ++ks) {
+              umma_f16(d_tmem, dah + ks * a_k16, dbh + ks * b_k16, idesc, acc);
+              acc = 1;
+              umma_f16(d_tmem, dah + LO16 + ks * a_k16, dbh + ks * b_k16, idesc, 1u);
+              umma_f16(d_tmem, dah + ks * a_k16, dbh + LO16 + ks * b_k16, idesc, 1u);
+            }
+            umma_commit(empty_bar(s));
+          }
+          __syncwarp();
+        }
+        if (issuer) umma_commit(acc_full_bar(b));
+        __syncwarp();
+        kb += n;
+      }
+    }
+  } else {
+    // ===================== workers: chunk drains + epilogue =====================
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(half * CPW);
+    float sa, sb, ia, ib;
+    h3_scale(pp.a_amax ? *pp.a_amax : 0x3F800000u, sa, ia);
+    h3_scale(pp.b_amax ? *pp.b_amax : 0x3F800000u, sb, ib);
+    const float inv = ia * ib;
+    float4* stg = reinterpret_cast<float4*>(base_ptr + C::STAGES * C::STAGE_BYTES + (32 * C::EPI_COLS * 4) * (warp - 2));
+    uint32_t g = 0;
+    float vmax = 0.f;
+    float* const vm = p.c_amax ? &vmax : nullptr;
+    for (int t = blockIdx.x; t < pp.total_tiles; t += gridDim.x) {
+      const int z = t / tiles_mn, r = t - z * tiles_mn;
+      const int m0 = (r / pp.tiles_n) * BM, n0 = (r % pp.tiles_n) * BN;
+      const int kb_begin = z * p.kb_per_split;
+      const int num_kb = min(kb_total, kb_begin + p.kb_per_split) - kb_begin;
+      float acc[CPW];
+#pragma unroll
+      for (int j = 0; j < CPW; ++j) acc[j] = 0.f;
+      for (int kb = 0; kb < num_kb; ++g) {
+        const uint32_t b = g & 1u;
+        const int n = min(pp.chunk_kb, num_kb - kb);
+        const float comp = pp.comp_per_mma * (float)(n * (BK / UK) * 3);
+        mbar_wait(acc_full_bar(b), (g >> 1) & 1u);
+        tc_fence_after();
+#pragma unroll
+        for (int cc = 0; cc < NCH; ++cc) {
+          if (p.pair_flags & 2) break;             // experiment: no drain
+          uint32_t v[32];
+          tmem_ld32(t_lane + b * BN + (uint32_t)(cc * 32), v);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[cc * 32 + j] += fmaf(__uint_as_float(v[j]), comp, __uint_as_float(v[j]));
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_empty_bar(b));
+        kb += n;
+      }
+      // ---- epilogue: 32 rows x CPW columns of this warp, EPI_COLS at a time through the warp's staging tile
+      float* Cz = p.C + (size_t)z * p.slab_stride;
+      const bool vec = epilogue_vec_ok(p, Cz);
+      const int row = m0 + 32 * q + lane;
+      const int cw0 = n0 + half * CPW;
+#pragma unroll
+      for (int ps = 0; ps < CPW / C::EPI_COLS; ++ps) {
+        const int c0 = cw0 + ps * C::EPI_COLS;
+        if (c0 < p.N && !(p.pair_flags & 1)) {   // warp-uniform (flag: experiment without the stores)
+          if (vec) {
+#pragma unroll
+            for (int sl = 0; sl < C::EPI_COLS / 4; ++sl) {
+              const int j = ps * C::EPI_COLS + 4 * sl;
+              stage_put<C::EPI_COLS>(stg, lane, sl, acc[j] * inv, acc[j + 1] * inv, acc[j + 2] * inv, acc[j + 3] * inv);
+            }
+            __syncwarp();
+            store_staged<C::EPI_COLS>(p, Cz, stg, lane, m0 + 32 * q, c0, vm);
+            __syncwarp();
+          } else if (row < p.M) {
+            float f[32];
+#pragma unroll
+            for (int cc = 0; cc < C::EPI_COLS / 32; ++cc) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = acc[ps * C::EPI_COLS + cc * 32 + j] * inv;
+              store_row_scalar(p, Cz, row, c0 + cc * 32, f, vm);
+            }
+          }
+        }
+      }
+    }
+    if (p.c_amax) {
+      const uint32_t mx = __reduce_max_sync(0xffffffffu, __float_as_uint(vmax));
+      if (lane == 0 && mx) atomicMax(p.c_amax, mx);
     }
   }
   tc_fence_before();
@@ -1592,6 +1856,33 @@ static int launch_h3(cudaStream_t st, const CUtensorMap& tah, const CUtensorMap&
     configured = true;
   }
   gemm_tc_h3_kernel<BN><<<grid, X3_THREADS, C::SMEM_BYTES, st>>>(tah, tal, tbh, tbl, p);
+  return ADDK_OK;
+}
+
+static int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <int BN>
+static int launch_h3p(cudaStream_t st, const CUtensorMap& tah, const CUtensorMap& tal, const CUtensorMap& tbh,
+                      const CUtensorMap& tbl, ParamsP& pp, int M, int N, int split) {
+  using C = CfgP<BN>;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(gemm_tc_h3p_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES) != cudaSuccess) {
+      addk_set_error("gemm_tc: cannot raise the dynamic shared memory limit");
+      return ADDK_ERR_LAUNCH;
+    }
+    configured = true;
+  }
+  pp.tiles_m = (M + BM - 1) / BM; pp.tiles_n = (N + BN - 1) / BN; pp.total_tiles = pp.tiles_m * pp.tiles_n * split;
+  const int grid = pp.total_tiles < sm_count() ? pp.total_tiles : sm_count();
+  gemm_tc_h3p_kernel<BN><<<grid, X3_THREADS, C::SMEM_BYTES, st>>>(tah, tal, tbh, tbl, pp);
   return ADDK_OK;
 }
 
@@ -1633,7 +1924,7 @@ __global__ void h3_amax_kernel(const float* __restrict__ x, long long rows, int 
 __device__ __forceinline__ void h3_split1(float x, float s, uint16_t& hi, uint16_t& lo) {
   const float xs = x * s;                                   // exact (power of two)
   const __half h = __float2half_rn(xs);
-  const float r = (xs - __half2float(h)) * 2048.0f;         // exact difference, exact scaling
+  const float r = xs - __half2float(h);                     // exact difference
   hi = __half_as_ushort(h);
   lo = __half_as_ushort(__float2half_rn(r));
 }
@@ -1667,12 +1958,15 @@ __global__ void h3_split_kernel(const float* __restrict__ x, long long rows, int
   }
 }
 
-static int h3_convert(cudaStream_t st, const float* x, long long rows, int cols, int ld, void* hi, long long plane, uint32_t* slot) {
+static int h3_convert(cudaStream_t st, const float* x, long long rows, int cols, int ld, void* hi, long long plane, uint32_t* slot,
+                      bool have_amax = false) {
   if (!x || !hi || !slot || rows <= 0 || cols <= 0 || ld < cols || plane <= 0) { addk_set_error("f16x3 convert: bad arguments"); return ADDK_ERR_ARG; }
-  if (cudaMemsetAsync(slot, 0, sizeof(uint32_t), st) != cudaSuccess) { addk_set_error("f16x3 convert: memset failed"); return ADDK_ERR_LAUNCH; }
   const long long work = ld == cols ? (rows * cols / 4 + 255) / 256 : rows;
   const unsigned blocks = (unsigned)(work < 1 ? 1 : (work > 148 * 8 ? 148 * 8 : work));
-  h3_amax_kernel<<<blocks, 256, 0, st>>>(x, rows, cols, ld, slot);
+  if (!have_amax) {      // otherwise the producing dense layer left max|x| in the slot (addk_gemm_args::c_amax)
+    if (cudaMemsetAsync(slot, 0, sizeof(uint32_t), st) != cudaSuccess) { addk_set_error("f16x3 convert: memset failed"); return ADDK_ERR_LAUNCH; }
+    h3_amax_kernel<<<blocks, 256, 0, st>>>(x, rows, cols, ld, slot);
+  }
   h3_split_kernel<<<blocks, 256, 0, st>>>(x, rows, cols, ld, slot, reinterpret_cast<uint16_t*>(hi), reinterpret_cast<uint16_t*>(hi) + plane);
   return ADDK_OK;
 }
@@ -1721,7 +2015,7 @@ static int gemm_bf16(cudaStream_t st, const addk_gemm_args& a) {
   p.C = a.C; p.ldc = a.ldc; p.M = a.M; p.N = a.N; p.K = a.K; p.bias = a.bias; p.mask = a.relu_mask_src;
   p.ld_mask = a.ld_mask; p.relu = a.relu; p.accumulate = 0; p.kb_per_split = kb_per;
   p.slab_stride = a.slab_stride > 0 ? a.slab_stride : (long long)a.M * a.ldc;
-  p.pair_flags = 0; p.dbg = nullptr; p.C16 = a.C16;
+  p.pair_flags = 0; p.dbg = nullptr; p.C16 = a.C16; p.c_amax = nullptr;
   p.a_mn = a.trans_a ? 1 : 0;
   p.b_mn = a.trans_b ? 0 : 1;
   const int BN = a.N > 128 ? 256 : (a.N > 64 ? 128 : 64);
@@ -1769,14 +2063,15 @@ static int gemm_h3(cudaStream_t st, const addk_gemm_args& a) {
   // operand geometry as stored: A is [M,K] (trans_a = 0) or [K,M]; B is [N,K] (trans_b = 1) or [K,N]
   const long long a_rows = a.trans_a ? a.K : a.M, b_rows = a.trans_b ? a.N : a.K;
   const int a_cols = a.trans_a ? a.M : a.K, b_cols = a.trans_b ? a.K : a.N;
-  if (!a.a16_ready) { const int rc = h3_convert(st, a.A, a_rows, a_cols, a.lda, const_cast<void*>(a.A16), a.a16_plane, a.a_amax); if (rc != ADDK_OK) return rc; }
-  if (!a.b16_ready) { const int rc = h3_convert(st, a.B, b_rows, b_cols, a.ldb, const_cast<void*>(a.B16), a.b16_plane, a.b_amax); if (rc != ADDK_OK) return rc; }
+  if (a.a16_ready != 1) { const int rc = h3_convert(st, a.A, a_rows, a_cols, a.lda, const_cast<void*>(a.A16), a.a16_plane, a.a_amax, a.a16_ready == 2); if (rc != ADDK_OK) return rc; }
+  if (a.b16_ready != 1) { const int rc = h3_convert(st, a.B, b_rows, b_cols, a.ldb, const_cast<void*>(a.B16), a.b16_plane, a.b_amax, a.b16_ready == 2); if (rc != ADDK_OK) return rc; }
   ParamsH3 ph;
   Params& p = ph.p;
   p.C = a.C; p.ldc = a.ldc; p.M = a.M; p.N = a.N; p.K = a.K; p.bias = a.bias; p.mask = a.relu_mask_src;
   p.ld_mask = a.ld_mask; p.relu = a.relu; p.accumulate = a.accumulate; p.kb_per_split = kb_per;
   p.slab_stride = a.slab_stride > 0 ? a.slab_stride : (long long)a.M * a.ldc;
-  p.pair_flags = 0; p.dbg = nullptr; p.C16 = nullptr;
+  { const char* e = getenv("ADDK_H3_FLAGS"); p.pair_flags = e ? atoi(e) : 0; }
+  p.dbg = nullptr; p.C16 = nullptr; p.c_amax = split == 1 ? a.c_amax : nullptr;
   p.a_mn = a.trans_a ? 1 : 0;
   p.b_mn = a.trans_b ? 0 : 1;
   ph.a_amax = a.a_amax; ph.b_amax = a.b_amax; ph.comp_per_mma = addk_h3_comp();
@@ -1790,6 +2085,14 @@ static int gemm_h3(cudaStream_t st, const addk_gemm_args& a) {
                      : (make_map_f16(&tbh, Bh, a.K, a.N, a.ldb, BKh, BN) && make_map_f16(&tbl, Bl, a.K, a.N, a.ldb, BKh, BN)));
   if (!ok) { addk_set_error("gemm f16x3: cuTensorMapEncodeTiled rejected an operand"); return ADDK_ERR_ARG; }
   dim3 grid((a.N + BN - 1) / BN, (a.M + BM - 1) / BM, split);
+  static int persistent = -1;
+  if (persistent < 0) { const char* e = getenv("ADDK_H3_PERSISTENT"); persistent = e ? atoi(e) : 1; }
+  if (BN == 256 && persistent) {
+    ParamsP pp;
+    pp.p = p; pp.a_amax = a.a_amax; pp.b_amax = a.b_amax; pp.comp_per_mma = ph.comp_per_mma;
+    { static int ck = 0; if (!ck) { const char* e = getenv("ADDK_H3_CHUNK_KB"); ck = e ? atoi(e) : H3P_CHUNK_KB; if (ck < 1) ck = 1; } pp.chunk_kb = ck; }
+    return launch_h3p<256>(st, tah, tal, tbh, tbl, pp, a.M, a.N, split);
+  }
   if (BN == 256) return launch_h3<256>(st, tah, tal, tbh, tbl, ph, grid);
   if (BN == 128) return launch_h3<128>(st, tah, tal, tbh, tbl, ph, grid);
   return launch_h3<64>(st, tah, tal, tbh, tbl, ph, grid);
@@ -1847,7 +2150,7 @@ int addk_gemm_tc(cudaStream_t st, const addk_gemm_args& a, int precision) {
   p.slab_stride = a.slab_stride > 0 ? a.slab_stride : (long long)a.M * a.ldc;
   { const char* e = getenv("ADDK_TC_PAIR_FLAGS"); p.pair_flags = e ? atoi(e) : 2; }
   { const char* e = getenv("ADDK_TC_DBG"); p.dbg = e ? (long long*)strtoull(e, nullptr, 0) : nullptr; }
-  p.C16 = nullptr;
+  p.C16 = nullptr; p.c_amax = nullptr;
   p.a_mn = a.trans_a ? 1 : 0;          // A given as [K,M]: rows are the contraction index
   p.b_mn = a.trans_b ? 0 : 1;          // B given as [K,N]
   const int BN = a.N > 128 ? 256 : (a.N > 64 ? 128 : 64);

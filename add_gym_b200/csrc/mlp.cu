@@ -494,7 +494,7 @@ static thread_local const addk_update_ctx* g_twin_ctx = nullptr;
 // gradient AND the weight gradient).  This table is host-side bookkeeping in ISSUE order; the kernels themselves are
 // stream-ordered, so a twin may only be shared by calls on one stream -- tensors read by several chains (xn, dn, the
 // parameters) are converted before the streams fork.  Slot 0 belongs to the flat parameter vector.
-struct TwinEnt { const float* p; long long rows; int cols, ld; cudaStream_t st; bool valid, shared; };
+struct TwinEnt { const float* p; long long rows; int cols, ld; cudaStream_t st; bool valid, shared, amax_known; };
 static thread_local TwinEnt g_tw[63];
 static thread_local int g_ntw = 0;
 static void twin_reset() { g_ntw = 0; }
@@ -502,7 +502,7 @@ static void twin_invalidate(const void* p, size_t bytes) {
   const char* b = (const char*)p;
   for (int i = 0; i < g_ntw; ++i) {
     const char* q = (const char*)g_tw[i].p;
-    if (q >= b && q < b + (bytes ? bytes : 1)) g_tw[i].valid = false;
+    if (q >= b && q < b + (bytes ? bytes : 1)) { g_tw[i].valid = false; g_tw[i].amax_known = false; }
   }
 }
 struct H3Op { const void* hi; long long plane; uint32_t* amax; int ready; };
@@ -523,12 +523,14 @@ static H3Op h3_operand(const addk_update_ctx& c, cudaStream_t st, const float* p
   if (e < 0) {
     if (g_ntw >= 63) return o;
     e = g_ntw++;
-    g_tw[e] = TwinEnt{p, 0, 0, 0, nullptr, false, false};
+    g_tw[e] = TwinEnt{p, 0, 0, 0, nullptr, false, false, false};
   }
   TwinEnt& t = g_tw[e];
   o.hi = (const uint16_t*)c.arena16 + (p - a0); o.plane = c.arena_elems; o.amax = slots + 1 + e;
   if (t.valid && t.cols == cols && t.ld == ld && rows <= t.rows && (t.st == st || t.shared)) { o.ready = 1; return o; }
-  t.rows = rows; t.cols = cols; t.ld = ld; t.st = st; t.valid = true; t.shared = false;   // the call about to be issued converts it
+  // the call about to be issued converts it; the max pass is skipped when the producing dense layer left max|x| behind
+  if (t.amax_known && t.cols == cols && t.ld == ld && rows <= t.rows && t.st == st) o.ready = 2;
+  t.rows = rows; t.cols = cols; t.ld = ld; t.st = st; t.valid = true; t.shared = false; t.amax_known = false;
   return o;
 }
 extern "C" int addk_f16x3_convert(void* stream, const float* x, long long rows, int cols, int ld, void* hi16, long long plane,
@@ -538,7 +540,7 @@ static int h3_prepare(const addk_update_ctx& c, cudaStream_t st, const float* p,
   H3Op o = h3_operand(c, st, p, rows, cols, ld);
   if (!o.hi) { addk_set_error("f16x3: tensor has no twin"); return ADDK_ERR_ARG; }
   for (int i = 0; i < g_ntw; ++i) if (g_tw[i].p == p) g_tw[i].shared = true;     // converted before the fork: any stream may read it
-  if (o.ready) return ADDK_OK;
+  if (o.ready == 1) return ADDK_OK;
   return addk_f16x3_convert(st, p, rows, cols, ld, const_cast<void*>(o.hi), o.plane, o.amax);
 }
 // the fp16 planes of the whole flat parameter vector (one scale: slot 0)
@@ -569,7 +571,7 @@ static int gemm(cudaStream_t st, int prec, const float* A, int lda, int ta, cons
                 long long slab_stride = 0) {
   addk_gemm_args a;
   a.A16 = prec == 3 ? twin16(A) : nullptr; a.B16 = prec == 3 ? twin16(B) : nullptr; a.C16 = prec == 3 ? twin16(C) : nullptr;
-  a.a16_plane = a.b16_plane = 0; a.a_amax = a.b_amax = nullptr; a.a16_ready = a.b16_ready = 0;
+  a.a16_plane = a.b16_plane = 0; a.a_amax = a.b_amax = a.c_amax = nullptr; a.a16_ready = a.b16_ready = 0;
   a.A = A; a.lda = lda; a.B = B; a.ldb = ldb; a.C = C; a.ldc = ldc; a.M = M; a.N = N; a.K = K;
   a.bias = bias; a.a_mean = nmean; a.a_std = nstd; a.relu_mask_src = mask; a.ld_mask = ld_mask;
   a.trans_a = ta; a.trans_b = tb; a.relu = relu; a.split_k = split; a.accumulate = 0; a.slab_stride = slab_stride;
@@ -586,6 +588,23 @@ static int gemm(cudaStream_t st, int prec, const float* A, int lda, int ta, cons
       }
     }
     twin_invalidate(C, (size_t)(split > 1 ? 1 : M) * ldc * sizeof(float));
+    if (a.A16 && split == 1) {      // the f16x3 kernel runs: let its epilogue leave max|C| in C's slot for C's first reader
+      const addk_update_ctx& c = *g_twin_ctx;
+      const float* a0 = (const float*)c.arena;
+      if (a0 && C >= a0 && C < a0 + c.arena_elems) {
+        int e = -1;
+        for (int i = 0; i < g_ntw; ++i) if (g_tw[i].p == C) { e = i; break; }
+        if (e < 0 && g_ntw < 63) { e = g_ntw++; g_tw[e] = TwinEnt{C, 0, 0, 0, nullptr, false, false, false}; }
+        if (e >= 0) {
+          uint32_t* slot = (uint32_t*)c.amax_slots + 1 + e;
+          if (cudaMemsetAsync(slot, 0, sizeof(uint32_t), st) == cudaSuccess) {
+            TwinEnt& t = g_tw[e];
+            t.rows = M; t.cols = N; t.ld = ldc; t.st = st; t.valid = false; t.shared = false; t.amax_known = true;
+            a.c_amax = slot;
+          }
+        }
+      }
+    }
   }
   int rc = prec == 0 ? addk::sgemm_launch(st, a) : addk_gemm_tc(st, a, prec);
   if (rc != ADDK_OK) return rc;

@@ -200,7 +200,9 @@ typedef struct addk_gemm_args {
    * holds this operand (converted by an earlier call).  NULL twins -> the call runs in tf32x3. */
   int64_t a16_plane, b16_plane;
   uint32_t* a_amax; uint32_t* b_amax;
-  int32_t a16_ready, b16_ready;
+  int32_t a16_ready, b16_ready;      /* 0 convert (max pass + split pass) | 1 twin ready | 2 *amax valid: split pass only */
+  uint32_t* c_amax;                  /* optional, single-slab calls: atomicMax of the bit patterns of |C| as stored, so a
+                                      * later call that reads C can pass ready = 2; the caller zeroes the word first */
 } addk_gemm_args;
 int addk_gemm(void* stream, const addk_gemm_args* args_host, int precision);
 /* precision "f16x3": max|x| of the [rows, cols] fp32 tensor x (pitch ld) -> *amax_slot (bit pattern), then the two

@@ -144,7 +144,8 @@ class _Twin:
         self.amax = torch.zeros(1, device=t.device, dtype=torch.int32)
 
 
-def _gemm_h3(A, B, Cout, M, N, K, ta, tb, tw_a, tw_b, ready=(0, 0), bias=None, relu=0, mask=None, split=1, accumulate=0):
+def _gemm_h3(A, B, Cout, M, N, K, ta, tb, tw_a, tw_b, ready=(0, 0), bias=None, relu=0, mask=None, split=1, accumulate=0,
+             c_amax=None):
     from add_gym_b200 import _lib
     a = _lib.AddkGemmArgs(A=A.data_ptr(), lda=A.stride(0), B=B.data_ptr(), ldb=B.stride(0), C=Cout.data_ptr(),
                           ldc=Cout.stride(-2), M=M, N=N, K=K, bias=bias.data_ptr() if bias is not None else None,
@@ -152,7 +153,8 @@ def _gemm_h3(A, B, Cout, M, N, K, ta, tb, tw_a, tw_b, ready=(0, 0), bias=None, r
                           ld_mask=mask.stride(0) if mask is not None else 0, trans_a=ta, trans_b=tb, relu=relu,
                           split_k=split, accumulate=accumulate, slab_stride=0, A16=tw_a.planes.data_ptr(),
                           B16=tw_b.planes.data_ptr(), C16=None, a16_plane=tw_a.n, b16_plane=tw_b.n,
-                          a_amax=tw_a.amax.data_ptr(), b_amax=tw_b.amax.data_ptr(), a16_ready=ready[0], b16_ready=ready[1])
+                          a_amax=tw_a.amax.data_ptr(), b_amax=tw_b.amax.data_ptr(), a16_ready=ready[0], b16_ready=ready[1],
+                          c_amax=c_amax.data_ptr() if c_amax is not None else None)
     _lib.check(_lib.lib().addk_gemm(_lib.stream(), C.byref(a), C.c_int(_lib.PRECISIONS["f16x3"])), "addk_gemm")
 
 
@@ -195,6 +197,17 @@ def test_gemm_f16x3_epilogues_split_k_and_reuse():
     out2 = torch.empty(M, N, device="cuda")
     _gemm_h3(A, W, out2, M, N, K, 0, 1, tA, tW, ready=(1, 1), bias=bias, relu=1)
     assert torch.equal(out, out2)
+    # the epilogue can leave max|C| behind, so that the next layer's conversion of C skips its max pass (ready = 2)
+    tOut = _Twin(out)
+    out3 = torch.empty(M, N, device="cuda")
+    _gemm_h3(A, W, out3, M, N, K, 0, 1, tA, tW, ready=(1, 1), bias=bias, relu=1, c_amax=tOut.amax)
+    torch.cuda.synchronize()
+    assert torch.equal(out3, out)
+    assert int(tOut.amax.item()) == int(out.abs().max().view(torch.int32).item()), "max|C| word written by the epilogue"
+    W2 = torch.randn(256, N, device="cuda", generator=g) * 0.05
+    y = torch.empty(M, 256, device="cuda")
+    _gemm_h3(out, W2, y, M, 256, N, 0, 1, tOut, _Twin(W2), ready=(2, 0))
+    assert _rel(y, out.double() @ W2.double().t()) <= TOL["f16x3"]
     h = torch.randn(M, K, device="cuda", generator=g)
     dY = torch.randn(M, N, device="cuda", generator=g) * 1e-6          # gradient-sized values: far below fp16's range unscaled
     dX = torch.empty(M, K, device="cuda")

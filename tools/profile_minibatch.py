@@ -21,11 +21,16 @@ a._rollout_train(a._steps_per_iter)
 a._build_train_data()
 torch.cuda.synchronize()
 _lib.launch_count(reset=True)
+import time
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+idxs = [a._exp_buffer.sample_indices(a._mb_rows) for _ in range(steps)]
+torch.cuda.synchronize()
 e0.record()
+t0 = time.perf_counter()
 for s in range(steps):
-    idx = a._exp_buffer.sample_indices(a._mb_rows)
-    _lib.check(_lib.lib().addk_update_minibatch(_lib.stream(), a._ctx.buf, _lib.ptr(idx), C.c_int(s), C.c_int(s + 1)), "mb")
+    _lib.check(_lib.lib().addk_update_minibatch(_lib.stream(), a._ctx.buf, _lib.ptr(idxs[s]), C.c_int(s % a._max_steps), C.c_int(s + 1)), "mb")
+host_ms = (time.perf_counter() - t0) * 1e3 / steps
 e1.record()
 torch.cuda.synchronize()
+print("host issue ms/step: %.3f" % host_ms)
 print("minibatch ms:", e0.elapsed_time(e1) / steps, "launches/step:", _lib.launch_count() / steps, "loss", float(a._ws["info"][0, 0]))
