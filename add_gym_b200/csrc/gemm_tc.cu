@@ -216,6 +216,50 @@ __device__ __forceinline__ void store_staged(const Params& p, float* Cz, const f
   }
 }
 
+// The same walk for a sub-tile that lies completely inside the matrix and does not accumulate: no bounds checks, one
+// pointer increment per store.  (ncu on the persistent f16x3 kernel: the general version above executes ~300
+// instructions per 16-byte store -- 64-bit address arithmetic, constant-bank reloads and tail predicates -- which made
+// the epilogue of a 128 x 256 tile 17.7k cycles and instruction-bound.)
+template <int CW, bool MASK>
+__device__ __forceinline__ void store_staged_interior(const Params& p, float* __restrict__ Cz, const float4* stg, int lane,
+                                                      int grow0, int col0, float* vmax) {
+  constexpr int S = CW / 4;                        // float4 slots per row
+  static_assert(S <= 32 && 32 % S == 0, "one store instruction covers 32 / S whole rows");
+  constexpr int RPI = 32 / S;
+  const int sub_r = lane / S, sl = lane % S;
+  const int col = col0 + 4 * sl;
+  float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (p.bias) bb = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+  const bool relu = p.relu != 0;
+  float* dst = Cz + (size_t)(grow0 + sub_r) * p.ldc + col;
+  const float* mk = MASK ? p.mask + (size_t)(grow0 + sub_r) * p.ld_mask + col : nullptr;
+  const size_t dstep = (size_t)RPI * p.ldc, mstep = MASK ? (size_t)RPI * p.ld_mask : 0;
+  float vm = 0.f;
+#pragma unroll
+  for (int i0 = 0; i0 < 32 / RPI; i0 += 8) {
+    float4 m4[8];
+    if (MASK) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) m4[u] = __ldg(reinterpret_cast<const float4*>(mk + (size_t)(i0 + u) * mstep));
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int r = (i0 + u) * RPI + sub_r;
+      float4 o = stg[r * S + (sl ^ (r & 7))];
+      o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+      if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+      if (MASK) {
+        o.x = m4[u].x > 0.f ? o.x : 0.f; o.y = m4[u].y > 0.f ? o.y : 0.f;
+        o.z = m4[u].z > 0.f ? o.z : 0.f; o.w = m4[u].w > 0.f ? o.w : 0.f;
+      }
+      *reinterpret_cast<float4*>(dst) = o;
+      dst += dstep;
+      vm = fmaxf(fmaxf(vm, fmaxf(fabsf(o.x), fabsf(o.y))), fmaxf(fabsf(o.z), fabsf(o.w)));
+    }
+  }
+  if (vmax) *vmax = fmaxf(*vmax, vm);
+}
+
 // row-per-lane scalar fallback for outputs that are not 16-byte aligned (ldc % 4 != 0)
 __device__ __forceinline__ void store_row_scalar(const Params& p, float* Cz, int row, int cbase, const float* acc32,
                                                  float* vmax = nullptr) {
@@ -1713,20 +1757,27 @@ gemm_tc_h3p_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
     constexpr uint64_t LO16 = (C::A_BYTES + C::B_BYTES) >> 4, STAGE16 = C::STAGE_BYTES >> 4;
     const bool issuer = elect_one();
     uint32_t it = 0, g = 0;
+    long long* const dbg = (p.dbg && blockIdx.x == 0) ? p.dbg : nullptr;
+    long long w_empty = 0, w_full = 0;
+    const long long t_begin = clock64();
     for (int t = blockIdx.x; t < pp.total_tiles; t += gridDim.x) {
       const int z = t / tiles_mn;
       const int kb_begin = z * p.kb_per_split;
       const int num_kb = min(kb_total, kb_begin + p.kb_per_split) - kb_begin;
       for (int kb = 0; kb < num_kb; ++g) {
         const uint32_t b = g & 1u;
+        const long long c0 = dbg ? clock64() : 0;
         mbar_wait(acc_empty_bar(b), ((g >> 1) & 1u) ^ 1u);      // the workers have copied chunk g-2 out of this buffer
+        if (dbg) w_empty += clock64() - c0;
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + b * BN;
         const int n = min(pp.chunk_kb, num_kb - kb);
         uint32_t acc = 0;
         for (int j = 0; j < n; ++j, ++it) {
           const int s = (int)(it % C::STAGES);
+          const long long c1 = dbg ? clock64() : 0;
           mbar_wait(full_bar(s), (it / C::STAGES) & 1u);
+          if (dbg) w_full += clock64() - c1;
           tc_fence_after();
           if (issuer) {
             const uint64_t dah = dA0 + (uint64_t)s * STAGE16, dbh = dB0 + (uint64_t)s * STAGE16;
@@ -1746,6 +1797,7 @@ gemm_tc_h3p_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
         kb += n;
       }
     }
+    if (dbg && lane == 0) { dbg[0] = clock64() - t_begin; dbg[1] = w_empty; dbg[2] = w_full; }
   } else {
     // ===================== workers: chunk drains + epilogue =====================
     const int q = warp & 3;
@@ -1759,6 +1811,9 @@ gemm_tc_h3p_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
     uint32_t g = 0;
     float vmax = 0.f;
     float* const vm = p.c_amax ? &vmax : nullptr;
+    long long* const dbg = (p.dbg && blockIdx.x == 0 && warp == 2) ? p.dbg : nullptr;
+    long long w_accfull = 0, t_drain = 0, t_epi = 0;
+    const long long t_begin = clock64();
     for (int t = blockIdx.x; t < pp.total_tiles; t += gridDim.x) {
       const int z = t / tiles_mn, r = t - z * tiles_mn;
       const int m0 = (r / pp.tiles_n) * BM, n0 = (r % pp.tiles_n) * BN;
@@ -1771,7 +1826,9 @@ gemm_tc_h3p_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
         const uint32_t b = g & 1u;
         const int n = min(pp.chunk_kb, num_kb - kb);
         const float comp = pp.comp_per_mma * (float)(n * (BK / UK) * 3);
+        const long long c0 = dbg ? clock64() : 0;
         mbar_wait(acc_full_bar(b), (g >> 1) & 1u);
+        const long long c1 = dbg ? clock64() : 0;
         tc_fence_after();
 #pragma unroll
         for (int cc = 0; cc < NCH; ++cc) {
@@ -1784,8 +1841,10 @@ gemm_tc_h3p_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(acc_empty_bar(b));
+        if (dbg) { w_accfull += c1 - c0; t_drain += clock64() - c1; }
         kb += n;
       }
+      const long long c2 = dbg ? clock64() : 0;
       // ---- epilogue: 32 rows x CPW columns of this warp, EPI_COLS at a time through the warp's staging tile
       float* Cz = p.C + (size_t)z * p.slab_stride;
       const bool vec = epilogue_vec_ok(p, Cz);
@@ -1802,7 +1861,12 @@ gemm_tc_h3p_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
               stage_put<C::EPI_COLS>(stg, lane, sl, acc[j] * inv, acc[j + 1] * inv, acc[j + 2] * inv, acc[j + 3] * inv);
             }
             __syncwarp();
-            store_staged<C::EPI_COLS>(p, Cz, stg, lane, m0 + 32 * q, c0, vm);
+            if (m0 + 32 * q + 32 <= p.M && c0 + C::EPI_COLS <= p.N && !p.accumulate) {     // warp-uniform
+              if (p.mask) store_staged_interior<C::EPI_COLS, true>(p, Cz, stg, lane, m0 + 32 * q, c0, vm);
+              else store_staged_interior<C::EPI_COLS, false>(p, Cz, stg, lane, m0 + 32 * q, c0, vm);
+            } else {
+              store_staged<C::EPI_COLS>(p, Cz, stg, lane, m0 + 32 * q, c0, vm);
+            }
             __syncwarp();
           } else if (row < p.M) {
             float f[32];
@@ -1815,7 +1879,9 @@ gemm_tc_h3p_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
           }
         }
       }
+      if (dbg) t_epi += clock64() - c2;
     }
+    if (dbg && lane == 0) { dbg[3] = clock64() - t_begin; dbg[4] = w_accfull; dbg[5] = t_drain; dbg[6] = t_epi; }
     if (p.c_amax) {
       const uint32_t mx = __reduce_max_sync(0xffffffffu, __float_as_uint(vmax));
       if (lane == 0 && mx) atomicMax(p.c_amax, mx);
@@ -2071,7 +2137,7 @@ static int gemm_h3(cudaStream_t st, const addk_gemm_args& a) {
   p.ld_mask = a.ld_mask; p.relu = a.relu; p.accumulate = a.accumulate; p.kb_per_split = kb_per;
   p.slab_stride = a.slab_stride > 0 ? a.slab_stride : (long long)a.M * a.ldc;
   { const char* e = getenv("ADDK_H3_FLAGS"); p.pair_flags = e ? atoi(e) : 0; }
-  p.dbg = nullptr; p.C16 = nullptr; p.c_amax = split == 1 ? a.c_amax : nullptr;
+  { const char* e = getenv("ADDK_TC_DBG"); p.dbg = e ? (long long*)strtoull(e, nullptr, 0) : nullptr; } p.C16 = nullptr; p.c_amax = split == 1 ? a.c_amax : nullptr;
   p.a_mn = a.trans_a ? 1 : 0;
   p.b_mn = a.trans_b ? 0 : 1;
   ph.a_amax = a.a_amax; ph.b_amax = a.b_amax; ph.comp_per_mma = addk_h3_comp();

@@ -69,5 +69,8 @@ if os.environ.get("ADDK_TC_STAMPS"):
     torch.cuda.synchronize()
     del os.environ["ADDK_TC_DBG"]
     t = dbg.tolist()
+    if H3:
+        print("h3p CTA 0 (cycles): mma loop %d, waiting acc_empty %d, waiting stage full %d | worker loop %d, waiting acc_full %d, drains %d, epilogues %d" % tuple(t[:7]))
+        sys.exit(0)
     names = ["entry", "setup done", "first stage ready", "all MMAs issued", "accumulator complete", "epilogue done", "cluster exit"]
     print("stamps (cycles since entry): " + ", ".join("%s %d" % (n, t[i] - t[0]) for i, n in enumerate(names)))
