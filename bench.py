@@ -1,6 +1,6 @@
 """bench.py -- add-gym rollout + update hot path on B200 (contract: see DESIGN.md "Measurement").
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--envs 4096] [--precision fp32|tf32x3|tf32|bf16]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--envs 4096] [--precision f16x3|tf32x3|fp32|tf32|bf16]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
     python bench.py --impl reference ...        # the reference's CPU implementation (oracle port), host cores
@@ -33,8 +33,9 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--envs", type=int, default=4096, help="envs per GPU (BASELINE configs[1]: 4096)")
-    ap.add_argument("--precision", default="tf32x3", choices=["fp32", "tf32x3", "tf32", "bf16", "f16x3"],
-                    help="MLP arithmetic: tf32x3 = tcgen05 3-pass split (fp32-parity mode, default); fp32 = CUDA cores; tf32 = single pass")
+    ap.add_argument("--precision", default="f16x3", choices=["fp32", "tf32x3", "tf32", "bf16", "f16x3"],
+                    help="MLP arithmetic: f16x3 = tcgen05 kind::f16 on fp16 hi/lo planes (fp32-parity mode, default); tf32x3 = "
+                         "kind::tf32 3-pass split (fp32 parity); fp32 = CUDA cores; tf32 = single pass; bf16 = config 4")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-envs", type=int, default=512, help="envs of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -217,9 +217,10 @@ def test_full_size_rollout_steps_match_oracle(num_envs):
     assert int((oracle.buf["done"][:4] != 0).sum()) > 0, "the case must exercise resets"
 
 
-def test_full_size_update_tensor_core_vs_cuda_core_gradients():
-    """One optimizer step at the full minibatch (16384 rows) computed twice by independent arithmetic: the tcgen05 tf32x3
-    tiles and the exact-fp32 CUDA-core kernel.  Gradients must agree to 1e-5 (median tensor) with a ReLU-flip allowance
+@pytest.mark.parametrize("tc_mode", ["f16x3", "tf32x3"])
+def test_full_size_update_tensor_core_vs_cuda_core_gradients(tc_mode):
+    """One optimizer step at the full minibatch (16384 rows) computed twice by independent arithmetic: the tcgen05
+    fp32-parity tiles (f16x3: fp16 hi/lo planes; tf32x3) and the exact-fp32 CUDA-core kernel.  Gradients must agree to 1e-5 (median tensor) with a ReLU-flip allowance
     for the worst one, the loss terms to 1e-5; the same call repeated must reproduce itself bit for bit."""
     from add_gym_b200 import _lib
     from add_gym_b200.add_agent import ADDAgent
@@ -244,12 +245,12 @@ def test_full_size_update_tensor_core_vs_cuda_core_gradients():
         names, tensors = a._model.trainable()
         return {n: out[0][0][a._model.offsets["o_" + n]:a._model.offsets["o_" + n] + t.numel()].clone() for n, t in zip(names, tensors)}, out[0][1]
 
-    g1, i1 = grads("tf32x3")
+    g1, i1 = grads(tc_mode)
     g0, i0 = grads("fp32")
     for k in range(13):
         assert abs(float(i1[k]) - float(i0[k])) <= 2e-5 * max(1.0, abs(float(i0[k]))), (k, float(i1[k]), float(i0[k]))
     errs = {n: _rel(g1[n], g0[n]) for n in g0}
-    print("full-size gradient agreement tf32x3 vs fp32:", {k: "%.1e" % v for k, v in errs.items()})
+    print("full-size gradient agreement %s vs fp32:" % tc_mode, {k: "%.1e" % v for k, v in errs.items()})
     assert float(np.median(list(errs.values()))) <= 5e-5
     assert max(errs.values()) <= 5e-3, "beyond a few ReLU boundary flips (1/sqrt(8M active units) = 3.5e-4 each)"
 
