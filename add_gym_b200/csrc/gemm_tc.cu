@@ -45,7 +45,10 @@ struct Params {
   void* C16;                   // bf16 kernel: optional bf16 copy of the output (same leading dimension)
   long long* dbg;              // experiment: clock64 stamps of CTA (0,0,0) of the pair kernel (env ADDK_TC_DBG = address)
   int pair_flags;              // CTA-pair kernel experiments: bit0 cluster-scope waits, bit1 relaxed remote arrives
-  uint32_t* c_amax;            // f16x3 kernels: atomicMax of the bit patterns of |C| as stored (NULL: not wanted)
+  uint32_t* c_amax;            // f16x3 kernels: slot {W, max} of C: atomicMax of the bit patterns of |C| as stored into [1]
+  uint16_t* c_hi;              // f16x3 persistent kernel: fp16 planes of C written by the epilogue with the scale of the
+  long long c_plane;           //   slot's sticky word W (NULL: not wanted); lo plane c_plane elements after the hi plane
+  float c_scale;               // device-side only: filled in by the kernel
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -119,6 +122,22 @@ __device__ __forceinline__ bool elect_one() {
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(pred));
   return pred != 0;
+}
+
+// f16x3: x * s -> (hi, lo) fp16 pair, four at a time (see the f16x3 section below)
+__device__ __forceinline__ void h3_split4(const float4& o, float s, uint2& h, uint2& l) {
+  const float x0 = o.x * s, x1 = o.y * s, x2 = o.z * s, x3 = o.w * s;
+  const __half2 h01 = __floats2half2_rn(x0, x1), h23 = __floats2half2_rn(x2, x3);
+  const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+  const __half2 l01 = __floats2half2_rn(x0 - f01.x, x1 - f01.y), l23 = __floats2half2_rn(x2 - f23.x, x3 - f23.y);
+  h = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+  l = make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
+}
+__device__ __forceinline__ void h3_emit1(const Params& p, size_t off, float v) {
+  const float xs = v * p.c_scale;
+  const __half h = __float2half_rn(xs);
+  p.c_hi[off] = __half_as_ushort(h);
+  p.c_hi[p.c_plane + off] = __half_as_ushort(__float2half_rn(xs - __half2float(h)));
 }
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
@@ -201,6 +220,13 @@ __device__ __forceinline__ void store_staged(const Params& p, float* Cz, const f
           o.x += a4[u].x; o.y += a4[u].y; o.z += a4[u].z; o.w += a4[u].w;
           *reinterpret_cast<float4*>(dstp) = o;
           if (vmax) *vmax = fmaxf(fmaxf(*vmax, fmaxf(fabsf(o.x), fabsf(o.y))), fmaxf(fabsf(o.z), fabsf(o.w)));
+          if (p.c_hi) {
+            uint2 h, l;
+            h3_split4(o, p.c_scale, h, l);
+            const size_t off = (size_t)grow * p.ldc + col;
+            *reinterpret_cast<uint2*>(p.c_hi + off) = h;
+            *reinterpret_cast<uint2*>(p.c_hi + p.c_plane + off) = l;
+          }
         } else {
           const float oo[4] = {o.x, o.y, o.z, o.w};
           for (int e = 0; e < 4 && col + e < p.N; ++e) {
@@ -209,6 +235,7 @@ __device__ __forceinline__ void store_staged(const Params& p, float* Cz, const f
             if (p.accumulate) xv += dstp[e];
             dstp[e] = xv;
             if (vmax) *vmax = fmaxf(*vmax, fabsf(xv));
+            if (p.c_hi) h3_emit1(p, (size_t)grow * p.ldc + col + e, xv);
           }
         }
       }
@@ -220,7 +247,7 @@ __device__ __forceinline__ void store_staged(const Params& p, float* Cz, const f
 // pointer increment per store.  (ncu on the persistent f16x3 kernel: the general version above executes ~300
 // instructions per 16-byte store -- 64-bit address arithmetic, constant-bank reloads and tail predicates -- which made
 // the epilogue of a 128 x 256 tile 17.7k cycles and instruction-bound.)
-template <int CW, bool MASK>
+template <int CW, bool MASK, bool PLANES>
 __device__ __forceinline__ void store_staged_interior(const Params& p, float* __restrict__ Cz, const float4* stg, int lane,
                                                       int grow0, int col0, float* vmax) {
   constexpr int S = CW / 4;                        // float4 slots per row
@@ -232,6 +259,8 @@ __device__ __forceinline__ void store_staged_interior(const Params& p, float* __
   if (p.bias) bb = __ldg(reinterpret_cast<const float4*>(p.bias + col));
   const bool relu = p.relu != 0;
   float* dst = Cz + (size_t)(grow0 + sub_r) * p.ldc + col;
+  uint16_t* dhi = PLANES ? p.c_hi + (size_t)(grow0 + sub_r) * p.ldc + col : nullptr;
+  const float cs = p.c_scale;
   const float* mk = MASK ? p.mask + (size_t)(grow0 + sub_r) * p.ld_mask + col : nullptr;
   const size_t dstep = (size_t)RPI * p.ldc, mstep = MASK ? (size_t)RPI * p.ld_mask : 0;
   float vm = 0.f;
@@ -254,6 +283,13 @@ __device__ __forceinline__ void store_staged_interior(const Params& p, float* __
       }
       *reinterpret_cast<float4*>(dst) = o;
       dst += dstep;
+      if (PLANES) {
+        uint2 h, l;
+        h3_split4(o, cs, h, l);
+        *reinterpret_cast<uint2*>(dhi) = h;
+        *reinterpret_cast<uint2*>(dhi + p.c_plane) = l;
+        dhi += dstep;
+      }
       vm = fmaxf(fmaxf(vm, fmaxf(fabsf(o.x), fabsf(o.y))), fmaxf(fabsf(o.z), fabsf(o.w)));
     }
   }
@@ -276,6 +312,7 @@ __device__ __forceinline__ void store_row_scalar(const Params& p, float* Cz, int
       if (p.accumulate) xv += dstp[j];
       dstp[j] = xv;
       if (vmax) *vmax = fmaxf(*vmax, fabsf(xv));
+      if (p.c_hi) h3_emit1(p, (size_t)row * p.ldc + col, xv);
     }
   }
 }
@@ -1408,6 +1445,21 @@ __device__ __forceinline__ void h3_scale(uint32_t amax_bits, float& s, float& in
   inv_s = __uint_as_float((uint32_t)(E - 14) << 23);
 }
 
+// A twin's slot is two words {W, max}: max = bit pattern of max|x|, W = a sticky scale word.  The scale in force is that
+// of W while max|x| * s(W) stays inside [2^9, 2^15) -- so a dense layer can write the planes of its OUTPUT in its
+// epilogue with the scale its previous output had, before max|x| is known -- and that of 4 * max|x| otherwise (the
+// planes are then rewritten by h3_repair_kernel).  Every reader derives the scale from the two words the same way.
+__device__ __forceinline__ uint32_t h3_eff_word(uint32_t W, uint32_t amax) {
+  const int Ew = (int)((W >> 23) & 0xFFu), Ea = (int)((amax >> 23) & 0xFFu);
+  const int d = Ea - Ew + 14;                                  // floor(log2(max|x| * s(W)))
+  if (W != 0u && Ew >= 16 && Ew <= 250 && d >= 9 && d <= 14) return W;
+  const int En = Ea + 2 > 250 ? 250 : Ea + 2;
+  return (amax & 0x007FFFFFu) | ((uint32_t)En << 23);
+}
+__device__ __forceinline__ void h3_slot_scale(const uint32_t* slot, float& s, float& inv_s) {
+  h3_scale(slot ? h3_eff_word(slot[0], slot[1]) : 0x3F800000u, s, inv_s);
+}
+
 struct ParamsH3 {
   Params p;
   const uint32_t* a_amax; const uint32_t* b_amax;
@@ -1577,8 +1629,8 @@ gemm_tc_h3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
     float sa, sb, ia, ib;
-    h3_scale(ph.a_amax ? *ph.a_amax : 0x3F800000u, sa, ia);
-    h3_scale(ph.b_amax ? *ph.b_amax : 0x3F800000u, sb, ib);
+    h3_slot_scale(ph.a_amax, sa, ia);
+    h3_slot_scale(ph.b_amax, sb, ib);
     const float inv = ia * ib;
     const float comp_last = ph.comp_per_mma * (float)((num_kb - n_mid * H3_CHUNK_KB) * (BK / UK));
 #pragma unroll
@@ -1613,7 +1665,7 @@ gemm_tc_h3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
     }
     if (p.c_amax) {
       const uint32_t mx = __reduce_max_sync(0xffffffffu, __float_as_uint(vmax));
-      if (lane == 0 && mx) atomicMax(p.c_amax, mx);
+      if (lane == 0 && mx) atomicMax(p.c_amax + 1, mx);
     }
   }
   tc_fence_before();
@@ -1804,11 +1856,17 @@ gemm_tc_h3p_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
     const int half = (warp - 2) >> 2;
     const uint32_t t_lane = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(half * CPW);
     float sa, sb, ia, ib;
-    h3_scale(pp.a_amax ? *pp.a_amax : 0x3F800000u, sa, ia);
-    h3_scale(pp.b_amax ? *pp.b_amax : 0x3F800000u, sb, ib);
+    h3_slot_scale(pp.a_amax, sa, ia);
+    h3_slot_scale(pp.b_amax, sb, ib);
     const float inv = ia * ib;
     float4* stg = reinterpret_cast<float4*>(base_ptr + C::STAGES * C::STAGE_BYTES + (32 * C::EPI_COLS * 4) * (warp - 2));
     uint32_t g = 0;
+    Params p = pp.p;                             // worker-local copy: the scale of C's planes is read from C's slot
+    if (p.c_hi) {
+      const uint32_t W = p.c_amax[0];            // prepared by h3_prep_kernel before this launch; 0 = no history
+      if (W == 0u) p.c_hi = nullptr;             // the repair pass will write the planes once max|C| is known
+      else { float is; h3_scale(W, p.c_scale, is); }
+    }
     float vmax = 0.f;
     float* const vm = p.c_amax ? &vmax : nullptr;
     long long* const dbg = (p.dbg && blockIdx.x == 0 && warp == 2) ? p.dbg : nullptr;
@@ -1862,8 +1920,13 @@ gemm_tc_h3p_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
             }
             __syncwarp();
             if (m0 + 32 * q + 32 <= p.M && c0 + C::EPI_COLS <= p.N && !p.accumulate) {     // warp-uniform
-              if (p.mask) store_staged_interior<C::EPI_COLS, true>(p, Cz, stg, lane, m0 + 32 * q, c0, vm);
-              else store_staged_interior<C::EPI_COLS, false>(p, Cz, stg, lane, m0 + 32 * q, c0, vm);
+              if (p.c_hi) {
+                if (p.mask) store_staged_interior<C::EPI_COLS, true, true>(p, Cz, stg, lane, m0 + 32 * q, c0, vm);
+                else store_staged_interior<C::EPI_COLS, false, true>(p, Cz, stg, lane, m0 + 32 * q, c0, vm);
+              } else {
+                if (p.mask) store_staged_interior<C::EPI_COLS, true, false>(p, Cz, stg, lane, m0 + 32 * q, c0, vm);
+                else store_staged_interior<C::EPI_COLS, false, false>(p, Cz, stg, lane, m0 + 32 * q, c0, vm);
+              }
             } else {
               store_staged<C::EPI_COLS>(p, Cz, stg, lane, m0 + 32 * q, c0, vm);
             }
@@ -1884,7 +1947,7 @@ gemm_tc_h3p_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
     if (dbg && lane == 0) { dbg[3] = clock64() - t_begin; dbg[4] = w_accfull; dbg[5] = t_drain; dbg[6] = t_epi; }
     if (p.c_amax) {
       const uint32_t mx = __reduce_max_sync(0xffffffffu, __float_as_uint(vmax));
-      if (lane == 0 && mx) atomicMax(p.c_amax, mx);
+      if (lane == 0 && mx) atomicMax(p.c_amax + 1, mx);
     }
   }
   tc_fence_before();
@@ -1983,7 +2046,7 @@ __global__ void h3_amax_kernel(const float* __restrict__ x, long long rows, int 
   if (threadIdx.x < 32) {
     m = threadIdx.x < (blockDim.x >> 5) ? sm[threadIdx.x] : 0u;
     m = __reduce_max_sync(0xffffffffu, m);
-    if (threadIdx.x == 0 && m) atomicMax(slot, m);
+    if (threadIdx.x == 0 && m) atomicMax(slot + 1, m);
   }
 }
 
@@ -1995,10 +2058,17 @@ __device__ __forceinline__ void h3_split1(float x, float s, uint16_t& hi, uint16
   lo = __half_as_ushort(__float2half_rn(r));
 }
 
+// slot[0] = effective sticky word, slot[1] = 0: issued before a dense layer that writes the planes of its output
+__global__ void h3_prep_kernel(uint32_t* slot, int keep) {
+  slot[0] = keep ? h3_eff_word(slot[0], slot[1]) : 0u;      // keep = 0: no history, the scale follows max|x| alone
+  slot[1] = 0u;
+}
+
 __global__ void h3_split_kernel(const float* __restrict__ x, long long rows, int cols, int ld, const uint32_t* __restrict__ slot,
-                                uint16_t* __restrict__ hi, uint16_t* __restrict__ lo) {
+                                uint16_t* __restrict__ hi, uint16_t* __restrict__ lo, int repair) {
   float s, inv;
-  h3_scale(*slot, s, inv);
+  h3_slot_scale(slot, s, inv);
+  if (repair && h3_eff_word(slot[0], slot[1]) == slot[0]) return;      // the epilogue's planes stand
   const bool flat = ld == cols;
   const bool vec = ((cols & 3) == 0) && ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) &&
                    ((reinterpret_cast<uintptr_t>(hi) & 7) == 0) && ((reinterpret_cast<uintptr_t>(lo) & 7) == 0);
@@ -2030,10 +2100,10 @@ static int h3_convert(cudaStream_t st, const float* x, long long rows, int cols,
   const long long work = ld == cols ? (rows * cols / 4 + 255) / 256 : rows;
   const unsigned blocks = (unsigned)(work < 1 ? 1 : (work > 148 * 8 ? 148 * 8 : work));
   if (!have_amax) {      // otherwise the producing dense layer left max|x| in the slot (addk_gemm_args::c_amax)
-    if (cudaMemsetAsync(slot, 0, sizeof(uint32_t), st) != cudaSuccess) { addk_set_error("f16x3 convert: memset failed"); return ADDK_ERR_LAUNCH; }
+    if (cudaMemsetAsync(slot, 0, 2 * sizeof(uint32_t), st) != cudaSuccess) { addk_set_error("f16x3 convert: memset failed"); return ADDK_ERR_LAUNCH; }
     h3_amax_kernel<<<blocks, 256, 0, st>>>(x, rows, cols, ld, slot);
   }
-  h3_split_kernel<<<blocks, 256, 0, st>>>(x, rows, cols, ld, slot, reinterpret_cast<uint16_t*>(hi), reinterpret_cast<uint16_t*>(hi) + plane);
+  h3_split_kernel<<<blocks, 256, 0, st>>>(x, rows, cols, ld, slot, reinterpret_cast<uint16_t*>(hi), reinterpret_cast<uint16_t*>(hi) + plane, 0);
   return ADDK_OK;
 }
 
@@ -2081,7 +2151,7 @@ static int gemm_bf16(cudaStream_t st, const addk_gemm_args& a) {
   p.C = a.C; p.ldc = a.ldc; p.M = a.M; p.N = a.N; p.K = a.K; p.bias = a.bias; p.mask = a.relu_mask_src;
   p.ld_mask = a.ld_mask; p.relu = a.relu; p.accumulate = 0; p.kb_per_split = kb_per;
   p.slab_stride = a.slab_stride > 0 ? a.slab_stride : (long long)a.M * a.ldc;
-  p.pair_flags = 0; p.dbg = nullptr; p.C16 = a.C16; p.c_amax = nullptr;
+  p.pair_flags = 0; p.dbg = nullptr; p.C16 = a.C16; p.c_amax = nullptr; p.c_hi = nullptr; p.c_plane = 0; p.c_scale = 1.f;
   p.a_mn = a.trans_a ? 1 : 0;
   p.b_mn = a.trans_b ? 0 : 1;
   const int BN = a.N > 128 ? 256 : (a.N > 64 ? 128 : 64);
@@ -2099,6 +2169,23 @@ extern "C" int addk_f16x3_convert(void* stream, const float* x, long long rows, 
                                   uint32_t* amax_slot) {
   const int rc = addk_tc::h3_convert((cudaStream_t)stream, x, rows, cols, ld, hi16, plane, amax_slot);
   if (rc != ADDK_OK) return rc;
+  ADDK_CHECK_LAUNCH();
+  return ADDK_OK;
+}
+
+extern "C" int addk_f16x3_prep(void* stream, uint32_t* slot, int keep_sticky_word) {
+  if (!slot) return ADDK_ERR_ARG;
+  addk_tc::h3_prep_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(slot, keep_sticky_word);
+  ADDK_CHECK_LAUNCH();
+  return ADDK_OK;
+}
+extern "C" int addk_f16x3_repair(void* stream, const float* x, long long rows, int cols, int ld, void* hi16, long long plane,
+                                 uint32_t* slot) {
+  if (!x || !hi16 || !slot || rows <= 0 || cols <= 0 || ld < cols || plane <= 0) return ADDK_ERR_ARG;
+  const long long work = ld == cols ? (rows * cols / 4 + 255) / 256 : rows;
+  const unsigned blocks = (unsigned)(work < 1 ? 1 : (work > 148 * 8 ? 148 * 8 : work));
+  addk_tc::h3_split_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, rows, cols, ld, slot, reinterpret_cast<uint16_t*>(hi16),
+                                                                     reinterpret_cast<uint16_t*>(hi16) + plane, 1);
   ADDK_CHECK_LAUNCH();
   return ADDK_OK;
 }
@@ -2138,6 +2225,7 @@ static int gemm_h3(cudaStream_t st, const addk_gemm_args& a) {
   p.slab_stride = a.slab_stride > 0 ? a.slab_stride : (long long)a.M * a.ldc;
   { const char* e = getenv("ADDK_H3_FLAGS"); p.pair_flags = e ? atoi(e) : 0; }
   { const char* e = getenv("ADDK_TC_DBG"); p.dbg = e ? (long long*)strtoull(e, nullptr, 0) : nullptr; } p.C16 = nullptr; p.c_amax = split == 1 ? a.c_amax : nullptr;
+  p.c_hi = nullptr; p.c_plane = 0; p.c_scale = 1.f;
   p.a_mn = a.trans_a ? 1 : 0;
   p.b_mn = a.trans_b ? 0 : 1;
   ph.a_amax = a.a_amax; ph.b_amax = a.b_amax; ph.comp_per_mma = addk_h3_comp();
@@ -2156,6 +2244,9 @@ static int gemm_h3(cudaStream_t st, const addk_gemm_args& a) {
   if (BN == 256 && persistent) {
     ParamsP pp;
     pp.p = p; pp.a_amax = a.a_amax; pp.b_amax = a.b_amax; pp.comp_per_mma = ph.comp_per_mma;
+    if (a.C16 && a.c_amax && split == 1 && a.c16_plane > 0 && (a.ldc & 7) == 0 && (reinterpret_cast<uintptr_t>(a.C16) & 15) == 0) {
+      pp.p.c_hi = reinterpret_cast<uint16_t*>(a.C16); pp.p.c_plane = a.c16_plane;
+    }
     { static int ck = 0; if (!ck) { const char* e = getenv("ADDK_H3_CHUNK_KB"); ck = e ? atoi(e) : H3P_CHUNK_KB; if (ck < 1) ck = 1; } pp.chunk_kb = ck; }
     return launch_h3p<256>(st, tah, tal, tbh, tbl, pp, a.M, a.N, split);
   }
@@ -2216,7 +2307,7 @@ int addk_gemm_tc(cudaStream_t st, const addk_gemm_args& a, int precision) {
   p.slab_stride = a.slab_stride > 0 ? a.slab_stride : (long long)a.M * a.ldc;
   { const char* e = getenv("ADDK_TC_PAIR_FLAGS"); p.pair_flags = e ? atoi(e) : 2; }
   { const char* e = getenv("ADDK_TC_DBG"); p.dbg = e ? (long long*)strtoull(e, nullptr, 0) : nullptr; }
-  p.C16 = nullptr; p.c_amax = nullptr;
+  p.C16 = nullptr; p.c_amax = nullptr; p.c_hi = nullptr; p.c_plane = 0; p.c_scale = 1.f;
   p.a_mn = a.trans_a ? 1 : 0;          // A given as [K,M]: rows are the contraction index
   p.b_mn = a.trans_b ? 0 : 1;          // B given as [K,N]
   const int BN = a.N > 128 ? 256 : (a.N > 64 ? 128 : 64);

@@ -21,6 +21,7 @@
 // The "zero diff" positive sample D(0) is carried as one extra row (row M) of the minibatch.
 #include "common.cuh"
 #include "addk.h"
+#include <stdlib.h>
 
 struct addk_update_ctx {
 #define ADDK_PTR(n) void* n;
@@ -497,7 +498,9 @@ static thread_local const addk_update_ctx* g_twin_ctx = nullptr;
 struct TwinEnt { const float* p; long long rows; int cols, ld; cudaStream_t st; bool valid, shared, amax_known; };
 static thread_local TwinEnt g_tw[63];
 static thread_local int g_ntw = 0;
-static void twin_reset() { g_ntw = 0; }
+static thread_local int g_slot_base = 0;       // each entry point owns 64 slots, so the sticky scale words keep their tensors
+static void twin_reset(int entry_point) { g_ntw = 0; g_slot_base = 64 * entry_point; }
+static uint32_t* twin_slot(const addk_update_ctx& c, int e) { return (uint32_t*)c.amax_slots + 2 * (1 + g_slot_base + e); }
 static void twin_invalidate(const void* p, size_t bytes) {
   const char* b = (const char*)p;
   for (int i = 0; i < g_ntw; ++i) {
@@ -526,7 +529,7 @@ static H3Op h3_operand(const addk_update_ctx& c, cudaStream_t st, const float* p
     g_tw[e] = TwinEnt{p, 0, 0, 0, nullptr, false, false, false};
   }
   TwinEnt& t = g_tw[e];
-  o.hi = (const uint16_t*)c.arena16 + (p - a0); o.plane = c.arena_elems; o.amax = slots + 1 + e;
+  o.hi = (const uint16_t*)c.arena16 + (p - a0); o.plane = c.arena_elems; o.amax = twin_slot(c, e);
   if (t.valid && t.cols == cols && t.ld == ld && rows <= t.rows && (t.st == st || t.shared)) { o.ready = 1; return o; }
   // the call about to be issued converts it; the max pass is skipped when the producing dense layer left max|x| behind
   if (t.amax_known && t.cols == cols && t.ld == ld && rows <= t.rows && t.st == st) o.ready = 2;
@@ -535,6 +538,9 @@ static H3Op h3_operand(const addk_update_ctx& c, cudaStream_t st, const float* p
 }
 extern "C" int addk_f16x3_convert(void* stream, const float* x, long long rows, int cols, int ld, void* hi16, long long plane,
                                   uint32_t* amax_slot);
+extern "C" int addk_f16x3_prep(void* stream, uint32_t* slot, int keep_sticky_word);
+extern "C" int addk_f16x3_repair(void* stream, const float* x, long long rows, int cols, int ld, void* hi16, long long plane,
+                                 uint32_t* slot);
 // convert now (used for tensors several streams read: must happen before the fork)
 static int h3_prepare(const addk_update_ctx& c, cudaStream_t st, const float* p, long long rows, int cols, int ld) {
   H3Op o = h3_operand(c, st, p, rows, cols, ld);
@@ -544,9 +550,9 @@ static int h3_prepare(const addk_update_ctx& c, cudaStream_t st, const float* p,
   return addk_f16x3_convert(st, p, rows, cols, ld, const_cast<void*>(o.hi), o.plane, o.amax);
 }
 // the fp16 planes of the whole flat parameter vector (one scale: slot 0)
-static int h3_params(const addk_update_ctx& c, cudaStream_t st) {
+static int h3_params(const addk_update_ctx& c, cudaStream_t st, int entry_point) {
   if (c.precision != 4) return ADDK_OK;
-  twin_reset();
+  twin_reset(entry_point);
   if (!c.params16 || !c.amax_slots) { addk_set_error("f16x3: the context has no parameter twin / max|x| slots"); return ADDK_ERR_ARG; }
   return addk_f16x3_convert(st, (const float*)c.params, 1, (int)c.num_params, (int)c.num_params, c.params16, c.num_params,
                             (uint32_t*)c.amax_slots);
@@ -571,7 +577,8 @@ static int gemm(cudaStream_t st, int prec, const float* A, int lda, int ta, cons
                 long long slab_stride = 0) {
   addk_gemm_args a;
   a.A16 = prec == 3 ? twin16(A) : nullptr; a.B16 = prec == 3 ? twin16(B) : nullptr; a.C16 = prec == 3 ? twin16(C) : nullptr;
-  a.a16_plane = a.b16_plane = 0; a.a_amax = a.b_amax = a.c_amax = nullptr; a.a16_ready = a.b16_ready = 0;
+  a.a16_plane = a.b16_plane = a.c16_plane = 0; a.a_amax = a.b_amax = a.c_amax = nullptr; a.a16_ready = a.b16_ready = 0;
+  int c_ent = -1;
   a.A = A; a.lda = lda; a.B = B; a.ldb = ldb; a.C = C; a.ldc = ldc; a.M = M; a.N = N; a.K = K;
   a.bias = bias; a.a_mean = nmean; a.a_std = nstd; a.relu_mask_src = mask; a.ld_mask = ld_mask;
   a.trans_a = ta; a.trans_b = tb; a.relu = relu; a.split_k = split; a.accumulate = 0; a.slab_stride = slab_stride;
@@ -596,11 +603,20 @@ static int gemm(cudaStream_t st, int prec, const float* A, int lda, int ta, cons
         for (int i = 0; i < g_ntw; ++i) if (g_tw[i].p == C) { e = i; break; }
         if (e < 0 && g_ntw < 63) { e = g_ntw++; g_tw[e] = TwinEnt{C, 0, 0, 0, nullptr, false, false, false}; }
         if (e >= 0) {
-          uint32_t* slot = (uint32_t*)c.amax_slots + 1 + e;
-          if (cudaMemsetAsync(slot, 0, sizeof(uint32_t), st) == cudaSuccess) {
+          uint32_t* slot = twin_slot(c, e);
+          // Letting the epilogue write C's planes too (sticky scale word, prep -> layer -> repair) is implemented and
+          // tested but off: measured at 4096 envs it removes 0.18 ms of split passes per optimizer step and adds 0.25 ms
+          // to the dense layers (the epilogue's 8-byte stores are far from the split kernel's 6 TB/s).
+          static int fused = -1;
+          if (fused < 0) { const char* ev = getenv("ADDK_H3_FUSED_PLANES"); fused = ev ? atoi(ev) : 0; }
+          if (addk_f16x3_prep(st, slot, fused) == ADDK_OK) {     // max <- 0, W <- scale in force | 0
             TwinEnt& t = g_tw[e];
             t.rows = M; t.cols = N; t.ld = ldc; t.st = st; t.valid = false; t.shared = false; t.amax_known = true;
             a.c_amax = slot;
+            if (fused && N > 128 && (ldc & 7) == 0) {     // the persistent kernel also writes C's planes in its epilogue
+              a.C16 = (uint16_t*)c.arena16 + (C - a0); a.c16_plane = c.arena_elems;
+              c_ent = e;
+            }
           }
         }
       }
@@ -609,6 +625,11 @@ static int gemm(cudaStream_t st, int prec, const float* A, int lda, int ta, cons
   int rc = prec == 0 ? addk::sgemm_launch(st, a) : addk_gemm_tc(st, a, prec);
   if (rc != ADDK_OK) return rc;
   ADDK_CHECK_LAUNCH();
+  if (c_ent >= 0) {     // planes written by the epilogue: rewritten only if the sticky scale did not fit max|C|
+    rc = addk_f16x3_repair(st, C, M, N, ldc, a.C16, a.c16_plane, a.c_amax);
+    if (rc != ADDK_OK) return rc;
+    g_tw[c_ent].valid = true;
+  }
   return ADDK_OK;
 }
 #define TRY(x) do { int rc__ = (x); if (rc__ != ADDK_OK) return rc__; } while (0)
@@ -744,7 +765,7 @@ extern "C" int addk_update_minibatch(void* stream, void* ctx_host, const long lo
     f32_to_bf16_flat_kernel<<<148 * 4, 256, 0, st>>>(F(c.params), (uint16_t*)c.params16, c.num_params);
     ADDK_CHECK_LAUNCH();
   }
-  TRY(h3_params(c, st));
+  TRY(h3_params(c, st, 0));
 
   gather_minibatch_kernel<<<(M + 7) / 8, 256, 0, st>>>(
       idx, M, OD, AD, AL, DD, DL, F(c.buf_obs), F(c.buf_action), F(c.buf_a_logp), F(c.buf_adv), F(c.buf_tar_val),
@@ -889,7 +910,7 @@ extern "C" int addk_actor_step(void* stream, void* ctx_host, const float* obs, c
     f32_to_bf16_flat_kernel<<<148 * 4, 256, 0, st>>>(F(c.params), (uint16_t*)c.params16, c.num_params);
     ADDK_CHECK_LAUNCH();
   }
-  TRY(h3_params(c, st));
+  TRY(h3_params(c, st, 1));
   if (obs_rec) cudaMemcpyAsync(obs_rec, obs, (size_t)n * OD * sizeof(float), cudaMemcpyDeviceToDevice, st);
   TRY(trunk_forward(st, c, main_ws(c), obs, OD, OD, n, c.o_a_w0, c.o_a_b0, c.o_a_w1, c.o_a_b1, c.o_a_w2, c.o_a_b2, F(c.obs_mean),
                     F(c.obs_std)));
@@ -912,7 +933,7 @@ extern "C" int addk_critic_eval(void* stream, void* ctx_host, const float* obs, 
     f32_to_bf16_flat_kernel<<<148 * 4, 256, 0, st>>>(F(c.params), (uint16_t*)c.params16, c.num_params);
     ADDK_CHECK_LAUNCH();
   }
-  TRY(h3_params(c, st));
+  TRY(h3_params(c, st, 2));
   for (long long r0 = 0; r0 < n; r0 += chunk) {
     int rows = (int)((n - r0 < chunk) ? n - r0 : chunk);
     TRY(trunk_forward(st, c, main_ws(c), obs + r0 * OD, OD, OD, rows, c.o_c_w0, c.o_c_b0, c.o_c_w1, c.o_c_b1, c.o_c_w2, c.o_c_b2,
@@ -936,7 +957,7 @@ extern "C" int addk_disc_eval(void* stream, void* ctx_host, const float* disc_ob
     f32_to_bf16_flat_kernel<<<148 * 4, 256, 0, st>>>(F(c.params), (uint16_t*)c.params16, c.num_params);
     ADDK_CHECK_LAUNCH();
   }
-  TRY(h3_params(c, st));
+  TRY(h3_params(c, st, 3));
   pad_rows_kernel<<<(E1 * DL + 255) / 256, 256, 0, st>>>(W + c.o_d_w0, E1, DD, DL, F(c.wd0_pad), twin16(c.wd0_pad));
   ADDK_CHECK_LAUNCH();
   for (long long r0 = 0; r0 < n; r0 += chunk) {

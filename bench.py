@@ -418,7 +418,7 @@ def dominant_kernel_roofline(agent, args, hbm_peak, tc_peak, peak_src):
         # timed launches are the dense-layer kernel itself, the split pre-pass is part of the step numbers
         A16 = [torch.zeros(2 * M * Kd, device=m.flat.device, dtype=torch.float16) for _ in range(nbuf)]
         W16 = torch.zeros(2 * Nd * Kd, device=m.flat.device, dtype=torch.float16)
-        slots = torch.zeros(nbuf + 1, device=m.flat.device, dtype=torch.int32)
+        slots = torch.zeros(2 * (nbuf + 1), device=m.flat.device, dtype=torch.int32)     # {sticky scale word, max|x|} pairs
 
     def launch(i):
         a = _lib.AddkGemmArgs(A=A[i % nbuf].data_ptr(), lda=Kd, B=Wt.data_ptr(), ldb=Kd, C=Cc[i % 2].data_ptr(), ldc=Nd,
@@ -428,7 +428,7 @@ def dominant_kernel_roofline(agent, args, hbm_peak, tc_peak, peak_src):
                               C16=C16[i % 2].data_ptr() if bf16 else None)
         if h3:
             a.a16_plane, a.b16_plane = M * Kd, Nd * Kd
-            a.a_amax, a.b_amax = slots[1 + i % nbuf:].data_ptr(), slots.data_ptr()
+            a.a_amax, a.b_amax = slots[2 * (1 + i % nbuf):].data_ptr(), slots.data_ptr()
             a.a16_ready = a.b16_ready = ready[0]
         _lib.check(L.addk_gemm(_lib.stream(), C.byref(a), C.c_int(m.precision)), "addk_gemm")
     for i in range(max(3, nbuf if h3 else 0)):

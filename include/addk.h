@@ -195,20 +195,32 @@ typedef struct addk_gemm_args {
   /* precision "f16x3" only (fp32-parity mode on the fp16 tensor pipe): A16 / B16 point at the fp16 "hi" plane of the
    * operand's twin (same shape / leading dimension as the fp32 operand, x*s rounded to fp16, s = the power of two that
    * puts max|x| into [2^14, 2^15)); the "lo" plane ((x*s - hi) * 2^11 rounded to fp16) starts a16_plane / b16_plane
-   * ELEMENTS after it; a_amax / b_amax are device words holding the bit pattern of max|x|.  a16_ready / b16_ready = 0:
+   * ELEMENTS after it; a_amax / b_amax are device slots of two words {W, max}: max = the bit pattern of max|x|, W = a sticky scale
+   * word that stays in force while max|x| * s(W) is inside [2^9, 2^15) (zero it if unused).  a16_ready / b16_ready = 0:
    * the call computes max|x| and writes both planes first (two extra launches per operand); != 0: the twin already
    * holds this operand (converted by an earlier call).  NULL twins -> the call runs in tf32x3. */
   int64_t a16_plane, b16_plane;
   uint32_t* a_amax; uint32_t* b_amax;
   int32_t a16_ready, b16_ready;      /* 0 convert (max pass + split pass) | 1 twin ready | 2 *amax valid: split pass only */
-  uint32_t* c_amax;                  /* optional, single-slab calls: atomicMax of the bit patterns of |C| as stored, so a
-                                      * later call that reads C can pass ready = 2; the caller zeroes the word first */
+  uint32_t* c_amax;                  /* optional, single-slab calls: C's slot; max|C| as stored is atomicMax-ed into word [1], so
+                                      * a later call that reads C can pass ready = 2; the caller zeroes word [1] first
+                                      * (addk_f16x3_prep) */
+  int64_t c16_plane;                 /* optional, with C16 + c_amax, N > 128: the epilogue also writes C's fp16 planes with the
+                                      * scale of the slot's sticky word [0]; addk_f16x3_repair afterwards rewrites them in
+                                      * the rare case that scale does not fit max|C|; then readers of C pass ready = 1 */
 } addk_gemm_args;
 int addk_gemm(void* stream, const addk_gemm_args* args_host, int precision);
 /* precision "f16x3": max|x| of the [rows, cols] fp32 tensor x (pitch ld) -> *amax_slot (bit pattern), then the two
  * fp16 planes hi16[0 .. rows*ld) and hi16[plane .. plane + rows*ld) described above.  Three stream-ordered operations. */
 int addk_f16x3_convert(void* stream, const float* x, long long rows, int cols, int ld, void* hi16, long long plane,
                        uint32_t* amax_slot);
+/* before a dense layer that leaves max|C| (c_amax) or the planes of its output (c16_plane) behind: clears the max word
+ * and either folds the scale in force into the slot's sticky word (keep_sticky_word = 1, needed for c16_plane) or
+ * clears it (0: the scale then follows max|x| alone and results do not depend on earlier calls); addk_f16x3_repair,
+ * after the layer, rewrites the planes if the sticky scale turned out not to fit max|C| */
+int addk_f16x3_prep(void* stream, uint32_t* slot, int keep_sticky_word);
+int addk_f16x3_repair(void* stream, const float* x, long long rows, int cols, int ld, void* hi16, long long plane,
+                      uint32_t* slot);
 
 /* ----- PPO / ADD minibatch (csrc/mlp.cu) ------------------------------------------------------ */
 struct addk_update_ctx;  /* opaque; plain host struct of device pointers, see csrc/mlp.cu */

@@ -141,20 +141,21 @@ class _Twin:
     def __init__(self, t):
         self.n = (t.numel() + 7) & ~7
         self.planes = torch.zeros(2 * self.n, device=t.device, dtype=torch.float16)
-        self.amax = torch.zeros(1, device=t.device, dtype=torch.int32)
+        self.amax = torch.zeros(2, device=t.device, dtype=torch.int32)      # slot: {sticky scale word, max|x|}
 
 
 def _gemm_h3(A, B, Cout, M, N, K, ta, tb, tw_a, tw_b, ready=(0, 0), bias=None, relu=0, mask=None, split=1, accumulate=0,
-             c_amax=None):
+             c_amax=None, c16=None):
     from add_gym_b200 import _lib
     a = _lib.AddkGemmArgs(A=A.data_ptr(), lda=A.stride(0), B=B.data_ptr(), ldb=B.stride(0), C=Cout.data_ptr(),
                           ldc=Cout.stride(-2), M=M, N=N, K=K, bias=bias.data_ptr() if bias is not None else None,
                           a_mean=None, a_std=None, relu_mask_src=mask.data_ptr() if mask is not None else None,
                           ld_mask=mask.stride(0) if mask is not None else 0, trans_a=ta, trans_b=tb, relu=relu,
                           split_k=split, accumulate=accumulate, slab_stride=0, A16=tw_a.planes.data_ptr(),
-                          B16=tw_b.planes.data_ptr(), C16=None, a16_plane=tw_a.n, b16_plane=tw_b.n,
+                          B16=tw_b.planes.data_ptr(), a16_plane=tw_a.n, b16_plane=tw_b.n,
                           a_amax=tw_a.amax.data_ptr(), b_amax=tw_b.amax.data_ptr(), a16_ready=ready[0], b16_ready=ready[1],
-                          c_amax=c_amax.data_ptr() if c_amax is not None else None)
+                          c_amax=c_amax.data_ptr() if c_amax is not None else None,
+                          C16=c16.planes.data_ptr() if c16 is not None else None, c16_plane=c16.n if c16 is not None else 0)
     _lib.check(_lib.lib().addk_gemm(_lib.stream(), C.byref(a), C.c_int(_lib.PRECISIONS["f16x3"])), "addk_gemm")
 
 
@@ -174,7 +175,7 @@ def test_gemm_f16x3_layouts(ta, tb):
         torch.cuda.synchronize()
         if min(M, N, K) >= 16:   # smaller shapes run the tf32x3 fallback and leave the twins untouched
             used = A[:, :M] if ta else A[:, :K]
-            assert int(tw_a.amax.item()) == int(used.abs().max().view(torch.int32).item()), "max|A| word"
+            assert int(tw_a.amax[1].item()) == int(used.abs().max().view(torch.int32).item()), "max|A| word"
             assert bool((tw_a.planes != 0).any()), "the fp16 planes were not written: the call fell back"
         e = _rel(out[:, :N], ref)
         assert e <= TOL["f16x3"], "f16x3 ta=%d tb=%d %s: rel err %.3e" % (ta, tb, (M, N, K), e)
@@ -203,11 +204,32 @@ def test_gemm_f16x3_epilogues_split_k_and_reuse():
     _gemm_h3(A, W, out3, M, N, K, 0, 1, tA, tW, ready=(1, 1), bias=bias, relu=1, c_amax=tOut.amax)
     torch.cuda.synchronize()
     assert torch.equal(out3, out)
-    assert int(tOut.amax.item()) == int(out.abs().max().view(torch.int32).item()), "max|C| word written by the epilogue"
+    assert int(tOut.amax[1].item()) == int(out.abs().max().view(torch.int32).item()), "max|C| word written by the epilogue"
     W2 = torch.randn(256, N, device="cuda", generator=g) * 0.05
     y = torch.empty(M, 256, device="cuda")
-    _gemm_h3(out, W2, y, M, 256, N, 0, 1, tOut, _Twin(W2), ready=(2, 0))
+    tW2 = _Twin(W2)
+    _gemm_h3(out, W2, y, M, 256, N, 0, 1, tOut, tW2, ready=(2, 0))
     assert _rel(y, out.double() @ W2.double().t()) <= TOL["f16x3"]
+    # ... or write C's planes itself with the slot's sticky scale (prep -> layer -> repair); the next layer passes ready = 1.
+    # First round: no history (W = 0) -> the repair pass writes the planes; second round: the epilogue's planes stand,
+    # also when the data shrinks 8x (still inside the window); a 2^20 jump forces the repair again.
+    from add_gym_b200 import _lib
+    L = _lib.lib()
+    slot = C.c_void_p(tOut.amax.data_ptr())
+    for scale in (1.0, 1.0, 0.125, 2.0 ** 20):
+        As = A * scale
+        tOut.planes.zero_()
+        _lib.check(L.addk_f16x3_prep(_lib.stream(), slot, C.c_int(1)), "prep")
+        W_before = int(tOut.amax[0].item())
+        _gemm_h3(As, W, out3, M, N, K, 0, 1, _Twin(As), tW, ready=(0, 1), bias=None, relu=1, c_amax=tOut.amax, c16=tOut)
+        _lib.check(L.addk_f16x3_repair(_lib.stream(), C.c_void_p(out3.data_ptr()), C.c_longlong(M), C.c_int(N), C.c_int(N),
+                                       C.c_void_p(tOut.planes.data_ptr()), C.c_longlong(tOut.n), slot), "repair")
+        _gemm_h3(out3, W2, y, M, 256, N, 0, 1, tOut, tW2, ready=(1, 1))
+        torch.cuda.synchronize()
+        assert _rel(y, out3.double() @ W2.double().t()) <= TOL["f16x3"], scale
+        assert bool((tOut.planes != 0).any())
+        if scale == 0.125:
+            assert W_before != 0, "sticky word carried over"
     h = torch.randn(M, K, device="cuda", generator=g)
     dY = torch.randn(M, N, device="cuda", generator=g) * 1e-6          # gradient-sized values: far below fp16's range unscaled
     dX = torch.empty(M, K, device="cuda")

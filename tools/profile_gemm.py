@@ -21,7 +21,7 @@ H3 = prec == "f16x3"
 READY = int(os.environ.get("H3_READY", "0"))
 def twin(t):
     n = (t.numel() + 7) & ~7
-    return dict(p=torch.zeros(2 * n, device=dev, dtype=torch.float16), n=n, s=torch.zeros(1, device=dev, dtype=torch.int32))
+    return dict(p=torch.zeros(2 * n, device=dev, dtype=torch.float16), n=n, s=torch.zeros(2, device=dev, dtype=torch.int32))
 TA = [twin(a) for a in A]; TW = twin(W)
 def h3(a, ta, tb):
     if H3:
