@@ -1741,6 +1741,7 @@ gemm_tc_h3p_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kb_total = (p.K + BK - 1) / BK;
   const int tiles_mn = pp.tiles_m * pp.tiles_n;
+  const long long t_entry = clock64();
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmAh); tma_prefetch_desc(&tmAl); tma_prefetch_desc(&tmBh); tma_prefetch_desc(&tmBl);
@@ -1849,7 +1850,7 @@ gemm_tc_h3p_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
         kb += n;
       }
     }
-    if (dbg && lane == 0) { dbg[0] = clock64() - t_begin; dbg[1] = w_empty; dbg[2] = w_full; }
+    if (dbg && lane == 0) { dbg[0] = clock64() - t_begin; dbg[1] = w_empty; dbg[2] = w_full; dbg[7] = t_begin - t_entry; }
   } else {
     // ===================== workers: chunk drains + epilogue =====================
     const int q = warp & 3;
@@ -1944,7 +1945,7 @@ gemm_tc_h3p_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
       }
       if (dbg) t_epi += clock64() - c2;
     }
-    if (dbg && lane == 0) { dbg[3] = clock64() - t_begin; dbg[4] = w_accfull; dbg[5] = t_drain; dbg[6] = t_epi; }
+    if (dbg && lane == 0) { dbg[3] = clock64() - t_begin; dbg[4] = w_accfull; dbg[5] = t_drain; dbg[6] = t_epi; dbg[8] = clock64() - t_entry; }
     if (p.c_amax) {
       const uint32_t mx = __reduce_max_sync(0xffffffffu, __float_as_uint(vmax));
       if (lane == 0 && mx) atomicMax(p.c_amax + 1, mx);
@@ -2229,7 +2230,11 @@ static int gemm_h3(cudaStream_t st, const addk_gemm_args& a) {
   p.a_mn = a.trans_a ? 1 : 0;
   p.b_mn = a.trans_b ? 0 : 1;
   ph.a_amax = a.a_amax; ph.b_amax = a.b_amax; ph.comp_per_mma = addk_h3_comp();
-  const int BN = a.N > 128 ? 256 : (a.N > 64 ? 128 : 64);
+  int BN = a.N > 128 ? 256 : (a.N > 64 ? 128 : 64);
+  // few, long tiles (the weight gradient of a head: 29 x 512 outputs, K = 16384 / 9): narrower tiles put 4x the SMs to work
+  const bool want_planes = a.C16 && a.c16_plane > 0;       // only the persistent 256-wide kernel writes C's planes
+  if (want_planes && (BN != 256 || split != 1 || !a.c_amax)) { addk_set_error("gemm f16x3: c16_plane needs N > 128, one slab and c_amax"); return ADDK_ERR_ARG; }
+  if (!want_planes && BN > 64 && (long long)((a.M + BM - 1) / BM) * ((a.N + BN - 1) / BN) * split <= 37) BN = 64;
   const uint16_t* Ah = reinterpret_cast<const uint16_t*>(a.A16); const uint16_t* Al = Ah + a.a16_plane;
   const uint16_t* Bh = reinterpret_cast<const uint16_t*>(a.B16); const uint16_t* Bl = Bh + a.b16_plane;
   CUtensorMap tah, tal, tbh, tbl;
@@ -2241,7 +2246,7 @@ static int gemm_h3(cudaStream_t st, const addk_gemm_args& a) {
   dim3 grid((a.N + BN - 1) / BN, (a.M + BM - 1) / BM, split);
   static int persistent = -1;
   if (persistent < 0) { const char* e = getenv("ADDK_H3_PERSISTENT"); persistent = e ? atoi(e) : 1; }
-  if (BN == 256 && persistent) {
+  if (BN == 256 && (persistent || want_planes)) {
     ParamsP pp;
     pp.p = p; pp.a_amax = a.a_amax; pp.b_amax = a.b_amax; pp.comp_per_mma = ph.comp_per_mma;
     if (a.C16 && a.c_amax && split == 1 && a.c16_plane > 0 && (a.ldc & 7) == 0 && (reinterpret_cast<uintptr_t>(a.C16) & 15) == 0) {

@@ -295,10 +295,10 @@ def run_b200(args):
     # ---- CPU baseline (rank 0, N=1 only) -----------------------------------------------------------------------
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        v, s, cores = cpu_iteration_rate(args.cpu_envs, 1, 1)
+        v, s, cores = cpu_iteration_rate(args.cpu_envs, 4, 1)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": "oracle port of the reference agent (torch CPU fp32, %d threads), 1 warm-up + 1 timed full "
-                         "iteration at %d envs (%.1f s)" % (cores, args.cpu_envs, s)}
+               "sample": "oracle port of the reference agent (torch CPU fp32, %d threads), 1 warm-up + 4 timed full "
+                         "iterations at %d envs (%.1f s each)" % (cores, args.cpu_envs, s)}
 
     fl = flops_per_iteration(N)
     stages = {
@@ -445,10 +445,19 @@ def dominant_kernel_roofline(agent, args, hbm_peak, tc_peak, peak_src):
     ms = sum(a.elapsed_time(b) for a, b in evs) / reps
     flops = 2.0 * M * Nd * Kd
     achieved = flops / (ms * 1e-3) / 1e12
-    traffic = _ncu_traffic("dense_layer_16384x1024x1024_tf32x3") if (args.precision == "tf32x3" and M == 16384) else None
-    return {"bound": "tensor", "kernel": "dense layer %dx%dx%d (%s)" % (M, Nd, Kd, args.precision), "achieved": achieved,
-            "peak": tc_peak, "unit": "TFLOP/s", "frac": achieved / tc_peak, "traffic": traffic, "peak_source": peak_src,
-            "avg_launch_ms": ms, "algorithmic_flops_per_launch": flops}
+    traffic = _ncu_traffic("dense_layer_16384x1024x1024_%s" % args.precision) if M == 16384 else None
+    passes = {"f16x3": 3, "tf32x3": 3}.get(args.precision, 1)
+    out = {"bound": "tensor", "kernel": "dense layer %dx%dx%d (%s)" % (M, Nd, Kd, args.precision), "achieved": achieved,
+           "peak": tc_peak, "unit": "TFLOP/s", "frac": achieved / tc_peak, "traffic": traffic, "peak_source": peak_src,
+           "avg_launch_ms": ms, "algorithmic_flops_per_launch": flops}
+    if passes > 1:   # fp32-parity modes issue 3 tensor-core products per algorithmic one (hi.hi + lo.hi + hi.lo)
+        out["mma_passes"] = passes
+        out["tensor_pipe_tflops"] = passes * achieved
+        out["note"] = ("achieved / frac count the ALGORITHMIC 2MNK flops of the fp32 layer; the tensor pipe executes %d MMA "
+                       "passes per layer (%s), i.e. %.0f TFLOP/s of %s work = %.0f %% of the measured bf16 peak" %
+                       (passes, "fp16 hi/lo planes" if args.precision == "f16x3" else "tf32 hi/lo split", passes * achieved,
+                        "kind::f16" if args.precision == "f16x3" else "kind::tf32", 100.0 * passes * achieved / tc_peak))
+    return out
 
 
 def main():

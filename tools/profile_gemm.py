@@ -9,7 +9,7 @@ prec = sys.argv[1] if len(sys.argv) > 1 else "tf32x3"
 M = int(sys.argv[2]) if len(sys.argv) > 2 else 16384
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 5
 layout = sys.argv[4] if len(sys.argv) > 4 else "fwd"
-K = N = 1024
+K = int(os.environ.get('GK', '1024')); N = int(os.environ.get('GN', '1024'))
 dev = "cuda:0"
 A = [torch.randn(M, K, device=dev) for _ in range(3)]
 W = torch.randn(N, K, device=dev) * 0.03
@@ -70,7 +70,7 @@ if os.environ.get("ADDK_TC_STAMPS"):
     del os.environ["ADDK_TC_DBG"]
     t = dbg.tolist()
     if H3:
-        print("h3p CTA 0 (cycles): mma loop %d, waiting acc_empty %d, waiting stage full %d | worker loop %d, waiting acc_full %d, drains %d, epilogues %d" % tuple(t[:7]))
+        print("h3p CTA 0 (cycles): mma loop %d, waiting acc_empty %d, waiting stage full %d | worker loop %d, waiting acc_full %d, drains %d, epilogues %d | entry->mma loop %d, entry->worker done %d" % tuple(t[:9]))
         sys.exit(0)
     names = ["entry", "setup done", "first stage ready", "all MMAs issued", "accumulator complete", "epilogue done", "cluster exit"]
     print("stamps (cycles since entry): " + ", ".join("%s %d" % (n, t[i] - t[0]) for i, n in enumerate(names)))
