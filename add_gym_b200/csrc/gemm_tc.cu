@@ -49,6 +49,7 @@ struct Params {
   uint16_t* c_hi;              // f16x3 persistent kernel: fp16 planes of C written by the epilogue with the scale of the
   long long c_plane;           //   slot's sticky word W (NULL: not wanted); lo plane c_plane elements after the hi plane
   float c_scale;               // device-side only: filled in by the kernel
+  int c16_in_staged;           // persistent kernel in bf16 mode: the shared epilogue helpers also write the bf16 copy C16
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -124,6 +125,11 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
 // f16x3: x * s -> (hi, lo) fp16 pair, four at a time (see the f16x3 section below)
 __device__ __forceinline__ void h3_split4(const float4& o, float s, uint2& h, uint2& l) {
   const float x0 = o.x * s, x1 = o.y * s, x2 = o.z * s, x3 = o.w * s;
@@ -227,6 +233,9 @@ __device__ __forceinline__ void store_staged(const Params& p, float* Cz, const f
             *reinterpret_cast<uint2*>(p.c_hi + off) = h;
             *reinterpret_cast<uint2*>(p.c_hi + p.c_plane + off) = l;
           }
+          if (p.C16 && p.c16_in_staged)
+            *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(p.C16) + (size_t)grow * p.ldc + col) =
+                make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
         } else {
           const float oo[4] = {o.x, o.y, o.z, o.w};
           for (int e = 0; e < 4 && col + e < p.N; ++e) {
@@ -236,6 +245,7 @@ __device__ __forceinline__ void store_staged(const Params& p, float* Cz, const f
             dstp[e] = xv;
             if (vmax) *vmax = fmaxf(*vmax, fabsf(xv));
             if (p.c_hi) h3_emit1(p, (size_t)grow * p.ldc + col + e, xv);
+            if (p.C16 && p.c16_in_staged) reinterpret_cast<uint16_t*>(p.C16)[(size_t)grow * p.ldc + col + e] = (uint16_t)(pack_bf16x2(xv, 0.f) & 0xFFFFu);
           }
         }
       }
@@ -247,7 +257,7 @@ __device__ __forceinline__ void store_staged(const Params& p, float* Cz, const f
 // pointer increment per store.  (ncu on the persistent f16x3 kernel: the general version above executes ~300
 // instructions per 16-byte store -- 64-bit address arithmetic, constant-bank reloads and tail predicates -- which made
 // the epilogue of a 128 x 256 tile 17.7k cycles and instruction-bound.)
-template <int CW, bool MASK, bool PLANES>
+template <int CW, bool MASK, bool PLANES, bool BF16OUT = false>
 __device__ __forceinline__ void store_staged_interior(const Params& p, float* __restrict__ Cz, const float4* stg, int lane,
                                                       int grow0, int col0, float* vmax) {
   constexpr int S = CW / 4;                        // float4 slots per row
@@ -260,6 +270,7 @@ __device__ __forceinline__ void store_staged_interior(const Params& p, float* __
   const bool relu = p.relu != 0;
   float* dst = Cz + (size_t)(grow0 + sub_r) * p.ldc + col;
   uint16_t* dhi = PLANES ? p.c_hi + (size_t)(grow0 + sub_r) * p.ldc + col : nullptr;
+  uint16_t* d16 = BF16OUT ? reinterpret_cast<uint16_t*>(p.C16) + (size_t)(grow0 + sub_r) * p.ldc + col : nullptr;
   const float cs = p.c_scale;
   const float* mk = MASK ? p.mask + (size_t)(grow0 + sub_r) * p.ld_mask + col : nullptr;
   const size_t dstep = (size_t)RPI * p.ldc, mstep = MASK ? (size_t)RPI * p.ld_mask : 0;
@@ -290,6 +301,10 @@ __device__ __forceinline__ void store_staged_interior(const Params& p, float* __
         *reinterpret_cast<uint2*>(dhi + p.c_plane) = l;
         dhi += dstep;
       }
+      if (BF16OUT) {
+        *reinterpret_cast<uint2*>(d16) = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+        d16 += dstep;
+      }
       vm = fmaxf(fmaxf(vm, fmaxf(fabsf(o.x), fabsf(o.y))), fmaxf(fabsf(o.z), fabsf(o.w)));
     }
   }
@@ -313,6 +328,7 @@ __device__ __forceinline__ void store_row_scalar(const Params& p, float* Cz, int
       dstp[j] = xv;
       if (vmax) *vmax = fmaxf(*vmax, fabsf(xv));
       if (p.c_hi) h3_emit1(p, (size_t)row * p.ldc + col, xv);
+      if (p.C16 && p.c16_in_staged) reinterpret_cast<uint16_t*>(p.C16)[(size_t)row * p.ldc + col] = (uint16_t)(pack_bf16x2(xv, 0.f) & 0xFFFFu);
     }
   }
 }
@@ -1185,12 +1201,6 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
 }
-__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
-  uint32_t r;
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
-  return r;
-}
-
 template <int BN>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_tc_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
@@ -1687,12 +1697,12 @@ gemm_tc_h3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
 //     drain of a tile is followed by its global stores while the tensor core is already on the next tile.
 // Warps as above (0 TMA, 1 MMA, 2..9 workers); barriers: full/empty per stage, acc_full/acc_empty per buffer.
 // ---------------------------------------------------------------------------------------------------------------
-template <int BN>
+template <int BN, bool SINGLE = false>    // SINGLE: one 16-bit plane per operand and one MMA per 16 k (precision "bf16")
 struct CfgP {
   static constexpr int BK = 32;
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
-  static constexpr int STAGE_BYTES = 2 * (A_BYTES + B_BYTES);
+  static constexpr int STAGE_BYTES = (SINGLE ? 1 : 2) * (A_BYTES + B_BYTES);
 #ifndef ADDK_H3P_EPI_COLS
 #define ADDK_H3P_EPI_COLS 64
 #endif
@@ -1712,13 +1722,14 @@ struct ParamsP {
   float comp_per_mma;
   int tiles_m, tiles_n, total_tiles;
   int chunk_kb;                 // k-blocks per accumulator chunk (drain period)
+  int bf16;                     // SINGLE kernel: operands are bf16 (instruction descriptor format 1)
 };
 
-template <int BN>
+template <int BN, bool SINGLE>
 __global__ void __launch_bounds__(X3_THREADS, 1)
 gemm_tc_h3p_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                    const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl, const ParamsP pp) {
-  using C = CfgP<BN>;
+  using C = CfgP<BN, SINGLE>;
   const Params& p = pp.p;
   constexpr int BK = C::BK, UK = 16;
   constexpr int CPW = BN / 2, NCH = CPW / 32;
@@ -1744,7 +1755,8 @@ gemm_tc_h3p_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
   const long long t_entry = clock64();
 
   if (threadIdx.x == 0) {
-    tma_prefetch_desc(&tmAh); tma_prefetch_desc(&tmAl); tma_prefetch_desc(&tmBh); tma_prefetch_desc(&tmBl);
+    tma_prefetch_desc(&tmAh); tma_prefetch_desc(&tmBh);
+    if (!SINGLE) { tma_prefetch_desc(&tmAl); tma_prefetch_desc(&tmBl); }
     for (int s = 0; s < C::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(acc_full_bar(b), 1); mbar_init(acc_empty_bar(b), 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -1776,22 +1788,22 @@ gemm_tc_h3p_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
           const int k0 = (kb_begin + i) * BK;
           if (!p.a_mn) {
             tma_load_2d(a_hi(s), &tmAh, full_bar(s), k0, m0);
-            tma_load_2d(a_lo(s), &tmAl, full_bar(s), k0, m0);
+            if (!SINGLE) tma_load_2d(a_lo(s), &tmAl, full_bar(s), k0, m0);
           } else {
 #pragma unroll
             for (int j = 0; j < BM / 64; ++j) {
               tma_load_2d(a_hi(s) + j * C::MN_BOX_BYTES, &tmAh, full_bar(s), m0 + 64 * j, k0);
-              tma_load_2d(a_lo(s) + j * C::MN_BOX_BYTES, &tmAl, full_bar(s), m0 + 64 * j, k0);
+              if (!SINGLE) tma_load_2d(a_lo(s) + j * C::MN_BOX_BYTES, &tmAl, full_bar(s), m0 + 64 * j, k0);
             }
           }
           if (!p.b_mn) {
             tma_load_2d(b_hi(s), &tmBh, full_bar(s), k0, n0);
-            tma_load_2d(b_lo(s), &tmBl, full_bar(s), k0, n0);
+            if (!SINGLE) tma_load_2d(b_lo(s), &tmBl, full_bar(s), k0, n0);
           } else {
 #pragma unroll
             for (int j = 0; j < BN / 64; ++j) {
               tma_load_2d(b_hi(s) + j * C::MN_BOX_BYTES, &tmBh, full_bar(s), n0 + 64 * j, k0);
-              tma_load_2d(b_lo(s) + j * C::MN_BOX_BYTES, &tmBl, full_bar(s), n0 + 64 * j, k0);
+              if (!SINGLE) tma_load_2d(b_lo(s) + j * C::MN_BOX_BYTES, &tmBl, full_bar(s), n0 + 64 * j, k0);
             }
           }
         }
@@ -1799,7 +1811,8 @@ gemm_tc_h3p_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    const uint32_t idesc = (1u << 4) | ((uint32_t)(p.a_mn ? 1 : 0) << 15) | ((uint32_t)(p.b_mn ? 1 : 0) << 16) |
+    const uint32_t fmt = (SINGLE && pp.bf16) ? ((1u << 7) | (1u << 10)) : 0u;      // A / B format: 0 = fp16, 1 = bf16
+    const uint32_t idesc = (1u << 4) | fmt | ((uint32_t)(p.a_mn ? 1 : 0) << 15) | ((uint32_t)(p.b_mn ? 1 : 0) << 16) |
                            ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
     const uint32_t a_lbo = p.a_mn ? C::MN_BOX_BYTES : 16u, b_lbo = p.b_mn ? C::MN_BOX_BYTES : 16u;
     const uint32_t a_sbo = p.a_mn ? 1024u : C::K_SBO, b_sbo = p.b_mn ? 1024u : C::K_SBO;
@@ -1838,8 +1851,10 @@ gemm_tc_h3p_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
             for (int ks = 0; ks < BK / UK; ++ks) {
               umma_f16(d_tmem, dah + ks * a_k16, dbh + ks * b_k16, idesc, acc);
               acc = 1;
-              umma_f16(d_tmem, dah + LO16 + ks * a_k16, dbh + ks * b_k16, idesc, 1u);
-              umma_f16(d_tmem, dah + ks * a_k16, dbh + LO16 + ks * b_k16, idesc, 1u);
+              if (!SINGLE) {
+                umma_f16(d_tmem, dah + LO16 + ks * a_k16, dbh + ks * b_k16, idesc, 1u);
+                umma_f16(d_tmem, dah + ks * a_k16, dbh + LO16 + ks * b_k16, idesc, 1u);
+              }
             }
             umma_commit(empty_bar(s));
           }
@@ -1859,7 +1874,7 @@ gemm_tc_h3p_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
     float sa, sb, ia, ib;
     h3_slot_scale(pp.a_amax, sa, ia);
     h3_slot_scale(pp.b_amax, sb, ib);
-    const float inv = ia * ib;
+    const float inv = SINGLE ? 1.0f : ia * ib;       // one-plane operands are not scaled
     float4* stg = reinterpret_cast<float4*>(base_ptr + C::STAGES * C::STAGE_BYTES + (32 * C::EPI_COLS * 4) * (warp - 2));
     uint32_t g = 0;
     Params p = pp.p;                             // worker-local copy: the scale of C's planes is read from C's slot
@@ -1884,7 +1899,7 @@ gemm_tc_h3p_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
       for (int kb = 0; kb < num_kb; ++g) {
         const uint32_t b = g & 1u;
         const int n = min(pp.chunk_kb, num_kb - kb);
-        const float comp = pp.comp_per_mma * (float)(n * (BK / UK) * 3);
+        const float comp = pp.comp_per_mma * (float)(n * (BK / UK) * (SINGLE ? 1 : 3));
         const long long c0 = dbg ? clock64() : 0;
         mbar_wait(acc_full_bar(b), (g >> 1) & 1u);
         const long long c1 = dbg ? clock64() : 0;
@@ -1921,7 +1936,10 @@ gemm_tc_h3p_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
             }
             __syncwarp();
             if (m0 + 32 * q + 32 <= p.M && c0 + C::EPI_COLS <= p.N && !p.accumulate) {     // warp-uniform
-              if (p.c_hi) {
+              if (SINGLE && p.C16) {
+                if (p.mask) store_staged_interior<C::EPI_COLS, true, false, true>(p, Cz, stg, lane, m0 + 32 * q, c0, vm);
+                else store_staged_interior<C::EPI_COLS, false, false, true>(p, Cz, stg, lane, m0 + 32 * q, c0, vm);
+              } else if (!SINGLE && p.c_hi) {
                 if (p.mask) store_staged_interior<C::EPI_COLS, true, true>(p, Cz, stg, lane, m0 + 32 * q, c0, vm);
                 else store_staged_interior<C::EPI_COLS, false, true>(p, Cz, stg, lane, m0 + 32 * q, c0, vm);
               } else {
@@ -1962,12 +1980,13 @@ gemm_tc_h3p_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
 // 2-D fp16 tensor map: memory [outer, inner] with `ld` elements between rows; K-major: box {32 k, box_rows}, 64-byte
 // swizzle; MN-major: box {64 mn, 32 k}, 128-byte swizzle.
 static bool make_map_f16(CUtensorMap* map, const void* ptr, long long inner, long long outer, long long ld, int box_inner,
-                         int box_rows) {
+                         int box_rows, bool bf16 = false) {
   cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
   cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
   cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1u, 1u};
-  CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+  CUresult r = g_encode(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims,
+                        strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, box_inner == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
@@ -1998,21 +2017,24 @@ static int sm_count() {
   return n;
 }
 
-template <int BN>
+template <int BN, bool SINGLE = false>
 static int launch_h3p(cudaStream_t st, const CUtensorMap& tah, const CUtensorMap& tal, const CUtensorMap& tbh,
                       const CUtensorMap& tbl, ParamsP& pp, int M, int N, int split) {
-  using C = CfgP<BN>;
+  using C = CfgP<BN, SINGLE>;
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(gemm_tc_h3p_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES) != cudaSuccess) {
+    if (cudaFuncSetAttribute(gemm_tc_h3p_kernel<BN, SINGLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES) != cudaSuccess) {
       addk_set_error("gemm_tc: cannot raise the dynamic shared memory limit");
       return ADDK_ERR_LAUNCH;
     }
     configured = true;
   }
   pp.tiles_m = (M + BM - 1) / BM; pp.tiles_n = (N + BN - 1) / BN; pp.total_tiles = pp.tiles_m * pp.tiles_n * split;
-  const int grid = pp.total_tiles < sm_count() ? pp.total_tiles : sm_count();
-  gemm_tc_h3p_kernel<BN><<<grid, X3_THREADS, C::SMEM_BYTES, st>>>(tah, tal, tbh, tbl, pp);
+  static int cap = -1;       // experiment: fewer CTAs per layer so that layers of different streams run side by side
+  if (cap < 0) { const char* e = getenv("ADDK_H3_GRID"); cap = e ? atoi(e) : 0; }
+  const int nsm = cap > 0 && cap < sm_count() ? cap : sm_count();
+  const int grid = pp.total_tiles < nsm ? pp.total_tiles : nsm;
+  gemm_tc_h3p_kernel<BN, SINGLE><<<grid, X3_THREADS, C::SMEM_BYTES, st>>>(tah, tal, tbh, tbl, pp);
   return ADDK_OK;
 }
 
@@ -2152,10 +2174,27 @@ static int gemm_bf16(cudaStream_t st, const addk_gemm_args& a) {
   p.C = a.C; p.ldc = a.ldc; p.M = a.M; p.N = a.N; p.K = a.K; p.bias = a.bias; p.mask = a.relu_mask_src;
   p.ld_mask = a.ld_mask; p.relu = a.relu; p.accumulate = 0; p.kb_per_split = kb_per;
   p.slab_stride = a.slab_stride > 0 ? a.slab_stride : (long long)a.M * a.ldc;
-  p.pair_flags = 0; p.dbg = nullptr; p.C16 = a.C16; p.c_amax = nullptr; p.c_hi = nullptr; p.c_plane = 0; p.c_scale = 1.f;
+  p.pair_flags = 0; p.dbg = nullptr; p.C16 = a.C16; p.c_amax = nullptr; p.c_hi = nullptr; p.c_plane = 0; p.c_scale = 1.f; p.c16_in_staged = 0;
   p.a_mn = a.trans_a ? 1 : 0;
   p.b_mn = a.trans_b ? 0 : 1;
   const int BN = a.N > 128 ? 256 : (a.N > 64 ? 128 : 64);
+  static int persistent = -1;
+  if (persistent < 0) { const char* e = getenv("ADDK_BF16_PERSISTENT"); persistent = e ? atoi(e) : 1; }
+  if (BN == 256 && persistent && a.C && split == 1) {     // (split-K weight gradients: the one-tile-per-CTA kernel is faster, 54 vs 62 us)
+    // the persistent kernel of the f16x3 mode with one plane per operand: 32-k blocks, 6 stages, the accumulator of a
+    // whole tile is one chunk (no precision drains), the epilogue of a tile overlaps the next tile's MMAs
+    const int kbt = (a.K + 31) / 32;
+    const int kbp = (kbt + split - 1) / split;
+    if ((long long)kbp * (split - 1) < kbt) {
+      ParamsP pp;
+      pp.p = p; pp.p.kb_per_split = kbp; pp.p.c16_in_staged = 1;
+      pp.a_amax = nullptr; pp.b_amax = nullptr; pp.comp_per_mma = 0.f; pp.chunk_kb = kbp; pp.bf16 = 1;
+      CUtensorMap tah, tbh;
+      bool okp = p.a_mn ? make_map_f16(&tah, a.A16, a.M, a.K, a.lda, 64, 32, true) : make_map_f16(&tah, a.A16, a.K, a.M, a.lda, 32, BM, true);
+      okp = okp && (p.b_mn ? make_map_f16(&tbh, a.B16, a.N, a.K, a.ldb, 64, 32, true) : make_map_f16(&tbh, a.B16, a.K, a.N, a.ldb, 32, 256, true));
+      if (okp) return launch_h3p<256, true>(st, tah, tah, tbh, tbh, pp, a.M, a.N, split);
+    }
+  }
   CUtensorMap ta, tb;
   bool ok = p.a_mn ? make_map_bf16(&ta, a.A16, a.M, a.K, a.lda, 64) : make_map_bf16(&ta, a.A16, a.K, a.M, a.lda, BM);
   ok = ok && (p.b_mn ? make_map_bf16(&tb, a.B16, a.N, a.K, a.ldb, 64) : make_map_bf16(&tb, a.B16, a.K, a.N, a.ldb, BN));
@@ -2226,7 +2265,7 @@ static int gemm_h3(cudaStream_t st, const addk_gemm_args& a) {
   p.slab_stride = a.slab_stride > 0 ? a.slab_stride : (long long)a.M * a.ldc;
   { const char* e = getenv("ADDK_H3_FLAGS"); p.pair_flags = e ? atoi(e) : 0; }
   { const char* e = getenv("ADDK_TC_DBG"); p.dbg = e ? (long long*)strtoull(e, nullptr, 0) : nullptr; } p.C16 = nullptr; p.c_amax = split == 1 ? a.c_amax : nullptr;
-  p.c_hi = nullptr; p.c_plane = 0; p.c_scale = 1.f;
+  p.c_hi = nullptr; p.c_plane = 0; p.c_scale = 1.f; p.c16_in_staged = 0;
   p.a_mn = a.trans_a ? 1 : 0;
   p.b_mn = a.trans_b ? 0 : 1;
   ph.a_amax = a.a_amax; ph.b_amax = a.b_amax; ph.comp_per_mma = addk_h3_comp();
@@ -2248,7 +2287,7 @@ static int gemm_h3(cudaStream_t st, const addk_gemm_args& a) {
   if (persistent < 0) { const char* e = getenv("ADDK_H3_PERSISTENT"); persistent = e ? atoi(e) : 1; }
   if (BN == 256 && (persistent || want_planes)) {
     ParamsP pp;
-    pp.p = p; pp.a_amax = a.a_amax; pp.b_amax = a.b_amax; pp.comp_per_mma = ph.comp_per_mma;
+    pp.p = p; pp.a_amax = a.a_amax; pp.b_amax = a.b_amax; pp.comp_per_mma = ph.comp_per_mma; pp.bf16 = 0;
     if (a.C16 && a.c_amax && split == 1 && a.c16_plane > 0 && (a.ldc & 7) == 0 && (reinterpret_cast<uintptr_t>(a.C16) & 15) == 0) {
       pp.p.c_hi = reinterpret_cast<uint16_t*>(a.C16); pp.p.c_plane = a.c16_plane;
     }
@@ -2312,7 +2351,7 @@ int addk_gemm_tc(cudaStream_t st, const addk_gemm_args& a, int precision) {
   p.slab_stride = a.slab_stride > 0 ? a.slab_stride : (long long)a.M * a.ldc;
   { const char* e = getenv("ADDK_TC_PAIR_FLAGS"); p.pair_flags = e ? atoi(e) : 2; }
   { const char* e = getenv("ADDK_TC_DBG"); p.dbg = e ? (long long*)strtoull(e, nullptr, 0) : nullptr; }
-  p.C16 = nullptr; p.c_amax = nullptr; p.c_hi = nullptr; p.c_plane = 0; p.c_scale = 1.f;
+  p.C16 = nullptr; p.c_amax = nullptr; p.c_hi = nullptr; p.c_plane = 0; p.c_scale = 1.f; p.c16_in_staged = 0;
   p.a_mn = a.trans_a ? 1 : 0;          // A given as [K,M]: rows are the contraction index
   p.b_mn = a.trans_b ? 0 : 1;          // B given as [K,N]
   const int BN = a.N > 128 ? 256 : (a.N > 64 ? 128 : 64);

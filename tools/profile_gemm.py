@@ -23,7 +23,16 @@ def twin(t):
     n = (t.numel() + 7) & ~7
     return dict(p=torch.zeros(2 * n, device=dev, dtype=torch.float16), n=n, s=torch.zeros(2, device=dev, dtype=torch.int32))
 TA = [twin(a) for a in A]; TW = twin(W)
+BF = prec == "bf16"
+A_bf = [x.to(torch.bfloat16) for x in A] if BF else None
+W_bf = W.to(torch.bfloat16) if BF else None
+C_bf = [torch.empty(M, N, device=dev, dtype=torch.bfloat16) for _ in range(2)] if BF else None
 def h3(a, ta, tb):
+    if BF:
+        ia = [i for i, t in enumerate(TA) if t is ta][0]
+        a.A16 = A_bf[ia].data_ptr()
+        a.B16 = W_bf.data_ptr() if tb is TW else A_bf[[i for i, t in enumerate(TA) if t is tb][0]].data_ptr()
+        if layout != "wgrad": a.C16 = C_bf[0].data_ptr()
     if H3:
         a.A16 = ta["p"].data_ptr(); a.a16_plane = ta["n"]; a.a_amax = ta["s"].data_ptr(); a.a16_ready = READY
         a.B16 = tb["p"].data_ptr(); a.b16_plane = tb["n"]; a.b_amax = tb["s"].data_ptr(); a.b16_ready = READY
