@@ -2120,6 +2120,9 @@ __global__ void h3_split_kernel(const float* __restrict__ x, long long rows, int
 static int h3_convert(cudaStream_t st, const float* x, long long rows, int cols, int ld, void* hi, long long plane, uint32_t* slot,
                       bool have_amax = false) {
   if (!x || !hi || !slot || rows <= 0 || cols <= 0 || ld < cols || plane <= 0) { addk_set_error("f16x3 convert: bad arguments"); return ADDK_ERR_ARG; }
+  // A few alignment-padding columns (29 -> 32 actions, 114 -> 120 discriminator inputs) are part of the tensor's own
+  // buffer and hold zeros: scan them too, flat and vectorised, instead of one block per 29-column row (18 -> 3 us)
+  if (cols < ld && ld - cols < 8 && (ld & 3) == 0) cols = ld;
   const long long work = ld == cols ? (rows * cols / 4 + 255) / 256 : rows;
   const unsigned blocks = (unsigned)(work < 1 ? 1 : (work > 148 * 8 ? 148 * 8 : work));
   if (!have_amax) {      // otherwise the producing dense layer left max|x| in the slot (addk_gemm_args::c_amax)
