@@ -55,7 +55,57 @@ class MotionLib:
             return files, weights
         return [motion_file], [1.0]
 
+    def _load_baked(self, path):
+        """A pre-baked step table (`save_table`): upload and go -- no text parse, no resampling kernels."""
+        header, table = motion_io.load_step_table(path)
+        kin, dev = self._kin_char_model, self._device
+        D = kin.get_dof_size()
+        if int(header["num_dofs"]) != D or int(header["row_stride"]) != 2 * ((7 + D + 3) & ~3):
+            raise ValueError("%s was baked for %s dofs / row stride %s" % (path, header["num_dofs"], header["row_stride"]))
+        if abs(float(header["dt"]) - self._dt) > 1e-12:
+            raise ValueError("%s was baked at dt = %s, the task runs at %s" % (path, header["dt"], self._dt))
+        self._num_dofs, self._row_stride = D, int(header["row_stride"])
+        self._motion_files = list(header["files"])
+        # already normalised at bake time (float32 values, exact through the JSON header): dividing again would move an ulp
+        self._motion_weights = torch.tensor(header["weights"], dtype=torch.float32).to(dev)
+        self._motion_fps = torch.tensor(header["fps"], dtype=torch.float32, device=dev)
+        self._motion_num_frames = torch.tensor(header["num_frames"], dtype=torch.long, device=dev)
+        lengths_f32 = torch.tensor(header["lengths"], dtype=torch.float32)
+        self._motion_lengths_host = lengths_f32.clone()
+        self._motion_lengths = lengths_f32.to(dev)
+        self._motion_loop_modes = torch.tensor(header["loop_modes"], dtype=torch.int, device=dev)
+        n_steps = [int(v) for v in header["num_steps"]]
+        self._motion_num_steps = n_steps
+        true_start = np.concatenate([[0], np.cumsum(n_steps)[:-1]]).astype(np.int64)
+        quirk_start = np.concatenate([[0], np.cumsum(header["num_frames"])[:-1]]).astype(np.int64)
+        self._true_start_idx = torch.tensor(true_start, dtype=torch.long, device=dev)
+        self._motion_start_idx = self._true_start_idx if self._fix_start_idx else torch.tensor(
+            quirk_start, dtype=torch.long, device=dev)
+        self._s_total = int(header["s_total"])
+        self._table = torch.from_numpy(np.array(table, copy=True)).to(dev)
+        self._frame_idx = None          # build-time diagnostics do not exist for a baked table
+        self._frame_joint_rot, self._frame_vel = [], []
+        self._c_lib = _lib.AddkMotionLib(
+            table=self._table.data_ptr(), row_stride=self._row_stride, num_motions=len(n_steps), s_total=self._s_total,
+            start_idx=self._motion_start_idx.data_ptr(), lengths=self._motion_lengths.data_ptr(),
+            loop_modes=self._motion_loop_modes.data_ptr())
+
+    def save_table(self, path):
+        """Bake the library: the packed 100 Hz table as it sits in HBM + the per-clip metadata (motion_io.save_step_table).
+        `MotionLib(path_to_addkt, ...)` then skips the text parse and the table build."""
+        header = dict(row_stride=self._row_stride, num_dofs=self._num_dofs, dt=self._dt, s_total=self._s_total,
+                      files=[os.path.basename(f) for f in self._motion_files],
+                      weights=[float(v) for v in self._motion_weights.cpu().tolist()],
+                      fps=[float(v) for v in self._motion_fps.cpu().tolist()],
+                      num_frames=[int(v) for v in self._motion_num_frames.cpu().tolist()],
+                      lengths=[float(v) for v in self._motion_lengths_host.tolist()],
+                      loop_modes=[int(v) for v in self._motion_loop_modes.cpu().tolist()],
+                      num_steps=[int(v) for v in self._motion_num_steps])
+        motion_io.save_step_table(path, header, self._table.cpu().numpy())
+
     def _load_motions(self, motion_file, motion_order):
+        if motion_file.endswith(".addkt"):
+            return self._load_baked(motion_file)
         L = _lib.lib()
         kin = self._kin_char_model
         D = kin.get_dof_size()

@@ -228,6 +228,9 @@ def run_b200(args):
             marks.append(m)
             if e2e:   # the user-visible result of the iteration, read back to the host
                 info_host = {k: float(v) for k, v in {**train_info, **data_info}.items()}
+                bad = [k for k, v in info_host.items() if v != v or v in (float("inf"), float("-inf"))]
+                if bad:
+                    raise SystemExit("bench.py: non-finite diagnostics %s -- the timed path is numerically broken" % bad)
         t_end.record()
         barrier()
         total = t_begin.elapsed_time(t_end) * 1e-3

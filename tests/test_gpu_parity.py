@@ -151,6 +151,43 @@ def test_motion_gather_indices_bit_exact():
     assert e[0].shape == (0, 3)
 
 
+def test_baked_step_table_is_a_drop_in_for_the_built_one(tmp_path):
+    """MotionLib.save_table -> MotionLib("lib.addkt"): same bytes in HBM, same lookups (incl. the Q2 start
+    offsets of a multi-clip library), same lengths / weights / loop modes, and an agent constructed on it runs."""
+    import copy
+    from add_gym_b200.env import ImitationEnvironment
+    from add_gym_b200.add_motion import ADDMotion
+    cfg = b200_config.default_config(num_envs=4, motion_file=THREE_CLIPS)
+    env = ImitationEnvironment(cfg, "cuda:0")
+    lib = ADDMotion(cfg["task"], env, "cuda:0").motion_lib
+    baked_path = str(tmp_path / "three.addkt")
+    lib.save_table(baked_path)
+    cfg2 = copy.deepcopy(cfg)
+    cfg2["task"]["motion_file"] = baked_path
+    env2 = ImitationEnvironment(cfg2, "cuda:0")
+    lib2 = ADDMotion(cfg2["task"], env2, "cuda:0").motion_lib
+    assert torch.equal(lib.step_table, lib2.step_table)
+    for a, b in ((lib._motion_lengths, lib2._motion_lengths), (lib._motion_weights, lib2._motion_weights),
+                 (lib._motion_loop_modes, lib2._motion_loop_modes), (lib._motion_start_idx, lib2._motion_start_idx),
+                 (lib._true_start_idx, lib2._true_start_idx), (lib._motion_num_frames, lib2._motion_num_frames)):
+        assert torch.equal(a, b)
+    g = torch.Generator().manual_seed(9)
+    ids = torch.randint(0, 3, (5000,), generator=g).cuda()
+    times = (torch.rand(5000, generator=g) * 130.0).cuda()
+    for x, y in zip(lib.get_precomputed_motion_step(ids, times, return_index=True),
+                    lib2.get_precomputed_motion_step(ids, times, return_index=True)):
+        assert torch.equal(x, y)
+    from add_gym_b200.add_agent import ADDAgent
+    acfg = b200_config.default_config(num_envs=8, motion_file=baked_path)
+    acfg["agent"]["steps_per_iter"] = 4
+    acfg["engine"].update(seed=3, noise_device="device", fall_prob=0.01)
+    agent = ADDAgent(acfg, device="cuda:0")
+    agent._curr_obs, agent._curr_info = agent._reset_envs()
+    agent._exp_buffer.clear()
+    agent._rollout_train(4)
+    assert bool(torch.isfinite(agent._exp_buffer.get_data("obs")).all())
+
+
 # ---------------------------------------------------------------------------------------------------------
 # one full iteration: rollout -> train data -> 40 optimizer steps -> normalizers
 # ---------------------------------------------------------------------------------------------------------
