@@ -221,7 +221,12 @@ class ADDAgent(torch.nn.Module):
         assert M <= T * N, "minibatch larger than the rollout"
         R = M + 1
         od, dd, ad = m.obs_dim, m.disc_dim, m.act_dim
-        al, dl = (ad + 7) & ~7, (dd + 7) & ~7      # leading dimensions: 8 elements = 16 bytes in the bf16 twins too
+        # leading dimensions: 8 elements = 16 bytes in the 16-bit twins is what TMA needs; the wide inputs use 16 elements
+        # = 32 bytes, because a pitch that is an odd multiple of 16 bytes puts every other row across a sector boundary
+        # (measured: the K = 264 first layer at 60 us against 44 us with a 272-element pitch)
+        wo = int(os.environ.get("ADDK_OBS_LD_ALIGN", "16"))       # 8 = the minimum TMA accepts (A/B experiments)
+        wd = int(os.environ.get("ADDK_DISC_LD_ALIGN", "16"))
+        al, dl, ol = (ad + 7) & ~7, (dd + wd - 1) // wd * wd, (od + wo - 1) // wo * wo
         H, E = m.hidden
         # split-K slabs of the weight gradients: 9 x (16 | 32 | 16) output tiles = 144 | 288 | 144 fill the 148 SMs of the
         # persistent f16x3 kernel; 8 suits the CTA-pair tf32x3 kernel
@@ -232,7 +237,7 @@ class ADDAgent(torch.nn.Module):
         w1 = max(H[0], H[1], E[0])
         # every fp32 tensor a dense layer reads or writes is carved out of ONE arena (32-byte aligned pieces), so that in
         # the "bf16" mode the library finds the bf16 twin of any operand at arena16 + (ptr - arena)
-        shapes = dict(xn=(R, od), an=(R, al), dn=(R, dl), h1=(R, w1), h2=(R, w1), h3=(R, max(H[2], E[1])), g1=(R, w1),
+        shapes = dict(xn=(R, ol), wa0_pad=(H[0], ol), wc0_pad=(H[0], ol), an=(R, al), dn=(R, dl), h1=(R, w1), h2=(R, w1), h3=(R, max(H[2], E[1])), g1=(R, w1),
                       g2=(R, w1), g3=(R, max(H[2], E[1])), u1=(R, E[0]), u2=(R, E[1]), gx=(R, dl), dg=(R, dl), mean=(R, al),
                       dmean=(R, al), wd0_pad=(E[0], dl))
         # the critic and the discriminator chains of an optimizer step get workspaces of their own, so the library can
@@ -271,7 +276,7 @@ class ADDAgent(torch.nn.Module):
                     logstd=m._action_dist._logstd_net, buf_obs=fb("obs"), buf_action=fb("action"),
                     buf_a_logp=fb("a_logp"), buf_adv=fb("adv"), buf_tar_val=fb("tar_val"),
                     buf_mask=fb("rand_action_mask"), buf_disc_obs=fb("disc_obs"), buf_disc_demo=fb("disc_obs_demo"))
-        ints = dict(obs_dim=od, act_dim=ad, disc_dim=dd, act_ld=al, disc_ld=dl, mb_rows=M, num_params=m.num_params,
+        ints = dict(obs_dim=od, obs_ld=ol, act_dim=ad, disc_dim=dd, act_ld=al, disc_ld=dl, mb_rows=M, num_params=m.num_params,
                     split_k=S, arena_elems=total, precision=m.precision, n_streams=n_streams, hid_a1=H[0], hid_a2=H[1], hid_a3=H[2], hid_d1=E[0], hid_d2=E[1])
         ints.update(m.offsets)
         opt = self._optimizer

@@ -37,7 +37,7 @@ ADDK_PTR(buf_mask)
 ADDK_PTR(buf_disc_obs)
 ADDK_PTR(buf_disc_demo)
 // ---- minibatch workspace (R = mb_rows + 1 rows; the extra row is the discriminator's "zero diff" sample)
-ADDK_PTR(xn)            // [R, obs_dim]     normalised obs
+ADDK_PTR(xn)            // [R, obs_ld]      normalised obs (columns >= obs_dim are zero)
 ADDK_PTR(an)            // [R, act_ld]      normalised action
 ADDK_PTR(old_logp)      // [R]
 ADDK_PTR(adv)           // [R]
@@ -64,6 +64,8 @@ ADDK_PTR(info)          // [max_steps, 16] float diagnostics, one row per optimi
 ADDK_PTR(cnt)           // [1] int: rows of the minibatch with rand_action_mask == 1
 ADDK_PTR(colsum_work)   // [64*1024 + 64] floats: column-sum partials + ticket counters (zero-initialised)
 ADDK_PTR(wd0_pad)       // [hid_d1, disc_ld] discriminator first-layer weight with rows padded to 16 bytes
+ADDK_PTR(wa0_pad)       // [hid_a1, obs_ld] actor / critic first-layer weights with rows padded to obs_ld (tensor-core modes)
+ADDK_PTR(wc0_pad)
 // ---- precision "bf16": every fp32 workspace tensor above is carved out of ONE arena, so the bf16 twin of any
 //      operand is arena16 + (ptr - arena); params16 is the bf16 shadow of the flat parameter vector
 ADDK_PTR(arena)         // fp32 arena base (may be NULL when precision != bf16)
@@ -89,8 +91,9 @@ ADDK_PTR(colsum_work_d) // like colsum_work, for the discriminator's stream
 ADDK_INT(obs_dim)
 ADDK_INT(act_dim)
 ADDK_INT(disc_dim)
+ADDK_INT(obs_ld)        // obs_dim rounded up to a multiple of 16: row pitch of xn and of the padded first-layer weights
 ADDK_INT(act_ld)        // act_dim rounded up to a multiple of 8
-ADDK_INT(disc_ld)       // disc_dim rounded up to a multiple of 8
+ADDK_INT(disc_ld)       // disc_dim rounded up to a multiple of 16 (32-byte row pitch in the 16-bit twins)
 ADDK_INT(mb_rows)       // minibatch rows M
 ADDK_INT(num_params)    // P (including alignment padding)
 ADDK_INT(split_k)

@@ -40,7 +40,7 @@ enum { ST_SURR = 0, ST_CLIP, ST_RATIO, ST_BOUND, ST_CRITIC, ST_BCE_NEG, ST_BCE_P
        ST_POS_LOGIT, ST_NEG_ACC, ST_POS_ACC, ST_WL_SQ, ST_W_SQ, ST_COUNT = 32 };
 
 // ---- ExperienceBuffer.sample + normalisation: one warp per minibatch row ---------------------------------
-__global__ void gather_minibatch_kernel(const long long* __restrict__ idx, int M, int obs_dim, int act_dim, int act_ld,
+__global__ void gather_minibatch_kernel(const long long* __restrict__ idx, int M, int obs_dim, int obs_ld, int act_dim, int act_ld,
                                         int disc_dim, int disc_ld, const float* __restrict__ buf_obs,
                                         const float* __restrict__ buf_action, const float* __restrict__ buf_logp,
                                         const float* __restrict__ buf_adv, const float* __restrict__ buf_tar,
@@ -56,10 +56,10 @@ __global__ void gather_minibatch_kernel(const long long* __restrict__ idx, int M
   int lane = threadIdx.x & 31;
   if (i >= M) return;
   const size_t s = (size_t)idx[i];
-  for (int c = lane; c < obs_dim; c += 32) {
-    const float v = sub_rn(buf_obs[s * obs_dim + c], obs_mean[c]) / obs_std[c];
-    xn[(size_t)i * obs_dim + c] = v;
-    if (xn16) xn16[(size_t)i * obs_dim + c] = to_bf16(v);
+  for (int c = lane; c < obs_ld; c += 32) {           // columns obs_dim .. obs_ld-1 are alignment padding (zeros)
+    const float v = c < obs_dim ? sub_rn(buf_obs[s * obs_dim + c], obs_mean[c]) / obs_std[c] : 0.f;
+    xn[(size_t)i * obs_ld + c] = v;
+    if (xn16) xn16[(size_t)i * obs_ld + c] = to_bf16(v);
   }
   for (int c = lane; c < act_ld; c += 32)
     an[(size_t)i * act_ld + c] = c < act_dim ? sub_rn(buf_action[s * act_dim + c], a_mean[c]) / a_std[c] : 0.f;
@@ -420,14 +420,19 @@ __global__ void sample_action_kernel(const float* __restrict__ mean, int act_ld,
 
 // Normalizer.normalize for a block of rows (normalizer.py:107-110): out = (x - mean) / std, 128-bit when dim % 4 == 0
 __global__ void obs_normalize_kernel(const float* __restrict__ x, const float* __restrict__ mean,
-                                     const float* __restrict__ sd, long long rows, int dim, float* __restrict__ out,
+                                     const float* __restrict__ sd, long long rows, int dim, int ld_out, float* __restrict__ out,
                                      uint16_t* __restrict__ out16) {
-  const long long n4 = rows * dim / 4;
+  const int q = ld_out / 4;                          // float4 slots per output row; slots >= dim / 4 are zero padding
+  const long long n4 = rows * q;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)((i * 4) % dim);
-    const float4 v = ldg4(x + 4 * i);
-    const float4 m = ldg4(mean + c), s = ldg4(sd + c);
-    const float4 o = make_float4(sub_rn(v.x, m.x) / s.x, sub_rn(v.y, m.y) / s.y, sub_rn(v.z, m.z) / s.z, sub_rn(v.w, m.w) / s.w);
+    const long long r = i / q;
+    const int c = (int)(i - r * q) * 4;
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < dim) {
+      const float4 v = ldg4(x + r * dim + c);
+      const float4 m = ldg4(mean + c), s = ldg4(sd + c);
+      o = make_float4(sub_rn(v.x, m.x) / s.x, sub_rn(v.y, m.y) / s.y, sub_rn(v.z, m.z) / s.z, sub_rn(v.w, m.w) / s.w);
+    }
     stg4(out + 4 * i, o);
     if (out16) { out16[4 * i] = to_bf16(o.x); out16[4 * i + 1] = to_bf16(o.y); out16[4 * i + 2] = to_bf16(o.z); out16[4 * i + 3] = to_bf16(o.w); }
   }
@@ -668,18 +673,30 @@ static int head1_dgrad(cudaStream_t st, const float* d, const float* w, const fl
 // 3-hidden-layer trunk forward: X[rows,in] -> h1,h2,h3
 static int trunk_forward(cudaStream_t st, const Ctx& c, const ChainWs& ws, const float* X, int ldx, int in_dim, int rows, long long o_w0,
                          long long o_b0, long long o_w1, long long o_b1, long long o_w2, long long o_b2,
-                         const float* nmean = nullptr, const float* nstd = nullptr) {
+                         const float* nmean = nullptr, const float* nstd = nullptr, float* w0_pad = nullptr) {
   const float* P = F(c.params);
   const int H1 = (int)c.hid_a1, H2 = (int)c.hid_a2, H3 = (int)c.hid_a3, pr = (int)c.precision;
+  const int OL = (int)c.obs_ld;
   if (nmean && pr != 0 && (in_dim & 3) == 0 && ldx == in_dim && rows <= c.mb_rows + 1) {
     // tensor-core modes: normalise into the minibatch scratch first (TMA cannot apply it on load), then the TC tile
-    const long long n4 = (long long)rows * in_dim / 4;
+    const long long n4 = (long long)rows * OL / 4;
     int bl = (int)((n4 + 255) / 256); if (bl > 148 * 8) bl = 148 * 8;
-    obs_normalize_kernel<<<bl, 256, 0, st>>>(X, nmean, nstd, rows, in_dim, F(c.xn), twin16(c.xn));
+    obs_normalize_kernel<<<bl, 256, 0, st>>>(X, nmean, nstd, rows, in_dim, OL, F(c.xn), twin16(c.xn));
     ADDK_CHECK_LAUNCH();
-    X = F(c.xn); nmean = nullptr; nstd = nullptr;
+    X = F(c.xn); ldx = OL; nmean = nullptr; nstd = nullptr;
   }
-  TRY(gemm(st, nmean ? 0 : pr, X, ldx, 0, P + o_w0, in_dim, 1, ws.h1, H1, rows, H1, in_dim, P + o_b0, 1, nullptr, 0, 1,
+  // First-layer weight [H1, in_dim]: a row pitch of 264 elements is 528 bytes in the 16-bit twins -- legal for TMA (16)
+  // but every other row starts in the middle of a 32-byte sector, and the layer's main loop then waits for its loads
+  // (measured 60 us at K = 264 against 39 / 44 us at K = 256 / 288).  The tensor-core modes therefore read a copy
+  // with rows padded to obs_ld (a multiple of 16), like the discriminator's wd0_pad; xn has the same pitch.
+  const float* W0 = P + o_w0;
+  int ldw = in_dim;
+  if (w0_pad && !nmean && pr != 0 && X == F(c.xn) && OL > in_dim) {
+    pad_rows_kernel<<<(H1 * OL + 255) / 256, 256, 0, st>>>(P + o_w0, H1, in_dim, OL, w0_pad, twin16(w0_pad));
+    ADDK_CHECK_LAUNCH();
+    W0 = w0_pad; ldw = OL;
+  }
+  TRY(gemm(st, nmean ? 0 : pr, X, ldx, 0, W0, ldw, 1, ws.h1, H1, rows, H1, in_dim, P + o_b0, 1, nullptr, 0, 1,
            nmean, nstd));
   TRY(gemm(st, pr, ws.h1, H1, 0, P + o_w1, H1, 1, ws.h2, H2, rows, H2, H1, P + o_b1, 1));
   TRY(gemm(st, pr, ws.h2, H2, 0, P + o_w2, H2, 1, ws.h3, H3, rows, H3, H2, P + o_b2, 1));
@@ -750,7 +767,7 @@ extern "C" int addk_update_minibatch(void* stream, void* ctx_host, const long lo
   if (!ctx_host || !idx || step_index < 0) return ADDK_ERR_ARG;
   const Ctx& c = *(const Ctx*)ctx_host;
   cudaStream_t st = (cudaStream_t)stream;
-  const int M = (int)c.mb_rows, R = M + 1, OD = (int)c.obs_dim, AD = (int)c.act_dim, AL = (int)c.act_ld;
+  const int M = (int)c.mb_rows, R = M + 1, OD = (int)c.obs_dim, OL = (int)c.obs_ld, AD = (int)c.act_dim, AL = (int)c.act_ld;
   const int DD = (int)c.disc_dim, DL = (int)c.disc_ld, pr = (int)c.precision, S = (int)c.split_k;
   const int H1 = (int)c.hid_a1, H3 = (int)c.hid_a3, E1 = (int)c.hid_d1, E2 = (int)c.hid_d2;
   const long long P = c.num_params;
@@ -768,13 +785,13 @@ extern "C" int addk_update_minibatch(void* stream, void* ctx_host, const long lo
   TRY(h3_params(c, st, 0));
 
   gather_minibatch_kernel<<<(M + 7) / 8, 256, 0, st>>>(
-      idx, M, OD, AD, AL, DD, DL, F(c.buf_obs), F(c.buf_action), F(c.buf_a_logp), F(c.buf_adv), F(c.buf_tar_val),
+      idx, M, OD, OL, AD, AL, DD, DL, F(c.buf_obs), F(c.buf_action), F(c.buf_a_logp), F(c.buf_adv), F(c.buf_tar_val),
       F(c.buf_mask), F(c.buf_disc_obs), F(c.buf_disc_demo), F(c.obs_mean), F(c.obs_std), F(c.a_mean), F(c.a_std),
       F(c.disc_mean_abs), F(c.xn), F(c.an), F(c.old_logp), F(c.adv), F(c.tar), F(c.mask), F(c.dn), cnt, twin16(c.xn), twin16(c.dn));
   ADDK_CHECK_LAUNCH();
 
   if (pr == 4) {      // twins of the inputs the chains share, before the streams fork
-    TRY(h3_prepare(c, st, F(c.xn), M, OD, OD));
+    TRY(h3_prepare(c, st, F(c.xn), M, OD, OL));
     TRY(h3_prepare(c, st, F(c.dn), R, DL, DL));
   }
 
@@ -798,7 +815,7 @@ extern "C" int addk_update_minibatch(void* stream, void* ctx_host, const long lo
   float* dpred_d = multi ? F(c.d_dpred) : F(c.dpred);
 
   // ---------------- actor (stream sa) ----------------
-  TRY(trunk_forward(sa, c, wa, F(c.xn), OD, OD, M, c.o_a_w0, c.o_a_b0, c.o_a_w1, c.o_a_b1, c.o_a_w2, c.o_a_b2));
+  TRY(trunk_forward(sa, c, wa, F(c.xn), OL, OD, M, c.o_a_w0, c.o_a_b0, c.o_a_w1, c.o_a_b1, c.o_a_w2, c.o_a_b2, nullptr, nullptr, F(c.wa0_pad)));
   TRY(gemm(sa, pr, wa.h3, H3, 0, W + c.o_a_wm, H3, 1, F(c.mean), AL, M, AD, H3, W + c.o_a_bm, 0));
   actor_loss_kernel<<<(M + 7) / 8, 256, 0, sa>>>(F(c.mean), F(c.an), F(c.logstd), F(c.old_logp), F(c.adv), F(c.mask), M,
                                                  AD, AL, (float)c.ppo_clip_ratio, (float)c.action_bound_weight, cnt,
@@ -806,17 +823,17 @@ extern "C" int addk_update_minibatch(void* stream, void* ctx_host, const long lo
   ADDK_CHECK_LAUNCH();
   TRY(wgrad(sa, c, wa, F(c.dmean), AL, wa.h3, H3, M, AD, H3, c.o_a_wm, c.o_a_bm, 0));
   TRY(gemm(sa, pr, F(c.dmean), AL, 0, W + c.o_a_wm, H3, 0, wa.g3, H3, M, H3, AD, nullptr, 0, wa.h3, H3));
-  TRY(trunk_backward(sa, c, wa, F(c.xn), OD, OD, M, c.o_a_w0, c.o_a_b0, c.o_a_w1, c.o_a_b1, c.o_a_w2, c.o_a_b2));
+  TRY(trunk_backward(sa, c, wa, F(c.xn), OL, OD, M, c.o_a_w0, c.o_a_b0, c.o_a_w1, c.o_a_b1, c.o_a_w2, c.o_a_b2));
 
   // ---------------- critic (stream sc) ----------------
-  TRY(trunk_forward(sc, c, wc, F(c.xn), OD, OD, M, c.o_c_w0, c.o_c_b0, c.o_c_w1, c.o_c_b1, c.o_c_w2, c.o_c_b2));
+  TRY(trunk_forward(sc, c, wc, F(c.xn), OL, OD, M, c.o_c_w0, c.o_c_b0, c.o_c_w1, c.o_c_b1, c.o_c_w2, c.o_c_b2, nullptr, nullptr, F(c.wc0_pad)));
   TRY(head1_forward(sc, wc.h3, H3, M, H3, W + c.o_c_wo, W + c.o_c_bo, F(c.pred)));
   critic_loss_kernel<<<(M + 255) / 256, 256, 0, sc>>>(F(c.pred), F(c.tar), M, (float)c.critic_loss_weight, F(c.dpred),
                                                       stats);
   ADDK_CHECK_LAUNCH();
   TRY(wgrad(sc, c, wc, F(c.dpred), 1, wc.h3, H3, M, 1, H3, c.o_c_wo, c.o_c_bo, 0));
   TRY(head1_dgrad(sc, F(c.dpred), W + c.o_c_wo, wc.h3, M, H3, wc.g3));
-  TRY(trunk_backward(sc, c, wc, F(c.xn), OD, OD, M, c.o_c_w0, c.o_c_b0, c.o_c_w1, c.o_c_b1, c.o_c_w2, c.o_c_b2));
+  TRY(trunk_backward(sc, c, wc, F(c.xn), OL, OD, M, c.o_c_w0, c.o_c_b0, c.o_c_w1, c.o_c_b1, c.o_c_w2, c.o_c_b2));
 
   // ---------------- discriminator (stream sd; R = M + 1 rows) ----------------
   float *e1 = wd.h1, *e2 = wd.h3, *dh2 = wd.g3, *dv1 = wd.g1, *du2 = wd.g2;
@@ -913,7 +930,7 @@ extern "C" int addk_actor_step(void* stream, void* ctx_host, const float* obs, c
   TRY(h3_params(c, st, 1));
   if (obs_rec) cudaMemcpyAsync(obs_rec, obs, (size_t)n * OD * sizeof(float), cudaMemcpyDeviceToDevice, st);
   TRY(trunk_forward(st, c, main_ws(c), obs, OD, OD, n, c.o_a_w0, c.o_a_b0, c.o_a_w1, c.o_a_b1, c.o_a_w2, c.o_a_b2, F(c.obs_mean),
-                    F(c.obs_std)));
+                    F(c.obs_std), F(c.wa0_pad)));
   TRY(gemm(st, (int)c.precision, F(c.h3), H3, 0, W + c.o_a_wm, H3, 1, F(c.mean), AL, n, AD, H3, W + c.o_a_bm, 0));
   sample_action_kernel<<<(n + 7) / 8, 256, 0, st>>>(F(c.mean), AL, F(c.logstd), noise, exp_mask, F(c.a_mean), F(c.a_std),
                                                     n, AD, action, a_logp, action_rec, logp_rec, mask_rec);
@@ -937,7 +954,7 @@ extern "C" int addk_critic_eval(void* stream, void* ctx_host, const float* obs, 
   for (long long r0 = 0; r0 < n; r0 += chunk) {
     int rows = (int)((n - r0 < chunk) ? n - r0 : chunk);
     TRY(trunk_forward(st, c, main_ws(c), obs + r0 * OD, OD, OD, rows, c.o_c_w0, c.o_c_b0, c.o_c_w1, c.o_c_b1, c.o_c_w2, c.o_c_b2,
-                      F(c.obs_mean), F(c.obs_std)));
+                      F(c.obs_mean), F(c.obs_std), F(c.wc0_pad)));
     TRY(head1_forward(st, F(c.h3), H3, rows, H3, W + c.o_c_wo, W + c.o_c_bo, vals + r0));
   }
   return ADDK_OK;

@@ -11,8 +11,9 @@ reps = int(sys.argv[3]) if len(sys.argv) > 3 else 5
 layout = sys.argv[4] if len(sys.argv) > 4 else "fwd"
 K = int(os.environ.get('GK', '1024')); N = int(os.environ.get('GN', '1024'))
 dev = "cuda:0"
-A = [torch.randn(M, K, device=dev) for _ in range(3)]
-W = torch.randn(N, K, device=dev) * 0.03
+LD = int(os.environ.get('GLD', str(K)))      # row pitch of A and W (fwd layout only): LD >= K
+A = [torch.randn(M, LD, device=dev) for _ in range(3)]
+W = torch.randn(N, LD, device=dev) * 0.03
 bias = torch.zeros(N, device=dev)
 Cc = [torch.empty(M, N, device=dev) for _ in range(2)]
 slabs = torch.empty(8, N, K, device=dev)
@@ -42,7 +43,7 @@ def launch(i):
     _lib.check(L.addk_gemm(_lib.stream(), C.byref(a), C.c_int(_lib.PRECISIONS[prec])), "addk_gemm")
 def make(i):
     if layout == "fwd":
-        a = _lib.AddkGemmArgs(A=A[i % 3].data_ptr(), lda=K, B=W.data_ptr(), ldb=K, C=Cc[i % 2].data_ptr(), ldc=N, M=M, N=N, K=K,
+        a = _lib.AddkGemmArgs(A=A[i % 3].data_ptr(), lda=LD, B=W.data_ptr(), ldb=LD, C=Cc[i % 2].data_ptr(), ldc=N, M=M, N=N, K=K,
                               bias=bias.data_ptr(), a_mean=None, a_std=None, relu_mask_src=None, ld_mask=0, trans_a=0, trans_b=1,
                               relu=1, split_k=1, accumulate=0, slab_stride=0, A16=None, B16=None, C16=None)
         return h3(a, TA[i % 3], TW)
