@@ -340,13 +340,13 @@ __device__ __forceinline__ bool epilogue_vec_ok(const Params& p, const float* Cz
 
 // One stage of the ring.  A: 128 (rows | columns) x BK k;  B: BN x BK k.  tf32x3 adds the "lo" halves and uses
 // BK = 16 (64-byte rows) so that four stages still fit; the single-pass mode uses BK = 32 (128-byte rows).
-template <int BN, bool X3, int CAP_KB = 200>
+template <int BN, bool X3>
 struct Cfg {
   static constexpr int BK = X3 ? 16 : 32;
   static constexpr int A_BYTES = BM * BK * 4;
   static constexpr int B_BYTES = BN * BK * 4;
   static constexpr int STAGE_BYTES = (A_BYTES + B_BYTES) * (X3 ? 2 : 1);
-  static constexpr int STAGES = (CAP_KB * 1024) / STAGE_BYTES > 6 ? 6 : (CAP_KB * 1024) / STAGE_BYTES;
+  static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 6 ? 6 : (200 * 1024) / STAGE_BYTES;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
   // tf32x3 keeps the small cross terms (lo.hi + hi.lo) in a second accumulator: the tensor core truncates its
   // fp32 accumulator after every instruction, so three accumulations per k-step into ONE accumulator would
@@ -608,10 +608,10 @@ constexpr int X3_CHUNK_KB = 16;
 // 32-instruction chunk) and leaves the random part (~3e-7).
 constexpr float X3_TRUNC_LOSS_PER_MMA = 1.7e-8f;
 
-template <int BN, int CAP_KB = 200, int MINB = 1>
-__global__ void __launch_bounds__(X3_THREADS, MINB)
+template <int BN>
+__global__ void __launch_bounds__(X3_THREADS, 1)
 gemm_tc_x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
-  using C = Cfg<BN, true, CAP_KB>;
+  using C = Cfg<BN, true>;
   constexpr int BK = C::BK;
   constexpr int CPW = BN / 2;                     // accumulator columns per worker thread
   constexpr int NCH = CPW / 32;                   // 32-column chunks per worker
@@ -816,18 +816,18 @@ gemm_tc_x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   }
 }
 
-template <int BN, int CAP_KB = 200, int MINB = 1>
+template <int BN>
 static int launch_x3(cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, dim3 grid) {
-  using C = Cfg<BN, true, CAP_KB>;
+  using C = Cfg<BN, true>;
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(gemm_tc_x3_kernel<BN, CAP_KB, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES) != cudaSuccess) {
+    if (cudaFuncSetAttribute(gemm_tc_x3_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES) != cudaSuccess) {
       addk_set_error("gemm_tc: cannot raise the dynamic shared memory limit");
       return ADDK_ERR_LAUNCH;
     }
     configured = true;
   }
-  gemm_tc_x3_kernel<BN, CAP_KB, MINB><<<grid, X3_THREADS, C::SMEM_BYTES, st>>>(ta, tb, p);
+  gemm_tc_x3_kernel<BN><<<grid, X3_THREADS, C::SMEM_BYTES, st>>>(ta, tb, p);
   return ADDK_OK;
 }
 
@@ -1426,10 +1426,7 @@ struct CfgH3 {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = 2 * (A_BYTES + B_BYTES);  // [A_hi | B_hi | A_lo | B_lo]
-#ifndef ADDK_H3_CAP_KB
-#define ADDK_H3_CAP_KB 200
-#endif
-  static constexpr int STAGES = (ADDK_H3_CAP_KB * 1024) / STAGE_BYTES > 6 ? 6 : (ADDK_H3_CAP_KB * 1024) / STAGE_BYTES;
+  static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 6 ? 6 : (200 * 1024) / STAGE_BYTES;
   static constexpr int EPI_BYTES = 8 * 32 * (BN / 2) * 4;      // epilogue staging: 8 warps x 32 rows x BN/2 floats
   static constexpr int RING_BYTES = STAGES * STAGE_BYTES > EPI_BYTES ? STAGES * STAGE_BYTES : EPI_BYTES;
   static constexpr int SMEM_BYTES = RING_BYTES + 1024 + 256;
@@ -1703,10 +1700,7 @@ struct CfgP {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = (SINGLE ? 1 : 2) * (A_BYTES + B_BYTES);
-#ifndef ADDK_H3P_EPI_COLS
-#define ADDK_H3P_EPI_COLS 64
-#endif
-  static constexpr int EPI_COLS = ADDK_H3P_EPI_COLS;                // columns per staging pass
+  static constexpr int EPI_COLS = 64;           // columns per staging pass (32: a 4th stage fits, but 128-byte row segments store 40 % slower)
   static constexpr int EPI_BYTES = 8 * 32 * EPI_COLS * 4;           // 8 worker warps x 32 rows x 64 floats
   static constexpr int STAGES = (226 * 1024 - EPI_BYTES) / STAGE_BYTES > 6 ? 6 : (226 * 1024 - EPI_BYTES) / STAGE_BYTES;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 + 256;
@@ -2030,10 +2024,9 @@ static int launch_h3p(cudaStream_t st, const CUtensorMap& tah, const CUtensorMap
     configured = true;
   }
   pp.tiles_m = (M + BM - 1) / BM; pp.tiles_n = (N + BN - 1) / BN; pp.total_tiles = pp.tiles_m * pp.tiles_n * split;
-  static int cap = -1;       // experiment: fewer CTAs per layer so that layers of different streams run side by side
-  if (cap < 0) { const char* e = getenv("ADDK_H3_GRID"); cap = e ? atoi(e) : 0; }
-  const int nsm = cap > 0 && cap < sm_count() ? cap : sm_count();
-  const int grid = pp.total_tiles < nsm ? pp.total_tiles : nsm;
+  // (74 / 99 / 128 CTAs per layer, so that layers of the three streams run side by side, measured the same 2.6 ms per
+  // optimizer step as one CTA per SM)
+  const int grid = pp.total_tiles < sm_count() ? pp.total_tiles : sm_count();
   gemm_tc_h3p_kernel<BN, SINGLE><<<grid, X3_THREADS, C::SMEM_BYTES, st>>>(tah, tal, tbh, tbl, pp);
   return ADDK_OK;
 }
@@ -2363,15 +2356,6 @@ int addk_gemm_tc(cudaStream_t st, const addk_gemm_args& a, int precision) {
   ok = ok && (p.b_mn ? make_map(&tb, a.B, a.N, a.K, a.ldb, 32, BK, true) : make_map(&tb, a.B, a.K, a.N, a.ldb, BK, BN, false));
   if (!ok) return addk::sgemm_launch(st, a);
   dim3 grid((a.N + BN - 1) / BN, (a.M + BM - 1) / BM, split);
-  {
-    static int small = -1;
-    if (small < 0) { const char* e = getenv("ADDK_TC_X3_SMALL"); small = e ? atoi(e) : 0; }
-    if (x3 && BN == 256 && small) {        // experiment: 128x128 tiles, two CTAs per SM (one's epilogue overlaps the other's main loop)
-      if (!p.b_mn && !make_map(&tb, a.B, a.K, a.N, a.ldb, BK, 128, false)) return addk::sgemm_launch(st, a);
-      dim3 g2((a.N + 127) / 128, (a.M + BM - 1) / BM, split);
-      return launch_x3<128, 100, 2>(st, ta, tb, p, g2);
-    }
-  }
   if (x3 && BN == 256 && a.M > BM && addk_tc_pair_enabled()) {
     // CTA-pair kernel: each CTA of the pair stages 128 rows of B -> its tensor-map box has 128 rows
     if (!p.b_mn && !make_map(&tb, a.B, a.K, a.N, a.ldb, BK, Cfg2::BN / 2, false)) return addk::sgemm_launch(st, a);

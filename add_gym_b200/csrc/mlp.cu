@@ -52,28 +52,69 @@ __global__ void gather_minibatch_kernel(const long long* __restrict__ idx, int M
                                         float* __restrict__ adv, float* __restrict__ tar, float* __restrict__ mask,
                                         float* __restrict__ dn, int* __restrict__ cnt, uint16_t* __restrict__ xn16,
                                         uint16_t* __restrict__ dn16) {
-  int i = blockIdx.x * (blockDim.x / 32) + (threadIdx.x / 32);
-  int lane = threadIdx.x & 31;
-  if (i >= M) return;
-  const size_t s = (size_t)idx[i];
-  for (int c = lane; c < obs_ld; c += 32) {           // columns obs_dim .. obs_ld-1 are alignment padding (zeros)
-    const float v = c < obs_dim ? sub_rn(buf_obs[s * obs_dim + c], obs_mean[c]) / obs_std[c] : 0.f;
-    xn[(size_t)i * obs_ld + c] = v;
-    if (xn16) xn16[(size_t)i * obs_ld + c] = to_bf16(v);
+  __shared__ int s_cnt;
+  if (threadIdx.x == 0) s_cnt = 0;
+  __syncthreads();
+  const int i = blockIdx.x * (blockDim.x / 32) + (threadIdx.x / 32);
+  const int lane = threadIdx.x & 31;
+  if (i < M) {
+    const size_t s = (size_t)idx[i];
+    // same arithmetic per element as before ((x - mean) / std with a separate subtraction), 128- / 64-bit accesses where
+    // the row geometry allows: obs rows are 16-byte aligned when obs_dim % 4 == 0, disc rows 8-byte when disc_dim % 2 == 0
+    if ((obs_dim & 3) == 0 && (obs_ld & 3) == 0) {
+      const float* src = buf_obs + s * obs_dim;
+      float* dst = xn + (size_t)i * obs_ld;
+      for (int c = 4 * lane; c < obs_ld; c += 128) {        // columns obs_dim .. obs_ld-1 are alignment padding (zeros)
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c < obs_dim) {
+          const float4 v = ldg4(src + c), m = ldg4(obs_mean + c), d = ldg4(obs_std + c);
+          o = make_float4(sub_rn(v.x, m.x) / d.x, sub_rn(v.y, m.y) / d.y, sub_rn(v.z, m.z) / d.z, sub_rn(v.w, m.w) / d.w);
+        }
+        stg4(dst + c, o);
+        if (xn16) {
+          uint16_t* d16 = xn16 + (size_t)i * obs_ld + c;
+          d16[0] = to_bf16(o.x); d16[1] = to_bf16(o.y); d16[2] = to_bf16(o.z); d16[3] = to_bf16(o.w);
+        }
+      }
+    } else {
+      for (int c = lane; c < obs_ld; c += 32) {
+        const float v = c < obs_dim ? sub_rn(buf_obs[s * obs_dim + c], obs_mean[c]) / obs_std[c] : 0.f;
+        xn[(size_t)i * obs_ld + c] = v;
+        if (xn16) xn16[(size_t)i * obs_ld + c] = to_bf16(v);
+      }
+    }
+    for (int c = lane; c < act_ld; c += 32)
+      an[(size_t)i * act_ld + c] = c < act_dim ? sub_rn(buf_action[s * act_dim + c], a_mean[c]) / a_std[c] : 0.f;
+    if ((disc_dim & 1) == 0 && (disc_ld & 1) == 0) {
+      const float* pd = buf_demo + s * disc_dim;
+      const float* po = buf_dobs + s * disc_dim;
+      float* dst = dn + (size_t)i * disc_ld;
+      for (int c = 2 * lane; c < disc_ld; c += 64) {
+        float2 o = make_float2(0.f, 0.f);
+        if (c < disc_dim) {
+          const float2 a = __ldg(reinterpret_cast<const float2*>(pd + c)), b = __ldg(reinterpret_cast<const float2*>(po + c));
+          const float2 m = __ldg(reinterpret_cast<const float2*>(mean_abs + c));
+          o = make_float2(sub_rn(a.x, b.x) / fmaxf(m.x, 1e-4f), sub_rn(a.y, b.y) / fmaxf(m.y, 1e-4f));
+        }
+        *reinterpret_cast<float2*>(dst + c) = o;
+        if (dn16) { dn16[(size_t)i * disc_ld + c] = to_bf16(o.x); dn16[(size_t)i * disc_ld + c + 1] = to_bf16(o.y); }
+      }
+    } else {
+      for (int c = lane; c < disc_ld; c += 32) {
+        const float v = c < disc_dim ? sub_rn(buf_demo[s * disc_dim + c], buf_dobs[s * disc_dim + c]) / fmaxf(mean_abs[c], 1e-4f) : 0.f;
+        dn[(size_t)i * disc_ld + c] = v;
+        if (dn16) dn16[(size_t)i * disc_ld + c] = to_bf16(v);
+      }
+    }
+    if (lane == 0) {
+      old_logp[i] = buf_logp[s]; adv[i] = buf_adv[s]; tar[i] = buf_tar[s];
+      const float mk = buf_mask[s];
+      mask[i] = mk;
+      if (mk == 1.0f) atomicAdd(&s_cnt, 1);
+    }
   }
-  for (int c = lane; c < act_ld; c += 32)
-    an[(size_t)i * act_ld + c] = c < act_dim ? sub_rn(buf_action[s * act_dim + c], a_mean[c]) / a_std[c] : 0.f;
-  for (int c = lane; c < disc_ld; c += 32) {
-    const float v = c < disc_dim ? sub_rn(buf_demo[s * disc_dim + c], buf_dobs[s * disc_dim + c]) / fmaxf(mean_abs[c], 1e-4f) : 0.f;
-    dn[(size_t)i * disc_ld + c] = v;
-    if (dn16) dn16[(size_t)i * disc_ld + c] = to_bf16(v);
-  }
-  if (lane == 0) {
-    old_logp[i] = buf_logp[s]; adv[i] = buf_adv[s]; tar[i] = buf_tar[s];
-    float mk = buf_mask[s];
-    mask[i] = mk;
-    if (mk == 1.0f) atomicAdd(cnt, 1);
-  }
+  __syncthreads();
+  if (threadIdx.x == 0 && s_cnt) atomicAdd(cnt, s_cnt);       // one global atomic per block instead of one per row
 }
 
 __device__ __forceinline__ float gaussian_logp(float sq_sum, float logstd_sum, int dim) {
