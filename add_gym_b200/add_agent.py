@@ -256,7 +256,7 @@ class ADDAgent(torch.nn.Module):
         h3 = m.precision == _lib.PRECISIONS["f16x3"]      # two fp16 planes (hi, lo) per twin + one max|x| word per tensor
         self._arena16 = torch.zeros(2 * total if h3 else (total if bf16 else 8), device=dev, dtype=torch.bfloat16)
         self._params16 = torch.zeros(2 * m.num_params if h3 else (m.num_params if bf16 else 8), device=dev, dtype=torch.bfloat16)
-        self._amax_slots = torch.zeros(2 * (1 + 4 * 64), device=dev, dtype=torch.int32) if h3 else None
+        self._amax_slots = torch.zeros(2 * (1 + 4 * 128), device=dev, dtype=torch.int32) if h3 else None
         carve = {k: self._arena[offs[k]:offs[k] + int(np.prod(shp))].view(shp) for k, shp in shapes.items()}
         self._ws = dict(
             carve, old_logp=z(R), adv=z(R), tar=z(R), mask=z(R), pred=z(R), dpred=z(R), ones=torch.ones(R, device=dev),

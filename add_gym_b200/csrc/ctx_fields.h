@@ -73,7 +73,7 @@ ADDK_PTR(arena16)       // bf16 arena, same element offsets
 ADDK_PTR(params16)      // [P] bf16
 // ---- precision "f16x3": arena16 / params16 hold TWO fp16 planes each (hi, then lo arena_elems / num_params elements
 //      later) and amax_slots the max|x| words of the twins (slot 0 = the parameter vector); see csrc/gemm_tc.cu
-ADDK_PTR(amax_slots)    // [2 * (1 + 4 * 64)] uint32: {sticky scale word, max|x|} per twin (NULL unless precision == f16x3)
+ADDK_PTR(amax_slots)    // [2 * (1 + 4 * 128)] uint32: {sticky scale word, max|x|} per twin (NULL unless precision == f16x3)
 // ---- second and third workspace sets: the critic and the discriminator chains of one optimizer step run on their
 //      own streams next to the actor's (n_streams == 3), so the tail wave of one chain's dense layer overlaps the
 //      next chain's tiles; all NULL / n_streams == 1 = the three chains run back to back on the caller's stream

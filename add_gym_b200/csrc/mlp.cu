@@ -541,12 +541,15 @@ static thread_local const addk_update_ctx* g_twin_ctx = nullptr;
 // gradient AND the weight gradient).  This table is host-side bookkeeping in ISSUE order; the kernels themselves are
 // stream-ordered, so a twin may only be shared by calls on one stream -- tensors read by several chains (xn, dn, the
 // parameters) are converted before the streams fork.  Slot 0 belongs to the flat parameter vector.
-struct TwinEnt { const float* p; long long rows; int cols, ld; cudaStream_t st; bool valid, shared, amax_known; };
-static thread_local TwinEnt g_tw[63];
+struct TwinEnt { const float* p; long long rows; int cols, ld; cudaStream_t st; bool valid, shared, amax_known; int slot; };
+constexpr int TWIN_ENTRIES = 63, TWIN_SLOTS = 128;       // slots per entry point; slot 0 of the array = the parameters
+static thread_local TwinEnt g_tw[TWIN_ENTRIES];
 static thread_local int g_ntw = 0;
-static thread_local int g_slot_base = 0;       // each entry point owns 64 slots, so the sticky scale words keep their tensors
-static void twin_reset(int entry_point) { g_ntw = 0; g_slot_base = 64 * entry_point; }
-static uint32_t* twin_slot(const addk_update_ctx& c, int e) { return (uint32_t*)c.amax_slots + 2 * (1 + g_slot_base + e); }
+static thread_local int g_slot_base = 0;       // each entry point owns TWIN_SLOTS slots
+static thread_local int g_next_slot = 0;       // slots [TWIN_ENTRIES, TWIN_SLOTS) are handed out once per call, pre-zeroed
+static void twin_reset(int entry_point) { g_ntw = 0; g_slot_base = TWIN_SLOTS * entry_point; g_next_slot = TWIN_ENTRIES; }
+static uint32_t* slot_ptr(const addk_update_ctx& c, int slot) { return (uint32_t*)c.amax_slots + 2 * (1 + g_slot_base + slot); }
+static uint32_t* twin_slot(const addk_update_ctx& c, int e) { return slot_ptr(c, g_tw[e].slot); }
 static void twin_invalidate(const void* p, size_t bytes) {
   const char* b = (const char*)p;
   for (int i = 0; i < g_ntw; ++i) {
@@ -570,9 +573,9 @@ static H3Op h3_operand(const addk_update_ctx& c, cudaStream_t st, const float* p
   int e = -1;
   for (int i = 0; i < g_ntw; ++i) if (g_tw[i].p == p) { e = i; break; }
   if (e < 0) {
-    if (g_ntw >= 63) return o;
+    if (g_ntw >= TWIN_ENTRIES) return o;
     e = g_ntw++;
-    g_tw[e] = TwinEnt{p, 0, 0, 0, nullptr, false, false, false};
+    g_tw[e] = TwinEnt{p, 0, 0, 0, nullptr, false, false, false, e};
   }
   TwinEnt& t = g_tw[e];
   o.hi = (const uint16_t*)c.arena16 + (p - a0); o.plane = c.arena_elems; o.amax = twin_slot(c, e);
@@ -600,6 +603,10 @@ static int h3_params(const addk_update_ctx& c, cudaStream_t st, int entry_point)
   if (c.precision != 4) return ADDK_OK;
   twin_reset(entry_point);
   if (!c.params16 || !c.amax_slots) { addk_set_error("f16x3: the context has no parameter twin / max|x| slots"); return ADDK_ERR_ARG; }
+  // the once-per-call slots: a dense layer that leaves max|C| behind takes a fresh, already zeroed one (no launch per layer)
+  if (cudaMemsetAsync(slot_ptr(c, TWIN_ENTRIES), 0, 2 * sizeof(uint32_t) * (TWIN_SLOTS - TWIN_ENTRIES), st) != cudaSuccess) {
+    addk_set_error("f16x3: memset of the max|x| slots failed"); return ADDK_ERR_LAUNCH;
+  }
   return addk_f16x3_convert(st, (const float*)c.params, 1, (int)c.num_params, (int)c.num_params, c.params16, c.num_params,
                             (uint32_t*)c.amax_slots);
 }
@@ -647,15 +654,18 @@ static int gemm(cudaStream_t st, int prec, const float* A, int lda, int ta, cons
       if (a0 && C >= a0 && C < a0 + c.arena_elems) {
         int e = -1;
         for (int i = 0; i < g_ntw; ++i) if (g_tw[i].p == C) { e = i; break; }
-        if (e < 0 && g_ntw < 63) { e = g_ntw++; g_tw[e] = TwinEnt{C, 0, 0, 0, nullptr, false, false, false}; }
+        if (e < 0 && g_ntw < TWIN_ENTRIES) { e = g_ntw++; g_tw[e] = TwinEnt{C, 0, 0, 0, nullptr, false, false, false, e}; }
         if (e >= 0) {
-          uint32_t* slot = twin_slot(c, e);
           // Letting the epilogue write C's planes too (sticky scale word, prep -> layer -> repair) is implemented and
           // tested but off: measured at 4096 envs it removes 0.18 ms of split passes per optimizer step and adds 0.25 ms
           // to the dense layers (the epilogue's 8-byte stores are far from the split kernel's 6 TB/s).
           static int fused = -1;
           if (fused < 0) { const char* ev = getenv("ADDK_H3_FUSED_PLANES"); fused = ev ? atoi(ev) : 0; }
-          if (addk_f16x3_prep(st, slot, fused) == ADDK_OK) {     // max <- 0, W <- scale in force | 0
+          bool ready = false;
+          if (!fused && g_next_slot < TWIN_SLOTS) { g_tw[e].slot = g_next_slot++; ready = true; }     // zeroed by h3_params
+          else { g_tw[e].slot = e; }
+          uint32_t* slot = twin_slot(c, e);
+          if (ready || addk_f16x3_prep(st, slot, fused) == ADDK_OK) {     // max <- 0, W <- scale in force | 0
             TwinEnt& t = g_tw[e];
             t.rows = M; t.cols = N; t.ld = ldc; t.st = st; t.valid = false; t.shared = false; t.amax_known = true;
             a.c_amax = slot;
