@@ -202,7 +202,7 @@ def run_b200(args):
         stage = {"rollout": 0.0, "build_train_data": 0.0, "update": 0.0, "normalizers": 0.0}
         ev = lambda: torch.cuda.Event(enable_timing=True)
         info_host = None
-        for _ in range(W):
+        for _ in range(max(W, 2)):      # at least two: the second rollout captures the CUDA graphs of the rollout step
             info = agent._train_iter()
             if e2e:
                 info_host = {k: float(v) for k, v in info.items()}
@@ -329,7 +329,9 @@ def run_b200(args):
                   "bf16": "bf16 (fp32 accumulate, fp32 master weights)",
                   "f16x3": "f32 (fp16 hi/lo split on the tensor cores, fp32 accumulate)"}[args.precision],
         "data": "synthetic",
-        "config": {"workload": "BASELINE configs[1]: G1 walk1_subject1_trimmed, %d envs/GPU, %s MLPs, one iteration = "
+        "config": {"workload": ("BASELINE configs[1]" if N == 4096 else "BASELINE configs[4] shape (physics-free synthetic-state benchmark)" if N == 32768
+                                else "BASELINE configs[1] at another env count") +
+                               ": G1 walk1_subject1_trimmed, %d envs/GPU, %s MLPs, one iteration = "
                                "32-step rollout + build_train_data + 5x8 ADD/PPO minibatches; synthetic engine stands in "
                                "for Genesis (not installed), scene.step() timed separately and excluded" % (N, args.precision),
                    "envs_per_gpu": N, "steps_per_iter": T, "minibatch": 4 * N, "optimizer_steps": 40,
