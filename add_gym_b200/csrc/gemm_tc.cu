@@ -2040,9 +2040,14 @@ __global__ void h3_amax_kernel(const float* __restrict__ x, long long rows, int 
     const int c4 = cols >> 2;
     if (flat) {
       const long long n4 = rows * c4;
-      for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
-        const float4 v = reinterpret_cast<const float4*>(x)[i];
-        m = max(max(m, __float_as_uint(fabsf(v.x))), max(__float_as_uint(fabsf(v.y)), max(__float_as_uint(fabsf(v.z)), __float_as_uint(fabsf(v.w)))));
+      const long long step = (long long)gridDim.x * blockDim.x;
+      for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < n4; i0 += 4 * step) {     // 4 loads in flight
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = i0 + u * step < n4 ? reinterpret_cast<const float4*>(x)[i0 + u * step] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          m = max(max(m, __float_as_uint(fabsf(v[u].x))), max(__float_as_uint(fabsf(v[u].y)), max(__float_as_uint(fabsf(v[u].z)), __float_as_uint(fabsf(v[u].w)))));
       }
     } else {
       for (long long r = blockIdx.x; r < rows; r += gridDim.x)
@@ -2095,13 +2100,25 @@ __global__ void h3_split_kernel(const float* __restrict__ x, long long rows, int
     for (long long r = flat ? 0 : blockIdx.x; r < nrow; r += gridDim.x) {
       const long long start = flat ? (long long)blockIdx.x * blockDim.x + threadIdx.x : threadIdx.x;
       const long long step = flat ? (long long)gridDim.x * blockDim.x : blockDim.x;
-      for (long long c = start; c < per; c += step) {
-        const long long off = r * ld + 4 * c;
-        const float4 v = *reinterpret_cast<const float4*>(x + off);
-        uint16_t h[4], l[4];
-        h3_split1(v.x, s, h[0], l[0]); h3_split1(v.y, s, h[1], l[1]); h3_split1(v.z, s, h[2], l[2]); h3_split1(v.w, s, h[3], l[3]);
-        *reinterpret_cast<uint2*>(hi + off) = make_uint2((uint32_t)h[0] | ((uint32_t)h[1] << 16), (uint32_t)h[2] | ((uint32_t)h[3] << 16));
-        *reinterpret_cast<uint2*>(lo + off) = make_uint2((uint32_t)l[0] | ((uint32_t)l[1] << 16), (uint32_t)l[2] | ((uint32_t)l[3] << 16));
+      // back to front: the end of the tensor is what the producer (or the max pass) touched last and is still in L2;
+      // four 128-bit loads in flight per thread
+      for (long long c0 = start; c0 < per; c0 += 4 * step) {
+        float4 v[4];
+        long long off[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const long long c = c0 + u * step;
+          off[u] = c < per ? r * ld + 4 * (per - 1 - c) : -1;
+          if (off[u] >= 0) v[u] = *reinterpret_cast<const float4*>(x + off[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (off[u] < 0) continue;
+          uint2 h2, l2;
+          h3_split4(v[u], s, h2, l2);
+          *reinterpret_cast<uint2*>(hi + off[u]) = h2;
+          *reinterpret_cast<uint2*>(lo + off[u]) = l2;
+        }
       }
     }
   } else {
@@ -2113,9 +2130,9 @@ __global__ void h3_split_kernel(const float* __restrict__ x, long long rows, int
 static int h3_convert(cudaStream_t st, const float* x, long long rows, int cols, int ld, void* hi, long long plane, uint32_t* slot,
                       bool have_amax = false) {
   if (!x || !hi || !slot || rows <= 0 || cols <= 0 || ld < cols || plane <= 0) { addk_set_error("f16x3 convert: bad arguments"); return ADDK_ERR_ARG; }
-  // A few alignment-padding columns (29 -> 32 actions, 114 -> 120 discriminator inputs) are part of the tensor's own
+  // A few alignment-padding columns (29 -> 32 actions, 264 -> 272 observations) are part of the tensor's own
   // buffer and hold zeros: scan them too, flat and vectorised, instead of one block per 29-column row (18 -> 3 us)
-  if (cols < ld && ld - cols < 8 && (ld & 3) == 0) cols = ld;
+  if (cols < ld && ld - cols <= 8 && (ld & 3) == 0) cols = ld;
   const long long work = ld == cols ? (rows * cols / 4 + 255) / 256 : rows;
   const unsigned blocks = (unsigned)(work < 1 ? 1 : (work > 148 * 8 ? 148 * 8 : work));
   if (!have_amax) {      // otherwise the producing dense layer left max|x| in the slot (addk_gemm_args::c_amax)
