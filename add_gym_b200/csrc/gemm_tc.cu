@@ -2226,6 +2226,13 @@ extern "C" int addk_f16x3_convert(void* stream, const float* x, long long rows, 
   return ADDK_OK;
 }
 
+extern "C" int addk_f16x3_split(void* stream, const float* x, long long rows, int cols, int ld, void* hi16, long long plane,
+                                uint32_t* amax_slot) {
+  const int rc = addk_tc::h3_convert((cudaStream_t)stream, x, rows, cols, ld, hi16, plane, amax_slot, true);
+  if (rc != ADDK_OK) return rc;
+  ADDK_CHECK_LAUNCH();
+  return ADDK_OK;
+}
 extern "C" int addk_f16x3_prep(void* stream, uint32_t* slot, int keep_sticky_word) {
   if (!slot) return ADDK_ERR_ARG;
   addk_tc::h3_prep_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(slot, keep_sticky_word);

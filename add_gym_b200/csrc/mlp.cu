@@ -39,6 +39,25 @@ namespace addk {
 enum { ST_SURR = 0, ST_CLIP, ST_RATIO, ST_BOUND, ST_CRITIC, ST_BCE_NEG, ST_BCE_POS, ST_PEN, ST_NEG_LOGIT,
        ST_POS_LOGIT, ST_NEG_ACC, ST_POS_ACC, ST_WL_SQ, ST_W_SQ, ST_COUNT = 32 };
 
+// precision "f16x3": an elementwise kernel that produces a dense-layer operand also leaves max|x| of what it wrote in
+// the operand's slot (word [1]), so the conversion that follows is the split pass alone.  EVERY thread of the block
+// calls this once with its own maximum (no early returns before it): block reduction, then one thread looks at the slot
+// and issues the atomic only if it would raise it.  (A first version did this per warp: 262k warps polling one L2
+// address made the optimizer step 3 % slower than the separate max passes it replaced.)
+__device__ __forceinline__ void amax_commit(float v, uint32_t* slot) {
+  if (!slot) return;                                   // uniform across the grid
+  __shared__ uint32_t s_m[32];
+  uint32_t m = __reduce_max_sync(0xffffffffu, __float_as_uint(v));
+  if ((threadIdx.x & 31) == 0) s_m[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    m = threadIdx.x < (blockDim.x >> 5) ? s_m[threadIdx.x] : 0u;
+    m = __reduce_max_sync(0xffffffffu, m);
+    if (threadIdx.x == 0 && m > *reinterpret_cast<volatile uint32_t*>(slot + 1)) atomicMax(slot + 1, m);
+  }
+  __syncthreads();                                     // s_m is reused by the next call
+}
+
 // ---- ExperienceBuffer.sample + normalisation: one warp per minibatch row ---------------------------------
 __global__ void gather_minibatch_kernel(const long long* __restrict__ idx, int M, int obs_dim, int obs_ld, int act_dim, int act_ld,
                                         int disc_dim, int disc_ld, const float* __restrict__ buf_obs,
@@ -51,12 +70,13 @@ __global__ void gather_minibatch_kernel(const long long* __restrict__ idx, int M
                                         float* __restrict__ xn, float* __restrict__ an, float* __restrict__ old_logp,
                                         float* __restrict__ adv, float* __restrict__ tar, float* __restrict__ mask,
                                         float* __restrict__ dn, int* __restrict__ cnt, uint16_t* __restrict__ xn16,
-                                        uint16_t* __restrict__ dn16) {
+                                        uint16_t* __restrict__ dn16, uint32_t* xn_slot, uint32_t* dn_slot) {
   __shared__ int s_cnt;
   if (threadIdx.x == 0) s_cnt = 0;
   __syncthreads();
   const int i = blockIdx.x * (blockDim.x / 32) + (threadIdx.x / 32);
   const int lane = threadIdx.x & 31;
+  float vx = 0.f, vd = 0.f;                              // max|xn|, max|dn| of what this thread writes
   if (i < M) {
     const size_t s = (size_t)idx[i];
     // same arithmetic per element as before ((x - mean) / std with a separate subtraction), 128- / 64-bit accesses where
@@ -71,6 +91,7 @@ __global__ void gather_minibatch_kernel(const long long* __restrict__ idx, int M
           o = make_float4(sub_rn(v.x, m.x) / d.x, sub_rn(v.y, m.y) / d.y, sub_rn(v.z, m.z) / d.z, sub_rn(v.w, m.w) / d.w);
         }
         stg4(dst + c, o);
+        vx = fmaxf(fmaxf(vx, fmaxf(fabsf(o.x), fabsf(o.y))), fmaxf(fabsf(o.z), fabsf(o.w)));
         if (xn16) {
           uint16_t* d16 = xn16 + (size_t)i * obs_ld + c;
           d16[0] = to_bf16(o.x); d16[1] = to_bf16(o.y); d16[2] = to_bf16(o.z); d16[3] = to_bf16(o.w);
@@ -80,6 +101,7 @@ __global__ void gather_minibatch_kernel(const long long* __restrict__ idx, int M
       for (int c = lane; c < obs_ld; c += 32) {
         const float v = c < obs_dim ? sub_rn(buf_obs[s * obs_dim + c], obs_mean[c]) / obs_std[c] : 0.f;
         xn[(size_t)i * obs_ld + c] = v;
+        vx = fmaxf(vx, fabsf(v));
         if (xn16) xn16[(size_t)i * obs_ld + c] = to_bf16(v);
       }
     }
@@ -97,12 +119,14 @@ __global__ void gather_minibatch_kernel(const long long* __restrict__ idx, int M
           o = make_float2(sub_rn(a.x, b.x) / fmaxf(m.x, 1e-4f), sub_rn(a.y, b.y) / fmaxf(m.y, 1e-4f));
         }
         *reinterpret_cast<float2*>(dst + c) = o;
+        vd = fmaxf(vd, fmaxf(fabsf(o.x), fabsf(o.y)));
         if (dn16) { dn16[(size_t)i * disc_ld + c] = to_bf16(o.x); dn16[(size_t)i * disc_ld + c + 1] = to_bf16(o.y); }
       }
     } else {
       for (int c = lane; c < disc_ld; c += 32) {
         const float v = c < disc_dim ? sub_rn(buf_demo[s * disc_dim + c], buf_dobs[s * disc_dim + c]) / fmaxf(mean_abs[c], 1e-4f) : 0.f;
         dn[(size_t)i * disc_ld + c] = v;
+        vd = fmaxf(vd, fabsf(v));
         if (dn16) dn16[(size_t)i * disc_ld + c] = to_bf16(v);
       }
     }
@@ -113,6 +137,8 @@ __global__ void gather_minibatch_kernel(const long long* __restrict__ idx, int M
       if (mk == 1.0f) atomicAdd(&s_cnt, 1);
     }
   }
+  amax_commit(vx, xn_slot);
+  amax_commit(vd, dn_slot);
   __syncthreads();
   if (threadIdx.x == 0 && s_cnt) atomicAdd(cnt, s_cnt);       // one global atomic per block instead of one per row
 }
@@ -128,11 +154,13 @@ __global__ void actor_loss_kernel(const float* __restrict__ mean, const float* _
                                   const float* __restrict__ logstd, const float* __restrict__ old_logp,
                                   const float* __restrict__ adv, const float* __restrict__ mask, int M, int act_dim,
                                   int act_ld, float clip, float bound_w, const int* __restrict__ cnt,
-                                  float* __restrict__ dmean, double* __restrict__ stats, uint16_t* __restrict__ dmean16) {
+                                  float* __restrict__ dmean, double* __restrict__ stats, uint16_t* __restrict__ dmean16,
+                                  uint32_t* dmean_slot) {
   __shared__ double s_acc[8][4];
   const int warp = threadIdx.x / 32, lane = threadIdx.x & 31;
   const int i = blockIdx.x * (blockDim.x / 32) + warp;
   double a_surr = 0.0, a_clip = 0.0, a_ratio = 0.0, a_bound = 0.0;
+  float gabs = 0.f;
   if (i < M) {
     const bool on = mask[i] == 1.0f;
     float m = 0.f, d = 0.f, sd = 1.f, ls = 0.f;
@@ -167,12 +195,14 @@ __global__ void actor_loss_kernel(const float* __restrict__ mean, const float* _
       float g = 0.f;
       if (on && lane < act_dim) g = dlogp * (d / (sd * sd)) + bound_w * 2.0f * (vmin + vmax) / n;
       dmean[(size_t)i * act_ld + lane] = g;
+      gabs = fabsf(g);
       if (dmean16) dmean16[(size_t)i * act_ld + lane] = to_bf16(g);
     }
     if (on) {
       a_surr = surr; a_clip = fabsf(sub_rn(ratio, 1.0f)) > clip ? 1.0 : 0.0; a_ratio = ratio; a_bound = viol_sum;
     }
   }
+  amax_commit(gabs, dmean_slot);
   if (lane == 0) { s_acc[warp][0] = a_surr; s_acc[warp][1] = a_clip; s_acc[warp][2] = a_ratio; s_acc[warp][3] = a_bound; }
   __syncthreads();
   if (threadIdx.x < 4) {          // one atomic per statistic per block instead of one per row
@@ -226,36 +256,47 @@ __global__ void disc_loss_kernel(const float* __restrict__ logit, int M, float w
 // u2 = relu'(h2) * w3 (gradient of the logit w.r.t. the last hidden layer) and dh2 = dlogit * u2
 __global__ void disc_head_backward_kernel(const float* __restrict__ h2, const float* __restrict__ wl,
                                           const float* __restrict__ dlogit, int R, int H, float* __restrict__ u2,
-                                          float* __restrict__ dh2, uint16_t* __restrict__ u2_16, uint16_t* __restrict__ dh2_16) {
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (size_t)R * H) return;
-  int r = (int)(i / H), k = (int)(i - (size_t)r * H);
-  float u = h2[i] > 0.f ? wl[k] : 0.f;
-  u2[i] = u;
-  const float dh = dlogit[r] * u;
-  dh2[i] = dh;
-  if (u2_16) u2_16[i] = to_bf16(u);
-  if (dh2_16) dh2_16[i] = to_bf16(dh);
+                                          float* __restrict__ dh2, uint16_t* __restrict__ u2_16, uint16_t* __restrict__ dh2_16,
+                                          uint32_t* u2_slot, uint32_t* dh2_slot) {
+  float um = 0.f, dm = 0.f;
+  const size_t tot = (size_t)R * H;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (size_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / H), k = (int)(i - (size_t)r * H);
+    const float u = h2[i] > 0.f ? wl[k] : 0.f;
+    u2[i] = u;
+    const float dh = dlogit[r] * u;
+    dh2[i] = dh;
+    if (u2_16) u2_16[i] = to_bf16(u);
+    if (dh2_16) dh2_16[i] = to_bf16(dh);
+    um = fmaxf(um, fabsf(u)); dm = fmaxf(dm, fabsf(dh));
+  }
+  amax_commit(um, u2_slot);
+  amax_commit(dm, dh2_slot);
 }
 
 // gradient penalty on the input gradient: one warp per row (add_agent.py:167-178)
 __global__ void grad_penalty_kernel(const float* __restrict__ gx, int M, int R, int dim, int ld, float coef,
-                                    float* __restrict__ dg, double* __restrict__ stats, uint16_t* __restrict__ dg16) {
+                                    float* __restrict__ dg, double* __restrict__ stats, uint16_t* __restrict__ dg16,
+                                    uint32_t* dg_slot) {
   int i = blockIdx.x * (blockDim.x / 32) + (threadIdx.x / 32);
   int lane = threadIdx.x & 31;
-  if (i >= R) return;
-  float s = 0.f;
-  for (int c = lane; c < dim; c += 32) { float v = gx[(size_t)i * ld + c]; s += v * v; }
-  s = warp_sum(s);
-  float gn = sqrtf(s + 1e-8f);
-  float e = gn - 1.0f;
-  float sc = i < M ? coef * 2.0f * e / (gn * (float)M) : 0.f;
-  for (int c = lane; c < ld; c += 32) {
-    const float v = c < dim ? sc * gx[(size_t)i * ld + c] : 0.f;
-    dg[(size_t)i * ld + c] = v;
-    if (dg16) dg16[(size_t)i * ld + c] = to_bf16(v);
+  float vm = 0.f;
+  if (i < R) {                                        // whole warps
+    float s = 0.f;
+    for (int c = lane; c < dim; c += 32) { float v = gx[(size_t)i * ld + c]; s += v * v; }
+    s = warp_sum(s);
+    float gn = sqrtf(s + 1e-8f);
+    float e = gn - 1.0f;
+    float sc = i < M ? coef * 2.0f * e / (gn * (float)M) : 0.f;
+    for (int c = lane; c < ld; c += 32) {
+      const float v = c < dim ? sc * gx[(size_t)i * ld + c] : 0.f;
+      dg[(size_t)i * ld + c] = v;
+      vm = fmaxf(vm, fabsf(v));
+      if (dg16) dg16[(size_t)i * ld + c] = to_bf16(v);
+    }
+    if (lane == 0 && i < M) atomicAdd(stats + ST_PEN, (double)e * e);
   }
-  if (lane == 0 && i < M) atomicAdd(stats + ST_PEN, (double)e * e);
+  amax_commit(vm, dg_slot);
 }
 
 __global__ void sumsq_kernel(const float* __restrict__ x, long long n, double* __restrict__ out) {
@@ -370,8 +411,9 @@ __global__ void rowdot_kernel(const float* __restrict__ X, int ld, long long row
 
 // 1-output head input gradient through the ReLU: g[r, k] = (h[r, k] > 0) ? d[r] * w[k] : 0
 __global__ void outer_mask_kernel(const float* __restrict__ d, const float* __restrict__ w, const float* __restrict__ h,
-                                  long long rows, int K, float* __restrict__ g, uint16_t* __restrict__ g16) {
+                                  long long rows, int K, float* __restrict__ g, uint16_t* __restrict__ g16, uint32_t* g_slot) {
   const long long n4 = rows * K / 4;
+  float vm = 0.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     const long long r = (i * 4) / K;
     const int k = (int)((i * 4) % K);
@@ -380,8 +422,10 @@ __global__ void outer_mask_kernel(const float* __restrict__ d, const float* __re
     const float4 o = make_float4(m.x > 0.f ? dv * u.x : 0.f, m.y > 0.f ? dv * u.y : 0.f, m.z > 0.f ? dv * u.z : 0.f,
                                  m.w > 0.f ? dv * u.w : 0.f);
     stg4(g + 4 * i, o);
+    vm = fmaxf(fmaxf(vm, fmaxf(fabsf(o.x), fabsf(o.y))), fmaxf(fabsf(o.z), fabsf(o.w)));
     if (g16) { g16[4 * i] = to_bf16(o.x); g16[4 * i + 1] = to_bf16(o.y); g16[4 * i + 2] = to_bf16(o.z); g16[4 * i + 3] = to_bf16(o.w); }
   }
+  amax_commit(vm, g_slot);
 }
 
 struct Seg { long long begin, end; int nslabs; float l2; };
@@ -557,10 +601,10 @@ static void twin_invalidate(const void* p, size_t bytes) {
     if (q >= b && q < b + (bytes ? bytes : 1)) { g_tw[i].valid = false; g_tw[i].amax_known = false; }
   }
 }
-struct H3Op { const void* hi; long long plane; uint32_t* amax; int ready; };
+struct H3Op { const void* hi; long long plane; uint32_t* amax; int ready; long long full_rows; int full_cols; };
 // looks the operand up; on a miss the entry is created / refreshed and ready = 0 tells the library to convert first
 static H3Op h3_operand(const addk_update_ctx& c, cudaStream_t st, const float* p, long long rows, int cols, int ld) {
-  H3Op o{nullptr, 0, nullptr, 0};
+  H3Op o{nullptr, 0, nullptr, 0, rows, cols};
   uint32_t* slots = (uint32_t*)c.amax_slots;
   if (!slots || !p) return o;
   const float* p0 = (const float*)c.params;
@@ -579,14 +623,21 @@ static H3Op h3_operand(const addk_update_ctx& c, cudaStream_t st, const float* p
   }
   TwinEnt& t = g_tw[e];
   o.hi = (const uint16_t*)c.arena16 + (p - a0); o.plane = c.arena_elems; o.amax = twin_slot(c, e);
-  if (t.valid && t.cols == cols && t.ld == ld && rows <= t.rows && (t.st == st || t.shared)) { o.ready = 1; return o; }
+  // (a twin of [t.rows, t.cols] with the same pitch also serves a request for fewer rows / columns)
+  if (t.valid && cols <= t.cols && t.ld == ld && rows <= t.rows && (t.st == st || t.shared)) { o.ready = 1; return o; }
   // the call about to be issued converts it; the max pass is skipped when the producing dense layer left max|x| behind
-  if (t.amax_known && t.cols == cols && t.ld == ld && rows <= t.rows && t.st == st) o.ready = 2;
+  if (t.amax_known && cols <= t.cols && t.ld == ld && rows <= t.rows && t.st == st) {
+    o.ready = 2;
+    rows = t.rows; cols = t.cols;       // the caller converts everything max|x| covers: later, wider requests are served too
+    o.full_rows = rows; o.full_cols = cols;
+  }
   t.rows = rows; t.cols = cols; t.ld = ld; t.st = st; t.valid = true; t.shared = false; t.amax_known = false;
   return o;
 }
 extern "C" int addk_f16x3_convert(void* stream, const float* x, long long rows, int cols, int ld, void* hi16, long long plane,
                                   uint32_t* amax_slot);
+extern "C" int addk_f16x3_split(void* stream, const float* x, long long rows, int cols, int ld, void* hi16, long long plane,
+                                uint32_t* amax_slot);
 extern "C" int addk_f16x3_prep(void* stream, uint32_t* slot, int keep_sticky_word);
 extern "C" int addk_f16x3_repair(void* stream, const float* x, long long rows, int cols, int ld, void* hi16, long long plane,
                                  uint32_t* slot);
@@ -596,7 +647,33 @@ static int h3_prepare(const addk_update_ctx& c, cudaStream_t st, const float* p,
   if (!o.hi) { addk_set_error("f16x3: tensor has no twin"); return ADDK_ERR_ARG; }
   for (int i = 0; i < g_ntw; ++i) if (g_tw[i].p == p) g_tw[i].shared = true;     // converted before the fork: any stream may read it
   if (o.ready == 1) return ADDK_OK;
+  if (o.ready == 2)                     // the producing kernel left max|x| behind (amax_hook): the split pass alone
+    return addk_f16x3_split(st, p, o.full_rows, o.full_cols, ld, const_cast<void*>(o.hi), o.plane, o.amax);
   return addk_f16x3_convert(st, p, rows, cols, ld, const_cast<void*>(o.hi), o.plane, o.amax);
+}
+// An elementwise kernel is about to write the arena tensor p ([rows, cols], pitch ld) on stream st and will leave max|p|
+// in the returned slot (a fresh one, zeroed by h3_params); NULL = not in f16x3 mode / no slot left (the conversion
+// then runs its own max pass).  Call AFTER twin16(p), which forgets the old twin.
+static uint32_t* amax_hook(cudaStream_t st, const void* p, long long rows, int cols, int ld) {
+  const addk_update_ctx* c = g_twin_ctx;
+  if (!c || c->precision != 4 || !c->amax_slots || !p || g_next_slot >= TWIN_SLOTS) return nullptr;
+  static int on = -1;                                   // ADDK_H3_AMAX_HOOKS=0: A/B switch (separate max passes)
+  if (on < 0) { const char* ev = getenv("ADDK_H3_AMAX_HOOKS"); on = ev ? atoi(ev) : 1; }
+  if (!on) return nullptr;
+  const float* f = (const float*)p;
+  const float* a0 = (const float*)c->arena;
+  if (!a0 || f < a0 || f >= a0 + c->arena_elems) return nullptr;
+  int e = -1;
+  for (int i = 0; i < g_ntw; ++i) if (g_tw[i].p == f) { e = i; break; }
+  if (e < 0) {
+    if (g_ntw >= TWIN_ENTRIES) return nullptr;
+    e = g_ntw++;
+    g_tw[e] = TwinEnt{f, 0, 0, 0, nullptr, false, false, false, e};
+  }
+  TwinEnt& t = g_tw[e];
+  t.slot = g_next_slot++;
+  t.rows = rows; t.cols = cols; t.ld = ld; t.st = st; t.valid = false; t.shared = false; t.amax_known = true;
+  return twin_slot(*c, e);
 }
 // the fp16 planes of the whole flat parameter vector (one scale: slot 0)
 static int h3_params(const addk_update_ctx& c, cudaStream_t st, int entry_point) {
@@ -642,9 +719,20 @@ static int gemm(cudaStream_t st, int prec, const float* A, int lda, int ta, cons
       if (oa.hi && ob.hi) {
         a.A16 = oa.hi; a.a16_plane = oa.plane; a.a_amax = oa.amax; a.a16_ready = oa.ready;
         a.B16 = ob.hi; a.b16_plane = ob.plane; a.b_amax = ob.amax; a.b16_ready = ob.ready;
+        // max|x| already known (left by the producer): split the WHOLE region it covers here, not just this call's view
+        if (oa.ready == 2) {
+          const int rc = addk_f16x3_split(st, A, oa.full_rows, oa.full_cols, lda, const_cast<void*>(oa.hi), oa.plane, oa.amax);
+          if (rc != ADDK_OK) return rc;
+          a.a16_ready = 1;
+        }
+        if (ob.ready == 2) {
+          const int rc = addk_f16x3_split(st, B, ob.full_rows, ob.full_cols, ldb, const_cast<void*>(ob.hi), ob.plane, ob.amax);
+          if (rc != ADDK_OK) return rc;
+          a.b16_ready = 1;
+        }
       } else {                      // the call runs in tf32x3 and converts nothing: forget what h3_operand assumed
-        if (oa.hi && !oa.ready) twin_invalidate(A, 0);
-        if (ob.hi && !ob.ready) twin_invalidate(B, 0);
+        if (oa.hi && oa.ready != 1) twin_invalidate(A, 0);
+        if (ob.hi && ob.ready != 1) twin_invalidate(B, 0);
       }
     }
     twin_invalidate(C, (size_t)(split > 1 ? 1 : M) * ldc * sizeof(float));
@@ -716,7 +804,8 @@ static int head1_forward(cudaStream_t st, const float* X, int ld, long long rows
 static int head1_dgrad(cudaStream_t st, const float* d, const float* w, const float* h, long long rows, int K, float* g) {
   const long long n4 = rows * K / 4;
   long long bl = (n4 + 255) / 256; if (bl > 148 * 16) bl = 148 * 16;
-  outer_mask_kernel<<<(unsigned)bl, 256, 0, st>>>(d, w, h, rows, K, g, twin16(g));
+  uint16_t* g16 = twin16(g);
+  outer_mask_kernel<<<(unsigned)bl, 256, 0, st>>>(d, w, h, rows, K, g, g16, amax_hook(st, g, rows, K, K));
   ADDK_CHECK_LAUNCH();
   return ADDK_OK;
 }
@@ -835,10 +924,13 @@ extern "C" int addk_update_minibatch(void* stream, void* ctx_host, const long lo
   }
   TRY(h3_params(c, st, 0));
 
+  uint16_t* const xn16 = twin16(c.xn);
+  uint16_t* const dn16 = twin16(c.dn);
   gather_minibatch_kernel<<<(M + 7) / 8, 256, 0, st>>>(
       idx, M, OD, OL, AD, AL, DD, DL, F(c.buf_obs), F(c.buf_action), F(c.buf_a_logp), F(c.buf_adv), F(c.buf_tar_val),
       F(c.buf_mask), F(c.buf_disc_obs), F(c.buf_disc_demo), F(c.obs_mean), F(c.obs_std), F(c.a_mean), F(c.a_std),
-      F(c.disc_mean_abs), F(c.xn), F(c.an), F(c.old_logp), F(c.adv), F(c.tar), F(c.mask), F(c.dn), cnt, twin16(c.xn), twin16(c.dn));
+      F(c.disc_mean_abs), F(c.xn), F(c.an), F(c.old_logp), F(c.adv), F(c.tar), F(c.mask), F(c.dn), cnt, xn16, dn16,
+      amax_hook(st, c.xn, M, OL, OL), amax_hook(st, c.dn, R, DL, DL));      // (row M of dn is the constant zero row)
   ADDK_CHECK_LAUNCH();
 
   if (pr == 4) {      // twins of the inputs the chains share, before the streams fork
@@ -868,9 +960,10 @@ extern "C" int addk_update_minibatch(void* stream, void* ctx_host, const long lo
   // ---------------- actor (stream sa) ----------------
   TRY(trunk_forward(sa, c, wa, F(c.xn), OL, OD, M, c.o_a_w0, c.o_a_b0, c.o_a_w1, c.o_a_b1, c.o_a_w2, c.o_a_b2, nullptr, nullptr, F(c.wa0_pad)));
   TRY(gemm(sa, pr, wa.h3, H3, 0, W + c.o_a_wm, H3, 1, F(c.mean), AL, M, AD, H3, W + c.o_a_bm, 0));
+  uint16_t* const dmean16 = twin16(c.dmean);
   actor_loss_kernel<<<(M + 7) / 8, 256, 0, sa>>>(F(c.mean), F(c.an), F(c.logstd), F(c.old_logp), F(c.adv), F(c.mask), M,
                                                  AD, AL, (float)c.ppo_clip_ratio, (float)c.action_bound_weight, cnt,
-                                                 F(c.dmean), stats, twin16(c.dmean));
+                                                 F(c.dmean), stats, dmean16, amax_hook(sa, c.dmean, M, AL, AL));
   ADDK_CHECK_LAUNCH();
   TRY(wgrad(sa, c, wa, F(c.dmean), AL, wa.h3, H3, M, AD, H3, c.o_a_wm, c.o_a_bm, 0));
   TRY(gemm(sa, pr, F(c.dmean), AL, 0, W + c.o_a_wm, H3, 0, wa.g3, H3, M, H3, AD, nullptr, 0, wa.h3, H3));
@@ -898,15 +991,21 @@ extern "C" int addk_update_minibatch(void* stream, void* ctx_host, const long lo
   ADDK_CHECK_LAUNCH();
   {
     size_t tot = (size_t)R * E2;
-    disc_head_backward_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, sd>>>(e2, W + c.o_d_wl, dpred_d, R, E2, F(c.u2),
-                                                                            dh2, twin16(c.u2), twin16(dh2));
+    uint16_t* const u2_16 = twin16(c.u2);
+    uint16_t* const dh2_16 = twin16(dh2);
+    const size_t nb = (tot + 255) / 256;
+    disc_head_backward_kernel<<<(unsigned)(nb < 148 * 16 ? nb : 148 * 16), 256, 0, sd>>>(e2, W + c.o_d_wl, dpred_d, R, E2, F(c.u2),
+                                                                            dh2, u2_16, dh2_16, amax_hook(sd, c.u2, R, E2, E2),
+                                                                            amax_hook(sd, dh2, R, E2, E2));
     ADDK_CHECK_LAUNCH();
   }
   // input-gradient chain: u1 = m1 * (u2 W2), gx = u1 W1
   TRY(gemm(sd, pr, F(c.u2), E2, 0, W + c.o_d_w1, E1, 0, F(c.u1), E1, R, E1, E2, nullptr, 0, e1, E1));
   TRY(gemm(sd, pr, F(c.u1), E1, 0, Wd0, DL, 0, F(c.gx), DL, R, DL, E1));
+  uint16_t* const dg16 = twin16(c.dg);
   grad_penalty_kernel<<<(R + 7) / 8, 256, 0, sd>>>(F(c.gx), M, R, DD, DL,
-                                                   (float)(c.disc_loss_weight * c.disc_grad_penalty), F(c.dg), stats, twin16(c.dg));
+                                                   (float)(c.disc_loss_weight * c.disc_grad_penalty), F(c.dg), stats, dg16,
+                                                   amax_hook(sd, c.dg, R, DL, DL));
   ADDK_CHECK_LAUNCH();
   // backward of the chain (second set of slabs)
   TRY(gemm(sd, pr, F(c.u1), E1, 1, F(c.dg), DL, 0, F(c.slabs) + (size_t)S * P + c.o_d_w0, DD, E1, DD, R, nullptr, 0,
