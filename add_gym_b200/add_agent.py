@@ -263,6 +263,8 @@ class ADDAgent(torch.nn.Module):
             stats=z(32, dt=torch.float64), info=z(self._max_steps, 16), cnt=z(1, dt=torch.int32),
             slabs=z(2 * S, m.num_params), colsum_work=z(64 * 1024 + 64), arena=self._arena, arena16=self._arena16,
             params16=self._params16, amax_slots=self._amax_slots)
+        for k in ("colpart_a", "colpart_c", "colpart_d"):
+            self._ws[k] = z(148 * 8, 1024) if h3 else None
         if n_streams == 3:
             self._ws.update(d_pred=z(R), d_dpred=z(R), colsum_work_c=z(64 * 1024 + 64), colsum_work_d=z(64 * 1024 + 64))
         else:

@@ -87,6 +87,9 @@ ADDK_PTR(d_pred)        // [R]
 ADDK_PTR(d_dpred)       // [R]
 ADDK_PTR(colsum_work_c) // like colsum_work, for the critic's stream
 ADDK_PTR(colsum_work_d) // like colsum_work, for the discriminator's stream
+// ---- precision "f16x3": per-block column sums the split pass of a gradient tensor leaves behind (bias gradients), one
+//      buffer per chain: [148 * 8, 1024] floats each (NULL: the separate column-sum kernel runs)
+ADDK_PTR(colpart_a) ADDK_PTR(colpart_c) ADDK_PTR(colpart_d)
 
 ADDK_INT(obs_dim)
 ADDK_INT(act_dim)

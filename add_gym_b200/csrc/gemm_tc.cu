@@ -2085,8 +2085,13 @@ __global__ void h3_prep_kernel(uint32_t* slot, int keep) {
   slot[1] = 0u;
 }
 
-__global__ void h3_split_kernel(const float* __restrict__ x, long long rows, int cols, int ld, const uint32_t* __restrict__ slot,
-                                uint16_t* __restrict__ hi, uint16_t* __restrict__ lo, int repair) {
+// colpart (optional, flat vectorised tensors whose float4 columns divide the block: cols / 4 in {256, 128, 64, 32}):
+// the pass also leaves per-block column sums of x in colpart[blockIdx.x, 0 .. cols) -- every thread only ever sees one
+// float4 column (the grid stride is a multiple of cols / 4), so the bias gradient 1^T dY costs no extra read of dY.
+__global__ void __launch_bounds__(256)
+h3_split_kernel(const float* __restrict__ x, long long rows, int cols, int ld, const uint32_t* __restrict__ slot,
+                uint16_t* __restrict__ hi, uint16_t* __restrict__ lo, int repair, float* __restrict__ colpart) {
+  __shared__ float4 s_cs[256];
   float s, inv;
   h3_slot_scale(slot, s, inv);
   if (repair && h3_eff_word(slot[0], slot[1]) == slot[0]) return;      // the epilogue's planes stand
@@ -2102,6 +2107,7 @@ __global__ void h3_split_kernel(const float* __restrict__ x, long long rows, int
       const long long step = flat ? (long long)gridDim.x * blockDim.x : blockDim.x;
       // back to front: the end of the tensor is what the producer (or the max pass) touched last and is still in L2;
       // four 128-bit loads in flight per thread
+      float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
       for (long long c0 = start; c0 < per; c0 += 4 * step) {
         float4 v[4];
         long long off[4];
@@ -2118,6 +2124,17 @@ __global__ void h3_split_kernel(const float* __restrict__ x, long long rows, int
           h3_split4(v[u], s, h2, l2);
           *reinterpret_cast<uint2*>(hi + off[u]) = h2;
           *reinterpret_cast<uint2*>(lo + off[u]) = l2;
+          cs.x += v[u].x; cs.y += v[u].y; cs.z += v[u].z; cs.w += v[u].w;
+        }
+      }
+      if (colpart && flat) {                     // host guarantees: 256 % c4 == 0, grid stride % c4 == 0
+        s_cs[threadIdx.x] = cs;
+        __syncthreads();
+        if ((int)threadIdx.x < c4) {
+          float4 t = s_cs[threadIdx.x];
+          for (int j = threadIdx.x + c4; j < 256; j += c4) { t.x += s_cs[j].x; t.y += s_cs[j].y; t.z += s_cs[j].z; t.w += s_cs[j].w; }
+          // this thread's float4 column: element (per - 1 - c) with c = tid (mod c4)  ->  column group c4 - 1 - tid
+          *reinterpret_cast<float4*>(colpart + (size_t)blockIdx.x * cols + 4 * (c4 - 1 - (int)threadIdx.x)) = t;
         }
       }
     }
@@ -2128,18 +2145,25 @@ __global__ void h3_split_kernel(const float* __restrict__ x, long long rows, int
 }
 
 static int h3_convert(cudaStream_t st, const float* x, long long rows, int cols, int ld, void* hi, long long plane, uint32_t* slot,
-                      bool have_amax = false) {
+                      bool have_amax = false, float* colpart = nullptr, int* colpart_rows = nullptr) {
   if (!x || !hi || !slot || rows <= 0 || cols <= 0 || ld < cols || plane <= 0) { addk_set_error("f16x3 convert: bad arguments"); return ADDK_ERR_ARG; }
   // A few alignment-padding columns (29 -> 32 actions, 264 -> 272 observations) are part of the tensor's own
   // buffer and hold zeros: scan them too, flat and vectorised, instead of one block per 29-column row (18 -> 3 us)
   if (cols < ld && ld - cols <= 8 && (ld & 3) == 0) cols = ld;
   const long long work = ld == cols ? (rows * cols / 4 + 255) / 256 : rows;
   const unsigned blocks = (unsigned)(work < 1 ? 1 : (work > 148 * 8 ? 148 * 8 : work));
+  if (colpart) {         // column sums ride along only for flat tensors whose float4 columns divide the 256-thread block
+    const int c4 = cols / 4;
+    const bool okc = ld == cols && (cols & 3) == 0 && c4 >= 32 && c4 <= 256 && 256 % c4 == 0 &&
+                     ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && ((reinterpret_cast<uintptr_t>(colpart) & 15) == 0);
+    if (!okc) colpart = nullptr;
+    if (colpart_rows) *colpart_rows = colpart ? (int)blocks : 0;
+  }
   if (!have_amax) {      // otherwise the producing dense layer left max|x| in the slot (addk_gemm_args::c_amax)
     if (cudaMemsetAsync(slot, 0, 2 * sizeof(uint32_t), st) != cudaSuccess) { addk_set_error("f16x3 convert: memset failed"); return ADDK_ERR_LAUNCH; }
     h3_amax_kernel<<<blocks, 256, 0, st>>>(x, rows, cols, ld, slot);
   }
-  h3_split_kernel<<<blocks, 256, 0, st>>>(x, rows, cols, ld, slot, reinterpret_cast<uint16_t*>(hi), reinterpret_cast<uint16_t*>(hi) + plane, 0);
+  h3_split_kernel<<<blocks, 256, 0, st>>>(x, rows, cols, ld, slot, reinterpret_cast<uint16_t*>(hi), reinterpret_cast<uint16_t*>(hi) + plane, 0, colpart);
   return ADDK_OK;
 }
 
@@ -2227,8 +2251,10 @@ extern "C" int addk_f16x3_convert(void* stream, const float* x, long long rows, 
 }
 
 extern "C" int addk_f16x3_split(void* stream, const float* x, long long rows, int cols, int ld, void* hi16, long long plane,
-                                uint32_t* amax_slot) {
-  const int rc = addk_tc::h3_convert((cudaStream_t)stream, x, rows, cols, ld, hi16, plane, amax_slot, true);
+                                uint32_t* amax_slot, float* colsum_partials, int* colsum_partial_rows) {
+  if (colsum_partial_rows) *colsum_partial_rows = 0;
+  const int rc = addk_tc::h3_convert((cudaStream_t)stream, x, rows, cols, ld, hi16, plane, amax_slot, true, colsum_partials,
+                                     colsum_partial_rows);
   if (rc != ADDK_OK) return rc;
   ADDK_CHECK_LAUNCH();
   return ADDK_OK;
@@ -2245,7 +2271,7 @@ extern "C" int addk_f16x3_repair(void* stream, const float* x, long long rows, i
   const long long work = ld == cols ? (rows * cols / 4 + 255) / 256 : rows;
   const unsigned blocks = (unsigned)(work < 1 ? 1 : (work > 148 * 8 ? 148 * 8 : work));
   addk_tc::h3_split_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, rows, cols, ld, slot, reinterpret_cast<uint16_t*>(hi16),
-                                                                     reinterpret_cast<uint16_t*>(hi16) + plane, 1);
+                                                                     reinterpret_cast<uint16_t*>(hi16) + plane, 1, nullptr);
   ADDK_CHECK_LAUNCH();
   return ADDK_OK;
 }

@@ -428,6 +428,34 @@ __global__ void outer_mask_kernel(const float* __restrict__ d, const float* __re
   amax_commit(vm, g_slot);
 }
 
+// out[n] = sum over the `parts` per-block partial rows the f16x3 split pass left behind (h3_split_kernel), in a fixed
+// order; slabs 1..nsplit-1 are zeroed like colsum_slabs_kernel does.  grid = ceil(n / 128), 256 threads.
+__global__ void __launch_bounds__(256) colsum_parts_kernel(const float* __restrict__ part, int parts, int n, float* __restrict__ out,
+                                                           long long slab_stride, int nsplit) {
+  __shared__ float4 sm[8][32];
+  const int cq = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int col = (blockIdx.x * 32 + cq) * 4;
+  float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (col < n) {
+    for (int r = rl; r < parts; r += 8) {
+      const float4 v = ldg4(part + (size_t)r * n + col);
+      t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+    }
+  }
+  sm[rl][cq] = t;
+  __syncthreads();
+  if (rl == 0 && col < n) {
+    t = sm[0][cq];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) { t.x += sm[i][cq].x; t.y += sm[i][cq].y; t.z += sm[i][cq].z; t.w += sm[i][cq].w; }
+    const float tv[4] = {t.x, t.y, t.z, t.w};
+    for (int e = 0; e < 4 && col + e < n; ++e) {
+      out[col + e] = tv[e];
+      for (int z = 1; z < nsplit; ++z) out[(size_t)z * slab_stride + col + e] = 0.f;
+    }
+  }
+}
+
 struct Seg { long long begin, end; int nslabs; float l2; };
 struct SegTable { Seg s[24]; int n; long long P; };
 
@@ -562,7 +590,12 @@ typedef addk_update_ctx Ctx;
 struct ChainWs {
   float *h1, *h2, *h3, *g1, *g2, *g3;
   float* colsum_work;
+  float* colpart;       // [148 * 8, 1024] per-block column sums left behind by the f16x3 split pass (NULL: not available)
 };
+// wgrad() asks the conversion of its dY operand (inside gemm()) to leave column partial sums behind
+static thread_local const float* g_colpart_for = nullptr;
+static thread_local float* g_colpart_buf = nullptr;
+static thread_local int g_colpart_rows = 0;
 
 static int colsum(cudaStream_t st, const addk_update_ctx& c, const ChainWs& ws, const float* dY, int ld, int rows, int n,
                   float* out, const float* rw) {
@@ -637,7 +670,7 @@ static H3Op h3_operand(const addk_update_ctx& c, cudaStream_t st, const float* p
 extern "C" int addk_f16x3_convert(void* stream, const float* x, long long rows, int cols, int ld, void* hi16, long long plane,
                                   uint32_t* amax_slot);
 extern "C" int addk_f16x3_split(void* stream, const float* x, long long rows, int cols, int ld, void* hi16, long long plane,
-                                uint32_t* amax_slot);
+                                uint32_t* amax_slot, float* colsum_partials, int* colsum_partial_rows);
 extern "C" int addk_f16x3_prep(void* stream, uint32_t* slot, int keep_sticky_word);
 extern "C" int addk_f16x3_repair(void* stream, const float* x, long long rows, int cols, int ld, void* hi16, long long plane,
                                  uint32_t* slot);
@@ -648,7 +681,7 @@ static int h3_prepare(const addk_update_ctx& c, cudaStream_t st, const float* p,
   for (int i = 0; i < g_ntw; ++i) if (g_tw[i].p == p) g_tw[i].shared = true;     // converted before the fork: any stream may read it
   if (o.ready == 1) return ADDK_OK;
   if (o.ready == 2)                     // the producing kernel left max|x| behind (amax_hook): the split pass alone
-    return addk_f16x3_split(st, p, o.full_rows, o.full_cols, ld, const_cast<void*>(o.hi), o.plane, o.amax);
+    return addk_f16x3_split(st, p, o.full_rows, o.full_cols, ld, const_cast<void*>(o.hi), o.plane, o.amax, nullptr, nullptr);
   return addk_f16x3_convert(st, p, rows, cols, ld, const_cast<void*>(o.hi), o.plane, o.amax);
 }
 // An elementwise kernel is about to write the arena tensor p ([rows, cols], pitch ld) on stream st and will leave max|p|
@@ -721,12 +754,15 @@ static int gemm(cudaStream_t st, int prec, const float* A, int lda, int ta, cons
         a.B16 = ob.hi; a.b16_plane = ob.plane; a.b_amax = ob.amax; a.b16_ready = ob.ready;
         // max|x| already known (left by the producer): split the WHOLE region it covers here, not just this call's view
         if (oa.ready == 2) {
-          const int rc = addk_f16x3_split(st, A, oa.full_rows, oa.full_cols, lda, const_cast<void*>(oa.hi), oa.plane, oa.amax);
+          const bool want = g_colpart_buf && g_colpart_for == A && oa.full_rows == (ta ? K : M) && oa.full_cols == (ta ? M : K);
+          const int rc = addk_f16x3_split(st, A, oa.full_rows, oa.full_cols, lda, const_cast<void*>(oa.hi), oa.plane, oa.amax,
+                                          want ? g_colpart_buf : nullptr, want ? &g_colpart_rows : nullptr);
           if (rc != ADDK_OK) return rc;
           a.a16_ready = 1;
         }
         if (ob.ready == 2) {
-          const int rc = addk_f16x3_split(st, B, ob.full_rows, ob.full_cols, ldb, const_cast<void*>(ob.hi), ob.plane, ob.amax);
+          const int rc = addk_f16x3_split(st, B, ob.full_rows, ob.full_cols, ldb, const_cast<void*>(ob.hi), ob.plane, ob.amax,
+                                          nullptr, nullptr);
           if (rc != ADDK_OK) return rc;
           a.b16_ready = 1;
         }
@@ -786,8 +822,23 @@ static int wgrad(cudaStream_t st, const Ctx& c, const ChainWs& ws, const float* 
   if (n_out == 1 && ldy == 1) {
     TRY(colsum(st, c, ws, X, ldx, rows, k_in, F(c.slabs) + (size_t)slab0 * P + o_w, dY));
   } else {
-    TRY(gemm(st, (int)c.precision, dY, ldy, 1, X, ldx, 0, F(c.slabs) + (size_t)slab0 * P + o_w, k_in, n_out, k_in, rows,
-             nullptr, 0, nullptr, 0, S, nullptr, nullptr, P));
+    // f16x3: if this call is the one that converts dY, its split pass also leaves the column sums of dY (the bias gradient)
+    static int fuse = -1;                                 // ADDK_H3_COLPART=0: A/B switch (separate column-sum kernels)
+    if (fuse < 0) { const char* ev = getenv("ADDK_H3_COLPART"); fuse = ev ? atoi(ev) : 1; }
+    g_colpart_rows = 0;
+    g_colpart_for = (o_b >= 0 && fuse) ? dY : nullptr;
+    g_colpart_buf = (o_b >= 0 && fuse) ? ws.colpart : nullptr;
+    const int rc = gemm(st, (int)c.precision, dY, ldy, 1, X, ldx, 0, F(c.slabs) + (size_t)slab0 * P + o_w, k_in, n_out, k_in, rows,
+                        nullptr, 0, nullptr, 0, S, nullptr, nullptr, P);
+    g_colpart_for = nullptr; g_colpart_buf = nullptr;
+    if (rc != ADDK_OK) return rc;
+    if (o_b >= 0 && g_colpart_rows > 0) {
+      colsum_parts_kernel<<<(n_out + 127) / 128, 256, 0, st>>>(ws.colpart, g_colpart_rows, n_out,
+                                                              F(c.slabs) + (size_t)slab0 * P + o_b, P, S);
+      ADDK_CHECK_LAUNCH();
+      g_colpart_rows = 0;
+      return ADDK_OK;
+    }
   }
   if (o_b >= 0) {
     TRY(colsum(st, c, ws, dY, ldy, rows, n_out, F(c.slabs) + (size_t)slab0 * P + o_b, nullptr));
@@ -857,7 +908,7 @@ static int trunk_backward(cudaStream_t st, const Ctx& c, const ChainWs& ws, cons
 }
 
 static ChainWs main_ws(const Ctx& c) {
-  return ChainWs{F(c.h1), F(c.h2), F(c.h3), F(c.g1), F(c.g2), F(c.g3), F(c.colsum_work)};
+  return ChainWs{F(c.h1), F(c.h2), F(c.h3), F(c.g1), F(c.g2), F(c.g3), F(c.colsum_work), F(c.colpart_a)};
 }
 
 // Two helper streams (+ fork / join events) per device for the critic and the discriminator chains, created on first use.
@@ -952,8 +1003,8 @@ extern "C" int addk_update_minibatch(void* stream, void* ctx_host, const long lo
     cudaStreamWaitEvent(sd, aux->fork, 0);
   }
   const ChainWs wa = main_ws(c);
-  const ChainWs wc = multi ? ChainWs{F(c.c_h1), F(c.c_h2), F(c.c_h3), F(c.c_g1), F(c.c_g2), F(c.c_g3), F(c.colsum_work_c)} : wa;
-  const ChainWs wd = multi ? ChainWs{F(c.d_e1), nullptr, F(c.d_e2), F(c.d_dv1), F(c.d_du2), F(c.d_dh2), F(c.colsum_work_d)} : wa;
+  const ChainWs wc = multi ? ChainWs{F(c.c_h1), F(c.c_h2), F(c.c_h3), F(c.c_g1), F(c.c_g2), F(c.c_g3), F(c.colsum_work_c), F(c.colpart_c)} : wa;
+  const ChainWs wd = multi ? ChainWs{F(c.d_e1), nullptr, F(c.d_e2), F(c.d_dv1), F(c.d_du2), F(c.d_dh2), F(c.colsum_work_d), F(c.colpart_d)} : wa;
   float* pred_d = multi ? F(c.d_pred) : F(c.pred);
   float* dpred_d = multi ? F(c.d_dpred) : F(c.dpred);
 

@@ -233,6 +233,11 @@ def run_b200(args):
                     raise SystemExit("bench.py: non-finite diagnostics %s -- the timed path is numerically broken" % bad)
         t_end.record()
         barrier()
+        if not e2e:   # outside the timed region: the last iteration's diagnostics and the parameters must be finite
+            last = {k: float(v) for k, v in {**train_info, **data_info}.items()}
+            bad = [k for k, v in last.items() if v != v or v in (float("inf"), float("-inf"))]
+            if bad or not bool(torch.isfinite(agent._model.flat).all()):
+                raise SystemExit("bench.py: non-finite diagnostics %s / parameters -- the timed path is numerically broken" % bad)
         total = t_begin.elapsed_time(t_end) * 1e-3
         phys = sum(a.elapsed_time(b) for a, b in agent.engine_time_events) * 1e-3
         agent.engine_time_events = None

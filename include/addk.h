@@ -214,9 +214,11 @@ int addk_gemm(void* stream, const addk_gemm_args* args_host, int precision);
  * fp16 planes hi16[0 .. rows*ld) and hi16[plane .. plane + rows*ld) described above.  Three stream-ordered operations. */
 int addk_f16x3_convert(void* stream, const float* x, long long rows, int cols, int ld, void* hi16, long long plane,
                        uint32_t* amax_slot);
-/* the split pass alone: *amax_slot already holds max|x| (left there by the kernel that produced x) */
+/* the split pass alone: *amax_slot already holds max|x| (left there by the kernel that produced x).  Optional:
+ * colsum_partials [148 * 8, cols] floats -- the pass also leaves per-block column sums of x there (the bias gradient
+ * 1^T dY for free) and *colsum_partial_rows (host int) says how many rows were written; 0 = shape not supported */
 int addk_f16x3_split(void* stream, const float* x, long long rows, int cols, int ld, void* hi16, long long plane,
-                     uint32_t* amax_slot);
+                     uint32_t* amax_slot, float* colsum_partials, int* colsum_partial_rows);
 /* before a dense layer that leaves max|C| (c_amax) or the planes of its output (c16_plane) behind: clears the max word
  * and either folds the scale in force into the slot's sticky word (keep_sticky_word = 1, needed for c16_plane) or
  * clears it (0: the scale then follows max|x| alone and results do not depend on earlier calls); addk_f16x3_repair,
