@@ -429,25 +429,38 @@ __global__ void outer_mask_kernel(const float* __restrict__ d, const float* __re
 }
 
 // out[n] = sum over the `parts` per-block partial rows the f16x3 split pass left behind (h3_split_kernel), in a fixed
-// order; slabs 1..nsplit-1 are zeroed like colsum_slabs_kernel does.  grid = ceil(n / 128), 256 threads.
+// order; slabs 1..nsplit-1 are zeroed like colsum_slabs_kernel does.  grid = ceil(n / 32), 256 threads = 8 float4
+// columns (one 128-byte line per partial row) x 32 row lanes, four independent loads in flight per thread: with up to
+// 1184 partial rows a block of 32 column quads x 8 row lanes walked 148 dependent loads per thread on 8 SMs (41 us).
 __global__ void __launch_bounds__(256) colsum_parts_kernel(const float* __restrict__ part, int parts, int n, float* __restrict__ out,
                                                            long long slab_stride, int nsplit) {
-  __shared__ float4 sm[8][32];
-  const int cq = threadIdx.x & 31, rl = threadIdx.x >> 5;
-  const int col = (blockIdx.x * 32 + cq) * 4;
+  __shared__ float4 sm[32][8];
+  const int cq = threadIdx.x & 7, rl = threadIdx.x >> 3;
+  const int col = (blockIdx.x * 8 + cq) * 4;
   float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
   if (col < n) {
-    for (int r = rl; r < parts; r += 8) {
-      const float4 v = ldg4(part + (size_t)r * n + col);
-      t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+    float4 u[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) u[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r = rl; r < parts; r += 128) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int rr = r + 32 * j;
+        if (rr < parts) {
+          const float4 v = ldg4(part + (size_t)rr * n + col);
+          u[j].x += v.x; u[j].y += v.y; u[j].z += v.z; u[j].w += v.w;
+        }
+      }
     }
+    t.x = (u[0].x + u[1].x) + (u[2].x + u[3].x); t.y = (u[0].y + u[1].y) + (u[2].y + u[3].y);
+    t.z = (u[0].z + u[1].z) + (u[2].z + u[3].z); t.w = (u[0].w + u[1].w) + (u[2].w + u[3].w);
   }
   sm[rl][cq] = t;
   __syncthreads();
   if (rl == 0 && col < n) {
     t = sm[0][cq];
 #pragma unroll
-    for (int i = 1; i < 8; ++i) { t.x += sm[i][cq].x; t.y += sm[i][cq].y; t.z += sm[i][cq].z; t.w += sm[i][cq].w; }
+    for (int i = 1; i < 32; ++i) { t.x += sm[i][cq].x; t.y += sm[i][cq].y; t.z += sm[i][cq].z; t.w += sm[i][cq].w; }
     const float tv[4] = {t.x, t.y, t.z, t.w};
     for (int e = 0; e < 4 && col + e < n; ++e) {
       out[col + e] = tv[e];
@@ -833,7 +846,7 @@ static int wgrad(cudaStream_t st, const Ctx& c, const ChainWs& ws, const float* 
     g_colpart_for = nullptr; g_colpart_buf = nullptr;
     if (rc != ADDK_OK) return rc;
     if (o_b >= 0 && g_colpart_rows > 0) {
-      colsum_parts_kernel<<<(n_out + 127) / 128, 256, 0, st>>>(ws.colpart, g_colpart_rows, n_out,
+      colsum_parts_kernel<<<(n_out + 31) / 32, 256, 0, st>>>(ws.colpart, g_colpart_rows, n_out,
                                                               F(c.slabs) + (size_t)slab0 * P + o_b, P, S);
       ADDK_CHECK_LAUNCH();
       g_colpart_rows = 0;
