@@ -14,31 +14,47 @@
 
 namespace addk {
 
-// thread per env, serial over T (reverse), coalesced over N
-__global__ void td_lambda_kernel(const float* __restrict__ reward, const float* __restrict__ next_vals,
+// thread per env, serial over T (reverse), coalesced over N.  The recurrence only chains `next_ret`: the four loads of
+// eight time steps are issued before the first dependent add, so a thread keeps 32 loads in flight instead of 4.
+__global__ void __launch_bounds__(64) td_lambda_kernel(const float* __restrict__ reward, const float* __restrict__ next_vals,
                                  const float* __restrict__ vals, const int32_t* __restrict__ done, int T, int N,
                                  float discount, float td_lambda, float succ_val, float fail_val,
                                  float* __restrict__ tar_val, float* __restrict__ adv) {
-  int n = blockIdx.x * blockDim.x + threadIdx.x;
+  constexpr int U = 8;
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
   float next_ret = 0.f;
-  for (int t = T - 1; t >= 0; --t) {
-    size_t i = (size_t)t * N + n;
-    float nv = next_vals[i];
-    int d = done[i];
-    if (d == 2) nv = succ_val;
-    if (d == 1) nv = fail_val;
-    float r = reward[i], ret;
-    if (t == T - 1) {
-      ret = add_rn(r, mul_rn(discount, nv));
-    } else {
-      float reset = (d != 0) ? 1.0f : 0.0f;
-      float lam = mul_rn(td_lambda, sub_rn(1.0f, reset));
-      ret = add_rn(r, mul_rn(discount, add_rn(mul_rn(sub_rn(1.0f, lam), nv), mul_rn(lam, next_ret))));
+  for (int t0 = T - 1; t0 >= 0; t0 -= U) {
+    float nv[U], r[U], vl[U];
+    int d[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int t = t0 - u;
+      if (t >= 0) {
+        const size_t i = (size_t)t * N + n;
+        nv[u] = __ldg(next_vals + i); d[u] = __ldg(done + i); r[u] = __ldg(reward + i); vl[u] = __ldg(vals + i);
+      }
     }
-    tar_val[i] = ret;
-    adv[i] = sub_rn(ret, vals[i]);
-    next_ret = ret;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int t = t0 - u;
+      if (t < 0) break;
+      const size_t i = (size_t)t * N + n;
+      float nvu = nv[u];
+      if (d[u] == 2) nvu = succ_val;
+      if (d[u] == 1) nvu = fail_val;
+      float ret;
+      if (t == T - 1) {
+        ret = add_rn(r[u], mul_rn(discount, nvu));
+      } else {
+        const float reset = (d[u] != 0) ? 1.0f : 0.0f;
+        const float lam = mul_rn(td_lambda, sub_rn(1.0f, reset));
+        ret = add_rn(r[u], mul_rn(discount, add_rn(mul_rn(sub_rn(1.0f, lam), nvu), mul_rn(lam, next_ret))));
+      }
+      tar_val[i] = ret;
+      adv[i] = sub_rn(ret, vl[u]);
+      next_ret = ret;
+    }
   }
 }
 
@@ -143,18 +159,42 @@ __global__ void diff_normalizer_update_kernel(const double* __restrict__ sum_abs
 }
 
 // torch.optim.AdamW, amsgrad=False, maximize=False (torch/optim/adamw.py -> adam.py _single_tensor_adam)
+struct AdamK { float lr_wd_factor, one_minus_b1, b2, one_minus_b2, step_size, bc2_sqrt, eps, grad_scale; };
+__device__ __forceinline__ void adam1(const AdamK& k, float& p, float g, float& m, float& v) {
+  const float grad = mul_rn(g, k.grad_scale);
+  const float w = mul_rn(p, k.lr_wd_factor);                                     // param.mul_(1 - lr*wd)
+  const float mi = add_rn(m, mul_rn(k.one_minus_b1, sub_rn(grad, m)));           // exp_avg.lerp_(grad, 1-b1)
+  const float vi = add_rn(mul_rn(v, k.b2), mul_rn(mul_rn(k.one_minus_b2, grad), grad));  // mul_(b2).addcmul_(g, g, 1-b2)
+  const float denom = add_rn(sqrtf(vi) / k.bc2_sqrt, k.eps);
+  p = add_rn(w, mul_rn(-k.step_size, mi / denom));                               // addcdiv_(exp_avg, denom, -step_size)
+  m = mi; v = vi;
+}
 __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
-                             float* __restrict__ v, long long n, float lr_wd_factor, float one_minus_b1, float b2,
-                             float one_minus_b2, float step_size, float bc2_sqrt, float eps, float grad_scale) {
+                             float* __restrict__ v, long long n, const AdamK k) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  float grad = mul_rn(g[i], grad_scale);
-  float w = mul_rn(p[i], lr_wd_factor);                                   // param.mul_(1 - lr*wd)
-  float mi = add_rn(m[i], mul_rn(one_minus_b1, sub_rn(grad, m[i])));      // exp_avg.lerp_(grad, 1-b1)
-  float vi = add_rn(mul_rn(v[i], b2), mul_rn(mul_rn(one_minus_b2, grad), grad));  // mul_(b2).addcmul_(g, g, 1-b2)
-  float denom = add_rn(sqrtf(vi) / bc2_sqrt, eps);
-  p[i] = add_rn(w, mul_rn(-step_size, mi / denom));                       // addcdiv_(exp_avg, denom, -step_size)
-  m[i] = mi; v[i] = vi;
+  float pi = p[i], mi = m[i], vi = v[i];
+  adam1(k, pi, g[i], mi, vi);
+  p[i] = pi; m[i] = mi; v[i] = vi;
+}
+// 16-byte aligned vectors: four parameters per thread (7 x 128-bit accesses), the n % 4 tail by the thread after the last quad
+__global__ void __launch_bounds__(256) adamw_vec4_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                         float* __restrict__ v, long long n, const AdamK k) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long n4 = n >> 2;
+  if (i < n4) {
+    float4 P = *reinterpret_cast<const float4*>(p + 4 * i), M = *reinterpret_cast<const float4*>(m + 4 * i),
+           V = *reinterpret_cast<const float4*>(v + 4 * i);
+    const float4 G = ldg4(g + 4 * i);
+    adam1(k, P.x, G.x, M.x, V.x); adam1(k, P.y, G.y, M.y, V.y); adam1(k, P.z, G.z, M.z, V.z); adam1(k, P.w, G.w, M.w, V.w);
+    stg4(p + 4 * i, P); stg4(m + 4 * i, M); stg4(v + 4 * i, V);
+  } else if (i == n4) {
+    for (long long j = 4 * n4; j < n; ++j) {
+      float pj = p[j], mj = m[j], vj = v[j];
+      adam1(k, pj, g[j], mj, vj);
+      p[j] = pj; m[j] = mj; v[j] = vj;
+    }
+  }
 }
 
 }  // namespace addk
@@ -165,7 +205,7 @@ extern "C" int addk_td_lambda(void* stream, const float* reward, const float* ne
                               const int32_t* done, int T, int N, float discount, float td_lambda, float succ_val,
                               float fail_val, float* tar_val, float* adv) {
   if (!reward || !next_vals || !vals || !done || !tar_val || !adv || T <= 0 || N <= 0) return ADDK_ERR_ARG;
-  td_lambda_kernel<<<(N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(reward, next_vals, vals, done, T, N, discount,
+  td_lambda_kernel<<<(N + 63) / 64, 64, 0, (cudaStream_t)stream>>>(reward, next_vals, vals, done, T, N, discount,
                                                                      td_lambda, succ_val, fail_val, tar_val, adv);
   ADDK_CHECK_LAUNCH();
   return ADDK_OK;
@@ -236,9 +276,13 @@ extern "C" int addk_adamw(void* stream, float* param, const float* grad, float* 
   float step_size = (float)(lr / bc1);
   float bc2_sqrt = (float)sqrt(bc2);
   float lr_wd = (float)(1.0 - lr * weight_decay);
-  adamw_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      param, grad, exp_avg, exp_avg_sq, n, lr_wd, (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2),
-      step_size, bc2_sqrt, (float)eps, (float)grad_scale);
+  const AdamK k = {lr_wd, (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2), step_size, bc2_sqrt, (float)eps, (float)grad_scale};
+  const bool aligned = ((reinterpret_cast<uintptr_t>(param) | reinterpret_cast<uintptr_t>(grad) | reinterpret_cast<uintptr_t>(exp_avg) |
+                         reinterpret_cast<uintptr_t>(exp_avg_sq)) & 15) == 0;
+  if (aligned)
+    adamw_vec4_kernel<<<(unsigned)(((n >> 2) + 1 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, k);
+  else
+    adamw_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, k);
   ADDK_CHECK_LAUNCH();
   return ADDK_OK;
 }

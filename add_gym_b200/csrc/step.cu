@@ -398,15 +398,13 @@ constexpr int O_ROWS = 0, O_REFV = 9 * HALF, O_SIM = O_REFV + HALF, O_HIST = O_S
               O_DISC = O_OBS + OBS, O_DEMO = O_DISC + 116, PER_WARP = O_DEMO + 116;
 }  // namespace fast
 
-__global__ void __launch_bounds__(WPB * 32) env_step_fast_kernel(const __grid_constant__ StepParams p) {
+struct FastTail { float pe, ve, de, t, mt, m_len, ret0; int contact, m_loop; long long len0; };
+
+// Everything a warp does for its env up to the warp-wide reductions of the reward terms; `sw` = this warp's shared-memory
+// slice.  Lane 0's `o` is complete (clip length / loop mode / return-tracker state are loaded by lane 0 only).
+__device__ __forceinline__ void env_step_fast_main(const StepParams& p, float* const sw, const int lane, const int e, FastTail& o) {
   using namespace fast;
-  extern __shared__ __align__(16) float smem[];
   const addk_task& tk = p.task;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int e = blockIdx.x * WPB + warp;
-  if (e >= p.n) return;
-  if ((p.flags & F_MASKED) && !p.env_mask[e]) return;
-  float* const sw = smem + (size_t)warp * PER_WARP;
   float* const s_rows = sw + O_ROWS;
   float* const s_refv = sw + O_REFV;
   float* const s_sim = sw + O_SIM;
@@ -604,64 +602,105 @@ __global__ void __launch_bounds__(WPB * 32) env_step_fast_kernel(const __grid_co
     contact = (ha || hb) ? 1 : 0;
   }
   contact = __any_sync(0xffffffffu, contact);
-  if (lane == 0) {
-    const Vec3 rp = {s_sim[0], s_sim[1], s_sim[2]}, tp = {s_rows[0], s_rows[1], s_rows[2]};
-    const Vec3 dpos = {sub_rn(tp.x, rp.x), sub_rn(tp.y, rp.y), sub_rn(tp.z, rp.z)};
-    Vec3 dpos_r = dpos;
-    if (!tk.track_root) { dpos_r.x = 0.f; dpos_r.y = 0.f; }
-    if (!tk.track_root_h) dpos_r.z = 0.f;
-    const float root_pos_err = add_rn(add_rn(mul_rn(dpos_r.x, dpos_r.x), mul_rn(dpos_r.y, dpos_r.y)), mul_rn(dpos_r.z, dpos_r.z));
-    Quat rq = ldq(s_sim + 3), tq = ldq(s_rows + 3);
-    Vec3 rv = {s_sim[HALF], s_sim[HALF + 1], s_sim[HALF + 2]}, ra = {s_sim[HALF + 3], s_sim[HALF + 4], s_sim[HALF + 5]};
-    Vec3 tv = {s_refv[0], s_refv[1], s_refv[2]}, ta = {s_refv[3], s_refv[4], s_refv[5]};
-    if (!tk.track_root) {  // convert_to_local_root (add_reward.py:91-102)
-      const Quat h0 = calc_heading_quat_inv(rq), h1 = calc_heading_quat_inv(tq);
-      rv = quat_rotate(h0, rv); ra = quat_rotate(h0, ra); rq = quat_mul(h0, rq);
-      tv = quat_rotate(h1, tv); ta = quat_rotate(h1, ta); tq = quat_mul(h1, tq);
-    }
-    float rot_err = quat_diff_angle(rq, tq);
-    rot_err = mul_rn(rot_err, rot_err);
-    const Vec3 dv = {sub_rn(tv.x, rv.x), sub_rn(tv.y, rv.y), sub_rn(tv.z, rv.z)};
-    const Vec3 da = {sub_rn(ta.x, ra.x), sub_rn(ta.y, ra.y), sub_rn(ta.z, ra.z)};
-    const float vel_err = add_rn(add_rn(mul_rn(dv.x, dv.x), mul_rn(dv.y, dv.y)), mul_rn(dv.z, dv.z));
-    const float ang_err = add_rn(add_rn(mul_rn(da.x, da.x), mul_rn(da.y, da.y)), mul_rn(da.z, da.z));
-    const float pose_r = expf(mul_rn(-tk.pose_scale, pe));
-    const float vel_r = expf(mul_rn(-tk.vel_scale, ve));
-    const float root_pose_r = expf(mul_rn(-tk.root_pose_scale, add_rn(root_pos_err, mul_rn(0.1f, rot_err))));
-    const float root_vel_r = expf(mul_rn(-tk.root_vel_scale, add_rn(vel_err, mul_rn(0.1f, ang_err))));
-    const float r = add_rn(add_rn(add_rn(mul_rn(tk.pose_w, pose_r), mul_rn(tk.vel_w, vel_r)), mul_rn(tk.root_pose_w, root_pose_r)),
-                           mul_rn(tk.root_vel_w, root_vel_r));
-    int done = 0;
-    if (t >= tk.ep_len) done = 3;
-    if (mt >= m_len && m_loop != 1) done = 2;
-    if (tk.enable_early_termination) {
-      bool failed = contact != 0;
-      if (tk.pose_termination) {
-        bool pf = (de / (float)D) > tk.pose_termination_dist;
-        if (tk.track_root) {
-          const float re = add_rn(add_rn(mul_rn(dpos.x, dpos.x), mul_rn(dpos.y, dpos.y)), mul_rn(dpos.z, dpos.z));
-          pf = pf || (re > tk.pose_termination_dist);
-        }
-        failed = failed || pf;
+  o.pe = pe; o.ve = ve; o.de = de; o.contact = contact; o.t = t; o.mt = mt; o.m_len = m_len; o.m_loop = m_loop;
+  o.ret0 = ret0; o.len0 = len0;
+}
+
+// The scalar end of the step: reward terms -> reward, done flag, return tracker.  ONE thread per env; `sw` = the shared
+// memory slice env_step_fast_main filled for that env.
+__device__ __forceinline__ void env_step_fast_tail(const StepParams& p, const int e, const float* const sw, const FastTail& o) {
+  using namespace fast;
+  const addk_task& tk = p.task;
+  const float* const s_rows = sw + O_ROWS;
+  const float* const s_refv = sw + O_REFV;
+  const float* const s_sim = sw + O_SIM;
+  const float pe = o.pe, ve = o.ve, de = o.de, t = o.t, mt = o.mt, m_len = o.m_len, ret0 = o.ret0;
+  const int contact = o.contact, m_loop = o.m_loop;
+  const long long len0 = o.len0;
+  const Vec3 rp = {s_sim[0], s_sim[1], s_sim[2]}, tp = {s_rows[0], s_rows[1], s_rows[2]};
+  const Vec3 dpos = {sub_rn(tp.x, rp.x), sub_rn(tp.y, rp.y), sub_rn(tp.z, rp.z)};
+  Vec3 dpos_r = dpos;
+  if (!tk.track_root) { dpos_r.x = 0.f; dpos_r.y = 0.f; }
+  if (!tk.track_root_h) dpos_r.z = 0.f;
+  const float root_pos_err = add_rn(add_rn(mul_rn(dpos_r.x, dpos_r.x), mul_rn(dpos_r.y, dpos_r.y)), mul_rn(dpos_r.z, dpos_r.z));
+  Quat rq = ldq(s_sim + 3), tq = ldq(s_rows + 3);
+  Vec3 rv = {s_sim[HALF], s_sim[HALF + 1], s_sim[HALF + 2]}, ra = {s_sim[HALF + 3], s_sim[HALF + 4], s_sim[HALF + 5]};
+  Vec3 tv = {s_refv[0], s_refv[1], s_refv[2]}, ta = {s_refv[3], s_refv[4], s_refv[5]};
+  if (!tk.track_root) {  // convert_to_local_root (add_reward.py:91-102)
+    const Quat h0 = calc_heading_quat_inv(rq), h1 = calc_heading_quat_inv(tq);
+    rv = quat_rotate(h0, rv); ra = quat_rotate(h0, ra); rq = quat_mul(h0, rq);
+    tv = quat_rotate(h1, tv); ta = quat_rotate(h1, ta); tq = quat_mul(h1, tq);
+  }
+  float rot_err = quat_diff_angle(rq, tq);
+  rot_err = mul_rn(rot_err, rot_err);
+  const Vec3 dv = {sub_rn(tv.x, rv.x), sub_rn(tv.y, rv.y), sub_rn(tv.z, rv.z)};
+  const Vec3 da = {sub_rn(ta.x, ra.x), sub_rn(ta.y, ra.y), sub_rn(ta.z, ra.z)};
+  const float vel_err = add_rn(add_rn(mul_rn(dv.x, dv.x), mul_rn(dv.y, dv.y)), mul_rn(dv.z, dv.z));
+  const float ang_err = add_rn(add_rn(mul_rn(da.x, da.x), mul_rn(da.y, da.y)), mul_rn(da.z, da.z));
+  const float pose_r = expf(mul_rn(-tk.pose_scale, pe));
+  const float vel_r = expf(mul_rn(-tk.vel_scale, ve));
+  const float root_pose_r = expf(mul_rn(-tk.root_pose_scale, add_rn(root_pos_err, mul_rn(0.1f, rot_err))));
+  const float root_vel_r = expf(mul_rn(-tk.root_vel_scale, add_rn(vel_err, mul_rn(0.1f, ang_err))));
+  const float r = add_rn(add_rn(add_rn(mul_rn(tk.pose_w, pose_r), mul_rn(tk.vel_w, vel_r)), mul_rn(tk.root_pose_w, root_pose_r)),
+                         mul_rn(tk.root_vel_w, root_vel_r));
+  int done = 0;
+  if (t >= tk.ep_len) done = 3;
+  if (mt >= m_len && m_loop != 1) done = 2;
+  if (tk.enable_early_termination) {
+    bool failed = contact != 0;
+    if (tk.pose_termination) {
+      bool pf = (de / (float)D) > tk.pose_termination_dist;
+      if (tk.track_root) {
+        const float re = add_rn(add_rn(mul_rn(dpos.x, dpos.x), mul_rn(dpos.y, dpos.y)), mul_rn(dpos.z, dpos.z));
+        pf = pf || (re > tk.pose_termination_dist);
       }
-      if (failed && t > 0.0f) done = 1;
+      failed = failed || pf;
     }
-    p.env.reward[e] = r;
-    p.env.done[e] = done;
-    if (p.has_exp) { p.exp.reward[e] = r; p.exp.done[e] = done; }
-    if (p.env.return_buf) {        // ReturnTracker.update (base_agent.py:596-621)
-      float ret = add_rn(ret0, r);
-      long long len = len0 + 1;
-      if (done != 0) {
-        atomicAdd(p.env.tracker_sums, (double)ret);
-        atomicAdd(p.env.tracker_sums + 1, (double)len);
-        atomicAdd(reinterpret_cast<unsigned long long*>(p.env.tracker_count), 1ull);
-        p.env.eps_per_env[e] += 1;
-        ret = 0.f; len = 0;
-      }
-      p.env.return_buf[e] = ret;
-      p.env.ep_len_buf[e] = len;
+    if (failed && t > 0.0f) done = 1;
+  }
+  p.env.reward[e] = r;
+  p.env.done[e] = done;
+  if (p.has_exp) { p.exp.reward[e] = r; p.exp.done[e] = done; }
+  if (p.env.return_buf) {        // ReturnTracker.update (base_agent.py:596-621)
+    float ret = add_rn(ret0, r);
+    long long len = len0 + 1;
+    if (done != 0) {
+      atomicAdd(p.env.tracker_sums, (double)ret);
+      atomicAdd(p.env.tracker_sums + 1, (double)len);
+      atomicAdd(reinterpret_cast<unsigned long long*>(p.env.tracker_count), 1ull);
+      p.env.eps_per_env[e] += 1;
+      ret = 0.f; len = 0;
     }
+    p.env.return_buf[e] = ret;
+    p.env.ep_len_buf[e] = len;
+  }
+}
+
+// CTA_TAIL = false: lane 0 of every warp runs the scalar end for its own env (273 warp-instructions of one-lane work per
+// env: a quarter of the kernel's issue slots, ncu r01_step_fast).  CTA_TAIL = true: the warps leave their reduced terms
+// in shared memory and lanes 0..7 of warp 0 run the scalar end for the block's eight envs at once.
+template <bool CTA_TAIL>
+__global__ void __launch_bounds__(WPB * 32) env_step_fast_kernel(const __grid_constant__ StepParams p) {
+  using namespace fast;
+  extern __shared__ __align__(16) float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int e = blockIdx.x * WPB + warp;
+  const bool active = e < p.n && !((p.flags & F_MASKED) && !p.env_mask[e]);
+  float* const sw = smem + (size_t)warp * PER_WARP;
+  FastTail o;
+  if (!CTA_TAIL) {
+    if (!active) return;
+    env_step_fast_main(p, sw, lane, e, o);
+    if ((p.flags & F_REWARD_DONE) && lane == 0) env_step_fast_tail(p, e, sw, o);
+  } else {
+    __shared__ FastTail s_tail[WPB];
+    __shared__ int s_active[WPB];
+    if (active) env_step_fast_main(p, sw, lane, e, o);
+    if (!(p.flags & F_REWARD_DONE)) return;                 // uniform over the grid
+    if (lane == 0) { s_active[warp] = active ? 1 : 0; if (active) s_tail[warp] = o; }
+    __syncthreads();
+    if (warp == 0 && lane < WPB && s_active[lane])
+      env_step_fast_tail(p, blockIdx.x * WPB + lane, smem + (size_t)lane * PER_WARP, s_tail[lane]);
   }
 }
 
@@ -866,7 +905,10 @@ extern "C" int addk_env_step(void* stream, const addk_task* task, const addk_mot
   }
   if (fast && env->hist_stride == 72) {
     const int fsm = fast::PER_WARP * WPB * (int)sizeof(float);
-    env_step_fast_kernel<<<(num_envs + WPB - 1) / WPB, WPB * 32, fsm, (cudaStream_t)stream>>>(p);
+    static int cta_tail = -1;                             // ADDK_STEP_CTA_TAIL=0: A/B switch (per-warp scalar end)
+    if (cta_tail < 0) { const char* ev = getenv("ADDK_STEP_CTA_TAIL"); cta_tail = ev ? atoi(ev) : 1; }
+    if (cta_tail) env_step_fast_kernel<true><<<(num_envs + WPB - 1) / WPB, WPB * 32, fsm, (cudaStream_t)stream>>>(p);
+    else env_step_fast_kernel<false><<<(num_envs + WPB - 1) / WPB, WPB * 32, fsm, (cudaStream_t)stream>>>(p);
   } else {
     env_step_kernel<false><<<(num_envs + WPB - 1) / WPB, WPB * 32, smem, (cudaStream_t)stream>>>(p);
   }

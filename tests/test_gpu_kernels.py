@@ -105,6 +105,29 @@ def test_adamw_matches_torch_at_full_parameter_count():
         assert _rel(p, q.data) <= 1e-7 and float((p.cpu() - q.data).abs().max()) <= 2e-8, "single-tensor AdamW op order (step %d)" % step
 
 
+@pytest.mark.parametrize("n,off", [(4349983, 0), (1003, 0), (1003, 1), (3, 0)])
+def test_adamw_vector_tail_and_unaligned_vectors(n, off):
+    """The 128-bit kernel handles n % 4 != 0 through one tail thread; vectors that are not 16-byte aligned take the scalar
+    kernel.  Both must give the bits of torch's single-tensor AdamW."""
+    _lib, L = _L()
+    g = torch.Generator().manual_seed(n + off)
+    p0, grad = torch.randn(n, generator=g) * 0.05, torch.randn(n, generator=g) * 0.01
+    q = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.AdamW([q], 1e-4, weight_decay=0.0)
+    q.grad = grad.clone()
+    opt.step()
+    bufs = [torch.zeros(n + off, device="cuda") for _ in range(4)]
+    p, gd, m, v = (b[off:] for b in bufs)
+    p.copy_(p0); gd.copy_(grad)
+    _lib.check(L.addk_adamw(_lib.stream(), _lib.ptr(p), _lib.ptr(gd), _lib.ptr(m), _lib.ptr(v), C.c_longlong(n), C.c_int(1),
+                            C.c_double(1e-4), C.c_double(0.9), C.c_double(0.999), C.c_double(1e-8), C.c_double(0.0),
+                            C.c_double(1.0)), "addk_adamw")
+    torch.cuda.synchronize()
+    assert float((p.cpu() - q.data).abs().max()) <= 2e-8
+    assert torch.equal(m.cpu(), (0.1 * grad)) or _rel(m, 0.1 * grad) <= 1e-7
+    assert all(float(b[:off].abs().sum()) == 0.0 for b in bufs), "nothing written before the vectors"
+
+
 def test_column_stats_and_normalizer_updates():
     from add_gym_b200.normalizer import DiffNormalizer, Normalizer
     g = torch.Generator().manual_seed(3)
