@@ -395,8 +395,10 @@ def step_kernel_roofline(agent, hbm_peak):
             "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
             "traffic": _ncu_traffic("env_step_kernel_32768") if N == 32768 else None, "avg_launch_ms": ms,
             "algorithmic_bytes_per_launch": nbytes, "envs": N,
-            "note": "issue-bound, not HBM-bound (ncu: 65 % issue slots busy, 15 % DRAM); one launch is shorter than "
-                    "the DRAM pipeline fill at 4096 envs -- the fraction is meaningful at 32768 envs (config 5)"}
+            "note": "not HBM-bound yet: a per-warp latency chain (ncu at 32768 envs: issue slots 64 % busy, 46 % of the "
+                    "warp slots occupied, 127 MB of DRAM traffic for 184 MB algorithmic; profiles/r01_ncu_step_fast_"
+                    "metrics.txt); one launch is shorter than the DRAM pipeline fill at 4096 envs -- the fraction is "
+                    "meaningful at 32768 envs (config 5: 52 %)"}
 
 
 def dominant_kernel_roofline(agent, args, hbm_peak, tc_peak, peak_src):
