@@ -679,8 +679,10 @@ __device__ __forceinline__ void env_step_fast_tail(const StepParams& p, const in
 // CTA_TAIL = false: lane 0 of every warp runs the scalar end for its own env (273 warp-instructions of one-lane work per
 // env: a quarter of the kernel's issue slots, ncu r01_step_fast).  CTA_TAIL = true: the warps leave their reduced terms
 // in shared memory and lanes 0..7 of warp 0 run the scalar end for the block's eight envs at once.
-template <bool CTA_TAIL>
-__global__ void __launch_bounds__(WPB * 32) env_step_fast_kernel(const __grid_constant__ StepParams p) {
+// MIN_BLOCKS caps the registers for that many resident blocks per SM (0, the default: no cap, 64; 5: 48 registers, 40 B of spills; 6: 40
+// registers, 128 B) -- candidates for the occupancy experiment (ncu: 4 blocks = 46 % of the warp slots); not the default.
+template <bool CTA_TAIL, int MIN_BLOCKS>
+__global__ void __launch_bounds__(WPB * 32, MIN_BLOCKS) env_step_fast_kernel(const __grid_constant__ StepParams p) {
   using namespace fast;
   extern __shared__ __align__(16) float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -905,10 +907,18 @@ extern "C" int addk_env_step(void* stream, const addk_task* task, const addk_mot
   }
   if (fast && env->hist_stride == 72) {
     const int fsm = fast::PER_WARP * WPB * (int)sizeof(float);
-    static int cta_tail = -1;                             // ADDK_STEP_CTA_TAIL=0: A/B switch (per-warp scalar end)
-    if (cta_tail < 0) { const char* ev = getenv("ADDK_STEP_CTA_TAIL"); cta_tail = ev ? atoi(ev) : 1; }
-    if (cta_tail) env_step_fast_kernel<true><<<(num_envs + WPB - 1) / WPB, WPB * 32, fsm, (cudaStream_t)stream>>>(p);
-    else env_step_fast_kernel<false><<<(num_envs + WPB - 1) / WPB, WPB * 32, fsm, (cudaStream_t)stream>>>(p);
+    static int cta_tail = -1, min_blocks = 0;             // ADDK_STEP_CTA_TAIL=0: A/B switch (per-warp scalar end)
+    if (cta_tail < 0) {                                   // ADDK_STEP_MIN_BLOCKS=5|6: occupancy experiment (CTA-level end only)
+      const char* ev = getenv("ADDK_STEP_CTA_TAIL"); cta_tail = ev ? atoi(ev) : 1;
+      ev = getenv("ADDK_STEP_MIN_BLOCKS"); min_blocks = ev ? atoi(ev) : 0;
+      if (min_blocks == 5) cudaFuncSetAttribute(env_step_fast_kernel<true, 5>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+      if (min_blocks == 6) cudaFuncSetAttribute(env_step_fast_kernel<true, 6>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    }
+    const dim3 fgrid((num_envs + WPB - 1) / WPB), fblock(WPB * 32);
+    if (!cta_tail) env_step_fast_kernel<false, 0><<<fgrid, fblock, fsm, (cudaStream_t)stream>>>(p);
+    else if (min_blocks == 5) env_step_fast_kernel<true, 5><<<fgrid, fblock, fsm, (cudaStream_t)stream>>>(p);
+    else if (min_blocks == 6) env_step_fast_kernel<true, 6><<<fgrid, fblock, fsm, (cudaStream_t)stream>>>(p);
+    else env_step_fast_kernel<true, 0><<<fgrid, fblock, fsm, (cudaStream_t)stream>>>(p);
   } else {
     env_step_kernel<false><<<(num_envs + WPB - 1) / WPB, WPB * 32, smem, (cudaStream_t)stream>>>(p);
   }
