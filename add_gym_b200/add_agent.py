@@ -112,6 +112,9 @@ class ADDAgent(torch.nn.Module):
 
     def __init__(self, env_config, distributed=False, device=None):
         super().__init__()
+        if type(self)._compute_loss is not ADDAgent._compute_loss:
+            raise _lib.AddkError("%s overrides _compute_loss, which is fused into addk_update_minibatch on the B200 path "
+                                 "and would be ignored" % type(self).__name__)
         if device is None:
             if not torch.cuda.is_available():
                 raise _lib.AddkError("add_gym_b200.ADDAgent needs a CUDA device: there is no CPU path")
@@ -472,10 +475,43 @@ class ADDAgent(torch.nn.Module):
         core.hist_head = (core.hist_head + 1) % nH
         self._curr_obs, self._curr_info = core.obs_buf, self._add_obs.info
 
+    # ---- reference hooks whose work is fused into the kernels ---------------------------------------------------
+    def _record_data_pre_step(self, obs, info, action, action_info):
+        """Reference hook (base_agent.py:437-442, ppo_agent.py:106-109).  On this path the actor kernel has already
+        written obs / action / a_logp / rand_action_mask into row t of the experience buffer, and the normalizer sums
+        are taken over the whole buffer at the end of the iteration: nothing is left to do here.  A subclass that
+        overrides it is called once per env step, before `_exp_buffer.inc()`, with row t of those buffers (the values
+        the reference passes; `obs_buf` itself has moved on by then) and may `_exp_buffer.record(...)` keys it added."""
+
+    def _record_data_post_step(self, next_obs, r, done, next_info):
+        """Reference hook (base_agent.py:444-447, amp_agent.py:52-59, add_agent.py:93-104): next_obs, reward, done,
+        disc_obs, disc_obs_demo, motion_ids and motion_times of row t are written by the fused step kernel.  Overrides
+        are called once per env step with the pre-reset values of row t, as in the reference."""
+
+    def _compute_loss(self, batch):
+        """Reference hook (ppo_agent.py:194-208, amp_agent.py:98-114).  The loss, its 13 diagnostics and the backward
+        pass of a minibatch are ONE native call here (`addk_update_minibatch`); there is no per-batch Python loss to
+        override, and silently ignoring an override would train something else than the subclass asked for."""
+        raise _lib.AddkError("ADDAgent._compute_loss is fused into addk_update_minibatch on the B200 path and cannot be "
+                             "overridden or called; change the loss in add_gym_b200/csrc/mlp.cu (DESIGN.md section 1)")
+
+    def _record_hooks_overridden(self):
+        cls = type(self)
+        return (cls._record_data_pre_step is not ADDAgent._record_data_pre_step
+                or cls._record_data_post_step is not ADDAgent._record_data_post_step)
+
+    def _call_record_hooks(self, t):
+        b = self._exp_buffer.get_data
+        self._record_data_pre_step(b("obs")[t], self._add_obs.info, b("action")[t],
+                                   {"a_logp": b("a_logp")[t], "rand_action_mask": b("rand_action_mask")[t]})
+        self._record_data_post_step(b("next_obs")[t], b("reward")[t], b("done")[t],
+                                    {"disc_obs": b("disc_obs")[t], "disc_obs_demo": b("disc_obs_demo")[t]})
+
     def _rollout_train(self, num_steps):
         graphed = self._graphs_ok()
         if graphed and not self._graphs_pre:
             self._capture_all()
+        hooks = self._record_hooks_overridden()
         for _ in range(num_steps):
             t = self._exp_buffer.get_buffer_head()
             if graphed:
@@ -484,6 +520,8 @@ class ADDAgent(torch.nn.Module):
                 action, _ = self._decide_action(self._curr_obs, self._curr_info, record_t=t)
                 _, _, done, _ = self._step_env(action, record_t=t)
                 self._curr_obs, self._curr_info = self._reset_done_envs(done)
+            if hooks:
+                self._call_record_hooks(t)
             self._exp_buffer.inc()
         self._rollouts_done += 1
 

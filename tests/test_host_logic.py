@@ -108,3 +108,55 @@ def test_default_config_matches_the_reference_yaml():
                 assert ours[k] == v, "%s.%s: %r != reference %r" % (path, k, ours[k], v)
     for group in ref:
         walk(cfg[group], ref[group], group)
+
+
+# ---- reference hooks of the agent whose work is fused into kernels -----------------------------------
+class _StubBuffer:
+    def __init__(self, T, N):
+        import torch
+        shapes = {"obs": (264,), "action": (29,), "a_logp": (), "rand_action_mask": (), "next_obs": (264,), "reward": (),
+                  "done": (), "disc_obs": (114,), "disc_obs_demo": (114,)}
+        self.data = {k: torch.arange(T * N * max(1, int(np.prod(s))), dtype=torch.float32).reshape((T, N) + s)
+                     for k, s in shapes.items()}
+
+    def get_data(self, name):
+        return self.data[name]
+
+
+def test_agent_record_hooks_are_called_only_when_overridden_and_compute_loss_refuses():
+    import torch
+    from add_gym_b200 import _lib
+    from add_gym_b200.add_agent import ADDAgent
+
+    base = ADDAgent.__new__(ADDAgent)
+    assert not base._record_hooks_overridden()
+    assert base._record_data_pre_step(None, None, None, None) is None and base._record_data_post_step(None, None, None, None) is None
+    with pytest.raises(_lib.AddkError, match="fused into addk_update_minibatch"):
+        base._compute_loss({})
+
+    class Recording(ADDAgent):
+        def _record_data_post_step(self, next_obs, r, done, next_info):
+            self.seen.append(("post", next_obs, r, done, sorted(next_info)))
+
+        def _record_data_pre_step(self, obs, info, action, action_info):
+            self.seen.append(("pre", obs, action, sorted(action_info), info))
+
+    sub = Recording.__new__(Recording)
+    assert sub._record_hooks_overridden()
+    buf = _StubBuffer(4, 3)
+    info = {"disc_obs": torch.zeros(3, 114), "disc_obs_demo": torch.zeros(3, 114)}
+    for k, v in (("seen", []), ("_exp_buffer", buf), ("_add_obs", type("O", (), {"info": info})())):
+        object.__setattr__(sub, k, v)
+    sub._call_record_hooks(2)
+    (pre, obs, action, a_keys, got_info), (post, next_obs, r, done, n_keys) = sub.seen
+    assert (pre, post) == ("pre", "post") and got_info is info
+    assert torch.equal(obs, buf.data["obs"][2]) and torch.equal(action, buf.data["action"][2]) and a_keys == ["a_logp", "rand_action_mask"]
+    assert torch.equal(next_obs, buf.data["next_obs"][2]) and torch.equal(r, buf.data["reward"][2]) and torch.equal(done, buf.data["done"][2])
+    assert n_keys == ["disc_obs", "disc_obs_demo"]
+
+    class OwnLoss(ADDAgent):
+        def _compute_loss(self, batch):
+            return {"loss": 0.0}
+
+    with pytest.raises(_lib.AddkError, match="overrides _compute_loss"):
+        OwnLoss(b200_config.default_config(num_envs=4))
