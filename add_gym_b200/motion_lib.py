@@ -188,6 +188,13 @@ class MotionLib:
     def sample_motions(self, n):
         return torch.multinomial(self._motion_weights, num_samples=n, replacement=True)
 
+    def sample_time(self, motion_ids):
+        """Uniform start time per clip, floored to the control step (motion_lib.py:40-46).  The ADD path samples through
+        ADDMotion.sample_time (segment sampler) instead; kept for callers of the plain library."""
+        phase = torch.rand(motion_ids.shape, device=self._device)
+        motion_time = phase * self._motion_lengths[motion_ids]
+        return (motion_time // self._dt) * self._dt
+
     def calc_motion_phase(self, motion_ids, times):
         length = self._motion_lengths[motion_ids]
         phase = times / length
