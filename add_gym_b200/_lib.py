@@ -11,7 +11,9 @@ import re
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libaddk.so")
+# ADDK_LIB selects another build of the same C-ABI (e.g. libaddk_legacy.so from `make LEGACY=1`, which adds the superseded
+# "tf32" / "tf32x3" precision modes); it is read once, at import
+LIB_PATH = os.environ.get("ADDK_LIB") or os.path.join(_HERE, "libaddk.so")
 CTX_FIELDS_PATH = os.path.join(_HERE, "csrc", "ctx_fields.h")
 
 ADDK_MAX_TAR_STEPS = 16
@@ -94,6 +96,11 @@ def lib():
         _lib.addk_launch_count.restype = C.c_longlong
         _lib.addk_launch_count.argtypes = [C.c_int]
     return _lib
+
+
+def has_legacy_kernels():
+    """True when the loaded library was built with the superseded tf32 / tf32x3 kernels (make LEGACY=1)."""
+    return bool(lib().addk_build_flags() & 1)
 
 
 def check(rc, what):

@@ -102,7 +102,11 @@ class ADDModel(torch.nn.Module):
         torch.nn.init.uniform_(self._disc_logits.weight, -1.0, 1.0)
         torch.nn.init.zeros_(self._disc_logits.bias)
         self.obs_dim, self.disc_dim, self.act_dim = obs_dim, disc_dim, act_dim
-        self.precision = _lib.PRECISIONS[config.get("mlp_precision", "fp32")]
+        prec = config.get("mlp_precision", "fp32")
+        self.precision = _lib.PRECISIONS[prec]
+        if prec in ("tf32x3", "tf32") and not _lib.has_legacy_kernels():
+            raise _lib.AddkError("mlp_precision %r is a superseded mode: build csrc with `make LEGACY=1` and set "
+                                 "ADDK_LIB=.../libaddk_legacy.so (default modes: f16x3, bf16, fp32)" % prec)
         self._pack(torch.device(device))
 
     # ---- flat parameter vector -----------------------------------------------------------------------------

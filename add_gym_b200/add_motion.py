@@ -62,6 +62,19 @@ class AdaptiveSegmentSampler:
             _lib.ptr(ids_out), _lib.ptr(times_out))
         _lib.check(rc, "addk_sample_motion_time")
 
+    def start_times_from_draws(self, clip_ids, segments, uniforms):
+        """The arithmetic of sample_start_frame AFTER its two draws (sampler.py:84-92), for callers that keep the
+        reference's own torch.multinomial / torch.rand calls: t = seg * size + U * size -> (t // dt) * dt ->
+        clamp(min = min_start_time).  Bit-exact with the reference on identical draws."""
+        n = clip_ids.shape[0]
+        times = torch.empty(n, dtype=torch.float32, device=clip_ids.device)
+        rc = _lib.lib().addk_start_time_from_draws(
+            _lib.stream(), _lib.ptr(self.segment_sizes), C.c_float(self.dt), C.c_float(self.min_start_time),
+            _lib.ptr(clip_ids.to(torch.long).contiguous()), _lib.ptr(segments.to(torch.long).contiguous()),
+            _lib.ptr(uniforms.to(torch.float32).contiguous()), C.c_int(n), _lib.ptr(times))
+        _lib.check(rc, "addk_start_time_from_draws")
+        return times
+
     def sample_start_frame(self, clip_ids=None):
         """Reference signature: start times for the given clips (sampler.py:75-92)."""
         n = clip_ids.shape[0]

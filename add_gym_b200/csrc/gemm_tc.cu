@@ -24,6 +24,10 @@
 #include <cudaTypedefs.h>
 #include <stdlib.h>
 #include <cuda_fp16.h>
+#include "switches.h"
+
+extern int g_addk_last_gemm_kernel;      // api.cu: id of the kernel the last addk_gemm dispatched to (tests)
+extern long long* g_addk_stamps;         // api.cu: optional device buffer for clock stamps (addk_debug_set_stamp_buffer)
 
 namespace addk { int sgemm_launch(cudaStream_t st, const addk_gemm_args& a); }
 
@@ -43,7 +47,7 @@ struct Params {
   int a_mn, b_mn;              // operand is MN-major (memory rows = contraction index)
   long long slab_stride;       // floats between split-K slabs
   void* C16;                   // bf16 kernel: optional bf16 copy of the output (same leading dimension)
-  long long* dbg;              // experiment: clock64 stamps of CTA (0,0,0) of the pair kernel (env ADDK_TC_DBG = address)
+  long long* dbg;              // experiment: clock64 stamps of CTA 0 (addk_debug_set_stamp_buffer; NULL = off)
   int pair_flags;              // CTA-pair kernel experiments: bit0 cluster-scope waits, bit1 relaxed remote arrives
   uint32_t* c_amax;            // f16x3 kernels: slot {W, max} of C: atomicMax of the bit patterns of |C| as stored into [1]
   uint16_t* c_hi;              // f16x3 persistent kernel: fp16 planes of C written by the epilogue with the scale of the
@@ -338,230 +342,6 @@ __device__ __forceinline__ bool epilogue_vec_ok(const Params& p, const float* Cz
          (!p.mask || (((p.ld_mask & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.mask) & 15) == 0)));
 }
 
-// One stage of the ring.  A: 128 (rows | columns) x BK k;  B: BN x BK k.  tf32x3 adds the "lo" halves and uses
-// BK = 16 (64-byte rows) so that four stages still fit; the single-pass mode uses BK = 32 (128-byte rows).
-template <int BN, bool X3>
-struct Cfg {
-  static constexpr int BK = X3 ? 16 : 32;
-  static constexpr int A_BYTES = BM * BK * 4;
-  static constexpr int B_BYTES = BN * BK * 4;
-  static constexpr int STAGE_BYTES = (A_BYTES + B_BYTES) * (X3 ? 2 : 1);
-  static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 6 ? 6 : (200 * 1024) / STAGE_BYTES;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
-  // tf32x3 keeps the small cross terms (lo.hi + hi.lo) in a second accumulator: the tensor core truncates its
-  // fp32 accumulator after every instruction, so three accumulations per k-step into ONE accumulator would
-  // triple that bias; the cross-term accumulator is 2^-11 smaller and its truncation is negligible.
-  static constexpr int TMEM_COLS = (X3 ? 2 : 1) * (BN < 32 ? 32 : BN);
-  // K-major tiles: 128-byte rows -> SWIZZLE_128B (UMMA layout 2), 64-byte rows -> SWIZZLE_64B (layout 4);
-  // 8-row groups are 8 * row bytes apart (SBO).  MN-major tiles: one TMA box = 32 MN x BK k (BK * 128 bytes),
-  // 128B swizzle with 32-byte atoms (layout 1), MN atoms one box apart (LBO), 4-k groups 512 B apart (SBO).
-  static constexpr uint32_t K_LAYOUT = BK == 32 ? 2u : 4u;
-  static constexpr uint32_t K_SBO = 8u * BK * 4u;
-  static constexpr uint32_t MN_BOX_BYTES = BK * 128u;
-};
-
-template <int BN, bool X3>
-__global__ void __launch_bounds__(NTHREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
-  using C = Cfg<BN, X3>;
-  constexpr int BK = C::BK;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw_u32 = smem_u32(smem_raw);
-  const uint32_t base = (raw_u32 + 1023u) & ~1023u;
-  uint8_t* const base_ptr = smem_raw + (base - raw_u32);
-  const uint32_t bars = base + C::STAGES * C::STAGE_BYTES;      // full[S] | empty[S] | ready[S] | tmem_full | tmem_ptr
-  auto full_bar = [&](int s) { return bars + 8u * s; };
-  auto empty_bar = [&](int s) { return bars + 8u * (C::STAGES + s); };
-  auto ready_bar = [&](int s) { return bars + 8u * (2 * C::STAGES + s); };
-  const uint32_t tmem_full_bar = bars + 8u * (3 * C::STAGES);
-  const uint32_t tmem_ptr_addr = bars + 8u * (3 * C::STAGES + 1);
-  auto a_hi = [&](int s) { return base + (uint32_t)s * C::STAGE_BYTES; };
-  auto b_hi = [&](int s) { return a_hi(s) + C::A_BYTES; };
-  auto a_lo = [&](int s) { return b_hi(s) + C::B_BYTES; };
-  auto b_lo = [&](int s) { return a_lo(s) + C::A_BYTES; };
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-  const int kb_total = (p.K + BK - 1) / BK;
-  const int kb_begin = blockIdx.z * p.kb_per_split;
-  const int kb_end = min(kb_total, kb_begin + p.kb_per_split);
-  const int num_kb = kb_end - kb_begin;          // host guarantees >= 1
-
-  if (threadIdx.x == 0) {
-    tma_prefetch_desc(&tmA);
-    tma_prefetch_desc(&tmB);
-    for (int s = 0; s < C::STAGES; ++s) {
-      mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
-      mbar_init(ready_bar(s), 128);
-    }
-    mbar_init(tmem_full_bar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "r"((uint32_t)C::TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  uint32_t tmem_base;
-  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr) : "memory");
-
-  if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      for (int i = 0; i < num_kb; ++i) {
-        const int s = i % C::STAGES;
-        const uint32_t ph = (uint32_t)(i / C::STAGES) & 1u;
-        mbar_wait(empty_bar(s), ph ^ 1u);
-        mbar_expect_tx(full_bar(s), C::A_BYTES + C::B_BYTES);
-        const int k0 = (kb_begin + i) * BK;
-        if (!p.a_mn) {
-          tma_load_2d(a_hi(s), &tmA, full_bar(s), k0, m0);                      // box {BK k, 128 rows}
-        } else {
-#pragma unroll
-          for (int j = 0; j < BM / 32; ++j)                                      // box {32 m, BK k}
-            tma_load_2d(a_hi(s) + j * C::MN_BOX_BYTES, &tmA, full_bar(s), m0 + 32 * j, k0);
-        }
-        if (!p.b_mn) {
-          tma_load_2d(b_hi(s), &tmB, full_bar(s), k0, n0);                      // box {BK k, BN rows}
-        } else {
-#pragma unroll
-          for (int j = 0; j < BN / 32; ++j)
-            tma_load_2d(b_hi(s) + j * C::MN_BOX_BYTES, &tmB, full_bar(s), n0 + 32 * j, k0);
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      // instruction descriptor: D fp32, A/B tf32, majors, N>>3, M>>4
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.a_mn ? 1 : 0) << 15) |
-                             ((uint32_t)(p.b_mn ? 1 : 0) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-      const uint32_t a_lbo = p.a_mn ? C::MN_BOX_BYTES : 16u, b_lbo = p.b_mn ? C::MN_BOX_BYTES : 16u;
-      const uint32_t a_sbo = p.a_mn ? 512u : C::K_SBO, b_sbo = p.b_mn ? 512u : C::K_SBO;
-      const uint32_t a_lay = p.a_mn ? 1u : C::K_LAYOUT, b_lay = p.b_mn ? 1u : C::K_LAYOUT;
-      const uint32_t a_kstep = p.a_mn ? 1024u : 32u, b_kstep = p.b_mn ? 1024u : 32u;   // 8 k per MMA
-      uint32_t acc = 0, acc_x = 0;
-      for (int i = 0; i < num_kb; ++i) {
-        const int s = i % C::STAGES;
-        const uint32_t ph = (uint32_t)(i / C::STAGES) & 1u;
-        mbar_wait(full_bar(s), ph);
-        tc_fence_after();
-        // main term: the tensor core truncates the fp32 operands to tf32 itself, so hi(x) is the landed tile as is
-#pragma unroll
-        for (int ks = 0; ks < BK / UMMA_K; ++ks) {
-          umma_tf32(tmem_base, smem_desc(a_hi(s) + ks * a_kstep, a_lbo, a_sbo, a_lay),
-                    smem_desc(b_hi(s) + ks * b_kstep, b_lbo, b_sbo, b_lay), idesc, acc);
-          acc = 1;
-        }
-        if (X3) {
-          mbar_wait(ready_bar(s), ph);         // lo tiles written by the splitter warps
-          tc_fence_after();
-#pragma unroll
-          for (int ks = 0; ks < BK / UMMA_K; ++ks) {
-            const uint64_t dah = smem_desc(a_hi(s) + ks * a_kstep, a_lbo, a_sbo, a_lay);
-            const uint64_t dbh = smem_desc(b_hi(s) + ks * b_kstep, b_lbo, b_sbo, b_lay);
-            const uint64_t dal = smem_desc(a_lo(s) + ks * a_kstep, a_lbo, a_sbo, a_lay);
-            const uint64_t dbl = smem_desc(b_lo(s) + ks * b_kstep, b_lbo, b_sbo, b_lay);
-            umma_tf32(tmem_base + BN, dal, dbh, idesc, acc_x);
-            acc_x = 1;
-            umma_tf32(tmem_base + BN, dah, dbl, idesc, acc_x);
-          }
-        }
-        umma_commit(empty_bar(s));          // stage reusable once these MMAs have read it
-      }
-      umma_commit(tmem_full_bar);           // accumulators complete
-    }
-  } else {
-    // ===================== splitter (tf32x3) + epilogue: warps 2..5 =====================
-    const int t = threadIdx.x - 64;          // 0..127
-    if (X3) {
-      // lo = x - tf32_trunc(x), elementwise (so the swizzled placement does not matter; A and B are contiguous
-      // in the stage and so are their lo twins).  The hi tile is left untouched: the MMA reads it concurrently.
-      constexpr int N4 = (C::A_BYTES + C::B_BYTES) / 16;
-      constexpr int PER = N4 / 128;
-      static_assert(N4 % 128 == 0, "tile size");
-      for (int i = 0; i < num_kb; ++i) {
-        const int s = i % C::STAGES;
-        const uint32_t ph = (uint32_t)(i / C::STAGES) & 1u;
-        mbar_wait(full_bar(s), ph);
-        const float4* src = reinterpret_cast<const float4*>(base_ptr + (size_t)s * C::STAGE_BYTES);
-        float4* dst = reinterpret_cast<float4*>(base_ptr + (size_t)s * C::STAGE_BYTES + C::A_BYTES + C::B_BYTES);
-#pragma unroll
-        for (int j0 = 0; j0 < PER; j0 += 4) {
-          float4 x[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) if (j0 + u < PER) x[u] = src[t + 128 * (j0 + u)];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            if (j0 + u < PER) {
-              float4 l;
-              l.x = x[u].x - __uint_as_float(__float_as_uint(x[u].x) & 0xFFFFE000u);
-              l.y = x[u].y - __uint_as_float(__float_as_uint(x[u].y) & 0xFFFFE000u);
-              l.z = x[u].z - __uint_as_float(__float_as_uint(x[u].z) & 0xFFFFE000u);
-              l.w = x[u].w - __uint_as_float(__float_as_uint(x[u].w) & 0xFFFFE000u);
-              dst[t + 128 * (j0 + u)] = l;
-            }
-          }
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
-        mbar_arrive(ready_bar(s));
-      }
-    }
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
-    const int q = warp & 3;                  // TMEM lane quarter this warp may access
-    const int row = m0 + 32 * q + lane;
-    float* Cz = p.C + (size_t)blockIdx.z * p.slab_stride;
-    const bool vec = epilogue_vec_ok(p, Cz);
-    // Each warp owns rows [32q, 32q+32) of the tile: blocks of up to 128 columns go TMEM -> registers -> a 16 KB
-    // staging tile per warp (the operand stages are idle by now) -> full-row stores (store_staged).
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    constexpr int CWB = BN < 128 ? BN : 128;
-    float4* stg = reinterpret_cast<float4*>(base_ptr + (32 * CWB * 4) * q);
-#pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += CWB) {
-      if (n0 + c0 >= p.N) break;             // warp-uniform
-#pragma unroll
-      for (int cc = 0; cc < CWB / 32; ++cc) {
-        uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(c0 + cc * 32), v);
-        if (X3) {
-          uint32_t w[32];
-          tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(BN + c0 + cc * 32), w);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w[j]));
-        }
-        if (vec) {
-#pragma unroll
-          for (int c4 = 0; c4 < 8; ++c4)
-            stage_put<CWB>(stg, lane, cc * 8 + c4, __uint_as_float(v[4 * c4]), __uint_as_float(v[4 * c4 + 1]),
-                           __uint_as_float(v[4 * c4 + 2]), __uint_as_float(v[4 * c4 + 3]));
-        } else if (row < p.M) {
-          float f[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-          store_row_scalar(p, Cz, row, n0 + c0 + cc * 32, f);
-        }
-      }
-      if (vec) {
-        __syncwarp();
-        store_staged<CWB>(p, Cz, stg, lane, m0 + 32 * q, n0 + c0);
-        __syncwarp();
-      }
-    }
-  }
-  // ===================== teardown =====================
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS) : "memory");
-  }
-}
-
 // ---------------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------------
@@ -574,606 +354,9 @@ static bool resolve_encode() {
   return true;
 }
 
-// 2-D fp32 tensor map: memory [outer, inner] with `ld` floats between rows; box {32, box_rows}, 128-byte swizzle.
-static bool make_map(CUtensorMap* map, const float* ptr, long long inner, long long outer, long long ld, int box_inner,
-                     int box_rows, bool mn_major) {
-  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
-  cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_rows};
-  cuuint32_t estr[2] = {1u, 1u};
-  CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B
-                                 : (box_inner == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B),
-                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS;
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// tf32x3 ("fp32-parity") kernel.  Same TMA / tcgen05 pipeline as above plus two things the accuracy bar needs:
-//  * the cross terms lo.hi + hi.lo go to a second TMEM accumulator;
-//  * the main accumulator is DRAINED into fp32 registers every X3_CHUNK_KB k-blocks (K = 256): the tensor core
-//    truncates its accumulator after every instruction (measured bias -1.64e-8 per accumulated MMA, i.e. -2.1e-6 at
-//    K = 1024), so the tensor core only ever sums 32 instructions and the CUDA cores add the chunks with
-//    round-to-nearest -> 5e-7, the level of an fp32 FMA loop.
-// 10 warps: 0 = TMA producer, 1 = MMA issuer / TMEM allocator, 2..9 = workers (hi/lo split of every landed tile,
-// chunk drains, epilogue).  Worker w owns TMEM lanes 32*(w%4).. and column half (w-2)/4, BN/2 running sums per thread.
-// ---------------------------------------------------------------------------------------------------------------
+// tf32x3 drains share these with the f16x3 kernels
 constexpr int X3_THREADS = 320;
-constexpr int X3_CHUNK_KB = 16;
-// Expected truncation loss of the tensor core's accumulator per accumulated instruction, relative to the chunk sum
-// (measured on B200 with tf32-exact operands: -1.68e-8 .. -2.1e-8 per instruction for 4..2048 instructions,
-// tools/tc_accuracy.py).  The drain adds it back, which removes the systematic part of the bias (-5.4e-7 per
-// 32-instruction chunk) and leaves the random part (~3e-7).
 constexpr float X3_TRUNC_LOSS_PER_MMA = 1.7e-8f;
-
-template <int BN>
-__global__ void __launch_bounds__(X3_THREADS, 1)
-gemm_tc_x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
-  using C = Cfg<BN, true>;
-  constexpr int BK = C::BK;
-  constexpr int CPW = BN / 2;                     // accumulator columns per worker thread
-  constexpr int NCH = CPW / 32;                   // 32-column chunks per worker
-  static_assert(CPW % 32 == 0, "BN must be a multiple of 64");
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw_u32 = smem_u32(smem_raw);
-  const uint32_t base = (raw_u32 + 1023u) & ~1023u;
-  uint8_t* const base_ptr = smem_raw + (base - raw_u32);
-  const uint32_t bars = base + C::STAGES * C::STAGE_BYTES;
-  auto full_bar = [&](int s) { return bars + 8u * s; };
-  auto empty_bar = [&](int s) { return bars + 8u * (C::STAGES + s); };
-  auto ready_bar = [&](int s) { return bars + 8u * (2 * C::STAGES + s); };
-  const uint32_t tmem_full_bar = bars + 8u * (3 * C::STAGES);
-  const uint32_t chunk_full_bar = bars + 8u * (3 * C::STAGES + 1);
-  const uint32_t chunk_empty_bar = bars + 8u * (3 * C::STAGES + 2);
-  const uint32_t tmem_ptr_addr = bars + 8u * (3 * C::STAGES + 3);
-  auto a_hi = [&](int s) { return base + (uint32_t)s * C::STAGE_BYTES; };
-  auto b_hi = [&](int s) { return a_hi(s) + C::A_BYTES; };
-  auto a_lo = [&](int s) { return b_hi(s) + C::B_BYTES; };
-  auto b_lo = [&](int s) { return a_lo(s) + C::A_BYTES; };
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-  const int kb_total = (p.K + BK - 1) / BK;
-  const int kb_begin = blockIdx.z * p.kb_per_split;
-  const int kb_end = min(kb_total, kb_begin + p.kb_per_split);
-  const int num_kb = kb_end - kb_begin;
-
-  if (threadIdx.x == 0) {
-    tma_prefetch_desc(&tmA);
-    tma_prefetch_desc(&tmB);
-    for (int s = 0; s < C::STAGES; ++s) {
-      mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
-      mbar_init(ready_bar(s), 256);
-    }
-    mbar_init(tmem_full_bar, 1);
-    mbar_init(chunk_full_bar, 1);
-    mbar_init(chunk_empty_bar, 256);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "r"((uint32_t)C::TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  uint32_t tmem_base;
-  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr) : "memory");
-
-  if (warp == 0) {
-    if (lane == 0) {
-      for (int i = 0; i < num_kb; ++i) {
-        const int s = i % C::STAGES;
-        const uint32_t ph = (uint32_t)(i / C::STAGES) & 1u;
-        mbar_wait(empty_bar(s), ph ^ 1u);
-        if ((p.pair_flags & 8) && i >= C::STAGES) { mbar_arrive(full_bar(s)); continue; }   // experiment: no TMA traffic
-        mbar_expect_tx(full_bar(s), C::A_BYTES + C::B_BYTES);
-        const int k0 = (kb_begin + i) * BK;
-        if (!p.a_mn) {
-          tma_load_2d(a_hi(s), &tmA, full_bar(s), k0, m0);
-        } else {
-#pragma unroll
-          for (int j = 0; j < BM / 32; ++j) tma_load_2d(a_hi(s) + j * C::MN_BOX_BYTES, &tmA, full_bar(s), m0 + 32 * j, k0);
-        }
-        if (!p.b_mn) {
-          tma_load_2d(b_hi(s), &tmB, full_bar(s), k0, n0);
-        } else {
-#pragma unroll
-          for (int j = 0; j < BN / 32; ++j) tma_load_2d(b_hi(s) + j * C::MN_BOX_BYTES, &tmB, full_bar(s), n0 + 32 * j, k0);
-        }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.a_mn ? 1 : 0) << 15) |
-                             ((uint32_t)(p.b_mn ? 1 : 0) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-      const uint32_t a_lbo = p.a_mn ? C::MN_BOX_BYTES : 16u, b_lbo = p.b_mn ? C::MN_BOX_BYTES : 16u;
-      const uint32_t a_sbo = p.a_mn ? 512u : C::K_SBO, b_sbo = p.b_mn ? 512u : C::K_SBO;
-      const uint32_t a_lay = p.a_mn ? 1u : C::K_LAYOUT, b_lay = p.b_mn ? 1u : C::K_LAYOUT;
-      const uint32_t a_kstep = p.a_mn ? 1024u : 32u, b_kstep = p.b_mn ? 1024u : 32u;
-      uint32_t acc = 0, acc_x = 0;
-      for (int i = 0; i < num_kb; ++i) {
-        const int s = i % C::STAGES;
-        const uint32_t ph = (uint32_t)(i / C::STAGES) & 1u;
-        const bool new_chunk = (i % X3_CHUNK_KB == 0) && i > 0;
-        // cross terms first at a chunk boundary: they go to the other accumulator and overlap the drain
-        mbar_wait(ready_bar(s), ph);
-        tc_fence_after();
-#pragma unroll
-        for (int ks = 0; ks < BK / UMMA_K; ++ks) {
-          const uint64_t dah = smem_desc(a_hi(s) + ks * a_kstep, a_lbo, a_sbo, a_lay);
-          const uint64_t dbh = smem_desc(b_hi(s) + ks * b_kstep, b_lbo, b_sbo, b_lay);
-          const uint64_t dal = smem_desc(a_lo(s) + ks * a_kstep, a_lbo, a_sbo, a_lay);
-          const uint64_t dbl = smem_desc(b_lo(s) + ks * b_kstep, b_lbo, b_sbo, b_lay);
-          umma_tf32(tmem_base + BN, dal, dbh, idesc, acc_x);
-          acc_x = 1;
-          umma_tf32(tmem_base + BN, dah, dbl, idesc, acc_x);
-        }
-        if (new_chunk && !(p.pair_flags & 4)) {   // the workers have copied the previous chunk out of the main accumulator
-          mbar_wait(chunk_empty_bar, (uint32_t)(i / X3_CHUNK_KB - 1) & 1u);
-          tc_fence_after();
-          acc = 0;
-        }
-#pragma unroll
-        for (int ks = 0; ks < BK / UMMA_K; ++ks) {
-          umma_tf32(tmem_base, smem_desc(a_hi(s) + ks * a_kstep, a_lbo, a_sbo, a_lay),
-                    smem_desc(b_hi(s) + ks * b_kstep, b_lbo, b_sbo, b_lay), idesc, acc);
-          acc = 1;
-        }
-        umma_commit(empty_bar(s));
-        if (((i + 1) % X3_CHUNK_KB == 0) && (i + 1 < num_kb)) umma_commit(chunk_full_bar);
-      }
-      umma_commit(tmem_full_bar);
-    }
-  } else {
-    // ===================== workers: warps 2..9 =====================
-    const int t = threadIdx.x - 64;          // 0..255
-    const int q = warp & 3;                  // TMEM lane quarter
-    const int half = (warp - 2) >> 2;        // column half
-    const uint32_t t_main = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(half * CPW);
-    float acc[CPW];
-#pragma unroll
-    for (int j = 0; j < CPW; ++j) acc[j] = 0.f;
-    constexpr int N4 = (C::A_BYTES + C::B_BYTES) / 16;
-    constexpr int PER = N4 / 256;
-    static_assert(N4 % 256 == 0, "tile size");
-    for (int i = 0; i < num_kb; ++i) {
-      const int s = i % C::STAGES;
-      const uint32_t ph = (uint32_t)(i / C::STAGES) & 1u;
-      mbar_wait(full_bar(s), ph);
-      const float4* src = reinterpret_cast<const float4*>(base_ptr + (size_t)s * C::STAGE_BYTES);
-      float4* dst = reinterpret_cast<float4*>(base_ptr + (size_t)s * C::STAGE_BYTES + C::A_BYTES + C::B_BYTES);
-      if (p.pair_flags & 4) { mbar_arrive(ready_bar(s)); continue; }   // experiment: no split work (and no drain)
-      float4 x[PER];
-#pragma unroll
-      for (int u = 0; u < PER; ++u) x[u] = src[t + 256 * u];
-#pragma unroll
-      for (int u = 0; u < PER; ++u) {
-        float4 l;
-        l.x = x[u].x - __uint_as_float(__float_as_uint(x[u].x) & 0xFFFFE000u);
-        l.y = x[u].y - __uint_as_float(__float_as_uint(x[u].y) & 0xFFFFE000u);
-        l.z = x[u].z - __uint_as_float(__float_as_uint(x[u].z) & 0xFFFFE000u);
-        l.w = x[u].w - __uint_as_float(__float_as_uint(x[u].w) & 0xFFFFE000u);
-        dst[t + 256 * u] = l;
-      }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      mbar_arrive(ready_bar(s));
-      if ((i % X3_CHUNK_KB == 0) && i > 0) {   // drain the chunk that ended with k-block i-1
-        mbar_wait(chunk_full_bar, (uint32_t)(i / X3_CHUNK_KB - 1) & 1u);
-        tc_fence_after();
-        const float comp = X3_TRUNC_LOSS_PER_MMA * (float)(X3_CHUNK_KB * (BK / UMMA_K));
-#pragma unroll
-        for (int cc = 0; cc < NCH; ++cc) {
-          uint32_t v[32];
-          tmem_ld32(t_main + (uint32_t)(cc * 32), v);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) acc[cc * 32 + j] += fmaf(__uint_as_float(v[j]), comp, __uint_as_float(v[j]));
-        }
-        tc_fence_before();
-        mbar_arrive(chunk_empty_bar);
-      }
-    }
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
-    const float comp_last = X3_TRUNC_LOSS_PER_MMA * (float)((((num_kb - 1) % X3_CHUNK_KB) + 1) * (BK / UMMA_K));
-#pragma unroll
-    for (int cc = 0; cc < NCH; ++cc) {         // last chunk of the main accumulator + the cross-term accumulator
-      uint32_t v[32];
-      tmem_ld32(t_main + (uint32_t)(cc * 32), v);
-#pragma unroll
-      for (int j = 0; j < 32; ++j) acc[cc * 32 + j] += fmaf(__uint_as_float(v[j]), comp_last, __uint_as_float(v[j]));
-      tmem_ld32(t_main + (uint32_t)(BN + cc * 32), v);
-#pragma unroll
-      for (int j = 0; j < 32; ++j) acc[cc * 32 + j] += __uint_as_float(v[j]);
-    }
-    // ---- epilogue: this warp's 32 x CPW accumulators -> staging tile -> full-row stores (store_staged)
-    float* Cz = p.C + (size_t)blockIdx.z * p.slab_stride;
-    const bool vec = epilogue_vec_ok(p, Cz);
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    float4* stg = reinterpret_cast<float4*>(base_ptr + (32 * CPW * 4) * (warp - 2));
-    const int row = m0 + 32 * q + lane;
-    const int cw0 = n0 + half * CPW;
-    if (cw0 < p.N) {                           // warp-uniform
-      if (vec) {
-#pragma unroll
-        for (int sl = 0; sl < CPW / 4; ++sl) stage_put<CPW>(stg, lane, sl, acc[4 * sl], acc[4 * sl + 1], acc[4 * sl + 2], acc[4 * sl + 3]);
-        __syncwarp();
-        store_staged<CPW>(p, Cz, stg, lane, m0 + 32 * q, cw0);
-      } else if (row < p.M) {
-#pragma unroll
-        for (int cc = 0; cc < NCH; ++cc) store_row_scalar(p, Cz, row, cw0 + cc * 32, acc + cc * 32);
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS) : "memory");
-  }
-}
-
-template <int BN>
-static int launch_x3(cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, dim3 grid) {
-  using C = Cfg<BN, true>;
-  static bool configured = false;
-  if (!configured) {
-    if (cudaFuncSetAttribute(gemm_tc_x3_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES) != cudaSuccess) {
-      addk_set_error("gemm_tc: cannot raise the dynamic shared memory limit");
-      return ADDK_ERR_LAUNCH;
-    }
-    configured = true;
-  }
-  gemm_tc_x3_kernel<BN><<<grid, X3_THREADS, C::SMEM_BYTES, st>>>(ta, tb, p);
-  return ADDK_OK;
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// tf32x3, CTA-pair version (tcgen05 cta_group::2): a cluster of two CTAs on one TPC computes a 256 x 256 tile.
-// Each CTA stages its own 128 rows of A and its own 128-row half of B; the leader CTA's single thread issues
-// M = 256 MMAs that read both CTAs' shared memory, so per CTA the operand traffic per k-block drops from
-// (128 + 256) to (128 + 128) rows -- less L2->smem traffic, less splitting work, 1/3 fewer operand bytes per MMA.
-// Everything else (hi/lo split, second accumulator for the cross terms, chunked drain, coalesced epilogue) is the
-// 1-CTA kernel above; each CTA drains / stores its own 128 accumulator rows.
-// Barriers: full/empty are CTA-local (local TMA; multicast tcgen05.commit frees the stage in both CTAs);
-// ready / chunk_empty live in the leader and collect one arrival per worker warp of BOTH CTAs (remote arrive).
-// ---------------------------------------------------------------------------------------------------------------
-struct Cfg2 {
-  static constexpr int BN = 256;                  // tile N; each CTA stages BN/2 rows of B
-  static constexpr int BK = 16;
-  static constexpr int A_BYTES = BM * BK * 4;     // 8 KB
-  static constexpr int B_BYTES = (BN / 2) * BK * 4;
-  static constexpr int STAGE_BYTES = 2 * (A_BYTES + B_BYTES);
-  static constexpr int STAGES = 6;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
-  static constexpr int TMEM_COLS = 512;
-  static constexpr uint32_t K_LAYOUT = 4u;
-  static constexpr uint32_t K_SBO = 8u * BK * 4u;
-  static constexpr uint32_t MN_BOX_BYTES = BK * 128u;
-};
-
-__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ uint32_t mapa_rank0(uint32_t addr) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(r) : "r"(addr));
-  return r;
-}
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-// Remote arrive without the cluster-scope release: measured, `arrive.release.cluster` stalls the issuing warp for
-// ~1.5k cycles, which made the worker warps the bottleneck (301 us vs 199 us per 16384x1024x1024 layer).  What the
-// leader's MMAs must see is this CTA's OWN shared memory; every writer has already executed fence.proxy.async
-// (generic -> async proxy) and the warp has re-converged, so a CTA-scope fence followed by a relaxed arrive is enough.
-__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
-  __threadfence_block();
-  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait_cluster(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait_cluster(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) __trap();
-  }
-}
-__device__ __forceinline__ void umma_tf32_2cta(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
-}
-__device__ __forceinline__ void umma_commit_2cta(uint32_t bar) {   // arrives on `bar` (same offset) in both CTAs
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               ::"r"(bar), "h"((uint16_t)3) : "memory");
-}
-
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(X3_THREADS, 1)
-gemm_tc_x3_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
-  using C = Cfg2;
-  constexpr int BK = C::BK, BN = C::BN;
-  constexpr int CPW = BN / 2, NCH = CPW / 32;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw_u32 = smem_u32(smem_raw);
-  const uint32_t base = (raw_u32 + 1023u) & ~1023u;
-  uint8_t* const base_ptr = smem_raw + (base - raw_u32);
-  const uint32_t bars = base + C::STAGES * C::STAGE_BYTES;
-  auto full_bar = [&](int s) { return bars + 8u * s; };
-  auto empty_bar = [&](int s) { return bars + 8u * (C::STAGES + s); };
-  auto ready_bar = [&](int s) { return bars + 8u * (2 * C::STAGES + s); };
-  const uint32_t tmem_full_bar = bars + 8u * (3 * C::STAGES);
-  const uint32_t chunk_full_bar = bars + 8u * (3 * C::STAGES + 1);
-  const uint32_t chunk_empty_bar = bars + 8u * (3 * C::STAGES + 2);
-  const uint32_t tmem_ptr_addr = bars + 8u * (3 * C::STAGES + 3);
-  auto a_hi = [&](int s) { return base + (uint32_t)s * C::STAGE_BYTES; };
-  auto b_hi = [&](int s) { return a_hi(s) + C::A_BYTES; };
-  auto a_lo = [&](int s) { return b_hi(s) + C::B_BYTES; };
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();
-  const bool leader = rank == 0;
-  const int m0 = (blockIdx.y * 2 + (int)rank) * BM;          // this CTA's 128 accumulator rows
-  const int n0 = (blockIdx.x >> 1) * BN;                      // tile columns
-  const int nb0 = n0 + (int)rank * (BN / 2);                  // this CTA's half of B
-  const int kb_total = (p.K + BK - 1) / BK;
-  const int kb_begin = blockIdx.z * p.kb_per_split;
-  const int kb_end = min(kb_total, kb_begin + p.kb_per_split);
-  const int num_kb = kb_end - kb_begin;
-  long long* const dbg = (p.dbg && leader && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) ? p.dbg : nullptr;
-  if (dbg && threadIdx.x == 32) dbg[0] = clock64();
-
-  if (threadIdx.x == 0) {
-    tma_prefetch_desc(&tmA);
-    tma_prefetch_desc(&tmB);
-    for (int s = 0; s < C::STAGES; ++s) {
-      mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
-      mbar_init(ready_bar(s), 16);            // 8 worker warps x 2 CTAs (only the leader's copy is used)
-    }
-    mbar_init(tmem_full_bar, 1);
-    mbar_init(chunk_full_bar, 1);
-    mbar_init(chunk_empty_bar, 16);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "r"((uint32_t)C::TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-  }
-  tc_fence_before();
-  cluster_sync_all();
-  tc_fence_after();
-  uint32_t tmem_base;
-  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr) : "memory");
-  if (dbg && threadIdx.x == 32) dbg[1] = clock64();
-
-  if (warp == 0) {
-    // ---- TMA producer (each CTA loads its own tiles)
-    if (lane == 0) {
-      for (int i = 0; i < num_kb; ++i) {
-        const int s = i % C::STAGES;
-        const uint32_t ph = (uint32_t)(i / C::STAGES) & 1u;
-        mbar_wait(empty_bar(s), ph ^ 1u);
-        if ((p.pair_flags & 8) && i >= C::STAGES) { mbar_arrive(full_bar(s)); continue; }   // experiment: no TMA traffic
-        mbar_expect_tx(full_bar(s), C::A_BYTES + C::B_BYTES);
-        const int k0 = (kb_begin + i) * BK;
-        if (!p.a_mn) {
-          tma_load_2d(a_hi(s), &tmA, full_bar(s), k0, m0);
-        } else {
-#pragma unroll
-          for (int j = 0; j < BM / 32; ++j) tma_load_2d(a_hi(s) + j * C::MN_BOX_BYTES, &tmA, full_bar(s), m0 + 32 * j, k0);
-        }
-        if (!p.b_mn) {
-          tma_load_2d(b_hi(s), &tmB, full_bar(s), k0, nb0);
-        } else {
-#pragma unroll
-          for (int j = 0; j < BN / 64; ++j) tma_load_2d(b_hi(s) + j * C::MN_BOX_BYTES, &tmB, full_bar(s), nb0 + 32 * j, k0);
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ---- MMA issuer: leader CTA only.  The WHOLE warp runs the loop so that the descriptors stay warp-uniform
-    // (uniform registers, no per-MMA R2UR / address arithmetic); one elected lane issues.  Measured: with a single
-    // divergent thread computing descriptors the issue thread, not the tensor pipe, paced the kernel (230 cycles per
-    // 128x256x8 MMA against a floor of 128).
-    if (leader) {
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.a_mn ? 1 : 0) << 15) |
-                             ((uint32_t)(p.b_mn ? 1 : 0) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
-      const uint32_t a_lbo = p.a_mn ? C::MN_BOX_BYTES : 16u, b_lbo = p.b_mn ? C::MN_BOX_BYTES : 16u;
-      const uint32_t a_sbo = p.a_mn ? 512u : C::K_SBO, b_sbo = p.b_mn ? 512u : C::K_SBO;
-      const uint32_t a_lay = p.a_mn ? 1u : C::K_LAYOUT, b_lay = p.b_mn ? 1u : C::K_LAYOUT;
-      // descriptors of stage 0, k-step 0; everything else is a constant added to the 14-bit start-address field
-      const uint64_t dA0 = smem_desc(a_hi(0), a_lbo, a_sbo, a_lay);
-      const uint64_t dB0 = smem_desc(b_hi(0), b_lbo, b_sbo, b_lay);
-      const uint64_t a_k16 = p.a_mn ? (1024u >> 4) : (32u >> 4), b_k16 = p.b_mn ? (1024u >> 4) : (32u >> 4);
-      constexpr uint64_t LO16 = (C::A_BYTES + C::B_BYTES) >> 4, STAGE16 = C::STAGE_BYTES >> 4;
-      const bool issuer = elect_one();
-      const bool no_drain = (p.pair_flags & 4) != 0;
-      const bool pair_wait_cluster = (p.pair_flags & 1) != 0;
-      uint32_t acc = 0, acc_x = 0, ph = 0, chunk_par = 0;
-      int chunk_left = X3_CHUNK_KB;       // k-blocks left in the current drain chunk
-      for (int i = 0; i < num_kb; ph ^= 1u) {
-#pragma unroll
-        for (int s = 0; s < C::STAGES; ++s) {
-          if (i >= num_kb) break;
-          if (pair_wait_cluster) mbar_wait_cluster(ready_bar(s), ph); else mbar_wait(ready_bar(s), ph);   // both CTAs: tiles landed, lo halves written
-          tc_fence_after();
-          if (dbg && i == 0 && lane == 0) dbg[2] = clock64();
-          const uint64_t dah = dA0 + s * STAGE16, dbh = dB0 + s * STAGE16;
-          if (issuer) {
-#pragma unroll
-            for (int ks = 0; ks < BK / UMMA_K; ++ks) {
-              umma_tf32_2cta(tmem_base + BN, dah + LO16 + ks * a_k16, dbh + ks * b_k16, idesc, acc_x);
-              acc_x = 1;
-              umma_tf32_2cta(tmem_base + BN, dah + ks * a_k16, dbh + LO16 + ks * b_k16, idesc, acc_x);
-            }
-          }
-          if (chunk_left == 0) {          // the workers have copied the previous chunk out of the main accumulator
-            if (!no_drain) {
-              if (pair_wait_cluster) mbar_wait_cluster(chunk_empty_bar, chunk_par); else mbar_wait(chunk_empty_bar, chunk_par);
-              tc_fence_after();
-              acc = 0;
-            }
-            chunk_par ^= 1u;
-            chunk_left = X3_CHUNK_KB;
-          }
-          --chunk_left;
-          ++i;
-          if (issuer) {
-#pragma unroll
-            for (int ks = 0; ks < BK / UMMA_K; ++ks) {
-              umma_tf32_2cta(tmem_base, dah + ks * a_k16, dbh + ks * b_k16, idesc, acc);
-              acc = 1;
-            }
-            umma_commit_2cta(empty_bar(s));
-            if (chunk_left == 0 && i < num_kb) umma_commit_2cta(chunk_full_bar);
-          }
-          __syncwarp();
-        }
-      }
-      if (issuer) umma_commit_2cta(tmem_full_bar);
-      __syncwarp();
-      if (dbg && lane == 0) dbg[3] = clock64();
-    }
-  } else {
-    // ---- workers: warps 2..9
-    const int t = threadIdx.x - 64;
-    const int q = warp & 3;
-    const int half = (warp - 2) >> 2;
-    const uint32_t t_main = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(half * CPW);
-    float acc[CPW];
-#pragma unroll
-    for (int j = 0; j < CPW; ++j) acc[j] = 0.f;
-    constexpr int N4 = (C::A_BYTES + C::B_BYTES) / 16;
-    constexpr int PER = N4 / 256;
-    static_assert(N4 % 256 == 0, "tile size");
-    uint32_t ready_remote[C::STAGES];
-#pragma unroll
-    for (int s = 0; s < C::STAGES; ++s) ready_remote[s] = mapa_rank0(ready_bar(s));
-    const uint32_t chunk_empty_remote = mapa_rank0(chunk_empty_bar);
-    for (int i = 0; i < num_kb; ++i) {
-      const int s = i % C::STAGES;
-      const uint32_t ph = (uint32_t)(i / C::STAGES) & 1u;
-      mbar_wait(full_bar(s), ph);
-      const float4* src = reinterpret_cast<const float4*>(base_ptr + (size_t)s * C::STAGE_BYTES);
-      float4* dst = reinterpret_cast<float4*>(base_ptr + (size_t)s * C::STAGE_BYTES + C::A_BYTES + C::B_BYTES);
-      if (p.pair_flags & 4) {   // experiment: no split work (and no drain)
-        __syncwarp();
-        if (lane == 0) {
-          uint32_t ra = ready_remote[0];
-#pragma unroll
-          for (int ss = 1; ss < C::STAGES; ++ss) if (s == ss) ra = ready_remote[ss];
-          mbar_arrive_cluster_relaxed(ra);
-        }
-        continue;
-      }
-      float4 x[PER];
-#pragma unroll
-      for (int u = 0; u < PER; ++u) x[u] = src[t + 256 * u];
-#pragma unroll
-      for (int u = 0; u < PER; ++u) {
-        float4 l;
-        l.x = x[u].x - __uint_as_float(__float_as_uint(x[u].x) & 0xFFFFE000u);
-        l.y = x[u].y - __uint_as_float(__float_as_uint(x[u].y) & 0xFFFFE000u);
-        l.z = x[u].z - __uint_as_float(__float_as_uint(x[u].z) & 0xFFFFE000u);
-        l.w = x[u].w - __uint_as_float(__float_as_uint(x[u].w) & 0xFFFFE000u);
-        dst[t + 256 * u] = l;
-      }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      __syncwarp();
-      if (lane == 0) {
-        uint32_t ra = ready_remote[0];
-#pragma unroll
-        for (int ss = 1; ss < C::STAGES; ++ss) if (s == ss) ra = ready_remote[ss];
-        if (p.pair_flags & 2) mbar_arrive_cluster_relaxed(ra); else mbar_arrive_cluster(ra);
-      }
-      if ((i % X3_CHUNK_KB == 0) && i > 0) {
-        mbar_wait(chunk_full_bar, (uint32_t)(i / X3_CHUNK_KB - 1) & 1u);
-        tc_fence_after();
-        const float comp = X3_TRUNC_LOSS_PER_MMA * (float)(X3_CHUNK_KB * (BK / UMMA_K));
-#pragma unroll
-        for (int cc = 0; cc < NCH; ++cc) {
-          uint32_t v[32];
-          tmem_ld32(t_main + (uint32_t)(cc * 32), v);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) acc[cc * 32 + j] += fmaf(__uint_as_float(v[j]), comp, __uint_as_float(v[j]));
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) { if (p.pair_flags & 2) mbar_arrive_cluster_relaxed(chunk_empty_remote); else mbar_arrive_cluster(chunk_empty_remote); }
-      }
-    }
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
-    if (dbg && threadIdx.x == 64) dbg[4] = clock64();
-    const float comp_last = X3_TRUNC_LOSS_PER_MMA * (float)((((num_kb - 1) % X3_CHUNK_KB) + 1) * (BK / UMMA_K));
-#pragma unroll
-    for (int cc = 0; cc < NCH; ++cc) {
-      uint32_t v[32];
-      tmem_ld32(t_main + (uint32_t)(cc * 32), v);
-#pragma unroll
-      for (int j = 0; j < 32; ++j) acc[cc * 32 + j] += fmaf(__uint_as_float(v[j]), comp_last, __uint_as_float(v[j]));
-      tmem_ld32(t_main + (uint32_t)(BN + cc * 32), v);
-#pragma unroll
-      for (int j = 0; j < 32; ++j) acc[cc * 32 + j] += __uint_as_float(v[j]);
-    }
-    // ---- epilogue: this warp's 32 x 128 accumulators -> 16 KB staging tile -> full-row stores (store_staged)
-    float* Cz = p.C + (size_t)blockIdx.z * p.slab_stride;
-    const bool vec = epilogue_vec_ok(p, Cz);
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    float4* stg = reinterpret_cast<float4*>(base_ptr + (32 * CPW * 4) * (warp - 2));
-    const int row = m0 + 32 * q + lane;
-    const int cw0 = n0 + half * CPW;                 // first column of this warp
-    if (cw0 < p.N) {
-      if (vec) {
-#pragma unroll
-        for (int sl = 0; sl < CPW / 4; ++sl) stage_put<CPW>(stg, lane, sl, acc[4 * sl], acc[4 * sl + 1], acc[4 * sl + 2], acc[4 * sl + 3]);
-        __syncwarp();
-        store_staged<CPW>(p, Cz, stg, lane, m0 + 32 * q, cw0);
-      } else if (row < p.M) {
-#pragma unroll
-        for (int cc = 0; cc < NCH; ++cc) store_row_scalar(p, Cz, row, cw0 + cc * 32, acc + cc * 32);
-      }
-    }
-  }
-  if (dbg && threadIdx.x == 64) dbg[5] = clock64();
-  tc_fence_before();
-  cluster_sync_all();
-  if (dbg && threadIdx.x == 32) dbg[6] = clock64();
-  if (warp == 1) {
-    tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS) : "memory");
-  }
-}
-
-static int launch_x3_pair(cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, int M, int N, int split) {
-  static bool configured = false;
-  if (!configured) {
-    if (cudaFuncSetAttribute(gemm_tc_x3_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2::SMEM_BYTES) != cudaSuccess) {
-      addk_set_error("gemm_tc: cannot raise the dynamic shared memory limit");
-      return ADDK_ERR_LAUNCH;
-    }
-    configured = true;
-  }
-  dim3 grid(2 * ((N + Cfg2::BN - 1) / Cfg2::BN), (M + 2 * BM - 1) / (2 * BM), split);
-  gemm_tc_x3_pair_kernel<<<grid, X3_THREADS, Cfg2::SMEM_BYTES, st>>>(ta, tb, p);
-  return ADDK_OK;
-}
 
 // ---------------------------------------------------------------------------------------------------------------
 // bf16 kernel (precision "bf16", BASELINE config 4): bf16 operands in HBM (the producers write a bf16 twin of every
@@ -2167,28 +1350,15 @@ static int h3_convert(cudaStream_t st, const float* x, long long rows, int cols,
   return ADDK_OK;
 }
 
-template <int BN, bool X3>
-static int launch(cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, dim3 grid) {
-  using C = Cfg<BN, X3>;
-  static bool configured = false;
-  if (!configured) {
-    if (cudaFuncSetAttribute(gemm_tc_kernel<BN, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES) != cudaSuccess) {
-      addk_set_error("gemm_tc: cannot raise the dynamic shared memory limit");
-      return ADDK_ERR_LAUNCH;
-    }
-    configured = true;
-  }
-  gemm_tc_kernel<BN, X3><<<grid, NTHREADS, C::SMEM_BYTES, st>>>(ta, tb, p);
-  return ADDK_OK;
-}
+#ifdef ADDK_LEGACY_KERNELS
+#include "gemm_tc_legacy.cuh"
+#endif
 
 }  // namespace addk_tc
 
-static bool addk_tc_pair_enabled() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("ADDK_TC_PAIR"); v = (e && e[0] == '0') ? 0 : 1; }
-  return v == 1;
-}
+// ids reported by addk_debug_last_gemm_kernel(): which kernel a call was dispatched to
+enum { ADDK_K_SGEMM = 0, ADDK_K_TF32 = 10, ADDK_K_TF32X3 = 11, ADDK_K_TF32X3_PAIR = 12, ADDK_K_BF16_TILE = 20,
+       ADDK_K_BF16_PERSISTENT = 21, ADDK_K_H3_TILE = 30, ADDK_K_H3_PERSISTENT = 31 };
 
 // precision: 1 = tf32x3, 2 = tf32.  Shapes the tensor-core tiles do not cover (heads with 1 or 29 outputs,
 // contraction shorter than one k-block, misaligned leading dimensions, fused input normalisation) run on the
@@ -2215,8 +1385,7 @@ static int gemm_bf16(cudaStream_t st, const addk_gemm_args& a) {
   p.a_mn = a.trans_a ? 1 : 0;
   p.b_mn = a.trans_b ? 0 : 1;
   const int BN = a.N > 128 ? 256 : (a.N > 64 ? 128 : 64);
-  static int persistent = -1;
-  if (persistent < 0) { const char* e = getenv("ADDK_BF16_PERSISTENT"); persistent = e ? atoi(e) : 1; }
+  const int persistent = addk_switches().bf16_persistent;
   if (BN == 256 && persistent && a.C && split == 1) {     // (split-K weight gradients: the one-tile-per-CTA kernel is faster, 54 vs 62 us)
     // the persistent kernel of the f16x3 mode with one plane per operand: 32-k blocks, 6 stages, the accumulator of a
     // whole tile is one chunk (no precision drains), the epilogue of a tile overlaps the next tile's MMAs
@@ -2229,7 +1398,7 @@ static int gemm_bf16(cudaStream_t st, const addk_gemm_args& a) {
       CUtensorMap tah, tbh;
       bool okp = p.a_mn ? make_map_f16(&tah, a.A16, a.M, a.K, a.lda, 64, 32, true) : make_map_f16(&tah, a.A16, a.K, a.M, a.lda, 32, BM, true);
       okp = okp && (p.b_mn ? make_map_f16(&tbh, a.B16, a.N, a.K, a.ldb, 64, 32, true) : make_map_f16(&tbh, a.B16, a.K, a.N, a.ldb, 32, 256, true));
-      if (okp) return launch_h3p<256, true>(st, tah, tah, tbh, tbh, pp, a.M, a.N, split);
+      if (okp) { g_addk_last_gemm_kernel = ADDK_K_BF16_PERSISTENT; return launch_h3p<256, true>(st, tah, tah, tbh, tbh, pp, a.M, a.N, split); }
     }
   }
   CUtensorMap ta, tb;
@@ -2237,6 +1406,7 @@ static int gemm_bf16(cudaStream_t st, const addk_gemm_args& a) {
   ok = ok && (p.b_mn ? make_map_bf16(&tb, a.B16, a.N, a.K, a.ldb, 64) : make_map_bf16(&tb, a.B16, a.K, a.N, a.ldb, BN));
   if (!ok) return -1;
   dim3 grid((a.N + BN - 1) / BN, (a.M + BM - 1) / BM, split);
+  g_addk_last_gemm_kernel = ADDK_K_BF16_TILE;
   if (BN == 256) return launch_bf16<256>(st, ta, tb, p, grid);
   if (BN == 128) return launch_bf16<128>(st, ta, tb, p, grid);
   return launch_bf16<64>(st, ta, tb, p, grid);
@@ -2276,11 +1446,7 @@ extern "C" int addk_f16x3_repair(void* stream, const float* x, long long rows, i
   return ADDK_OK;
 }
 
-static float addk_h3_comp() {
-  static float v = -1.f;
-  if (v < 0.f) { const char* e = getenv("ADDK_H3_COMP"); v = e ? (float)atof(e) : addk_tc::X3_TRUNC_LOSS_PER_MMA; }
-  return v;
-}
+static float addk_h3_comp() { return addk_switches().h3_comp; }
 
 // precision "f16x3": can this shape run on the fp16 planes (given 16-byte aligned twins)?  Shared with csrc/mlp.cu, whose
 // twin bookkeeping must know whether a call is going to convert its operands.
@@ -2309,8 +1475,8 @@ static int gemm_h3(cudaStream_t st, const addk_gemm_args& a) {
   p.C = a.C; p.ldc = a.ldc; p.M = a.M; p.N = a.N; p.K = a.K; p.bias = a.bias; p.mask = a.relu_mask_src;
   p.ld_mask = a.ld_mask; p.relu = a.relu; p.accumulate = a.accumulate; p.kb_per_split = kb_per;
   p.slab_stride = a.slab_stride > 0 ? a.slab_stride : (long long)a.M * a.ldc;
-  { const char* e = getenv("ADDK_H3_FLAGS"); p.pair_flags = e ? atoi(e) : 0; }
-  { const char* e = getenv("ADDK_TC_DBG"); p.dbg = e ? (long long*)strtoull(e, nullptr, 0) : nullptr; } p.C16 = nullptr; p.c_amax = split == 1 ? a.c_amax : nullptr;
+  p.pair_flags = addk_switches().h3_flags;
+  p.dbg = g_addk_stamps; p.C16 = nullptr; p.c_amax = split == 1 ? a.c_amax : nullptr;
   p.c_hi = nullptr; p.c_plane = 0; p.c_scale = 1.f; p.c16_in_staged = 0;
   p.a_mn = a.trans_a ? 1 : 0;
   p.b_mn = a.trans_b ? 0 : 1;
@@ -2331,36 +1497,41 @@ static int gemm_h3(cudaStream_t st, const addk_gemm_args& a) {
                      : (make_map_f16(&tbh, Bh, a.K, a.N, a.ldb, BKh, BN) && make_map_f16(&tbl, Bl, a.K, a.N, a.ldb, BKh, BN)));
   if (!ok) { addk_set_error("gemm f16x3: cuTensorMapEncodeTiled rejected an operand"); return ADDK_ERR_ARG; }
   dim3 grid((a.N + BN - 1) / BN, (a.M + BM - 1) / BM, split);
-  static int persistent = -1;
-  if (persistent < 0) { const char* e = getenv("ADDK_H3_PERSISTENT"); persistent = e ? atoi(e) : 1; }
+  const int persistent = addk_switches().h3_persistent;
   if (BN == 256 && (persistent || want_planes)) {
     ParamsP pp;
     pp.p = p; pp.a_amax = a.a_amax; pp.b_amax = a.b_amax; pp.comp_per_mma = ph.comp_per_mma; pp.bf16 = 0;
     if (a.C16 && a.c_amax && split == 1 && a.c16_plane > 0 && (a.ldc & 7) == 0 && (reinterpret_cast<uintptr_t>(a.C16) & 15) == 0) {
       pp.p.c_hi = reinterpret_cast<uint16_t*>(a.C16); pp.p.c_plane = a.c16_plane;
     }
-    { static int ck = 0; if (!ck) { const char* e = getenv("ADDK_H3_CHUNK_KB"); ck = e ? atoi(e) : H3P_CHUNK_KB; if (ck < 1) ck = 1; } pp.chunk_kb = ck; }
+    pp.chunk_kb = addk_switches().h3_chunk_kb;
+    g_addk_last_gemm_kernel = ADDK_K_H3_PERSISTENT;
     return launch_h3p<256>(st, tah, tal, tbh, tbl, pp, a.M, a.N, split);
   }
+  g_addk_last_gemm_kernel = ADDK_K_H3_TILE;
   if (BN == 256) return launch_h3<256>(st, tah, tal, tbh, tbl, ph, grid);
   if (BN == 128) return launch_h3<128>(st, tah, tal, tbh, tbl, ph, grid);
   return launch_h3<64>(st, tah, tal, tbh, tbl, ph, grid);
 }
 
+// Without the legacy tf32x3 kernels (default build) a call the fp16 / bf16 tiles cannot take runs on the exact-fp32
+// CUDA-core kernel, which is at least as accurate.
+static int gemm_fallback(cudaStream_t st, const addk_gemm_args& a);
+
 int addk_gemm_tc(cudaStream_t st, const addk_gemm_args& a, int precision) {
   if (precision == 4) {
     // fp16 hi/lo planes when the call carries twins that TMA can address (16-byte row pitch = 8 elements, 16-byte
-    // aligned planes); otherwise tf32x3 on the fp32 operands
+    // aligned planes); otherwise the fallback on the fp32 operands
     const bool ok16 = a.A16 && a.B16 && a.a_amax && a.b_amax &&
                       ((reinterpret_cast<uintptr_t>(a.A16) & 15) == 0) && ((reinterpret_cast<uintptr_t>(a.B16) & 15) == 0) &&
                       ((a.a16_plane & 7) == 0) && ((a.b16_plane & 7) == 0) && a.a16_plane > 0 && a.b16_plane > 0 &&
                       addk_gemm_h3_usable(a);
     if (ok16) return gemm_h3(st, a);
-    return addk_gemm_tc(st, a, 1);
+    return gemm_fallback(st, a);
   }
   if (precision == 3) {
     // bf16 tensor-core tiles when the call carries bf16 twins that TMA can address (16-byte row pitch = 8 elements);
-    // otherwise tf32x3 on the fp32 operands, followed by the bf16 copy of the output the caller asked for
+    // otherwise the fallback on the fp32 operands, followed by the bf16 copy of the output the caller asked for
     const bool ok16 = a.A16 && a.B16 && ((a.lda & 7) == 0) && ((a.ldb & 7) == 0) && ((reinterpret_cast<uintptr_t>(a.A16) & 15) == 0) &&
                       ((reinterpret_cast<uintptr_t>(a.B16) & 15) == 0) && !a.a_mean && !a.accumulate && a.M >= 16 && a.N >= 16 &&
                       a.K >= 16 && (a.split_k <= 1 || !(a.bias || a.relu || a.relu_mask_src)) && addk_tc::resolve_encode();
@@ -2369,7 +1540,7 @@ int addk_gemm_tc(cudaStream_t st, const addk_gemm_args& a, int precision) {
       if (rc >= 0) return rc;
     }
     if (!a.C) { addk_set_error("gemm: bf16 call without an fp32 output cannot fall back"); return ADDK_ERR_ARG; }
-    const int rc = addk_gemm_tc(st, a, 1);
+    const int rc = gemm_fallback(st, a);
     if (rc != ADDK_OK) return rc;
     if (a.C16 && a.split_k <= 1) {
       const long long n = (long long)a.M * a.N;
@@ -2377,6 +1548,12 @@ int addk_gemm_tc(cudaStream_t st, const addk_gemm_args& a, int precision) {
     }
     return ADDK_OK;
   }
+#ifndef ADDK_LEGACY_KERNELS
+  addk_set_error(precision == 1 || precision == 2
+                     ? "gemm: precision tf32x3 / tf32 needs a library built with make LEGACY=1 (superseded by f16x3 / bf16)"
+                     : "gemm: unknown precision mode");
+  return ADDK_ERR_UNSUPPORTED;
+#else
   using namespace addk_tc;
   if (precision != 1 && precision != 2) {
     addk_set_error("gemm: unknown precision mode");
@@ -2384,6 +1561,7 @@ int addk_gemm_tc(cudaStream_t st, const addk_gemm_args& a, int precision) {
   }
   const bool aligned = ((a.lda & 3) == 0) && ((a.ldb & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.A) & 15) == 0) &&
                        ((reinterpret_cast<uintptr_t>(a.B) & 15) == 0);
+  g_addk_last_gemm_kernel = ADDK_K_SGEMM;
   if (!aligned || a.a_mean || a.M < 16 || a.N < 16 || a.K < 16 || !resolve_encode()) return addk::sgemm_launch(st, a);
   int split = a.split_k > 1 ? a.split_k : 1;
   if (split > 1 && (a.bias || a.relu || a.relu_mask_src || a.accumulate)) return ADDK_ERR_ARG;
@@ -2397,8 +1575,8 @@ int addk_gemm_tc(cudaStream_t st, const addk_gemm_args& a, int precision) {
   p.C = a.C; p.ldc = a.ldc; p.M = a.M; p.N = a.N; p.K = a.K; p.bias = a.bias; p.mask = a.relu_mask_src;
   p.ld_mask = a.ld_mask; p.relu = a.relu; p.accumulate = a.accumulate; p.kb_per_split = kb_per;
   p.slab_stride = a.slab_stride > 0 ? a.slab_stride : (long long)a.M * a.ldc;
-  { const char* e = getenv("ADDK_TC_PAIR_FLAGS"); p.pair_flags = e ? atoi(e) : 2; }
-  { const char* e = getenv("ADDK_TC_DBG"); p.dbg = e ? (long long*)strtoull(e, nullptr, 0) : nullptr; }
+  p.pair_flags = addk_switches().tc_pair_flags;
+  p.dbg = g_addk_stamps;
   p.C16 = nullptr; p.c_amax = nullptr; p.c_hi = nullptr; p.c_plane = 0; p.c_scale = 1.f; p.c16_in_staged = 0;
   p.a_mn = a.trans_a ? 1 : 0;          // A given as [K,M]: rows are the contraction index
   p.b_mn = a.trans_b ? 0 : 1;          // B given as [K,N]
@@ -2408,12 +1586,24 @@ int addk_gemm_tc(cudaStream_t st, const addk_gemm_args& a, int precision) {
   ok = ok && (p.b_mn ? make_map(&tb, a.B, a.N, a.K, a.ldb, 32, BK, true) : make_map(&tb, a.B, a.K, a.N, a.ldb, BK, BN, false));
   if (!ok) return addk::sgemm_launch(st, a);
   dim3 grid((a.N + BN - 1) / BN, (a.M + BM - 1) / BM, split);
-  if (x3 && BN == 256 && a.M > BM && addk_tc_pair_enabled()) {
+  if (x3 && BN == 256 && a.M > BM && addk_switches().tc_pair) {
     // CTA-pair kernel: each CTA of the pair stages 128 rows of B -> its tensor-map box has 128 rows
     if (!p.b_mn && !make_map(&tb, a.B, a.K, a.N, a.ldb, BK, Cfg2::BN / 2, false)) return addk::sgemm_launch(st, a);
+    g_addk_last_gemm_kernel = ADDK_K_TF32X3_PAIR;
     return launch_x3_pair(st, ta, tb, p, a.M, a.N, split);
   }
+  g_addk_last_gemm_kernel = x3 ? ADDK_K_TF32X3 : ADDK_K_TF32;
   if (BN == 256) return x3 ? launch_x3<256>(st, ta, tb, p, grid) : launch<256, false>(st, ta, tb, p, grid);
   if (BN == 128) return x3 ? launch_x3<128>(st, ta, tb, p, grid) : launch<128, false>(st, ta, tb, p, grid);
   return x3 ? launch_x3<64>(st, ta, tb, p, grid) : launch<64, false>(st, ta, tb, p, grid);
+#endif
+}
+
+static int gemm_fallback(cudaStream_t st, const addk_gemm_args& a) {
+#ifdef ADDK_LEGACY_KERNELS
+  return addk_gemm_tc(st, a, 1);
+#else
+  g_addk_last_gemm_kernel = ADDK_K_SGEMM;
+  return addk::sgemm_launch(st, a);
+#endif
 }

@@ -22,6 +22,7 @@
 #include "common.cuh"
 #include "addk.h"
 #include <stdlib.h>
+#include "switches.h"
 
 struct addk_update_ctx {
 #define ADDK_PTR(n) void* n;
@@ -703,9 +704,7 @@ static int h3_prepare(const addk_update_ctx& c, cudaStream_t st, const float* p,
 static uint32_t* amax_hook(cudaStream_t st, const void* p, long long rows, int cols, int ld) {
   const addk_update_ctx* c = g_twin_ctx;
   if (!c || c->precision != 4 || !c->amax_slots || !p || g_next_slot >= TWIN_SLOTS) return nullptr;
-  static int on = -1;                                   // ADDK_H3_AMAX_HOOKS=0: A/B switch (separate max passes)
-  if (on < 0) { const char* ev = getenv("ADDK_H3_AMAX_HOOKS"); on = ev ? atoi(ev) : 1; }
-  if (!on) return nullptr;
+  if (!addk_switches().h3_amax_hooks) return nullptr;   // ADDK_H3_AMAX_HOOKS=0: A/B switch (separate max passes)
   const float* f = (const float*)p;
   const float* a0 = (const float*)c->arena;
   if (!a0 || f < a0 || f >= a0 + c->arena_elems) return nullptr;
@@ -796,8 +795,7 @@ static int gemm(cudaStream_t st, int prec, const float* A, int lda, int ta, cons
           // Letting the epilogue write C's planes too (sticky scale word, prep -> layer -> repair) is implemented and
           // tested but off: measured at 4096 envs it removes 0.18 ms of split passes per optimizer step and adds 0.25 ms
           // to the dense layers (the epilogue's 8-byte stores are far from the split kernel's 6 TB/s).
-          static int fused = -1;
-          if (fused < 0) { const char* ev = getenv("ADDK_H3_FUSED_PLANES"); fused = ev ? atoi(ev) : 0; }
+          const int fused = addk_switches().h3_fused_planes;
           bool ready = false;
           if (!fused && g_next_slot < TWIN_SLOTS) { g_tw[e].slot = g_next_slot++; ready = true; }     // zeroed by h3_params
           else { g_tw[e].slot = e; }
@@ -836,8 +834,7 @@ static int wgrad(cudaStream_t st, const Ctx& c, const ChainWs& ws, const float* 
     TRY(colsum(st, c, ws, X, ldx, rows, k_in, F(c.slabs) + (size_t)slab0 * P + o_w, dY));
   } else {
     // f16x3: if this call is the one that converts dY, its split pass also leaves the column sums of dY (the bias gradient)
-    static int fuse = -1;                                 // ADDK_H3_COLPART=0: A/B switch (separate column-sum kernels)
-    if (fuse < 0) { const char* ev = getenv("ADDK_H3_COLPART"); fuse = ev ? atoi(ev) : 1; }
+    const int fuse = addk_switches().h3_colpart;          // ADDK_H3_COLPART=0: A/B switch (separate column-sum kernels)
     g_colpart_rows = 0;
     g_colpart_for = (o_b >= 0 && fuse) ? dY : nullptr;
     g_colpart_buf = (o_b >= 0 && fuse) ? ws.colpart : nullptr;

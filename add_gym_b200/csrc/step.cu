@@ -17,6 +17,7 @@
 // HBM-bound: ~2.0 KB read + ~3.6 KB written per env-step.
 #include "common.cuh"
 #include "addk.h"
+#include "switches.h"
 
 namespace addk {
 
@@ -792,15 +793,40 @@ __global__ void sample_clip_kernel(const float* __restrict__ weights, int C, con
   if (e >= n) return;
   if (done && done[e] == 0) return;
   // inverse CDF over the (normalised) clip weights -- torch.multinomial with replacement (motion_lib.py:35-39)
+  // (the fp32 running sum can end below 1: the fallback is the last clip with a positive weight, never a
+  // zero-weight clip -- torch.multinomial cannot draw those either)
   float u0 = u[3 * (size_t)e], cum = 0.f;
-  int c = C - 1;
-  for (int k = 0; k < C; ++k) { cum = add_rn(cum, weights[k]); if (u0 < cum) { c = k; break; } }
+  int c = -1, last_pos = 0;
+  for (int k = 0; k < C; ++k) {
+    const float w = weights[k];
+    if (w > 0.f) last_pos = k;
+    cum = add_rn(cum, w);
+    if (u0 < cum && w > 0.f) { c = k; break; }
+  }
+  if (c < 0) c = last_pos;
   ids_out[e] = c;
   if (temp_bits) {  // temperature None: max error over the clips drawn in this batch (sampler.py:66-69)
     float m = 0.f;
     for (int s = 0; s < S; ++s) m = fmaxf(m, errors[c * S + s]);
     atomicMax(temp_bits, __float_as_uint(m));
   }
+}
+
+// AdaptiveSegmentSampler.sample_start_frame after the draws (sampler.py:86-92): seg * size + U * size, (t // dt) * dt,
+// clamp(min = min_start) -- every product and sum rounded to fp32 on its own, like the reference's tensor ops.
+__device__ __forceinline__ float start_time_of(int seg, float u2, float sz, float dt, float min_start) {
+  float tm = add_rn(mul_rn((float)seg, sz), mul_rn(u2, sz));
+  tm = mul_rn(floor_div(tm, dt), dt);
+  return fmaxf(tm, min_start);
+}
+
+// the same arithmetic from GIVEN (segment, U) draws: what a host that keeps torch.multinomial / torch.rand calls
+__global__ void start_time_from_draws_kernel(const float* __restrict__ seg_sizes, float dt, float min_start,
+                                             const long long* __restrict__ clip_ids, const long long* __restrict__ segs,
+                                             const float* __restrict__ u, int n, float* __restrict__ times_out) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  times_out[e] = start_time_of((int)segs[e], u[e], seg_sizes[clip_ids[e]], dt, min_start);
 }
 
 __global__ void sample_time_kernel(const float* __restrict__ errors, int S, const float* __restrict__ seg_sizes,
@@ -821,10 +847,7 @@ __global__ void sample_time_kernel(const float* __restrict__ errors, int S, cons
   float u1 = u[3 * (size_t)e + 1], cum = 0.f;
   int seg = S - 1;
   for (int s = 0; s < S; ++s) { cum = add_rn(cum, expf(sub_rn(er[s] / temp, mx)) / z); if (u1 < cum) { seg = s; break; } }
-  float sz = seg_sizes[c];
-  float tm = add_rn(mul_rn((float)seg, sz), mul_rn(u[3 * (size_t)e + 2], sz));
-  tm = mul_rn(floor_div(tm, dt), dt);
-  times_out[e] = fmaxf(tm, min_start);
+  times_out[e] = start_time_of(seg, u[3 * (size_t)e + 2], seg_sizes[c], dt, min_start);
 }
 
 __global__ void sampler_accum_kernel(const long long* __restrict__ clip_ids, const float* __restrict__ timesteps,
@@ -907,10 +930,11 @@ extern "C" int addk_env_step(void* stream, const addk_task* task, const addk_mot
   }
   if (fast && env->hist_stride == 72) {
     const int fsm = fast::PER_WARP * WPB * (int)sizeof(float);
-    static int cta_tail = -1, min_blocks = 0;             // ADDK_STEP_CTA_TAIL=0: A/B switch (per-warp scalar end)
-    if (cta_tail < 0) {                                   // ADDK_STEP_MIN_BLOCKS=5|6: occupancy experiment (CTA-level end only)
-      const char* ev = getenv("ADDK_STEP_CTA_TAIL"); cta_tail = ev ? atoi(ev) : 1;
-      ev = getenv("ADDK_STEP_MIN_BLOCKS"); min_blocks = ev ? atoi(ev) : 0;
+    const int cta_tail = addk_switches().step_cta_tail;       // ADDK_STEP_CTA_TAIL=0: A/B switch (per-warp scalar end)
+    const int min_blocks = addk_switches().step_min_blocks;   // ADDK_STEP_MIN_BLOCKS=5|6: occupancy experiment (CTA-level end only)
+    static bool carveout_set = false;
+    if (!carveout_set) {
+      carveout_set = true;
       if (min_blocks == 5) cudaFuncSetAttribute(env_step_fast_kernel<true, 5>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
       if (min_blocks == 6) cudaFuncSetAttribute(env_step_fast_kernel<true, 6>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     }
@@ -968,6 +992,16 @@ extern "C" int addk_sample_start_time(void* stream, const float* errors, int num
   sample_time_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(errors, num_segments, seg_sizes, dt,
                                                                         min_start_time, temperature, 1, nullptr, uniforms,
                                                                         n, nullptr, clip_ids, times_out);
+  ADDK_CHECK_LAUNCH();
+  return ADDK_OK;
+}
+
+extern "C" int addk_start_time_from_draws(void* stream, const float* seg_sizes, float dt, float min_start_time,
+                                          const long long* clip_ids, const long long* segments, const float* uniforms,
+                                          int n, float* times_out) {
+  if (!seg_sizes || !clip_ids || !segments || !uniforms || !times_out || n <= 0) return ADDK_ERR_ARG;
+  start_time_from_draws_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(seg_sizes, dt, min_start_time, clip_ids,
+                                                                                  segments, uniforms, n, times_out);
   ADDK_CHECK_LAUNCH();
   return ADDK_OK;
 }

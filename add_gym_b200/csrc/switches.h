@@ -1,0 +1,19 @@
+// Experiment / A-B switches of libaddk.so, read from the environment ONCE (first use) -- never on a launch path.
+// Defaults are the shipped configuration; every switch is documented where it is consumed.
+#pragma once
+
+struct AddkSwitches {
+  int tc_pair;            // ADDK_TC_PAIR         (legacy tf32x3) CTA-pair kernel on / off                      default 1
+  int tc_pair_flags;      // ADDK_TC_PAIR_FLAGS   (legacy tf32x3) bit0 cluster-scope waits, bit1 relaxed arrives default 2
+  int h3_flags;           // ADDK_H3_FLAGS        f16x3 persistent kernel experiments: bit0 no stores, bit1 no drains   0
+  int h3_persistent;      // ADDK_H3_PERSISTENT   persistent f16x3 kernel for 256-wide layers                    default 1
+  int h3_chunk_kb;        // ADDK_H3_CHUNK_KB     k-blocks per accumulator drain                                 default 8
+  float h3_comp;          // ADDK_H3_COMP         expected accumulator truncation loss per MMA                   1.7e-8
+  int bf16_persistent;    // ADDK_BF16_PERSISTENT persistent one-plane kernel in bf16 mode                       default 1
+  int h3_amax_hooks;      // ADDK_H3_AMAX_HOOKS   elementwise producers leave max|x| behind                      default 1
+  int h3_fused_planes;    // ADDK_H3_FUSED_PLANES dense-layer epilogue writes the fp16 planes of its output      default 0
+  int h3_colpart;         // ADDK_H3_COLPART      split pass leaves bias-gradient column sums behind             default 1
+  int step_cta_tail;      // ADDK_STEP_CTA_TAIL   reward / done tail of the step kernel run per CTA              default 1
+  int step_min_blocks;    // ADDK_STEP_MIN_BLOCKS occupancy experiment of the step kernel (0 | 5 | 6)            default 0
+};
+const AddkSwitches& addk_switches();

@@ -16,8 +16,6 @@ import os
 
 import numpy as np
 import torch
-import yaml
-
 from . import _lib, motion_io
 
 ROW_STRIDE_ALIGN = 4
@@ -39,21 +37,8 @@ class MotionLib:
 
     # ---- loading ----------------------------------------------------------------------------------------
     def _fetch_motion_files(self, motion_file):
-        if os.path.splitext(motion_file)[1] == ".yaml":
-            with open(motion_file, "r") as f:
-                cfg = yaml.load(f, Loader=yaml.SafeLoader)
-            files, weights = [], []
-            base = os.path.dirname(os.path.abspath(motion_file))
-            for entry in cfg["motions"]:
-                w = entry["weight"]
-                assert w >= 0
-                path = entry["file"]
-                if not os.path.isabs(path) and not os.path.exists(path):
-                    path = os.path.join(base, path)
-                files.append(path)
-                weights.append(w)
-            return files, weights
-        return [motion_file], [1.0]
+        """YAML library (motion_lib.py:337-358), clip pack (all clips, weight 1.0) or a single clip."""
+        return motion_io.fetch_motion_files(motion_file)
 
     def _load_baked(self, path):
         """A pre-baked step table (`save_table`): upload and go -- no text parse, no resampling kernels."""

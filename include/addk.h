@@ -28,6 +28,14 @@ const char* addk_last_error(void);
 int addk_version(void);
 /* number of kernel launches issued through this library since the last reset (bench.py "gpu_launches") */
 long long addk_launch_count(int reset);
+/* bit 0: built with the superseded tf32 / tf32x3 kernels (make LEGACY=1; precision modes 1 and 2 need it) */
+int addk_build_flags(void);
+/* test / profiling hooks: id of the kernel the last addk_gemm call was dispatched to (0 CUDA-core fp32, 10 tf32,
+ * 11 tf32x3, 12 tf32x3 CTA pair, 20 bf16 one tile per CTA, 21 bf16 persistent, 30 f16x3 one tile per CTA,
+ * 31 f16x3 persistent); a device buffer of 16 int64 that CTA 0 of the persistent kernels fills with clock stamps
+ * (NULL switches the stamps off, the default) */
+int addk_debug_last_gemm_kernel(void);
+int addk_debug_set_stamp_buffer(long long* device_buffer16);
 
 /* ---------------------------------------------------------------------------------------------
  * Task description shared by the per-step kernels.  Plain data, filled once by the host from the
@@ -146,6 +154,12 @@ int addk_sample_motion_time(void* stream, const float* motion_weights, int num_m
 int addk_sample_start_time(void* stream, const float* errors, int num_segments, const float* seg_sizes, float dt,
                            float min_start_time, float temperature, const float* uniforms, int n,
                            const long long* clip_ids, float* times_out);
+/* The arithmetic of AdaptiveSegmentSampler.sample_start_frame after its two draws (sampler.py:84-92):
+ * t = seg * size[clip] + U * size[clip]; (t // dt) * dt; clamp(min = min_start_time) -- for callers that keep the
+ * reference's torch.multinomial / torch.rand draws (bit-exact start times on identical draws). */
+int addk_start_time_from_draws(void* stream, const float* seg_sizes, float dt, float min_start_time,
+                               const long long* clip_ids, const long long* segments, const float* uniforms, int n,
+                               float* times_out);
 /* AdaptiveSegmentSampler.update_errors (sampler.py:20-55). sums/counts are [C*S] work buffers.
  * disc_obs_demo == NULL: disc_obs is a ready [n] vector of tracking errors. */
 int addk_sampler_update_errors(void* stream, const long long* clip_ids, const float* timesteps,

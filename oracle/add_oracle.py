@@ -359,12 +359,19 @@ class TorchRandom:
 # ==================================================================================================
 # the agent: one rollout + ADD/PPO update                    learning/{base,ppo,amp}_agent.py, add/add_agent.py
 # ==================================================================================================
-def mlp_forward(x, layers):
-    """layers: list of (W, b, relu)"""
+def mlp_forward(x, layers, masks=None, rec=None):
+    """layers: list of (W, b, relu).  Test hooks for the ReLU-boundary measurement (tests/test_gpu_parity.py):
+    `rec` (a list) receives the boolean mask `pre-activation > 0` of every ReLU layer; `masks` (a list of boolean
+    tensors, one per ReLU layer) replaces relu(z) by z * mask -- the same function wherever the mask agrees with
+    z > 0, zero second derivative like ReLU, so autograd's double backward is unchanged."""
+    k = 0
     for W, b, relu in layers:
         x = torch.nn.functional.linear(x, W, b)
         if relu:
-            x = torch.relu(x)
+            if rec is not None:
+                rec.append((x > 0).detach())
+            x = torch.relu(x) if masks is None else x * masks[k].to(x.dtype)
+            k += 1
     return x
 
 
@@ -490,23 +497,24 @@ class OracleAgent:
         self.ep_sum, self.len_sum, self.episodes = 0.0, 0.0, 0
         self.sample_count = 0
         self.trace = {"reset_ids": [], "reset_times": [], "reset_envs": []}
+        self.record_masks, self.last_masks = False, None          # test hook: ReLU masks of the last optimizer step
 
     # ---- nets ------------------------------------------------------------------------------------------------
     def _trunk(self, prefix, n):
         return [(self.params["%s.%d.weight" % (prefix, 2 * i)], self.params["%s.%d.bias" % (prefix, 2 * i)], True)
                 for i in range(n)]
 
-    def actor_mean(self, x):
-        h = mlp_forward(x, self._trunk("_actor_layers", 3))
+    def actor_mean(self, x, masks=None, rec=None):
+        h = mlp_forward(x, self._trunk("_actor_layers", 3), masks, rec)
         return torch.nn.functional.linear(h, self.params["_action_dist._mean_net.weight"],
                                           self.params["_action_dist._mean_net.bias"])
 
-    def critic(self, x):
-        h = mlp_forward(x, self._trunk("_critic_layers", 3))
+    def critic(self, x, masks=None, rec=None):
+        h = mlp_forward(x, self._trunk("_critic_layers", 3), masks, rec)
         return torch.nn.functional.linear(h, self.params["_critic_out.weight"], self.params["_critic_out.bias"])
 
-    def disc(self, x):
-        h = mlp_forward(x, self._trunk("_disc_layers", 2))
+    def disc(self, x, masks=None, rec=None):
+        h = mlp_forward(x, self._trunk("_disc_layers", 2), masks, rec)
         return torch.nn.functional.linear(h, self.params["_disc_logits.weight"], self.params["_disc_logits.bias"])
 
     def logp(self, x, mean):                                                # distribution_gaussian_diag.py:90-94
@@ -725,17 +733,23 @@ class OracleAgent:
             self.perm_head = rem
         return torch.remainder(idx, min(self.total_samples, L))
 
-    def loss(self, idx):
+    def loss(self, idx, masks=None, rec=None):
         """AMPAgent._compute_loss with ADD's discriminator loss (amp_agent.py:98-114; ppo_agent.py:194-261;
-        base_agent.py:522-546; add_agent.py:141-202)."""
+        base_agent.py:522-546; add_agent.py:141-202).
+
+        Test hooks (see mlp_forward): `rec` (a dict) receives the ReLU masks of the five forward passes under the keys
+        "actor", "critic", "disc" (minibatch rows) and "disc_pos" (the zero-difference row); `masks` (same keys) forces
+        them -- used to measure how much of a gradient difference is ReLU boundary flips."""
         a, b = self.acfg, self.buf
+        mk = lambda k: None if masks is None else masks[k]
+        rc = lambda k: None if rec is None else rec.setdefault(k, [])
         flat = lambda k: b[k].view([self.T * self.N] + list(b[k].shape[2:]))[idx]
         norm_obs = self.norm_obs(flat("obs"))
         norm_a = (flat("action") - self.a_mean) / self.a_std
-        pred = self.critic(norm_obs).squeeze(-1)
+        pred = self.critic(norm_obs, mk("critic"), rc("critic")).squeeze(-1)
         critic_loss = torch.mean(torch.square(flat("tar_val") - pred))
         m = flat("rand_action_mask") == 1.0
-        mean = self.actor_mean(norm_obs[m])
+        mean = self.actor_mean(norm_obs[m], mk("actor"), rc("actor"))
         ratio = torch.exp(self.logp(norm_a[m], mean) - flat("a_logp")[m])
         adv = flat("adv")[m]
         clip = a["ppo_clip_ratio"]
@@ -750,9 +764,9 @@ class OracleAgent:
             info["action_bound_loss"] = bound.detach()
         loss = actor_loss + a["critic_loss_weight"] * critic_loss
         # discriminator
-        pos_logit = self.disc(torch.zeros(1, self.disc_dim)).squeeze(-1)
+        pos_logit = self.disc(torch.zeros(1, self.disc_dim), mk("disc_pos"), rc("disc_pos")).squeeze(-1)
         x = self.norm_diff(flat("disc_obs_demo") - flat("disc_obs")).requires_grad_(True)
-        neg_logit = self.disc(x).squeeze(-1)
+        neg_logit = self.disc(x, mk("disc"), rc("disc")).squeeze(-1)
         bce = torch.nn.BCEWithLogitsLoss()
         disc_loss = 0.5 * (bce(pos_logit, torch.ones_like(pos_logit) * .9) + bce(neg_logit, torch.ones_like(neg_logit) * .1))
         wl = torch.flatten(self.params["_disc_logits.weight"])
@@ -796,7 +810,9 @@ class OracleAgent:
                 if max_steps is not None and steps >= max_steps:
                     break
                 idx = self.sample_idx(M)
-                info = self.loss(idx)
+                rec = {} if self.record_masks else None
+                info = self.loss(idx, rec=rec)
+                self.last_masks = rec
                 self.optimizer_step(info["loss"], grad_hook)
                 if on_step is not None:
                     on_step(steps, idx, info, self)

@@ -21,19 +21,7 @@ from oracle import add_oracle  # noqa: E402
 
 
 def load_clips(motion_file):
-    if motion_file.endswith(".yaml"):
-        with open(motion_file, "r") as f:
-            cfg = yaml.safe_load(f)
-        base = os.path.dirname(os.path.abspath(motion_file))
-        files, weights = [], []
-        for e in cfg["motions"]:
-            p = e["file"]
-            if not os.path.isabs(p) and not os.path.exists(p):
-                p = os.path.join(base, p)
-            files.append(p)
-            weights.append(e["weight"])
-    else:
-        files, weights = [motion_file], [1.0]
+    files, weights = motion_io.fetch_motion_files(motion_file)
     clips = []
     for f in files:
         m = motion_io.load_motion(f)

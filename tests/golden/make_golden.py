@@ -20,20 +20,27 @@ REPO = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, REPO)
 from oracle import ref_harness  # noqa: E402
 
+from oracle.make_assets import SEVEN_CLIPS  # noqa: E402
+
+THREE = [("walk1_subject1_trimmed.motion", 1.0, None), ("run2_subject4_trimmed.motion", 0.5, 700),
+         ("fallAndGetUp3_subject1.motion", 0.25, 450)]
 CASES = {
     "walk_n12": dict(num_envs=12, motion_file=None, fall_prob=0.01),
-    "three_clips_n10": dict(num_envs=10, fall_prob=0.01,
-                            motion_file=[("walk1_subject1_trimmed.motion", 1.0, None),
-                                         ("run2_subject4_trimmed.motion", 0.5, 700),
-                                         ("fallAndGetUp3_subject1.motion", 0.25, 450)]),
+    "three_clips_n10": dict(num_envs=10, fall_prob=0.01, motion_file=THREE),
+    # non-default observation switches the reference keeps: local frame (heading-relative), velocity and phase features
+    "local_vel_phase_n9": dict(num_envs=9, fall_prob=0.01, motion_file=THREE,
+                               task_overrides={"global_obs": False, "enable_vel_obs": True, "enable_phase_obs": True}),
+    # seven clips (ids 0..6): the Q2 start-index quirk beyond clip 2, short CLAMP clips that end inside the rollout
+    "seven_clips_n14": dict(num_envs=14, fall_prob=0.01,
+                            motion_file=[(n + ".motion", w, cut) for n, w, cut in SEVEN_CLIPS]),
 }
 BUF_KEYS = ["obs", "next_obs", "action", "reward", "done", "a_logp", "tar_val", "adv", "rand_action_mask", "disc_obs",
             "disc_obs_demo", "motion_ids", "motion_times"]
 
 
-def run_case(name, num_envs, motion_file, fall_prob):
+def run_case(name, num_envs, motion_file, fall_prob, task_overrides=None):
     agent, cfg = ref_harness.make_reference_agent(num_envs, seed=0, engine_seed=1234, motion_file=motion_file,
-                                                  fall_prob=fall_prob)
+                                                  fall_prob=fall_prob, task_overrides=task_overrides)
     out = {}
     ml = agent._add_motion.motion_lib
     S = ml._step_root_pos.shape[0]
@@ -77,5 +84,7 @@ def run_case(name, num_envs, motion_file, fall_prob):
 
 
 if __name__ == "__main__":
+    only = sys.argv[1:]
     for name, kw in CASES.items():
-        run_case(name, **kw)
+        if not only or name in only:
+            run_case(name, **kw)

@@ -10,6 +10,22 @@ from oracle import add_oracle
 class RecordRandom(add_oracle.TorchRandom):
     def __init__(self):
         self.noise, self.masks, self.perms = [], [], []
+        self.clip_draws, self.segment_draws, self.uniform_draws = [], [], []
+
+    def motions(self, weights, n):
+        v = super().motions(weights, n)
+        self.clip_draws.append(v.clone())
+        return v
+
+    def segments(self, probs):
+        v = super().segments(probs)
+        self.segment_draws.append(v.clone())
+        return v
+
+    def uniform(self, n):
+        v = super().uniform(n)
+        self.uniform_draws.append(v.clone())
+        return v
 
     def action_noise(self, n, dim):
         v = super().action_noise(n, dim)

@@ -15,6 +15,7 @@ from add_gym_b200 import config as b200_config
 pytestmark = pytest.mark.gpu
 TOL = 1e-5
 THREE_CLIPS = os.path.join(b200_config.ASSET_DIR, "three_clips.yaml")
+SEVEN_CLIPS = os.path.join(b200_config.ASSET_DIR, "seven_clips.yaml")
 
 
 def _rel(a, b):
@@ -196,6 +197,42 @@ def test_masked_reset_sampling_distribution_and_time_grid():
     assert torch.equal(ids2[sel], ids[sel]) and torch.equal(times2[sel], times[sel])
 
 
+def test_start_time_arithmetic_is_bit_exact_on_the_oracle_draws():
+    """the start-time arithmetic of AdaptiveSegmentSampler.sample_start_frame / ADDMotion.sample_time
+    (sampler.py:75-92, add_motion.py:53-61) -- seg * size + U * size, (t // dt) * dt (c10 floor division on fp32),
+    clamp(min = 0.02) -- fed with the ORACLE's recorded (clip, segment, U) draws must give the oracle's start times bit
+    for bit.  The oracle draws come from the reference's own torch calls (multinomial / rand on the CPU generator)."""
+    from add_gym_b200.add_motion import ADDMotion
+    from add_gym_b200.env import ImitationEnvironment
+    from oracle import harness
+    import parity_helpers as helpers
+    for motion in (None, THREE_CLIPS, SEVEN_CLIPS):
+        cfg = b200_config.default_config(num_envs=4, motion_file=motion)
+        env = ImitationEnvironment(cfg, "cuda:0")
+        gmotion = ADDMotion(cfg["task"], env, "cuda:0")
+        rec = helpers.RecordRandom()
+        oracle = harness.make_oracle_agent(4, seed=3, engine_seed=1234, cfg=b200_config.default_config(num_envs=4, motion_file=motion), rng=rec)
+        assert torch.equal(gmotion.sampler.segment_sizes.cpu(), oracle.seg_sizes), "segment sizes: fp32 len / 20"
+        oracle.errors = torch.rand_like(oracle.errors) * 3.0           # non-uniform segment probabilities
+        torch.manual_seed(11)
+        n0 = len(rec.clip_draws)
+        ids, times = oracle.sample_time(200000)
+        clip, seg, u = rec.clip_draws[n0], rec.segment_draws[n0], rec.uniform_draws[n0]
+        assert torch.equal(clip, ids)
+        got = gmotion.sampler.start_times_from_draws(clip.cuda(), seg.cuda(), u.cuda())
+        assert torch.equal(got.cpu(), times), "start times must be bit-exact on identical draws"
+        # edge draws: U = 0, U just below 1, first / last segment, the clamp at (num_disc_obs_steps - 1) * dt
+        C_ = oracle.seg_sizes.shape[0]
+        e_clip = torch.arange(C_).repeat_interleave(6)
+        e_seg = torch.tensor([0, 0, 19, 19, 7, 0]).repeat(C_)
+        e_u = torch.tensor([0.0, 1.0 - 2.0 ** -24, 0.0, 1.0 - 2.0 ** -24, 0.5, 1e-4]).repeat(C_)
+        sz = oracle.seg_sizes[e_clip]
+        t = e_seg * sz + e_u * sz
+        ref = torch.clamp((t // oracle.dt) * oracle.dt, min=oracle.min_start)
+        got = gmotion.sampler.start_times_from_draws(e_clip.cuda(), e_seg.cuda(), e_u.cuda())
+        assert torch.equal(got.cpu(), ref)
+
+
 def test_sampler_update_errors_matches_oracle():
     from add_gym_b200.add_motion import AdaptiveSegmentSampler
     g = torch.Generator().manual_seed(5)
@@ -242,11 +279,17 @@ def test_full_size_rollout_steps_match_oracle(num_envs):
 
 @pytest.mark.parametrize("tc_mode", ["f16x3", "tf32x3"])
 def test_full_size_update_tensor_core_vs_cuda_core_gradients(tc_mode):
-    """One optimizer step at the full minibatch (16384 rows) computed twice by independent arithmetic: the tcgen05
-    fp32-parity tiles (f16x3: fp16 hi/lo planes; tf32x3) and the exact-fp32 CUDA-core kernel.  Gradients must agree to 1e-5 (median tensor) with a ReLU-flip allowance
-    for the worst one, the loss terms to 1e-5; the same call repeated must reproduce itself bit for bit."""
+    """A SECOND check next to the oracle comparison at full size (test_gpu_parity.py::test_full_size_iteration_parity_*):
+    one optimizer step at the full minibatch (16384 rows) computed twice by independent arithmetic inside the library,
+    the tcgen05 fp32-parity tiles (f16x3: fp16 hi/lo planes; tf32x3 in the legacy build) and the exact-fp32 CUDA-core
+    kernel.  The loss terms must agree to 2e-5; the median gradient tensor to 5e-5 and the worst one to 5e-3: the two
+    runs take different ReLU branches for a few of the 50M pre-activations (1/sqrt(8M active units) = 3.5e-4 per flipped
+    unit and tensor -- the per-flip accounting is done against the oracle, where the masks can be forced equal).  The
+    same call repeated must reproduce itself bit for bit."""
     from add_gym_b200 import _lib
     from add_gym_b200.add_agent import ADDAgent
+    import test_gpu_parity as T
+    T._need_legacy(tc_mode)
 
     def grads(prec):
         cfg = b200_config.default_config(num_envs=4096, mlp_precision=prec)

@@ -15,20 +15,26 @@ BUF_KEYS = ["obs", "next_obs", "action", "reward", "done", "a_logp", "tar_val", 
             "disc_obs_demo", "motion_ids", "motion_times"]
 
 
-def _run(case, num_envs, motion_file):
+def _run(case, num_envs, motion_file, task_overrides=None):
     cfg = b200_config.default_config(num_envs=num_envs, motion_file=motion_file)
+    cfg["task"].update(task_overrides or {})
     agent = harness.make_oracle_agent(num_envs, seed=0, engine_seed=1234, cfg=cfg, fall_prob=0.01)
     g = np.load(os.path.join(GOLD, case + ".npz"))
     return agent, g
 
 
-@pytest.mark.parametrize("case,num_envs,motion", [
-    ("walk_n12", 12, None),
-    ("three_clips_n10", 10, os.path.join(b200_config.ASSET_DIR, "three_clips.yaml")),
+LOCAL = {"global_obs": False, "enable_vel_obs": True, "enable_phase_obs": True}
+
+
+@pytest.mark.parametrize("case,num_envs,motion,overrides", [
+    ("walk_n12", 12, None, None),
+    ("three_clips_n10", 10, os.path.join(b200_config.ASSET_DIR, "three_clips.yaml"), None),
+    ("local_vel_phase_n9", 9, os.path.join(b200_config.ASSET_DIR, "three_clips.yaml"), LOCAL),
+    ("seven_clips_n14", 14, os.path.join(b200_config.ASSET_DIR, "seven_clips.yaml"), None),
 ])
-def test_oracle_reproduces_reference_iteration(case, num_envs, motion):
+def test_oracle_reproduces_reference_iteration(case, num_envs, motion, overrides):
     torch.set_num_threads(max(1, min(8, os.cpu_count() or 1)))
-    agent, g = _run(case, num_envs, motion)
+    agent, g = _run(case, num_envs, motion, overrides)
     lib = agent.lib
     # step table (slerp/lerp resampling) -- sampled rows, shape, column checksums
     assert list(g["table_shape"]) == list(lib.table.shape)
