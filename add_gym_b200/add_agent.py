@@ -72,6 +72,7 @@ class MPOptimizerState:
         self.exp_avg_sq = torch.zeros_like(model.flat)
         self.steps = 0
         self._model = model
+        self.on_hyperparams_changed = None
 
     def get_steps(self):
         return self.steps
@@ -101,6 +102,8 @@ class MPOptimizerState:
         g = sd["param_groups"][0]
         self.lr, self.betas, self.eps = float(g["lr"]), tuple(g["betas"]), float(g["eps"])
         self.weight_decay = float(g["weight_decay"])
+        if self.on_hyperparams_changed is not None:      # the update context bakes these scalars in: rebuild it
+            self.on_hyperparams_changed()
 
 
 INFO_KEYS = ["loss", "critic_loss", "actor_loss", "clip_frac", "imp_ratio", "action_bound_loss", "disc_loss",
@@ -289,9 +292,11 @@ class ADDAgent(torch.nn.Module):
                    critic_loss_weight=self._critic_loss_weight, disc_loss_weight=self._disc_loss_weight,
                    disc_logit_reg=self._disc_logit_reg, disc_grad_penalty=self._disc_grad_penalty,
                    disc_weight_decay=self._disc_weight_decay, lr=opt.lr, beta1=opt.betas[0], beta2=opt.betas[1],
-                   adam_eps=opt.eps, weight_decay=opt.weight_decay, grad_scale=1.0 / self._world)
+                   adam_eps=opt.eps, weight_decay=opt.weight_decay, grad_scale=1.0 / self._world,
+                   grad_clip=opt._grad_clip)
         self._mb_rows = M
         self._ctx = _lib.UpdateCtx(ptrs, ints, f64)
+        opt.on_hyperparams_changed = self._sync_optimizer_scalars
         # rollout scratch
         self._action = z(N, ad)
         self._a_logp = z(N)
@@ -301,6 +306,13 @@ class ADDAgent(torch.nn.Module):
         self._work3 = z(3, dt=torch.float64)
         self._adv_stats = z(2)
         self._disc_r_stats = z(2)
+
+    def _sync_optimizer_scalars(self):
+        """torch.optim.AdamW.load_state_dict overrides the param_group values (mp_optimizer.py:52-53): the scalars baked
+        into the update context follow the optimizer state after a checkpoint load."""
+        opt = self._optimizer
+        self._ctx = self._ctx.rebuild(lr=opt.lr, beta1=opt.betas[0], beta2=opt.betas[1], adam_eps=opt.eps,
+                                      weight_decay=opt.weight_decay, grad_clip=opt._grad_clip)
 
     # ---- small reference API -------------------------------------------------------------------------------------
     def get_num_envs(self):
@@ -571,6 +583,12 @@ class ADDAgent(torch.nn.Module):
                 _lib.check(rc, "addk_update_minibatch")
                 if not local:   # the one exchange step of the path: flat gradient all-reduce over NCCL
                     dist.all_reduce(self._model.flat_grad, op=dist.ReduceOp.SUM)
+                    if opt._grad_clip > 0.0:   # global-norm clip of the rank-averaged gradient (mp_optimizer.py:19-20)
+                        rc = L.addk_clip_grad_norm(_lib.stream(), _lib.ptr(self._model.flat_grad),
+                                                   C.c_longlong(self._model.num_params), C.c_double(opt._grad_clip),
+                                                   C.c_double(1.0 / self._world), _lib.ptr(self._ws["stats"][30:]),
+                                                   _lib.ptr(self._ws["info"][step, 14:]))
+                        _lib.check(rc, "addk_clip_grad_norm")
                     rc = L.addk_adamw(_lib.stream(), _lib.ptr(self._model.flat), _lib.ptr(self._model.flat_grad),
                                       _lib.ptr(opt.exp_avg), _lib.ptr(opt.exp_avg_sq), C.c_longlong(self._model.num_params),
                                       C.c_int(opt.steps + 1), C.c_double(opt.lr), C.c_double(opt.betas[0]),

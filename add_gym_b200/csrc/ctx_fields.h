@@ -128,6 +128,7 @@ ADDK_F64(beta2)
 ADDK_F64(adam_eps)
 ADDK_F64(weight_decay)
 ADDK_F64(grad_scale)    // 1/world_size when gradients were summed across ranks, else 1
+ADDK_F64(grad_clip)     // optimizer.grad_clip (mp_optimizer.py:10): global-norm clip before the step; 0 = off (the reference default, Q4)
 
 #undef ADDK_PTR
 #undef ADDK_INT

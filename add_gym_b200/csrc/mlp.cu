@@ -470,6 +470,23 @@ __global__ void __launch_bounds__(256) colsum_parts_kernel(const float* __restri
   }
 }
 
+// torch.nn.utils.clip_grad_norm_ (mp_optimizer.py:19-20,46-47): total = ||g||_2 over all parameters,
+// g *= min(1, max_norm / (total + 1e-6)).  `pre_scale` = 1/world when g still holds the cross-rank SUM.
+__global__ void clip_coef_kernel(const double* __restrict__ sumsq, float pre_scale, float max_norm, float* __restrict__ coef) {
+  const float total = pre_scale * (float)sqrt(*sumsq);
+  *coef = fminf(max_norm / (total + 1e-6f), 1.0f);
+}
+__global__ void scale_by_coef_kernel(float* __restrict__ g, long long n, const float* __restrict__ coef) {
+  const float c = *coef;
+  const long long n4 = n >> 2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 v = reinterpret_cast<float4*>(g)[i];
+    v.x *= c; v.y *= c; v.z *= c; v.w *= c;
+    reinterpret_cast<float4*>(g)[i] = v;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) g[4 * n4 + threadIdx.x] *= c;
+}
+
 struct Seg { long long begin, end; int nslabs; float l2; };
 struct SegTable { Seg s[24]; int n; long long P; };
 
@@ -947,6 +964,21 @@ static int aux_streams(AuxStreams** out) {
   return ADDK_OK;
 }
 
+extern "C" int addk_clip_grad_norm(void* stream, float* grads, long long n, double max_norm, double pre_scale,
+                                   double* sumsq_work, float* coef_out) {
+  if (!grads || !sumsq_work || !coef_out || n <= 0 || !(max_norm > 0.0)) return ADDK_ERR_ARG;
+  if (reinterpret_cast<uintptr_t>(grads) & 15) { addk_set_error("clip_grad_norm: the flat gradient must be 16-byte aligned"); return ADDK_ERR_ARG; }
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaMemsetAsync(sumsq_work, 0, sizeof(double), st);
+  sumsq_kernel<<<148 * 4, 256, 0, st>>>(grads, n, sumsq_work);
+  ADDK_CHECK_LAUNCH();
+  clip_coef_kernel<<<1, 1, 0, st>>>(sumsq_work, (float)pre_scale, (float)max_norm, coef_out);
+  ADDK_CHECK_LAUNCH();
+  scale_by_coef_kernel<<<148 * 4, 256, 0, st>>>(grads, n, coef_out);
+  ADDK_CHECK_LAUNCH();
+  return ADDK_OK;
+}
+
 extern "C" int addk_update_ctx_size(void) { return (int)sizeof(Ctx); }
 
 extern "C" int addk_update_ctx_init(void* ctx_host, const void* const* ptrs, int n_ptrs, const int64_t* ints,
@@ -1118,9 +1150,12 @@ extern "C" int addk_update_minibatch(void* stream, void* ctx_host, const long lo
                                         (float)c.disc_logit_reg, (float)c.disc_grad_penalty,
                                         (float)c.disc_weight_decay, F(c.info) + (size_t)step_index * 16);
   ADDK_CHECK_LAUNCH();
-  if (do_optim)
+  if (do_optim) {
+    if (c.grad_clip > 0.0)      // the coefficient lands in info[14] of this step (0 = clipping off)
+      TRY(addk_clip_grad_norm(stream, F(c.grads), P, c.grad_clip, c.grad_scale, stats + 30, F(c.info) + (size_t)step_index * 16 + 14));
     TRY(addk_adamw(stream, F(c.params), F(c.grads), F(c.exp_avg), F(c.exp_avg_sq), P, do_optim, c.lr, c.beta1, c.beta2,
                    c.adam_eps, c.weight_decay, c.grad_scale));
+  }
   return ADDK_OK;
 }
 

@@ -264,6 +264,12 @@ int addk_adamw(void* stream, float* param, const float* grad, float* exp_avg, fl
                int step, double lr, double beta1, double beta2, double eps, double weight_decay,
                double grad_scale);
 
+/* MPOptimizer._clip_grads = torch.nn.utils.clip_grad_norm_ (mp_optimizer.py:19-20,46-47) on the flat gradient:
+ * coef = min(1, max_norm / (pre_scale * ||g||_2 + 1e-6)); g *= coef.  pre_scale = 1/world while g holds the cross-rank
+ * sum.  sumsq_work: one double; *coef_out receives the coefficient. */
+int addk_clip_grad_norm(void* stream, float* grads, long long n, double max_norm, double pre_scale,
+                        double* sumsq_work, float* coef_out);
+
 #ifdef __cplusplus
 }
 #endif

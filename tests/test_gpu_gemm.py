@@ -308,7 +308,7 @@ H3P_CASES = [
     ("weight gradient dY^T.X split-K 9", 1024, 1024, MB, 1, 0, "split9"),
     ("weight gradient 512x1024 split-K 9, 16385 rows", 512, 1024, MB + 1, 1, 0, "split9"),
     ("weight gradient first layer N=272 split-K 9", 1024, 272, MB, 1, 0, "split9"),
-    ("A^T.B^T (both operands transposed)", 1024, 512, 4096, 1, 1, None),
+    ("A^T.B^T (both operands transposed)", 8192, 1024, 1024, 1, 1, None),
 ]
 
 
