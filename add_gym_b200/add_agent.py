@@ -154,6 +154,8 @@ class ADDAgent(torch.nn.Module):
         ent = self._env.robot.entity
         self._masked_engine = hasattr(ent, "set_state_masked")
         self.engine_time_events = None   # bench.py installs a list to time scene.step() separately
+        self.stage_events = None         # bench.py installs a list: _train_iter appends 5 events around its 4 stages
+        self._log_pending = None         # deferred logging: (iteration header, pinned host row, event)
         # CUDA graphs for the launch-bound rollout step (two segments around the physics step), see _rollout_train
         self._use_graphs = bool(config.get("cuda_graphs", True))
         self._graphs_pre, self._graphs_post = {}, {}
@@ -608,21 +610,33 @@ class ADDAgent(torch.nn.Module):
         self._disc_obs_norm.update()
 
     def _train_iter(self):
+        """One training iteration (base_agent.py:353-374).  Nothing in here synchronises with the host: every value of the
+        returned dict is a 0-d DEVICE tensor (the reference returns Python floats for the tracker entries and pays
+        `.item()` syncs for them, base_agent.py:603-621).  `stage_events`, when a list, receives five CUDA events around
+        the four stages (bench.py's per-stage timing)."""
+        marks = self.stage_events
+        ev = (lambda: None) if marks is None else (lambda: marks.append(torch.cuda.Event(enable_timing=True)) or marks[-1].record())
         self.set_mode(AgentMode.TRAIN)
+        ev()
         self._rollout_train(self._steps_per_iter)
+        ev()
         data_info = self._build_train_data()
+        ev()
         train_info = self._update_model()
+        ev()
         if self._need_normalizer_update():
             self._update_normalizers()
+        ev()
         info = {**train_info, **data_info}
         info.update(self._tracker_info())
         return info
 
     def _tracker_info(self):
+        """ReturnTracker.get_mean_return / get_mean_ep_len / get_episodes (base_agent.py:576-590) as device scalars."""
         c = self._core
-        cnt = int(c.tracker_count.item())
-        s = c.tracker_sums.tolist()
-        return {"mean_return": s[0] / cnt if cnt else 0.0, "mean_ep_len": s[1] / cnt if cnt else 0.0, "num_eps": cnt}
+        cnt = c.tracker_count.to(torch.float64)
+        mean = c.tracker_sums / torch.clamp(cnt, min=1.0)
+        return {"mean_return": mean[0], "mean_ep_len": mean[1], "num_eps": cnt[0]}
 
     def _reset_tracker(self):
         c = self._core
@@ -631,6 +645,9 @@ class ADDAgent(torch.nn.Module):
 
     # ---- outer loops ---------------------------------------------------------------------------------------------
     def train_model(self, out_model_file=None, int_output_dir="", log_file=None, max_iters=None):
+        """BaseAgent.train_model (base_agent.py:79-113).  Like the reference, the iteration that reaches the stop
+        condition (`max_samples`; here also `max_iters`) is forced to be an output iteration: final test rollout, log
+        flush and checkpoint, so the saved model is never stale."""
         max_samples = self._config.get("max_samples", int(1e6))
         start = time.time()
         self._curr_obs, self._curr_info = self._reset_envs()
@@ -638,23 +655,28 @@ class ADDAgent(torch.nn.Module):
             self._iter, self._sample_count = 0, 0
         self._exp_buffer.clear()
         self._reset_tracker()
-        test_info = {"mean_return": 0.0, "mean_ep_len": 0.0, "num_eps": 0}
+        test_info = None
         while self._sample_count < max_samples and (max_iters is None or self._iter < max_iters):
             output_iter = self._iter % self._iters_per_output == 0
-            if output_iter and self._test_episodes > 0:
+            if output_iter:
                 test_info = self.test_model(self._test_episodes)
-                self._curr_obs, self._curr_info = self._reset_envs()
             info = self._train_iter()
             self._sample_count = self._exp_buffer.get_total_samples()
+            last = self._sample_count >= max_samples or (max_iters is not None and self._iter + 1 >= max_iters)
+            if last:
+                output_iter = True
+                test_info = self.test_model(self._test_episodes)
             self._log(info, test_info, start)
-            if output_iter and out_model_file and (not self._distributed or dist.get_rank() == 0):
-                self.save(out_model_file)
-                if int_output_dir:
-                    self.save(os.path.join(int_output_dir, "model_{:010d}.pt".format(self._iter)))
             if output_iter:
+                self._flush_log()
+                if out_model_file and (not self._distributed or dist.get_rank() == 0):
+                    self.save(out_model_file)
+                    if int_output_dir:
+                        self.save(os.path.join(int_output_dir, "model_{:010d}.pt".format(self._iter)))
                 self._reset_tracker()
                 self._curr_obs, self._curr_info = self._reset_envs()
             self._iter += 1
+        self._flush_log()
 
     def test_model(self, num_episodes):
         """Deterministic-action evaluation over all envs until every env finished
@@ -675,18 +697,43 @@ class ADDAgent(torch.nn.Module):
                 self._curr_obs, self._curr_info = self._reset_done_envs(self._core.done_buf)
                 if bool(torch.all(self._core.eps_per_env > min_eps - 1)):
                     break
-            info = self._tracker_info()
+            info = {k: float(v) for k, v in self._tracker_info().items()}
         self._reset_tracker()
         self.set_mode(AgentMode.TRAIN)
         return info
 
+    LOG_KEYS = ("mean_return", "mean_ep_len", "num_eps", "loss", "critic_loss", "actor_loss", "disc_loss", "disc_reward_mean",
+                "adv_mean", "adv_std")
+
     def _log(self, info, test_info, start):
+        """Logger row of one iteration (base_agent.py:465-520, util/logger.py:160-184) WITHOUT serialising the iteration:
+        the row is stacked on the device, averaged over the ranks like the reference's Logger does (one small all-reduce),
+        copied to pinned host memory asynchronously and printed when the NEXT iteration is logged (or at a flush)."""
+        row = torch.stack([torch.as_tensor(info[k], device=self._device).to(torch.float64).reshape(()) for k in self.LOG_KEYS])
+        if self._distributed and self._world > 1:
+            dist.all_reduce(row, op=dist.ReduceOp.SUM)
+            row = row / self._world
+        host = torch.empty(row.shape, dtype=row.dtype, pin_memory=True)
+        host.copy_(row, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self._flush_log()        # the previous iteration's row: its copy finished an iteration ago
+        t = test_info or {}
+        head = "iter %d samples %d wall %.3fh test_return %.4f" % (
+            self._iter, self._sample_count, (time.time() - start) / 3600.0, float(t.get("mean_return", 0.0)))
+        self._log_pending = (head, host, ev)
+
+    def _flush_log(self):
+        if self._log_pending is None:
+            return
+        head, host, ev = self._log_pending
+        self._log_pending = None
+        ev.synchronize()
         if self._distributed and dist.get_rank() != 0:
             return
-        vals = {k: (float(v) if torch.is_tensor(v) else v) for k, v in info.items()}
-        print("iter %d samples %d wall %.3fh test_return %.4f train_return %.4f loss %.5f disc_reward %.4f" % (
-            self._iter, self._sample_count, (time.time() - start) / 3600.0, test_info["mean_return"],
-            vals["mean_return"], vals["loss"], vals["disc_reward_mean"]), flush=True)
+        v = dict(zip(self.LOG_KEYS, host.tolist()))
+        print("%s train_return %.4f loss %.5f disc_reward %.4f" % (head, v["mean_return"], v["loss"], v["disc_reward_mean"]),
+              flush=True)
 
     # ---- checkpoints (base_agent.py:148-208) -------------------------------------------------------------------------
     def save(self, out_file):

@@ -200,6 +200,15 @@ class OracleMotionLib:
         self.start_idx = true_start if fix_start_idx else quirk_start
         self.s_total = self.table.shape[0]
 
+    def to(self, device):
+        """Move every tensor (bench.py's GPU-eager comparator runs this port on the B200 as the reference would run)."""
+        for k, v in list(vars(self).items()):
+            if torch.is_tensor(v):
+                setattr(self, k, v.to(device))
+            elif isinstance(v, list) and v and torch.is_tensor(v[0]):
+                setattr(self, k, [t.to(device) for t in v])
+        return self
+
     def rows(self, ids, times):                                             # motion_lib.py:322-326
         fr = (times * self.dt_inv).long()
         fr = torch.clip(fr, 0, self.s_total - 1)
@@ -792,6 +801,9 @@ class OracleAgent:
         for p in self.params.values():
             p.grad = None
         loss.backward()
+        clip = float(self.acfg["optimizer"].get("grad_clip", 0.0))             # mp_optimizer.py:10,19-20,46-47 (0 by default: Q4)
+        if clip > 0.0:
+            torch.nn.utils.clip_grad_norm_([self.params[k] for k in self.names], clip)
         if grad_hook is not None:
             grad_hook({k: self.params[k].grad for k in self.names})
         self.adam_steps += 1

@@ -38,18 +38,26 @@ def make_oracle_lib(cfg, fix_start_idx=False, jrot_override=None):
                                       cfg["engine"]["ctrl_dt"], fix_start_idx=fix_start_idx, jrot_override=jrot_override)
 
 
-def make_cpu_env(cfg, engine_seed=1234, fall_prob=0.002):
-    c = {**cfg, "engine": {**cfg["engine"], "seed": engine_seed, "noise_device": "cpu", "fall_prob": fall_prob,
-                           "_target_": "add_gym_b200.engine.SyntheticEngine"}}
-    return ImitationEnvironment(c, "cpu")
+def make_cpu_env(cfg, engine_seed=1234, fall_prob=0.002, device="cpu"):
+    c = {**cfg, "engine": {**cfg["engine"], "seed": engine_seed, "noise_device": "cpu" if device == "cpu" else "device",
+                           "fall_prob": fall_prob, "_target_": "add_gym_b200.engine.SyntheticEngine"}}
+    return ImitationEnvironment(c, device)
 
 
 def make_oracle_agent(num_envs, seed=0, engine_seed=1234, cfg=None, rng=None, mimic_reference_rng=True,
-                      fall_prob=0.002, lib=None):
+                      fall_prob=0.002, lib=None, device="cpu"):
+    """device != "cpu": the GPU-eager comparator of bench.py -- the same port with every tensor on the device (the motion
+    table is built on the CPU and moved); the caller runs it inside `with torch.device(device):`."""
     cfg = cfg or b200_config.default_config(num_envs=num_envs)
     cfg["engine"]["num_envs"] = num_envs
-    env = make_cpu_env(cfg, engine_seed, fall_prob)
     lib = lib or make_oracle_lib(cfg, cfg["task"].get("fix_start_idx", False))
+    if device != "cpu":
+        lib = lib.to(device)
+        with torch.device(device):
+            env = make_cpu_env(cfg, engine_seed, fall_prob, device=device)
+            torch.manual_seed(seed)
+            return add_oracle.OracleAgent(cfg, env, lib, rng=rng, mimic_reference_rng=mimic_reference_rng)
+    env = make_cpu_env(cfg, engine_seed, fall_prob)
     torch.manual_seed(seed)
     agent = add_oracle.OracleAgent(cfg, env, lib, rng=rng, mimic_reference_rng=mimic_reference_rng)
     return agent

@@ -50,7 +50,7 @@ def _device_joint_rot(lib):
     return [j.cpu() for j in lib._frame_joint_rot]
 
 
-def _pair(num_envs, motion=None, fall_prob=0.01, precision="fp32", task_overrides=None):
+def _pair(num_envs, motion=None, fall_prob=0.01, precision="fp32", task_overrides=None, grad_clip=None):
     """(oracle agent with recorded randomness, CUDA agent replaying it) over the same synthetic physics stream.
 
     The oracle's motion library is built from the DEVICE-computed 30 fps joint rotations (stage A of the table
@@ -63,11 +63,15 @@ def _pair(num_envs, motion=None, fall_prob=0.01, precision="fp32", task_override
     torch.set_num_threads(max(1, min(8, os.cpu_count() or 1)))
     gcfg = b200_config.default_config(num_envs=num_envs, motion_file=motion, mlp_precision=precision)
     gcfg["task"].update(task_overrides or {})
+    if grad_clip is not None:
+        gcfg["agent"]["optimizer"]["grad_clip"] = grad_clip
     gcfg["engine"].update(seed=1234, noise_device="cpu", fall_prob=fall_prob)
     torch.manual_seed(0)
     agent = ADDAgent(gcfg, device="cuda:0")
     cfg = b200_config.default_config(num_envs=num_envs, motion_file=motion, mlp_precision=precision)
     cfg["task"].update(task_overrides or {})
+    if grad_clip is not None:
+        cfg["agent"]["optimizer"]["grad_clip"] = grad_clip
     olib = harness.make_oracle_lib(cfg, jrot_override=_device_joint_rot(agent._add_motion.motion_lib))
     rec = helpers.RecordRandom()
     oracle = harness.make_oracle_agent(num_envs, seed=0, engine_seed=1234, cfg=cfg, rng=rec, fall_prob=fall_prob,
@@ -215,11 +219,11 @@ def test_baked_step_table_is_a_drop_in_for_the_built_one(tmp_path):
 # one full iteration: rollout -> train data -> 40 optimizer steps -> normalizers
 # ---------------------------------------------------------------------------------------------------------
 def _iteration_parity(num_envs, motion, gold_case=None, task_overrides=None, steps_synced=None, precision="fp32",
-                      tol=FP32_TOL, reduced_grad_tol=2e-2):
+                      tol=FP32_TOL, reduced_grad_tol=2e-2, grad_clip=None):
     from parity_helpers import rel_err
     from add_gym_b200 import _lib
     _need_legacy(precision)
-    oracle, agent, rec = _pair(num_envs, motion, task_overrides=task_overrides, precision=precision)
+    oracle, agent, rec = _pair(num_envs, motion, task_overrides=task_overrides, precision=precision, grad_clip=grad_clip)
     _start(oracle, agent)
     assert rel_err(agent._curr_obs, oracle.curr_obs) <= FP32_TOL
     assert torch.equal(agent._add_obs._motion_ids.cpu(), oracle.motion_ids)
@@ -332,7 +336,10 @@ def _iteration_parity(num_envs, motion, gold_case=None, task_overrides=None, ste
                 for k in names:
                     o.params[k].copy_(snap["pre"][k])
             finfo = o.loss(idx, masks=gm)
-            fg = torch.autograd.grad(finfo["loss"], [o.params[k] for k in names])
+            fg = list(torch.autograd.grad(finfo["loss"], [o.params[k] for k in names]))
+            if grad_clip:      # the oracle's clip_grad_norm_ on the recomputed gradient
+                total = torch.linalg.vector_norm(torch.stack([torch.linalg.vector_norm(g) for g in fg]))
+                fg = [g * torch.clamp(grad_clip / (total + 1e-6), max=1.0) for g in fg]
             with torch.no_grad():
                 for k in names:
                     o.params[k].copy_(post[k])
@@ -442,6 +449,15 @@ def test_iteration_parity_local_obs_golden():
     (global_obs=False, enable_vel_obs=True, enable_phase_obs=True) on the three-clip library."""
     _iteration_parity(9, THREE_CLIPS, gold_case="local_vel_phase_n9", steps_synced=4,
                       task_overrides={"global_obs": False, "enable_vel_obs": True, "enable_phase_obs": True})
+
+
+def test_iteration_parity_with_gradient_clipping():
+    """optimizer.grad_clip > 0 (mp_optimizer.py:19-20,46-47; off in the reference's shipped config, quirk Q4): the global
+    norm clip runs natively before AdamW.  The oracle's gradients are compared AFTER its clip_grad_norm_, the CUDA path's
+    after addk_clip_grad_norm; the clip must have been active (coefficient < 1)."""
+    oracle, agent, _ = _iteration_parity(16, None, steps_synced=6, grad_clip=0.05)
+    coef = agent._ws["info"][:6, 14].cpu()
+    assert bool((coef > 0).all()) and bool((coef < 1).all()), coef
 
 
 def test_iteration_parity_seven_clips_golden():
