@@ -48,7 +48,8 @@ class AddkSimState(C.Structure):
     _fields_ = [("root_pos", C.c_void_p), ("ld_root_pos", C.c_int32), ("root_rot", C.c_void_p), ("ld_root_rot", C.c_int32),
                 ("root_vel", C.c_void_p), ("ld_root_vel", C.c_int32), ("root_ang", C.c_void_p), ("ld_root_ang", C.c_int32),
                 ("dof_pos", C.c_void_p), ("ld_dof_pos", C.c_int32), ("dof_vel", C.c_void_p), ("ld_dof_vel", C.c_int32),
-                ("link_a", C.c_void_p), ("link_b", C.c_void_p), ("valid", C.c_void_p)]
+                ("link_a", C.c_void_p), ("link_b", C.c_void_p), ("valid", C.c_void_p),
+                ("contact_slots", C.c_int32), ("ld_contact", C.c_int32), ("contact_link_masks", C.c_void_p)]
 
 
 class AddkEnvBuffers(C.Structure):

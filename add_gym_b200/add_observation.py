@@ -108,7 +108,7 @@ class StepCore:
         self.qvel_out = torch.zeros(N, 6 + D, **f32)
         self.reset_mask = torch.zeros(N, dtype=torch.uint8, device=dev)
         self._noncontact_mask = 0
-        self._contact_slots = 0
+        self.ground_plane = None
         self._env_struct(with_tracker=True)
         self._env_struct(with_tracker=False)
 
@@ -158,14 +158,30 @@ class StepCore:
         put("root_ang", r.base_ang_vel)
         put("dof_pos", r.dof_pos)
         put("dof_vel", r.dof_vel)
-        if self._contact_slots > 0:
+        # contacts are fetched EVERY step with the width the engine reports for this step: MJWarp returns [N, 0] while
+        # nothing touches (and at build time), Genesis pads to the per-step maximum (robot.py:221-231)
+        s.contact_slots, s.ld_contact = 0, 0
+        link_masks = getattr(r.entity, "get_contact_link_masks", None)
+        if self.ground_plane is not None and self.task.enable_early_termination and link_masks is not None:
+            # engine extension: per-env {self, other} link bitmasks straight from the backend's flat contact arrays
+            # (addk_contact_link_mask) -- no padded list, no host round trip
+            m = link_masks(with_entity=self.ground_plane, exclude_self_contact=True)
+            assert m.dtype == torch.int64 and m.shape == (self.N, 2) and m.is_contiguous()
+            self._keep.append(m)
+            s.contact_link_masks = m.data_ptr()
+        elif self.ground_plane is not None and self.task.enable_early_termination:
             c = r.entity.get_contacts(with_entity=self.ground_plane, exclude_self_contact=True)
             la, lb, va = c["link_a"], c["link_b"], c["valid_mask"]
-            if la.dtype != torch.int32:
-                la, lb = la.to(torch.int32), lb.to(torch.int32)
-            la, lb, va = la.contiguous(), lb.contiguous(), va.contiguous()
-            self._keep += [la, lb, va]
-            s.link_a, s.link_b, s.valid = la.data_ptr(), lb.data_ptr(), va.data_ptr()
+            width = int(la.shape[1]) if la.dim() == 2 else 0
+            if width > 0:
+                if la.dtype != torch.int32:
+                    la, lb = la.to(torch.int32), lb.to(torch.int32)
+                if va.dtype not in (torch.bool, torch.uint8):
+                    va = va != 0
+                la, lb, va = la.contiguous(), lb.contiguous(), va.contiguous()
+                self._keep += [la, lb, va]
+                s.link_a, s.link_b, s.valid = la.data_ptr(), lb.data_ptr(), va.data_ptr()
+                s.contact_slots, s.ld_contact = width, width
         return s
 
     def set_contact_model(self, ground_plane, noncontact_link_ids):
@@ -175,11 +191,8 @@ class StepCore:
             assert 0 <= l < 64, "link ids above 63 are not supported by the contact bitmask"
             mask |= (1 << l)
         self._noncontact_mask = mask
-        c = self.env.robot.entity.get_contacts(with_entity=ground_plane, exclude_self_contact=True)
-        self._contact_slots = int(c["link_a"].shape[1])
-        assert self._contact_slots <= 32
         self.task.noncontact_link_mask = mask
-        self.task.contact_slots = self._contact_slots
+        self.task.contact_slots = 0          # (per-step width: sim_struct)
 
     # ---- launches ---------------------------------------------------------------------------------------
     def step(self, flags, exp_row=None, env_mask=None, track_returns=True):

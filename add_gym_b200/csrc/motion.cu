@@ -139,6 +139,73 @@ __global__ void step_table_kernel(const float* __restrict__ frames, const float*
 }
 
 // ------------------------------------------------------------------------------------------------
+// MotionLib.calc_motion_frame (motion_lib.py:61-88) at ARBITRARY (clip, time) queries: the run-time form of the
+// interpolation the table build applies at the 100 Hz grid -- root lerp, root / joint slerp, twist angle, velocities
+// of frame i0, loop offset of WRAP clips.  The 30 fps source frames of all clips sit concatenated in HBM
+// (frames / jrot / fvel as produced by stage A); `frame_start` is the cumulative 30 fps frame count, which is
+// what the reference's `_motion_start_idx` really indexes (motion_lib.py:118-131).  One warp per query.
+// ------------------------------------------------------------------------------------------------
+__global__ void motion_frame_kernel(const float* __restrict__ frames, const float* __restrict__ jrot,
+                                    const float* __restrict__ fvel, const long long* __restrict__ frame_start,
+                                    const long long* __restrict__ num_frames, const float* __restrict__ lengths,
+                                    const int* __restrict__ loop_modes, int D, const float* __restrict__ dof_axis,
+                                    const long long* __restrict__ ids, const float* __restrict__ times, int n,
+                                    float* __restrict__ root_pos, float* __restrict__ root_rot, float* __restrict__ root_vel,
+                                    float* __restrict__ root_ang, float* __restrict__ joint_rot, float* __restrict__ dof_pos,
+                                    float* __restrict__ dof_vel) {
+  const int i = blockIdx.x * (blockDim.x / 32) + (threadIdx.x / 32);
+  const int d = threadIdx.x & 31;
+  if (i >= n || d > D) return;
+  const int W = 7 + D;
+  const long long m = ids[i];
+  const long long F = num_frames[m], f0 = frame_start[m];
+  const float t = times[i], len = lengths[m];
+  const bool wrap = loop_modes[m] == 1;
+  float phase = t / len;                                       // calc_phase (motion_lib.py:361-372)
+  if (wrap) phase = sub_rn(phase, floorf(phase));
+  phase = fminf(fmaxf(phase, 0.0f), 1.0f);
+  const float nf1 = (float)(F - 1);                            // _calc_frame_blend (motion_lib.py:118-131)
+  const float pf = mul_rn(phase, nf1);
+  long long i0 = (long long)pf;
+  long long i1 = (i0 + 1 < F - 1) ? i0 + 1 : F - 1;
+  const float blend = sub_rn(pf, (float)i0);
+  i0 += f0; i1 += f0;
+  if (d < D) {
+    const float* a = jrot + ((size_t)i0 * D + d) * 4;
+    const float* b = jrot + ((size_t)i1 * D + d) * 4;
+    const Quat q = slerp({a[0], a[1], a[2], a[3]}, {b[0], b[1], b[2], b[3]}, blend);
+    if (joint_rot) { float* o = joint_rot + ((size_t)i * D + d) * 4; o[0] = q.w; o[1] = q.x; o[2] = q.y; o[3] = q.z; }
+    if (dof_pos) {
+      const Vec3 ax = {dof_axis[3 * d], dof_axis[3 * d + 1], dof_axis[3 * d + 2]};
+      dof_pos[(size_t)i * D + d] = quat_twist_angle(q, ax);
+    }
+    if (dof_vel) dof_vel[(size_t)i * D + d] = fvel[(size_t)i0 * (6 + D) + 6 + d];
+  } else {
+    const float* a = frames + (size_t)i0 * W;
+    const float* b = frames + (size_t)i1 * W;
+    const float om = sub_rn(1.0f, blend);
+    float px = add_rn(mul_rn(om, a[0]), mul_rn(blend, b[0]));
+    float py = add_rn(mul_rn(om, a[1]), mul_rn(blend, b[1]));
+    const float pz = add_rn(mul_rn(om, a[2]), mul_rn(blend, b[2]));
+    if (wrap) {                                                // _calc_loop_offset (motion_lib.py:133-150)
+      const float wraps = floorf(t / len);
+      const float* first = frames + (size_t)f0 * W;
+      const float* last = frames + (size_t)(f0 + F - 1) * W;
+      px = add_rn(px, mul_rn(wraps, sub_rn(last[0], first[0])));
+      py = add_rn(py, mul_rn(wraps, sub_rn(last[1], first[1])));
+    }
+    if (root_pos) { root_pos[(size_t)i * 3] = px; root_pos[(size_t)i * 3 + 1] = py; root_pos[(size_t)i * 3 + 2] = pz; }
+    if (root_rot) {
+      const Quat r = slerp({a[6], a[3], a[4], a[5]}, {b[6], b[3], b[4], b[5]}, blend);
+      float* o = root_rot + (size_t)i * 4; o[0] = r.w; o[1] = r.x; o[2] = r.y; o[3] = r.z;
+    }
+    const float* v = fvel + (size_t)i0 * (6 + D);
+    if (root_vel) for (int k = 0; k < 3; ++k) root_vel[(size_t)i * 3 + k] = v[k];
+    if (root_ang) for (int k = 0; k < 3; ++k) root_ang[(size_t)i * 3 + k] = v[3 + k];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Runtime lookup (motion_lib.py:322-335):
 //   frame = trunc(time * dt_inv); frame = clip(frame, 0, S_total-1); idx = frame + start_idx[motion_id]
 // `start_idx` is whatever the caller's MotionLib holds -- by default the reference's cumulative sum of
@@ -204,6 +271,23 @@ extern "C" int addk_motion_table_build(void* stream, const float* frames, int nu
         row_stride, row0, joint_rot_out, frame_idx_out);
     ADDK_CHECK_LAUNCH();
   }
+  return ADDK_OK;
+}
+
+extern "C" int addk_motion_frame(void* stream, const float* frames, const float* jrot, const float* fvel,
+                                 const long long* frame_start, const long long* num_frames, const float* lengths,
+                                 const int* loop_modes, int num_dofs, const float* dof_axis, const long long* ids,
+                                 const float* times, int n, float* root_pos, float* root_rot, float* root_vel,
+                                 float* root_ang_vel, float* joint_rot, float* dof_pos, float* dof_vel) {
+  if (n == 0) return ADDK_OK;
+  if (!frames || !jrot || !fvel || !frame_start || !num_frames || !lengths || !loop_modes || !dof_axis || !ids || !times ||
+      n < 0 || num_dofs < 1 || num_dofs > 31)
+    return ADDK_ERR_ARG;
+  const int wpb = 8;
+  motion_frame_kernel<<<(n + wpb - 1) / wpb, wpb * 32, 0, (cudaStream_t)stream>>>(
+      frames, jrot, fvel, frame_start, num_frames, lengths, loop_modes, num_dofs, dof_axis, ids, times, n, root_pos,
+      root_rot, root_vel, root_ang_vel, joint_rot, dof_pos, dof_vel);
+  ADDK_CHECK_LAUNCH();
   return ADDK_OK;
 }
 

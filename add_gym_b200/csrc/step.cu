@@ -25,6 +25,31 @@ constexpr int WPB = 8;  // warps (= envs) per block
 
 enum { F_ADVANCE = 1, F_UPDATE_MOTION = 2, F_REWARD_DONE = 4, F_MASKED = 8 };
 
+// Manipulator.get_ground_contact_forces_v2 (robot.py:221-231): does any VALID contact of env e involve a link that may
+// not touch the plane?  The contact list is [N, contact_slots] with the engine's CURRENT width (MJWarp returns width 0
+// while nothing touches, Genesis pads to the per-step maximum): lanes stride over the slots from `first`; the caller
+// combines the lanes with __any_sync.
+__device__ __forceinline__ int contact_hit(const addk_sim_state& sim, uint64_t noncontact_mask, int e, int lane, int first) {
+  int hit = 0;
+  if (sim.contact_link_masks) {          // per-env link bitmasks (addk_contact_link_mask): isin(link_a | link_b, noncontact ids)
+    if (first == 0 && lane == 0)
+      hit = ((sim.contact_link_masks[2 * (size_t)e] | sim.contact_link_masks[2 * (size_t)e + 1]) & noncontact_mask) != 0ull;
+    return hit;
+  }
+  if (sim.valid) {
+    for (int c = first + lane; c < sim.contact_slots; c += 32) {
+      const size_t ci = (size_t)e * sim.ld_contact + c;
+      if (sim.valid[ci]) {
+        const int la = sim.link_a[ci], lb = sim.link_b[ci];
+        const bool ha = la >= 0 && la < 64 && ((noncontact_mask >> la) & 1ull);
+        const bool hb = lb >= 0 && lb < 64 && ((noncontact_mask >> lb) & 1ull);
+        hit |= (ha || hb) ? 1 : 0;
+      }
+    }
+  }
+  return hit;
+}
+
 struct StepParams {
   addk_task task;
   addk_motion_lib lib;
@@ -308,16 +333,7 @@ __global__ void __launch_bounds__(WPB * 32) env_step_kernel(const __grid_constan
     de = mul_rn(pd, pd);
   }
   pe = warp_sum(pe); ve = warp_sum(ve); de = warp_sum(de);
-  int contact = 0;
-  if (lane < tk.contact_slots && p.sim.valid) {
-    size_t ci = (size_t)e * tk.contact_slots + lane;
-    if (p.sim.valid[ci]) {
-      int la = p.sim.link_a[ci], lb = p.sim.link_b[ci];
-      bool ha = la >= 0 && la < 64 && ((tk.noncontact_link_mask >> la) & 1ull);
-      bool hb = lb >= 0 && lb < 64 && ((tk.noncontact_link_mask >> lb) & 1ull);
-      contact = (ha || hb) ? 1 : 0;
-    }
-  }
+  int contact = contact_hit(p.sim, tk.noncontact_link_mask, e, lane, 0);
   contact = __any_sync(0xffffffffu, contact);
   if (lane == 0) {
     Vec3 rp = {s_sim[0], s_sim[1], s_sim[2]}, tp = {s_ref[0], s_ref[1], s_ref[2]};
@@ -442,8 +458,8 @@ __device__ __forceinline__ void env_step_fast_main(const StepParams& p, float* c
     hv = *reinterpret_cast<const float4*>(g_hist + (size_t)slot * p.env.hist_stride + 4 * hc);
   }
   int c_valid = 0, c_la = -1, c_lb = -1;
-  if ((p.flags & F_REWARD_DONE) && lane < tk.contact_slots && p.sim.valid) {
-    const size_t ci = (size_t)e * tk.contact_slots + lane;
+  if ((p.flags & F_REWARD_DONE) && lane < p.sim.contact_slots && p.sim.valid) {     // first 32 slots, loaded up front
+    const size_t ci = (size_t)e * p.sim.ld_contact + lane;
     c_valid = p.sim.valid[ci]; c_la = p.sim.link_a[ci]; c_lb = p.sim.link_b[ci];
   }
   float ret0 = 0.f; long long len0 = 0;
@@ -602,6 +618,8 @@ __device__ __forceinline__ void env_step_fast_main(const StepParams& p, float* c
     const bool hb = c_lb >= 0 && c_lb < 64 && ((tk.noncontact_link_mask >> c_lb) & 1ull);
     contact = (ha || hb) ? 1 : 0;
   }
+  if ((p.flags & F_REWARD_DONE) && (p.sim.contact_slots > 32 || p.sim.contact_link_masks))   // wider lists / link bitmasks
+    contact |= contact_hit(p.sim, tk.noncontact_link_mask, e, lane, p.sim.contact_link_masks ? 0 : 32);
   contact = __any_sync(0xffffffffu, contact);
   o.pe = pe; o.ve = ve; o.de = de; o.contact = contact; o.t = t; o.mt = mt; o.m_len = m_len; o.m_loop = m_loop;
   o.ret0 = ret0; o.len0 = len0;
@@ -905,7 +923,8 @@ extern "C" int addk_env_step(void* stream, const addk_task* task, const addk_mot
   const int D = task->num_dofs, half = (7 + D + 3) & ~3;
   if (D < 1 || D > 31 || lib->row_stride < 2 * half || (lib->row_stride & 3) || env->hist_stride < lib->row_stride ||
       (env->hist_stride & 3) || task->num_tar_steps > ADDK_MAX_TAR_STEPS || task->num_tar_steps > 16 ||
-      task->num_disc_steps > ADDK_MAX_DISC_STEPS || task->num_disc_steps < 1 || task->contact_slots > 32)
+      task->num_disc_steps > ADDK_MAX_DISC_STEPS || task->num_disc_steps < 1 || sim->contact_slots < 0 ||
+      (sim->contact_slots > 0 && sim->valid && (!sim->link_a || !sim->link_b || sim->ld_contact < sim->contact_slots)))
     return ADDK_ERR_ARG;
   if ((flags & F_MASKED) && !env_mask) return ADDK_ERR_ARG;
   if ((flags & F_REWARD_DONE) && !dof_err_w) return ADDK_ERR_ARG;

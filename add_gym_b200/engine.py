@@ -403,6 +403,44 @@ class SyntheticEngine(BaseEngine):
 
 
 # ------------------------------------------------------------------------------------------------
+# An engine whose contact list changes its WIDTH from step to step, like the real backends do: MuJoCo-Warp's
+# get_contacts returns [nworld, 0] while nothing touches (the state at build time, mjwarp_engine.py:896-986), Genesis pads
+# to the per-step maximum.  Same random walk; the one synthetic contact lands in a different column every step.
+# ------------------------------------------------------------------------------------------------
+class DynamicContactEntity(SyntheticEntity):
+    persistent_state_tensors = False
+    WIDTHS = (0, 3, 40, 1, 33, 0, 7)
+
+    def get_contacts(self, with_entity=None, exclude_self_contact=False):
+        k = int(self._scene.t)
+        w = self.WIDTHS[k % len(self.WIDTHS)]
+        n, dev = self._n, self._link_a.device
+        la = torch.zeros(n, w, dtype=self._link_a.dtype, device=dev)
+        lb = torch.zeros(n, w, dtype=self._link_b.dtype, device=dev)
+        va = torch.zeros(n, w, dtype=self._valid.dtype, device=dev)
+        if w > 0:
+            col = (7 * k + 5) % w
+            la[:, col], lb[:, col], va[:, col] = self._link_a[:, 2], self._link_b[:, 2], self._valid[:, 2]
+        return {"link_a": la, "link_b": lb, "valid_mask": va}
+
+
+class DynamicContactScene(SyntheticScene):
+    def add_entity(self, morph_type, morph_file=None, **kwargs):
+        if morph_type == "plane":
+            return super().add_entity(morph_type, morph_file, **kwargs)
+        ent = DynamicContactEntity(self, morph_file, self._n_links)
+        self._n_links += len(ent.links)
+        self._robots.append(ent)
+        self._entities.append(ent)
+        return ent
+
+
+class DynamicContactEngine(SyntheticEngine):
+    def create_scene(self, show_viewer=False, **options):
+        return DynamicContactScene(self)
+
+
+# ------------------------------------------------------------------------------------------------
 # Host-boundary engine (bench.py "e2e"): a simulator whose state lives in pinned HOST memory
 # ------------------------------------------------------------------------------------------------
 class HostBoundaryEntity(SyntheticEntity):

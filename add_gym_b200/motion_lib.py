@@ -70,6 +70,7 @@ class MotionLib:
         self._table = torch.from_numpy(np.array(table, copy=True)).to(dev)
         self._frame_idx = None          # build-time diagnostics do not exist for a baked table
         self._frame_joint_rot, self._frame_vel = [], []
+        self._frames_cat = None         # a baked table carries no 30 fps source frames (calc_motion_frame refuses)
         self._c_lib = _lib.AddkMotionLib(
             table=self._table.data_ptr(), row_stride=self._row_stride, num_motions=len(n_steps), s_total=self._s_total,
             start_idx=self._motion_start_idx.data_ptr(), lengths=self._motion_lengths.data_ptr(),
@@ -129,12 +130,21 @@ class MotionLib:
         self._frame_idx = torch.zeros(s_total, 2, dtype=torch.long, device=dev)
         self._frame_joint_rot = []      # per clip [F, D, 4]: 30 fps joint rotations (reference `_frame_joint_rot`)
         self._frame_vel = []            # per clip [F, 6 + D]: root_vel, root_ang_vel, dof_vel of the source frames
+        # the 30 fps source data of all clips, concatenated (calc_motion_frame at arbitrary times reads them)
+        tot_f = int(np.sum(nframes))
+        f_start = np.concatenate([[0], np.cumsum(nframes)[:-1]]).astype(np.int64)
+        self._frames_cat = torch.empty(tot_f, 7 + D, dtype=torch.float32, device=dev)
+        self._jrot_cat = torch.empty(tot_f, D, 4, dtype=torch.float32, device=dev)
+        self._fvel_cat = torch.empty(tot_f, 6 + D, dtype=torch.float32, device=dev)
+        self._frame_start = torch.tensor(f_start, dtype=torch.long, device=dev)
         for m, clip in enumerate(clips):
-            frames = torch.tensor(clip.frames, dtype=torch.float32).to(dev).contiguous()   # fp64 -> fp32 rounding
-            F = frames.shape[0]
-            assert frames.shape[1] == 7 + D
-            jrot = torch.empty(F, D, 4, dtype=torch.float32, device=dev)
-            fvel = torch.empty(F, 6 + D, dtype=torch.float32, device=dev)
+            F = clip.frames.shape[0]
+            assert clip.frames.shape[1] == 7 + D
+            a, b = int(f_start[m]), int(f_start[m]) + F
+            frames = self._frames_cat[a:b]
+            frames.copy_(torch.tensor(clip.frames, dtype=torch.float32))                     # fp64 -> fp32 rounding
+            jrot = self._jrot_cat[a:b]
+            fvel = self._fvel_cat[a:b]
             rc = L.addk_motion_table_build(
                 _lib.stream(), _lib.ptr(frames), C.c_int(F), C.c_int(D), _lib.ptr(self._col_of_dof),
                 _lib.ptr(self._dof_axis), C.c_float(float(clip.fps)), C.c_float(float(np.float32(1.0 / clip.fps))),
@@ -186,6 +196,27 @@ class MotionLib:
         wrap = self._motion_loop_modes[motion_ids] == motion_io.LoopMode.WRAP.value
         phase = torch.where(wrap, phase - torch.floor(phase), phase)
         return torch.clip(phase, 0.0, 1.0)
+
+    def calc_motion_frame(self, motion_ids, motion_times):
+        """Reference MotionLib.calc_motion_frame (motion_lib.py:61-88): interpolate the 30 fps clips at ARBITRARY times --
+        root lerp, root / joint slerp, hinge angle = twist angle of the blended joint rotation, velocities of frame i0,
+        loop offset for WRAP clips.  -> (root_pos [n,3], root_rot [n,4] wxyz, root_vel [n,3], root_ang_vel [n,3],
+        joint_rot [n,D,4], dof_pos [n,D], dof_vel [n,D]).  The hot path itself never calls this (it reads the 100 Hz
+        table, quirk Q1); the table builder applies the same arithmetic at the grid times."""
+        if self._frames_cat is None:
+            raise _lib.AddkError("calc_motion_frame needs the 30 fps source clips: this library was loaded from a baked step table")
+        n, D, dev = int(motion_ids.shape[0]), self._num_dofs, self._device
+        ids = motion_ids.to(torch.long).contiguous()
+        times = motion_times.to(torch.float32).contiguous()
+        f = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
+        out = (f(n, 3), f(n, 4), f(n, 3), f(n, 3), f(n, D, 4), f(n, D), f(n, D))
+        rc = _lib.lib().addk_motion_frame(
+            _lib.stream(), _lib.ptr(self._frames_cat), _lib.ptr(self._jrot_cat), _lib.ptr(self._fvel_cat),
+            _lib.ptr(self._frame_start), _lib.ptr(self._motion_num_frames), _lib.ptr(self._motion_lengths),
+            _lib.ptr(self._motion_loop_modes), C.c_int(D), _lib.ptr(self._dof_axis), _lib.ptr(ids), _lib.ptr(times),
+            C.c_int(n), *[_lib.ptr(t) if n > 0 else C.c_void_p(0) for t in out])
+        _lib.check(rc, "addk_motion_frame")
+        return out
 
     def get_precomputed_motion_step(self, motion_ids, motion_times, return_index=False):
         """(root_pos, root_rot, root_vel, root_ang_vel, dof_pos, dof_vel) rows of the step table."""

@@ -50,7 +50,7 @@ typedef struct addk_task {
   int32_t obs_dim, disc_obs_dim;
   int32_t track_root, track_root_h;                 /* add_obs._track_global_root(), root_height_obs */
   int32_t enable_early_termination, pose_termination;
-  int32_t contact_slots;                            /* C of get_contacts()[...] [N,C] */
+  int32_t contact_slots;                            /* unused since round 2: the width travels per step in addk_sim_state */
   float tar_offsets[ADDK_MAX_TAR_STEPS];            /* fl32(dt * k)  (add_observation.py:214-215) */
   float disc_offsets[ADDK_MAX_DISC_STEPS];          /* oldest -> newest (add_observation.py:362-370) */
   float ctrl_dt;                                    /* env.time_buf += ctrl_dt (env.py:155) */
@@ -81,7 +81,12 @@ typedef struct addk_sim_state {
   const float* dof_pos;   int32_t ld_dof_pos;      /* [N,D] = get_dofs_position()[:,6:] */
   const float* dof_vel;   int32_t ld_dof_vel;      /* [N,D] */
   const int32_t* link_a;  const int32_t* link_b;   /* [N,C] contact pairs vs the ground plane */
-  const uint8_t* valid;                            /* [N,C] */
+  const uint8_t* valid;                            /* [N,C]; NULL = no contact list this step */
+  int32_t contact_slots;                           /* C = get_contacts()[...].shape[1] of THIS step: engines change it
+                                                      (MJWarp: 0 while nothing touches; Genesis: per-step maximum) */
+  int32_t ld_contact;                              /* elements between consecutive env rows of the three contact arrays */
+  const uint64_t* contact_link_masks;              /* optional [N,2] {self-side, other-side} link bitmasks from
+                                                      addk_contact_link_mask: used INSTEAD of the list when set */
 } addk_sim_state;
 
 /* Persistent per-env tensors owned by ADDObservation / ADDDone / Environment and mutated in place. */
@@ -118,6 +123,15 @@ int addk_motion_table_build(void* stream, const float* frames, int num_frames, i
                             int n_steps, double dt, float motion_len, int loop_wrap, float* jrot_work,
                             float* fvel_work, float* table, int row_stride, long long row0,
                             float* joint_rot_out, long long* frame_idx_out);
+/* MotionLib.calc_motion_frame (motion_lib.py:61-88,118-150): interpolation at arbitrary (clip id, time) queries from
+ * the 30 fps source frames of all clips concatenated -- frames [sumF, 7+D] (file layout), jrot [sumF, D, 4] and fvel
+ * [sumF, 6+D] as stage A of addk_motion_table_build leaves them; frame_start [C] = cumulative 30 fps frame counts,
+ * num_frames / lengths / loop_modes [C].  Outputs [n,3|4|3|3|D*4|D|D], any may be NULL. */
+int addk_motion_frame(void* stream, const float* frames, const float* jrot, const float* fvel,
+                      const long long* frame_start, const long long* num_frames, const float* lengths,
+                      const int* loop_modes, int num_dofs, const float* dof_axis, const long long* ids,
+                      const float* times, int n, float* root_pos, float* root_rot, float* root_vel,
+                      float* root_ang_vel, float* joint_rot, float* dof_pos, float* dof_vel);
 /* MotionLib.get_precomputed_motion_step (motion_lib.py:322-335); any output may be NULL. */
 int addk_motion_gather(void* stream, const float* table, int row_stride, int num_dofs, long long s_total,
                        const long long* start_idx, float dt_inv, const long long* ids, const float* times,
@@ -166,6 +180,28 @@ int addk_sampler_update_errors(void* stream, const long long* clip_ids, const fl
                                const float* disc_obs, const float* disc_obs_demo, int disc_dim, int n,
                                const float* seg_sizes, int num_motions, int num_segments, double* sums_work,
                                int* counts_work, float* errors);
+
+/* ----- engine-side hand-off (csrc/engine_side.cu) ------------------------- */
+/* MJWarpEntity.get_contacts without the host round trip (engine/mjwarp_engine.py:896-986): flat contact arrays of the
+ * backend (geom pairs [cap,2], world ids [cap], *nacon_dev valid entries -- read on the device) -> per world two uint64
+ * link bitmasks {self-side bodies, other-side bodies} of the contacts between `self` and `other` (bit b = body id b;
+ * ids >= 64 cannot be represented and are ignored).  link_masks_out [nworld, 2] is cleared by the call.  The step kernel
+ * takes the result through addk_sim_state::contact_link_masks. */
+int addk_contact_link_mask(void* stream, const int* geom_pairs, const int* world_ids, const int* nacon_dev,
+                           int nacon_cap, const int* geom_bodyid, int ngeom, unsigned long long self_body_mask,
+                           unsigned long long other_body_mask, int self_is_other, int exclude_self_contact, int nworld,
+                           unsigned long long* link_masks_out);
+/* The six state getters of robot.py:271-293 (MJWarp: mjwarp_engine.py:640-795) as ONE launch: qpos [nworld, ld_qpos] /
+ * qvel [nworld, ld_qvel] -> packed rows [pos3 | quat4 wxyz | dof D | pad][vel3 | ang3 | dofvel D | pad] (the step
+ * table's row format).  qpos_col [7+D] / qvel_col [6+D]: source column of every packed entry (-1 = 0.0). */
+int addk_pack_state(void* stream, const float* qpos, int ld_qpos, const float* qvel, int ld_qvel, const int* qpos_col,
+                    const int* qvel_col, int num_dofs, int nworld, float* rows_out, int row_stride);
+/* PD-control prologue of MJWarpScene.step (mjwarp_engine.py:1565-1604): qfrc[w, dof_ids[j]] += clamp(kp_j (target_wj -
+ * pos_wj) - kv_j vel_wj, +-max_torque) for local dofs j >= 6 with a non-zero gain; pos_col [n_local] = qpos column of
+ * local dof j (-1: reads as 0, ball joints); max_torque <= 0: no clamp.  qfrc is zeroed by the caller. */
+int addk_pd_control(void* stream, const float* qpos, int ld_qpos, const float* qvel, int ld_qvel, const float* target,
+                    const float* kp, const float* kv, const int* pos_col, const int* dof_ids, int n_local,
+                    float max_torque, int nworld, float* qfrc, int ld_qfrc);
 
 /* ----- returns / advantages / statistics (csrc/gae.cu) --------------------------------------- */
 /* compute_td_lambda_return + next_vals masking + adv (base_agent.py:624-647; ppo_agent.py:126-146). */

@@ -152,6 +152,7 @@ class OracleMotionLib:
         nframes = torch.tensor([f.shape[0] for f, _, _ in clips], dtype=torch.long)
         self.num_frames = nframes
         rows, fidx = [], []
+        self.clip_frames = []       # per clip (pos, rot, jrot, vel, ang, dofvel): the reference's _frame_* tensors
         for m, (frames, fps, loop) in enumerate(clips):
             fr = torch.tensor(frames, dtype=torch.float32)                  # motion_lib.py:108-110
             pos, rot = fr[:, 0:3], fr[:, [6, 3, 4, 5]]                      # xyzw -> wxyz, motion_lib.py:10-15
@@ -170,6 +171,7 @@ class OracleMotionLib:
             drot = v_unit(q_pos(q_mul(q_conj(jrot[:-1]), jrot[1:])))
             dv = torch.sum(self.axis * (q_exp_map(drot) / fdt), dim=-1)
             dofvel = torch.cat([dv, dv[-1:]], dim=0)
+            self.clip_frames.append((pos, rot, jrot, vel, ang, dofvel))
             # _precompute_motion_steps -> calc_motion_frame (motion_lib.py:285-320, 61-88)
             L = self.lengths[m]
             n = int(math.ceil(float(L) / dt))
@@ -208,6 +210,32 @@ class OracleMotionLib:
             elif isinstance(v, list) and v and torch.is_tensor(v[0]):
                 setattr(self, k, [t.to(device) for t in v])
         return self
+
+    def calc_motion_frame(self, ids, times):                                # motion_lib.py:61-88,118-150,361-372
+        """Interpolation at arbitrary (clip, time) queries from the concatenated 30 fps frames ->
+        (root_pos, root_rot, root_vel, root_ang_vel, joint_rot, dof_pos, dof_vel)."""
+        cat = [torch.cat([c[k] for c in self.clip_frames], dim=0) for k in range(6)]
+        pos, rot, jrot, vel, ang, dofvel = cat
+        start = torch.cumsum(self.num_frames, 0) - self.num_frames          # frame offsets (what _motion_start_idx is)
+        L, nf = self.lengths[ids], self.num_frames[ids]
+        wrap = self.loop_modes[ids] == WRAP
+        phase = times / L                                                   # calc_phase
+        phase = torch.where(wrap, phase - torch.floor(phase), phase)
+        phase = torch.clip(phase, 0.0, 1.0)
+        i0 = (phase * (nf - 1)).long()                                      # _calc_frame_blend
+        i1 = torch.min(i0 + 1, nf - 1)
+        blend = phase * (nf - 1) - i0
+        i0, i1 = i0 + start[ids], i1 + start[ids]
+        b = blend.unsqueeze(-1)
+        rp = (1.0 - b) * pos[i0] + b * pos[i1]
+        rr = q_slerp(rot[i0], rot[i1], blend)
+        jr = q_slerp(jrot[i0], jrot[i1], b)
+        D = self.D
+        dp = q_twist_angle(jr, self.axis.unsqueeze(0).expand(ids.shape[0], D, 3))
+        delta = torch.stack([c[0][-1] - c[0][0] for c in self.clip_frames], dim=0)    # _motion_root_pos_delta, z zeroed
+        delta[:, -1] = 0.0
+        off = torch.where(wrap.unsqueeze(-1), torch.floor(times / L).unsqueeze(-1) * delta[ids], torch.zeros_like(rp))
+        return rp + off, rr, vel[i0], ang[i0], jr, dp, dofvel[i0]
 
     def rows(self, ids, times):                                             # motion_lib.py:322-326
         fr = (times * self.dt_inv).long()
@@ -468,7 +496,7 @@ class OracleAgent:
         if mimic_reference_rng:
             self.sample_time(N)                                   # ADDAgent._build_normalizers
             self.sample_time(N)                                   # _build_model -> get_disc_obs_shape
-        aspace = env.robot.get_action_space()
+        aspace = env.robot.get_action_space().to(lib.table.device)
         self.act_dim = aspace.shape[0]
         self.a_mean = 0.5 * (aspace[:, 1] + aspace[:, 0])
         self.a_std = 0.5 * (aspace[:, 1] - aspace[:, 0])

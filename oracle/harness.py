@@ -40,7 +40,8 @@ def make_oracle_lib(cfg, fix_start_idx=False, jrot_override=None):
 
 def make_cpu_env(cfg, engine_seed=1234, fall_prob=0.002, device="cpu"):
     c = {**cfg, "engine": {**cfg["engine"], "seed": engine_seed, "noise_device": "cpu" if device == "cpu" else "device",
-                           "fall_prob": fall_prob, "_target_": "add_gym_b200.engine.SyntheticEngine"}}
+                           "fall_prob": fall_prob,
+                           "_target_": cfg["engine"].get("_target_", "add_gym_b200.engine.SyntheticEngine")}}
     return ImitationEnvironment(c, device)
 
 

@@ -83,8 +83,45 @@ def run_case(name, num_envs, motion_file, fall_prob, task_overrides=None):
     print(name, "written;", {k: float(v) for k, v in info.items() if k in ("loss", "mean_return", "num_eps")})
 
 
+def run_motion_frame_queries(name="motion_frame_queries"):
+    """MotionLib.calc_motion_frame of the executed reference at arbitrary (clip, time) queries on the seven-clip library
+    with two clips switched to WRAP: the runtime interpolation API (root lerp, root / joint slerp, twist angle, loop offset)."""
+    ref_harness._install_stubs()
+    import add_gym.anim.motion as ref_motion
+    orig = ref_motion.load_motion
+
+    def load_with_wrap(file):
+        m = orig(file)
+        if "run2" in file or "jumps1" in file:
+            m.loop_mode = ref_motion.LoopMode.WRAP
+        return m
+    agent, cfg = ref_harness.make_reference_agent(2, seed=0, engine_seed=1234,
+                                                  motion_file=[(n + ".motion", w, cut) for n, w, cut in SEVEN_CLIPS])
+    import add_gym.anim.motion_lib as ref_ml
+    ref_ml.motion.load_motion = load_with_wrap
+    try:
+        ml = ref_ml.MotionLib(motion_file=cfg["task"]["motion_file"], motion_order=list(cfg["task"]["motion_joint_order"]),
+                              kin_char_model=agent._env.robot._kin_char_model, dt=0.01, device="cpu")
+    finally:
+        ref_ml.motion.load_motion = orig
+    g = torch.Generator().manual_seed(21)
+    n = 4000
+    ids = torch.randint(0, 7, (n,), generator=g)
+    times = torch.rand(n, generator=g) * 30.0 - 2.0          # before the start, inside, beyond the end (CLAMP) / several loops (WRAP)
+    times[:14] = torch.tensor([0.0, 1.0 / 30.0, 13.3, 13.3 + 1e-4, 1e-6, -1.0, 100.0] * 2)
+    ids[:14] = torch.tensor([0] * 7 + [2] * 7)
+    out = ml.calc_motion_frame(ids, times)
+    res = {"ids": ids.numpy(), "times": times.numpy(), "loop_modes": ml._motion_loop_modes.numpy()}
+    for k, v in zip(("root_pos", "root_rot", "root_vel", "root_ang_vel", "joint_rot", "dof_pos", "dof_vel"), out):
+        res[k] = v.numpy()
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **res)
+    print(name, "written;", {k: v.shape for k, v in res.items()})
+
+
 if __name__ == "__main__":
     only = sys.argv[1:]
+    if not only or "motion_frame_queries" in only:
+        run_motion_frame_queries()
     for name, kw in CASES.items():
         if not only or name in only:
             run_case(name, **kw)

@@ -97,3 +97,20 @@ def test_td_lambda_properties():
     ret = f(r1, v1)
     cut = done[:-1] != 0
     assert torch.allclose(ret[:-1][cut], (r1[:-1] + 0.99 * v1[:-1])[cut], atol=1e-12)
+
+
+def test_oracle_calc_motion_frame_reproduces_reference():
+    """MotionLib.calc_motion_frame at arbitrary (clip, time) queries (motion_lib.py:61-88): the oracle's restatement against
+    the executed reference on the seven-clip library with two WRAP clips -- bit for bit."""
+    g = np.load(os.path.join(GOLD, "motion_frame_queries.npz"))
+    cfg = b200_config.default_config(num_envs=2, motion_file=os.path.join(b200_config.ASSET_DIR, "seven_clips.yaml"))
+    clips, weights = harness.load_clips(cfg["task"]["motion_file"])
+    clips = [(f, fps, int(lm)) for (f, fps, _), lm in zip(clips, g["loop_modes"])]
+    from add_gym_b200 import kinematics
+    kin = kinematics.KinCharModel()
+    kin.load_char_file(cfg["robot"]["urdf_path"])
+    lib = add_oracle.OracleMotionLib(clips, weights, kin.dof_axes(), kin.motion_column_of_dof(list(cfg["task"]["motion_joint_order"])),
+                                     cfg["engine"]["ctrl_dt"])
+    out = lib.calc_motion_frame(torch.from_numpy(g["ids"]), torch.from_numpy(g["times"]))
+    for k, v in zip(("root_pos", "root_rot", "root_vel", "root_ang_vel", "joint_rot", "dof_pos", "dof_vel"), out):
+        np.testing.assert_array_equal(v.numpy(), g[k], err_msg=k)
