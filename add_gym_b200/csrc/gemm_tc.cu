@@ -877,11 +877,17 @@ gemm_tc_h3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
 //     drain of a tile is followed by its global stores while the tensor core is already on the next tile.
 // Warps as above (0 TMA, 1 MMA, 2..9 workers); barriers: full/empty per stage, acc_full/acc_empty per buffer.
 // ---------------------------------------------------------------------------------------------------------------
-template <int BN, bool SINGLE = false>    // SINGLE: one 16-bit plane per operand and one MMA per 16 k (precision "bf16")
+// PAIR: tcgen05 cta_group::2 -- a cluster of two CTAs on one TPC computes a 256 x BN tile; each CTA stages its own 128 rows
+// of A and its own HALF of B, the leader's single thread issues M = 256 MMAs that read both shared memories.  Why: the
+// 1-CTA main loop pulls 48 KB per 32-k block and SM (62 B/clk/SM, 9.3 KB/clk chip-wide) through an L2 that delivers
+// ~6.3 KB/clk to the SMs: measured 33k cycles per 128x256x1024 tile against 24.6k of MMA issue -- L2-bound.  Pairs cut
+// the fill to 32 KB per block (and make room for 5 stages instead of 3).
+template <int BN, bool SINGLE = false, bool PAIR = false>    // SINGLE: one 16-bit plane per operand and one MMA per 16 k (precision "bf16")
 struct CfgP {
   static constexpr int BK = 32;
   static constexpr int A_BYTES = BM * BK * 2;
-  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int B_ROWS = PAIR ? BN / 2 : BN;            // rows of B this CTA stages
+  static constexpr int B_BYTES = B_ROWS * BK * 2;
   static constexpr int STAGE_BYTES = (SINGLE ? 1 : 2) * (A_BYTES + B_BYTES);
   static constexpr int EPI_COLS = 64;           // columns per staging pass (32: a 4th stage fits, but 128-byte row segments store 40 % slower)
   static constexpr int EPI_BYTES = 8 * 32 * EPI_COLS * 4;           // 8 worker warps x 32 rows x 64 floats
@@ -893,6 +899,53 @@ struct CfgP {
 };
 constexpr int H3P_CHUNK_KB = 8;                                     // 256 k = 48 instructions per drain (measured: rel 5e-7)
 
+// ---- cluster / cta_group::2 helpers ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_rank0(uint32_t addr) {      // shared::cluster address of `addr` in CTA rank 0
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(r) : "r"(addr));
+  return r;
+}
+// Remote arrive without the cluster-scope release (measured in round 1: `arrive.release.cluster` stalls the issuing warp
+// for ~1.5k cycles).  What the leader's MMA must observe is ordered by the tcgen05 fences the caller has executed.
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
+  __threadfence_block();
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load of a CTA pair: data lands in THIS CTA's shared memory, the transaction bytes are counted on the barrier
+// `bar_cluster` (a shared::cluster address: the leader's full barrier)
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_f16_2cta(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_commit_2cta(uint32_t bar) {   // arrives on `bar` (same offset) in both CTAs
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+
+// TMA store of one [32 rows x 32 fp32] staging box (128-byte rows, SWIZZLE_128B) into C; the hardware clips the box at
+// the tensor bounds, so ragged tiles need no edge path.  Coordinates: {column, row, split-K slab}.
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 struct ParamsP {
   Params p;
   const uint32_t* a_amax; const uint32_t* b_amax;
@@ -900,13 +953,15 @@ struct ParamsP {
   int tiles_m, tiles_n, total_tiles;
   int chunk_kb;                 // k-blocks per accumulator chunk (drain period)
   int bf16;                     // SINGLE kernel: operands are bf16 (instruction descriptor format 1)
+  int tma_store;                // the fp32 output leaves through TMA stores from the staging tile (tmC is valid)
 };
 
-template <int BN, bool SINGLE>
+template <int BN, bool SINGLE, bool PAIR>
 __global__ void __launch_bounds__(X3_THREADS, 1)
 gemm_tc_h3p_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
-                   const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl, const ParamsP pp) {
-  using C = CfgP<BN, SINGLE>;
+                   const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
+                   const __grid_constant__ CUtensorMap tmC, const ParamsP pp) {
+  using C = CfgP<BN, SINGLE, PAIR>;
   const Params& p = pp.p;
   constexpr int BK = C::BK, UK = 16;
   constexpr int CPW = BN / 2, NCH = CPW / 32;
@@ -927,6 +982,11 @@ gemm_tc_h3p_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
   auto b_lo = [&](int s) { return a_lo(s) + C::A_BYTES; };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;     // CTA of the pair; rank 0 issues the MMAs
+  const bool leader = rank == 0;
+  const int unit = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;          // tile walker: a CTA or a CTA pair
+  const int units = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  constexpr int TM = PAIR ? 2 * BM : BM;                   // rows of one tile
   const int kb_total = (p.K + BK - 1) / BK;
   const int tiles_mn = pp.tiles_m * pp.tiles_n;
   const long long t_entry = clock64();
@@ -935,15 +995,20 @@ gemm_tc_h3p_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
     tma_prefetch_desc(&tmAh); tma_prefetch_desc(&tmBh);
     if (!SINGLE) { tma_prefetch_desc(&tmAl); tma_prefetch_desc(&tmBl); }
     for (int s = 0; s < C::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(acc_full_bar(b), 1); mbar_init(acc_empty_bar(b), 8); }
+    for (int b = 0; b < 2; ++b) { mbar_init(acc_full_bar(b), 1); mbar_init(acc_empty_bar(b), PAIR ? 16 : 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "r"((uint32_t)C::TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "r"((uint32_t)C::TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "r"((uint32_t)C::TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr) : "memory");
@@ -952,45 +1017,50 @@ gemm_tc_h3p_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
     // ===================== TMA producer: runs ahead across tile boundaries =====================
     if (lane == 0) {
       uint32_t it = 0;
-      for (int t = blockIdx.x; t < pp.total_tiles; t += gridDim.x) {
+      // PAIR: every load of both CTAs counts its bytes on the LEADER's full barrier (one expect_tx of 2 stages there)
+      auto load = [&](uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+        if (PAIR) tma_load_2d_pair(dst, map, mapa_rank0(bar), c0, c1); else tma_load_2d(dst, map, bar, c0, c1);
+      };
+      for (int t = unit; t < pp.total_tiles; t += units) {
         const int z = t / tiles_mn, r = t - z * tiles_mn;
-        const int m0 = (r / pp.tiles_n) * BM, n0 = (r % pp.tiles_n) * BN;
+        const int m0 = (r / pp.tiles_n) * TM + (int)rank * BM;                 // this CTA's 128 rows of A
+        const int n0 = (r % pp.tiles_n) * BN + (int)rank * C::B_ROWS * (PAIR ? 1 : 0);     // this CTA's (half of the) B rows
         const int kb_begin = z * p.kb_per_split;
         const int num_kb = min(kb_total, kb_begin + p.kb_per_split) - kb_begin;
         for (int i = 0; i < num_kb; ++i, ++it) {
           const int s = (int)(it % C::STAGES);
           const uint32_t phs = (it / C::STAGES) & 1u;
           mbar_wait(empty_bar(s), phs ^ 1u);
-          mbar_expect_tx(full_bar(s), C::STAGE_BYTES);
+          if (!PAIR || leader) mbar_expect_tx(full_bar(s), (PAIR ? 2 : 1) * C::STAGE_BYTES);
           const int k0 = (kb_begin + i) * BK;
           if (!p.a_mn) {
-            tma_load_2d(a_hi(s), &tmAh, full_bar(s), k0, m0);
-            if (!SINGLE) tma_load_2d(a_lo(s), &tmAl, full_bar(s), k0, m0);
+            load(a_hi(s), &tmAh, full_bar(s), k0, m0);
+            if (!SINGLE) load(a_lo(s), &tmAl, full_bar(s), k0, m0);
           } else {
 #pragma unroll
             for (int j = 0; j < BM / 64; ++j) {
-              tma_load_2d(a_hi(s) + j * C::MN_BOX_BYTES, &tmAh, full_bar(s), m0 + 64 * j, k0);
-              if (!SINGLE) tma_load_2d(a_lo(s) + j * C::MN_BOX_BYTES, &tmAl, full_bar(s), m0 + 64 * j, k0);
+              load(a_hi(s) + j * C::MN_BOX_BYTES, &tmAh, full_bar(s), m0 + 64 * j, k0);
+              if (!SINGLE) load(a_lo(s) + j * C::MN_BOX_BYTES, &tmAl, full_bar(s), m0 + 64 * j, k0);
             }
           }
           if (!p.b_mn) {
-            tma_load_2d(b_hi(s), &tmBh, full_bar(s), k0, n0);
-            if (!SINGLE) tma_load_2d(b_lo(s), &tmBl, full_bar(s), k0, n0);
+            load(b_hi(s), &tmBh, full_bar(s), k0, n0);
+            if (!SINGLE) load(b_lo(s), &tmBl, full_bar(s), k0, n0);
           } else {
 #pragma unroll
-            for (int j = 0; j < BN / 64; ++j) {
-              tma_load_2d(b_hi(s) + j * C::MN_BOX_BYTES, &tmBh, full_bar(s), n0 + 64 * j, k0);
-              if (!SINGLE) tma_load_2d(b_lo(s) + j * C::MN_BOX_BYTES, &tmBl, full_bar(s), n0 + 64 * j, k0);
+            for (int j = 0; j < C::B_ROWS / 64; ++j) {
+              load(b_hi(s) + j * C::MN_BOX_BYTES, &tmBh, full_bar(s), n0 + 64 * j, k0);
+              if (!SINGLE) load(b_lo(s) + j * C::MN_BOX_BYTES, &tmBl, full_bar(s), n0 + 64 * j, k0);
             }
           }
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
+  } else if (warp == 1 && (!PAIR || leader)) {
+    // ===================== MMA issuer (PAIR: the leader CTA's, for both) =====================
     const uint32_t fmt = (SINGLE && pp.bf16) ? ((1u << 7) | (1u << 10)) : 0u;      // A / B format: 0 = fp16, 1 = bf16
     const uint32_t idesc = (1u << 4) | fmt | ((uint32_t)(p.a_mn ? 1 : 0) << 15) | ((uint32_t)(p.b_mn ? 1 : 0) << 16) |
-                           ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+                           ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
     const uint32_t a_lbo = p.a_mn ? C::MN_BOX_BYTES : 16u, b_lbo = p.b_mn ? C::MN_BOX_BYTES : 16u;
     const uint32_t a_sbo = p.a_mn ? 1024u : C::K_SBO, b_sbo = p.b_mn ? 1024u : C::K_SBO;
     const uint32_t a_lay = p.a_mn ? 2u : 4u, b_lay = p.b_mn ? 2u : 4u;
@@ -1003,7 +1073,7 @@ gemm_tc_h3p_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
     long long* const dbg = (p.dbg && blockIdx.x == 0) ? p.dbg : nullptr;
     long long w_empty = 0, w_full = 0;
     const long long t_begin = clock64();
-    for (int t = blockIdx.x; t < pp.total_tiles; t += gridDim.x) {
+    for (int t = unit; t < pp.total_tiles; t += units) {
       const int z = t / tiles_mn;
       const int kb_begin = z * p.kb_per_split;
       const int num_kb = min(kb_total, kb_begin + p.kb_per_split) - kb_begin;
@@ -1026,24 +1096,30 @@ gemm_tc_h3p_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
             const uint64_t dah = dA0 + (uint64_t)s * STAGE16, dbh = dB0 + (uint64_t)s * STAGE16;
 #pragma unroll
             for (int ks = 0; ks < BK / UK; ++ks) {
-              umma_f16(d_tmem, dah + ks * a_k16, dbh + ks * b_k16, idesc, acc);
+              if (PAIR) umma_f16_2cta(d_tmem, dah + ks * a_k16, dbh + ks * b_k16, idesc, acc);
+              else umma_f16(d_tmem, dah + ks * a_k16, dbh + ks * b_k16, idesc, acc);
               acc = 1;
               if (!SINGLE) {
-                umma_f16(d_tmem, dah + LO16 + ks * a_k16, dbh + ks * b_k16, idesc, 1u);
-                umma_f16(d_tmem, dah + ks * a_k16, dbh + LO16 + ks * b_k16, idesc, 1u);
+                if (PAIR) {
+                  umma_f16_2cta(d_tmem, dah + LO16 + ks * a_k16, dbh + ks * b_k16, idesc, 1u);
+                  umma_f16_2cta(d_tmem, dah + ks * a_k16, dbh + LO16 + ks * b_k16, idesc, 1u);
+                } else {
+                  umma_f16(d_tmem, dah + LO16 + ks * a_k16, dbh + ks * b_k16, idesc, 1u);
+                  umma_f16(d_tmem, dah + ks * a_k16, dbh + LO16 + ks * b_k16, idesc, 1u);
+                }
               }
             }
-            umma_commit(empty_bar(s));
+            if (PAIR) umma_commit_2cta(empty_bar(s)); else umma_commit(empty_bar(s));     // PAIR: frees the stage in both CTAs
           }
           __syncwarp();
         }
-        if (issuer) umma_commit(acc_full_bar(b));
+        if (issuer) { if (PAIR) umma_commit_2cta(acc_full_bar(b)); else umma_commit(acc_full_bar(b)); }
         __syncwarp();
         kb += n;
       }
     }
     if (dbg && lane == 0) { dbg[0] = clock64() - t_begin; dbg[1] = w_empty; dbg[2] = w_full; dbg[7] = t_begin - t_entry; }
-  } else {
+  } else if (warp >= 2) {
     // ===================== workers: chunk drains + epilogue =====================
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
@@ -1065,9 +1141,11 @@ gemm_tc_h3p_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
     long long* const dbg = (p.dbg && blockIdx.x == 0 && warp == 2) ? p.dbg : nullptr;
     long long w_accfull = 0, t_drain = 0, t_epi = 0;
     const long long t_begin = clock64();
-    for (int t = blockIdx.x; t < pp.total_tiles; t += gridDim.x) {
+    uint32_t acc_empty_remote[2];
+    if (PAIR) { acc_empty_remote[0] = mapa_rank0(acc_empty_bar(0)); acc_empty_remote[1] = mapa_rank0(acc_empty_bar(1)); }
+    for (int t = unit; t < pp.total_tiles; t += units) {
       const int z = t / tiles_mn, r = t - z * tiles_mn;
-      const int m0 = (r / pp.tiles_n) * BM, n0 = (r % pp.tiles_n) * BN;
+      const int m0 = (r / pp.tiles_n) * TM + (int)rank * BM, n0 = (r % pp.tiles_n) * BN;     // this CTA's 128 accumulator rows
       const int kb_begin = z * p.kb_per_split;
       const int num_kb = min(kb_total, kb_begin + p.kb_per_split) - kb_begin;
       float acc[CPW];
@@ -1091,16 +1169,69 @@ gemm_tc_h3p_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(acc_empty_bar(b));
+        if (lane == 0) {       // PAIR: the leader's MMA waits for the workers of BOTH CTAs (16 arrivals on its barrier)
+          if (PAIR && !leader) mbar_arrive_cluster_relaxed(b ? acc_empty_remote[1] : acc_empty_remote[0]);
+          else mbar_arrive(acc_empty_bar(b));
+        }
         if (dbg) { w_accfull += c1 - c0; t_drain += clock64() - c1; }
         kb += n;
       }
       const long long c2 = dbg ? clock64() : 0;
-      // ---- epilogue: 32 rows x CPW columns of this warp, EPI_COLS at a time through the warp's staging tile
+      // ---- epilogue: 32 rows x CPW columns of this warp
       float* Cz = p.C + (size_t)z * p.slab_stride;
       const bool vec = epilogue_vec_ok(p, Cz);
       const int row = m0 + 32 * q + lane;
       const int cw0 = n0 + half * CPW;
+      if (pp.tma_store) {
+        // 32 columns at a time, in the accumulator's own layout (lane = row): scale, bias / ReLU / ReLU-mask in registers,
+        // then a swizzled [32 x 32] box in shared memory (two boxes per warp, alternating) that ONE lane hands to the TMA
+        // engine.  The worker warps never touch global memory for C: no address arithmetic, no edge predicates (the
+        // hardware clips the box), and the store of box i overlaps the arithmetic of box i + 1.
+        const bool row_ok = row < p.M;
+        const float* const mk_row = (p.mask && row_ok) ? p.mask + (size_t)row * p.ld_mask : nullptr;
+        const bool relu = p.relu != 0;
+#pragma unroll
+        for (int cc = 0; cc < NCH; ++cc) {
+          const int c0 = cw0 + 32 * cc;
+          if (c0 < p.N && !(p.pair_flags & 1)) {             // warp-uniform
+            const bool full = c0 + 32 <= p.N;
+            float4* const buf = stg + (cc & 1) * (32 * 8);
+            if (lane == 0 && !(p.pair_flags & 4)) tma_store_wait_read<1>();          // the box that used this buffer two stores ago has been read
+            __syncwarp();
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const int col = c0 + 4 * j4;
+              float4 o = make_float4(acc[cc * 32 + 4 * j4] * inv, acc[cc * 32 + 4 * j4 + 1] * inv, acc[cc * 32 + 4 * j4 + 2] * inv,
+                                     acc[cc * 32 + 4 * j4 + 3] * inv);
+              if (full || col + 3 < p.N) {
+                if (p.bias) { const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + col)); o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w; }
+                if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                if (mk_row) {
+                  const float4 m4 = __ldg(reinterpret_cast<const float4*>(mk_row + col));
+                  o.x = m4.x > 0.f ? o.x : 0.f; o.y = m4.y > 0.f ? o.y : 0.f; o.z = m4.z > 0.f ? o.z : 0.f; o.w = m4.w > 0.f ? o.w : 0.f;
+                }
+                if (row_ok) vmax = fmaxf(fmaxf(vmax, fmaxf(fabsf(o.x), fabsf(o.y))), fmaxf(fabsf(o.z), fabsf(o.w)));
+              } else {                                          // ragged right edge: element-wise guards (the TMA clips the rest)
+                float e[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  if (col + u < p.N) {
+                    if (p.bias) e[u] += p.bias[col + u];
+                    if (relu) e[u] = fmaxf(e[u], 0.f);
+                    if (mk_row) e[u] = mk_row[col + u] > 0.f ? e[u] : 0.f;
+                    if (row_ok) vmax = fmaxf(vmax, fabsf(e[u]));
+                  }
+                }
+                o = make_float4(e[0], e[1], e[2], e[3]);
+              }
+              buf[lane * 8 + (j4 ^ (lane & 7))] = o;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0 && !(p.pair_flags & 8)) { tma_store_3d(&tmC, smem_u32(buf), c0, m0 + 32 * q, z); tma_store_commit(); }
+          }
+        }
+      } else {
 #pragma unroll
       for (int ps = 0; ps < CPW / C::EPI_COLS; ++ps) {
         const int c0 = cw0 + ps * C::EPI_COLS;
@@ -1138,19 +1269,22 @@ gemm_tc_h3p_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
           }
         }
       }
+      }
       if (dbg) t_epi += clock64() - c2;
     }
     if (dbg && lane == 0) { dbg[3] = clock64() - t_begin; dbg[4] = w_accfull; dbg[5] = t_drain; dbg[6] = t_epi; dbg[8] = clock64() - t_entry; }
+    if (pp.tma_store && lane == 0) tma_store_wait_all();      // shared memory must outlive the engine's reads
     if (p.c_amax) {
       const uint32_t mx = __reduce_max_sync(0xffffffffu, __float_as_uint(vmax));
       if (lane == 0 && mx) atomicMax(p.c_amax + 1, mx);
     }
   }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS) : "memory");
+    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS) : "memory");
   }
 }
 
@@ -1166,6 +1300,19 @@ static bool make_map_f16(CUtensorMap* map, const void* ptr, long long inner, lon
                         strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, box_inner == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+// 3-D fp32 tensor map of the output for TMA stores: {N columns, M rows, split-K slabs}, box 32 x 32 x 1, 128-byte swizzle
+// (the staging boxes are written with chunk ^ (row & 7)).  Needs a 16-byte aligned base, ldc and slab pitch multiples of 4.
+static bool make_map_c(CUtensorMap* map, float* ptr, long long N, long long M, long long ldc, long long slabs, long long slab_stride) {
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (ldc & 3) || (slab_stride & 3)) return false;
+  cuuint64_t dims[3] = {(cuuint64_t)N, (cuuint64_t)M, (cuuint64_t)(slabs < 1 ? 1 : slabs)};
+  cuuint64_t strides[2] = {(cuuint64_t)ldc * 4, (cuuint64_t)(slab_stride > 0 ? slab_stride : M * ldc) * 4};
+  cuuint32_t box[3] = {32u, 32u, 1u};
+  cuuint32_t estr[3] = {1u, 1u, 1u};
+  CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
 
@@ -1194,23 +1341,50 @@ static int sm_count() {
   return n;
 }
 
-template <int BN, bool SINGLE = false>
+template <int BN, bool SINGLE = false, bool PAIR = false>
 static int launch_h3p(cudaStream_t st, const CUtensorMap& tah, const CUtensorMap& tal, const CUtensorMap& tbh,
                       const CUtensorMap& tbl, ParamsP& pp, int M, int N, int split) {
-  using C = CfgP<BN, SINGLE>;
+  using C = CfgP<BN, SINGLE, PAIR>;
+  // the fp32 output leaves through TMA stores when its geometry allows (and nothing else rides on the epilogue)
+  CUtensorMap tc = tah;
+  pp.tma_store = 0;
+  if (addk_switches().h3_tma_store && pp.p.C && !pp.p.accumulate && !pp.p.c_hi && !(SINGLE && pp.p.C16) &&
+      (!pp.p.bias || (reinterpret_cast<uintptr_t>(pp.p.bias) & 15) == 0) &&
+      (!pp.p.mask || ((pp.p.ld_mask & 3) == 0 && (reinterpret_cast<uintptr_t>(pp.p.mask) & 15) == 0)) &&
+      make_map_c(&tc, pp.p.C, N, M, pp.p.ldc, split, pp.p.slab_stride))
+    pp.tma_store = 1;
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(gemm_tc_h3p_kernel<BN, SINGLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES) != cudaSuccess) {
+    if (cudaFuncSetAttribute(gemm_tc_h3p_kernel<BN, SINGLE, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES) != cudaSuccess) {
       addk_set_error("gemm_tc: cannot raise the dynamic shared memory limit");
       return ADDK_ERR_LAUNCH;
     }
     configured = true;
   }
-  pp.tiles_m = (M + BM - 1) / BM; pp.tiles_n = (N + BN - 1) / BN; pp.total_tiles = pp.tiles_m * pp.tiles_n * split;
+  constexpr int TM = PAIR ? 2 * BM : BM;
+  pp.tiles_m = (M + TM - 1) / TM; pp.tiles_n = (N + BN - 1) / BN; pp.total_tiles = pp.tiles_m * pp.tiles_n * split;
   // (74 / 99 / 128 CTAs per layer, so that layers of the three streams run side by side, measured the same 2.6 ms per
   // optimizer step as one CTA per SM)
-  const int grid = pp.total_tiles < sm_count() ? pp.total_tiles : sm_count();
-  gemm_tc_h3p_kernel<BN, SINGLE><<<grid, X3_THREADS, C::SMEM_BYTES, st>>>(tah, tal, tbh, tbl, pp);
+  if (!PAIR) {
+    const int grid = pp.total_tiles < sm_count() ? pp.total_tiles : sm_count();
+    gemm_tc_h3p_kernel<BN, SINGLE, PAIR><<<grid, X3_THREADS, C::SMEM_BYTES, st>>>(tah, tal, tbh, tbl, tc, pp);
+    return ADDK_OK;
+  }
+  const int pairs = sm_count() / 2;
+  const int units = pp.total_tiles < pairs ? pp.total_tiles : pairs;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * units, 1, 1);
+  cfg.blockDim = dim3(X3_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  if (cudaLaunchKernelEx(&cfg, gemm_tc_h3p_kernel<BN, SINGLE, PAIR>, tah, tal, tbh, tbl, tc, (const ParamsP)pp) != cudaSuccess) {
+    addk_set_error("gemm_tc: cluster launch of the CTA-pair kernel failed");
+    return ADDK_ERR_LAUNCH;
+  }
   return ADDK_OK;
 }
 
@@ -1358,7 +1532,7 @@ static int h3_convert(cudaStream_t st, const float* x, long long rows, int cols,
 
 // ids reported by addk_debug_last_gemm_kernel(): which kernel a call was dispatched to
 enum { ADDK_K_SGEMM = 0, ADDK_K_TF32 = 10, ADDK_K_TF32X3 = 11, ADDK_K_TF32X3_PAIR = 12, ADDK_K_BF16_TILE = 20,
-       ADDK_K_BF16_PERSISTENT = 21, ADDK_K_H3_TILE = 30, ADDK_K_H3_PERSISTENT = 31 };
+       ADDK_K_BF16_PERSISTENT = 21, ADDK_K_BF16_PAIR = 22, ADDK_K_H3_TILE = 30, ADDK_K_H3_PERSISTENT = 31, ADDK_K_H3_PAIR = 32 };
 
 // precision: 1 = tf32x3, 2 = tf32.  Shapes the tensor-core tiles do not cover (heads with 1 or 29 outputs,
 // contraction shorter than one k-block, misaligned leading dimensions, fused input normalisation) run on the
@@ -1398,6 +1572,11 @@ static int gemm_bf16(cudaStream_t st, const addk_gemm_args& a) {
       CUtensorMap tah, tbh;
       bool okp = p.a_mn ? make_map_f16(&tah, a.A16, a.M, a.K, a.lda, 64, 32, true) : make_map_f16(&tah, a.A16, a.K, a.M, a.lda, 32, BM, true);
       okp = okp && (p.b_mn ? make_map_f16(&tbh, a.B16, a.N, a.K, a.ldb, 64, 32, true) : make_map_f16(&tbh, a.B16, a.K, a.N, a.ldb, 32, 256, true));
+      if (okp && addk_switches().h3_pair && a.M > BM) {
+        CUtensorMap tbp = tbh;
+        const bool okb = p.b_mn || make_map_f16(&tbp, a.B16, a.K, a.N, a.ldb, 32, 128, true);
+        if (okb) { g_addk_last_gemm_kernel = ADDK_K_BF16_PAIR; return launch_h3p<256, true, true>(st, tah, tah, tbp, tbp, pp, a.M, a.N, split); }
+      }
       if (okp) { g_addk_last_gemm_kernel = ADDK_K_BF16_PERSISTENT; return launch_h3p<256, true>(st, tah, tah, tbh, tbh, pp, a.M, a.N, split); }
     }
   }
@@ -1506,6 +1685,10 @@ static int gemm_h3(cudaStream_t st, const addk_gemm_args& a) {
     }
     pp.chunk_kb = addk_switches().h3_chunk_kb;
     g_addk_last_gemm_kernel = ADDK_K_H3_PERSISTENT;
+    if (addk_switches().h3_pair && a.M > BM) {      // CTA pairs (cta_group::2): each CTA stages a 128-row half of B
+      if (!p.b_mn) ok = make_map_f16(&tbh, Bh, a.K, a.N, a.ldb, BKh, BN / 2) && make_map_f16(&tbl, Bl, a.K, a.N, a.ldb, BKh, BN / 2);
+      if (ok) { g_addk_last_gemm_kernel = ADDK_K_H3_PAIR; return launch_h3p<256, false, true>(st, tah, tal, tbh, tbl, pp, a.M, a.N, split); }
+    }
     return launch_h3p<256>(st, tah, tal, tbh, tbl, pp, a.M, a.N, split);
   }
   g_addk_last_gemm_kernel = ADDK_K_H3_TILE;

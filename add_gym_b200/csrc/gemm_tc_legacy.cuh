@@ -508,26 +508,8 @@ struct Cfg2 {
   static constexpr uint32_t MN_BOX_BYTES = BK * 128u;
 };
 
-__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ uint32_t mapa_rank0(uint32_t addr) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(r) : "r"(addr));
-  return r;
-}
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-// Remote arrive without the cluster-scope release: measured, `arrive.release.cluster` stalls the issuing warp for
-// ~1.5k cycles, which made the worker warps the bottleneck (301 us vs 199 us per 16384x1024x1024 layer).  What the
-// leader's MMAs must see is this CTA's OWN shared memory; every writer has already executed fence.proxy.async
-// (generic -> async proxy) and the warp has re-converged, so a CTA-scope fence followed by a relaxed arrive is enough.
-__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
-  __threadfence_block();
-  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
   uint32_t ok;
@@ -551,10 +533,6 @@ __device__ __forceinline__ void umma_tf32_2cta(uint32_t tmem_d, uint64_t da, uin
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
-}
-__device__ __forceinline__ void umma_commit_2cta(uint32_t bar) {   // arrives on `bar` (same offset) in both CTAs
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               ::"r"(bar), "h"((uint16_t)3) : "memory");
 }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(X3_THREADS, 1)

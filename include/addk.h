@@ -31,8 +31,8 @@ long long addk_launch_count(int reset);
 /* bit 0: built with the superseded tf32 / tf32x3 kernels (make LEGACY=1; precision modes 1 and 2 need it) */
 int addk_build_flags(void);
 /* test / profiling hooks: id of the kernel the last addk_gemm call was dispatched to (0 CUDA-core fp32, 10 tf32,
- * 11 tf32x3, 12 tf32x3 CTA pair, 20 bf16 one tile per CTA, 21 bf16 persistent, 30 f16x3 one tile per CTA,
- * 31 f16x3 persistent); a device buffer of 16 int64 that CTA 0 of the persistent kernels fills with clock stamps
+ * 11 tf32x3, 12 tf32x3 CTA pair, 20 bf16 one tile per CTA, 21 bf16 persistent, 22 bf16 persistent CTA pairs, 30 f16x3 one
+ * tile per CTA, 31 f16x3 persistent, 32 f16x3 persistent CTA pairs (cta_group::2)); a device buffer of 16 int64 that CTA 0 of the persistent kernels fills with clock stamps
  * (NULL switches the stamps off, the default) */
 int addk_debug_last_gemm_kernel(void);
 int addk_debug_set_stamp_buffer(long long* device_buffer16);

@@ -13,7 +13,8 @@ import torch
 pytestmark = pytest.mark.gpu
 
 TOL = {"fp32": 2e-6, "tf32x3": 2e-6, "tf32": 2e-3, "f16x3": 2e-6}
-K_SGEMM, K_BF16_TILE, K_BF16_PERSISTENT, K_H3_TILE, K_H3_PERSISTENT = 0, 20, 21, 30, 31     # addk_debug_last_gemm_kernel()
+K_SGEMM, K_BF16_TILE, K_BF16_PERSISTENT, K_H3_TILE = 0, 20, 21, 30     # addk_debug_last_gemm_kernel()
+K_H3_PERSISTENT = (31, 32)      # persistent f16x3 kernel: one CTA per SM (31) or cta_group::2 CTA pairs (32, the default)
 
 
 def _skip_without_legacy(prec):
@@ -329,7 +330,7 @@ def test_gemm_f16x3_persistent_kernel_layouts_and_epilogues(case):
         slabs = torch.full((S, M, N), float("nan"), device="cuda")
         _gemm_h3(A, B, slabs, M, N, K, ta, tb, tw_a, tw_b, split=S)
         torch.cuda.synchronize()
-        assert _last_kernel() == K_H3_PERSISTENT, name
+        assert _last_kernel() in K_H3_PERSISTENT, name
         assert not bool(torch.isnan(slabs).any()), "every slab element must be written"
         assert _rel(slabs.double().sum(0), ref) <= TOL["f16x3"], name
         return
@@ -351,7 +352,7 @@ def test_gemm_f16x3_persistent_kernel_layouts_and_epilogues(case):
     slot = torch.zeros(2, device="cuda", dtype=torch.int32)
     _gemm_h3(A, B, out, M, N, K, ta, tb, tw_a, tw_b, c_amax=slot, **kw)
     torch.cuda.synchronize()
-    assert _last_kernel() == K_H3_PERSISTENT, name
+    assert _last_kernel() in K_H3_PERSISTENT, name
     e = _rel(out, ref)
     assert e <= TOL["f16x3"], "%s: rel err %.3e" % (name, e)
     assert int(slot[1].item()) == int(out.abs().max().view(torch.int32).item()), "max|C| word left by the epilogue"
@@ -372,4 +373,4 @@ def test_gemm_small_shapes_run_the_one_tile_kernel():
     A = torch.randn(8192, 1024, device="cuda", generator=g)
     out = torch.empty(8192, 1024, device="cuda")
     _gemm_h3(A, B, out, 8192, 1024, 1024, 0, 1, _Twin(A), _Twin(B))
-    assert _last_kernel() == K_H3_PERSISTENT
+    assert _last_kernel() in K_H3_PERSISTENT

@@ -13,6 +13,7 @@ prec = sys.argv[2] if len(sys.argv) > 2 else "tf32x3"
 steps = int(sys.argv[3]) if len(sys.argv) > 3 else 2
 cfg = b200_config.default_config(num_envs=envs, mlp_precision=prec)
 cfg["engine"].update(seed=1234, noise_device="device", fall_prob=0.002)
+cfg["agent"]["update_streams"] = int(os.environ.get("STREAMS", "3"))
 torch.manual_seed(0)
 a = ADDAgent(cfg, device="cuda:0")
 a._curr_obs, a._curr_info = a._reset_envs()
