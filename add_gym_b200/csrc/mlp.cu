@@ -261,6 +261,24 @@ __global__ void disc_head_backward_kernel(const float* __restrict__ h2, const fl
                                           uint32_t* u2_slot, uint32_t* dh2_slot) {
   float um = 0.f, dm = 0.f;
   const size_t tot = (size_t)R * H;
+  if ((H & 3) == 0 && !u2_16 && !dh2_16) {          // 128-bit path (f16x3 / fp32 modes)
+    const size_t n4 = tot >> 2;
+    const int h4 = H >> 2;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+      const int r = (int)(i / h4), k = (int)(i - (size_t)r * h4) * 4;
+      const float4 h = ldg4(h2 + 4 * i), w = ldg4(wl + k);
+      const float dl = dlogit[r];
+      const float4 u = make_float4(h.x > 0.f ? w.x : 0.f, h.y > 0.f ? w.y : 0.f, h.z > 0.f ? w.z : 0.f, h.w > 0.f ? w.w : 0.f);
+      const float4 d = make_float4(dl * u.x, dl * u.y, dl * u.z, dl * u.w);
+      stg4(u2 + 4 * i, u);
+      stg4(dh2 + 4 * i, d);
+      um = fmaxf(fmaxf(um, fmaxf(fabsf(u.x), fabsf(u.y))), fmaxf(fabsf(u.z), fabsf(u.w)));
+      dm = fmaxf(fmaxf(dm, fmaxf(fabsf(d.x), fabsf(d.y))), fmaxf(fabsf(d.z), fabsf(d.w)));
+    }
+    amax_commit(um, u2_slot);
+    amax_commit(dm, dh2_slot);
+    return;
+  }
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (size_t)gridDim.x * blockDim.x) {
     const int r = (int)(i / H), k = (int)(i - (size_t)r * H);
     const float u = h2[i] > 0.f ? wl[k] : 0.f;
@@ -279,9 +297,11 @@ __global__ void disc_head_backward_kernel(const float* __restrict__ h2, const fl
 __global__ void grad_penalty_kernel(const float* __restrict__ gx, int M, int R, int dim, int ld, float coef,
                                     float* __restrict__ dg, double* __restrict__ stats, uint16_t* __restrict__ dg16,
                                     uint32_t* dg_slot) {
+  __shared__ double s_pen[8];
   int i = blockIdx.x * (blockDim.x / 32) + (threadIdx.x / 32);
   int lane = threadIdx.x & 31;
   float vm = 0.f;
+  double pen = 0.0;
   if (i < R) {                                        // whole warps
     float s = 0.f;
     for (int c = lane; c < dim; c += 32) { float v = gx[(size_t)i * ld + c]; s += v * v; }
@@ -295,9 +315,36 @@ __global__ void grad_penalty_kernel(const float* __restrict__ gx, int M, int R, 
       vm = fmaxf(vm, fabsf(v));
       if (dg16) dg16[(size_t)i * ld + c] = to_bf16(v);
     }
-    if (lane == 0 && i < M) atomicAdd(stats + ST_PEN, (double)e * e);
+    if (i < M) pen = (double)e * e;
   }
   amax_commit(vm, dg_slot);
+  // one atomic per block (16384 double atomics on ONE address cost 30 us of a 33 us kernel); the 8 rows of a block are
+  // added in a fixed order, the blocks in arrival order as before
+  if (lane == 0) s_pen[threadIdx.x >> 5] = pen;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += s_pen[w];
+    if (t != 0.0) atomicAdd(stats + ST_PEN, t);
+  }
+}
+
+// sum of squares of the discriminator's three weight tensors in one launch: blockIdx.y selects the tensor;
+// y = 0 (logit weights) feeds both statistics (disc_logit_reg and disc_weight_decay terms, add_agent.py:157-202)
+__global__ void disc_weight_sumsq_kernel(const float* __restrict__ wl, long long nl, const float* __restrict__ w0, long long n0,
+                                         const float* __restrict__ w1, long long n1, double* __restrict__ stats) {
+  __shared__ double sm[32];
+  const float* x = blockIdx.y == 0 ? wl : (blockIdx.y == 1 ? w0 : w1);
+  const long long n = blockIdx.y == 0 ? nl : (blockIdx.y == 1 ? n0 : n1);
+  double s = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    double v = x[i]; s += v * v;
+  }
+  s = block_sum(s, sm);
+  if (threadIdx.x == 0 && s != 0.0) {
+    atomicAdd(stats + ST_W_SQ, s);
+    if (blockIdx.y == 0) atomicAdd(stats + ST_WL_SQ, s);
+  }
 }
 
 __global__ void sumsq_kernel(const float* __restrict__ x, long long n, double* __restrict__ out) {
@@ -430,24 +477,31 @@ __global__ void outer_mask_kernel(const float* __restrict__ d, const float* __re
 }
 
 // out[n] = sum over the `parts` per-block partial rows the f16x3 split pass left behind (h3_split_kernel), in a fixed
-// order; slabs 1..nsplit-1 are zeroed like colsum_slabs_kernel does.  grid = ceil(n / 32), 256 threads = 8 float4
-// columns (one 128-byte line per partial row) x 32 row lanes, four independent loads in flight per thread: with up to
-// 1184 partial rows a block of 32 column quads x 8 row lanes walked 148 dependent loads per thread on 8 SMs (41 us).
+// order; slabs 1..nsplit-1 are zeroed like colsum_slabs_kernel does.  grid = (ceil(n / 32), CP_CHUNKS): every block adds
+// its chunk of the partial rows for 8 float4 columns x 32 row lanes (four independent loads in flight per thread) and
+// leaves one row in `work`; the last block of a column group to finish (ticket counter, self-resetting) adds the
+// CP_CHUNKS rows in a fixed order.  (One block per column group walked up to 1184 rows with 16 - 32 blocks in the whole
+// grid: 10 us per launch, eight launches per optimizer step.)
+constexpr int CP_CHUNKS = 8;
 __global__ void __launch_bounds__(256) colsum_parts_kernel(const float* __restrict__ part, int parts, int n, float* __restrict__ out,
-                                                           long long slab_stride, int nsplit) {
+                                                           long long slab_stride, int nsplit, float* __restrict__ work,
+                                                           unsigned int* __restrict__ tickets) {
   __shared__ float4 sm[32][8];
+  __shared__ unsigned int s_last;
   const int cq = threadIdx.x & 7, rl = threadIdx.x >> 3;
   const int col = (blockIdx.x * 8 + cq) * 4;
+  const int per = (parts + CP_CHUNKS - 1) / CP_CHUNKS;
+  const int r_begin = blockIdx.y * per, r_end = min(parts, r_begin + per);
   float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
   if (col < n) {
     float4 u[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) u[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int r = rl; r < parts; r += 128) {
+    for (int r = r_begin + rl; r < r_end; r += 128) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int rr = r + 32 * j;
-        if (rr < parts) {
+        if (rr < r_end) {
           const float4 v = ldg4(part + (size_t)rr * n + col);
           u[j].x += v.x; u[j].y += v.y; u[j].z += v.z; u[j].w += v.w;
         }
@@ -458,16 +512,31 @@ __global__ void __launch_bounds__(256) colsum_parts_kernel(const float* __restri
   }
   sm[rl][cq] = t;
   __syncthreads();
-  if (rl == 0 && col < n) {
+  if (rl == 0) {
     t = sm[0][cq];
 #pragma unroll
     for (int i = 1; i < 32; ++i) { t.x += sm[i][cq].x; t.y += sm[i][cq].y; t.z += sm[i][cq].z; t.w += sm[i][cq].w; }
-    const float tv[4] = {t.x, t.y, t.z, t.w};
+    *reinterpret_cast<float4*>(work + ((size_t)blockIdx.y * COLSUM_MAX_N + blockIdx.x * 32 + cq * 4)) = t;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(tickets + blockIdx.x, 1u) == CP_CHUNKS - 1) ? 1u : 0u;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (rl == 0 && col < n) {
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int ch = 0; ch < CP_CHUNKS; ++ch) {
+      const float4 v = __ldcg(reinterpret_cast<const float4*>(work + ((size_t)ch * COLSUM_MAX_N + blockIdx.x * 32 + cq * 4)));
+      a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+    }
+    const float tv[4] = {a.x, a.y, a.z, a.w};
     for (int e = 0; e < 4 && col + e < n; ++e) {
       out[col + e] = tv[e];
       for (int z = 1; z < nsplit; ++z) out[(size_t)z * slab_stride + col + e] = 0.f;
     }
   }
+  if (threadIdx.x == 0) tickets[blockIdx.x] = 0u;
 }
 
 // torch.nn.utils.clip_grad_norm_ (mp_optimizer.py:19-20,46-47): total = ||g||_2 over all parameters,
@@ -860,8 +929,12 @@ static int wgrad(cudaStream_t st, const Ctx& c, const ChainWs& ws, const float* 
     g_colpart_for = nullptr; g_colpart_buf = nullptr;
     if (rc != ADDK_OK) return rc;
     if (o_b >= 0 && g_colpart_rows > 0) {
-      colsum_parts_kernel<<<(n_out + 31) / 32, 256, 0, st>>>(ws.colpart, g_colpart_rows, n_out,
-                                                              F(c.slabs) + (size_t)slab0 * P + o_b, P, S);
+      // (scratch: the chain's colsum work area -- the two kernels never overlap inside one chain; tickets live behind the
+      //  64 chunk rows of colsum_slabs_kernel, a second set of 32 counters)
+      float* cwork = ws.colsum_work;
+      unsigned int* ctick = (unsigned int*)(cwork + (size_t)COLSUM_CHUNKS * COLSUM_MAX_N) + 32;
+      colsum_parts_kernel<<<dim3((n_out + 31) / 32, CP_CHUNKS), 256, 0, st>>>(ws.colpart, g_colpart_rows, n_out,
+                                                                               F(c.slabs) + (size_t)slab0 * P + o_b, P, S, cwork, ctick);
       ADDK_CHECK_LAUNCH();
       g_colpart_rows = 0;
       return ADDK_OK;
@@ -1120,13 +1193,8 @@ extern "C" int addk_update_minibatch(void* stream, void* ctx_host, const long lo
     cudaStreamWaitEvent(st, aux->join[1], 0);
   }
   // regularisers (values for the log; their gradients are folded into the slab reduction)
-  sumsq_kernel<<<8, 256, 0, st>>>(W + c.o_d_wl, E2, stats + ST_WL_SQ);
-  ADDK_CHECK_LAUNCH();
-  sumsq_kernel<<<8, 256, 0, st>>>(W + c.o_d_wl, E2, stats + ST_W_SQ);
-  ADDK_CHECK_LAUNCH();
-  sumsq_kernel<<<148, 256, 0, st>>>(W + c.o_d_w0, (long long)E1 * DD, stats + ST_W_SQ);
-  ADDK_CHECK_LAUNCH();
-  sumsq_kernel<<<148, 256, 0, st>>>(W + c.o_d_w1, (long long)E2 * E1, stats + ST_W_SQ);
+  disc_weight_sumsq_kernel<<<dim3(64, 3), 256, 0, st>>>(W + c.o_d_wl, E2, W + c.o_d_w0, (long long)E1 * DD, W + c.o_d_w1,
+                                                        (long long)E2 * E1, stats);
   ADDK_CHECK_LAUNCH();
 
   // ---------------- reduce slabs -> grads, AdamW, diagnostics ----------------
