@@ -54,6 +54,9 @@ struct Params {
   long long c_plane;           //   slot's sticky word W (NULL: not wanted); lo plane c_plane elements after the hi plane
   float c_scale;               // device-side only: filled in by the kernel
   int c16_in_staged;           // persistent kernel in bf16 mode: the shared epilogue helpers also write the bf16 copy C16
+  int no_f32;                  // persistent kernel: the fp32 output is NOT written (C lives only as its 16-bit copy / planes)
+  const uint16_t* mask16;      // persistent kernel: ReLU-mask source as 16-bit values (bf16 copy or fp16 hi plane, pitch ld_mask):
+                               //   element > 0  <=>  sign bit clear and magnitude bits non-zero; used instead of `mask`
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -172,6 +175,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 // earlier shape (4 rows x 128 B per instruction, every warp of every CTA on the same 128-byte column phase at the same
 // time) kept address bits 7-8 constant GPU-wide and drained at 2.7 B/clk/SM (38k of a CTA's 108k cycles); full rows
 // take 11k.
+// ReLU mask of four consecutive elements from 16-bit values (bf16 or fp16: same sign / zero encoding): 1.0 where > 0
+__device__ __forceinline__ float4 mask4_from16(const uint16_t* m) {
+  const uint2 r = __ldg(reinterpret_cast<const uint2*>(m));
+  const uint32_t a = r.x & 0xFFFFu, b = r.x >> 16, c = r.y & 0xFFFFu, d = r.y >> 16;
+  return make_float4((a - 1u) < 0x7FFFu ? 1.f : 0.f, (b - 1u) < 0x7FFFu ? 1.f : 0.f, (c - 1u) < 0x7FFFu ? 1.f : 0.f,
+                     (d - 1u) < 0x7FFFu ? 1.f : 0.f);          // 0x0001 .. 0x7FFF: positive, non-zero (NaN cannot occur here)
+}
+__device__ __forceinline__ bool mask1_from16(const uint16_t* m) { return ((uint32_t)__ldg(m) - 1u) < 0x7FFFu; }
+
 template <int CW>
 __device__ __forceinline__ void stage_put(float4* stg, int lane, int slot, float a, float b, float c, float d) {
   stg[lane * (CW / 4) + (slot ^ (lane & 7))] = make_float4(a, b, c, d);
@@ -208,7 +220,8 @@ __device__ __forceinline__ void store_staged(const Params& p, float* Cz, const f
       m4[u] = make_float4(1.f, 1.f, 1.f, 1.f);
       a4[u] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (grow < p.M && col + 3 < p.N) {
-        if (p.mask) m4[u] = *reinterpret_cast<const float4*>(p.mask + (size_t)grow * p.ld_mask + col);
+        if (p.mask16) m4[u] = mask4_from16(p.mask16 + (size_t)grow * p.ld_mask + col);
+        else if (p.mask) m4[u] = *reinterpret_cast<const float4*>(p.mask + (size_t)grow * p.ld_mask + col);
         if (p.accumulate) a4[u] = *reinterpret_cast<const float4*>(Cz + (size_t)grow * p.ldc + col);
       }
     }
@@ -228,7 +241,7 @@ __device__ __forceinline__ void store_staged(const Params& p, float* Cz, const f
           o.x = m4[u].x > 0.f ? o.x : 0.f; o.y = m4[u].y > 0.f ? o.y : 0.f;
           o.z = m4[u].z > 0.f ? o.z : 0.f; o.w = m4[u].w > 0.f ? o.w : 0.f;
           o.x += a4[u].x; o.y += a4[u].y; o.z += a4[u].z; o.w += a4[u].w;
-          *reinterpret_cast<float4*>(dstp) = o;
+          if (!p.no_f32) *reinterpret_cast<float4*>(dstp) = o;
           if (vmax) *vmax = fmaxf(fmaxf(*vmax, fmaxf(fabsf(o.x), fabsf(o.y))), fmaxf(fabsf(o.z), fabsf(o.w)));
           if (p.c_hi) {
             uint2 h, l;
@@ -244,9 +257,10 @@ __device__ __forceinline__ void store_staged(const Params& p, float* Cz, const f
           const float oo[4] = {o.x, o.y, o.z, o.w};
           for (int e = 0; e < 4 && col + e < p.N; ++e) {
             float xv = oo[e];
-            if (p.mask) xv = p.mask[(size_t)grow * p.ld_mask + col + e] > 0.f ? xv : 0.f;
+            if (p.mask16) xv = mask1_from16(p.mask16 + (size_t)grow * p.ld_mask + col + e) ? xv : 0.f;
+            else if (p.mask) xv = p.mask[(size_t)grow * p.ld_mask + col + e] > 0.f ? xv : 0.f;
             if (p.accumulate) xv += dstp[e];
-            dstp[e] = xv;
+            if (!p.no_f32) dstp[e] = xv;
             if (vmax) *vmax = fmaxf(*vmax, fabsf(xv));
             if (p.c_hi) h3_emit1(p, (size_t)grow * p.ldc + col + e, xv);
             if (p.C16 && p.c16_in_staged) reinterpret_cast<uint16_t*>(p.C16)[(size_t)grow * p.ldc + col + e] = (uint16_t)(pack_bf16x2(xv, 0.f) & 0xFFFFu);
@@ -276,15 +290,23 @@ __device__ __forceinline__ void store_staged_interior(const Params& p, float* __
   uint16_t* dhi = PLANES ? p.c_hi + (size_t)(grow0 + sub_r) * p.ldc + col : nullptr;
   uint16_t* d16 = BF16OUT ? reinterpret_cast<uint16_t*>(p.C16) + (size_t)(grow0 + sub_r) * p.ldc + col : nullptr;
   const float cs = p.c_scale;
-  const float* mk = MASK ? p.mask + (size_t)(grow0 + sub_r) * p.ld_mask + col : nullptr;
+  const bool m16 = MASK && p.mask16 != nullptr;       // uniform
+  const float* mk = (MASK && !m16) ? p.mask + (size_t)(grow0 + sub_r) * p.ld_mask + col : nullptr;
+  const uint16_t* mk16 = m16 ? p.mask16 + (size_t)(grow0 + sub_r) * p.ld_mask + col : nullptr;
   const size_t dstep = (size_t)RPI * p.ldc, mstep = MASK ? (size_t)RPI * p.ld_mask : 0;
+  const bool f32 = !p.no_f32;
   float vm = 0.f;
 #pragma unroll
   for (int i0 = 0; i0 < 32 / RPI; i0 += 8) {
     float4 m4[8];
     if (MASK) {
+      if (m16) {
 #pragma unroll
-      for (int u = 0; u < 8; ++u) m4[u] = __ldg(reinterpret_cast<const float4*>(mk + (size_t)(i0 + u) * mstep));
+        for (int u = 0; u < 8; ++u) m4[u] = mask4_from16(mk16 + (size_t)(i0 + u) * mstep);
+      } else {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) m4[u] = __ldg(reinterpret_cast<const float4*>(mk + (size_t)(i0 + u) * mstep));
+      }
     }
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
@@ -296,7 +318,7 @@ __device__ __forceinline__ void store_staged_interior(const Params& p, float* __
         o.x = m4[u].x > 0.f ? o.x : 0.f; o.y = m4[u].y > 0.f ? o.y : 0.f;
         o.z = m4[u].z > 0.f ? o.z : 0.f; o.w = m4[u].w > 0.f ? o.w : 0.f;
       }
-      *reinterpret_cast<float4*>(dst) = o;
+      if (f32) *reinterpret_cast<float4*>(dst) = o;
       dst += dstep;
       if (PLANES) {
         uint2 h, l;
@@ -327,9 +349,10 @@ __device__ __forceinline__ void store_row_scalar(const Params& p, float* Cz, int
       float xv = acc32[j];
       if (p.bias) xv += p.bias[col];
       if (p.relu) xv = fmaxf(xv, 0.f);
-      if (mk) xv = mk[j] > 0.f ? xv : 0.f;
+      if (p.mask16) xv = mask1_from16(p.mask16 + (size_t)row * p.ld_mask + col) ? xv : 0.f;
+      else if (mk) xv = mk[j] > 0.f ? xv : 0.f;
       if (p.accumulate) xv += dstp[j];
-      dstp[j] = xv;
+      if (!p.no_f32) dstp[j] = xv;
       if (vmax) *vmax = fmaxf(*vmax, fabsf(xv));
       if (p.c_hi) h3_emit1(p, (size_t)row * p.ldc + col, xv);
       if (p.C16 && p.c16_in_staged) reinterpret_cast<uint16_t*>(p.C16)[(size_t)row * p.ldc + col] = (uint16_t)(pack_bf16x2(xv, 0.f) & 0xFFFFu);
@@ -339,7 +362,8 @@ __device__ __forceinline__ void store_row_scalar(const Params& p, float* Cz, int
 __device__ __forceinline__ bool epilogue_vec_ok(const Params& p, const float* Cz) {
   return ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(Cz) & 15) == 0) &&
          (!p.bias || ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0)) &&
-         (!p.mask || (((p.ld_mask & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.mask) & 15) == 0)));
+         (!p.mask || (((p.ld_mask & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.mask) & 15) == 0))) &&
+         (!p.mask16 || (((p.ld_mask & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.mask16) & 7) == 0)));
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1178,7 +1202,7 @@ gemm_tc_h3p_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
       }
       const long long c2 = dbg ? clock64() : 0;
       // ---- epilogue: 32 rows x CPW columns of this warp
-      float* Cz = p.C + (size_t)z * p.slab_stride;
+      float* Cz = p.C ? p.C + (size_t)z * p.slab_stride : nullptr;
       const bool vec = epilogue_vec_ok(p, Cz);
       const int row = m0 + 32 * q + lane;
       const int cw0 = n0 + half * CPW;
@@ -1245,13 +1269,13 @@ gemm_tc_h3p_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
             __syncwarp();
             if (m0 + 32 * q + 32 <= p.M && c0 + C::EPI_COLS <= p.N && !p.accumulate) {     // warp-uniform
               if (SINGLE && p.C16) {
-                if (p.mask) store_staged_interior<C::EPI_COLS, true, false, true>(p, Cz, stg, lane, m0 + 32 * q, c0, vm);
+                if (p.mask || p.mask16) store_staged_interior<C::EPI_COLS, true, false, true>(p, Cz, stg, lane, m0 + 32 * q, c0, vm);
                 else store_staged_interior<C::EPI_COLS, false, false, true>(p, Cz, stg, lane, m0 + 32 * q, c0, vm);
               } else if (!SINGLE && p.c_hi) {
-                if (p.mask) store_staged_interior<C::EPI_COLS, true, true>(p, Cz, stg, lane, m0 + 32 * q, c0, vm);
+                if (p.mask || p.mask16) store_staged_interior<C::EPI_COLS, true, true>(p, Cz, stg, lane, m0 + 32 * q, c0, vm);
                 else store_staged_interior<C::EPI_COLS, false, true>(p, Cz, stg, lane, m0 + 32 * q, c0, vm);
               } else {
-                if (p.mask) store_staged_interior<C::EPI_COLS, true, false>(p, Cz, stg, lane, m0 + 32 * q, c0, vm);
+                if (p.mask || p.mask16) store_staged_interior<C::EPI_COLS, true, false>(p, Cz, stg, lane, m0 + 32 * q, c0, vm);
                 else store_staged_interior<C::EPI_COLS, false, false>(p, Cz, stg, lane, m0 + 32 * q, c0, vm);
               }
             } else {
@@ -1555,12 +1579,16 @@ static int gemm_bf16(cudaStream_t st, const addk_gemm_args& a) {
   p.C = a.C; p.ldc = a.ldc; p.M = a.M; p.N = a.N; p.K = a.K; p.bias = a.bias; p.mask = a.relu_mask_src;
   p.ld_mask = a.ld_mask; p.relu = a.relu; p.accumulate = 0; p.kb_per_split = kb_per;
   p.slab_stride = a.slab_stride > 0 ? a.slab_stride : (long long)a.M * a.ldc;
-  p.pair_flags = 0; p.dbg = nullptr; p.C16 = a.C16; p.c_amax = nullptr; p.c_hi = nullptr; p.c_plane = 0; p.c_scale = 1.f; p.c16_in_staged = 0;
+  p.pair_flags = 0; p.dbg = nullptr; p.C16 = a.C16; p.c_amax = nullptr; p.c_hi = nullptr; p.c_plane = 0; p.c_scale = 1.f; p.c16_in_staged = 0; p.no_f32 = 0; p.mask16 = nullptr;
   p.a_mn = a.trans_a ? 1 : 0;
   p.b_mn = a.trans_b ? 0 : 1;
   const int BN = a.N > 128 ? 256 : (a.N > 64 ? 128 : 64);
   const int persistent = addk_switches().bf16_persistent;
-  if (BN == 256 && persistent && a.C && split == 1) {     // (split-K weight gradients: the one-tile-per-CTA kernel is faster, 54 vs 62 us)
+  if ((a.no_f32 || a.relu_mask_src16) && !(BN == 256 && persistent && split == 1 && a.C16)) {
+    addk_set_error("gemm bf16: no_f32 / relu_mask_src16 need the persistent kernel (N > 128, one slab) and a bf16 output");
+    return ADDK_ERR_ARG;
+  }
+  if (BN == 256 && persistent && (a.C || a.no_f32) && split == 1) {     // (split-K weight gradients: the one-tile-per-CTA kernel is faster, 54 vs 62 us)
     // the persistent kernel of the f16x3 mode with one plane per operand: 32-k blocks, 6 stages, the accumulator of a
     // whole tile is one chunk (no precision drains), the epilogue of a tile overlaps the next tile's MMAs
     const int kbt = (a.K + 31) / 32;
@@ -1568,6 +1596,8 @@ static int gemm_bf16(cudaStream_t st, const addk_gemm_args& a) {
     if ((long long)kbp * (split - 1) < kbt) {
       ParamsP pp;
       pp.p = p; pp.p.kb_per_split = kbp; pp.p.c16_in_staged = 1;
+      pp.p.no_f32 = a.no_f32 ? 1 : 0;
+      if (a.relu_mask_src16) { pp.p.mask16 = reinterpret_cast<const uint16_t*>(a.relu_mask_src16); pp.p.mask = nullptr; }
       pp.a_amax = nullptr; pp.b_amax = nullptr; pp.comp_per_mma = 0.f; pp.chunk_kb = kbp; pp.bf16 = 1;
       CUtensorMap tah, tbh;
       bool okp = p.a_mn ? make_map_f16(&tah, a.A16, a.M, a.K, a.lda, 64, 32, true) : make_map_f16(&tah, a.A16, a.K, a.M, a.lda, 32, BM, true);
@@ -1656,7 +1686,7 @@ static int gemm_h3(cudaStream_t st, const addk_gemm_args& a) {
   p.slab_stride = a.slab_stride > 0 ? a.slab_stride : (long long)a.M * a.ldc;
   p.pair_flags = addk_switches().h3_flags;
   p.dbg = g_addk_stamps; p.C16 = nullptr; p.c_amax = split == 1 ? a.c_amax : nullptr;
-  p.c_hi = nullptr; p.c_plane = 0; p.c_scale = 1.f; p.c16_in_staged = 0;
+  p.c_hi = nullptr; p.c_plane = 0; p.c_scale = 1.f; p.c16_in_staged = 0; p.no_f32 = 0; p.mask16 = nullptr;
   p.a_mn = a.trans_a ? 1 : 0;
   p.b_mn = a.trans_b ? 0 : 1;
   ph.a_amax = a.a_amax; ph.b_amax = a.b_amax; ph.comp_per_mma = addk_h3_comp();
@@ -1695,6 +1725,17 @@ static int gemm_h3(cudaStream_t st, const addk_gemm_args& a) {
   if (BN == 256) return launch_h3<256>(st, tah, tal, tbh, tbl, ph, grid);
   if (BN == 128) return launch_h3<128>(st, tah, tal, tbh, tbl, ph, grid);
   return launch_h3<64>(st, tah, tal, tbh, tbl, ph, grid);
+}
+
+extern "C" int addk_gemm_is_persistent(const addk_gemm_args* a, int precision) {
+  if (!a) return 0;
+  const int split = a->split_k > 1 ? a->split_k : 1;
+  if (precision == 3) return (a->N > 128 && split == 1 && addk_switches().bf16_persistent) ? 1 : 0;
+  if (precision == 4) {
+    if (a->N <= 128 || !addk_switches().h3_persistent) return 0;
+    return ((long long)((a->M + addk_tc::BM - 1) / addk_tc::BM) * ((a->N + 255) / 256) * split > 37) ? 1 : 0;
+  }
+  return 0;
 }
 
 // Without the legacy tf32x3 kernels (default build) a call the fp16 / bf16 tiles cannot take runs on the exact-fp32
@@ -1760,7 +1801,7 @@ int addk_gemm_tc(cudaStream_t st, const addk_gemm_args& a, int precision) {
   p.slab_stride = a.slab_stride > 0 ? a.slab_stride : (long long)a.M * a.ldc;
   p.pair_flags = addk_switches().tc_pair_flags;
   p.dbg = g_addk_stamps;
-  p.C16 = nullptr; p.c_amax = nullptr; p.c_hi = nullptr; p.c_plane = 0; p.c_scale = 1.f; p.c16_in_staged = 0;
+  p.C16 = nullptr; p.c_amax = nullptr; p.c_hi = nullptr; p.c_plane = 0; p.c_scale = 1.f; p.c16_in_staged = 0; p.no_f32 = 0; p.mask16 = nullptr;
   p.a_mn = a.trans_a ? 1 : 0;          // A given as [K,M]: rows are the contraction index
   p.b_mn = a.trans_b ? 0 : 1;          // B given as [K,N]
   const int BN = a.N > 128 ? 256 : (a.N > 64 ? 128 : 64);

@@ -364,7 +364,18 @@ __global__ void sumsq_kernel(const float* __restrict__ x, long long n, double* _
 // to slab 0 and zeroes slabs 1..nsplit-1 so the common slab reduction stays valid.  Deterministic, no float atomics.
 constexpr int COLSUM_CHUNKS = 64;
 constexpr int COLSUM_MAX_N = 1024;
-__global__ void __launch_bounds__(256) colsum_slabs_kernel(const float* __restrict__ dY, int ld, int rows, int n,
+// IN16: dY is read from its bf16 copy (a tensor that has no fp32 copy, precision "bf16")
+__device__ __forceinline__ float4 ld_row4(const float* p) { return ldg4(p); }
+__device__ __forceinline__ float4 ld_row4(const uint16_t* p) {
+  const uint2 r = __ldg(reinterpret_cast<const uint2*>(p));
+  return make_float4(__uint_as_float(r.x << 16), __uint_as_float(r.x & 0xFFFF0000u), __uint_as_float(r.y << 16),
+                     __uint_as_float(r.y & 0xFFFF0000u));
+}
+__device__ __forceinline__ float ld_row1(const float* p) { return *p; }
+__device__ __forceinline__ float ld_row1(const uint16_t* p) { return __uint_as_float((uint32_t)*p << 16); }
+
+template <typename TIN>
+__global__ void __launch_bounds__(256) colsum_slabs_kernel(const TIN* __restrict__ dY, int ld, int rows, int n,
                                                            float* __restrict__ out, long long slab_stride, int nsplit,
                                                            const float* __restrict__ rw, float* __restrict__ work,
                                                            unsigned int* __restrict__ tickets) {
@@ -379,8 +390,8 @@ __global__ void __launch_bounds__(256) colsum_slabs_kernel(const float* __restri
     if (col + 3 < n && (ld & 3) == 0) {
       int r = r0 + rl;
       for (; r + 24 < r1; r += 32) {          // 4 independent 128-bit loads in flight per thread
-        const float4 v0 = ldg4(dY + (size_t)r * ld + col), v1 = ldg4(dY + (size_t)(r + 8) * ld + col);
-        const float4 v2 = ldg4(dY + (size_t)(r + 16) * ld + col), v3 = ldg4(dY + (size_t)(r + 24) * ld + col);
+        const float4 v0 = ld_row4(dY + (size_t)r * ld + col), v1 = ld_row4(dY + (size_t)(r + 8) * ld + col);
+        const float4 v2 = ld_row4(dY + (size_t)(r + 16) * ld + col), v3 = ld_row4(dY + (size_t)(r + 24) * ld + col);
         const float w0 = rw ? rw[r] : 1.f, w1 = rw ? rw[r + 8] : 1.f, w2 = rw ? rw[r + 16] : 1.f, w3 = rw ? rw[r + 24] : 1.f;
         acc.x = fmaf(w0, v0.x, acc.x); acc.y = fmaf(w0, v0.y, acc.y); acc.z = fmaf(w0, v0.z, acc.z); acc.w = fmaf(w0, v0.w, acc.w);
         acc.x = fmaf(w1, v1.x, acc.x); acc.y = fmaf(w1, v1.y, acc.y); acc.z = fmaf(w1, v1.z, acc.z); acc.w = fmaf(w1, v1.w, acc.w);
@@ -388,18 +399,18 @@ __global__ void __launch_bounds__(256) colsum_slabs_kernel(const float* __restri
         acc.x = fmaf(w3, v3.x, acc.x); acc.y = fmaf(w3, v3.y, acc.y); acc.z = fmaf(w3, v3.z, acc.z); acc.w = fmaf(w3, v3.w, acc.w);
       }
       for (; r < r1; r += 8) {
-        const float4 v = ldg4(dY + (size_t)r * ld + col);
+        const float4 v = ld_row4(dY + (size_t)r * ld + col);
         const float w = rw ? rw[r] : 1.f;
         acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y); acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
       }
     } else {
       for (int r = r0 + rl; r < r1; r += 8) {
-        const float* q = dY + (size_t)r * ld + col;
+        const TIN* q = dY + (size_t)r * ld + col;
         const float w = rw ? rw[r] : 1.f;
-        acc.x = fmaf(w, q[0], acc.x);
-        if (col + 1 < n) acc.y = fmaf(w, q[1], acc.y);
-        if (col + 2 < n) acc.z = fmaf(w, q[2], acc.z);
-        if (col + 3 < n) acc.w = fmaf(w, q[3], acc.w);
+        acc.x = fmaf(w, ld_row1(q), acc.x);
+        if (col + 1 < n) acc.y = fmaf(w, ld_row1(q + 1), acc.y);
+        if (col + 2 < n) acc.z = fmaf(w, ld_row1(q + 2), acc.z);
+        if (col + 3 < n) acc.w = fmaf(w, ld_row1(q + 3), acc.w);
       }
     }
   }
@@ -698,13 +709,17 @@ static thread_local float* g_colpart_buf = nullptr;
 static thread_local int g_colpart_rows = 0;
 
 static int colsum(cudaStream_t st, const addk_update_ctx& c, const ChainWs& ws, const float* dY, int ld, int rows, int n,
-                  float* out, const float* rw) {
+                  float* out, const float* rw, const uint16_t* dY16 = nullptr) {
   using addk::COLSUM_MAX_N; using addk::COLSUM_CHUNKS;
   if (n > COLSUM_MAX_N) { addk_set_error("colsum: more than 1024 columns"); return ADDK_ERR_UNSUPPORTED; }
   float* work = ws.colsum_work;
   unsigned int* tickets = (unsigned int*)(work + (size_t)COLSUM_CHUNKS * COLSUM_MAX_N);
-  addk::colsum_slabs_kernel<<<dim3((n + 127) / 128, COLSUM_CHUNKS), 256, 0, st>>>(dY, ld, rows, n, out, c.num_params,
-                                                                         (int)c.split_k, rw, work, tickets);
+  if (dY16 && (ld & 3) == 0)      // the tensor has no fp32 copy (precision "bf16"): read its bf16 copy
+    addk::colsum_slabs_kernel<uint16_t><<<dim3((n + 127) / 128, COLSUM_CHUNKS), 256, 0, st>>>(dY16, ld, rows, n, out, c.num_params,
+                                                                                     (int)c.split_k, rw, work, tickets);
+  else
+    addk::colsum_slabs_kernel<float><<<dim3((n + 127) / 128, COLSUM_CHUNKS), 256, 0, st>>>(dY, ld, rows, n, out, c.num_params,
+                                                                                  (int)c.split_k, rw, work, tickets);
   ADDK_CHECK_LAUNCH();
   return ADDK_OK;
 }
@@ -832,11 +847,27 @@ static uint16_t* twin16(const void* p) {
   return nullptr;
 }
 
+enum { F16_DROP_C = 1, F16_MASK = 2 };
+static bool drop16_enabled() { return addk_switches().bf16_drop_f32 != 0; }
+// would a [rows, cols] layer output be 16-bit only in this mode?  (same rule as gemm(): bf16 mode, persistent kernel)
+static bool is_16only(const addk_update_ctx& c, long long rows, int cols) {
+  if (c.precision != 3 || !drop16_enabled() || !c.arena16) return false;
+  // every consumer must be able to run on the 16-bit copy: the split-K weight gradient (contraction over the rows) needs
+  // at least one 64-row k-block per slab, otherwise it falls back to the fp32 operands
+  if (rows < 64 * c.split_k) return false;
+  addk_gemm_args a{};
+  a.M = (int)rows; a.N = cols; a.split_k = 1;
+  return addk_gemm_is_persistent(&a, 3) != 0;
+}
+
 static int gemm(cudaStream_t st, int prec, const float* A, int lda, int ta, const float* B, int ldb, int tb, float* C,
                 int ldc, int M, int N, int K, const float* bias = nullptr, int relu = 0, const float* mask = nullptr,
                 int ld_mask = 0, int split = 1, const float* nmean = nullptr, const float* nstd = nullptr,
-                long long slab_stride = 0) {
+                long long slab_stride = 0, int flags16 = 0) {
+  // flags16 (precision "bf16"): F16_DROP_C -- C is only ever read by dense layers / as a ReLU mask / by colsum: do not
+  // write its fp32 copy when the persistent kernel runs; F16_MASK -- the mask source was produced that way: read its bf16 copy
   addk_gemm_args a;
+  a.relu_mask_src16 = nullptr; a.no_f32 = 0;
   a.A16 = prec == 3 ? twin16(A) : nullptr; a.B16 = prec == 3 ? twin16(B) : nullptr; a.C16 = prec == 3 ? twin16(C) : nullptr;
   a.a16_plane = a.b16_plane = a.c16_plane = 0; a.a_amax = a.b_amax = a.c_amax = nullptr; a.a16_ready = a.b16_ready = 0;
   int c_ent = -1;
@@ -881,16 +912,18 @@ static int gemm(cudaStream_t st, int prec, const float* A, int lda, int ta, cons
           // Letting the epilogue write C's planes too (sticky scale word, prep -> layer -> repair) is implemented and
           // tested but off: measured at 4096 envs it removes 0.18 ms of split passes per optimizer step and adds 0.25 ms
           // to the dense layers (the epilogue's 8-byte stores are far from the split kernel's 6 TB/s).
-          const int fused = addk_switches().h3_fused_planes;
+          // fused = 2: only behind a long contraction (K >= 1024), where the worker warps wait for the tensor core anyway
+          const int fused_sw = addk_switches().h3_fused_planes;
+          const bool fused = fused_sw && N > 128 && (ldc & 7) == 0 && (fused_sw != 2 || K >= 1024);
           bool ready = false;
           if (!fused && g_next_slot < TWIN_SLOTS) { g_tw[e].slot = g_next_slot++; ready = true; }     // zeroed by h3_params
           else { g_tw[e].slot = e; }
           uint32_t* slot = twin_slot(c, e);
-          if (ready || addk_f16x3_prep(st, slot, fused) == ADDK_OK) {     // max <- 0, W <- scale in force | 0
+          if (ready || addk_f16x3_prep(st, slot, fused ? 1 : 0) == ADDK_OK) {     // max <- 0, W <- scale in force | 0
             TwinEnt& t = g_tw[e];
             t.rows = M; t.cols = N; t.ld = ldc; t.st = st; t.valid = false; t.shared = false; t.amax_known = true;
             a.c_amax = slot;
-            if (fused && N > 128 && (ldc & 7) == 0) {     // the persistent kernel also writes C's planes in its epilogue
+            if (fused) {     // the persistent kernel also writes C's planes in its epilogue
               a.C16 = (uint16_t*)c.arena16 + (C - a0); a.c16_plane = c.arena_elems;
               c_ent = e;
             }
@@ -898,6 +931,10 @@ static int gemm(cudaStream_t st, int prec, const float* A, int lda, int ta, cons
         }
       }
     }
+  }
+  if (prec == 3 && flags16 && a.A16 && a.B16 && a.C16 && g_twin_ctx && is_16only(*g_twin_ctx, M, N)) {
+    if (flags16 & F16_DROP_C) a.no_f32 = 1;
+    if ((flags16 & F16_MASK) && mask) { a.relu_mask_src16 = twin16(mask); if (a.relu_mask_src16) a.relu_mask_src = nullptr; }
   }
   int rc = prec == 0 ? addk::sgemm_launch(st, a) : addk_gemm_tc(st, a, prec);
   if (rc != ADDK_OK) return rc;
@@ -913,7 +950,7 @@ static int gemm(cudaStream_t st, int prec, const float* A, int lda, int ta, cons
 
 // weight gradient dW[N_out, K_in] = dY^T X and bias gradient db = 1^T dY, as split-K slabs
 static int wgrad(cudaStream_t st, const Ctx& c, const ChainWs& ws, const float* dY, int ldy, const float* X, int ldx,
-                 int rows, int n_out, int k_in, long long o_w, long long o_b, int slab0) {
+                 int rows, int n_out, int k_in, long long o_w, long long o_b, int slab0, bool dy_16only = false) {
   const int S = (int)c.split_k;
   const long long P = c.num_params;
   if (n_out == 1 && ldy == 1) {
@@ -941,7 +978,8 @@ static int wgrad(cudaStream_t st, const Ctx& c, const ChainWs& ws, const float* 
     }
   }
   if (o_b >= 0) {
-    TRY(colsum(st, c, ws, dY, ldy, rows, n_out, F(c.slabs) + (size_t)slab0 * P + o_b, nullptr));
+    const uint16_t* dY16 = (dy_16only && is_16only(c, rows, n_out)) ? twin16(dY) : nullptr;
+    TRY(colsum(st, c, ws, dY, ldy, rows, n_out, F(c.slabs) + (size_t)slab0 * P + o_b, nullptr, dY16));
   }
   return ADDK_OK;
 }
@@ -987,9 +1025,10 @@ static int trunk_forward(cudaStream_t st, const Ctx& c, const ChainWs& ws, const
     ADDK_CHECK_LAUNCH();
     W0 = w0_pad; ldw = OL;
   }
+  // (h1, h2 are read by dense layers and as ReLU masks only: 16-bit only in bf16 mode)
   TRY(gemm(st, nmean ? 0 : pr, X, ldx, 0, W0, ldw, 1, ws.h1, H1, rows, H1, in_dim, P + o_b0, 1, nullptr, 0, 1,
-           nmean, nstd));
-  TRY(gemm(st, pr, ws.h1, H1, 0, P + o_w1, H1, 1, ws.h2, H2, rows, H2, H1, P + o_b1, 1));
+           nmean, nstd, 0, F16_DROP_C));
+  TRY(gemm(st, pr, ws.h1, H1, 0, P + o_w1, H1, 1, ws.h2, H2, rows, H2, H1, P + o_b1, 1, nullptr, 0, 1, nullptr, nullptr, 0, F16_DROP_C));
   TRY(gemm(st, pr, ws.h2, H2, 0, P + o_w2, H2, 1, ws.h3, H3, rows, H3, H2, P + o_b2, 1));
   return ADDK_OK;
 }
@@ -1000,10 +1039,11 @@ static int trunk_backward(cudaStream_t st, const Ctx& c, const ChainWs& ws, cons
   const float* P = F(c.params);
   const int H1 = (int)c.hid_a1, H2 = (int)c.hid_a2, H3 = (int)c.hid_a3, pr = (int)c.precision;
   TRY(wgrad(st, c, ws, ws.g3, H3, ws.h2, H2, rows, H3, H2, o_w2, o_b2, 0));
-  TRY(gemm(st, pr, ws.g3, H3, 0, P + o_w2, H2, 0, ws.g2, H2, rows, H2, H3, nullptr, 0, ws.h2, H2));
-  TRY(wgrad(st, c, ws, ws.g2, H2, ws.h1, H1, rows, H2, H1, o_w1, o_b1, 0));
-  TRY(gemm(st, pr, ws.g2, H2, 0, P + o_w1, H1, 0, ws.g1, H1, rows, H1, H2, nullptr, 0, ws.h1, H1));
-  TRY(wgrad(st, c, ws, ws.g1, H1, X, ldx, rows, H1, in_dim, o_w0, o_b0, 0));
+  // (g2, g1: dense-layer operands + bias column sums only; their masks h2, h1 have no fp32 copy in bf16 mode)
+  TRY(gemm(st, pr, ws.g3, H3, 0, P + o_w2, H2, 0, ws.g2, H2, rows, H2, H3, nullptr, 0, ws.h2, H2, 1, nullptr, nullptr, 0, F16_DROP_C | F16_MASK));
+  TRY(wgrad(st, c, ws, ws.g2, H2, ws.h1, H1, rows, H2, H1, o_w1, o_b1, 0, true));
+  TRY(gemm(st, pr, ws.g2, H2, 0, P + o_w1, H1, 0, ws.g1, H1, rows, H1, H2, nullptr, 0, ws.h1, H1, 1, nullptr, nullptr, 0, F16_DROP_C | F16_MASK));
+  TRY(wgrad(st, c, ws, ws.g1, H1, X, ldx, rows, H1, in_dim, o_w0, o_b0, 0, true));
   return ADDK_OK;
 }
 
@@ -1150,7 +1190,7 @@ extern "C" int addk_update_minibatch(void* stream, void* ctx_host, const long lo
   const float* Wd0 = F(c.wd0_pad);
   pad_rows_kernel<<<(E1 * DL + 255) / 256, 256, 0, sd>>>(W + c.o_d_w0, E1, DD, DL, F(c.wd0_pad), twin16(c.wd0_pad));
   ADDK_CHECK_LAUNCH();
-  TRY(gemm(sd, pr, F(c.dn), DL, 0, Wd0, DL, 1, e1, E1, R, E1, DL, W + c.o_d_b0, 1));
+  TRY(gemm(sd, pr, F(c.dn), DL, 0, Wd0, DL, 1, e1, E1, R, E1, DL, W + c.o_d_b0, 1, nullptr, 0, 1, nullptr, nullptr, 0, F16_DROP_C));
   TRY(gemm(sd, pr, e1, E1, 0, W + c.o_d_w1, E1, 1, e2, E2, R, E2, E1, W + c.o_d_b1, 1));
   TRY(head1_forward(sd, e2, E2, R, E2, W + c.o_d_wl, W + c.o_d_bl, pred_d));
   disc_loss_kernel<<<(R + 255) / 256, 256, 0, sd>>>(pred_d, M, (float)c.disc_loss_weight, dpred_d, stats);
@@ -1166,7 +1206,7 @@ extern "C" int addk_update_minibatch(void* stream, void* ctx_host, const long lo
     ADDK_CHECK_LAUNCH();
   }
   // input-gradient chain: u1 = m1 * (u2 W2), gx = u1 W1
-  TRY(gemm(sd, pr, F(c.u2), E2, 0, W + c.o_d_w1, E1, 0, F(c.u1), E1, R, E1, E2, nullptr, 0, e1, E1));
+  TRY(gemm(sd, pr, F(c.u2), E2, 0, W + c.o_d_w1, E1, 0, F(c.u1), E1, R, E1, E2, nullptr, 0, e1, E1, 1, nullptr, nullptr, 0, F16_DROP_C | F16_MASK));
   TRY(gemm(sd, pr, F(c.u1), E1, 0, Wd0, DL, 0, F(c.gx), DL, R, DL, E1));
   uint16_t* const dg16 = twin16(c.dg);
   grad_penalty_kernel<<<(R + 7) / 8, 256, 0, sd>>>(F(c.gx), M, R, DD, DL,
@@ -1176,7 +1216,7 @@ extern "C" int addk_update_minibatch(void* stream, void* ctx_host, const long lo
   // backward of the chain (second set of slabs)
   TRY(gemm(sd, pr, F(c.u1), E1, 1, F(c.dg), DL, 0, F(c.slabs) + (size_t)S * P + c.o_d_w0, DD, E1, DD, R, nullptr, 0,
            nullptr, 0, S, nullptr, nullptr, P));
-  TRY(gemm(sd, pr, F(c.dg), DL, 0, Wd0, DL, 1, dv1, E1, R, E1, DL, nullptr, 0, e1, E1));
+  TRY(gemm(sd, pr, F(c.dg), DL, 0, Wd0, DL, 1, dv1, E1, R, E1, DL, nullptr, 0, e1, E1, 1, nullptr, nullptr, 0, F16_DROP_C | F16_MASK));
   TRY(gemm(sd, pr, F(c.u2), E2, 1, dv1, E1, 0, F(c.slabs) + (size_t)S * P + c.o_d_w1, E1, E2, E1, R, nullptr, 0, nullptr, 0,
            S, nullptr, nullptr, P));
   TRY(gemm(sd, pr, dv1, E1, 0, W + c.o_d_w1, E1, 1, du2, E2, R, E2, E1, nullptr, 0, e2, E2));
@@ -1184,8 +1224,8 @@ extern "C" int addk_update_minibatch(void* stream, void* ctx_host, const long lo
   // ordinary backward of the BCE terms
   TRY(wgrad(sd, c, wd, dpred_d, 1, e2, E2, R, 1, E2, c.o_d_wl, c.o_d_bl, 0));
   TRY(wgrad(sd, c, wd, dh2, E2, e1, E1, R, E2, E1, c.o_d_w1, c.o_d_b1, 0));
-  TRY(gemm(sd, pr, dh2, E2, 0, W + c.o_d_w1, E1, 0, F(c.u1), E1, R, E1, E2, nullptr, 0, e1, E1));
-  TRY(wgrad(sd, c, wd, F(c.u1), E1, F(c.dn), DL, R, E1, DD, c.o_d_w0, c.o_d_b0, 0));
+  TRY(gemm(sd, pr, dh2, E2, 0, W + c.o_d_w1, E1, 0, F(c.u1), E1, R, E1, E2, nullptr, 0, e1, E1, 1, nullptr, nullptr, 0, F16_DROP_C | F16_MASK));
+  TRY(wgrad(sd, c, wd, F(c.u1), E1, F(c.dn), DL, R, E1, DD, c.o_d_w0, c.o_d_b0, 0, true));
   if (multi) {
     cudaEventRecord(aux->join[0], sc);
     cudaEventRecord(aux->join[1], sd);
@@ -1297,7 +1337,7 @@ extern "C" int addk_disc_eval(void* stream, void* ctx_host, const float* disc_ob
     diff_normalize_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(disc_obs + r0 * DD, disc_obs_demo + r0 * DD,
                                                                         F(c.disc_mean_abs), rows, DD, DL, F(c.gx), twin16(c.gx));
     ADDK_CHECK_LAUNCH();
-    TRY(gemm(st, pr, F(c.gx), DL, 0, F(c.wd0_pad), DL, 1, e1, E1, rows, E1, DL, W + c.o_d_b0, 1));
+    TRY(gemm(st, pr, F(c.gx), DL, 0, F(c.wd0_pad), DL, 1, e1, E1, rows, E1, DL, W + c.o_d_b0, 1, nullptr, 0, 1, nullptr, nullptr, 0, F16_DROP_C));
     TRY(gemm(st, pr, e1, E1, 0, W + c.o_d_w1, E1, 1, e2, E2, rows, E2, E1, W + c.o_d_b1, 1));
     TRY(head1_forward(st, e2, E2, rows, E2, W + c.o_d_wl, W + c.o_d_bl, logits + r0));
   }

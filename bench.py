@@ -562,6 +562,8 @@ def dominant_kernel_roofline(agent, args, tc_peak, peak_src):
                               ld_mask=0, trans_a=0, trans_b=1, relu=1, split_k=1, accumulate=0, slab_stride=0,
                               A16=A16[i % nbuf].data_ptr() if (bf16 or h3) else None, B16=W16.data_ptr() if (bf16 or h3) else None,
                               C16=C16[i % 2].data_ptr() if bf16 else None)
+        if bf16:      # as in the update: a hidden layer's output is read by dense layers / as a mask only -> 16-bit only
+            a.no_f32 = 1
         if h3:
             a.a16_plane, a.b16_plane = M * Kd, Nd * Kd
             a.a_amax, a.b_amax = slots[2 * (1 + i % nbuf):].data_ptr(), slots.data_ptr()

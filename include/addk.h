@@ -258,7 +258,16 @@ typedef struct addk_gemm_args {
   int64_t c16_plane;                 /* optional, with C16 + c_amax, N > 128: the epilogue also writes C's fp16 planes with the
                                       * scale of the slot's sticky word [0]; addk_f16x3_repair afterwards rewrites them in
                                       * the rare case that scale does not fit max|C|; then readers of C pass ready = 1 */
+  /* 16-bit-only tensors (layers wider than 128 outputs, single slab: the persistent kernels).  no_f32 = 1: the fp32
+   * output is NOT written -- C lives only as its 16-bit copy C16 (precision "bf16"); C may then be NULL.
+   * relu_mask_src16: the ReLU-mask source as 16-bit values (bf16 copy / fp16 hi plane of a tensor that has no fp32
+   * copy), pitch ld_mask ELEMENTS, used instead of relu_mask_src: element > 0 <=> sign clear and magnitude non-zero. */
+  const void* relu_mask_src16;
+  int32_t no_f32;
 } addk_gemm_args;
+/* 1 if addk_gemm would run this call on a persistent tensor-core kernel (the only ones that honour no_f32 /
+ * relu_mask_src16), given 16-bit operands TMA can address */
+int addk_gemm_is_persistent(const addk_gemm_args* args_host, int precision);
 int addk_gemm(void* stream, const addk_gemm_args* args_host, int precision);
 /* precision "f16x3": max|x| of the [rows, cols] fp32 tensor x (pitch ld) -> *amax_slot (bit pattern), then the two
  * fp16 planes hi16[0 .. rows*ld) and hi16[plane .. plane + rows*ld) described above.  Three stream-ordered operations. */

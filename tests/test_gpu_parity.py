@@ -31,6 +31,11 @@ def _need_legacy(precision):
         pytest.skip("precision %s: superseded kernels, only in libaddk_legacy.so (make LEGACY=1, ADDK_LIB=...)" % precision)
 
 
+def _lib_mod():
+    from add_gym_b200 import _lib
+    return _lib
+
+
 def _gpu_relu_masks(agent):
     """ReLU masks (activation > 0) of the optimizer step that just ran, read from the three chains' workspaces
     (update_streams = 3: every chain keeps its own activations).  Keys as OracleAgent.loss(masks=...)."""
@@ -38,8 +43,17 @@ def _gpu_relu_masks(agent):
     H, E = m.hidden
     assert agent._ctx.ints["n_streams"] == 3
 
+    # bf16 mode: h1 / h2 / e1 of every chain exist only as their bf16 copies (same element offsets in the 16-bit arena)
+    # (when every consumer can read them: at least 64 rows per split-K slab of the weight gradients, csrc/mlp.cu is_16only)
+    bf16 = m.precision == _lib_mod().PRECISIONS["bf16"] and M >= 64 * agent._ctx.ints["split_k"]
+    only16 = {"h1", "h2", "c_h1", "c_h2", "d_e1"} if bf16 else set()
+
     def g(key, width, r0, r1):
-        return (ws[key].flatten()[:(M + 1) * width].view(M + 1, width)[r0:r1] > 0).cpu()
+        t = ws[key]
+        if key in only16:
+            off = (t.data_ptr() - agent._arena.data_ptr()) // 4
+            t = agent._arena16[off:off + t.numel()]
+        return (t.flatten()[:(M + 1) * width].view(M + 1, width)[r0:r1] > 0).cpu()
     return {"actor": [g("h1", H[0], 0, M), g("h2", H[1], 0, M), g("h3", H[2], 0, M)],
             "critic": [g("c_h1", H[0], 0, M), g("c_h2", H[1], 0, M), g("c_h3", H[2], 0, M)],
             "disc": [g("d_e1", E[0], 0, M), g("d_e2", E[1], 0, M)],
