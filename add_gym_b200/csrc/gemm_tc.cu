@@ -908,7 +908,9 @@ gemm_tc_h3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
 // the fill to 32 KB per block (and make room for 5 stages instead of 3).
 template <int BN, bool SINGLE = false, bool PAIR = false>    // SINGLE: one 16-bit plane per operand and one MMA per 16 k (precision "bf16")
 struct CfgP {
-  static constexpr int BK = 32;
+  // k-block: 32 elements (64-byte rows, SWIZZLE_64B) with two planes per operand; the one-plane (bf16) kernel takes 64
+  // (128-byte rows, SWIZZLE_128B): half as many TMA row requests per byte -- its main loop waited for its loads
+  static constexpr int BK = SINGLE ? 64 : 32;
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_ROWS = PAIR ? BN / 2 : BN;            // rows of B this CTA stages
   static constexpr int B_BYTES = B_ROWS * BK * 2;
@@ -1087,7 +1089,8 @@ gemm_tc_h3p_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
                            ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
     const uint32_t a_lbo = p.a_mn ? C::MN_BOX_BYTES : 16u, b_lbo = p.b_mn ? C::MN_BOX_BYTES : 16u;
     const uint32_t a_sbo = p.a_mn ? 1024u : C::K_SBO, b_sbo = p.b_mn ? 1024u : C::K_SBO;
-    const uint32_t a_lay = p.a_mn ? 2u : 4u, b_lay = p.b_mn ? 2u : 4u;
+    constexpr uint32_t K_LAY = BK == 64 ? 2u : 4u;            // K-major tiles: SWIZZLE_128B (128-byte rows) | SWIZZLE_64B
+    const uint32_t a_lay = p.a_mn ? 2u : K_LAY, b_lay = p.b_mn ? 2u : K_LAY;
     const uint64_t dA0 = smem_desc(a_hi(0), a_lbo, a_sbo, a_lay);
     const uint64_t dB0 = smem_desc(b_hi(0), b_lbo, b_sbo, b_lay);
     const uint64_t a_k16 = p.a_mn ? (2048u >> 4) : (32u >> 4), b_k16 = p.b_mn ? (2048u >> 4) : (32u >> 4);
@@ -1579,7 +1582,7 @@ static int gemm_bf16(cudaStream_t st, const addk_gemm_args& a) {
   p.C = a.C; p.ldc = a.ldc; p.M = a.M; p.N = a.N; p.K = a.K; p.bias = a.bias; p.mask = a.relu_mask_src;
   p.ld_mask = a.ld_mask; p.relu = a.relu; p.accumulate = 0; p.kb_per_split = kb_per;
   p.slab_stride = a.slab_stride > 0 ? a.slab_stride : (long long)a.M * a.ldc;
-  p.pair_flags = 0; p.dbg = nullptr; p.C16 = a.C16; p.c_amax = nullptr; p.c_hi = nullptr; p.c_plane = 0; p.c_scale = 1.f; p.c16_in_staged = 0; p.no_f32 = 0; p.mask16 = nullptr;
+  p.pair_flags = 0; p.dbg = g_addk_stamps; p.C16 = a.C16; p.c_amax = nullptr; p.c_hi = nullptr; p.c_plane = 0; p.c_scale = 1.f; p.c16_in_staged = 0; p.no_f32 = 0; p.mask16 = nullptr;
   p.a_mn = a.trans_a ? 1 : 0;
   p.b_mn = a.trans_b ? 0 : 1;
   const int BN = a.N > 128 ? 256 : (a.N > 64 ? 128 : 64);
@@ -1588,10 +1591,11 @@ static int gemm_bf16(cudaStream_t st, const addk_gemm_args& a) {
     addk_set_error("gemm bf16: no_f32 / relu_mask_src16 need the persistent kernel (N > 128, one slab) and a bf16 output");
     return ADDK_ERR_ARG;
   }
-  if (BN == 256 && persistent && (a.C || a.no_f32) && split == 1) {     // (split-K weight gradients: the one-tile-per-CTA kernel is faster, 54 vs 62 us)
+  // (split-K weight gradients too since the 64-k blocks and the CTA pairs: 57 -> see profiles/r02_SUMMARY.md)
+  if (BN == 256 && persistent && (a.C || a.no_f32) && (split == 1 || a.M > BM)) {     // (split-K weight gradients: the one-tile-per-CTA kernel is faster, 54 vs 62 us)
     // the persistent kernel of the f16x3 mode with one plane per operand: 32-k blocks, 6 stages, the accumulator of a
     // whole tile is one chunk (no precision drains), the epilogue of a tile overlaps the next tile's MMAs
-    const int kbt = (a.K + 31) / 32;
+    const int kbt = (a.K + 63) / 64;                 // the one-plane persistent kernel walks 64-k blocks
     const int kbp = (kbt + split - 1) / split;
     if ((long long)kbp * (split - 1) < kbt) {
       ParamsP pp;
@@ -1600,11 +1604,11 @@ static int gemm_bf16(cudaStream_t st, const addk_gemm_args& a) {
       if (a.relu_mask_src16) { pp.p.mask16 = reinterpret_cast<const uint16_t*>(a.relu_mask_src16); pp.p.mask = nullptr; }
       pp.a_amax = nullptr; pp.b_amax = nullptr; pp.comp_per_mma = 0.f; pp.chunk_kb = kbp; pp.bf16 = 1;
       CUtensorMap tah, tbh;
-      bool okp = p.a_mn ? make_map_f16(&tah, a.A16, a.M, a.K, a.lda, 64, 32, true) : make_map_f16(&tah, a.A16, a.K, a.M, a.lda, 32, BM, true);
-      okp = okp && (p.b_mn ? make_map_f16(&tbh, a.B16, a.N, a.K, a.ldb, 64, 32, true) : make_map_f16(&tbh, a.B16, a.K, a.N, a.ldb, 32, 256, true));
+      bool okp = p.a_mn ? make_map_f16(&tah, a.A16, a.M, a.K, a.lda, 64, 64, true) : make_map_f16(&tah, a.A16, a.K, a.M, a.lda, 64, BM, true);
+      okp = okp && (p.b_mn ? make_map_f16(&tbh, a.B16, a.N, a.K, a.ldb, 64, 64, true) : make_map_f16(&tbh, a.B16, a.K, a.N, a.ldb, 64, 256, true));
       if (okp && addk_switches().h3_pair && a.M > BM) {
         CUtensorMap tbp = tbh;
-        const bool okb = p.b_mn || make_map_f16(&tbp, a.B16, a.K, a.N, a.ldb, 32, 128, true);
+        const bool okb = p.b_mn || make_map_f16(&tbp, a.B16, a.K, a.N, a.ldb, 64, 128, true);
         if (okb) { g_addk_last_gemm_kernel = ADDK_K_BF16_PAIR; return launch_h3p<256, true, true>(st, tah, tah, tbp, tbp, pp, a.M, a.N, split); }
       }
       if (okp) { g_addk_last_gemm_kernel = ADDK_K_BF16_PERSISTENT; return launch_h3p<256, true>(st, tah, tah, tbh, tbh, pp, a.M, a.N, split); }

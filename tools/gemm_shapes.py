@@ -41,6 +41,8 @@ def run(name, M, N, K, ta, tb, A, B, bias=False, relu=0, mask=False, split=1, ld
         if H3:
             a.a16_plane, a.b16_plane, a.a_amax, a.b_amax = A.n, B.n, A.s.data_ptr(), B.s.data_ptr()
             a.a16_ready = a.b16_ready = ready[0]
+        if BF and NO_F32 and split == 1 and N > 128:
+            a.no_f32 = 1
         _lib.check(L.addk_gemm(_lib.stream(), C.byref(a), C.c_int(_lib.PRECISIONS[prec])), "addk_gemm " + name)
     launch(); ready[0] = 1; launch()
     torch.cuda.synchronize()
@@ -69,6 +71,7 @@ def run(name, M, N, K, ta, tb, A, B, bias=False, relu=0, mask=False, split=1, ld
 R = MB + 1
 tot = [0.0, 0.0]
 QUICK = os.environ.get("QUICK") == "1"
+NO_F32 = os.environ.get("NO_F32", "1") == "1"
 def acc(r, times=1):
     tot[0] += r[0] * times; tot[1] += r[1] * times
 X272, H1024, H512 = Op(R, 264, 272), Op(R, 1024), Op(R, 512)
