@@ -37,6 +37,7 @@ const AddkSwitches& addk_switches() {
     s.h3_comp = e ? (float)atof(e) : 1.7e-8f;
     s.bf16_persistent = env_int("ADDK_BF16_PERSISTENT", 1);
     s.bf16_drop_f32 = env_int("ADDK_BF16_DROP_F32", 1);
+    s.h3_planes_only = env_int("ADDK_H3_PLANES_ONLY", 1);
     s.h3_amax_hooks = env_int("ADDK_H3_AMAX_HOOKS", 1);
     s.h3_fused_planes = env_int("ADDK_H3_FUSED_PLANES", 0);
     s.h3_colpart = env_int("ADDK_H3_COLPART", 1);

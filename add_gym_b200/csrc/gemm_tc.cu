@@ -25,6 +25,7 @@
 #include <stdlib.h>
 #include <cuda_fp16.h>
 #include "switches.h"
+#include "h3_scale.cuh"
 
 extern int g_addk_last_gemm_kernel;      // api.cu: id of the kernel the last addk_gemm dispatched to (tests)
 extern long long* g_addk_stamps;         // api.cu: optional device buffer for clock stamps (addk_debug_set_stamp_buffer)
@@ -651,29 +652,6 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t 
       ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
 }
 
-// the power-of-two scale of a tensor whose max|x| has the bit pattern `amax_bits`: s = 2^(14 - e), returns s and 1/s
-__device__ __forceinline__ void h3_scale(uint32_t amax_bits, float& s, float& inv_s) {
-  int E = (int)((amax_bits >> 23) & 0xFFu);
-  E = E < 16 ? 16 : (E > 250 ? 250 : E);                       // zero / denormal / huge: any finite scale will do
-  s = __uint_as_float((uint32_t)(268 - E) << 23);              // 2^(14 - (E - 127))
-  inv_s = __uint_as_float((uint32_t)(E - 14) << 23);
-}
-
-// A twin's slot is two words {W, max}: max = bit pattern of max|x|, W = a sticky scale word.  The scale in force is that
-// of W while max|x| * s(W) stays inside [2^9, 2^15) -- so a dense layer can write the planes of its OUTPUT in its
-// epilogue with the scale its previous output had, before max|x| is known -- and that of 4 * max|x| otherwise (the
-// planes are then rewritten by h3_repair_kernel).  Every reader derives the scale from the two words the same way.
-__device__ __forceinline__ uint32_t h3_eff_word(uint32_t W, uint32_t amax) {
-  const int Ew = (int)((W >> 23) & 0xFFu), Ea = (int)((amax >> 23) & 0xFFu);
-  const int d = Ea - Ew + 14;                                  // floor(log2(max|x| * s(W)))
-  if (W != 0u && Ew >= 16 && Ew <= 250 && d >= 9 && d <= 14) return W;
-  const int En = Ea + 2 > 250 ? 250 : Ea + 2;
-  return (amax & 0x007FFFFFu) | ((uint32_t)En << 23);
-}
-__device__ __forceinline__ void h3_slot_scale(const uint32_t* slot, float& s, float& inv_s) {
-  h3_scale(slot ? h3_eff_word(slot[0], slot[1]) : 0x3F800000u, s, inv_s);
-}
-
 struct ParamsH3 {
   Params p;
   const uint32_t* a_amax; const uint32_t* b_amax;
@@ -980,6 +958,9 @@ struct ParamsP {
   int chunk_kb;                 // k-blocks per accumulator chunk (drain period)
   int bf16;                     // SINGLE kernel: operands are bf16 (instruction descriptor format 1)
   int tma_store;                // the fp32 output leaves through TMA stores from the staging tile (tmC is valid)
+  int repair;                   // second launch of a layer whose output exists only as fp16 planes: exits at once when the
+                                //   sticky scale the first launch used fits max|C| (the normal case), else recomputes the
+                                //   layer and writes the planes with the scale that max|C| asks for
 };
 
 template <int BN, bool SINGLE, bool PAIR>
@@ -989,6 +970,10 @@ gemm_tc_h3p_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
                    const __grid_constant__ CUtensorMap tmC, const ParamsP pp) {
   using C = CfgP<BN, SINGLE, PAIR>;
   const Params& p = pp.p;
+  if (pp.repair) {      // uniform over the grid: two words every thread reads the same
+    const uint32_t W = __ldcg(p.c_amax), mx = __ldcg(p.c_amax + 1);
+    if (h3_eff_word(W, mx) == W) return;
+  }
   constexpr int BK = C::BK, UK = 16;
   constexpr int CPW = BN / 2, NCH = CPW / 32;
   static_assert(CPW % C::EPI_COLS == 0, "BN must be a multiple of 128");
@@ -1160,11 +1145,13 @@ gemm_tc_h3p_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
     Params p = pp.p;                             // worker-local copy: the scale of C's planes is read from C's slot
     if (p.c_hi) {
       const uint32_t W = p.c_amax[0];            // prepared by h3_prep_kernel before this launch; 0 = no history
-      if (W == 0u) p.c_hi = nullptr;             // the repair pass will write the planes once max|C| is known
-      else { float is; h3_scale(W, p.c_scale, is); }
+      float is;
+      if (pp.repair) h3_scale(h3_eff_word(W, p.c_amax[1]), p.c_scale, is);     // the scale max|C| asks for (now known)
+      else if (W == 0u) p.c_hi = nullptr;        // the repair pass will write the planes once max|C| is known
+      else h3_scale(W, p.c_scale, is);
     }
     float vmax = 0.f;
-    float* const vm = p.c_amax ? &vmax : nullptr;
+    float* const vm = (p.c_amax && !pp.repair) ? &vmax : nullptr;
     long long* const dbg = (p.dbg && blockIdx.x == 0 && warp == 2) ? p.dbg : nullptr;
     long long w_accfull = 0, t_drain = 0, t_epi = 0;
     const long long t_begin = clock64();
@@ -1301,7 +1288,7 @@ gemm_tc_h3p_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
     }
     if (dbg && lane == 0) { dbg[3] = clock64() - t_begin; dbg[4] = w_accfull; dbg[5] = t_drain; dbg[6] = t_epi; dbg[8] = clock64() - t_entry; }
     if (pp.tma_store && lane == 0) tma_store_wait_all();      // shared memory must outlive the engine's reads
-    if (p.c_amax) {
+    if (p.c_amax && !pp.repair) {
       const uint32_t mx = __reduce_max_sync(0xffffffffu, __float_as_uint(vmax));
       if (lane == 0 && mx) atomicMax(p.c_amax + 1, mx);
     }
@@ -1374,7 +1361,7 @@ static int launch_h3p(cudaStream_t st, const CUtensorMap& tah, const CUtensorMap
   using C = CfgP<BN, SINGLE, PAIR>;
   // the fp32 output leaves through TMA stores when its geometry allows (and nothing else rides on the epilogue)
   CUtensorMap tc = tah;
-  pp.tma_store = 0;
+  pp.tma_store = 0; pp.repair = 0;
   if (addk_switches().h3_tma_store && pp.p.C && !pp.p.accumulate && !pp.p.c_hi && !(SINGLE && pp.p.C16) &&
       (!pp.p.bias || (reinterpret_cast<uintptr_t>(pp.p.bias) & 15) == 0) &&
       (!pp.p.mask || ((pp.p.ld_mask & 3) == 0 && (reinterpret_cast<uintptr_t>(pp.p.mask) & 15) == 0)) &&
@@ -1392,9 +1379,13 @@ static int launch_h3p(cudaStream_t st, const CUtensorMap& tah, const CUtensorMap
   pp.tiles_m = (M + TM - 1) / TM; pp.tiles_n = (N + BN - 1) / BN; pp.total_tiles = pp.tiles_m * pp.tiles_n * split;
   // (74 / 99 / 128 CTAs per layer, so that layers of the three streams run side by side, measured the same 2.6 ms per
   // optimizer step as one CTA per SM)
+  const int launches = (pp.p.no_f32 && pp.p.c_hi) ? 2 : 1;      // planes-only output: main launch + repair launch
   if (!PAIR) {
     const int grid = pp.total_tiles < sm_count() ? pp.total_tiles : sm_count();
-    gemm_tc_h3p_kernel<BN, SINGLE, PAIR><<<grid, X3_THREADS, C::SMEM_BYTES, st>>>(tah, tal, tbh, tbl, tc, pp);
+    for (int l = 0; l < launches; ++l) {
+      pp.repair = l;
+      gemm_tc_h3p_kernel<BN, SINGLE, PAIR><<<grid, X3_THREADS, C::SMEM_BYTES, st>>>(tah, tal, tbh, tbl, tc, pp);
+    }
     return ADDK_OK;
   }
   const int pairs = sm_count() / 2;
@@ -1408,9 +1399,12 @@ static int launch_h3p(cudaStream_t st, const CUtensorMap& tah, const CUtensorMap
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  if (cudaLaunchKernelEx(&cfg, gemm_tc_h3p_kernel<BN, SINGLE, PAIR>, tah, tal, tbh, tbl, tc, (const ParamsP)pp) != cudaSuccess) {
-    addk_set_error("gemm_tc: cluster launch of the CTA-pair kernel failed");
-    return ADDK_ERR_LAUNCH;
+  for (int l = 0; l < launches; ++l) {
+    pp.repair = l;
+    if (cudaLaunchKernelEx(&cfg, gemm_tc_h3p_kernel<BN, SINGLE, PAIR>, tah, tal, tbh, tbl, tc, (const ParamsP)pp) != cudaSuccess) {
+      addk_set_error("gemm_tc: cluster launch of the CTA-pair kernel failed");
+      return ADDK_ERR_LAUNCH;
+    }
   }
   return ADDK_OK;
 }
@@ -1717,6 +1711,11 @@ static int gemm_h3(cudaStream_t st, const addk_gemm_args& a) {
     if (a.C16 && a.c_amax && split == 1 && a.c16_plane > 0 && (a.ldc & 7) == 0 && (reinterpret_cast<uintptr_t>(a.C16) & 15) == 0) {
       pp.p.c_hi = reinterpret_cast<uint16_t*>(a.C16); pp.p.c_plane = a.c16_plane;
     }
+    if (a.no_f32) {
+      if (!pp.p.c_hi) { addk_set_error("gemm f16x3: no_f32 needs C16 / c16_plane / c_amax (the output lives as fp16 planes)"); return ADDK_ERR_ARG; }
+      pp.p.no_f32 = 1;
+    }
+    if (a.relu_mask_src16) { pp.p.mask16 = reinterpret_cast<const uint16_t*>(a.relu_mask_src16); pp.p.mask = nullptr; }
     pp.chunk_kb = addk_switches().h3_chunk_kb;
     g_addk_last_gemm_kernel = ADDK_K_H3_PERSISTENT;
     if (addk_switches().h3_pair && a.M > BM) {      // CTA pairs (cta_group::2): each CTA stages a 128-row half of B
@@ -1726,6 +1725,7 @@ static int gemm_h3(cudaStream_t st, const addk_gemm_args& a) {
     return launch_h3p<256>(st, tah, tal, tbh, tbl, pp, a.M, a.N, split);
   }
   g_addk_last_gemm_kernel = ADDK_K_H3_TILE;
+  if (a.no_f32 || a.relu_mask_src16) { addk_set_error("gemm f16x3: no_f32 / relu_mask_src16 need the persistent kernel"); return ADDK_ERR_ARG; }
   if (BN == 256) return launch_h3<256>(st, tah, tal, tbh, tbl, ph, grid);
   if (BN == 128) return launch_h3<128>(st, tah, tal, tbh, tbl, ph, grid);
   return launch_h3<64>(st, tah, tal, tbh, tbl, ph, grid);

@@ -23,6 +23,8 @@
 #include "addk.h"
 #include <stdlib.h>
 #include "switches.h"
+#include "h3_scale.cuh"
+#include <cuda_fp16.h>
 
 struct addk_update_ctx {
 #define ADDK_PTR(n) void* n;
@@ -373,14 +375,35 @@ __device__ __forceinline__ float4 ld_row4(const uint16_t* p) {
 }
 __device__ __forceinline__ float ld_row1(const float* p) { return *p; }
 __device__ __forceinline__ float ld_row1(const uint16_t* p) { return __uint_as_float((uint32_t)*p << 16); }
+// precision "f16x3": a tensor that exists only as its fp16 planes: x = (hi + lo) / s   (22+ bits, see gemm_tc.cu)
+struct PlanesPtr { const __half* hi; long long plane; float inv; };
+__device__ __forceinline__ PlanesPtr operator+(const PlanesPtr& p, size_t off) { return PlanesPtr{p.hi + off, p.plane, p.inv}; }
+__device__ __forceinline__ float4 ld_row4(const PlanesPtr& p) {
+  const uint2 h = __ldg(reinterpret_cast<const uint2*>(p.hi)), l = __ldg(reinterpret_cast<const uint2*>(p.hi + p.plane));
+  const float2 h01 = __half22float2(*reinterpret_cast<const __half2*>(&h.x)), h23 = __half22float2(*reinterpret_cast<const __half2*>(&h.y));
+  const float2 l01 = __half22float2(*reinterpret_cast<const __half2*>(&l.x)), l23 = __half22float2(*reinterpret_cast<const __half2*>(&l.y));
+  return make_float4((h01.x + l01.x) * p.inv, (h01.y + l01.y) * p.inv, (h23.x + l23.x) * p.inv, (h23.y + l23.y) * p.inv);
+}
+__device__ __forceinline__ float ld_row1(const PlanesPtr& p) { return (__half2float(*p.hi) + __half2float(p.hi[p.plane])) * p.inv; }
+template <typename T> struct ColIn { typedef const T* type; };
+template <> struct ColIn<PlanesPtr> { typedef PlanesPtr type; };
+struct PlanesArg { const __half* hi; long long plane; const uint32_t* slot; };
 
 template <typename TIN>
-__global__ void __launch_bounds__(256) colsum_slabs_kernel(const TIN* __restrict__ dY, int ld, int rows, int n,
+__global__ void __launch_bounds__(256) colsum_slabs_kernel(const TIN* __restrict__ dY_raw, PlanesArg pl, int ld, int rows, int n,
                                                            float* __restrict__ out, long long slab_stride, int nsplit,
                                                            const float* __restrict__ rw, float* __restrict__ work,
                                                            unsigned int* __restrict__ tickets) {
   __shared__ float4 sm[8][32];
   __shared__ unsigned int s_last;
+  typename ColIn<TIN>::type dY;
+  if constexpr (sizeof(TIN) == sizeof(PlanesPtr)) {
+    float sc, inv;
+    addk_tc::h3_slot_scale(pl.slot, sc, inv);
+    dY = PlanesPtr{pl.hi, pl.plane, inv};
+  } else {
+    dY = dY_raw;
+  }
   const int cq = threadIdx.x & 31, rl = threadIdx.x >> 5;
   const int col = (blockIdx.x * 32 + cq) * 4;
   const int per = (rows + COLSUM_CHUNKS - 1) / COLSUM_CHUNKS;
@@ -405,7 +428,7 @@ __global__ void __launch_bounds__(256) colsum_slabs_kernel(const TIN* __restrict
       }
     } else {
       for (int r = r0 + rl; r < r1; r += 8) {
-        const TIN* q = dY + (size_t)r * ld + col;
+        const typename ColIn<TIN>::type q = dY + (size_t)r * ld + col;
         const float w = rw ? rw[r] : 1.f;
         acc.x = fmaf(w, ld_row1(q), acc.x);
         if (col + 1 < n) acc.y = fmaf(w, ld_row1(q + 1), acc.y);
@@ -709,16 +732,21 @@ static thread_local float* g_colpart_buf = nullptr;
 static thread_local int g_colpart_rows = 0;
 
 static int colsum(cudaStream_t st, const addk_update_ctx& c, const ChainWs& ws, const float* dY, int ld, int rows, int n,
-                  float* out, const float* rw, const uint16_t* dY16 = nullptr) {
+                  float* out, const float* rw, const uint16_t* dY16 = nullptr, const uint32_t* planes_slot = nullptr) {
   using addk::COLSUM_MAX_N; using addk::COLSUM_CHUNKS;
   if (n > COLSUM_MAX_N) { addk_set_error("colsum: more than 1024 columns"); return ADDK_ERR_UNSUPPORTED; }
   float* work = ws.colsum_work;
   unsigned int* tickets = (unsigned int*)(work + (size_t)COLSUM_CHUNKS * COLSUM_MAX_N);
-  if (dY16 && (ld & 3) == 0)      // the tensor has no fp32 copy (precision "bf16"): read its bf16 copy
-    addk::colsum_slabs_kernel<uint16_t><<<dim3((n + 127) / 128, COLSUM_CHUNKS), 256, 0, st>>>(dY16, ld, rows, n, out, c.num_params,
+  const addk::PlanesArg none{nullptr, 0, nullptr};
+  if (dY16 && planes_slot && (ld & 3) == 0)      // no fp32 copy (precision "f16x3"): read the fp16 planes
+    addk::colsum_slabs_kernel<addk::PlanesPtr><<<dim3((n + 127) / 128, COLSUM_CHUNKS), 256, 0, st>>>(
+        nullptr, addk::PlanesArg{reinterpret_cast<const __half*>(dY16), c.arena_elems, planes_slot}, ld, rows, n, out, c.num_params,
+        (int)c.split_k, rw, work, tickets);
+  else if (dY16 && (ld & 3) == 0)      // the tensor has no fp32 copy (precision "bf16"): read its bf16 copy
+    addk::colsum_slabs_kernel<uint16_t><<<dim3((n + 127) / 128, COLSUM_CHUNKS), 256, 0, st>>>(dY16, none, ld, rows, n, out, c.num_params,
                                                                                      (int)c.split_k, rw, work, tickets);
   else
-    addk::colsum_slabs_kernel<float><<<dim3((n + 127) / 128, COLSUM_CHUNKS), 256, 0, st>>>(dY, ld, rows, n, out, c.num_params,
+    addk::colsum_slabs_kernel<float><<<dim3((n + 127) / 128, COLSUM_CHUNKS), 256, 0, st>>>(dY, none, ld, rows, n, out, c.num_params,
                                                                                   (int)c.split_k, rw, work, tickets);
   ADDK_CHECK_LAUNCH();
   return ADDK_OK;
@@ -848,10 +876,11 @@ static uint16_t* twin16(const void* p) {
 }
 
 enum { F16_DROP_C = 1, F16_MASK = 2 };
-static bool drop16_enabled() { return addk_switches().bf16_drop_f32 != 0; }
-// would a [rows, cols] layer output be 16-bit only in this mode?  (same rule as gemm(): bf16 mode, persistent kernel)
+static bool drop16_enabled(int prec) { return prec == 3 ? addk_switches().bf16_drop_f32 != 0 : addk_switches().h3_planes_only != 0; }
+// would a [rows, cols] layer output be 16-bit only in this mode?  (same rule as gemm(): bf16 / f16x3 mode, persistent kernel)
 static bool is_16only(const addk_update_ctx& c, long long rows, int cols) {
-  if (c.precision != 3 || !drop16_enabled() || !c.arena16) return false;
+  if ((c.precision != 3 && c.precision != 4) || !drop16_enabled((int)c.precision) || !c.arena16) return false;
+  if (c.precision == 4) return cols > 128 && (cols & 7) == 0 && rows >= 64 * c.split_k && c.amax_slots;
   // every consumer must be able to run on the 16-bit copy: the split-K weight gradient (contraction over the rows) needs
   // at least one 64-row k-block per slab, otherwise it falls back to the fp32 operands
   if (rows < 64 * c.split_k) return false;
@@ -868,6 +897,7 @@ static int gemm(cudaStream_t st, int prec, const float* A, int lda, int ta, cons
   // write its fp32 copy when the persistent kernel runs; F16_MASK -- the mask source was produced that way: read its bf16 copy
   addk_gemm_args a;
   a.relu_mask_src16 = nullptr; a.no_f32 = 0;
+  bool planes_only = false;
   a.A16 = prec == 3 ? twin16(A) : nullptr; a.B16 = prec == 3 ? twin16(B) : nullptr; a.C16 = prec == 3 ? twin16(C) : nullptr;
   a.a16_plane = a.b16_plane = a.c16_plane = 0; a.a_amax = a.b_amax = a.c_amax = nullptr; a.a16_ready = a.b16_ready = 0;
   int c_ent = -1;
@@ -914,7 +944,11 @@ static int gemm(cudaStream_t st, int prec, const float* A, int lda, int ta, cons
           // to the dense layers (the epilogue's 8-byte stores are far from the split kernel's 6 TB/s).
           // fused = 2: only behind a long contraction (K >= 1024), where the worker warps wait for the tensor core anyway
           const int fused_sw = addk_switches().h3_fused_planes;
-          const bool fused = fused_sw && N > 128 && (ldc & 7) == 0 && (fused_sw != 2 || K >= 1024);
+          // planes only: the layer's output is read by dense layers / as a ReLU mask / by the bias column sums alone, so it
+          // never exists in fp32 -- the epilogue writes the two fp16 planes with the scale of the previous optimizer step
+          // (sticky word) and a second launch repairs them in the rare case that scale does not fit (gemm_tc.cu: repair)
+          planes_only = (flags16 & F16_DROP_C) && is_16only(c, M, N);
+          const bool fused = planes_only || (fused_sw && N > 128 && (ldc & 7) == 0 && (fused_sw != 2 || K >= 1024));
           bool ready = false;
           if (!fused && g_next_slot < TWIN_SLOTS) { g_tw[e].slot = g_next_slot++; ready = true; }     // zeroed by h3_params
           else { g_tw[e].slot = e; }
@@ -926,6 +960,7 @@ static int gemm(cudaStream_t st, int prec, const float* A, int lda, int ta, cons
             if (fused) {     // the persistent kernel also writes C's planes in its epilogue
               a.C16 = (uint16_t*)c.arena16 + (C - a0); a.c16_plane = c.arena_elems;
               c_ent = e;
+              if (planes_only) a.no_f32 = 1;
             }
           }
         }
@@ -936,12 +971,25 @@ static int gemm(cudaStream_t st, int prec, const float* A, int lda, int ta, cons
     if (flags16 & F16_DROP_C) a.no_f32 = 1;
     if ((flags16 & F16_MASK) && mask) { a.relu_mask_src16 = twin16(mask); if (a.relu_mask_src16) a.relu_mask_src = nullptr; }
   }
+  if (prec == 4 && (flags16 & F16_DROP_C) && !planes_only && g_twin_ctx && is_16only(*g_twin_ctx, M, N)) {
+    // the rule said "planes only" but the call cannot deliver them (no twin / tf32 fallback): consumers would read stale planes
+    addk_set_error("f16x3: a planes-only layer fell off the fp16 path");
+    return ADDK_ERR_UNSUPPORTED;
+  }
+  if (prec == 4 && (flags16 & F16_MASK) && mask && g_twin_ctx && is_16only(*g_twin_ctx, M, N)) {
+    // the mask source (same shape as this output) exists only as planes: sign test on its hi plane
+    const addk_update_ctx& c = *g_twin_ctx;
+    a.relu_mask_src16 = (const uint16_t*)c.arena16 + (mask - (const float*)c.arena);
+    a.relu_mask_src = nullptr;
+  }
   int rc = prec == 0 ? addk::sgemm_launch(st, a) : addk_gemm_tc(st, a, prec);
   if (rc != ADDK_OK) return rc;
   ADDK_CHECK_LAUNCH();
   if (c_ent >= 0) {     // planes written by the epilogue: rewritten only if the sticky scale did not fit max|C|
-    rc = addk_f16x3_repair(st, C, M, N, ldc, a.C16, a.c16_plane, a.c_amax);
-    if (rc != ADDK_OK) return rc;
+    if (!planes_only) {   // (planes-only layers repair themselves: second launch inside addk_gemm)
+      rc = addk_f16x3_repair(st, C, M, N, ldc, a.C16, a.c16_plane, a.c_amax);
+      if (rc != ADDK_OK) return rc;
+    }
     g_tw[c_ent].valid = true;
   }
   return ADDK_OK;
@@ -978,8 +1026,16 @@ static int wgrad(cudaStream_t st, const Ctx& c, const ChainWs& ws, const float* 
     }
   }
   if (o_b >= 0) {
-    const uint16_t* dY16 = (dy_16only && is_16only(c, rows, n_out)) ? twin16(dY) : nullptr;
-    TRY(colsum(st, c, ws, dY, ldy, rows, n_out, F(c.slabs) + (size_t)slab0 * P + o_b, nullptr, dY16));
+    const bool only16 = dy_16only && is_16only(c, rows, n_out);
+    const uint16_t* dY16 = nullptr;
+    const uint32_t* pslot = nullptr;
+    if (only16 && c.precision == 3) dY16 = twin16(dY);
+    if (only16 && c.precision == 4) {     // the fp16 planes of dY and the slot that holds their scale
+      for (int i = 0; i < g_ntw; ++i) if (g_tw[i].p == dY && g_tw[i].valid) { pslot = twin_slot(c, i); break; }
+      if (!pslot) { addk_set_error("f16x3: planes-only gradient without a valid twin"); return ADDK_ERR_UNSUPPORTED; }
+      dY16 = (const uint16_t*)c.arena16 + (dY - (const float*)c.arena);
+    }
+    TRY(colsum(st, c, ws, dY, ldy, rows, n_out, F(c.slabs) + (size_t)slab0 * P + o_b, nullptr, dY16, pslot));
   }
   return ADDK_OK;
 }

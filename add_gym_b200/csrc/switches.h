@@ -15,6 +15,7 @@ struct AddkSwitches {
   float h3_comp;          // ADDK_H3_COMP         expected accumulator truncation loss per MMA                   1.7e-8
   int bf16_persistent;    // ADDK_BF16_PERSISTENT persistent one-plane kernel in bf16 mode                       default 1
   int bf16_drop_f32;      // ADDK_BF16_DROP_F32   bf16 mode: layer outputs read only by dense layers / masks / column sums are 16-bit only   default 1
+  int h3_planes_only;     // ADDK_H3_PLANES_ONLY  f16x3: such outputs exist only as their fp16 planes (sticky scale + repair launch)     default 1
   int h3_amax_hooks;      // ADDK_H3_AMAX_HOOKS   elementwise producers leave max|x| behind                      default 1
   int h3_fused_planes;    // ADDK_H3_FUSED_PLANES dense-layer epilogue writes the fp16 planes of its output      default 0
   int h3_colpart;         // ADDK_H3_COLPART      split pass leaves bias-gradient column sums behind             default 1

@@ -45,14 +45,17 @@ def _gpu_relu_masks(agent):
 
     # bf16 mode: h1 / h2 / e1 of every chain exist only as their bf16 copies (same element offsets in the 16-bit arena)
     # (when every consumer can read them: at least 64 rows per split-K slab of the weight gradients, csrc/mlp.cu is_16only)
-    bf16 = m.precision == _lib_mod().PRECISIONS["bf16"] and M >= 64 * agent._ctx.ints["split_k"]
-    only16 = {"h1", "h2", "c_h1", "c_h2", "d_e1"} if bf16 else set()
+    # f16x3 mode: the same tensors exist only as their fp16 planes (hi plane at the same element offsets; the 16-bit arena is
+    # typed bfloat16 but holds fp16 bit patterns there: "> 0" is a sign / zero test on the int16 view in both cases)
+    P = _lib_mod().PRECISIONS
+    mode16 = m.precision in (P["bf16"], P["f16x3"]) and M >= 64 * agent._ctx.ints["split_k"]
+    only16 = {"h1", "h2", "c_h1", "c_h2", "d_e1"} if mode16 else set()
 
     def g(key, width, r0, r1):
         t = ws[key]
         if key in only16:
             off = (t.data_ptr() - agent._arena.data_ptr()) // 4
-            t = agent._arena16[off:off + t.numel()]
+            t = agent._arena16[off:off + t.numel()].view(torch.int16)
         return (t.flatten()[:(M + 1) * width].view(M + 1, width)[r0:r1] > 0).cpu()
     return {"actor": [g("h1", H[0], 0, M), g("h2", H[1], 0, M), g("h3", H[2], 0, M)],
             "critic": [g("c_h1", H[0], 0, M), g("c_h2", H[1], 0, M), g("c_h3", H[2], 0, M)],
