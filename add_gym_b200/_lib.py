@@ -166,3 +166,75 @@ class UpdateCtx:
         for k, v in changes.items():
             (iv if k in iv else fv if k in fv else pv)[k] = v
         return UpdateCtx(pv, iv, fv)
+
+
+# ---- exchange step over NVLink peer memory (csrc/p2p.cu) -------------------------------------------------------------
+class _ForeignCuda:
+    """__cuda_array_interface__ holder: lets torch view device memory this library allocated (no copy, no ownership)."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+def foreign_tensor(ptr, n, dtype, device):
+    typestr = {torch.float32: "<f4", torch.int32: "<i4", torch.uint8: "|u1"}[dtype]
+    return torch.as_tensor(_ForeignCuda(ptr, (n,), typestr), device=device)
+
+
+class P2PExchange:
+    """Peer-mapped flat gradient / parameter vectors of all ranks of one box + the flags of the fused exchange kernel.
+
+    Every rank cudaMallocs its three buffers, the 64-byte cudaIpc handles travel once through torch.distributed, and each
+    rank maps its peers' buffers.  `grad` / `param` are torch views of THIS rank's buffers (the model's flat vectors are
+    rebound to them); `step()` launches addk_p2p_adamw."""
+
+    FLAG_WORDS = 16
+
+    def __init__(self, num_params, device, dist):
+        L = lib()
+        self.rank, self.world, self.n = dist.get_rank(), dist.get_world_size(), int(num_params)
+        if self.world > 8:
+            raise AddkError("the peer-memory exchange kernel addresses at most 8 ranks")
+        own = []
+        for nbytes in (4 * self.n, 4 * self.n, 4 * self.FLAG_WORDS):
+            p = C.c_void_p()
+            check(L.addk_p2p_alloc(C.c_longlong(nbytes), C.byref(p)), "addk_p2p_alloc")
+            own.append(p.value)
+        handles = []
+        for p in own:
+            h = (C.c_ubyte * 64)()
+            check(L.addk_p2p_export(C.c_void_p(p), h), "addk_p2p_export")
+            handles.append(bytes(h))
+        everyone = [None] * self.world
+        dist.all_gather_object(everyone, handles)
+        ptrs = [[0] * self.world for _ in range(3)]
+        for r, hs in enumerate(everyone):
+            for k in range(3):
+                if r == self.rank:
+                    ptrs[k][r] = own[k]
+                else:
+                    q = C.c_void_p()
+                    hb = (C.c_ubyte * 64).from_buffer_copy(hs[k])
+                    check(L.addk_p2p_open(hb, C.byref(q)), "addk_p2p_open (rank %d)" % r)
+                    ptrs[k][r] = q.value
+        self._own = own
+        self.grad_ptrs = (C.c_void_p * self.world)(*ptrs[0])
+        self.param_ptrs = (C.c_void_p * self.world)(*ptrs[1])
+        self.flag_ptrs = (C.c_void_p * self.world)(*ptrs[2])
+        self.grad = foreign_tensor(own[0], self.n, torch.float32, device)
+        self.param = foreign_tensor(own[1], self.n, torch.float32, device)
+        self.ticket = torch.zeros(1, dtype=torch.int32, device=device)
+        dist.barrier()      # every mapping exists before anyone launches
+
+    def shard(self):
+        """[begin, end) of the parameter shard whose AdamW moments this rank keeps current."""
+        n4 = (self.n + 3) // 4
+        per = (n4 + self.world - 1) // self.world
+        return min(self.n, 4 * self.rank * per), min(self.n, 4 * (self.rank + 1) * per)
+
+    def step(self, exp_avg, exp_avg_sq, step, lr, betas, eps, weight_decay):
+        rc = lib().addk_p2p_adamw(stream(), C.c_int(self.rank), C.c_int(self.world), self.grad_ptrs, self.param_ptrs, self.flag_ptrs,
+                                  ptr(exp_avg), ptr(exp_avg_sq), C.c_longlong(self.n), C.c_int(step), C.c_double(lr),
+                                  C.c_double(betas[0]), C.c_double(betas[1]), C.c_double(eps), C.c_double(weight_decay),
+                                  ptr(self.ticket), C.c_int(0))
+        check(rc, "addk_p2p_adamw")

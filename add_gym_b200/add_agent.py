@@ -73,11 +73,28 @@ class MPOptimizerState:
         self.steps = 0
         self._model = model
         self.on_hyperparams_changed = None
+        self.shard = None          # (begin, end): with the peer-memory exchange only this slice of the moments is current
 
     def get_steps(self):
         return self.steps
 
+    def _gather_moments(self):
+        """Peer-memory exchange: every rank keeps the moments of its own shard current -- assemble the full vectors."""
+        if self.shard is None or not dist.is_initialized() or dist.get_world_size() == 1:
+            return
+        world = dist.get_world_size()
+        n = self.exp_avg.numel()
+        per = 4 * (((n + 3) // 4 + world - 1) // world)
+        for vec in (self.exp_avg, self.exp_avg_sq):
+            pad = torch.zeros(per * world, dtype=vec.dtype, device=vec.device)
+            mine = torch.zeros(per, dtype=vec.dtype, device=vec.device)
+            b, e = self.shard
+            mine[:e - b] = vec[b:e]
+            dist.all_gather_into_tensor(pad, mine)
+            vec.copy_(pad[:n])
+
     def state_dict(self):
+        self._gather_moments()
         names, tensors = self._model.trainable()
         state = {}
         for i, (n, t) in enumerate(zip(names, tensors)):
@@ -144,6 +161,15 @@ class ADDAgent(torch.nn.Module):
         if self._world > 1:   # what DDP's constructor does: every rank starts from rank 0's weights
             dist.broadcast(self._model.flat, src=0)
         self._optimizer = MPOptimizerState(config["optimizer"], self._model)
+        # The exchange step: one kernel over NVLink peer memory (gradient reduce-scatter + AdamW on the owned shard +
+        # all-gather of the parameters, csrc/p2p.cu) instead of an NCCL all-reduce + a separate AdamW launch.  Needs every
+        # rank on the same box with its own device; ADDK_P2P=0 or optimizer.grad_clip > 0 keep the NCCL path.
+        self._p2p = None
+        if (self._world > 1 and os.environ.get("ADDK_P2P", "1") != "0" and self._optimizer._grad_clip == 0.0
+                and dist.get_backend() == "nccl" and self._world <= 8):
+            self._p2p = _lib.P2PExchange(self._model.num_params, device, dist)
+            self._model.rebind_storage(self._p2p.param, self._p2p.grad)
+            self._optimizer.shard = self._p2p.shard()
         self._build_exp_buffer(config)
         self._build_update_ctx()
         self._mode = AgentMode.TRAIN
@@ -583,7 +609,9 @@ class ADDAgent(torch.nn.Module):
                 rc = L.addk_update_minibatch(_lib.stream(), self._ctx.buf, _lib.ptr(idx), C.c_int(step),
                                              C.c_int(opt.steps + 1 if local else 0))
                 _lib.check(rc, "addk_update_minibatch")
-                if not local:   # the one exchange step of the path: flat gradient all-reduce over NCCL
+                if self._p2p is not None:   # the one exchange step of the path, fused with the optimizer (csrc/p2p.cu)
+                    self._p2p.step(opt.exp_avg, opt.exp_avg_sq, opt.steps + 1, opt.lr, opt.betas, opt.eps, opt.weight_decay)
+                elif not local:   # ... or as an NCCL all-reduce of the flat gradient + AdamW
                     dist.all_reduce(self._model.flat_grad, op=dist.ReduceOp.SUM)
                     if opt._grad_clip > 0.0:   # global-norm clip of the rank-averaged gradient (mp_optimizer.py:19-20)
                         rc = L.addk_clip_grad_norm(_lib.stream(), _lib.ptr(self._model.flat_grad),

@@ -143,6 +143,19 @@ class ADDModel(torch.nn.Module):
                        [self._disc_layers[i].out_features for i in (0, 2)])
         assert [self._critic_layers[i].out_features for i in (0, 2, 4)] == self.hidden[0]
 
+    def rebind_storage(self, flat, flat_grad):
+        """Move the flat parameter / gradient vectors into caller-provided device memory (the peer-mapped buffers of
+        _lib.P2PExchange): values are copied, every parameter and its .grad become views of the new vectors."""
+        assert flat.numel() == self.num_params and flat_grad.numel() == self.num_params
+        flat.copy_(self.flat)
+        flat_grad.copy_(self.flat_grad)
+        names, tensors = self.trainable()
+        for n, t in zip(names, tensors):
+            o = self.offsets["o_" + n]
+            t.data = flat[o:o + t.numel()].view(t.shape)
+            t.grad = flat_grad[o:o + t.numel()].view(t.shape)
+        self.flat, self.flat_grad = flat, flat_grad
+
     # ---- reference API ---------------------------------------------------------------------------------------
     def _linear(self, x, lin, relu):
         x = x.contiguous()

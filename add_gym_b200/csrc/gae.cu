@@ -11,6 +11,7 @@
 // at least as accurate as the reference's fp32 cascade sums; elementwise formulas keep its op order.
 #include "common.cuh"
 #include "addk.h"
+#include "adam.cuh"
 
 namespace addk {
 
@@ -158,17 +159,6 @@ __global__ void diff_normalizer_update_kernel(const double* __restrict__ sum_abs
   if (c == 0) count[0] = total;
 }
 
-// torch.optim.AdamW, amsgrad=False, maximize=False (torch/optim/adamw.py -> adam.py _single_tensor_adam)
-struct AdamK { float lr_wd_factor, one_minus_b1, b2, one_minus_b2, step_size, bc2_sqrt, eps, grad_scale; };
-__device__ __forceinline__ void adam1(const AdamK& k, float& p, float g, float& m, float& v) {
-  const float grad = mul_rn(g, k.grad_scale);
-  const float w = mul_rn(p, k.lr_wd_factor);                                     // param.mul_(1 - lr*wd)
-  const float mi = add_rn(m, mul_rn(k.one_minus_b1, sub_rn(grad, m)));           // exp_avg.lerp_(grad, 1-b1)
-  const float vi = add_rn(mul_rn(v, k.b2), mul_rn(mul_rn(k.one_minus_b2, grad), grad));  // mul_(b2).addcmul_(g, g, 1-b2)
-  const float denom = add_rn(sqrtf(vi) / k.bc2_sqrt, k.eps);
-  p = add_rn(w, mul_rn(-k.step_size, mi / denom));                               // addcdiv_(exp_avg, denom, -step_size)
-  m = mi; v = vi;
-}
 __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                              float* __restrict__ v, long long n, const AdamK k) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;

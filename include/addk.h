@@ -309,6 +309,22 @@ int addk_adamw(void* stream, float* param, const float* grad, float* exp_avg, fl
                int step, double lr, double beta1, double beta2, double eps, double weight_decay,
                double grad_scale);
 
+/* ----- the exchange step over NVLink peer memory (csrc/p2p.cu) ---------------------------------- */
+/* Device memory the peers can map (cudaMalloc, zeroed) and its 64-byte cudaIpc handle; addk_p2p_open maps a peer's. */
+int addk_p2p_alloc(long long bytes, void** ptr_out);
+int addk_p2p_free(void* ptr);
+int addk_p2p_export(void* ptr, unsigned char* handle64_host);
+int addk_p2p_open(const unsigned char* handle64_host, void** ptr_out);
+/* Gradient reduce-scatter + AdamW on this rank's shard + all-gather of the updated parameters in ONE kernel (replaces
+ * dist.all_reduce(flat_grad) + addk_adamw; the all-reduce the reference's DDP would issue, base_agent.py:47-57).
+ * grad / param / flag pointers of all `world` ranks in rank order (own entries included; flags: [2][8] uint32, zeroed).
+ * `n` floats (vectors padded to a multiple of 4); `step` = optimizer step number, identical on all ranks (it is the
+ * epoch of the flags); only this rank's shard of exp_avg / exp_avg_sq is updated.  ticket: one zeroed uint32. */
+int addk_p2p_adamw(void* stream, int rank, int world, float* const* grad_ptrs_host, float* const* param_ptrs_host,
+                   unsigned int* const* flag_ptrs_host, float* exp_avg, float* exp_avg_sq, long long n, int step,
+                   double lr, double beta1, double beta2, double eps, double weight_decay, unsigned int* ticket,
+                   int max_blocks);
+
 /* MPOptimizer._clip_grads = torch.nn.utils.clip_grad_norm_ (mp_optimizer.py:19-20,46-47) on the flat gradient:
  * coef = min(1, max_norm / (pre_scale * ||g||_2 + 1e-6)); g *= coef.  pre_scale = 1/world while g holds the cross-rank
  * sum.  sumsq_work: one double; *coef_out receives the coefficient. */

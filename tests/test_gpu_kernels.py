@@ -337,3 +337,48 @@ def test_empty_and_ragged_requests():
                             C.c_float(0), C.c_float(0), None, None) != 0
     assert L.addk_adamw(_lib.stream(), None, None, None, None, C.c_longlong(0), C.c_int(1), C.c_double(1e-4), C.c_double(0.9),
                         C.c_double(0.999), C.c_double(1e-8), C.c_double(0.0), C.c_double(1.0)) != 0
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the exchange step as one kernel over peer memory (csrc/p2p.cu), emulated on ONE device: three "ranks" = three
+# concurrent launches on three streams that address each other's buffers directly (no cudaIpc needed in one process)
+# ---------------------------------------------------------------------------------------------------------------
+def test_p2p_exchange_kernel_three_ranks_on_one_device():
+    _lib, L = _L()
+    world, n = 3, 4349984                       # the model's padded parameter count
+    g = torch.Generator(device="cuda").manual_seed(3)
+    grads = [torch.randn(n, device="cuda", generator=g) * 1e-3 for _ in range(world)]
+    p0 = torch.randn(n, device="cuda", generator=g) * 0.05
+    m0 = torch.randn(n, device="cuda", generator=g) * 1e-4
+    v0 = torch.rand(n, device="cuda", generator=g) * 1e-6
+    params = [p0.clone() for _ in range(world)]
+    ms, vs = [m0.clone() for _ in range(world)], [v0.clone() for _ in range(world)]
+    flags = [torch.zeros(16, dtype=torch.int32, device="cuda") for _ in range(world)]
+    tickets = [torch.zeros(1, dtype=torch.int32, device="cuda") for _ in range(world)]
+    arr = lambda ts: (C.c_void_p * world)(*[t.data_ptr() for t in ts])
+    gp, pp, fp = arr(grads), arr(params), arr(flags)
+    streams = [torch.cuda.Stream() for _ in range(world)]
+    torch.cuda.synchronize()
+    for step in (1, 2):                          # two consecutive epochs: the flags are reused
+        for r in reversed(range(world)):         # launch order must not matter
+            rc = L.addk_p2p_adamw(C.c_void_p(streams[r].cuda_stream), C.c_int(r), C.c_int(world), gp, pp, fp, _lib.ptr(ms[r]),
+                                  _lib.ptr(vs[r]), C.c_longlong(n), C.c_int(step), C.c_double(1e-4), C.c_double(0.9),
+                                  C.c_double(0.999), C.c_double(1e-8), C.c_double(0.0), _lib.ptr(tickets[r]), C.c_int(32))
+            _lib.check(rc, "addk_p2p_adamw")
+        torch.cuda.synchronize()
+        # reference: the all-reduced gradient (rank-order sum) through the flat AdamW kernel with grad_scale = 1 / world
+        gsum = grads[0].clone()
+        for r in range(1, world):
+            gsum += grads[r]
+        _lib.check(L.addk_adamw(_lib.stream(), _lib.ptr(p0), _lib.ptr(gsum), _lib.ptr(m0), _lib.ptr(v0), C.c_longlong(n), C.c_int(step),
+                                C.c_double(1e-4), C.c_double(0.9), C.c_double(0.999), C.c_double(1e-8), C.c_double(0.0),
+                                C.c_double(1.0 / world)), "addk_adamw")
+        torch.cuda.synchronize()
+        for r in range(world):
+            assert torch.equal(params[r], p0), "every rank holds the same bits as all-reduce + AdamW (step %d, rank %d)" % (step, r)
+        per = 4 * (((n + 3) // 4 + world - 1) // world)
+        for r in range(world):                   # the moments are sharded: rank r keeps [r * per, (r + 1) * per) current
+            b, e = r * per, min(n, (r + 1) * per)
+            assert torch.equal(ms[r][b:e], m0[b:e]) and torch.equal(vs[r][b:e], v0[b:e])
+        for t in grads:                          # next epoch: new gradients
+            t.mul_(-0.5).add_(1e-4)
