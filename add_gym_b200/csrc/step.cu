@@ -868,29 +868,47 @@ __global__ void sample_time_kernel(const float* __restrict__ errors, int S, cons
   times_out[e] = start_time_of(seg, u[3 * (size_t)e + 2], seg_sizes[c], dt, min_start);
 }
 
+// One warp per sample; the (clip, segment) bins are first accumulated per BLOCK in shared memory (131072 double atomics on
+// the 20 bins of a single clip took 241 us), then every block adds its non-empty bins to the global sums.  Libraries with
+// more bins than SAMPLER_SMEM_BINS fall back to direct global atomics.
+constexpr int SAMPLER_SMEM_BINS = 1024;
 __global__ void sampler_accum_kernel(const long long* __restrict__ clip_ids, const float* __restrict__ timesteps,
                                      const float* __restrict__ a, const float* __restrict__ b, int dim, int n,
-                                     const float* __restrict__ seg_sizes, int S, double* sums, int* counts) {
-  int i = blockIdx.x * (blockDim.x / 32) + (threadIdx.x / 32);
-  int lane = threadIdx.x & 31;
-  if (i >= n) return;
-  float acc = 0.f;
-  if (b) {  // tracking error = sum((disc_obs - disc_obs_demo)^2)  (add_agent.py:120-122)
-    for (int c = lane; c < dim; c += 32) {
-      float d = sub_rn(a[(size_t)i * dim + c], b[(size_t)i * dim + c]);
-      acc += d * d;
-    }
-    acc = warp_sum(acc);
-  } else {  // `a` already holds one tracking error per sample
-    acc = a[i];
+                                     const float* __restrict__ seg_sizes, int S, int bins, double* sums, int* counts) {
+  __shared__ double s_sum[SAMPLER_SMEM_BINS];
+  __shared__ int s_cnt[SAMPLER_SMEM_BINS];
+  const bool local = bins <= SAMPLER_SMEM_BINS;
+  if (local) {
+    for (int i = threadIdx.x; i < bins; i += blockDim.x) { s_sum[i] = 0.0; s_cnt[i] = 0; }
+    __syncthreads();
   }
-  if (lane == 0) {
-    long long c = clip_ids[i];
-    float sz = fmaxf(seg_sizes[c], 1e-6f);
-    long long seg = (long long)(timesteps[i] / sz);
-    seg = seg < 0 ? 0 : (seg > S - 1 ? S - 1 : seg);
-    atomicAdd(sums + c * S + seg, (double)acc);
-    atomicAdd(counts + c * S + seg, 1);
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int i = blockIdx.x * (blockDim.x / 32) + (threadIdx.x / 32); i < n; i += warps) {
+    float acc = 0.f;
+    if (b) {  // tracking error = sum((disc_obs - disc_obs_demo)^2)  (add_agent.py:120-122)
+      for (int c = lane; c < dim; c += 32) {
+        float d = sub_rn(a[(size_t)i * dim + c], b[(size_t)i * dim + c]);
+        acc += d * d;
+      }
+      acc = warp_sum(acc);
+    } else {  // `a` already holds one tracking error per sample
+      acc = a[i];
+    }
+    if (lane == 0) {
+      long long c = clip_ids[i];
+      float sz = fmaxf(seg_sizes[c], 1e-6f);
+      long long seg = (long long)(timesteps[i] / sz);
+      seg = seg < 0 ? 0 : (seg > S - 1 ? S - 1 : seg);
+      const long long bin = c * S + seg;
+      if (local) { atomicAdd(&s_sum[bin], (double)acc); atomicAdd(&s_cnt[bin], 1); }
+      else { atomicAdd(sums + bin, (double)acc); atomicAdd(counts + bin, 1); }
+    }
+  }
+  if (local) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < bins; i += blockDim.x)
+      if (s_cnt[i]) { atomicAdd(sums + i, s_sum[i]); atomicAdd(counts + i, s_cnt[i]); }
   }
 }
 
@@ -1032,8 +1050,10 @@ extern "C" int addk_sampler_update_errors(void* stream, const long long* clip_id
   // disc_obs_demo == NULL: `disc_obs` is a ready-made [n] vector of tracking errors (sampler.py:21 signature)
   if (!clip_ids || !timesteps || !disc_obs || !sums_work || !counts_work || !errors || n <= 0) return ADDK_ERR_ARG;
   cudaStream_t st = (cudaStream_t)stream;
-  sampler_accum_kernel<<<(n + 7) / 8, 256, 0, st>>>(clip_ids, timesteps, disc_obs, disc_obs_demo, disc_dim, n,
-                                                    seg_sizes, num_segments, sums_work, counts_work);
+  int blocks = (n + 7) / 8;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  sampler_accum_kernel<<<blocks, 256, 0, st>>>(clip_ids, timesteps, disc_obs, disc_obs_demo, disc_dim, n, seg_sizes,
+                                               num_segments, num_motions * num_segments, sums_work, counts_work);
   ADDK_CHECK_LAUNCH();
   int bins = num_motions * num_segments;
   sampler_ema_kernel<<<(bins + 127) / 128, 128, 0, st>>>(sums_work, counts_work, bins, errors);
