@@ -494,7 +494,8 @@ def _ncu_traffic(key):
 def step_kernel_roofline(agent, hbm_peak, motions="walk"):
     """The HBM-bound stage: the fused per-env step kernel (csrc/step.cu), 5,624 algorithmic bytes per env-step
     (SURVEY 8d).  `reps` back-to-back launches through the C-ABI (structs prepared beforehand, successive experience
-    rows) between one CUDA-event pair on the launch stream -> average launch duration."""
+    rows), captured into one CUDA graph; the replay sits between one CUDA-event pair on the launch stream -> average
+    launch duration."""
     import ctypes as C
 
     import torch
@@ -508,14 +509,26 @@ def step_kernel_roofline(agent, hbm_peak, motions="walk"):
     rows = [agent._exp_row(i % T) for i in range(reps)]
     sim = core.sim_struct()
     L = _lib.lib()
+
+    def issue():
+        for i in range(reps):
+            L.addk_env_step(_lib.stream(), C.byref(core.task), C.byref(core.c_lib), C.byref(sim), C.byref(core.c_env),
+                            C.byref(rows[i]), _lib.ptr(core.dof_err_w), None, C.c_int(N), C.c_int(i % 3), C.c_int(flags))
+
+    # The rollout runs this kernel from a captured CUDA graph (add_agent._capture_all); so does the measurement: `reps`
+    # launches captured once, the replay timed -- at 4096 envs the kernel (about 10 us) is shorter than one ctypes call
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, capture_error_mode="thread_local"):
+        issue()
+    g.replay()
+    torch.cuda.synchronize()
     e0.record()
-    for i in range(reps):
-        L.addk_env_step(_lib.stream(), C.byref(core.task), C.byref(core.c_lib), C.byref(sim), C.byref(core.c_env),
-                        C.byref(rows[i]), _lib.ptr(core.dof_err_w), None, C.c_int(N), C.c_int(i % 3), C.c_int(flags))
+    g.replay()
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
+    del g
     nbytes = 5624.0 * N
     achieved = nbytes / (ms * 1e-3) / 1e9
     return {"bound": "hbm", "kernel": "env_step_kernel (fused obs/disc-obs/reward/done/record)", "achieved": achieved,
