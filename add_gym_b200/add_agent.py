@@ -284,19 +284,21 @@ class ADDAgent(torch.nn.Module):
         offs, total = {}, 0
         for k, shp in shapes.items():
             offs[k] = total
-            total += (int(np.prod(shp)) + 7) & ~7
+            total += (int(np.prod(shp)) + 127) & ~127      # 128 elements: a piece's ReLU bit plane starts on a 16-byte boundary
         self._arena = z(total)
         bf16 = m.precision == _lib.PRECISIONS["bf16"]
         h3 = m.precision == _lib.PRECISIONS["f16x3"]      # two fp16 planes (hi, lo) per twin + one max|x| word per tensor
         self._arena16 = torch.zeros(2 * total if h3 else (total if bf16 else 8), device=dev, dtype=torch.bfloat16)
         self._params16 = torch.zeros(2 * m.num_params if h3 else (m.num_params if bf16 else 8), device=dev, dtype=torch.bfloat16)
         self._amax_slots = torch.zeros(2 * (1 + 4 * 128), device=dev, dtype=torch.int32) if h3 else None
+        # ReLU masks as bit planes (one bit per arena element; written by the forward layers of an optimizer step)
+        self._arena_bits = torch.zeros(total // 32 + 4, device=dev, dtype=torch.int32) if h3 else None
         carve = {k: self._arena[offs[k]:offs[k] + int(np.prod(shp))].view(shp) for k, shp in shapes.items()}
         self._ws = dict(
             carve, old_logp=z(R), adv=z(R), tar=z(R), mask=z(R), pred=z(R), dpred=z(R), ones=torch.ones(R, device=dev),
             stats=z(32, dt=torch.float64), info=z(self._max_steps, 16), cnt=z(1, dt=torch.int32),
             slabs=z(2 * S, m.num_params), colsum_work=z(64 * 1024 + 64), arena=self._arena, arena16=self._arena16,
-            params16=self._params16, amax_slots=self._amax_slots)
+            params16=self._params16, amax_slots=self._amax_slots, arena_bits=self._arena_bits)
         for k in ("colpart_a", "colpart_c", "colpart_d"):
             self._ws[k] = z(148 * 8, 1024) if h3 else None
         if n_streams == 3:

@@ -41,6 +41,7 @@ const AddkSwitches& addk_switches() {
     s.h3_amax_hooks = env_int("ADDK_H3_AMAX_HOOKS", 1);
     s.h3_fused_planes = env_int("ADDK_H3_FUSED_PLANES", 0);
     s.h3_colpart = env_int("ADDK_H3_COLPART", 1);
+    s.h3_relu_bits = env_int("ADDK_H3_RELU_BITS", 1);
     s.step_cta_tail = env_int("ADDK_STEP_CTA_TAIL", 1);
     s.step_min_blocks = env_int("ADDK_STEP_MIN_BLOCKS", 0);
     return s;

@@ -74,6 +74,8 @@ ADDK_PTR(params16)      // [P] bf16
 // ---- precision "f16x3": arena16 / params16 hold TWO fp16 planes each (hi, then lo arena_elems / num_params elements
 //      later) and amax_slots the max|x| words of the twins (slot 0 = the parameter vector); see csrc/gemm_tc.cu
 ADDK_PTR(amax_slots)    // [2 * (1 + 4 * 128)] uint32: {sticky scale word, max|x|} per twin (NULL unless precision == f16x3)
+ADDK_PTR(arena_bits)    // [arena_elems / 32] uint32: ReLU bit planes, the mask of the arena tensor at element offset o starts at word o / 32
+                        //   (arena pieces start at multiples of 128 elements; NULL: masks are read from the tensors themselves)
 // ---- second and third workspace sets: the critic and the discriminator chains of one optimizer step run on their
 //      own streams next to the actor's (n_streams == 3), so the tail wave of one chain's dense layer overlaps the
 //      next chain's tiles; all NULL / n_streams == 1 = the three chains run back to back on the caller's stream

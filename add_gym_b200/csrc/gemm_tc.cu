@@ -58,6 +58,10 @@ struct Params {
   int no_f32;                  // persistent kernel: the fp32 output is NOT written (C lives only as its 16-bit copy / planes)
   const uint16_t* mask16;      // persistent kernel: ReLU-mask source as 16-bit values (bf16 copy or fp16 hi plane, pitch ld_mask):
                                //   element > 0  <=>  sign bit clear and magnitude bits non-zero; used instead of `mask`
+  // ReLU masks as bit planes (persistent f16x3 kernel, N % 128 == 0): bit c % 32 of word [row * ld_bits + c / 32]
+  uint32_t* bits_out = nullptr;        // written by the store loop of a layer: output element > 0
+  const uint32_t* bits_in = nullptr;   // applied in the accumulator's own layout (lane = row) before staging: replaces mask / mask16
+  int ld_bits = 0;                     // words per row (a multiple of 4)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -185,6 +189,19 @@ __device__ __forceinline__ float4 mask4_from16(const uint16_t* m) {
 }
 __device__ __forceinline__ bool mask1_from16(const uint16_t* m) { return ((uint32_t)__ldg(m) - 1u) < 0x7FFFu; }
 
+// ReLU bit planes.  One store instruction of the row-major store loops covers two rows x 64 columns: lane = 16 * (row & 1)
+// + i holds columns 4i .. 4i+3 of its row and `nib` = their four "> 0" bits.  Four ballots (one per component, independent
+// of each other -- a shuffle reduction was a dependent chain of three per store and cost 6k cycles per tile) give, per
+// row, the two words of this 64-column group:  word 0 = {x bits of i = 0..15 | y bits << 16}, word 1 = {z | w << 16},
+// i.e. column 4i + k of group g lives in word 2g + (k >> 1), bit 16 (k & 1) + i.  The consumer (lane = row, before
+// staging) undoes exactly this; nothing else reads the planes.
+__device__ __forceinline__ uint2 relu_bits_words(uint32_t nib, int lane) {
+  const uint32_t bx = __ballot_sync(0xffffffffu, nib & 1u), by = __ballot_sync(0xffffffffu, nib & 2u);
+  const uint32_t bz = __ballot_sync(0xffffffffu, nib & 4u), bw = __ballot_sync(0xffffffffu, nib & 8u);
+  return (lane & 16) ? make_uint2((bx >> 16) | (by & 0xFFFF0000u), (bz >> 16) | (bw & 0xFFFF0000u))
+                     : make_uint2((bx & 0xFFFFu) | (by << 16), (bz & 0xFFFFu) | (bw << 16));
+}
+
 template <int CW>
 __device__ __forceinline__ void stage_put(float4* stg, int lane, int slot, float a, float b, float c, float d) {
   stg[lane * (CW / 4) + (slot ^ (lane & 7))] = make_float4(a, b, c, d);
@@ -233,6 +250,7 @@ __device__ __forceinline__ void store_staged(const Params& p, float* Cz, const f
       const int sl = sl0 + 32 * (it % PPR);
       const int grow = grow0 + r, col = col0 + 4 * sl;
       float4 o = stg[r * S + (sl ^ (r & 7))];
+      uint32_t nib = 0u;                 // ReLU bits of this lane's four outputs (bits_out)
       if (grow < p.M && col < p.N) {
         const float4 bb = b4[it % PPR];
         o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
@@ -242,6 +260,7 @@ __device__ __forceinline__ void store_staged(const Params& p, float* Cz, const f
           o.x = m4[u].x > 0.f ? o.x : 0.f; o.y = m4[u].y > 0.f ? o.y : 0.f;
           o.z = m4[u].z > 0.f ? o.z : 0.f; o.w = m4[u].w > 0.f ? o.w : 0.f;
           o.x += a4[u].x; o.y += a4[u].y; o.z += a4[u].z; o.w += a4[u].w;
+          nib = (o.x > 0.f ? 1u : 0u) | (o.y > 0.f ? 2u : 0u) | (o.z > 0.f ? 4u : 0u) | (o.w > 0.f ? 8u : 0u);
           if (!p.no_f32) *reinterpret_cast<float4*>(dstp) = o;
           if (vmax) *vmax = fmaxf(fmaxf(*vmax, fmaxf(fabsf(o.x), fabsf(o.y))), fmaxf(fabsf(o.z), fabsf(o.w)));
           if (p.c_hi) {
@@ -268,6 +287,11 @@ __device__ __forceinline__ void store_staged(const Params& p, float* Cz, const f
           }
         }
       }
+      if (p.bits_out) {                  // uniform (CW == 64: 16 lanes per row, two rows per instruction); layout: relu_bits_words
+        const uint2 w = relu_bits_words(nib, lane);
+        if ((lane & 15) == 0 && grow < p.M && col < p.N)
+          *reinterpret_cast<uint2*>(p.bits_out + (size_t)grow * p.ld_bits + (col >> 5)) = w;
+      }
     }
   }
 }
@@ -276,7 +300,7 @@ __device__ __forceinline__ void store_staged(const Params& p, float* Cz, const f
 // pointer increment per store.  (ncu on the persistent f16x3 kernel: the general version above executes ~300
 // instructions per 16-byte store -- 64-bit address arithmetic, constant-bank reloads and tail predicates -- which made
 // the epilogue of a 128 x 256 tile 17.7k cycles and instruction-bound.)
-template <int CW, bool MASK, bool PLANES, bool BF16OUT = false>
+template <int CW, bool MASK, bool PLANES, bool BF16OUT = false, bool BITS = false>
 __device__ __forceinline__ void store_staged_interior(const Params& p, float* __restrict__ Cz, const float4* stg, int lane,
                                                       int grow0, int col0, float* vmax) {
   constexpr int S = CW / 4;                        // float4 slots per row
@@ -295,6 +319,10 @@ __device__ __forceinline__ void store_staged_interior(const Params& p, float* __
   const float* mk = (MASK && !m16) ? p.mask + (size_t)(grow0 + sub_r) * p.ld_mask + col : nullptr;
   const uint16_t* mk16 = m16 ? p.mask16 + (size_t)(grow0 + sub_r) * p.ld_mask + col : nullptr;
   const size_t dstep = (size_t)RPI * p.ldc, mstep = MASK ? (size_t)RPI * p.ld_mask : 0;
+  // (every lane of a row's half-warp stores the same two words to the same address: one transaction, and no divergent
+  //  branch in the loop -- a lane-0-only store put a BSSY / BSYNC region into every iteration and serialised the loop)
+  uint32_t* dbits = BITS ? p.bits_out + (size_t)(grow0 + sub_r) * p.ld_bits + (col0 >> 5) : nullptr;
+  const size_t bstep = BITS ? (size_t)RPI * p.ld_bits : 0;
   const bool f32 = !p.no_f32;
   float vm = 0.f;
 #pragma unroll
@@ -321,6 +349,11 @@ __device__ __forceinline__ void store_staged_interior(const Params& p, float* __
       }
       if (f32) *reinterpret_cast<float4*>(dst) = o;
       dst += dstep;
+      if (BITS) {
+        const uint2 w = relu_bits_words((o.x > 0.f ? 1u : 0u) | (o.y > 0.f ? 2u : 0u) | (o.z > 0.f ? 4u : 0u) | (o.w > 0.f ? 8u : 0u), lane);
+        *reinterpret_cast<uint2*>(dbits) = w;
+        dbits += bstep;
+      }
       if (PLANES) {
         uint2 h, l;
         h3_split4(o, cs, h, l);
@@ -333,6 +366,55 @@ __device__ __forceinline__ void store_staged_interior(const Params& p, float* __
         d16 += dstep;
       }
       vm = fmaxf(fmaxf(vm, fmaxf(fabsf(o.x), fabsf(o.y))), fmaxf(fabsf(o.z), fabsf(o.w)));
+    }
+  }
+  if (vmax) *vmax = fmaxf(*vmax, vm);
+}
+
+// A sub-tile whose columns lie inside the matrix but whose LAST rows do not (M = 16385: the discriminator chain's extra
+// row makes a 65th row tile with one valid row): one compact, non-unrolled loop over the valid row pairs with every
+// epilogue option decided at run time.  (The general walk above spends ~10k instructions per warp on such a sub-tile
+// whatever the number of valid rows; as the tail of a persistent kernel that was ~20 us per layer.)
+template <int CW>
+__device__ __forceinline__ void store_staged_rows(const Params& p, float* __restrict__ Cz, const float4* stg, int lane, int grow0,
+                                                  int col0, int nrows, float* vmax) {
+  constexpr int S = CW / 4, RPI = 32 / S;
+  static_assert(S == 16, "two rows per store instruction (relu_bits_words)");
+  const int sub_r = lane / S, sl = lane % S, col = col0 + 4 * sl;
+  float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (p.bias) bb = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+  float vm = 0.f;
+#pragma unroll 1
+  for (int i = 0; i * RPI < nrows; ++i) {          // warp-uniform bound
+    const int r = i * RPI + sub_r;
+    const bool ok = r < nrows;
+    const size_t grow = (size_t)(grow0 + r);
+    float4 o = stg[r * S + (sl ^ (r & 7))];
+    o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+    if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+    uint32_t nib = 0u;
+    if (ok) {
+      if (p.mask16 || p.mask) {
+        const float4 m4 = p.mask16 ? mask4_from16(p.mask16 + grow * p.ld_mask + col)
+                                   : __ldg(reinterpret_cast<const float4*>(p.mask + grow * p.ld_mask + col));
+        o.x = m4.x > 0.f ? o.x : 0.f; o.y = m4.y > 0.f ? o.y : 0.f; o.z = m4.z > 0.f ? o.z : 0.f; o.w = m4.w > 0.f ? o.w : 0.f;
+      }
+      nib = (o.x > 0.f ? 1u : 0u) | (o.y > 0.f ? 2u : 0u) | (o.z > 0.f ? 4u : 0u) | (o.w > 0.f ? 8u : 0u);
+      const size_t off = grow * p.ldc + col;
+      if (!p.no_f32) *reinterpret_cast<float4*>(Cz + off) = o;
+      if (p.c_hi) {
+        uint2 h, l;
+        h3_split4(o, p.c_scale, h, l);
+        *reinterpret_cast<uint2*>(p.c_hi + off) = h;
+        *reinterpret_cast<uint2*>(p.c_hi + p.c_plane + off) = l;
+      }
+      if (p.C16 && p.c16_in_staged)
+        *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(p.C16) + off) = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+      vm = fmaxf(fmaxf(vm, fmaxf(fabsf(o.x), fabsf(o.y))), fmaxf(fabsf(o.z), fabsf(o.w)));
+    }
+    if (p.bits_out) {                                // uniform: the ballots need every lane
+      const uint2 w = relu_bits_words(nib, lane);
+      if (ok) *reinterpret_cast<uint2*>(p.bits_out + grow * p.ld_bits + (col0 >> 5)) = w;
     }
   }
   if (vmax) *vmax = fmaxf(*vmax, vm);
@@ -963,8 +1045,16 @@ struct ParamsP {
                                 //   layer and writes the planes with the scale that max|C| asks for
 };
 
+// Warps of the persistent kernel: warpgroup 0 = {TMA producer, MMA issuer, two idle warps}, warpgroups 1 and 2 = the eight
+// workers.  Registers are re-split after the set-up (setmaxnreg): an SM sub-partition holds 16K registers and, with ten
+// warps, three warps -- a cap of 168 per thread, under which the workers (128 accumulator registers + a 32-register TMEM
+// load + addressing) spilled 264 .. 424 bytes in the drain loop.  Twelve warps = three per sub-partition (one of
+// warpgroup 0, two workers): 56 + 2 x 224 = 504 <= 512.
+constexpr int P_THREADS = 384;
+constexpr int P_WORKER0 = 4;          // first worker warp
+constexpr int P_REGS_LIGHT = 56, P_REGS_WORKER = 224;
 template <int BN, bool SINGLE, bool PAIR>
-__global__ void __launch_bounds__(X3_THREADS, 1)
+__global__ void __launch_bounds__(P_THREADS, 1)
 gemm_tc_h3p_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                    const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
                    const __grid_constant__ CUtensorMap tmC, const ParamsP pp) {
@@ -1024,6 +1114,10 @@ gemm_tc_h3p_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr) : "memory");
 
+  // (the register re-split sits INSIDE each warpgroup's branch: ptxas allocates the code behind a setmaxnreg with that
+  //  count, and code behind a merge of both branches with the smaller one)
+  if (warp < P_WORKER0) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(P_REGS_LIGHT));
   if (warp == 0) {
     // ===================== TMA producer: runs ahead across tile boundaries =====================
     if (lane == 0) {
@@ -1131,16 +1225,18 @@ gemm_tc_h3p_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
       }
     }
     if (dbg && lane == 0) { dbg[0] = clock64() - t_begin; dbg[1] = w_empty; dbg[2] = w_full; dbg[7] = t_begin - t_entry; }
-  } else if (warp >= 2) {
+  }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(P_REGS_WORKER));
     // ===================== workers: chunk drains + epilogue =====================
     const int q = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int half = (warp - P_WORKER0) >> 2;
     const uint32_t t_lane = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(half * CPW);
     float sa, sb, ia, ib;
     h3_slot_scale(pp.a_amax, sa, ia);
     h3_slot_scale(pp.b_amax, sb, ib);
     const float inv = SINGLE ? 1.0f : ia * ib;       // one-plane operands are not scaled
-    float4* stg = reinterpret_cast<float4*>(base_ptr + C::STAGES * C::STAGE_BYTES + (32 * C::EPI_COLS * 4) * (warp - 2));
+    float4* stg = reinterpret_cast<float4*>(base_ptr + C::STAGES * C::STAGE_BYTES + (32 * C::EPI_COLS * 4) * (warp - P_WORKER0));
     uint32_t g = 0;
     Params p = pp.p;                             // worker-local copy: the scale of C's planes is read from C's slot
     if (p.c_hi) {
@@ -1152,7 +1248,7 @@ gemm_tc_h3p_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
     }
     float vmax = 0.f;
     float* const vm = (p.c_amax && !pp.repair) ? &vmax : nullptr;
-    long long* const dbg = (p.dbg && blockIdx.x == 0 && warp == 2) ? p.dbg : nullptr;
+    long long* const dbg = (p.dbg && blockIdx.x == 0 && warp == P_WORKER0) ? p.dbg : nullptr;
     long long w_accfull = 0, t_drain = 0, t_epi = 0;
     const long long t_begin = clock64();
     uint32_t acc_empty_remote[2];
@@ -1165,6 +1261,15 @@ gemm_tc_h3p_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
       float acc[CPW];
 #pragma unroll
       for (int j = 0; j < CPW; ++j) acc[j] = 0.f;
+      // ReLU bit plane of the mask source: this lane's accumulator row x the warp's CPW columns = CPW / 32 words = one
+      // 16-byte load at the start of the epilogue (host: CPW == 128, ld_bits % 4 == 0, N % 128 == 0).  Only a prefetch
+      // here: holding the four words across the chunk drains cost more (register cap 168: 29k -> 47k cycles of drains
+      // per four tiles) than the L2 round trip they would hide.
+      if (!SINGLE && CPW == 128 && p.bits_in) {
+        const int brow = m0 + 32 * q + lane, bc0 = n0 + half * CPW;
+        if (brow < p.M && bc0 < p.N)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(p.bits_in + (size_t)brow * p.ld_bits + (bc0 >> 5)));
+      }
       for (int kb = 0; kb < num_kb; ++g) {
         const uint32_t b = g & 1u;
         const int n = min(pp.chunk_kb, num_kb - kb);
@@ -1196,6 +1301,9 @@ gemm_tc_h3p_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
       const bool vec = epilogue_vec_ok(p, Cz);
       const int row = m0 + 32 * q + lane;
       const int cw0 = n0 + half * CPW;
+      uint4 mbits = make_uint4(0u, 0u, 0u, 0u);
+      if (!SINGLE && CPW == 128 && p.bits_in && row < p.M && cw0 < p.N)
+        mbits = __ldg(reinterpret_cast<const uint4*>(p.bits_in + (size_t)row * p.ld_bits + (cw0 >> 5)));
       if (pp.tma_store) {
         // 32 columns at a time, in the accumulator's own layout (lane = row): scale, bias / ReLU / ReLU-mask in registers,
         // then a swizzled [32 x 32] box in shared memory (two boxes per warp, alternating) that ONE lane hands to the TMA
@@ -1249,12 +1357,26 @@ gemm_tc_h3p_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
 #pragma unroll
       for (int ps = 0; ps < CPW / C::EPI_COLS; ++ps) {
         const int c0 = cw0 + ps * C::EPI_COLS;
-        if (c0 < p.N && !(p.pair_flags & 1)) {   // warp-uniform (flag: experiment without the stores)
+        // warp-uniform (flag: experiment without the stores).  A warp whose 32 rows all lie beyond M has nothing to store:
+        // with M = 16385 (the discriminator chain) the guarded edge path below ran for all 16 warps of the last row tile
+        // and made every such layer ~20 us longer than its 16384-row twin.
+        if (c0 < p.N && m0 + 32 * q < p.M && !(p.pair_flags & 1)) {
           if (vec) {
+            if (!SINGLE && CPW == 128 && p.bits_in) {      // the ReLU mask, applied where a lane still owns its row
+              static_assert(C::EPI_COLS == 64, "the bit-plane layout is defined per 64-column staging pass");
+              const uint32_t w0 = ps == 0 ? mbits.x : mbits.z, w1 = ps == 0 ? mbits.y : mbits.w;      // relu_bits_words
+#pragma unroll
+              for (int sl = 0; sl < C::EPI_COLS / 4; ++sl) {
+                const int j = ps * C::EPI_COLS + 4 * sl;
+                stage_put<C::EPI_COLS>(stg, lane, sl, ((w0 >> sl) & 1u) ? acc[j] * inv : 0.f, ((w0 >> (16 + sl)) & 1u) ? acc[j + 1] * inv : 0.f,
+                                       ((w1 >> sl) & 1u) ? acc[j + 2] * inv : 0.f, ((w1 >> (16 + sl)) & 1u) ? acc[j + 3] * inv : 0.f);
+              }
+            } else {
 #pragma unroll
             for (int sl = 0; sl < C::EPI_COLS / 4; ++sl) {
               const int j = ps * C::EPI_COLS + 4 * sl;
               stage_put<C::EPI_COLS>(stg, lane, sl, acc[j] * inv, acc[j + 1] * inv, acc[j + 2] * inv, acc[j + 3] * inv);
+            }
             }
             __syncwarp();
             if (m0 + 32 * q + 32 <= p.M && c0 + C::EPI_COLS <= p.N && !p.accumulate) {     // warp-uniform
@@ -1263,6 +1385,9 @@ gemm_tc_h3p_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
                 else store_staged_interior<C::EPI_COLS, false, false, true>(p, Cz, stg, lane, m0 + 32 * q, c0, vm);
               // (a variant with eight columns per lane -- 16-byte plane stores, 16-byte mask loads -- measured slower in the
               //  whole update: 90.8 against 88.4 ms per iteration on one box)
+              } else if (!SINGLE && p.bits_out) {          // a ReLU layer that leaves its mask behind as bits (never masked itself)
+                if (p.c_hi) store_staged_interior<C::EPI_COLS, false, true, false, true>(p, Cz, stg, lane, m0 + 32 * q, c0, vm);
+                else store_staged_interior<C::EPI_COLS, false, false, false, true>(p, Cz, stg, lane, m0 + 32 * q, c0, vm);
               } else if (!SINGLE && p.c_hi) {
                 if (p.mask || p.mask16) store_staged_interior<C::EPI_COLS, true, true>(p, Cz, stg, lane, m0 + 32 * q, c0, vm);
                 else store_staged_interior<C::EPI_COLS, false, true>(p, Cz, stg, lane, m0 + 32 * q, c0, vm);
@@ -1270,6 +1395,8 @@ gemm_tc_h3p_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
                 if (p.mask || p.mask16) store_staged_interior<C::EPI_COLS, true, false>(p, Cz, stg, lane, m0 + 32 * q, c0, vm);
                 else store_staged_interior<C::EPI_COLS, false, false>(p, Cz, stg, lane, m0 + 32 * q, c0, vm);
               }
+            } else if (c0 + C::EPI_COLS <= p.N && !p.accumulate) {      // ragged rows only
+              store_staged_rows<C::EPI_COLS>(p, Cz, stg, lane, m0 + 32 * q, c0, p.M - (m0 + 32 * q), vm);
             } else {
               store_staged<C::EPI_COLS>(p, Cz, stg, lane, m0 + 32 * q, c0, vm);
             }
@@ -1364,7 +1491,7 @@ static int launch_h3p(cudaStream_t st, const CUtensorMap& tah, const CUtensorMap
   // the fp32 output leaves through TMA stores when its geometry allows (and nothing else rides on the epilogue)
   CUtensorMap tc = tah;
   pp.tma_store = 0; pp.repair = 0;
-  if (addk_switches().h3_tma_store && pp.p.C && !pp.p.accumulate && !pp.p.c_hi && !(SINGLE && pp.p.C16) &&
+  if (addk_switches().h3_tma_store && pp.p.C && !pp.p.accumulate && !pp.p.c_hi && !(SINGLE && pp.p.C16) && !pp.p.bits_out && !pp.p.bits_in &&
       (!pp.p.bias || (reinterpret_cast<uintptr_t>(pp.p.bias) & 15) == 0) &&
       (!pp.p.mask || ((pp.p.ld_mask & 3) == 0 && (reinterpret_cast<uintptr_t>(pp.p.mask) & 15) == 0)) &&
       make_map_c(&tc, pp.p.C, N, M, pp.p.ldc, split, pp.p.slab_stride))
@@ -1386,7 +1513,7 @@ static int launch_h3p(cudaStream_t st, const CUtensorMap& tah, const CUtensorMap
     const int grid = pp.total_tiles < sm_count() ? pp.total_tiles : sm_count();
     for (int l = 0; l < launches; ++l) {
       pp.repair = l;
-      gemm_tc_h3p_kernel<BN, SINGLE, PAIR><<<grid, X3_THREADS, C::SMEM_BYTES, st>>>(tah, tal, tbh, tbl, tc, pp);
+      gemm_tc_h3p_kernel<BN, SINGLE, PAIR><<<grid, P_THREADS, C::SMEM_BYTES, st>>>(tah, tal, tbh, tbl, tc, pp);
     }
     return ADDK_OK;
   }
@@ -1394,7 +1521,7 @@ static int launch_h3p(cudaStream_t st, const CUtensorMap& tah, const CUtensorMap
   const int units = pp.total_tiles < pairs ? pp.total_tiles : pairs;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(2 * units, 1, 1);
-  cfg.blockDim = dim3(X3_THREADS, 1, 1);
+  cfg.blockDim = dim3(P_THREADS, 1, 1);
   cfg.dynamicSmemBytes = C::SMEM_BYTES;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -1718,6 +1845,17 @@ static int gemm_h3(cudaStream_t st, const addk_gemm_args& a) {
       pp.p.no_f32 = 1;
     }
     if (a.relu_mask_src16) { pp.p.mask16 = reinterpret_cast<const uint16_t*>(a.relu_mask_src16); pp.p.mask = nullptr; }
+    if (a.relu_bits_out || a.relu_bits_in) {      // ReLU masks as bit planes
+      const uintptr_t bo = reinterpret_cast<uintptr_t>(a.relu_bits_out), bi = reinterpret_cast<uintptr_t>(a.relu_bits_in);
+      if ((a.N & 127) || (a.ld_bits & 3) || a.ld_bits * 32 < a.N || ((bo | bi) & 15) || (a.ldc & 3) || split != 1 || a.accumulate ||
+          (a.relu_bits_out && (!a.relu || a.relu_bits_in || a.relu_mask_src || a.relu_mask_src16))) {
+        addk_set_error("gemm f16x3: relu_bits_* need N % 128 == 0, ld_bits % 4 == 0 (>= N / 32), 16-byte aligned bit planes, one slab; "
+                       "relu_bits_out a ReLU layer without a mask of its own");
+        return ADDK_ERR_ARG;
+      }
+      pp.p.bits_out = a.relu_bits_out; pp.p.ld_bits = a.ld_bits;
+      if (a.relu_bits_in) { pp.p.bits_in = a.relu_bits_in; pp.p.mask = nullptr; pp.p.mask16 = nullptr; }
+    }
     pp.chunk_kb = addk_switches().h3_chunk_kb;
     g_addk_last_gemm_kernel = ADDK_K_H3_PERSISTENT;
     if (addk_switches().h3_pair && a.M > BM) {      // CTA pairs (cta_group::2): each CTA stages a 128-row half of B
@@ -1727,7 +1865,7 @@ static int gemm_h3(cudaStream_t st, const addk_gemm_args& a) {
     return launch_h3p<256>(st, tah, tal, tbh, tbl, pp, a.M, a.N, split);
   }
   g_addk_last_gemm_kernel = ADDK_K_H3_TILE;
-  if (a.no_f32 || a.relu_mask_src16) { addk_set_error("gemm f16x3: no_f32 / relu_mask_src16 need the persistent kernel"); return ADDK_ERR_ARG; }
+  if (a.no_f32 || a.relu_mask_src16 || a.relu_bits_in || a.relu_bits_out) { addk_set_error("gemm f16x3: no_f32 / relu_mask_src16 / relu_bits_* need the persistent kernel"); return ADDK_ERR_ARG; }
   if (BN == 256) return launch_h3<256>(st, tah, tal, tbh, tbl, ph, grid);
   if (BN == 128) return launch_h3<128>(st, tah, tal, tbh, tbl, ph, grid);
   return launch_h3<64>(st, tah, tal, tbh, tbl, ph, grid);
@@ -1749,6 +1887,10 @@ extern "C" int addk_gemm_is_persistent(const addk_gemm_args* a, int precision) {
 static int gemm_fallback(cudaStream_t st, const addk_gemm_args& a);
 
 int addk_gemm_tc(cudaStream_t st, const addk_gemm_args& a, int precision) {
+  if ((a.relu_bits_in || a.relu_bits_out) && !(precision == 4 && addk_gemm_is_persistent(&a, 4))) {
+    addk_set_error("gemm: relu_bits_in / relu_bits_out are honoured by the persistent f16x3 kernel only (addk_gemm_is_persistent)");
+    return ADDK_ERR_ARG;
+  }
   if (precision == 4) {
     // fp16 hi/lo planes when the call carries twins that TMA can address (16-byte row pitch = 8 elements, 16-byte
     // aligned planes); otherwise the fallback on the fp32 operands

@@ -767,7 +767,14 @@ static thread_local TwinEnt g_tw[TWIN_ENTRIES];
 static thread_local int g_ntw = 0;
 static thread_local int g_slot_base = 0;       // each entry point owns TWIN_SLOTS slots
 static thread_local int g_next_slot = 0;       // slots [TWIN_ENTRIES, TWIN_SLOTS) are handed out once per call, pre-zeroed
-static void twin_reset(int entry_point) { g_ntw = 0; g_slot_base = TWIN_SLOTS * entry_point; g_next_slot = TWIN_ENTRIES; }
+// ReLU masks as bit planes (f16x3, optimizer step only): which arena tensors currently have a valid bit plane in
+// arena_bits (written by the epilogue of the ReLU layer that produced them), in ISSUE order like the twin table
+struct BitsEnt { const float* p; long long rows; int cols, ld; cudaStream_t st; bool valid; };
+constexpr int BITS_ENTRIES = 16;
+static thread_local BitsEnt g_bits[BITS_ENTRIES];
+static thread_local int g_nbits = 0;
+static thread_local bool g_want_bits = false;      // set by addk_update_minibatch (inference entry points do not need masks)
+static void twin_reset(int entry_point) { g_ntw = 0; g_slot_base = TWIN_SLOTS * entry_point; g_next_slot = TWIN_ENTRIES; g_nbits = 0; g_want_bits = false; }
 static uint32_t* slot_ptr(const addk_update_ctx& c, int slot) { return (uint32_t*)c.amax_slots + 2 * (1 + g_slot_base + slot); }
 static uint32_t* twin_slot(const addk_update_ctx& c, int e) { return slot_ptr(c, g_tw[e].slot); }
 static void twin_invalidate(const void* p, size_t bytes) {
@@ -776,6 +783,16 @@ static void twin_invalidate(const void* p, size_t bytes) {
     const char* q = (const char*)g_tw[i].p;
     if (q >= b && q < b + (bytes ? bytes : 1)) { g_tw[i].valid = false; g_tw[i].amax_known = false; }
   }
+  for (int i = 0; i < g_nbits; ++i) {
+    const char* q = (const char*)g_bits[i].p;
+    if (q >= b && q < b + (bytes ? bytes : 1)) g_bits[i].valid = false;
+  }
+}
+// word pointer of the bit plane of arena tensor p (NULL: no bit planes / not an arena tensor / not on a 128-element boundary)
+static uint32_t* bits_ptr(const addk_update_ctx& c, const float* p, int ld) {
+  const float* a0 = (const float*)c.arena;
+  if (!c.arena_bits || !a0 || !p || p < a0 || p >= a0 + c.arena_elems || ((p - a0) & 127) || (ld & 127)) return nullptr;
+  return (uint32_t*)c.arena_bits + (p - a0) / 32;
 }
 struct H3Op { const void* hi; long long plane; uint32_t* amax; int ready; long long full_rows; int full_cols; };
 // looks the operand up; on a miss the entry is created / refreshed and ready = 0 tells the library to convert first
@@ -982,9 +999,34 @@ static int gemm(cudaStream_t st, int prec, const float* A, int lda, int ta, cons
     a.relu_mask_src16 = (const uint16_t*)c.arena16 + (mask - (const float*)c.arena);
     a.relu_mask_src = nullptr;
   }
+  a.relu_bits_out = nullptr; a.relu_bits_in = nullptr; a.ld_bits = 0;
+  int bits_ent = -1;
+  if (prec == 4 && g_twin_ctx && g_want_bits && a.A16 && a.B16 && split == 1 && (N & 127) == 0 && addk_gemm_is_persistent(&a, 4)) {
+    const addk_update_ctx& c = *g_twin_ctx;
+    if (mask) {                  // the mask source's ReLU bits, if the layer that produced it left them behind (same stream)
+      for (int i = 0; i < g_nbits; ++i) {
+        const BitsEnt& b = g_bits[i];
+        if (b.p == mask && b.valid && b.st == st && b.ld == ld_mask && N <= b.cols && M <= b.rows) {
+          a.relu_bits_in = bits_ptr(c, mask, ld_mask); a.ld_bits = ld_mask / 32;
+          break;
+        }
+      }
+    } else if (relu) {           // a ReLU layer of the optimizer step: its output is (also) the mask of the backward pass
+      uint32_t* bo = bits_ptr(c, C, ldc);
+      if (bo) {
+        for (int i = 0; i < g_nbits; ++i) if (g_bits[i].p == C) { bits_ent = i; break; }
+        if (bits_ent < 0 && g_nbits < BITS_ENTRIES) bits_ent = g_nbits++;
+        if (bits_ent >= 0) {
+          g_bits[bits_ent] = BitsEnt{C, M, N, ldc, st, false};
+          a.relu_bits_out = bo; a.ld_bits = ldc / 32;
+        }
+      }
+    }
+  }
   int rc = prec == 0 ? addk::sgemm_launch(st, a) : addk_gemm_tc(st, a, prec);
   if (rc != ADDK_OK) return rc;
   ADDK_CHECK_LAUNCH();
+  if (bits_ent >= 0) g_bits[bits_ent].valid = true;
   if (c_ent >= 0) {     // planes written by the epilogue: rewritten only if the sticky scale did not fit max|C|
     if (!planes_only) {   // (planes-only layers repair themselves: second launch inside addk_gemm)
       rc = addk_f16x3_repair(st, C, M, N, ldc, a.C16, a.c16_plane, a.c_amax);
@@ -1185,6 +1227,7 @@ extern "C" int addk_update_minibatch(void* stream, void* ctx_host, const long lo
     ADDK_CHECK_LAUNCH();
   }
   TRY(h3_params(c, st, 0));
+  g_want_bits = c.precision == 4 && c.arena_bits != nullptr && addk_switches().h3_relu_bits != 0;
 
   uint16_t* const xn16 = twin16(c.xn);
   uint16_t* const dn16 = twin16(c.dn);

@@ -264,6 +264,16 @@ typedef struct addk_gemm_args {
    * copy), pitch ld_mask ELEMENTS, used instead of relu_mask_src: element > 0 <=> sign clear and magnitude non-zero. */
   const void* relu_mask_src16;
   int32_t no_f32;
+  /* ReLU masks as bit planes (precision "f16x3", persistent kernel, N a multiple of 128): a layer with relu = 1 and
+   * relu_bits_out != NULL also leaves one bit per output element behind (set where the output is > 0; column
+   * c = 64 g + 4 i + k, i < 16, k < 4, of a row lives in word [row * ld_bits + 2 g + (k >> 1)], bit 16 (k & 1) + i --
+   * the order the store loop's warp ballots produce); a later layer masks its output with relu_bits_in instead of reading a whole
+   * [M,N] mask tensor (relu_mask_src / relu_mask_src16 are then ignored): 1/32 .. 1/16 of the bytes, one 16-byte load
+   * per accumulator row and tile instead of 32 latency-bound loads in the store loop.  ld_bits in 32-bit WORDS, a
+   * multiple of 4; both pointers 16-byte aligned.  Only the kernels addk_gemm_is_persistent() reports honour them. */
+  uint32_t* relu_bits_out;
+  const uint32_t* relu_bits_in;
+  int32_t ld_bits;
 } addk_gemm_args;
 /* 1 if addk_gemm would run this call on a persistent tensor-core kernel (the only ones that honour no_f32 /
  * relu_mask_src16), given 16-bit operands TMA can address */

@@ -161,7 +161,7 @@ class _Twin:
 
 
 def _gemm_h3(A, B, Cout, M, N, K, ta, tb, tw_a, tw_b, ready=(0, 0), bias=None, relu=0, mask=None, split=1, accumulate=0,
-             c_amax=None, c16=None):
+             c_amax=None, c16=None, bits_out=None, bits_in=None, no_f32=0):
     from add_gym_b200 import _lib
     a = _lib.AddkGemmArgs(A=A.data_ptr(), lda=A.stride(0), B=B.data_ptr(), ldb=B.stride(0), C=Cout.data_ptr(),
                           ldc=Cout.stride(-2), M=M, N=N, K=K, bias=bias.data_ptr() if bias is not None else None,
@@ -171,7 +171,13 @@ def _gemm_h3(A, B, Cout, M, N, K, ta, tb, tw_a, tw_b, ready=(0, 0), bias=None, r
                           B16=tw_b.planes.data_ptr(), a16_plane=tw_a.n, b16_plane=tw_b.n,
                           a_amax=tw_a.amax.data_ptr(), b_amax=tw_b.amax.data_ptr(), a16_ready=ready[0], b16_ready=ready[1],
                           c_amax=c_amax.data_ptr() if c_amax is not None else None,
-                          C16=c16.planes.data_ptr() if c16 is not None else None, c16_plane=c16.n if c16 is not None else 0)
+                          C16=c16.planes.data_ptr() if c16 is not None else None, c16_plane=c16.n if c16 is not None else 0,
+                          no_f32=no_f32)
+    bits = bits_out if bits_out is not None else bits_in
+    if bits is not None:      # ReLU bit plane [rows, ld_bits] int32
+        a.ld_bits = bits.stride(0)
+        a.relu_bits_out = bits.data_ptr() if bits_out is not None else None
+        a.relu_bits_in = bits.data_ptr() if bits_in is not None else None
     _lib.check(_lib.lib().addk_gemm(_lib.stream(), C.byref(a), C.c_int(_lib.PRECISIONS["f16x3"])), "addk_gemm")
 
 
@@ -360,6 +366,67 @@ def test_gemm_f16x3_persistent_kernel_layouts_and_epilogues(case):
     out2 = torch.full((M, N), float("nan"), device="cuda") if epi != "accumulate" else base.clone()
     _gemm_h3(A, B, out2, M, N, K, ta, tb, tw_a, tw_b, ready=(1, 1), **kw)
     assert torch.equal(out, out2)
+
+
+@pytest.mark.parametrize("M,planes_only", [(MB, False), (MB + 1, False), (MB + 1, True), (5000, True)])
+def test_gemm_f16x3_relu_bit_planes(M, planes_only):
+    """ReLU masks as bit planes: a forward layer (bias + ReLU, fp32 or planes-only output) leaves one bit per output
+    element behind; the input-gradient layer masked by those bits equals the layer masked by the fp32 tensor itself
+    (bit for bit) and float64 masked by (forward output > 0).  Ragged row counts exercise the edge path of both sides."""
+    from add_gym_b200 import _lib
+    g = torch.Generator(device="cuda").manual_seed(11)
+    K, N = 512, 1024
+    X = torch.randn(M, K, device="cuda", generator=g)
+    W = torch.randn(N, K, device="cuda", generator=g) * 0.05
+    bias = torch.randn(N, device="cuda", generator=g) * 0.1
+    tX, tW = _Twin(X), _Twin(W)
+    h = torch.full((M, N), float("nan"), device="cuda")
+    bits = torch.full((M, N // 32), -1, device="cuda", dtype=torch.int32)
+    kw = {}
+    if planes_only:
+        tH = _Twin(h)
+        slot = C.c_void_p(tH.amax.data_ptr())
+        for _ in range(2):      # second round: the sticky scale is in force and the epilogue's planes stand
+            _lib.check(_lib.lib().addk_f16x3_prep(_lib.stream(), slot, C.c_int(1)), "prep")
+            _gemm_h3(X, W, h, M, N, K, 0, 1, tX, tW, bias=bias, relu=1, c_amax=tH.amax, c16=tH, bits_out=bits, no_f32=1)
+    else:
+        _gemm_h3(X, W, h, M, N, K, 0, 1, tX, tW, bias=bias, relu=1, bits_out=bits)
+    torch.cuda.synchronize()
+    assert _last_kernel() in K_H3_PERSISTENT
+    href = torch.relu(X.double() @ W.double().t() + bias.double())
+    if planes_only:
+        assert bool(torch.isnan(h).all()), "planes-only: the fp32 output must not be written"
+        s = 2.0 ** (14 - (((int(tH.amax[0].item()) >> 23) & 0xFF) - 127))
+        hval = (tH.planes[:M * N].view(M, N).double() + tH.planes[tH.n:tH.n + M * N].view(M, N).double()) / s
+        assert _rel(hval, href) <= TOL["f16x3"]
+    else:
+        hval = h.double()
+    # the bit plane against the kernel's own output: bit set <=> element > 0 (elements within rounding of zero excluded
+    # when the comparison is against float64)
+    # layout (include/addk.h): column 64 g + 4 i + k of a row -> word 2 g + (k >> 1), bit 16 (k & 1) + i
+    col = torch.arange(N, device="cuda")
+    gi, ii, kk = col // 64, (col % 64) // 4, col % 4
+    word = bits[:, (2 * gi + (kk >> 1))]
+    got = ((word >> (16 * (kk & 1) + ii).to(torch.int32)) & 1).bool()
+    if not planes_only:
+        assert torch.equal(got, h > 0)
+    clear = href.abs() > 1e-4
+    assert torch.equal(got[clear], (href > 0)[clear])
+    # consumer: dX = (dY . W2) * mask with W2 [N2 = 256... here the mask has N columns, so the product must be [M, N]
+    K2 = 512
+    dY = torch.randn(M, K2, device="cuda", generator=g) * 1e-5
+    W2 = torch.randn(K2, N, device="cuda", generator=g) * 0.05
+    tdY, tW2 = _Twin(dY), _Twin(W2)
+    out_bits = torch.full((M, N), float("nan"), device="cuda")
+    _gemm_h3(dY, W2, out_bits, M, N, K2, 0, 0, tdY, tW2, bits_in=bits)
+    torch.cuda.synchronize()
+    assert _last_kernel() in K_H3_PERSISTENT
+    ref = (dY.double() @ W2.double()) * got.double()
+    assert _rel(out_bits, ref) <= TOL["f16x3"]
+    maskf = got.float()                                     # the same mask as an fp32 tensor through the old path
+    out_mask = torch.full((M, N), float("nan"), device="cuda")
+    _gemm_h3(dY, W2, out_mask, M, N, K2, 0, 0, tdY, tW2, ready=(1, 1), mask=maskf)
+    assert torch.equal(out_bits, out_mask)
 
 
 def test_gemm_small_shapes_run_the_one_tile_kernel():

@@ -25,6 +25,11 @@ _lib.launch_count(reset=True)
 import time
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 idxs = [a._exp_buffer.sample_indices(a._mb_rows) for _ in range(steps)]
+if not os.environ.get("NO_WARM"):      # (ncu launch lists: NO_WARM=1 keeps the list short)
+    for s in range(3):                 # helper streams, tensor maps, sticky scales of the planes-only layers
+        _lib.check(_lib.lib().addk_update_minibatch(_lib.stream(), a._ctx.buf, _lib.ptr(idxs[s % steps]), C.c_int(s % a._max_steps), C.c_int(s + 1)), "mb")
+    torch.cuda.synchronize()
+    _lib.launch_count(reset=True)
 torch.cuda.synchronize()
 e0.record()
 t0 = time.perf_counter()
