@@ -151,11 +151,14 @@ __device__ __forceinline__ void h3_split4(const float4& o, float s, uint2& h, ui
   h = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
   l = make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
 }
-__device__ __forceinline__ void h3_emit1(const Params& p, size_t off, float v) {
-  const float xs = v * p.c_scale;
+// The epilogue fields a worker warp decides for itself (the rest of Params is read from the kernel parameters where it is
+// used: a whole worker-local copy of Params stayed live across the drain loop and pushed it over the register budget)
+struct EpiOv { uint16_t* c_hi; float c_scale; const float* bias; int relu; };
+__device__ __forceinline__ void h3_emit1(const Params& p, const EpiOv& e, size_t off, float v) {
+  const float xs = v * e.c_scale;
   const __half h = __float2half_rn(xs);
-  p.c_hi[off] = __half_as_ushort(h);
-  p.c_hi[p.c_plane + off] = __half_as_ushort(__float2half_rn(xs - __half2float(h)));
+  e.c_hi[off] = __half_as_ushort(h);
+  e.c_hi[p.c_plane + off] = __half_as_ushort(__float2half_rn(xs - __half2float(h)));
 }
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
@@ -189,27 +192,20 @@ __device__ __forceinline__ float4 mask4_from16(const uint16_t* m) {
 }
 __device__ __forceinline__ bool mask1_from16(const uint16_t* m) { return ((uint32_t)__ldg(m) - 1u) < 0x7FFFu; }
 
-// ReLU bit planes.  One store instruction of the row-major store loops covers two rows x 64 columns: lane = 16 * (row & 1)
-// + i holds columns 4i .. 4i+3 of its row and `nib` = their four "> 0" bits.  Four ballots (one per component, independent
-// of each other -- a shuffle reduction was a dependent chain of three per store and cost 6k cycles per tile) give, per
-// row, the two words of this 64-column group:  word 0 = {x bits of i = 0..15 | y bits << 16}, word 1 = {z | w << 16},
-// i.e. column 4i + k of group g lives in word 2g + (k >> 1), bit 16 (k & 1) + i.  The consumer (lane = row, before
-// staging) undoes exactly this; nothing else reads the planes.
-__device__ __forceinline__ uint2 relu_bits_words(uint32_t nib, int lane) {
-  const uint32_t bx = __ballot_sync(0xffffffffu, nib & 1u), by = __ballot_sync(0xffffffffu, nib & 2u);
-  const uint32_t bz = __ballot_sync(0xffffffffu, nib & 4u), bw = __ballot_sync(0xffffffffu, nib & 8u);
-  return (lane & 16) ? make_uint2((bx >> 16) | (by & 0xFFFF0000u), (bz >> 16) | (bw & 0xFFFF0000u))
-                     : make_uint2((bx & 0xFFFFu) | (by << 16), (bz & 0xFFFFu) | (bw << 16));
-}
-
+// ReLU bit planes (persistent f16x3 kernel).  Both sides work in the accumulator's own layout, where a lane owns one row
+// and the warp's 128 columns: the ReLU layer adds the bias, clamps and collects "> 0" bits BEFORE staging (four words per
+// lane and tile, one 16-byte store), the masked layer loads the same four words and zeroes its accumulators before
+// staging.  Layout of a row's words: column 64 g + 4 i + k (i < 16, k < 4) -> word 2 g + (k >> 1), bit 16 (k & 1) + i.
+// (First versions produced the bits in the row-major store loop -- a shuffle reduction, then four ballots per store
+// instruction: +28 instructions per 16-byte store and 4.5k cycles per tile on every ReLU layer.)
 template <int CW>
 __device__ __forceinline__ void stage_put(float4* stg, int lane, int slot, float a, float b, float c, float d) {
   stg[lane * (CW / 4) + (slot ^ (lane & 7))] = make_float4(a, b, c, d);
 }
 
 template <int CW>
-__device__ __forceinline__ void store_staged(const Params& p, float* Cz, const float4* stg, int lane, int grow0, int col0,
-                                             float* vmax = nullptr) {
+__device__ __forceinline__ void store_staged(const Params& p, const EpiOv& e, float* Cz, const float4* stg, int lane, int grow0, int col0,
+                                             float* vmax) {
   constexpr int S = CW / 4;                        // float4 slots per row
   constexpr int RPI = S >= 32 ? 1 : 32 / S;        // rows per store instruction
   constexpr int PPR = S > 32 ? S / 32 : 1;         // instructions per row
@@ -222,9 +218,9 @@ __device__ __forceinline__ void store_staged(const Params& p, float* Cz, const f
   for (int ps = 0; ps < PPR; ++ps) {
     const int col = col0 + 4 * (sl0 + 32 * ps);
     b4[ps] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (p.bias) {
-      if (col + 3 < p.N) b4[ps] = *reinterpret_cast<const float4*>(p.bias + col);
-      else { if (col < p.N) b4[ps].x = p.bias[col]; if (col + 1 < p.N) b4[ps].y = p.bias[col + 1]; if (col + 2 < p.N) b4[ps].z = p.bias[col + 2]; }
+    if (e.bias) {
+      if (col + 3 < p.N) b4[ps] = *reinterpret_cast<const float4*>(e.bias + col);
+      else { if (col < p.N) b4[ps].x = e.bias[col]; if (col + 1 < p.N) b4[ps].y = e.bias[col + 1]; if (col + 2 < p.N) b4[ps].z = e.bias[col + 2]; }
     }
   }
 #pragma unroll 1
@@ -250,47 +246,40 @@ __device__ __forceinline__ void store_staged(const Params& p, float* Cz, const f
       const int sl = sl0 + 32 * (it % PPR);
       const int grow = grow0 + r, col = col0 + 4 * sl;
       float4 o = stg[r * S + (sl ^ (r & 7))];
-      uint32_t nib = 0u;                 // ReLU bits of this lane's four outputs (bits_out)
       if (grow < p.M && col < p.N) {
         const float4 bb = b4[it % PPR];
         o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
-        if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+        if (e.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
         float* dstp = Cz + (size_t)grow * p.ldc + col;
         if (col + 3 < p.N) {
           o.x = m4[u].x > 0.f ? o.x : 0.f; o.y = m4[u].y > 0.f ? o.y : 0.f;
           o.z = m4[u].z > 0.f ? o.z : 0.f; o.w = m4[u].w > 0.f ? o.w : 0.f;
           o.x += a4[u].x; o.y += a4[u].y; o.z += a4[u].z; o.w += a4[u].w;
-          nib = (o.x > 0.f ? 1u : 0u) | (o.y > 0.f ? 2u : 0u) | (o.z > 0.f ? 4u : 0u) | (o.w > 0.f ? 8u : 0u);
           if (!p.no_f32) *reinterpret_cast<float4*>(dstp) = o;
           if (vmax) *vmax = fmaxf(fmaxf(*vmax, fmaxf(fabsf(o.x), fabsf(o.y))), fmaxf(fabsf(o.z), fabsf(o.w)));
-          if (p.c_hi) {
+          if (e.c_hi) {
             uint2 h, l;
-            h3_split4(o, p.c_scale, h, l);
+            h3_split4(o, e.c_scale, h, l);
             const size_t off = (size_t)grow * p.ldc + col;
-            *reinterpret_cast<uint2*>(p.c_hi + off) = h;
-            *reinterpret_cast<uint2*>(p.c_hi + p.c_plane + off) = l;
+            *reinterpret_cast<uint2*>(e.c_hi + off) = h;
+            *reinterpret_cast<uint2*>(e.c_hi + p.c_plane + off) = l;
           }
           if (p.C16 && p.c16_in_staged)
             *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(p.C16) + (size_t)grow * p.ldc + col) =
                 make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
         } else {
           const float oo[4] = {o.x, o.y, o.z, o.w};
-          for (int e = 0; e < 4 && col + e < p.N; ++e) {
-            float xv = oo[e];
-            if (p.mask16) xv = mask1_from16(p.mask16 + (size_t)grow * p.ld_mask + col + e) ? xv : 0.f;
-            else if (p.mask) xv = p.mask[(size_t)grow * p.ld_mask + col + e] > 0.f ? xv : 0.f;
-            if (p.accumulate) xv += dstp[e];
-            if (!p.no_f32) dstp[e] = xv;
+          for (int q4 = 0; q4 < 4 && col + q4 < p.N; ++q4) {
+            float xv = oo[q4];
+            if (p.mask16) xv = mask1_from16(p.mask16 + (size_t)grow * p.ld_mask + col + q4) ? xv : 0.f;
+            else if (p.mask) xv = p.mask[(size_t)grow * p.ld_mask + col + q4] > 0.f ? xv : 0.f;
+            if (p.accumulate) xv += dstp[q4];
+            if (!p.no_f32) dstp[q4] = xv;
             if (vmax) *vmax = fmaxf(*vmax, fabsf(xv));
-            if (p.c_hi) h3_emit1(p, (size_t)grow * p.ldc + col + e, xv);
-            if (p.C16 && p.c16_in_staged) reinterpret_cast<uint16_t*>(p.C16)[(size_t)grow * p.ldc + col + e] = (uint16_t)(pack_bf16x2(xv, 0.f) & 0xFFFFu);
+            if (e.c_hi) h3_emit1(p, e, (size_t)grow * p.ldc + col + q4, xv);
+            if (p.C16 && p.c16_in_staged) reinterpret_cast<uint16_t*>(p.C16)[(size_t)grow * p.ldc + col + q4] = (uint16_t)(pack_bf16x2(xv, 0.f) & 0xFFFFu);
           }
         }
-      }
-      if (p.bits_out) {                  // uniform (CW == 64: 16 lanes per row, two rows per instruction); layout: relu_bits_words
-        const uint2 w = relu_bits_words(nib, lane);
-        if ((lane & 15) == 0 && grow < p.M && col < p.N)
-          *reinterpret_cast<uint2*>(p.bits_out + (size_t)grow * p.ld_bits + (col >> 5)) = w;
       }
     }
   }
@@ -300,8 +289,8 @@ __device__ __forceinline__ void store_staged(const Params& p, float* Cz, const f
 // pointer increment per store.  (ncu on the persistent f16x3 kernel: the general version above executes ~300
 // instructions per 16-byte store -- 64-bit address arithmetic, constant-bank reloads and tail predicates -- which made
 // the epilogue of a 128 x 256 tile 17.7k cycles and instruction-bound.)
-template <int CW, bool MASK, bool PLANES, bool BF16OUT = false, bool BITS = false>
-__device__ __forceinline__ void store_staged_interior(const Params& p, float* __restrict__ Cz, const float4* stg, int lane,
+template <int CW, bool MASK, bool PLANES, bool BF16OUT = false>
+__device__ __forceinline__ void store_staged_interior(const Params& p, const EpiOv& e, float* __restrict__ Cz, const float4* stg, int lane,
                                                       int grow0, int col0, float* vmax) {
   constexpr int S = CW / 4;                        // float4 slots per row
   static_assert(S <= 32 && 32 % S == 0, "one store instruction covers 32 / S whole rows");
@@ -309,20 +298,16 @@ __device__ __forceinline__ void store_staged_interior(const Params& p, float* __
   const int sub_r = lane / S, sl = lane % S;
   const int col = col0 + 4 * sl;
   float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (p.bias) bb = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-  const bool relu = p.relu != 0;
+  if (e.bias) bb = __ldg(reinterpret_cast<const float4*>(e.bias + col));
+  const bool relu = e.relu != 0;
   float* dst = Cz + (size_t)(grow0 + sub_r) * p.ldc + col;
-  uint16_t* dhi = PLANES ? p.c_hi + (size_t)(grow0 + sub_r) * p.ldc + col : nullptr;
+  uint16_t* dhi = PLANES ? e.c_hi + (size_t)(grow0 + sub_r) * p.ldc + col : nullptr;
   uint16_t* d16 = BF16OUT ? reinterpret_cast<uint16_t*>(p.C16) + (size_t)(grow0 + sub_r) * p.ldc + col : nullptr;
-  const float cs = p.c_scale;
+  const float cs = e.c_scale;
   const bool m16 = MASK && p.mask16 != nullptr;       // uniform
   const float* mk = (MASK && !m16) ? p.mask + (size_t)(grow0 + sub_r) * p.ld_mask + col : nullptr;
   const uint16_t* mk16 = m16 ? p.mask16 + (size_t)(grow0 + sub_r) * p.ld_mask + col : nullptr;
   const size_t dstep = (size_t)RPI * p.ldc, mstep = MASK ? (size_t)RPI * p.ld_mask : 0;
-  // (every lane of a row's half-warp stores the same two words to the same address: one transaction, and no divergent
-  //  branch in the loop -- a lane-0-only store put a BSSY / BSYNC region into every iteration and serialised the loop)
-  uint32_t* dbits = BITS ? p.bits_out + (size_t)(grow0 + sub_r) * p.ld_bits + (col0 >> 5) : nullptr;
-  const size_t bstep = BITS ? (size_t)RPI * p.ld_bits : 0;
   const bool f32 = !p.no_f32;
   float vm = 0.f;
 #pragma unroll
@@ -349,11 +334,6 @@ __device__ __forceinline__ void store_staged_interior(const Params& p, float* __
       }
       if (f32) *reinterpret_cast<float4*>(dst) = o;
       dst += dstep;
-      if (BITS) {
-        const uint2 w = relu_bits_words((o.x > 0.f ? 1u : 0u) | (o.y > 0.f ? 2u : 0u) | (o.z > 0.f ? 4u : 0u) | (o.w > 0.f ? 8u : 0u), lane);
-        *reinterpret_cast<uint2*>(dbits) = w;
-        dbits += bstep;
-      }
       if (PLANES) {
         uint2 h, l;
         h3_split4(o, cs, h, l);
@@ -376,13 +356,12 @@ __device__ __forceinline__ void store_staged_interior(const Params& p, float* __
 // epilogue option decided at run time.  (The general walk above spends ~10k instructions per warp on such a sub-tile
 // whatever the number of valid rows; as the tail of a persistent kernel that was ~20 us per layer.)
 template <int CW>
-__device__ __forceinline__ void store_staged_rows(const Params& p, float* __restrict__ Cz, const float4* stg, int lane, int grow0,
+__device__ __forceinline__ void store_staged_rows(const Params& p, const EpiOv& e, float* __restrict__ Cz, const float4* stg, int lane, int grow0,
                                                   int col0, int nrows, float* vmax) {
   constexpr int S = CW / 4, RPI = 32 / S;
-  static_assert(S == 16, "two rows per store instruction (relu_bits_words)");
   const int sub_r = lane / S, sl = lane % S, col = col0 + 4 * sl;
   float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (p.bias) bb = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+  if (e.bias) bb = __ldg(reinterpret_cast<const float4*>(e.bias + col));
   float vm = 0.f;
 #pragma unroll 1
   for (int i = 0; i * RPI < nrows; ++i) {          // warp-uniform bound
@@ -391,38 +370,32 @@ __device__ __forceinline__ void store_staged_rows(const Params& p, float* __rest
     const size_t grow = (size_t)(grow0 + r);
     float4 o = stg[r * S + (sl ^ (r & 7))];
     o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
-    if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-    uint32_t nib = 0u;
+    if (e.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
     if (ok) {
       if (p.mask16 || p.mask) {
         const float4 m4 = p.mask16 ? mask4_from16(p.mask16 + grow * p.ld_mask + col)
                                    : __ldg(reinterpret_cast<const float4*>(p.mask + grow * p.ld_mask + col));
         o.x = m4.x > 0.f ? o.x : 0.f; o.y = m4.y > 0.f ? o.y : 0.f; o.z = m4.z > 0.f ? o.z : 0.f; o.w = m4.w > 0.f ? o.w : 0.f;
       }
-      nib = (o.x > 0.f ? 1u : 0u) | (o.y > 0.f ? 2u : 0u) | (o.z > 0.f ? 4u : 0u) | (o.w > 0.f ? 8u : 0u);
       const size_t off = grow * p.ldc + col;
       if (!p.no_f32) *reinterpret_cast<float4*>(Cz + off) = o;
-      if (p.c_hi) {
+      if (e.c_hi) {
         uint2 h, l;
-        h3_split4(o, p.c_scale, h, l);
-        *reinterpret_cast<uint2*>(p.c_hi + off) = h;
-        *reinterpret_cast<uint2*>(p.c_hi + p.c_plane + off) = l;
+        h3_split4(o, e.c_scale, h, l);
+        *reinterpret_cast<uint2*>(e.c_hi + off) = h;
+        *reinterpret_cast<uint2*>(e.c_hi + p.c_plane + off) = l;
       }
       if (p.C16 && p.c16_in_staged)
         *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(p.C16) + off) = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
       vm = fmaxf(fmaxf(vm, fmaxf(fabsf(o.x), fabsf(o.y))), fmaxf(fabsf(o.z), fabsf(o.w)));
-    }
-    if (p.bits_out) {                                // uniform: the ballots need every lane
-      const uint2 w = relu_bits_words(nib, lane);
-      if (ok) *reinterpret_cast<uint2*>(p.bits_out + grow * p.ld_bits + (col0 >> 5)) = w;
     }
   }
   if (vmax) *vmax = fmaxf(*vmax, vm);
 }
 
 // row-per-lane scalar fallback for outputs that are not 16-byte aligned (ldc % 4 != 0)
-__device__ __forceinline__ void store_row_scalar(const Params& p, float* Cz, int row, int cbase, const float* acc32,
-                                                 float* vmax = nullptr) {
+__device__ __forceinline__ void store_row_scalar(const Params& p, const EpiOv& e, float* Cz, int row, int cbase, const float* acc32,
+                                                 float* vmax) {
   float* dstp = Cz + (size_t)row * p.ldc + cbase;
   const float* mk = p.mask ? p.mask + (size_t)row * p.ld_mask + cbase : nullptr;
 #pragma unroll
@@ -430,17 +403,26 @@ __device__ __forceinline__ void store_row_scalar(const Params& p, float* Cz, int
     const int col = cbase + j;
     if (col < p.N) {
       float xv = acc32[j];
-      if (p.bias) xv += p.bias[col];
-      if (p.relu) xv = fmaxf(xv, 0.f);
+      if (e.bias) xv += e.bias[col];
+      if (e.relu) xv = fmaxf(xv, 0.f);
       if (p.mask16) xv = mask1_from16(p.mask16 + (size_t)row * p.ld_mask + col) ? xv : 0.f;
       else if (mk) xv = mk[j] > 0.f ? xv : 0.f;
       if (p.accumulate) xv += dstp[j];
       if (!p.no_f32) dstp[j] = xv;
       if (vmax) *vmax = fmaxf(*vmax, fabsf(xv));
-      if (p.c_hi) h3_emit1(p, (size_t)row * p.ldc + col, xv);
+      if (e.c_hi) h3_emit1(p, e, (size_t)row * p.ldc + col, xv);
       if (p.C16 && p.c16_in_staged) reinterpret_cast<uint16_t*>(p.C16)[(size_t)row * p.ldc + col] = (uint16_t)(pack_bf16x2(xv, 0.f) & 0xFFFFu);
     }
   }
+}
+// the kernels that take every epilogue field from Params
+template <int CW>
+__device__ __forceinline__ void store_staged(const Params& p, float* Cz, const float4* stg, int lane, int grow0, int col0,
+                                             float* vmax = nullptr) {
+  store_staged<CW>(p, EpiOv{p.c_hi, p.c_scale, p.bias, p.relu}, Cz, stg, lane, grow0, col0, vmax);
+}
+__device__ __forceinline__ void store_row_scalar(const Params& p, float* Cz, int row, int cbase, const float* acc32, float* vmax = nullptr) {
+  store_row_scalar(p, EpiOv{p.c_hi, p.c_scale, p.bias, p.relu}, Cz, row, cbase, acc32, vmax);
 }
 __device__ __forceinline__ bool epilogue_vec_ok(const Params& p, const float* Cz) {
   return ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(Cz) & 15) == 0) &&
@@ -1049,10 +1031,10 @@ struct ParamsP {
 // workers.  Registers are re-split after the set-up (setmaxnreg): an SM sub-partition holds 16K registers and, with ten
 // warps, three warps -- a cap of 168 per thread, under which the workers (128 accumulator registers + a 32-register TMEM
 // load + addressing) spilled 264 .. 424 bytes in the drain loop.  Twelve warps = three per sub-partition (one of
-// warpgroup 0, two workers): 56 + 2 x 224 = 504 <= 512.
+// warpgroup 0, two workers): 40 + 2 x 232 = 504 <= 512.
 constexpr int P_THREADS = 384;
 constexpr int P_WORKER0 = 4;          // first worker warp
-constexpr int P_REGS_LIGHT = 56, P_REGS_WORKER = 224;
+constexpr int P_REGS_LIGHT = 40, P_REGS_WORKER = 232;
 template <int BN, bool SINGLE, bool PAIR>
 __global__ void __launch_bounds__(P_THREADS, 1)
 gemm_tc_h3p_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
@@ -1238,13 +1220,17 @@ gemm_tc_h3p_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
     const float inv = SINGLE ? 1.0f : ia * ib;       // one-plane operands are not scaled
     float4* stg = reinterpret_cast<float4*>(base_ptr + C::STAGES * C::STAGE_BYTES + (32 * C::EPI_COLS * 4) * (warp - P_WORKER0));
     uint32_t g = 0;
-    Params p = pp.p;                             // worker-local copy: the scale of C's planes is read from C's slot
-    if (p.c_hi) {
+    // worker-decided epilogue fields: the scale of C's planes is read from C's slot; bits_out layers apply bias + ReLU
+    // before staging, not in the store loop
+    EpiOv ov{p.c_hi, 1.f, p.bias, p.relu};
+    const float* const bias_pre = p.bias;
+    if (!SINGLE && CPW == 128 && p.bits_out) { ov.bias = nullptr; ov.relu = 0; }
+    if (ov.c_hi) {
       const uint32_t W = p.c_amax[0];            // prepared by h3_prep_kernel before this launch; 0 = no history
       float is;
-      if (pp.repair) h3_scale(h3_eff_word(W, p.c_amax[1]), p.c_scale, is);     // the scale max|C| asks for (now known)
-      else if (W == 0u) p.c_hi = nullptr;        // the repair pass will write the planes once max|C| is known
-      else h3_scale(W, p.c_scale, is);
+      if (pp.repair) h3_scale(h3_eff_word(W, p.c_amax[1]), ov.c_scale, is);     // the scale max|C| asks for (now known)
+      else if (W == 0u) ov.c_hi = nullptr;       // the repair pass will write the planes once max|C| is known
+      else h3_scale(W, ov.c_scale, is);
     }
     float vmax = 0.f;
     float* const vm = (p.c_amax && !pp.repair) ? &vmax : nullptr;
@@ -1301,7 +1287,7 @@ gemm_tc_h3p_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
       const bool vec = epilogue_vec_ok(p, Cz);
       const int row = m0 + 32 * q + lane;
       const int cw0 = n0 + half * CPW;
-      uint4 mbits = make_uint4(0u, 0u, 0u, 0u);
+      uint4 mbits = make_uint4(0u, 0u, 0u, 0u), obits = make_uint4(0u, 0u, 0u, 0u);
       if (!SINGLE && CPW == 128 && p.bits_in && row < p.M && cw0 < p.N)
         mbits = __ldg(reinterpret_cast<const uint4*>(p.bits_in + (size_t)row * p.ld_bits + (cw0 >> 5)));
       if (pp.tma_store) {
@@ -1364,13 +1350,30 @@ gemm_tc_h3p_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
           if (vec) {
             if (!SINGLE && CPW == 128 && p.bits_in) {      // the ReLU mask, applied where a lane still owns its row
               static_assert(C::EPI_COLS == 64, "the bit-plane layout is defined per 64-column staging pass");
-              const uint32_t w0 = ps == 0 ? mbits.x : mbits.z, w1 = ps == 0 ? mbits.y : mbits.w;      // relu_bits_words
+              const uint32_t w0 = ps == 0 ? mbits.x : mbits.z, w1 = ps == 0 ? mbits.y : mbits.w;      // (layout: see "ReLU bit planes" above)
 #pragma unroll
               for (int sl = 0; sl < C::EPI_COLS / 4; ++sl) {
                 const int j = ps * C::EPI_COLS + 4 * sl;
                 stage_put<C::EPI_COLS>(stg, lane, sl, ((w0 >> sl) & 1u) ? acc[j] * inv : 0.f, ((w0 >> (16 + sl)) & 1u) ? acc[j + 1] * inv : 0.f,
                                        ((w1 >> sl) & 1u) ? acc[j + 2] * inv : 0.f, ((w1 >> (16 + sl)) & 1u) ? acc[j + 3] * inv : 0.f);
               }
+            } else if (!SINGLE && CPW == 128 && p.bits_out) {   // ReLU layer that leaves its mask behind: bias + clamp + bits here
+              uint32_t w0 = 0u, w1 = 0u;
+#pragma unroll
+              for (int sl = 0; sl < C::EPI_COLS / 4; ++sl) {
+                const int j = ps * C::EPI_COLS + 4 * sl;
+                float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (bias_pre) bb = __ldg(reinterpret_cast<const float4*>(bias_pre + c0 + 4 * sl));      // one address per warp
+                // (same operations, in the same order, as the store loop: acc * inv is exact -- inv is a power of two)
+                const float a0 = fmaxf(__fadd_rn(__fmul_rn(acc[j], inv), bb.x), 0.f), a1 = fmaxf(__fadd_rn(__fmul_rn(acc[j + 1], inv), bb.y), 0.f);
+                const float a2 = fmaxf(__fadd_rn(__fmul_rn(acc[j + 2], inv), bb.z), 0.f), a3 = fmaxf(__fadd_rn(__fmul_rn(acc[j + 3], inv), bb.w), 0.f);
+                if (a0 > 0.f) w0 |= 1u << sl;
+                if (a1 > 0.f) w0 |= 1u << (16 + sl);
+                if (a2 > 0.f) w1 |= 1u << sl;
+                if (a3 > 0.f) w1 |= 1u << (16 + sl);
+                stage_put<C::EPI_COLS>(stg, lane, sl, a0, a1, a2, a3);
+              }
+              if (ps == 0) { obits.x = w0; obits.y = w1; } else { obits.z = w0; obits.w = w1; }
             } else {
 #pragma unroll
             for (int sl = 0; sl < C::EPI_COLS / 4; ++sl) {
@@ -1381,24 +1384,21 @@ gemm_tc_h3p_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
             __syncwarp();
             if (m0 + 32 * q + 32 <= p.M && c0 + C::EPI_COLS <= p.N && !p.accumulate) {     // warp-uniform
               if (SINGLE && p.C16) {
-                if (p.mask || p.mask16) store_staged_interior<C::EPI_COLS, true, false, true>(p, Cz, stg, lane, m0 + 32 * q, c0, vm);
-                else store_staged_interior<C::EPI_COLS, false, false, true>(p, Cz, stg, lane, m0 + 32 * q, c0, vm);
+                if (p.mask || p.mask16) store_staged_interior<C::EPI_COLS, true, false, true>(p, ov, Cz, stg, lane, m0 + 32 * q, c0, vm);
+                else store_staged_interior<C::EPI_COLS, false, false, true>(p, ov, Cz, stg, lane, m0 + 32 * q, c0, vm);
               // (a variant with eight columns per lane -- 16-byte plane stores, 16-byte mask loads -- measured slower in the
               //  whole update: 90.8 against 88.4 ms per iteration on one box)
-              } else if (!SINGLE && p.bits_out) {          // a ReLU layer that leaves its mask behind as bits (never masked itself)
-                if (p.c_hi) store_staged_interior<C::EPI_COLS, false, true, false, true>(p, Cz, stg, lane, m0 + 32 * q, c0, vm);
-                else store_staged_interior<C::EPI_COLS, false, false, false, true>(p, Cz, stg, lane, m0 + 32 * q, c0, vm);
-              } else if (!SINGLE && p.c_hi) {
-                if (p.mask || p.mask16) store_staged_interior<C::EPI_COLS, true, true>(p, Cz, stg, lane, m0 + 32 * q, c0, vm);
-                else store_staged_interior<C::EPI_COLS, false, true>(p, Cz, stg, lane, m0 + 32 * q, c0, vm);
+              } else if (!SINGLE && ov.c_hi) {
+                if (p.mask || p.mask16) store_staged_interior<C::EPI_COLS, true, true>(p, ov, Cz, stg, lane, m0 + 32 * q, c0, vm);
+                else store_staged_interior<C::EPI_COLS, false, true>(p, ov, Cz, stg, lane, m0 + 32 * q, c0, vm);
               } else {
-                if (p.mask || p.mask16) store_staged_interior<C::EPI_COLS, true, false>(p, Cz, stg, lane, m0 + 32 * q, c0, vm);
-                else store_staged_interior<C::EPI_COLS, false, false>(p, Cz, stg, lane, m0 + 32 * q, c0, vm);
+                if (p.mask || p.mask16) store_staged_interior<C::EPI_COLS, true, false>(p, ov, Cz, stg, lane, m0 + 32 * q, c0, vm);
+                else store_staged_interior<C::EPI_COLS, false, false>(p, ov, Cz, stg, lane, m0 + 32 * q, c0, vm);
               }
             } else if (c0 + C::EPI_COLS <= p.N && !p.accumulate) {      // ragged rows only
-              store_staged_rows<C::EPI_COLS>(p, Cz, stg, lane, m0 + 32 * q, c0, p.M - (m0 + 32 * q), vm);
+              store_staged_rows<C::EPI_COLS>(p, ov, Cz, stg, lane, m0 + 32 * q, c0, p.M - (m0 + 32 * q), vm);
             } else {
-              store_staged<C::EPI_COLS>(p, Cz, stg, lane, m0 + 32 * q, c0, vm);
+              store_staged<C::EPI_COLS>(p, ov, Cz, stg, lane, m0 + 32 * q, c0, vm);
             }
             __syncwarp();
           } else if (row < p.M) {
@@ -1407,12 +1407,14 @@ gemm_tc_h3p_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
             for (int cc = 0; cc < C::EPI_COLS / 32; ++cc) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) f[j] = acc[ps * C::EPI_COLS + cc * 32 + j] * inv;
-              store_row_scalar(p, Cz, row, c0 + cc * 32, f, vm);
+              store_row_scalar(p, ov, Cz, row, c0 + cc * 32, f, vm);
             }
           }
         }
       }
       }
+      if (!SINGLE && CPW == 128 && p.bits_out && row < p.M && cw0 < p.N && !(p.pair_flags & 1))
+        *reinterpret_cast<uint4*>(p.bits_out + (size_t)row * p.ld_bits + (cw0 >> 5)) = obits;
       if (dbg) t_epi += clock64() - c2;
     }
     if (dbg && lane == 0) { dbg[3] = clock64() - t_begin; dbg[4] = w_accfull; dbg[5] = t_drain; dbg[6] = t_epi; dbg[8] = clock64() - t_entry; }
@@ -1848,6 +1850,7 @@ static int gemm_h3(cudaStream_t st, const addk_gemm_args& a) {
     if (a.relu_bits_out || a.relu_bits_in) {      // ReLU masks as bit planes
       const uintptr_t bo = reinterpret_cast<uintptr_t>(a.relu_bits_out), bi = reinterpret_cast<uintptr_t>(a.relu_bits_in);
       if ((a.N & 127) || (a.ld_bits & 3) || a.ld_bits * 32 < a.N || ((bo | bi) & 15) || (a.ldc & 3) || split != 1 || a.accumulate ||
+          (reinterpret_cast<uintptr_t>(a.C) & 15) || (reinterpret_cast<uintptr_t>(a.bias) & 15) ||
           (a.relu_bits_out && (!a.relu || a.relu_bits_in || a.relu_mask_src || a.relu_mask_src16))) {
         addk_set_error("gemm f16x3: relu_bits_* need N % 128 == 0, ld_bits % 4 == 0 (>= N / 32), 16-byte aligned bit planes, one slab; "
                        "relu_bits_out a ReLU layer without a mask of its own");
@@ -1864,8 +1867,10 @@ static int gemm_h3(cudaStream_t st, const addk_gemm_args& a) {
     }
     return launch_h3p<256>(st, tah, tal, tbh, tbl, pp, a.M, a.N, split);
   }
-  g_addk_last_gemm_kernel = ADDK_K_H3_TILE;
   if (a.no_f32 || a.relu_mask_src16 || a.relu_bits_in || a.relu_bits_out) { addk_set_error("gemm f16x3: no_f32 / relu_mask_src16 / relu_bits_* need the persistent kernel"); return ADDK_ERR_ARG; }
+  // (a 256 x 128 instance of the CTA-pair kernel for the 65 .. 128-column layers -- gx = u1.W0, the 1024 x 114 weight
+  //  gradients -- measured 27 vs 31 and 43 vs 53 us in isolation and nothing in the whole optimizer step: not kept)
+  g_addk_last_gemm_kernel = ADDK_K_H3_TILE;
   if (BN == 256) return launch_h3<256>(st, tah, tal, tbh, tbl, ph, grid);
   if (BN == 128) return launch_h3<128>(st, tah, tal, tbh, tbl, ph, grid);
   return launch_h3<64>(st, tah, tal, tbh, tbl, ph, grid);
