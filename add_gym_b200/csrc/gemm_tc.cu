@@ -310,20 +310,23 @@ __device__ __forceinline__ void store_staged_interior(const Params& p, const Epi
   const size_t dstep = (size_t)RPI * p.ldc, mstep = MASK ? (size_t)RPI * p.ld_mask : 0;
   const bool f32 = !p.no_f32;
   float vm = 0.f;
-#pragma unroll
-  for (int i0 = 0; i0 < 32 / RPI; i0 += 8) {
-    float4 m4[8];
+  constexpr int EB = MASK ? 8 : 4;       // store instructions per loop iteration (masked: eight mask loads in flight)
+  // (a real loop: fully unrolled, the store walk of one pass was 13 KB of straight-line code that every warp streamed
+  //  through the instruction caches once per tile -- ncu: "no instruction" was the top stall reason of the epilogue)
+#pragma unroll 1
+  for (int i0 = 0; i0 < 32 / RPI; i0 += EB) {
+    float4 m4[EB];
     if (MASK) {
       if (m16) {
 #pragma unroll
-        for (int u = 0; u < 8; ++u) m4[u] = mask4_from16(mk16 + (size_t)(i0 + u) * mstep);
+        for (int u = 0; u < EB; ++u) m4[u] = mask4_from16(mk16 + (size_t)(i0 + u) * mstep);
       } else {
 #pragma unroll
-        for (int u = 0; u < 8; ++u) m4[u] = __ldg(reinterpret_cast<const float4*>(mk + (size_t)(i0 + u) * mstep));
+        for (int u = 0; u < EB; ++u) m4[u] = __ldg(reinterpret_cast<const float4*>(mk + (size_t)(i0 + u) * mstep));
       }
     }
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
+    for (int u = 0; u < EB; ++u) {
       const int r = (i0 + u) * RPI + sub_r;
       float4 o = stg[r * S + (sl ^ (r & 7))];
       o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
