@@ -292,7 +292,7 @@ class ADDAgent(torch.nn.Module):
         self._params16 = torch.zeros(2 * m.num_params if h3 else (m.num_params if bf16 else 8), device=dev, dtype=torch.bfloat16)
         self._amax_slots = torch.zeros(2 * (1 + 4 * 128), device=dev, dtype=torch.int32) if h3 else None
         # ReLU masks as bit planes (one bit per arena element; written by the forward layers of an optimizer step)
-        self._arena_bits = torch.zeros(total // 32 + 4, device=dev, dtype=torch.int32) if h3 else None
+        self._arena_bits = torch.zeros(total // 32 + 4, device=dev, dtype=torch.int32) if (h3 or bf16) else None
         carve = {k: self._arena[offs[k]:offs[k] + int(np.prod(shp))].view(shp) for k, shp in shapes.items()}
         self._ws = dict(
             carve, old_logp=z(R), adv=z(R), tar=z(R), mask=z(R), pred=z(R), dpred=z(R), ones=torch.ones(R, device=dev),

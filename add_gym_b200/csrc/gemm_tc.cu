@@ -1227,7 +1227,7 @@ gemm_tc_h3p_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
     // before staging, not in the store loop
     EpiOv ov{p.c_hi, 1.f, p.bias, p.relu};
     const float* const bias_pre = p.bias;
-    if (!SINGLE && CPW == 128 && p.bits_out) { ov.bias = nullptr; ov.relu = 0; }
+    if (CPW == 128 && p.bits_out) { ov.bias = nullptr; ov.relu = 0; }
     if (ov.c_hi) {
       const uint32_t W = p.c_amax[0];            // prepared by h3_prep_kernel before this launch; 0 = no history
       float is;
@@ -1254,7 +1254,7 @@ gemm_tc_h3p_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
       // 16-byte load at the start of the epilogue (host: CPW == 128, ld_bits % 4 == 0, N % 128 == 0).  Only a prefetch
       // here: holding the four words across the chunk drains cost more (register cap 168: 29k -> 47k cycles of drains
       // per four tiles) than the L2 round trip they would hide.
-      if (!SINGLE && CPW == 128 && p.bits_in) {
+      if (CPW == 128 && p.bits_in) {
         const int brow = m0 + 32 * q + lane, bc0 = n0 + half * CPW;
         if (brow < p.M && bc0 < p.N)
           asm volatile("prefetch.global.L2 [%0];" ::"l"(p.bits_in + (size_t)brow * p.ld_bits + (bc0 >> 5)));
@@ -1291,7 +1291,7 @@ gemm_tc_h3p_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
       const int row = m0 + 32 * q + lane;
       const int cw0 = n0 + half * CPW;
       uint4 mbits = make_uint4(0u, 0u, 0u, 0u), obits = make_uint4(0u, 0u, 0u, 0u);
-      if (!SINGLE && CPW == 128 && p.bits_in && row < p.M && cw0 < p.N)
+      if (CPW == 128 && p.bits_in && row < p.M && cw0 < p.N)
         mbits = __ldg(reinterpret_cast<const uint4*>(p.bits_in + (size_t)row * p.ld_bits + (cw0 >> 5)));
       if (pp.tma_store) {
         // 32 columns at a time, in the accumulator's own layout (lane = row): scale, bias / ReLU / ReLU-mask in registers,
@@ -1351,7 +1351,7 @@ gemm_tc_h3p_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
         // and made every such layer ~20 us longer than its 16384-row twin.
         if (c0 < p.N && m0 + 32 * q < p.M && !(p.pair_flags & 1)) {
           if (vec) {
-            if (!SINGLE && CPW == 128 && p.bits_in) {      // the ReLU mask, applied where a lane still owns its row
+            if (CPW == 128 && p.bits_in) {      // the ReLU mask, applied where a lane still owns its row
               static_assert(C::EPI_COLS == 64, "the bit-plane layout is defined per 64-column staging pass");
               const uint32_t w0 = ps == 0 ? mbits.x : mbits.z, w1 = ps == 0 ? mbits.y : mbits.w;      // (layout: see "ReLU bit planes" above)
 #pragma unroll
@@ -1360,7 +1360,7 @@ gemm_tc_h3p_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
                 stage_put<C::EPI_COLS>(stg, lane, sl, ((w0 >> sl) & 1u) ? acc[j] * inv : 0.f, ((w0 >> (16 + sl)) & 1u) ? acc[j + 1] * inv : 0.f,
                                        ((w1 >> sl) & 1u) ? acc[j + 2] * inv : 0.f, ((w1 >> (16 + sl)) & 1u) ? acc[j + 3] * inv : 0.f);
               }
-            } else if (!SINGLE && CPW == 128 && p.bits_out) {   // ReLU layer that leaves its mask behind: bias + clamp + bits here
+            } else if (CPW == 128 && p.bits_out) {   // ReLU layer that leaves its mask behind: bias + clamp + bits here
               uint32_t w0 = 0u, w1 = 0u;
 #pragma unroll
               for (int sl = 0; sl < C::EPI_COLS / 4; ++sl) {
@@ -1416,7 +1416,7 @@ gemm_tc_h3p_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
         }
       }
       }
-      if (!SINGLE && CPW == 128 && p.bits_out && row < p.M && cw0 < p.N && !(p.pair_flags & 1))
+      if (CPW == 128 && p.bits_out && row < p.M && cw0 < p.N && !(p.pair_flags & 1))
         *reinterpret_cast<uint4*>(p.bits_out + (size_t)row * p.ld_bits + (cw0 >> 5)) = obits;
       if (dbg) t_epi += clock64() - c2;
     }
@@ -1699,6 +1699,22 @@ __global__ void f32_to_bf16_rows_kernel(const float* __restrict__ src, uint16_t*
   dst[(size_t)r * ld + c] = (uint16_t)(addk_tc::pack_bf16x2(src[(size_t)r * ld + c], 0.f) & 0xFFFFu);
 }
 
+// ReLU masks as bit planes (persistent kernels, f16x3 and bf16): validate and hand them to the kernel parameters
+static int apply_relu_bits(const addk_gemm_args& a, addk_tc::Params& p, int split) {
+  if (!a.relu_bits_out && !a.relu_bits_in) return ADDK_OK;
+  const uintptr_t bo = reinterpret_cast<uintptr_t>(a.relu_bits_out), bi = reinterpret_cast<uintptr_t>(a.relu_bits_in);
+  if ((a.N & 127) || (a.ld_bits & 3) || a.ld_bits * 32 < a.N || ((bo | bi) & 15) || (a.ldc & 3) || split != 1 || a.accumulate ||
+      (reinterpret_cast<uintptr_t>(a.C) & 15) || (reinterpret_cast<uintptr_t>(a.bias) & 15) ||
+      (a.relu_bits_out && (!a.relu || a.relu_bits_in || a.relu_mask_src || a.relu_mask_src16))) {
+    addk_set_error("gemm: relu_bits_* need N % 128 == 0, ld_bits % 4 == 0 (>= N / 32), 16-byte aligned bit planes, one slab; "
+                   "relu_bits_out a ReLU layer without a mask of its own");
+    return ADDK_ERR_ARG;
+  }
+  p.bits_out = a.relu_bits_out; p.ld_bits = a.ld_bits;
+  if (a.relu_bits_in) { p.bits_in = a.relu_bits_in; p.mask = nullptr; p.mask16 = nullptr; }
+  return ADDK_OK;
+}
+
 static int gemm_bf16(cudaStream_t st, const addk_gemm_args& a) {
   using namespace addk_tc;
   const int BKh = 64;
@@ -1730,6 +1746,7 @@ static int gemm_bf16(cudaStream_t st, const addk_gemm_args& a) {
       pp.p = p; pp.p.kb_per_split = kbp; pp.p.c16_in_staged = 1;
       pp.p.no_f32 = a.no_f32 ? 1 : 0;
       if (a.relu_mask_src16) { pp.p.mask16 = reinterpret_cast<const uint16_t*>(a.relu_mask_src16); pp.p.mask = nullptr; }
+      { const int rcb = apply_relu_bits(a, pp.p, split); if (rcb != ADDK_OK) return rcb; }
       pp.a_amax = nullptr; pp.b_amax = nullptr; pp.comp_per_mma = 0.f; pp.chunk_kb = kbp; pp.bf16 = 1;
       CUtensorMap tah, tbh;
       bool okp = p.a_mn ? make_map_f16(&tah, a.A16, a.M, a.K, a.lda, 64, 64, true) : make_map_f16(&tah, a.A16, a.K, a.M, a.lda, 64, BM, true);
@@ -1742,6 +1759,7 @@ static int gemm_bf16(cudaStream_t st, const addk_gemm_args& a) {
       if (okp) { g_addk_last_gemm_kernel = ADDK_K_BF16_PERSISTENT; return launch_h3p<256, true>(st, tah, tah, tbh, tbh, pp, a.M, a.N, split); }
     }
   }
+  if (a.relu_bits_in || a.relu_bits_out) { addk_set_error("gemm bf16: relu_bits_* need the persistent kernel"); return ADDK_ERR_ARG; }
   CUtensorMap ta, tb;
   bool ok = p.a_mn ? make_map_bf16(&ta, a.A16, a.M, a.K, a.lda, 64) : make_map_bf16(&ta, a.A16, a.K, a.M, a.lda, BM);
   ok = ok && (p.b_mn ? make_map_bf16(&tb, a.B16, a.N, a.K, a.ldb, 64) : make_map_bf16(&tb, a.B16, a.K, a.N, a.ldb, BN));
@@ -1850,18 +1868,7 @@ static int gemm_h3(cudaStream_t st, const addk_gemm_args& a) {
       pp.p.no_f32 = 1;
     }
     if (a.relu_mask_src16) { pp.p.mask16 = reinterpret_cast<const uint16_t*>(a.relu_mask_src16); pp.p.mask = nullptr; }
-    if (a.relu_bits_out || a.relu_bits_in) {      // ReLU masks as bit planes
-      const uintptr_t bo = reinterpret_cast<uintptr_t>(a.relu_bits_out), bi = reinterpret_cast<uintptr_t>(a.relu_bits_in);
-      if ((a.N & 127) || (a.ld_bits & 3) || a.ld_bits * 32 < a.N || ((bo | bi) & 15) || (a.ldc & 3) || split != 1 || a.accumulate ||
-          (reinterpret_cast<uintptr_t>(a.C) & 15) || (reinterpret_cast<uintptr_t>(a.bias) & 15) ||
-          (a.relu_bits_out && (!a.relu || a.relu_bits_in || a.relu_mask_src || a.relu_mask_src16))) {
-        addk_set_error("gemm f16x3: relu_bits_* need N % 128 == 0, ld_bits % 4 == 0 (>= N / 32), 16-byte aligned bit planes, one slab; "
-                       "relu_bits_out a ReLU layer without a mask of its own");
-        return ADDK_ERR_ARG;
-      }
-      pp.p.bits_out = a.relu_bits_out; pp.p.ld_bits = a.ld_bits;
-      if (a.relu_bits_in) { pp.p.bits_in = a.relu_bits_in; pp.p.mask = nullptr; pp.p.mask16 = nullptr; }
-    }
+    { const int rcb = apply_relu_bits(a, pp.p, split); if (rcb != ADDK_OK) return rcb; }
     pp.chunk_kb = addk_switches().h3_chunk_kb;
     g_addk_last_gemm_kernel = ADDK_K_H3_PERSISTENT;
     if (addk_switches().h3_pair && a.M > BM) {      // CTA pairs (cta_group::2): each CTA stages a 128-row half of B
@@ -1895,8 +1902,8 @@ extern "C" int addk_gemm_is_persistent(const addk_gemm_args* a, int precision) {
 static int gemm_fallback(cudaStream_t st, const addk_gemm_args& a);
 
 int addk_gemm_tc(cudaStream_t st, const addk_gemm_args& a, int precision) {
-  if ((a.relu_bits_in || a.relu_bits_out) && !(precision == 4 && addk_gemm_is_persistent(&a, 4))) {
-    addk_set_error("gemm: relu_bits_in / relu_bits_out are honoured by the persistent f16x3 kernel only (addk_gemm_is_persistent)");
+  if ((a.relu_bits_in || a.relu_bits_out) && !((precision == 4 || precision == 3) && addk_gemm_is_persistent(&a, precision))) {
+    addk_set_error("gemm: relu_bits_in / relu_bits_out are honoured by the persistent f16x3 / bf16 kernels only (addk_gemm_is_persistent)");
     return ADDK_ERR_ARG;
   }
   if (precision == 4) {

@@ -1001,7 +1001,8 @@ static int gemm(cudaStream_t st, int prec, const float* A, int lda, int ta, cons
   }
   a.relu_bits_out = nullptr; a.relu_bits_in = nullptr; a.ld_bits = 0;
   int bits_ent = -1;
-  if (prec == 4 && g_twin_ctx && g_want_bits && a.A16 && a.B16 && split == 1 && (N & 127) == 0 && addk_gemm_is_persistent(&a, 4)) {
+  if ((prec == 4 || prec == 3) && g_twin_ctx && g_want_bits && a.A16 && a.B16 && split == 1 && (N & 127) == 0 && addk_gemm_is_persistent(&a, prec) &&
+      (prec == 4 || (a.C16 && M > 128))) {      // (bf16: the calls gemm_bf16() routes to the persistent kernel)
     const addk_update_ctx& c = *g_twin_ctx;
     if (mask) {                  // the mask source's ReLU bits, if the layer that produced it left them behind (same stream)
       for (int i = 0; i < g_nbits; ++i) {
@@ -1227,7 +1228,8 @@ extern "C" int addk_update_minibatch(void* stream, void* ctx_host, const long lo
     ADDK_CHECK_LAUNCH();
   }
   TRY(h3_params(c, st, 0));
-  g_want_bits = c.precision == 4 && c.arena_bits != nullptr && addk_switches().h3_relu_bits != 0;
+  g_nbits = 0;      // (bf16 mode does not go through twin_reset)
+  g_want_bits = (c.precision == 4 || c.precision == 3) && c.arena_bits != nullptr && addk_switches().h3_relu_bits != 0;
 
   uint16_t* const xn16 = twin16(c.xn);
   uint16_t* const dn16 = twin16(c.dn);
