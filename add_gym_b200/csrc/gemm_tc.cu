@@ -1844,7 +1844,9 @@ static int gemm_h3(cudaStream_t st, const addk_gemm_args& a) {
   // few, long tiles (the weight gradient of a head: 29 x 512 outputs, K = 16384 / 9): narrower tiles put 4x the SMs to work
   const bool want_planes = a.C16 && a.c16_plane > 0;       // only the persistent 256-wide kernel writes C's planes
   if (want_planes && (BN != 256 || split != 1 || !a.c_amax)) { addk_set_error("gemm f16x3: c16_plane needs N > 128, one slab and c_amax"); return ADDK_ERR_ARG; }
-  if (!want_planes && BN > 64 && (long long)((a.M + BM - 1) / BM) * ((a.N + BN - 1) / BN) * split <= 37) BN = 64;
+  // (128-wide layers with at most half an SM-round of tiles -- the 1024 x 114 first-layer weight gradient of the
+  //  discriminator: 72 CTAs, load-latency bound -- also take 64-wide tiles: twice the CTAs)
+  if (!want_planes && BN > 64 && (long long)((a.M + BM - 1) / BM) * ((a.N + BN - 1) / BN) * split <= (BN == 128 ? 74 : 37)) BN = 64;
   // (128-wide tiles for a layer with half an SM-round of 256-wide ones -- rollout inference, 4096 x 512 = 64 tiles -- were
   // slower: 42.6 vs 35.3 us)
   const uint16_t* Ah = reinterpret_cast<const uint16_t*>(a.A16); const uint16_t* Al = Ah + a.a16_plane;

@@ -8,7 +8,7 @@ from add_gym_b200 import _lib, config as b200_config
 from add_gym_b200.add_agent import ADDAgent
 envs = int(sys.argv[1]) if len(sys.argv) > 1 else 32768
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 10
-cfg = b200_config.default_config(num_envs=envs, mlp_precision="tf32x3")
+cfg = b200_config.default_config(num_envs=envs, mlp_precision="f16x3")
 cfg["engine"].update(seed=1234, noise_device="device", fall_prob=0.002)
 torch.manual_seed(0)
 a = ADDAgent(cfg, device="cuda:0")
