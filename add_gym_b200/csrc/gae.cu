@@ -201,6 +201,26 @@ extern "C" int addk_td_lambda(void* stream, const float* reward, const float* ne
   return ADDK_OK;
 }
 
+// ExperienceBuffer._sample_rand_idx (experience_buffer.py:90-113): window of the permutation, modulo the sample count
+__global__ void perm_window_kernel(const long long* __restrict__ perm, long long len, long long head, int n, long long count,
+                                   long long* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  long long j = head + i;
+  if (j >= len) j -= len;                     // (n <= len: one wrap at most)
+  long long v = perm[j] % count;              // torch.remainder: the sign of the divisor (count > 0, perm >= 0)
+  out[i] = v < 0 ? v + count : v;
+}
+
+extern "C" int addk_perm_window(void* stream, const long long* perm, long long perm_len, long long head, int n,
+                                long long sample_count, long long* out_idx) {
+  if (!perm || !out_idx || n <= 0 || perm_len <= 0 || n > perm_len || head < 0 || head > perm_len || sample_count <= 0)
+    return ADDK_ERR_ARG;
+  perm_window_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(perm, perm_len, head, n, sample_count, out_idx);
+  ADDK_CHECK_LAUNCH();
+  return ADDK_OK;
+}
+
 extern "C" int addk_adv_normalize(void* stream, float* adv, const float* rand_action_mask, int n, float clip,
                                   double* work3, float* stats_out) {
   if (!adv || !work3 || n <= 0) return ADDK_ERR_ARG;

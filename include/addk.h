@@ -208,6 +208,13 @@ int addk_pd_control(void* stream, const float* qpos, int ld_qpos, const float* q
 int addk_td_lambda(void* stream, const float* reward, const float* next_vals, const float* vals,
                    const int32_t* done, int T, int N, float discount, float td_lambda, float succ_val,
                    float fail_val, float* tar_val, float* adv);
+/* The minibatch index window of ExperienceBuffer._sample_rand_idx (experience_buffer.py:90-113) in one launch:
+ *   out[i] = perm[(head + i) mod perm_len] mod sample_count,  i < n.
+ * The reference slices its device permutation, concatenates the tail with the head of the re-drawn permutation on
+ * wrap-around (the tail is a VIEW, so it also shows the re-drawn values) and applies torch.remainder: three or four
+ * library launches per optimizer step.  The caller re-draws `perm` in place BEFORE the call when head + n > perm_len. */
+int addk_perm_window(void* stream, const long long* perm, long long perm_len, long long head, int n,
+                     long long sample_count, long long* out_idx);
 /* std_mean over rand_action_mask == 1 (unbiased) then clamp((adv-mean)/max(std,1e-5), +-clip)
  * (ppo_agent.py:147-153).  stats_out: [mean, std]. */
 int addk_adv_normalize(void* stream, float* adv, const float* rand_action_mask, int n, float clip,
