@@ -297,12 +297,12 @@ class ADDAgent(torch.nn.Module):
         self._ws = dict(
             carve, old_logp=z(R), adv=z(R), tar=z(R), mask=z(R), pred=z(R), dpred=z(R), ones=torch.ones(R, device=dev),
             stats=z(32, dt=torch.float64), info=z(self._max_steps, 16), cnt=z(1, dt=torch.int32),
-            slabs=z(2 * S, m.num_params), colsum_work=z(64 * 1024 + 64), arena=self._arena, arena16=self._arena16,
+            slabs=z(2 * S, m.num_params), colsum_work=z(128 * 1024 + 64), arena=self._arena, arena16=self._arena16,
             params16=self._params16, amax_slots=self._amax_slots, arena_bits=self._arena_bits)
         for k in ("colpart_a", "colpart_c", "colpart_d"):
             self._ws[k] = z(148 * 8, 1024) if h3 else None
         if n_streams == 3:
-            self._ws.update(d_pred=z(R), d_dpred=z(R), colsum_work_c=z(64 * 1024 + 64), colsum_work_d=z(64 * 1024 + 64))
+            self._ws.update(d_pred=z(R), d_dpred=z(R), colsum_work_c=z(128 * 1024 + 64), colsum_work_d=z(128 * 1024 + 64))
         else:
             for k in ("c_h1", "c_h2", "c_h3", "c_g1", "c_g2", "c_g3", "d_e1", "d_e2", "d_dh2", "d_dv1", "d_du2", "d_pred",
                       "d_dpred", "colsum_work_c", "colsum_work_d"):

@@ -62,7 +62,7 @@ ADDK_PTR(ones)          // [R] all 1.0f
 ADDK_PTR(stats)         // [32] double accumulators of the current minibatch
 ADDK_PTR(info)          // [max_steps, 16] float diagnostics, one row per optimizer step
 ADDK_PTR(cnt)           // [1] int: rows of the minibatch with rand_action_mask == 1
-ADDK_PTR(colsum_work)   // [64*1024 + 64] floats: column-sum partials + ticket counters (zero-initialised)
+ADDK_PTR(colsum_work)   // [128*1024 + 64] floats: column-sum partials + ticket counters (zero-initialised)
 ADDK_PTR(wd0_pad)       // [hid_d1, disc_ld] discriminator first-layer weight with rows padded to 16 bytes
 ADDK_PTR(wa0_pad)       // [hid_a1, obs_ld] actor / critic first-layer weights with rows padded to obs_ld (tensor-core modes)
 ADDK_PTR(wc0_pad)

@@ -364,7 +364,7 @@ __global__ void sumsq_kernel(const float* __restrict__ x, long long n, double* _
 // grid = (ceil(n/128), COLSUM_CHUNKS): every block reduces a 128-column x rows/64 patch into `work`; the last block of
 // a column group to finish (ticket counter, self-resetting) adds the 64 partials in a fixed order, writes the total
 // to slab 0 and zeroes slabs 1..nsplit-1 so the common slab reduction stays valid.  Deterministic, no float atomics.
-constexpr int COLSUM_CHUNKS = 64;
+constexpr int COLSUM_CHUNKS = 128;      // rows of the work buffer = the largest gridDim.y (the launch picks ~1000 blocks)
 constexpr int COLSUM_MAX_N = 1024;
 // IN16: dY is read from its bf16 copy (a tensor that has no fp32 copy, precision "bf16")
 __device__ __forceinline__ float4 ld_row4(const float* p) { return ldg4(p); }
@@ -406,13 +406,25 @@ __global__ void __launch_bounds__(256) colsum_slabs_kernel(const TIN* __restrict
   }
   const int cq = threadIdx.x & 31, rl = threadIdx.x >> 5;
   const int col = (blockIdx.x * 32 + cq) * 4;
-  const int per = (rows + COLSUM_CHUNKS - 1) / COLSUM_CHUNKS;
+  const int chunks = (int)gridDim.y;
+  const int per = (rows + chunks - 1) / chunks;
   const int r0 = blockIdx.y * per, r1 = min(rows, r0 + per);
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   if (col < n) {
     if (col + 3 < n && (ld & 3) == 0) {
       int r = r0 + rl;
-      for (; r + 24 < r1; r += 32) {          // 4 independent 128-bit loads in flight per thread
+      // eight, then four independent 128-bit loads in flight per thread (64 chunks x 4 loads: 2.5 TB/s on a 64 MB tensor)
+      for (; r + 56 < r1; r += 64) {
+        float4 v[8];
+        float w[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { v[u] = ld_row4(dY + (size_t)(r + 8 * u) * ld + col); w[u] = rw ? rw[r + 8 * u] : 1.f; }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          acc.x = fmaf(w[u], v[u].x, acc.x); acc.y = fmaf(w[u], v[u].y, acc.y); acc.z = fmaf(w[u], v[u].z, acc.z); acc.w = fmaf(w[u], v[u].w, acc.w);
+        }
+      }
+      for (; r + 24 < r1; r += 32) {
         const float4 v0 = ld_row4(dY + (size_t)r * ld + col), v1 = ld_row4(dY + (size_t)(r + 8) * ld + col);
         const float4 v2 = ld_row4(dY + (size_t)(r + 16) * ld + col), v3 = ld_row4(dY + (size_t)(r + 24) * ld + col);
         const float w0 = rw ? rw[r] : 1.f, w1 = rw ? rw[r + 8] : 1.f, w2 = rw ? rw[r + 16] : 1.f, w3 = rw ? rw[r + 24] : 1.f;
@@ -447,12 +459,12 @@ __global__ void __launch_bounds__(256) colsum_slabs_kernel(const TIN* __restrict
   }
   __threadfence();
   __syncthreads();
-  if (threadIdx.x == 0) s_last = (atomicAdd(tickets + blockIdx.x, 1u) == COLSUM_CHUNKS - 1) ? 1u : 0u;
+  if (threadIdx.x == 0) s_last = (atomicAdd(tickets + blockIdx.x, 1u) == (unsigned)chunks - 1u) ? 1u : 0u;
   __syncthreads();
   if (!s_last) return;
   __threadfence();
   float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int ch = rl; ch < COLSUM_CHUNKS; ch += 8) {
+  for (int ch = rl; ch < chunks; ch += 8) {
     const float4 v = __ldcg(reinterpret_cast<const float4*>(work + ((size_t)ch * COLSUM_MAX_N + blockIdx.x * 128 + cq * 4)));
     t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
   }
@@ -738,15 +750,19 @@ static int colsum(cudaStream_t st, const addk_update_ctx& c, const ChainWs& ws, 
   float* work = ws.colsum_work;
   unsigned int* tickets = (unsigned int*)(work + (size_t)COLSUM_CHUNKS * COLSUM_MAX_N);
   const addk::PlanesArg none{nullptr, 0, nullptr};
+  const int groups = (n + 127) / 128;
+  int chunks = (148 * 8) / groups;                 // ~8 blocks per SM in total
+  chunks = chunks > COLSUM_CHUNKS ? COLSUM_CHUNKS : (chunks < 8 ? 8 : chunks);
+  if (chunks > rows) chunks = rows > 0 ? rows : 1;
   if (dY16 && planes_slot && (ld & 3) == 0)      // no fp32 copy (precision "f16x3"): read the fp16 planes
-    addk::colsum_slabs_kernel<addk::PlanesPtr><<<dim3((n + 127) / 128, COLSUM_CHUNKS), 256, 0, st>>>(
+    addk::colsum_slabs_kernel<addk::PlanesPtr><<<dim3(groups, chunks), 256, 0, st>>>(
         nullptr, addk::PlanesArg{reinterpret_cast<const __half*>(dY16), c.arena_elems, planes_slot}, ld, rows, n, out, c.num_params,
         (int)c.split_k, rw, work, tickets);
   else if (dY16 && (ld & 3) == 0)      // the tensor has no fp32 copy (precision "bf16"): read its bf16 copy
-    addk::colsum_slabs_kernel<uint16_t><<<dim3((n + 127) / 128, COLSUM_CHUNKS), 256, 0, st>>>(dY16, none, ld, rows, n, out, c.num_params,
+    addk::colsum_slabs_kernel<uint16_t><<<dim3(groups, chunks), 256, 0, st>>>(dY16, none, ld, rows, n, out, c.num_params,
                                                                                      (int)c.split_k, rw, work, tickets);
   else
-    addk::colsum_slabs_kernel<float><<<dim3((n + 127) / 128, COLSUM_CHUNKS), 256, 0, st>>>(dY, none, ld, rows, n, out, c.num_params,
+    addk::colsum_slabs_kernel<float><<<dim3(groups, chunks), 256, 0, st>>>(dY, none, ld, rows, n, out, c.num_params,
                                                                                   (int)c.split_k, rw, work, tickets);
   ADDK_CHECK_LAUNCH();
   return ADDK_OK;
