@@ -77,7 +77,8 @@ class AddkGemmArgs(C.Structure):
                 ("a16_plane", C.c_int64), ("b16_plane", C.c_int64), ("a_amax", C.c_void_p), ("b_amax", C.c_void_p),
                 ("a16_ready", C.c_int32), ("b16_ready", C.c_int32), ("c_amax", C.c_void_p), ("c16_plane", C.c_int64),
                 ("relu_mask_src16", C.c_void_p), ("no_f32", C.c_int32),
-                ("relu_bits_out", C.c_void_p), ("relu_bits_in", C.c_void_p), ("ld_bits", C.c_int32)]
+                ("relu_bits_out", C.c_void_p), ("relu_bits_in", C.c_void_p), ("ld_bits", C.c_int32),
+                ("colsum_partials", C.c_void_p)]
 
 
 class AddkError(RuntimeError):

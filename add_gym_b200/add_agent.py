@@ -300,7 +300,7 @@ class ADDAgent(torch.nn.Module):
             slabs=z(2 * S, m.num_params), colsum_work=z(128 * 1024 + 64), arena=self._arena, arena16=self._arena16,
             params16=self._params16, amax_slots=self._amax_slots, arena_bits=self._arena_bits)
         for k in ("colpart_a", "colpart_c", "colpart_d"):
-            self._ws[k] = z(148 * 8, 1024) if h3 else None
+            self._ws[k] = z(148 * 8, 1024) if (h3 or bf16) else None
         if n_streams == 3:
             self._ws.update(d_pred=z(R), d_dpred=z(R), colsum_work_c=z(128 * 1024 + 64), colsum_work_d=z(128 * 1024 + 64))
         else:

@@ -226,7 +226,7 @@ extern "C" int addk_gemm(void* stream, const addk_gemm_args* a, int precision) {
   if (!a || !a->A || !a->B || !a->C || a->M <= 0 || a->N <= 0 || a->K <= 0) return ADDK_ERR_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   int rc;
-  if (precision == 0 && (a->relu_bits_in || a->relu_bits_out)) { addk_set_error("gemm: relu_bits_* need precision f16x3"); return ADDK_ERR_ARG; }
+  if (precision == 0 && (a->relu_bits_in || a->relu_bits_out || a->colsum_partials)) { addk_set_error("gemm: relu_bits_* / colsum_partials need precision f16x3 or bf16"); return ADDK_ERR_ARG; }
   if (precision == 0) rc = addk::sgemm_launch(st, *a);
   else rc = addk_gemm_tc(st, *a, precision);
   if (rc != ADDK_OK) return rc;

@@ -62,6 +62,7 @@ struct Params {
   uint32_t* bits_out = nullptr;        // written by the store loop of a layer: output element > 0
   const uint32_t* bits_in = nullptr;   // applied in the accumulator's own layout (lane = row) before staging: replaces mask / mask16
   int ld_bits = 0;                     // words per row (a multiple of 4)
+  float* colpart = nullptr;            // persistent kernels: column sums per 32-row block of the output, [ceil(M / 32), N]
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -285,6 +286,18 @@ __device__ __forceinline__ void store_staged(const Params& p, const EpiOv& e, fl
   }
 }
 
+// Column sums of a 32-row block (p.colpart): the row-major walk leaves, in every lane, the sum of its four columns over
+// the rows it visited (lanes l and l + S hold the other half of the rows): add the halves, one float4 store per column quad.
+template <int S>
+__device__ __forceinline__ void colpart_put(const Params& p, float4 cs, int lane, int grow0, int col) {
+#pragma unroll
+  for (int d = S; d < 32; d <<= 1) {
+    cs.x += __shfl_xor_sync(0xffffffffu, cs.x, d); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, d);
+    cs.z += __shfl_xor_sync(0xffffffffu, cs.z, d); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, d);
+  }
+  if (lane < S) *reinterpret_cast<float4*>(p.colpart + (size_t)(grow0 >> 5) * p.N + col) = cs;
+}
+
 // The same walk for a sub-tile that lies completely inside the matrix and does not accumulate: no bounds checks, one
 // pointer increment per store.  (ncu on the persistent f16x3 kernel: the general version above executes ~300
 // instructions per 16-byte store -- 64-bit address arithmetic, constant-bank reloads and tail predicates -- which made
@@ -310,6 +323,7 @@ __device__ __forceinline__ void store_staged_interior(const Params& p, const Epi
   const size_t dstep = (size_t)RPI * p.ldc, mstep = MASK ? (size_t)RPI * p.ld_mask : 0;
   const bool f32 = !p.no_f32;
   float vm = 0.f;
+  float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);      // column sums of this lane's four columns over its 16 rows (p.colpart)
   constexpr int EB = MASK ? 8 : 4;       // store instructions per loop iteration (masked: eight mask loads in flight)
   // (a real loop: fully unrolled, the store walk of one pass was 13 KB of straight-line code that every warp streamed
   //  through the instruction caches once per tile -- ncu: "no instruction" was the top stall reason of the epilogue)
@@ -337,6 +351,7 @@ __device__ __forceinline__ void store_staged_interior(const Params& p, const Epi
       }
       if (f32) *reinterpret_cast<float4*>(dst) = o;
       dst += dstep;
+      csum.x += o.x; csum.y += o.y; csum.z += o.z; csum.w += o.w;
       if (PLANES) {
         uint2 h, l;
         h3_split4(o, cs, h, l);
@@ -352,6 +367,7 @@ __device__ __forceinline__ void store_staged_interior(const Params& p, const Epi
     }
   }
   if (vmax) *vmax = fmaxf(*vmax, vm);
+  if (p.colpart) colpart_put<S>(p, csum, lane, grow0, col);
 }
 
 // A sub-tile whose columns lie inside the matrix but whose LAST rows do not (M = 16385: the discriminator chain's extra
@@ -366,6 +382,7 @@ __device__ __forceinline__ void store_staged_rows(const Params& p, const EpiOv& 
   float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
   if (e.bias) bb = __ldg(reinterpret_cast<const float4*>(e.bias + col));
   float vm = 0.f;
+  float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 1
   for (int i = 0; i * RPI < nrows; ++i) {          // warp-uniform bound
     const int r = i * RPI + sub_r;
@@ -381,6 +398,7 @@ __device__ __forceinline__ void store_staged_rows(const Params& p, const EpiOv& 
         o.x = m4.x > 0.f ? o.x : 0.f; o.y = m4.y > 0.f ? o.y : 0.f; o.z = m4.z > 0.f ? o.z : 0.f; o.w = m4.w > 0.f ? o.w : 0.f;
       }
       const size_t off = grow * p.ldc + col;
+      cs.x += o.x; cs.y += o.y; cs.z += o.z; cs.w += o.w;
       if (!p.no_f32) *reinterpret_cast<float4*>(Cz + off) = o;
       if (e.c_hi) {
         uint2 h, l;
@@ -394,6 +412,7 @@ __device__ __forceinline__ void store_staged_rows(const Params& p, const EpiOv& 
     }
   }
   if (vmax) *vmax = fmaxf(*vmax, vm);
+  if (p.colpart) colpart_put<S>(p, cs, lane, grow0, col);
 }
 
 // row-per-lane scalar fallback for outputs that are not 16-byte aligned (ldc % 4 != 0)
@@ -1496,7 +1515,7 @@ static int launch_h3p(cudaStream_t st, const CUtensorMap& tah, const CUtensorMap
   // the fp32 output leaves through TMA stores when its geometry allows (and nothing else rides on the epilogue)
   CUtensorMap tc = tah;
   pp.tma_store = 0; pp.repair = 0;
-  if (addk_switches().h3_tma_store && pp.p.C && !pp.p.accumulate && !pp.p.c_hi && !(SINGLE && pp.p.C16) && !pp.p.bits_out && !pp.p.bits_in &&
+  if (addk_switches().h3_tma_store && pp.p.C && !pp.p.accumulate && !pp.p.c_hi && !(SINGLE && pp.p.C16) && !pp.p.bits_out && !pp.p.bits_in && !pp.p.colpart &&
       (!pp.p.bias || (reinterpret_cast<uintptr_t>(pp.p.bias) & 15) == 0) &&
       (!pp.p.mask || ((pp.p.ld_mask & 3) == 0 && (reinterpret_cast<uintptr_t>(pp.p.mask) & 15) == 0)) &&
       make_map_c(&tc, pp.p.C, N, M, pp.p.ldc, split, pp.p.slab_stride))
@@ -1714,6 +1733,19 @@ static int apply_relu_bits(const addk_gemm_args& a, addk_tc::Params& p, int spli
   if (a.relu_bits_in) { p.bits_in = a.relu_bits_in; p.mask = nullptr; p.mask16 = nullptr; }
   return ADDK_OK;
 }
+// column sums per 32-row block (persistent kernels): only the vectorised store paths produce them
+static int apply_colsum_partials(const addk_gemm_args& a, addk_tc::Params& p, int split) {
+  if (!a.colsum_partials) return ADDK_OK;
+  if (split != 1 || a.accumulate || (a.N & 63) || (a.ldc & 3) || (reinterpret_cast<uintptr_t>(a.colsum_partials) & 15) ||
+      (reinterpret_cast<uintptr_t>(a.C) & 15) || (reinterpret_cast<uintptr_t>(a.bias) & 15) ||
+      (a.relu_mask_src && ((a.ld_mask & 3) || (reinterpret_cast<uintptr_t>(a.relu_mask_src) & 15))) ||
+      (a.relu_mask_src16 && ((a.ld_mask & 3) || (reinterpret_cast<uintptr_t>(a.relu_mask_src16) & 7)))) {
+    addk_set_error("gemm: colsum_partials need one slab, no accumulate, N % 64 == 0 and 16-byte aligned rows");
+    return ADDK_ERR_ARG;
+  }
+  p.colpart = a.colsum_partials;
+  return ADDK_OK;
+}
 
 static int gemm_bf16(cudaStream_t st, const addk_gemm_args& a) {
   using namespace addk_tc;
@@ -1747,6 +1779,7 @@ static int gemm_bf16(cudaStream_t st, const addk_gemm_args& a) {
       pp.p.no_f32 = a.no_f32 ? 1 : 0;
       if (a.relu_mask_src16) { pp.p.mask16 = reinterpret_cast<const uint16_t*>(a.relu_mask_src16); pp.p.mask = nullptr; }
       { const int rcb = apply_relu_bits(a, pp.p, split); if (rcb != ADDK_OK) return rcb; }
+      { const int rcc = apply_colsum_partials(a, pp.p, split); if (rcc != ADDK_OK) return rcc; }
       pp.a_amax = nullptr; pp.b_amax = nullptr; pp.comp_per_mma = 0.f; pp.chunk_kb = kbp; pp.bf16 = 1;
       CUtensorMap tah, tbh;
       bool okp = p.a_mn ? make_map_f16(&tah, a.A16, a.M, a.K, a.lda, 64, 64, true) : make_map_f16(&tah, a.A16, a.K, a.M, a.lda, 64, BM, true);
@@ -1759,7 +1792,7 @@ static int gemm_bf16(cudaStream_t st, const addk_gemm_args& a) {
       if (okp) { g_addk_last_gemm_kernel = ADDK_K_BF16_PERSISTENT; return launch_h3p<256, true>(st, tah, tah, tbh, tbh, pp, a.M, a.N, split); }
     }
   }
-  if (a.relu_bits_in || a.relu_bits_out) { addk_set_error("gemm bf16: relu_bits_* need the persistent kernel"); return ADDK_ERR_ARG; }
+  if (a.relu_bits_in || a.relu_bits_out || a.colsum_partials) { addk_set_error("gemm bf16: relu_bits_* / colsum_partials need the persistent kernel"); return ADDK_ERR_ARG; }
   CUtensorMap ta, tb;
   bool ok = p.a_mn ? make_map_bf16(&ta, a.A16, a.M, a.K, a.lda, 64) : make_map_bf16(&ta, a.A16, a.K, a.M, a.lda, BM);
   ok = ok && (p.b_mn ? make_map_bf16(&tb, a.B16, a.N, a.K, a.ldb, 64) : make_map_bf16(&tb, a.B16, a.K, a.N, a.ldb, BN));
@@ -1871,6 +1904,7 @@ static int gemm_h3(cudaStream_t st, const addk_gemm_args& a) {
     }
     if (a.relu_mask_src16) { pp.p.mask16 = reinterpret_cast<const uint16_t*>(a.relu_mask_src16); pp.p.mask = nullptr; }
     { const int rcb = apply_relu_bits(a, pp.p, split); if (rcb != ADDK_OK) return rcb; }
+    { const int rcc = apply_colsum_partials(a, pp.p, split); if (rcc != ADDK_OK) return rcc; }
     pp.chunk_kb = addk_switches().h3_chunk_kb;
     g_addk_last_gemm_kernel = ADDK_K_H3_PERSISTENT;
     if (addk_switches().h3_pair && a.M > BM) {      // CTA pairs (cta_group::2): each CTA stages a 128-row half of B
@@ -1879,7 +1913,7 @@ static int gemm_h3(cudaStream_t st, const addk_gemm_args& a) {
     }
     return launch_h3p<256>(st, tah, tal, tbh, tbl, pp, a.M, a.N, split);
   }
-  if (a.no_f32 || a.relu_mask_src16 || a.relu_bits_in || a.relu_bits_out) { addk_set_error("gemm f16x3: no_f32 / relu_mask_src16 / relu_bits_* need the persistent kernel"); return ADDK_ERR_ARG; }
+  if (a.no_f32 || a.relu_mask_src16 || a.relu_bits_in || a.relu_bits_out || a.colsum_partials) { addk_set_error("gemm f16x3: no_f32 / relu_mask_src16 / relu_bits_* / colsum_partials need the persistent kernel"); return ADDK_ERR_ARG; }
   // (a 256 x 128 instance of the CTA-pair kernel for the 65 .. 128-column layers -- gx = u1.W0, the 1024 x 114 weight
   //  gradients -- measured 27 vs 31 and 43 vs 53 us in isolation and nothing in the whole optimizer step: not kept)
   g_addk_last_gemm_kernel = ADDK_K_H3_TILE;
@@ -1904,6 +1938,10 @@ extern "C" int addk_gemm_is_persistent(const addk_gemm_args* a, int precision) {
 static int gemm_fallback(cudaStream_t st, const addk_gemm_args& a);
 
 int addk_gemm_tc(cudaStream_t st, const addk_gemm_args& a, int precision) {
+  if (a.colsum_partials && !((precision == 4 || precision == 3) && addk_gemm_is_persistent(&a, precision))) {
+    addk_set_error("gemm: colsum_partials are produced by the persistent f16x3 / bf16 kernels only (addk_gemm_is_persistent)");
+    return ADDK_ERR_ARG;
+  }
   if ((a.relu_bits_in || a.relu_bits_out) && !((precision == 4 || precision == 3) && addk_gemm_is_persistent(&a, precision))) {
     addk_set_error("gemm: relu_bits_in / relu_bits_out are honoured by the persistent f16x3 / bf16 kernels only (addk_gemm_is_persistent)");
     return ADDK_ERR_ARG;

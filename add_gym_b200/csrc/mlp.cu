@@ -742,6 +742,9 @@ struct ChainWs {
 static thread_local const float* g_colpart_for = nullptr;
 static thread_local float* g_colpart_buf = nullptr;
 static thread_local int g_colpart_rows = 0;
+// ... or the dense layer that PRODUCED dY left them behind in its epilogue (gemm(..., colpart_out)): tensor and row count
+static thread_local const float* g_colpart_epi_for = nullptr;
+static thread_local int g_colpart_epi_rows = 0;
 
 static int colsum(cudaStream_t st, const addk_update_ctx& c, const ChainWs& ws, const float* dY, int ld, int rows, int n,
                   float* out, const float* rw, const uint16_t* dY16 = nullptr, const uint32_t* planes_slot = nullptr) {
@@ -925,7 +928,7 @@ static bool is_16only(const addk_update_ctx& c, long long rows, int cols) {
 static int gemm(cudaStream_t st, int prec, const float* A, int lda, int ta, const float* B, int ldb, int tb, float* C,
                 int ldc, int M, int N, int K, const float* bias = nullptr, int relu = 0, const float* mask = nullptr,
                 int ld_mask = 0, int split = 1, const float* nmean = nullptr, const float* nstd = nullptr,
-                long long slab_stride = 0, int flags16 = 0) {
+                long long slab_stride = 0, int flags16 = 0, float* colpart_out = nullptr) {
   // flags16 (precision "bf16"): F16_DROP_C -- C is only ever read by dense layers / as a ReLU mask / by colsum: do not
   // write its fp32 copy when the persistent kernel runs; F16_MASK -- the mask source was produced that way: read its bf16 copy
   addk_gemm_args a;
@@ -1016,6 +1019,15 @@ static int gemm(cudaStream_t st, int prec, const float* A, int lda, int ta, cons
     a.relu_mask_src = nullptr;
   }
   a.relu_bits_out = nullptr; a.relu_bits_in = nullptr; a.ld_bits = 0;
+  // the bias gradient of a gradient tensor that only exists as planes / its 16-bit copy: column sums per 32-row block
+  // from the epilogue of the layer that produces it (wgrad() reduces them), instead of a second pass over the tensor
+  a.colsum_partials = nullptr;
+  if (colpart_out || C == g_colpart_epi_for) g_colpart_epi_for = nullptr;      // (the buffer / the tensor is about to be rewritten)
+  if (colpart_out && (prec == 4 || prec == 3) && g_twin_ctx && a.A16 && a.B16 && split == 1 && (N & 63) == 0 && (ldc & 3) == 0 &&
+      addk_switches().h3_colpart && addk_gemm_is_persistent(&a, prec) && (prec == 4 || (a.C16 && M > 128)) &&
+      (long long)((M + 31) / 32) <= 148 * 8) {
+    a.colsum_partials = colpart_out;
+  }
   int bits_ent = -1;
   if ((prec == 4 || prec == 3) && g_twin_ctx && g_want_bits && a.A16 && a.B16 && split == 1 && (N & 127) == 0 && addk_gemm_is_persistent(&a, prec) &&
       (prec == 4 || (a.C16 && M > 128))) {      // (bf16: the calls gemm_bf16() routes to the persistent kernel)
@@ -1044,6 +1056,7 @@ static int gemm(cudaStream_t st, int prec, const float* A, int lda, int ta, cons
   if (rc != ADDK_OK) return rc;
   ADDK_CHECK_LAUNCH();
   if (bits_ent >= 0) g_bits[bits_ent].valid = true;
+  if (a.colsum_partials) { g_colpart_epi_for = C; g_colpart_epi_rows = (M + 31) / 32; }
   if (c_ent >= 0) {     // planes written by the epilogue: rewritten only if the sticky scale did not fit max|C|
     if (!planes_only) {   // (planes-only layers repair themselves: second launch inside addk_gemm)
       rc = addk_f16x3_repair(st, C, M, N, ldc, a.C16, a.c16_plane, a.c_amax);
@@ -1066,8 +1079,9 @@ static int wgrad(cudaStream_t st, const Ctx& c, const ChainWs& ws, const float* 
     // f16x3: if this call is the one that converts dY, its split pass also leaves the column sums of dY (the bias gradient)
     const int fuse = addk_switches().h3_colpart;          // ADDK_H3_COLPART=0: A/B switch (separate column-sum kernels)
     g_colpart_rows = 0;
-    g_colpart_for = (o_b >= 0 && fuse) ? dY : nullptr;
-    g_colpart_buf = (o_b >= 0 && fuse) ? ws.colpart : nullptr;
+    const bool have_epi = ws.colpart && g_colpart_epi_for == dY;      // the layer that produced dY left the partials already
+    g_colpart_for = (o_b >= 0 && fuse && !have_epi) ? dY : nullptr;
+    g_colpart_buf = (o_b >= 0 && fuse && !have_epi) ? ws.colpart : nullptr;
     const int rc = gemm(st, (int)c.precision, dY, ldy, 1, X, ldx, 0, F(c.slabs) + (size_t)slab0 * P + o_w, k_in, n_out, k_in, rows,
                         nullptr, 0, nullptr, 0, S, nullptr, nullptr, P);
     g_colpart_for = nullptr; g_colpart_buf = nullptr;
@@ -1083,6 +1097,15 @@ static int wgrad(cudaStream_t st, const Ctx& c, const ChainWs& ws, const float* 
       g_colpart_rows = 0;
       return ADDK_OK;
     }
+  }
+  if (o_b >= 0 && ws.colpart && g_colpart_epi_for == dY && g_colpart_epi_rows == (rows + 31) / 32) {
+    float* cwork = ws.colsum_work;
+    unsigned int* ctick = (unsigned int*)(cwork + (size_t)COLSUM_CHUNKS * COLSUM_MAX_N) + 32;
+    colsum_parts_kernel<<<dim3((n_out + 31) / 32, CP_CHUNKS), 256, 0, st>>>(ws.colpart, g_colpart_epi_rows, n_out,
+                                                                             F(c.slabs) + (size_t)slab0 * P + o_b, P, S, cwork, ctick);
+    ADDK_CHECK_LAUNCH();
+    g_colpart_epi_for = nullptr;
+    return ADDK_OK;
   }
   if (o_b >= 0) {
     const bool only16 = dy_16only && is_16only(c, rows, n_out);
@@ -1155,9 +1178,9 @@ static int trunk_backward(cudaStream_t st, const Ctx& c, const ChainWs& ws, cons
   const int H1 = (int)c.hid_a1, H2 = (int)c.hid_a2, H3 = (int)c.hid_a3, pr = (int)c.precision;
   TRY(wgrad(st, c, ws, ws.g3, H3, ws.h2, H2, rows, H3, H2, o_w2, o_b2, 0));
   // (g2, g1: dense-layer operands + bias column sums only; their masks h2, h1 have no fp32 copy in bf16 mode)
-  TRY(gemm(st, pr, ws.g3, H3, 0, P + o_w2, H2, 0, ws.g2, H2, rows, H2, H3, nullptr, 0, ws.h2, H2, 1, nullptr, nullptr, 0, F16_DROP_C | F16_MASK));
+  TRY(gemm(st, pr, ws.g3, H3, 0, P + o_w2, H2, 0, ws.g2, H2, rows, H2, H3, nullptr, 0, ws.h2, H2, 1, nullptr, nullptr, 0, F16_DROP_C | F16_MASK, ws.colpart));
   TRY(wgrad(st, c, ws, ws.g2, H2, ws.h1, H1, rows, H2, H1, o_w1, o_b1, 0, true));
-  TRY(gemm(st, pr, ws.g2, H2, 0, P + o_w1, H1, 0, ws.g1, H1, rows, H1, H2, nullptr, 0, ws.h1, H1, 1, nullptr, nullptr, 0, F16_DROP_C | F16_MASK));
+  TRY(gemm(st, pr, ws.g2, H2, 0, P + o_w1, H1, 0, ws.g1, H1, rows, H1, H2, nullptr, 0, ws.h1, H1, 1, nullptr, nullptr, 0, F16_DROP_C | F16_MASK, ws.colpart));
   TRY(wgrad(st, c, ws, ws.g1, H1, X, ldx, rows, H1, in_dim, o_w0, o_b0, 0, true));
   return ADDK_OK;
 }
@@ -1341,7 +1364,7 @@ extern "C" int addk_update_minibatch(void* stream, void* ctx_host, const long lo
   // ordinary backward of the BCE terms
   TRY(wgrad(sd, c, wd, dpred_d, 1, e2, E2, R, 1, E2, c.o_d_wl, c.o_d_bl, 0));
   TRY(wgrad(sd, c, wd, dh2, E2, e1, E1, R, E2, E1, c.o_d_w1, c.o_d_b1, 0));
-  TRY(gemm(sd, pr, dh2, E2, 0, W + c.o_d_w1, E1, 0, F(c.u1), E1, R, E1, E2, nullptr, 0, e1, E1, 1, nullptr, nullptr, 0, F16_DROP_C | F16_MASK));
+  TRY(gemm(sd, pr, dh2, E2, 0, W + c.o_d_w1, E1, 0, F(c.u1), E1, R, E1, E2, nullptr, 0, e1, E1, 1, nullptr, nullptr, 0, F16_DROP_C | F16_MASK, wd.colpart));
   TRY(wgrad(sd, c, wd, F(c.u1), E1, F(c.dn), DL, R, E1, DD, c.o_d_w0, c.o_d_b0, 0, true));
   if (multi) {
     cudaEventRecord(aux->join[0], sc);

@@ -281,6 +281,11 @@ typedef struct addk_gemm_args {
   uint32_t* relu_bits_out;
   const uint32_t* relu_bits_in;
   int32_t ld_bits;
+  /* Optional (persistent kernels, single slab, no accumulate, N and ldc multiples of 4): the epilogue also leaves the
+   * column sums of every 32-row block of the output behind -- colsum_partials[(row / 32) * N + col], ceil(M / 32) rows of
+   * N floats -- so that the bias gradient 1^T dY of a gradient tensor costs one small reduction over the partial rows
+   * instead of a second pass over dY (csrc/mlp.cu: colsum_parts_kernel). */
+  float* colsum_partials;
 } addk_gemm_args;
 /* 1 if addk_gemm would run this call on a persistent tensor-core kernel (the only ones that honour no_f32 /
  * relu_mask_src16), given 16-bit operands TMA can address */

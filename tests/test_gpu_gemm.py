@@ -161,7 +161,7 @@ class _Twin:
 
 
 def _gemm_h3(A, B, Cout, M, N, K, ta, tb, tw_a, tw_b, ready=(0, 0), bias=None, relu=0, mask=None, split=1, accumulate=0,
-             c_amax=None, c16=None, bits_out=None, bits_in=None, no_f32=0):
+             c_amax=None, c16=None, bits_out=None, bits_in=None, no_f32=0, colpart=None):
     from add_gym_b200 import _lib
     a = _lib.AddkGemmArgs(A=A.data_ptr(), lda=A.stride(0), B=B.data_ptr(), ldb=B.stride(0), C=Cout.data_ptr(),
                           ldc=Cout.stride(-2), M=M, N=N, K=K, bias=bias.data_ptr() if bias is not None else None,
@@ -173,6 +173,8 @@ def _gemm_h3(A, B, Cout, M, N, K, ta, tb, tw_a, tw_b, ready=(0, 0), bias=None, r
                           c_amax=c_amax.data_ptr() if c_amax is not None else None,
                           C16=c16.planes.data_ptr() if c16 is not None else None, c16_plane=c16.n if c16 is not None else 0,
                           no_f32=no_f32)
+    if colpart is not None:     # [ceil(M / 32), N] column sums per 32-row block of the output
+        a.colsum_partials = colpart.data_ptr()
     bits = bits_out if bits_out is not None else bits_in
     if bits is not None:      # ReLU bit plane [rows, ld_bits] int32
         a.ld_bits = bits.stride(0)
@@ -418,11 +420,20 @@ def test_gemm_f16x3_relu_bit_planes(M, planes_only):
     W2 = torch.randn(K2, N, device="cuda", generator=g) * 0.05
     tdY, tW2 = _Twin(dY), _Twin(W2)
     out_bits = torch.full((M, N), float("nan"), device="cuda")
-    _gemm_h3(dY, W2, out_bits, M, N, K2, 0, 0, tdY, tW2, bits_in=bits)
+    nblk = (M + 31) // 32
+    part = torch.full((nblk + 2, N), float("nan"), device="cuda")
+    _gemm_h3(dY, W2, out_bits, M, N, K2, 0, 0, tdY, tW2, bits_in=bits, colpart=part)
     torch.cuda.synchronize()
     assert _last_kernel() in K_H3_PERSISTENT
     ref = (dY.double() @ W2.double()) * got.double()
     assert _rel(out_bits, ref) <= TOL["f16x3"]
+    # column sums per 32-row block, left behind by the same epilogue (the bias gradient of a gradient tensor)
+    pad = torch.zeros(nblk * 32, N, device="cuda", dtype=torch.float64)
+    pad[:M] = out_bits.double()
+    blocks = pad.view(nblk, 32, N).sum(1)
+    assert not bool(torch.isnan(part[:nblk]).any()) and bool(torch.isnan(part[nblk:]).all())
+    assert float((part[:nblk].double() - blocks).abs().max()) <= 1e-5 * float(blocks.abs().max())
+    assert _rel(part[:nblk].double().sum(0), out_bits.double().sum(0)) <= 1e-6
     maskf = got.float()                                     # the same mask as an fp32 tensor through the old path
     out_mask = torch.full((M, N), float("nan"), device="cuda")
     _gemm_h3(dY, W2, out_mask, M, N, K2, 0, 0, tdY, tW2, ready=(1, 1), mask=maskf)
