@@ -1359,8 +1359,17 @@ extern "C" int addk_update_minibatch(void* stream, void* ctx_host, const long lo
   TRY(gemm(sd, pr, F(c.dg), DL, 0, Wd0, DL, 1, dv1, E1, R, E1, DL, nullptr, 0, e1, E1, 1, nullptr, nullptr, 0, F16_DROP_C | F16_MASK));
   TRY(gemm(sd, pr, F(c.u2), E2, 1, dv1, E1, 0, F(c.slabs) + (size_t)S * P + c.o_d_w1, E1, E2, E1, R, nullptr, 0, nullptr, 0,
            S, nullptr, nullptr, P));
-  TRY(gemm(sd, pr, dv1, E1, 0, W + c.o_d_w1, E1, 1, du2, E2, R, E2, E1, nullptr, 0, e2, E2));
-  TRY(colsum(sd, c, wd, du2, E2, R, E2, F(c.slabs) + (size_t)S * P + c.o_d_wl, nullptr));
+  TRY(gemm(sd, pr, dv1, E1, 0, W + c.o_d_w1, E1, 1, du2, E2, R, E2, E1, nullptr, 0, e2, E2, 1, nullptr, nullptr, 0, 0, wd.colpart));
+  if (wd.colpart && g_colpart_epi_for == du2 && g_colpart_epi_rows == (R + 31) / 32) {      // column sums left by the epilogue
+    float* cwork = wd.colsum_work;
+    unsigned int* ctick = (unsigned int*)(cwork + (size_t)COLSUM_CHUNKS * COLSUM_MAX_N) + 32;
+    colsum_parts_kernel<<<dim3((E2 + 31) / 32, CP_CHUNKS), 256, 0, sd>>>(wd.colpart, g_colpart_epi_rows, E2,
+                                                                          F(c.slabs) + (size_t)S * P + c.o_d_wl, P, S, cwork, ctick);
+    ADDK_CHECK_LAUNCH();
+    g_colpart_epi_for = nullptr;
+  } else {
+    TRY(colsum(sd, c, wd, du2, E2, R, E2, F(c.slabs) + (size_t)S * P + c.o_d_wl, nullptr));
+  }
   // ordinary backward of the BCE terms
   TRY(wgrad(sd, c, wd, dpred_d, 1, e2, E2, R, 1, E2, c.o_d_wl, c.o_d_bl, 0));
   TRY(wgrad(sd, c, wd, dh2, E2, e1, E1, R, E2, E1, c.o_d_w1, c.o_d_b1, 0));
