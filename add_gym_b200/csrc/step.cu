@@ -21,7 +21,7 @@
 
 namespace addk {
 
-constexpr int WPB = 8;  // warps (= envs) per block
+constexpr int WPB = 4;  // warps (= envs) per block
 
 enum { F_ADVANCE = 1, F_UPDATE_MOTION = 2, F_REWARD_DONE = 4, F_MASKED = 8 };
 
