@@ -417,9 +417,34 @@ constexpr int O_ROWS = 0, O_REFV = 9 * HALF, O_SIM = O_REFV + HALF, O_HIST = O_S
 
 struct FastTail { float pe, ve, de, t, mt, m_len, ret0; int contact, m_loop; long long len0; };
 
+// ---- bulk-copy staging (cp.async.bulk + mbarrier): one 144-byte copy per table / history row, issued by one lane each ----
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bulk_bar_init(uint32_t bar) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_bar_expect(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void bulk_bar_wait(uint32_t bar) {      // phase 0: the barrier is used once per launch
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(bar) : "memory");
+  }
+}
+
 // Everything a warp does for its env up to the warp-wide reductions of the reward terms; `sw` = this warp's shared-memory
 // slice.  Lane 0's `o` is complete (clip length / loop mode / return-tracker state are loaded by lane 0 only).
-__device__ __forceinline__ void env_step_fast_main(const StepParams& p, float* const sw, const int lane, const int e, FastTail& o) {
+__device__ __forceinline__ void env_step_fast_main(const StepParams& p, float* const sw, const uint32_t bar, const int lane, const int e,
+                                                   FastTail& o) {
   using namespace fast;
   const addk_task& tk = p.task;
   float* const s_rows = sw + O_ROWS;
@@ -450,12 +475,15 @@ __device__ __forceinline__ void env_step_fast_main(const StepParams& p, float* c
   }
   if (lane < 4) sim_q = p.sim.root_rot[(size_t)e * p.sim.ld_root_rot + lane];
   float* const g_hist = p.env.hist + (size_t)e * NH * p.env.hist_stride;
-  const int nload = push ? 2 * 9 : 3 * 9;        // with a push the newest history entry is the simulator state itself
-  float4 hv = make_float4(0.f, 0.f, 0.f, 0.f);
-  const int hj = lane / 9, hc = lane - 9 * hj;
-  if (lane < nload) {
+  const int nhist = push ? 2 : 3;                // with a push the newest history entry is the simulator state itself
+  // history rows (pose halves): one 144-byte bulk copy each, lanes 10 .. 10 + nhist - 1 (the table rows follow below:
+  // 13 copy instructions per env instead of 117 float4 loads, their address arithmetic and the register -> shared stores)
+  if (lane == 0) { bulk_bar_init(bar); bulk_bar_expect(bar, (uint32_t)((10 + nhist) * HALF * sizeof(float))); }
+  __syncwarp();
+  if (lane >= 10 && lane < 10 + nhist) {
+    const int hj = lane - 10;
     const int slot = (p.newest_slot + 1 + hj) % NH;   // logical j (oldest..newest) lives in slot (newest_slot+1+j) % NH
-    hv = *reinterpret_cast<const float4*>(g_hist + (size_t)slot * p.env.hist_stride + 4 * hc);
+    bulk_copy_g2s(smem_addr(s_hist + HALF * hj), g_hist + (size_t)slot * p.env.hist_stride, HALF * sizeof(float), bar);
   }
   int c_valid = 0, c_la = -1, c_lb = -1;
   if ((p.flags & F_REWARD_DONE) && lane < p.sim.contact_slots && p.sim.valid) {     // first 32 slots, loaded up front
@@ -474,37 +502,22 @@ __device__ __forceinline__ void env_step_fast_main(const StepParams& p, float* c
   }
   t = __shfl_sync(0xffffffffu, t, 0);
   const float mt = add_rn(t, off);
-  // lane b < 9 owns the row index of pose block b
-  long long my_row = 0;
-  if (lane < 9) {
+  // lane b < 9 owns pose block b (0 = ref at t, 1..6 = targets, 7..8 = demo t-0.02 / t-0.01), lane 9 the velocity half of
+  // the ref row: each computes its table row and issues ONE bulk copy of that half row into the staging area
+  if (lane < 10) {
     float tt = mt;
     if (lane >= 1 && lane <= 6) tt = add_rn(mt, tk.tar_offsets[lane - 1]);
-    if (lane >= 7) tt = add_rn(mt, tk.disc_offsets[lane - 7]);
-    my_row = table_row(p.lib, tt, tk.dt_inv, start);
+    if (lane >= 7 && lane <= 8) tt = add_rn(mt, tk.disc_offsets[lane - 7]);
+    const long long row = table_row(p.lib, tt, tk.dt_inv, start);
+    bulk_copy_g2s(smem_addr(lane < 9 ? s_rows + HALF * lane : s_refv), p.lib.table + (size_t)row * RS + (lane < 9 ? 0 : HALF),
+                  HALF * sizeof(float), bar);
   }
-  float4 tv4[3];
-#pragma unroll
-  for (int r = 0; r < 3; ++r) {        // 81 float4 of pose halves + 9 float4 of the ref row's velocity half
-    const int i = lane + 32 * r;
-    const int b = i < 81 ? i / 9 : 0;
-    const int c = i < 81 ? i - 9 * b : i - 81;
-    const long long row = __shfl_sync(0xffffffffu, my_row, b);
-    tv4[r] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (i < 90) tv4[r] = ldg4(p.lib.table + (size_t)row * RS + (i < 81 ? 0 : HALF) + 4 * c);
-  }
-  // ---- everything into shared memory -------------------------------------------------------------------------
+  // ---- the simulator state into shared memory (registers -> shared), then wait for the copies ---------------------
   if (lane < D) { s_sim[7 + lane] = sim_dp; s_sim[HALF + 6 + lane] = sim_dv; }
   if (lane < 3) { s_sim[lane] = sim_p; s_sim[HALF + lane] = sim_v; s_sim[HALF + 3 + lane] = sim_a; }
   if (lane < 4) s_sim[3 + lane] = sim_q;
   if (lane == 31) { s_sim[HALF + 6 + D] = 0.0f; }          // the one pad float of the velocity half (7 + D == HALF)
-  if (lane < nload) stg4(s_hist + HALF * hj + 4 * hc, hv);
-#pragma unroll
-  for (int r = 0; r < 3; ++r) {
-    const int i = lane + 32 * r;
-    const int b = i < 81 ? i / 9 : 0;
-    const int c = i < 81 ? i - 9 * b : i - 81;
-    if (i < 90) stg4((i < 81 ? s_rows + HALF * b : s_refv) + 4 * c, tv4[r]);
-  }
+  bulk_bar_wait(bar);
   __syncwarp();
   if (push) {
     if (lane < RS / 4) {
@@ -708,15 +721,17 @@ __global__ void __launch_bounds__(WPB * 32, MIN_BLOCKS) env_step_fast_kernel(con
   const int e = blockIdx.x * WPB + warp;
   const bool active = e < p.n && !((p.flags & F_MASKED) && !p.env_mask[e]);
   float* const sw = smem + (size_t)warp * PER_WARP;
+  __shared__ __align__(8) unsigned long long s_bar[WPB];      // one single-use mbarrier per warp (bulk-copy staging)
+  const uint32_t bar = smem_addr(&s_bar[warp]);
   FastTail o;
   if (!CTA_TAIL) {
     if (!active) return;
-    env_step_fast_main(p, sw, lane, e, o);
+    env_step_fast_main(p, sw, bar, lane, e, o);
     if ((p.flags & F_REWARD_DONE) && lane == 0) env_step_fast_tail(p, e, sw, o);
   } else {
     __shared__ FastTail s_tail[WPB];
     __shared__ int s_active[WPB];
-    if (active) env_step_fast_main(p, sw, lane, e, o);
+    if (active) env_step_fast_main(p, sw, bar, lane, e, o);
     if (!(p.flags & F_REWARD_DONE)) return;                 // uniform over the grid
     if (lane == 0) { s_active[warp] = active ? 1 : 0; if (active) s_tail[warp] = o; }
     __syncthreads();

@@ -525,6 +525,9 @@ def step_kernel_roofline(agent, hbm_peak, motions="walk"):
     # tensor load the clock is still at its power-capped 1.3-1.4 GHz (the rollout itself runs at full clock)
     for _ in range(40):
         g.replay()
+    # back to episode time 0: the launches above ran 800+ env steps without resets, and envs past the end of their clip
+    # report done on every step -- three double atomics each on the return tracker's three words (17.6 vs 8.1 us at 4096 envs)
+    agent._env.time_buf.zero_()
     torch.cuda.synchronize()
     runs = []
     for _ in range(5):
