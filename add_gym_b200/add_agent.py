@@ -315,7 +315,8 @@ class ADDAgent(torch.nn.Module):
                     buf_a_logp=fb("a_logp"), buf_adv=fb("adv"), buf_tar_val=fb("tar_val"),
                     buf_mask=fb("rand_action_mask"), buf_disc_obs=fb("disc_obs"), buf_disc_demo=fb("disc_obs_demo"))
         ints = dict(obs_dim=od, obs_ld=ol, act_dim=ad, disc_dim=dd, act_ld=al, disc_ld=dl, mb_rows=M, num_params=m.num_params,
-                    split_k=S, arena_elems=total, precision=m.precision, n_streams=n_streams, hid_a1=H[0], hid_a2=H[1], hid_a3=H[2], hid_d1=E[0], hid_d2=E[1])
+                    split_k=S, arena_elems=total, precision=m.precision, n_streams=n_streams, hid_a1=H[0], hid_a2=H[1], hid_a3=H[2], hid_d1=E[0], hid_d2=E[1],
+                    params16_current=0)
         ints.update(m.offsets)
         opt = self._optimizer
         f64 = dict(ppo_clip_ratio=self._ppo_clip_ratio, action_bound_weight=self._action_bound_weight,
@@ -326,6 +327,11 @@ class ADDAgent(torch.nn.Module):
                    grad_clip=opt._grad_clip)
         self._mb_rows = M
         self._ctx = _lib.UpdateCtx(ptrs, ints, f64)
+        # the same context for the env steps of ONE rollout: the weights do not change between them, so the 16-bit twin
+        # of the parameters and the padded first-layer weights are converted once (addk_params_refresh at the start of
+        # _rollout_train) instead of on each of the 32 actor calls
+        self._ctx_rollout = self._ctx.rebuild(params16_current=1)
+        self._actor_ctx = self._ctx
         opt.on_hyperparams_changed = self._sync_optimizer_scalars
         # rollout scratch
         self._action = z(N, ad)
@@ -343,6 +349,9 @@ class ADDAgent(torch.nn.Module):
         opt = self._optimizer
         self._ctx = self._ctx.rebuild(lr=opt.lr, beta1=opt.betas[0], beta2=opt.betas[1], adam_eps=opt.eps,
                                       weight_decay=opt.weight_decay, grad_clip=opt._grad_clip)
+        in_rollout = self._actor_ctx is self._ctx_rollout
+        self._ctx_rollout = self._ctx.rebuild(params16_current=1)
+        self._actor_ctx = self._ctx_rollout if in_rollout else self._ctx
 
     # ---- small reference API -------------------------------------------------------------------------------------
     def get_num_envs(self):
@@ -387,7 +396,7 @@ class ADDAgent(torch.nn.Module):
         if record_t is not None:
             rec = [b("obs")[record_t], b("action")[record_t], b("a_logp")[record_t], b("rand_action_mask")[record_t]]
         rc = _lib.lib().addk_actor_step(
-            _lib.stream(), self._ctx.buf, _lib.ptr(obs), _lib.ptr(noise), _lib.ptr(mask), C.c_int(N),
+            _lib.stream(), self._actor_ctx.buf, _lib.ptr(obs), _lib.ptr(noise), _lib.ptr(mask), C.c_int(N),
             _lib.ptr(self._action), _lib.ptr(self._a_logp), *[_lib.ptr(r) for r in rec])
         _lib.check(rc, "addk_actor_step")
         m = mask if mask is not None else torch.ones(N, device=self._device)
@@ -550,21 +559,27 @@ class ADDAgent(torch.nn.Module):
                                     {"disc_obs": b("disc_obs")[t], "disc_obs_demo": b("disc_obs_demo")[t]})
 
     def _rollout_train(self, num_steps):
-        graphed = self._graphs_ok()
-        if graphed and not self._graphs_pre:
-            self._capture_all()
-        hooks = self._record_hooks_overridden()
-        for _ in range(num_steps):
-            t = self._exp_buffer.get_buffer_head()
-            if graphed:
-                self._rollout_step_graphed(t)
-            else:
-                action, _ = self._decide_action(self._curr_obs, self._curr_info, record_t=t)
-                _, _, done, _ = self._step_env(action, record_t=t)
-                self._curr_obs, self._curr_info = self._reset_done_envs(done)
-            if hooks:
-                self._call_record_hooks(t)
-            self._exp_buffer.inc()
+        # one conversion of the parameters' 16-bit twin / padded first-layer weights for all env steps of this rollout
+        _lib.check(_lib.lib().addk_params_refresh(_lib.stream(), self._ctx.buf), "addk_params_refresh")
+        self._actor_ctx = self._ctx_rollout
+        try:
+            graphed = self._graphs_ok()
+            if graphed and not self._graphs_pre:
+                self._capture_all()
+            hooks = self._record_hooks_overridden()
+            for _ in range(num_steps):
+                t = self._exp_buffer.get_buffer_head()
+                if graphed:
+                    self._rollout_step_graphed(t)
+                else:
+                    action, _ = self._decide_action(self._curr_obs, self._curr_info, record_t=t)
+                    _, _, done, _ = self._step_env(action, record_t=t)
+                    self._curr_obs, self._curr_info = self._reset_done_envs(done)
+                if hooks:
+                    self._call_record_hooks(t)
+                self._exp_buffer.inc()
+        finally:
+            self._actor_ctx = self._ctx
         self._rollouts_done += 1
 
     # ---- training data ------------------------------------------------------------------------------------------

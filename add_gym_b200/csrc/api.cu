@@ -30,7 +30,6 @@ const AddkSwitches& addk_switches() {
     s.h3_flags = env_int("ADDK_H3_FLAGS", 0);
     s.h3_persistent = env_int("ADDK_H3_PERSISTENT", 1);
     s.h3_pair = env_int("ADDK_H3_PAIR", 1);
-    s.h3_tma_store = env_int("ADDK_H3_TMA_STORE", 0);
     s.h3_chunk_kb = env_int("ADDK_H3_CHUNK_KB", 8);
     if (s.h3_chunk_kb < 1) s.h3_chunk_kb = 1;
     const char* e = getenv("ADDK_H3_COMP");

@@ -105,6 +105,10 @@ ADDK_INT(split_k)
 ADDK_INT(arena_elems)   // elements in the arena
 ADDK_INT(precision)     // 0 fp32 | 1 tf32x3 | 2 tf32 | 3 bf16 | 4 f16x3
 ADDK_INT(n_streams)     // 1 | 3
+ADDK_INT(params16_current) // 1: the caller guarantees that nothing changed the parameters since addk_params_refresh() ran on this
+                        //    context's buffers -- the inference entry points then skip the per-call conversion of the flat
+                        //    parameter vector (max pass + split pass / bf16 copy, 17 MB) and the re-padding of the first-layer
+                        //    weights (32 env steps of one rollout share one set of weights).  addk_update_minibatch refuses it.
 ADDK_INT(hid_a1)        // actor/critic hidden sizes (1024, 1024, 512)
 ADDK_INT(hid_a2)
 ADDK_INT(hid_a3)

@@ -1025,17 +1025,6 @@ __device__ __forceinline__ void umma_commit_2cta(uint32_t bar) {   // arrives on
                ::"r"(bar), "h"((uint16_t)3) : "memory");
 }
 
-// TMA store of one [32 rows x 32 fp32] staging box (128-byte rows, SWIZZLE_128B) into C; the hardware clips the box at
-// the tensor bounds, so ragged tiles need no edge path.  Coordinates: {column, row, split-K slab}.
-__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
-  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
-               ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
-}
-__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
-__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-
 struct ParamsP {
   Params p;
   const uint32_t* a_amax; const uint32_t* b_amax;
@@ -1043,7 +1032,6 @@ struct ParamsP {
   int tiles_m, tiles_n, total_tiles;
   int chunk_kb;                 // k-blocks per accumulator chunk (drain period)
   int bf16;                     // SINGLE kernel: operands are bf16 (instruction descriptor format 1)
-  int tma_store;                // the fp32 output leaves through TMA stores from the staging tile (tmC is valid)
   int repair;                   // second launch of a layer whose output exists only as fp16 planes: exits at once when the
                                 //   sticky scale the first launch used fits max|C| (the normal case), else recomputes the
                                 //   layer and writes the planes with the scale that max|C| asks for
@@ -1061,7 +1049,7 @@ template <int BN, bool SINGLE, bool PAIR>
 __global__ void __launch_bounds__(P_THREADS, 1)
 gemm_tc_h3p_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                    const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
-                   const __grid_constant__ CUtensorMap tmC, const ParamsP pp) {
+                   const ParamsP pp) {
   using C = CfgP<BN, SINGLE, PAIR>;
   const Params& p = pp.p;
   if (pp.repair) {      // uniform over the grid: two words every thread reads the same
@@ -1312,56 +1300,7 @@ gemm_tc_h3p_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
       uint4 mbits = make_uint4(0u, 0u, 0u, 0u), obits = make_uint4(0u, 0u, 0u, 0u);
       if (CPW == 128 && p.bits_in && row < p.M && cw0 < p.N)
         mbits = __ldg(reinterpret_cast<const uint4*>(p.bits_in + (size_t)row * p.ld_bits + (cw0 >> 5)));
-      if (pp.tma_store) {
-        // 32 columns at a time, in the accumulator's own layout (lane = row): scale, bias / ReLU / ReLU-mask in registers,
-        // then a swizzled [32 x 32] box in shared memory (two boxes per warp, alternating) that ONE lane hands to the TMA
-        // engine.  The worker warps never touch global memory for C: no address arithmetic, no edge predicates (the
-        // hardware clips the box), and the store of box i overlaps the arithmetic of box i + 1.
-        const bool row_ok = row < p.M;
-        const float* const mk_row = (p.mask && row_ok) ? p.mask + (size_t)row * p.ld_mask : nullptr;
-        const bool relu = p.relu != 0;
-#pragma unroll
-        for (int cc = 0; cc < NCH; ++cc) {
-          const int c0 = cw0 + 32 * cc;
-          if (c0 < p.N && !(p.pair_flags & 1)) {             // warp-uniform
-            const bool full = c0 + 32 <= p.N;
-            float4* const buf = stg + (cc & 1) * (32 * 8);
-            if (lane == 0 && !(p.pair_flags & 4)) tma_store_wait_read<1>();          // the box that used this buffer two stores ago has been read
-            __syncwarp();
-#pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
-              const int col = c0 + 4 * j4;
-              float4 o = make_float4(acc[cc * 32 + 4 * j4] * inv, acc[cc * 32 + 4 * j4 + 1] * inv, acc[cc * 32 + 4 * j4 + 2] * inv,
-                                     acc[cc * 32 + 4 * j4 + 3] * inv);
-              if (full || col + 3 < p.N) {
-                if (p.bias) { const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + col)); o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w; }
-                if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-                if (mk_row) {
-                  const float4 m4 = __ldg(reinterpret_cast<const float4*>(mk_row + col));
-                  o.x = m4.x > 0.f ? o.x : 0.f; o.y = m4.y > 0.f ? o.y : 0.f; o.z = m4.z > 0.f ? o.z : 0.f; o.w = m4.w > 0.f ? o.w : 0.f;
-                }
-                if (row_ok) vmax = fmaxf(fmaxf(vmax, fmaxf(fabsf(o.x), fabsf(o.y))), fmaxf(fabsf(o.z), fabsf(o.w)));
-              } else {                                          // ragged right edge: element-wise guards (the TMA clips the rest)
-                float e[4] = {o.x, o.y, o.z, o.w};
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                  if (col + u < p.N) {
-                    if (p.bias) e[u] += p.bias[col + u];
-                    if (relu) e[u] = fmaxf(e[u], 0.f);
-                    if (mk_row) e[u] = mk_row[col + u] > 0.f ? e[u] : 0.f;
-                    if (row_ok) vmax = fmaxf(vmax, fabsf(e[u]));
-                  }
-                }
-                o = make_float4(e[0], e[1], e[2], e[3]);
-              }
-              buf[lane * 8 + (j4 ^ (lane & 7))] = o;
-            }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            __syncwarp();
-            if (lane == 0 && !(p.pair_flags & 8)) { tma_store_3d(&tmC, smem_u32(buf), c0, m0 + 32 * q, z); tma_store_commit(); }
-          }
-        }
-      } else {
+      {
 #pragma unroll
       for (int ps = 0; ps < CPW / C::EPI_COLS; ++ps) {
         const int c0 = cw0 + ps * C::EPI_COLS;
@@ -1440,7 +1379,6 @@ gemm_tc_h3p_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
       if (dbg) t_epi += clock64() - c2;
     }
     if (dbg && lane == 0) { dbg[3] = clock64() - t_begin; dbg[4] = w_accfull; dbg[5] = t_drain; dbg[6] = t_epi; dbg[8] = clock64() - t_entry; }
-    if (pp.tma_store && lane == 0) tma_store_wait_all();      // shared memory must outlive the engine's reads
     if (p.c_amax && !pp.repair) {
       const uint32_t mx = __reduce_max_sync(0xffffffffu, __float_as_uint(vmax));
       if (lane == 0 && mx) atomicMax(p.c_amax + 1, mx);
@@ -1467,19 +1405,6 @@ static bool make_map_f16(CUtensorMap* map, const void* ptr, long long inner, lon
                         strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, box_inner == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS;
-}
-
-// 3-D fp32 tensor map of the output for TMA stores: {N columns, M rows, split-K slabs}, box 32 x 32 x 1, 128-byte swizzle
-// (the staging boxes are written with chunk ^ (row & 7)).  Needs a 16-byte aligned base, ldc and slab pitch multiples of 4.
-static bool make_map_c(CUtensorMap* map, float* ptr, long long N, long long M, long long ldc, long long slabs, long long slab_stride) {
-  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (ldc & 3) || (slab_stride & 3)) return false;
-  cuuint64_t dims[3] = {(cuuint64_t)N, (cuuint64_t)M, (cuuint64_t)(slabs < 1 ? 1 : slabs)};
-  cuuint64_t strides[2] = {(cuuint64_t)ldc * 4, (cuuint64_t)(slab_stride > 0 ? slab_stride : M * ldc) * 4};
-  cuuint32_t box[3] = {32u, 32u, 1u};
-  cuuint32_t estr[3] = {1u, 1u, 1u};
-  CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
 
@@ -1512,14 +1437,7 @@ template <int BN, bool SINGLE = false, bool PAIR = false>
 static int launch_h3p(cudaStream_t st, const CUtensorMap& tah, const CUtensorMap& tal, const CUtensorMap& tbh,
                       const CUtensorMap& tbl, ParamsP& pp, int M, int N, int split) {
   using C = CfgP<BN, SINGLE, PAIR>;
-  // the fp32 output leaves through TMA stores when its geometry allows (and nothing else rides on the epilogue)
-  CUtensorMap tc = tah;
-  pp.tma_store = 0; pp.repair = 0;
-  if (addk_switches().h3_tma_store && pp.p.C && !pp.p.accumulate && !pp.p.c_hi && !(SINGLE && pp.p.C16) && !pp.p.bits_out && !pp.p.bits_in && !pp.p.colpart &&
-      (!pp.p.bias || (reinterpret_cast<uintptr_t>(pp.p.bias) & 15) == 0) &&
-      (!pp.p.mask || ((pp.p.ld_mask & 3) == 0 && (reinterpret_cast<uintptr_t>(pp.p.mask) & 15) == 0)) &&
-      make_map_c(&tc, pp.p.C, N, M, pp.p.ldc, split, pp.p.slab_stride))
-    pp.tma_store = 1;
+  pp.repair = 0;
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(gemm_tc_h3p_kernel<BN, SINGLE, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES) != cudaSuccess) {
@@ -1537,7 +1455,7 @@ static int launch_h3p(cudaStream_t st, const CUtensorMap& tah, const CUtensorMap
     const int grid = pp.total_tiles < sm_count() ? pp.total_tiles : sm_count();
     for (int l = 0; l < launches; ++l) {
       pp.repair = l;
-      gemm_tc_h3p_kernel<BN, SINGLE, PAIR><<<grid, P_THREADS, C::SMEM_BYTES, st>>>(tah, tal, tbh, tbl, tc, pp);
+      gemm_tc_h3p_kernel<BN, SINGLE, PAIR><<<grid, P_THREADS, C::SMEM_BYTES, st>>>(tah, tal, tbh, tbl, pp);
     }
     return ADDK_OK;
   }
@@ -1554,7 +1472,7 @@ static int launch_h3p(cudaStream_t st, const CUtensorMap& tah, const CUtensorMap
   cfg.attrs = attr; cfg.numAttrs = 1;
   for (int l = 0; l < launches; ++l) {
     pp.repair = l;
-    if (cudaLaunchKernelEx(&cfg, gemm_tc_h3p_kernel<BN, SINGLE, PAIR>, tah, tal, tbh, tbl, tc, (const ParamsP)pp) != cudaSuccess) {
+    if (cudaLaunchKernelEx(&cfg, gemm_tc_h3p_kernel<BN, SINGLE, PAIR>, tah, tal, tbh, tbl, (const ParamsP)pp) != cudaSuccess) {
       addk_set_error("gemm_tc: cluster launch of the CTA-pair kernel failed");
       return ADDK_ERR_LAUNCH;
     }

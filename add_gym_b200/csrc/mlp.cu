@@ -894,6 +894,7 @@ static int h3_params(const addk_update_ctx& c, cudaStream_t st, int entry_point)
   if (cudaMemsetAsync(slot_ptr(c, TWIN_ENTRIES), 0, 2 * sizeof(uint32_t) * (TWIN_SLOTS - TWIN_ENTRIES), st) != cudaSuccess) {
     addk_set_error("f16x3: memset of the max|x| slots failed"); return ADDK_ERR_LAUNCH;
   }
+  if (c.params16_current) return ADDK_OK;      // (addk_params_refresh ran after the last parameter change)
   return addk_f16x3_convert(st, (const float*)c.params, 1, (int)c.num_params, (int)c.num_params, c.params16, c.num_params,
                             (uint32_t*)c.amax_slots);
 }
@@ -1159,8 +1160,10 @@ static int trunk_forward(cudaStream_t st, const Ctx& c, const ChainWs& ws, const
   const float* W0 = P + o_w0;
   int ldw = in_dim;
   if (w0_pad && !nmean && pr != 0 && X == F(c.xn) && OL > in_dim) {
-    pad_rows_kernel<<<(H1 * OL + 255) / 256, 256, 0, st>>>(P + o_w0, H1, in_dim, OL, w0_pad, twin16(w0_pad));
-    ADDK_CHECK_LAUNCH();
+    if (!c.params16_current) {
+      pad_rows_kernel<<<(H1 * OL + 255) / 256, 256, 0, st>>>(P + o_w0, H1, in_dim, OL, w0_pad, twin16(w0_pad));
+      ADDK_CHECK_LAUNCH();
+    }
     W0 = w0_pad; ldw = OL;
   }
   // (h1, h2 are read by dense layers and as ReLU masks only: 16-bit only in bf16 mode)
@@ -1250,6 +1253,7 @@ extern "C" int addk_update_minibatch(void* stream, void* ctx_host, const long lo
                                      int do_optim) {
   if (!ctx_host || !idx || step_index < 0) return ADDK_ERR_ARG;
   const Ctx& c = *(const Ctx*)ctx_host;
+  if (c.params16_current) { addk_set_error("update_minibatch: a context with params16_current = 1 is for inference only"); return ADDK_ERR_ARG; }
   cudaStream_t st = (cudaStream_t)stream;
   const int M = (int)c.mb_rows, R = M + 1, OD = (int)c.obs_dim, OL = (int)c.obs_ld, AD = (int)c.act_dim, AL = (int)c.act_ld;
   const int DD = (int)c.disc_dim, DL = (int)c.disc_ld, pr = (int)c.precision, S = (int)c.split_k;
@@ -1262,7 +1266,7 @@ extern "C" int addk_update_minibatch(void* stream, void* ctx_host, const long lo
   cudaMemsetAsync(stats, 0, ST_COUNT * sizeof(double), st);
   cudaMemsetAsync(cnt, 0, sizeof(int), st);
   g_twin_ctx = &c;
-  if (c.precision == 3 && c.params16) {
+  if (c.precision == 3 && c.params16 && !c.params16_current) {
     f32_to_bf16_flat_kernel<<<148 * 4, 256, 0, st>>>(F(c.params), (uint16_t*)c.params16, c.num_params);
     ADDK_CHECK_LAUNCH();
   }
@@ -1416,6 +1420,32 @@ extern "C" int addk_update_minibatch(void* stream, void* ctx_host, const long lo
   return ADDK_OK;
 }
 
+// The derived copies of the parameters the inference entry points read: the 16-bit twin of the flat vector (fp16 hi / lo
+// planes + max|x| word, or the bf16 copy) and the first-layer weights with padded rows.  Once per rollout / evaluation;
+// contexts built with params16_current = 1 then skip these launches on every call.
+extern "C" int addk_params_refresh(void* stream, void* ctx_host) {
+  if (!ctx_host) return ADDK_ERR_ARG;
+  const Ctx& c = *(const Ctx*)ctx_host;
+  cudaStream_t st = (cudaStream_t)stream;
+  const float* W = F(c.params);
+  g_twin_ctx = &c;
+  if (c.precision == 3 && c.params16) {
+    f32_to_bf16_flat_kernel<<<148 * 4, 256, 0, st>>>(F(c.params), (uint16_t*)c.params16, c.num_params);
+    ADDK_CHECK_LAUNCH();
+  }
+  if (c.precision == 4) {
+    if (!c.params16 || !c.amax_slots) { addk_set_error("f16x3: the context has no parameter twin / max|x| slots"); return ADDK_ERR_ARG; }
+    TRY(addk_f16x3_convert(st, W, 1, (int)c.num_params, (int)c.num_params, c.params16, c.num_params, (uint32_t*)c.amax_slots));
+  }
+  if (c.precision != 0) {
+    const int OD = (int)c.obs_dim, OL = (int)c.obs_ld, DD = (int)c.disc_dim, DL = (int)c.disc_ld, H1 = (int)c.hid_a1, E1 = (int)c.hid_d1;
+    if (OL > OD && c.wa0_pad) { pad_rows_kernel<<<(H1 * OL + 255) / 256, 256, 0, st>>>(W + c.o_a_w0, H1, OD, OL, F(c.wa0_pad), twin16(c.wa0_pad)); ADDK_CHECK_LAUNCH(); }
+    if (OL > OD && c.wc0_pad) { pad_rows_kernel<<<(H1 * OL + 255) / 256, 256, 0, st>>>(W + c.o_c_w0, H1, OD, OL, F(c.wc0_pad), twin16(c.wc0_pad)); ADDK_CHECK_LAUNCH(); }
+    if (c.wd0_pad) { pad_rows_kernel<<<(E1 * DL + 255) / 256, 256, 0, st>>>(W + c.o_d_w0, E1, DD, DL, F(c.wd0_pad), twin16(c.wd0_pad)); ADDK_CHECK_LAUNCH(); }
+  }
+  return ADDK_OK;
+}
+
 extern "C" int addk_actor_step(void* stream, void* ctx_host, const float* obs, const float* noise,
                                const float* exp_mask, int n, float* action, float* a_logp, float* obs_rec,
                                float* action_rec, float* logp_rec, float* mask_rec) {
@@ -1426,7 +1456,7 @@ extern "C" int addk_actor_step(void* stream, void* ctx_host, const float* obs, c
   const int OD = (int)c.obs_dim, AD = (int)c.act_dim, AL = (int)c.act_ld, H3 = (int)c.hid_a3;
   const float* W = F(c.params);
   g_twin_ctx = &c;
-  if (c.precision == 3 && c.params16) {
+  if (c.precision == 3 && c.params16 && !c.params16_current) {
     f32_to_bf16_flat_kernel<<<148 * 4, 256, 0, st>>>(F(c.params), (uint16_t*)c.params16, c.num_params);
     ADDK_CHECK_LAUNCH();
   }
@@ -1449,7 +1479,7 @@ extern "C" int addk_critic_eval(void* stream, void* ctx_host, const float* obs, 
   const long long chunk = c.mb_rows + 1;
   const float* W = F(c.params);
   g_twin_ctx = &c;
-  if (c.precision == 3 && c.params16) {
+  if (c.precision == 3 && c.params16 && !c.params16_current) {
     f32_to_bf16_flat_kernel<<<148 * 4, 256, 0, st>>>(F(c.params), (uint16_t*)c.params16, c.num_params);
     ADDK_CHECK_LAUNCH();
   }
@@ -1473,13 +1503,15 @@ extern "C" int addk_disc_eval(void* stream, void* ctx_host, const float* disc_ob
   const float* W = F(c.params);
   float *e1 = F(c.h1), *e2 = F(c.h3);
   g_twin_ctx = &c;
-  if (c.precision == 3 && c.params16) {
+  if (c.precision == 3 && c.params16 && !c.params16_current) {
     f32_to_bf16_flat_kernel<<<148 * 4, 256, 0, st>>>(F(c.params), (uint16_t*)c.params16, c.num_params);
     ADDK_CHECK_LAUNCH();
   }
   TRY(h3_params(c, st, 3));
-  pad_rows_kernel<<<(E1 * DL + 255) / 256, 256, 0, st>>>(W + c.o_d_w0, E1, DD, DL, F(c.wd0_pad), twin16(c.wd0_pad));
-  ADDK_CHECK_LAUNCH();
+  if (!c.params16_current) {
+    pad_rows_kernel<<<(E1 * DL + 255) / 256, 256, 0, st>>>(W + c.o_d_w0, E1, DD, DL, F(c.wd0_pad), twin16(c.wd0_pad));
+    ADDK_CHECK_LAUNCH();
+  }
   for (long long r0 = 0; r0 < n; r0 += chunk) {
     int rows = (int)((n - r0 < chunk) ? n - r0 : chunk);
     long long tot = (long long)rows * DL;

@@ -8,9 +8,6 @@ struct AddkSwitches {
   int h3_flags;           // ADDK_H3_FLAGS        f16x3 persistent kernel experiments: bit0 no stores, bit1 no drains   0
   int h3_persistent;      // ADDK_H3_PERSISTENT   persistent f16x3 kernel for 256-wide layers                    default 1
   int h3_pair;            // ADDK_H3_PAIR         cta_group::2 CTA pairs for the persistent f16x3 / bf16 kernel          default 1
-  int h3_tma_store;       // ADDK_H3_TMA_STORE    persistent kernel: fp32 output through TMA stores (measured SLOWER: the
-                          //                      lane-per-row register work costs 56k cycles per 4 tiles against 34k for the
-                          //                      staged coalesced stores, with or without the TMA issue)                default 0
   int h3_chunk_kb;        // ADDK_H3_CHUNK_KB     k-blocks per accumulator drain                                 default 8
   float h3_comp;          // ADDK_H3_COMP         expected accumulator truncation loss per MMA                   1.7e-8
   int bf16_persistent;    // ADDK_BF16_PERSISTENT persistent one-plane kernel in bf16 mode                       default 1

@@ -318,6 +318,13 @@ int addk_update_ctx_init(void* ctx_host, const void* const* ptrs, int n_ptrs, co
  * (experience_buffer.py:74-113; amp_agent.py:98-114; ppo_agent.py:194-275; add_agent.py:141-202;
  *  mp_optimizer.py:14-23).  idx: the int64 minibatch permutation slice. */
 int addk_update_minibatch(void* stream, void* ctx_host, const long long* idx, int step_index, int do_optim);
+/* The derived copies of the parameters that the inference entry points (addk_actor_step / addk_critic_eval /
+ * addk_disc_eval) otherwise rebuild on every call: the 16-bit twin of the flat parameter vector and the first-layer
+ * weights with padded rows.  The reference has no counterpart (its nn.Linear weights are read directly,
+ * learning/ppo_model.py:13-21); here 32 env steps of one rollout share one conversion: call this once after the
+ * last parameter change and pass a context whose params16_current field is 1 to those entry points. */
+int addk_params_refresh(void* stream, void* ctx_host);
+
 /* actor inference for one env step (ppo_agent.py:72-104) */
 int addk_actor_step(void* stream, void* ctx_host, const float* obs, const float* noise, const float* exp_mask,
                     int n, float* action, float* a_logp, float* obs_rec, float* action_rec, float* logp_rec,
