@@ -1534,6 +1534,15 @@ __global__ void h3_prep_kernel(uint32_t* slot, int keep) {
   slot[1] = 0u;
 }
 
+// The same for a whole table of slots in one launch (an entry point's slots, before its first layer): slots
+// [0, n_sticky) keep their history as above, slots [n_sticky, n_total) are cleared (the once-per-call slots).
+__global__ void h3_prep_all_kernel(uint32_t* slots, int n_sticky, int n_total) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_total) return;
+  slots[2 * i] = i < n_sticky ? h3_eff_word(slots[2 * i], slots[2 * i + 1]) : 0u;
+  slots[2 * i + 1] = 0u;
+}
+
 // colpart (optional, flat vectorised tensors whose float4 columns divide the block: cols / 4 in {256, 128, 64, 32}):
 // the pass also leaves per-block column sums of x in colpart[blockIdx.x, 0 .. cols) -- every thread only ever sees one
 // float4 column (the grid stride is a multiple of cols / 4), so the bias gradient 1^T dY costs no extra read of dY.
@@ -1742,6 +1751,12 @@ extern "C" int addk_f16x3_split(void* stream, const float* x, long long rows, in
 extern "C" int addk_f16x3_prep(void* stream, uint32_t* slot, int keep_sticky_word) {
   if (!slot) return ADDK_ERR_ARG;
   addk_tc::h3_prep_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(slot, keep_sticky_word);
+  ADDK_CHECK_LAUNCH();
+  return ADDK_OK;
+}
+extern "C" int addk_f16x3_prep_all(void* stream, uint32_t* slots, int n_sticky, int n_total) {
+  if (!slots || n_total <= 0 || n_sticky < 0 || n_sticky > n_total) return ADDK_ERR_ARG;
+  addk_tc::h3_prep_all_kernel<<<(n_total + 127) / 128, 128, 0, (cudaStream_t)stream>>>(slots, n_sticky, n_total);
   ADDK_CHECK_LAUNCH();
   return ADDK_OK;
 }

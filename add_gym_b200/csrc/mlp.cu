@@ -793,6 +793,7 @@ constexpr int BITS_ENTRIES = 16;
 static thread_local BitsEnt g_bits[BITS_ENTRIES];
 static thread_local int g_nbits = 0;
 static thread_local bool g_want_bits = false;      // set by addk_update_minibatch (inference entry points do not need masks)
+static thread_local bool g_prepped = false;        // the slots of this call were prepared in one launch (h3_params)
 static void twin_reset(int entry_point) { g_ntw = 0; g_slot_base = TWIN_SLOTS * entry_point; g_next_slot = TWIN_ENTRIES; g_nbits = 0; g_want_bits = false; }
 static uint32_t* slot_ptr(const addk_update_ctx& c, int slot) { return (uint32_t*)c.amax_slots + 2 * (1 + g_slot_base + slot); }
 static uint32_t* twin_slot(const addk_update_ctx& c, int e) { return slot_ptr(c, g_tw[e].slot); }
@@ -851,6 +852,7 @@ extern "C" int addk_f16x3_convert(void* stream, const float* x, long long rows, 
 extern "C" int addk_f16x3_split(void* stream, const float* x, long long rows, int cols, int ld, void* hi16, long long plane,
                                 uint32_t* amax_slot, float* colsum_partials, int* colsum_partial_rows);
 extern "C" int addk_f16x3_prep(void* stream, uint32_t* slot, int keep_sticky_word);
+extern "C" int addk_f16x3_prep_all(void* stream, uint32_t* slots, int n_sticky, int n_total);
 extern "C" int addk_f16x3_repair(void* stream, const float* x, long long rows, int cols, int ld, void* hi16, long long plane,
                                  uint32_t* slot);
 // convert now (used for tensors several streams read: must happen before the fork)
@@ -890,10 +892,13 @@ static int h3_params(const addk_update_ctx& c, cudaStream_t st, int entry_point)
   if (c.precision != 4) return ADDK_OK;
   twin_reset(entry_point);
   if (!c.params16 || !c.amax_slots) { addk_set_error("f16x3: the context has no parameter twin / max|x| slots"); return ADDK_ERR_ARG; }
-  // the once-per-call slots: a dense layer that leaves max|C| behind takes a fresh, already zeroed one (no launch per layer)
-  if (cudaMemsetAsync(slot_ptr(c, TWIN_ENTRIES), 0, 2 * sizeof(uint32_t) * (TWIN_SLOTS - TWIN_ENTRIES), st) != cudaSuccess) {
-    addk_set_error("f16x3: memset of the max|x| slots failed"); return ADDK_ERR_LAUNCH;
-  }
+  // every slot of this entry point in ONE launch: the per-tensor slots keep their sticky scale word (W <- the scale in
+  // force, max <- 0: what a single-thread launch in front of every planes-writing layer used to do, twelve per optimizer
+  // step on the chains' critical paths), the once-per-call slots are cleared (a dense layer that leaves max|C| behind takes
+  // a fresh one).  A slot written twice in one call (u1 of the discriminator chain) accumulates the larger max|x|: its
+  // scale then fits both, and the readers derive the scale from the two words as before.
+  { const int rcp = addk_f16x3_prep_all(st, slot_ptr(c, 0), TWIN_ENTRIES, TWIN_SLOTS); if (rcp != ADDK_OK) return rcp; }
+  g_prepped = true;
   if (c.params16_current) return ADDK_OK;      // (addk_params_refresh ran after the last parameter change)
   return addk_f16x3_convert(st, (const float*)c.params, 1, (int)c.num_params, (int)c.num_params, c.params16, c.num_params,
                             (uint32_t*)c.amax_slots);
@@ -990,7 +995,7 @@ static int gemm(cudaStream_t st, int prec, const float* A, int lda, int ta, cons
           if (!fused && g_next_slot < TWIN_SLOTS) { g_tw[e].slot = g_next_slot++; ready = true; }     // zeroed by h3_params
           else { g_tw[e].slot = e; }
           uint32_t* slot = twin_slot(c, e);
-          if (ready || addk_f16x3_prep(st, slot, fused ? 1 : 0) == ADDK_OK) {     // max <- 0, W <- scale in force | 0
+          if (ready || g_prepped || addk_f16x3_prep(st, slot, fused ? 1 : 0) == ADDK_OK) {     // max <- 0, W <- scale in force | 0
             TwinEnt& t = g_tw[e];
             t.rows = M; t.cols = N; t.ld = ldc; t.st = st; t.valid = false; t.shared = false; t.amax_known = true;
             a.c_amax = slot;

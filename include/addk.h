@@ -305,6 +305,10 @@ int addk_f16x3_split(void* stream, const float* x, long long rows, int cols, int
  * clears it (0: the scale then follows max|x| alone and results do not depend on earlier calls); addk_f16x3_repair,
  * after the layer, rewrites the planes if the sticky scale turned out not to fit max|C| */
 int addk_f16x3_prep(void* stream, uint32_t* slot, int keep_sticky_word);
+/* the same for a table of n_total consecutive slots in one launch: slots [0, n_sticky) keep their history (sticky
+ * word <- the scale in force, max word <- 0), the rest are cleared.  addk_update_minibatch and the inference entry
+ * points issue it once per call instead of one single-thread launch in front of every layer. */
+int addk_f16x3_prep_all(void* stream, uint32_t* slots, int n_sticky, int n_total);
 int addk_f16x3_repair(void* stream, const float* x, long long rows, int cols, int ld, void* hi16, long long plane,
                       uint32_t* slot);
 
