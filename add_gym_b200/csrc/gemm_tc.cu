@@ -1455,7 +1455,7 @@ static int launch_h3p(cudaStream_t st, const CUtensorMap& tah, const CUtensorMap
     const int grid = pp.total_tiles < sm_count() ? pp.total_tiles : sm_count();
     for (int l = 0; l < launches; ++l) {
       pp.repair = l;
-      gemm_tc_h3p_kernel<BN, SINGLE, PAIR><<<grid, P_THREADS, C::SMEM_BYTES, st>>>(tah, tal, tbh, tbl, pp);
+      gemm_tc_h3p_kernel<BN, SINGLE, PAIR><<<l ? 1 : grid, P_THREADS, C::SMEM_BYTES, st>>>(tah, tal, tbh, tbl, pp);
     }
     return ADDK_OK;
   }
@@ -1472,6 +1472,9 @@ static int launch_h3p(cudaStream_t st, const CUtensorMap& tah, const CUtensorMap
   cfg.attrs = attr; cfg.numAttrs = 1;
   for (int l = 0; l < launches; ++l) {
     pp.repair = l;
+    // the repair launch (exits at once unless the sticky scale missed max|C|): ONE CTA pair walks every tile -- the rare
+    // repair takes milliseconds instead of ~90 us, the common early exit does not have to place 148 CTAs
+    if (l) cfg.gridDim = dim3(2, 1, 1);
     if (cudaLaunchKernelEx(&cfg, gemm_tc_h3p_kernel<BN, SINGLE, PAIR>, tah, tal, tbh, tbl, (const ParamsP)pp) != cudaSuccess) {
       addk_set_error("gemm_tc: cluster launch of the CTA-pair kernel failed");
       return ADDK_ERR_LAUNCH;
