@@ -1,6 +1,7 @@
 // AdamW on one element, in torch's single-tensor op order (shared by the flat AdamW kernels and the fused exchange kernel).
 #pragma once
 #include "common.cuh"
+#include <math.h>
 namespace addk {
 // torch.optim.AdamW, amsgrad=False, maximize=False (torch/optim/adamw.py -> adam.py _single_tensor_adam)
 struct AdamK { float lr_wd_factor, one_minus_b1, b2, one_minus_b2, step_size, bc2_sqrt, eps, grad_scale; };
@@ -12,5 +13,12 @@ __device__ __forceinline__ void adam1(const AdamK& k, float& p, float g, float& 
   const float denom = add_rn(sqrtf(vi) / k.bc2_sqrt, k.eps);
   p = add_rn(w, mul_rn(-k.step_size, mi / denom));                               // addcdiv_(exp_avg, denom, -step_size)
   m = mi; v = vi;
+}
+// scalar prep in double exactly as torch does it on the host, then rounded once to fp32
+inline AdamK adamk_host(int step, double lr, double beta1, double beta2, double eps, double weight_decay, double grad_scale) {
+  const double bc1 = 1.0 - pow(beta1, (double)step);
+  const double bc2 = 1.0 - pow(beta2, (double)step);
+  return AdamK{(float)(1.0 - lr * weight_decay), (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2), (float)(lr / bc1),
+               (float)sqrt(bc2), (float)eps, (float)grad_scale};
 }
 }  // namespace addk

@@ -42,6 +42,7 @@ const AddkSwitches& addk_switches() {
     s.h3_colpart = env_int("ADDK_H3_COLPART", 1);
     s.h3_relu_bits = env_int("ADDK_H3_RELU_BITS", 1);
     s.step_cta_tail = env_int("ADDK_STEP_CTA_TAIL", 1);
+    s.fused_tail = env_int("ADDK_FUSED_TAIL", 1);
     s.step_min_blocks = env_int("ADDK_STEP_MIN_BLOCKS", 0);
     return s;
   }();

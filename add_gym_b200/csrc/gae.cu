@@ -280,13 +280,7 @@ extern "C" int addk_adamw(void* stream, float* param, const float* grad, float* 
                           long long n, int step, double lr, double beta1, double beta2, double eps,
                           double weight_decay, double grad_scale) {
   if (!param || !grad || !exp_avg || !exp_avg_sq || n <= 0 || step < 1) return ADDK_ERR_ARG;
-  // scalar prep in double exactly as torch does it on the host, then rounded once to fp32
-  double bc1 = 1.0 - pow(beta1, (double)step);
-  double bc2 = 1.0 - pow(beta2, (double)step);
-  float step_size = (float)(lr / bc1);
-  float bc2_sqrt = (float)sqrt(bc2);
-  float lr_wd = (float)(1.0 - lr * weight_decay);
-  const AdamK k = {lr_wd, (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2), step_size, bc2_sqrt, (float)eps, (float)grad_scale};
+  const AdamK k = adamk_host(step, lr, beta1, beta2, eps, weight_decay, grad_scale);
   const bool aligned = ((reinterpret_cast<uintptr_t>(param) | reinterpret_cast<uintptr_t>(grad) | reinterpret_cast<uintptr_t>(exp_avg) |
                          reinterpret_cast<uintptr_t>(exp_avg_sq)) & 15) == 0;
   if (aligned)

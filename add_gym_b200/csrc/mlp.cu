@@ -24,6 +24,7 @@
 #include <stdlib.h>
 #include "switches.h"
 #include "h3_scale.cuh"
+#include "adam.cuh"
 #include <cuda_fp16.h>
 
 struct addk_update_ctx {
@@ -618,10 +619,13 @@ __global__ void reduce_slabs_kernel(const __grid_constant__ SegTable t, const fl
   grads[i] = g;
 }
 
-__global__ void finalize_info_kernel(const double* __restrict__ st, const int* __restrict__ cnt, int M, float bound_w,
-                                     float critic_w, float disc_w, float logit_reg, float gp, float wd,
-                                     float* __restrict__ info) {
-  double n = (double)max(*cnt, 1);
+struct InfoArgs { const double* st; const int* cnt; int M; float bound_w, critic_w, disc_w, logit_reg, gp, wd; float* info; };
+__device__ __forceinline__ void finalize_info(const InfoArgs& a) {
+  const double* st = a.st;
+  const int M = a.M;
+  const float bound_w = a.bound_w, critic_w = a.critic_w, disc_w = a.disc_w, logit_reg = a.logit_reg, gp = a.gp, wd = a.wd;
+  float* info = a.info;
+  double n = (double)max(*a.cnt, 1);
   double surr = st[ST_SURR] / n, bound = st[ST_BOUND] / n;
   double actor = -surr + (bound_w != 0.f ? bound_w * bound : 0.0);
   double critic = st[ST_CRITIC] / M;
@@ -642,6 +646,39 @@ __global__ void finalize_info_kernel(const double* __restrict__ st, const int* _
   info[12] = (float)(st[ST_NEG_LOGIT] / M);
   info[13] = (float)n;
   info[14] = 0.f; info[15] = 0.f;
+}
+__global__ void finalize_info_kernel(const InfoArgs a) { finalize_info(a); }
+
+// The tail of an optimizer step as ONE launch (single GPU, no gradient clipping): slab reduction + AdamW + the
+// diagnostics row.  Same arithmetic, element by element, as reduce_slabs_kernel -> adamw_vec4_kernel (adam1) and
+// finalize_info_kernel; the summed gradient is still written (diagnostics / tests read it).  As three launches behind
+// the join of the chains the tail ran alone on the GPU for ~80 us of a 1.7 ms step; fused it reads the slabs once and
+// never re-reads the gradient vector.
+__global__ void __launch_bounds__(256) reduce_slabs_adamw_kernel(const __grid_constant__ SegTable t, const float* __restrict__ slabs,
+                                                                  float* __restrict__ params, float* __restrict__ grads,
+                                                                  float* __restrict__ m, float* __restrict__ v, const AdamK k,
+                                                                  const InfoArgs ia) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) finalize_info(ia);
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= t.P) return;
+  int ns = 0; float l2 = 0.f;
+  for (int q = 0; q < t.n; ++q) if (i >= t.s[q].begin && i < t.s[q].end) { ns = t.s[q].nslabs; l2 = t.s[q].l2; break; }
+  float pi = params[i], mi = m[i], vi = v[i];
+  const float* sp = slabs + i;
+  float x[8];
+  float g = 0.f;
+  int s = 0;
+  for (; s + 8 <= ns; s += 8) {           // eight slab loads in flight, added in slab order
+#pragma unroll
+    for (int u = 0; u < 8; ++u) x[u] = __ldcs(sp + (size_t)(s + u) * t.P);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) g += x[u];
+  }
+  for (; s < ns; ++s) g += __ldcs(sp + (size_t)s * t.P);
+  if (l2 != 0.f) g += l2 * pi;
+  grads[i] = g;
+  adam1(k, pi, g, mi, vi);
+  params[i] = pi; m[i] = mi; v[i] = vi;
 }
 
 // DistributionGaussianDiag.sample/log_prob + rand_action_mask select + Normalizer.unnormalize: warp per env
@@ -1339,6 +1376,11 @@ extern "C" int addk_update_minibatch(void* stream, void* ctx_host, const long lo
   const float* Wd0 = F(c.wd0_pad);
   pad_rows_kernel<<<(E1 * DL + 255) / 256, 256, 0, sd>>>(W + c.o_d_w0, E1, DD, DL, F(c.wd0_pad), twin16(c.wd0_pad));
   ADDK_CHECK_LAUNCH();
+  // regularisers (values for the log; their gradients are folded into the slab reduction): they depend on the weights
+  // only, so they run here, next to the other chains, and not behind the join
+  disc_weight_sumsq_kernel<<<dim3(64, 3), 256, 0, sd>>>(W + c.o_d_wl, E2, W + c.o_d_w0, (long long)E1 * DD, W + c.o_d_w1,
+                                                        (long long)E2 * E1, stats);
+  ADDK_CHECK_LAUNCH();
   TRY(gemm(sd, pr, F(c.dn), DL, 0, Wd0, DL, 1, e1, E1, R, E1, DL, W + c.o_d_b0, 1, nullptr, 0, 1, nullptr, nullptr, 0, F16_DROP_C));
   TRY(gemm(sd, pr, e1, E1, 0, W + c.o_d_w1, E1, 1, e2, E2, R, E2, E1, W + c.o_d_b1, 1));
   TRY(head1_forward(sd, e2, E2, R, E2, W + c.o_d_wl, W + c.o_d_bl, pred_d));
@@ -1390,10 +1432,6 @@ extern "C" int addk_update_minibatch(void* stream, void* ctx_host, const long lo
     cudaStreamWaitEvent(st, aux->join[0], 0);
     cudaStreamWaitEvent(st, aux->join[1], 0);
   }
-  // regularisers (values for the log; their gradients are folded into the slab reduction)
-  disc_weight_sumsq_kernel<<<dim3(64, 3), 256, 0, st>>>(W + c.o_d_wl, E2, W + c.o_d_w0, (long long)E1 * DD, W + c.o_d_w1,
-                                                        (long long)E2 * E1, stats);
-  ADDK_CHECK_LAUNCH();
 
   // ---------------- reduce slabs -> grads, AdamW, diagnostics ----------------
   SegTable t;
@@ -1410,11 +1448,18 @@ extern "C" int addk_update_minibatch(void* stream, void* ctx_host, const long lo
     if (offs[k] == c.o_d_w0 || offs[k] == c.o_d_w1) { s.nslabs = 2 * S; s.l2 = dlw * 2.0f * (float)c.disc_weight_decay; }
     if (offs[k] == c.o_d_wl) { s.nslabs = 2 * S; s.l2 = dlw * 2.0f * (float)(c.disc_weight_decay + c.disc_logit_reg); }
   }
+  const InfoArgs ia{stats, cnt, M, (float)c.action_bound_weight, (float)c.critic_loss_weight, dlw, (float)c.disc_logit_reg,
+                    (float)c.disc_grad_penalty, (float)c.disc_weight_decay, F(c.info) + (size_t)step_index * 16};
+  if (do_optim && !(c.grad_clip > 0.0) && addk_switches().fused_tail) {
+    reduce_slabs_adamw_kernel<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(
+        t, F(c.slabs), F(c.params), F(c.grads), F(c.exp_avg), F(c.exp_avg_sq),
+        adamk_host(do_optim, c.lr, c.beta1, c.beta2, c.adam_eps, c.weight_decay, c.grad_scale), ia);
+    ADDK_CHECK_LAUNCH();
+    return ADDK_OK;
+  }
   reduce_slabs_kernel<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(t, F(c.slabs), W, F(c.grads));
   ADDK_CHECK_LAUNCH();
-  finalize_info_kernel<<<1, 1, 0, st>>>(stats, cnt, M, (float)c.action_bound_weight, (float)c.critic_loss_weight, dlw,
-                                        (float)c.disc_logit_reg, (float)c.disc_grad_penalty,
-                                        (float)c.disc_weight_decay, F(c.info) + (size_t)step_index * 16);
+  finalize_info_kernel<<<1, 1, 0, st>>>(ia);
   ADDK_CHECK_LAUNCH();
   if (do_optim) {
     if (c.grad_clip > 0.0)      // the coefficient lands in info[14] of this step (0 = clipping off)

@@ -18,6 +18,7 @@ struct AddkSwitches {
   int h3_colpart;         // ADDK_H3_COLPART      split pass leaves bias-gradient column sums behind             default 1
   int h3_relu_bits;       // ADDK_H3_RELU_BITS    optimizer step: ReLU masks travel as bit planes (arena_bits)  default 1
   int step_cta_tail;      // ADDK_STEP_CTA_TAIL   reward / done tail of the step kernel run per CTA              default 1
+  int fused_tail;         // ADDK_FUSED_TAIL      optimizer step: slab reduction + AdamW + diagnostics row in one launch      default 1
   int step_min_blocks;    // ADDK_STEP_MIN_BLOCKS occupancy experiment of the step kernel (0 | 5 | 6)            default 0
 };
 const AddkSwitches& addk_switches();
