@@ -137,9 +137,13 @@ def test_motion_table_matches_oracle_and_golden(motion):
     got = torch.cat([tab[:, :7 + D], tab[:, h:h + 6 + D]], dim=1)
     # ---- stage A (hinge angle -> joint quaternion, 30 fps): smooth, so elementwise: a few ulp of 1.0
     ocpu = harness.make_oracle_lib(cfg)
-    for jd, jo in zip(_device_joint_rot(lib), ocpu.frame_joint_rot):
+    for m, (jd, jo) in enumerate(zip(_device_joint_rot(lib), ocpu.frame_joint_rot)):
         assert jd.shape == jo.shape
-        assert float((jd - jo).abs().max()) <= 3e-7
+        diff = (jd - jo).abs()
+        bad = ~(diff <= 3e-7)                       # (NaN counts as a mismatch)
+        assert not bool(bad.any()), "clip %d: %d of %d stage-A entries off (max %.3e, NaNs %d, first at %s)" % (
+            m, int(bad.sum()), bad.numel(), float(diff[~torch.isnan(diff)].max()), int(torch.isnan(jd).sum()),
+            tuple(int(x) for x in bad.nonzero()[0]))
     # ---- stage B (100 Hz resampling: lerp / slerp / twist angle / frame velocities) on identical stage-A input
     olib = harness.make_oracle_lib(cfg, jrot_override=_device_joint_rot(lib))
     assert got.shape == olib.table.shape
