@@ -6,6 +6,7 @@ permutations; norm-wise relative error <= 1e-5 (fp32 MLPs) on observations, rewa
 the gradients.  Tolerances are spelled out at each assert.
 """
 import ctypes as C
+import math
 import os
 
 import numpy as np
@@ -617,6 +618,57 @@ def test_checkpoint_roundtrip_and_reference_key_names(tmp_path):
     b = ADDAgent(cfg, device="cuda:0")
     b.load(p)
     assert torch.equal(a._model.flat, b._model.flat)
+
+
+def test_loads_a_checkpoint_written_by_the_reference(tmp_path):
+    """f4: a checkpoint written by the executed reference's own `save()` (tests/golden/make_ref_checkpoint.py: real
+    ADDAgent, one iteration, per-tensor patterns in the weights and the AdamW state) loads into the drop-in agent --
+    every trainable tensor lands at its offset of the flat vector, the AdamW moments and step count follow, normalizer
+    statistics and counters are restored -- and training continues from optimizer step 41."""
+    import sys
+    import zipfile
+    from add_gym_b200.add_agent import ADDAgent
+    golden = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    sys.path.insert(0, golden)
+    from make_ref_checkpoint import pattern
+    with zipfile.ZipFile(os.path.join(golden, "ref_checkpoint.zip")) as z:
+        z.extract("model.pt", str(tmp_path))
+    path = str(tmp_path / "model.pt")
+    ck = torch.load(path, map_location="cpu")
+    cfg = b200_config.default_config(num_envs=4)
+    cfg["engine"].update(seed=1234, noise_device="device", fall_prob=0.01)
+    a = ADDAgent(cfg, device="cuda:0")
+    a.load(path)
+    assert a._iter == 7 and a._sample_count == 7 * 128 and a._is_restored
+    names, tensors = a._model.trainable()
+    opt = a._optimizer
+    assert opt.steps == 40 and opt.lr == 1e-4 and tuple(opt.betas) == (0.9, 0.999)
+    for i, (n, t) in enumerate(zip(names, tensors)):
+        o = a._model.offsets["o_" + n]
+        assert torch.equal(a._model.flat[o:o + t.numel()].cpu(), pattern(t.numel(), 0, i)), n
+        assert torch.equal(t.detach().flatten().cpu(), pattern(t.numel(), 0, i)), n          # the module view is the flat vector
+        assert torch.equal(opt.exp_avg[o:o + t.numel()].cpu(), pattern(t.numel(), 1, i)), n
+        assert torch.equal(opt.exp_avg_sq[o:o + t.numel()].cpu(), pattern(t.numel(), 2, i)), n
+    sd = a.state_dict()
+    for k in ("_obs_norm._count", "_obs_norm._mean", "_obs_norm._std", "_a_norm._mean", "_a_norm._std",
+              "_disc_obs_norm._count", "_disc_obs_norm._mean_abs", "_model._action_dist._logstd_net"):
+        assert torch.equal(sd[k].cpu(), ck["model"][k]), k
+    # the same file through the reference's DDP key prefix (base_agent.py:169-186)
+    ck2 = dict(ck)
+    ck2["model"] = {k.replace("_model.", "_model.module.", 1): v for k, v in ck["model"].items()}
+    path2 = str(tmp_path / "model_ddp.pt")
+    torch.save(ck2, path2)
+    b = ADDAgent(cfg, device="cuda:0")
+    b.load(path2)
+    assert torch.equal(a._model.flat, b._model.flat)
+    # training continues: one iteration = 40 optimizer steps on top of the restored count, everything finite
+    a._curr_obs, a._curr_info = a._reset_envs()
+    a._exp_buffer.clear()
+    a._reset_tracker()
+    info = a._train_iter()
+    assert a._optimizer.steps == 80
+    assert all(math.isfinite(float(v)) for v in info.values())
+    assert bool(torch.isfinite(a._model.flat).all()) and not torch.equal(a._model.flat, b._model.flat)
 
 
 def test_cuda_graph_rollout_is_bit_identical_to_eager():

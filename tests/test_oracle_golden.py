@@ -114,3 +114,35 @@ def test_oracle_calc_motion_frame_reproduces_reference():
     out = lib.calc_motion_frame(torch.from_numpy(g["ids"]), torch.from_numpy(g["times"]))
     for k, v in zip(("root_pos", "root_rot", "root_vel", "root_ang_vel", "joint_rot", "dof_pos", "dof_vel"), out):
         np.testing.assert_array_equal(v.numpy(), g[k], err_msg=k)
+
+
+def _ref_checkpoint():
+    """tests/golden/ref_checkpoint.zip: written by the executed reference's own save() (make_ref_checkpoint.py)"""
+    import io
+    import zipfile
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    with zipfile.ZipFile(os.path.join(here, "ref_checkpoint.zip")) as z:
+        return torch.load(io.BytesIO(z.read("model.pt")), map_location="cpu")
+
+
+def test_reference_checkpoint_fixture_has_the_layout_the_loader_expects():
+    """The checkpoint the reference wrote (base_agent.py:148-155): dict layout, state-dict key names, one optimizer state
+    entry per trainable tensor in `named_parameters()` order, the per-tensor patterns of make_ref_checkpoint.py."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    from make_ref_checkpoint import pattern
+    ck = _ref_checkpoint()
+    assert set(ck.keys()) == {"model", "optimizer", "iter", "sample_count"}
+    assert ck["iter"] == 7 and ck["sample_count"] == 7 * 128
+    trainable = [k for k in ck["model"] if k.startswith("_model.") and not k.endswith("_logstd_net")]
+    assert len(trainable) == 22 and len(ck["optimizer"]["state"]) == 22
+    assert trainable[0] == "_model._actor_layers.0.weight" and trainable[-1] == "_model._disc_logits.bias"
+    for i, k in enumerate(trainable):
+        p, st = ck["model"][k], ck["optimizer"]["state"][i]
+        assert st["exp_avg"].shape == p.shape and float(st["step"]) == 40.0
+        assert torch.equal(p.flatten(), pattern(p.numel(), 0, i)), k
+        assert torch.equal(st["exp_avg"].flatten(), pattern(p.numel(), 1, i)), k
+        assert torch.equal(st["exp_avg_sq"].flatten(), pattern(p.numel(), 2, i)), k
+    g = ck["optimizer"]["param_groups"][0]
+    assert g["lr"] == 1e-4 and tuple(g["betas"]) == (0.9, 0.999) and g["weight_decay"] == 0.0
+    assert int(ck["model"]["_obs_norm._count"]) == 128        # one iteration of 4 envs x 32 steps went into the normalizers
