@@ -124,7 +124,7 @@ def _check_buffers(agent, ref, keys_float=FLOAT_KEYS, keys_exact=EXACT_KEYS, tol
 # ---------------------------------------------------------------------------------------------------------
 # motion table + gather
 # ---------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("motion", [None, THREE_CLIPS, SEVEN_CLIPS])
+@pytest.mark.parametrize("motion", [None, THREE_CLIPS, SEVEN_CLIPS, ALL_CLIPS])
 def test_motion_table_matches_oracle_and_golden(motion):
     from add_gym_b200.env import ImitationEnvironment
     from add_gym_b200.add_motion import ADDMotion
@@ -155,6 +155,9 @@ def test_motion_table_matches_oracle_and_golden(motion):
     assert float((got - olib.table).abs().max()) <= 2e-5          # rad, m, rad/s, m/s
     # ---- against the executed reference's table (golden, torch-CPU cos/sin): the reference's own branch
     # discontinuities make a small set of entries libm-dependent; everything else must agree to 1e-5.
+    if motion == ALL_CLIPS:      # BASELINE configs[2]: all 42 clips, 906,203 rows (261 MB in HBM); no golden table of that size
+        assert len(olib.lengths) == 42 and got.shape[0] == 906203
+        return
     case = {None: "walk_n12", THREE_CLIPS: "three_clips_n10", SEVEN_CLIPS: "seven_clips_n14"}[motion]
     g = np.load(os.path.join(GOLD, case + ".npz"))
     assert list(g["table_shape"]) == list(got.shape)
@@ -451,6 +454,13 @@ def test_iteration_parity_walk_n12_and_golden():
 def test_iteration_parity_three_clips_golden():
     """Multi-clip library with the Q2 start-index quirk, WRAP and CLAMP clips, SUCC terminations."""
     _iteration_parity(10, THREE_CLIPS, gold_case="three_clips_n10", steps_synced=8)
+
+
+def test_iteration_parity_full_library_42_clips():
+    """BASELINE configs[2]: the whole assets/motions library (42 clips, 261 MB step table -- not L2-resident), clip ids up
+    to 41 through the Q2 start-index quirk, the global row clamp at the end of the table and CLAMP clips that end inside
+    the rollout: one full iteration against the oracle on the same library."""
+    _iteration_parity(24, ALL_CLIPS, steps_synced=8)
 
 
 def test_iteration_parity_config0_n64():
