@@ -27,7 +27,6 @@ const AddkSwitches& addk_switches() {
     AddkSwitches s;
     s.tc_pair = env_int("ADDK_TC_PAIR", 1);
     s.tc_pair_flags = env_int("ADDK_TC_PAIR_FLAGS", 2);
-    s.h3_flags = env_int("ADDK_H3_FLAGS", 0);
     s.h3_persistent = env_int("ADDK_H3_PERSISTENT", 1);
     s.h3_pair = env_int("ADDK_H3_PAIR", 1);
     s.h3_chunk_kb = env_int("ADDK_H3_CHUNK_KB", 8);
@@ -41,9 +40,7 @@ const AddkSwitches& addk_switches() {
     s.h3_fused_planes = env_int("ADDK_H3_FUSED_PLANES", 0);
     s.h3_colpart = env_int("ADDK_H3_COLPART", 1);
     s.h3_relu_bits = env_int("ADDK_H3_RELU_BITS", 1);
-    s.step_cta_tail = env_int("ADDK_STEP_CTA_TAIL", 1);
     s.fused_tail = env_int("ADDK_FUSED_TAIL", 1);
-    s.step_min_blocks = env_int("ADDK_STEP_MIN_BLOCKS", 0);
     return s;
   }();
   return sw;

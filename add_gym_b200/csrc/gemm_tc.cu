@@ -37,7 +37,6 @@ namespace addk_tc {
 static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
 
 constexpr int BM = 128;        // UMMA M
-constexpr int UMMA_K = 8;      // kind::tf32
 constexpr int NTHREADS = 192;
 
 struct Params {
@@ -467,7 +466,6 @@ static bool resolve_encode() {
 
 // tf32x3 drains share these with the f16x3 kernels
 constexpr int X3_THREADS = 320;
-constexpr float X3_TRUNC_LOSS_PER_MMA = 1.7e-8f;
 
 // ---------------------------------------------------------------------------------------------------------------
 // bf16 kernel (precision "bf16", BASELINE config 4): bf16 operands in HBM (the producers write a bf16 twin of every
@@ -987,7 +985,6 @@ struct CfgP {
   static constexpr uint32_t K_SBO = 8u * BK * 2u;
   static constexpr uint32_t MN_BOX_BYTES = BK * 128u;
 };
-constexpr int H3P_CHUNK_KB = 8;                                     // 256 k = 48 instructions per drain (measured: rel 5e-7)
 
 // ---- cluster / cta_group::2 helpers ---------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
@@ -1276,7 +1273,6 @@ gemm_tc_h3p_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
         tc_fence_after();
 #pragma unroll
         for (int cc = 0; cc < NCH; ++cc) {
-          if (p.pair_flags & 2) break;             // experiment: no drain
           uint32_t v[32];
           tmem_ld32(t_lane + b * BN + (uint32_t)(cc * 32), v);
 #pragma unroll
@@ -1304,10 +1300,10 @@ gemm_tc_h3p_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
 #pragma unroll
       for (int ps = 0; ps < CPW / C::EPI_COLS; ++ps) {
         const int c0 = cw0 + ps * C::EPI_COLS;
-        // warp-uniform (flag: experiment without the stores).  A warp whose 32 rows all lie beyond M has nothing to store:
+        // warp-uniform.  A warp whose 32 rows all lie beyond M has nothing to store:
         // with M = 16385 (the discriminator chain) the guarded edge path below ran for all 16 warps of the last row tile
         // and made every such layer ~20 us longer than its 16384-row twin.
-        if (c0 < p.N && m0 + 32 * q < p.M && !(p.pair_flags & 1)) {
+        if (c0 < p.N && m0 + 32 * q < p.M) {
           if (vec) {
             if (CPW == 128 && p.bits_in) {      // the ReLU mask, applied where a lane still owns its row
               static_assert(C::EPI_COLS == 64, "the bit-plane layout is defined per 64-column staging pass");
@@ -1374,7 +1370,7 @@ gemm_tc_h3p_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
         }
       }
       }
-      if (CPW == 128 && p.bits_out && row < p.M && cw0 < p.N && !(p.pair_flags & 1))
+      if (CPW == 128 && p.bits_out && row < p.M && cw0 < p.N)
         *reinterpret_cast<uint4*>(p.bits_out + (size_t)row * p.ld_bits + (cw0 >> 5)) = obits;
       if (dbg) t_epi += clock64() - c2;
     }
@@ -1803,7 +1799,7 @@ static int gemm_h3(cudaStream_t st, const addk_gemm_args& a) {
   p.C = a.C; p.ldc = a.ldc; p.M = a.M; p.N = a.N; p.K = a.K; p.bias = a.bias; p.mask = a.relu_mask_src;
   p.ld_mask = a.ld_mask; p.relu = a.relu; p.accumulate = a.accumulate; p.kb_per_split = kb_per;
   p.slab_stride = a.slab_stride > 0 ? a.slab_stride : (long long)a.M * a.ldc;
-  p.pair_flags = addk_switches().h3_flags;
+  p.pair_flags = 0;
   p.dbg = g_addk_stamps; p.C16 = nullptr; p.c_amax = split == 1 ? a.c_amax : nullptr;
   p.c_hi = nullptr; p.c_plane = 0; p.c_scale = 1.f; p.c16_in_staged = 0; p.no_f32 = 0; p.mask16 = nullptr;
   p.a_mn = a.trans_a ? 1 : 0;

@@ -2,6 +2,8 @@
 // (precision "tf32"), the in-kernel hi/lo split tf32x3 kernels (1-CTA and cta_group::2 pair, precision "tf32x3").
 // The default library runs f16x3 / bf16 on the kernels of gemm_tc.cu and falls back to the exact-fp32 CUDA-core kernel.
 // Included from gemm_tc.cu inside namespace addk_tc.
+constexpr int UMMA_K = 8;      // kind::tf32
+constexpr float X3_TRUNC_LOSS_PER_MMA = 1.7e-8f;      // measured: the tf32 accumulator truncates toward zero after every instruction
 
 // One stage of the ring.  A: 128 (rows | columns) x BK k;  B: BN x BK k.  tf32x3 adds the "lo" halves and uses
 // BK = 16 (64-byte rows) so that four stages still fit; the single-pass mode uses BK = 32 (128-byte rows).

@@ -708,13 +708,11 @@ __device__ __forceinline__ void env_step_fast_tail(const StepParams& p, const in
   }
 }
 
-// CTA_TAIL = false: lane 0 of every warp runs the scalar end for its own env (273 warp-instructions of one-lane work per
-// env: a quarter of the kernel's issue slots, ncu r01_step_fast).  CTA_TAIL = true: the warps leave their reduced terms
-// in shared memory and lanes 0..7 of warp 0 run the scalar end for the block's eight envs at once.
-// MIN_BLOCKS caps the registers for that many resident blocks per SM (0, the default: no cap, 64; 5: 48 registers, 40 B of spills; 6: 40
-// registers, 128 B) -- candidates for the occupancy experiment (ncu: 4 blocks = 46 % of the warp slots); not the default.
-template <bool CTA_TAIL, int MIN_BLOCKS>
-__global__ void __launch_bounds__(WPB * 32, MIN_BLOCKS) env_step_fast_kernel(const __grid_constant__ StepParams p) {
+// The warps leave their reduced reward terms in shared memory and lanes 0..WPB-1 of warp 0 run the scalar end for the
+// block's envs at once (lane 0 of every warp running it for its own env was 273 warp-instructions of one-lane work per
+// env: a quarter of the kernel's issue slots, ncu r01_step_fast).  Register caps for more resident blocks (48 / 40
+// registers: 40 / 128 B of spills) measured slower and are gone (profiles/r01_SUMMARY.md).
+__global__ void __launch_bounds__(WPB * 32) env_step_fast_kernel(const __grid_constant__ StepParams p) {
   using namespace fast;
   extern __shared__ __align__(16) float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -724,20 +722,14 @@ __global__ void __launch_bounds__(WPB * 32, MIN_BLOCKS) env_step_fast_kernel(con
   __shared__ __align__(8) unsigned long long s_bar[WPB];      // one single-use mbarrier per warp (bulk-copy staging)
   const uint32_t bar = smem_addr(&s_bar[warp]);
   FastTail o;
-  if (!CTA_TAIL) {
-    if (!active) return;
-    env_step_fast_main(p, sw, bar, lane, e, o);
-    if ((p.flags & F_REWARD_DONE) && lane == 0) env_step_fast_tail(p, e, sw, o);
-  } else {
-    __shared__ FastTail s_tail[WPB];
-    __shared__ int s_active[WPB];
-    if (active) env_step_fast_main(p, sw, bar, lane, e, o);
-    if (!(p.flags & F_REWARD_DONE)) return;                 // uniform over the grid
-    if (lane == 0) { s_active[warp] = active ? 1 : 0; if (active) s_tail[warp] = o; }
-    __syncthreads();
-    if (warp == 0 && lane < WPB && s_active[lane])
-      env_step_fast_tail(p, blockIdx.x * WPB + lane, smem + (size_t)lane * PER_WARP, s_tail[lane]);
-  }
+  __shared__ FastTail s_tail[WPB];
+  __shared__ int s_active[WPB];
+  if (active) env_step_fast_main(p, sw, bar, lane, e, o);
+  if (!(p.flags & F_REWARD_DONE)) return;                 // uniform over the grid
+  if (lane == 0) { s_active[warp] = active ? 1 : 0; if (active) s_tail[warp] = o; }
+  __syncthreads();
+  if (warp == 0 && lane < WPB && s_active[lane])
+    env_step_fast_tail(p, blockIdx.x * WPB + lane, smem + (size_t)lane * PER_WARP, s_tail[lane]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -982,19 +974,7 @@ extern "C" int addk_env_step(void* stream, const addk_task* task, const addk_mot
   }
   if (fast && env->hist_stride == 72) {
     const int fsm = fast::PER_WARP * WPB * (int)sizeof(float);
-    const int cta_tail = addk_switches().step_cta_tail;       // ADDK_STEP_CTA_TAIL=0: A/B switch (per-warp scalar end)
-    const int min_blocks = addk_switches().step_min_blocks;   // ADDK_STEP_MIN_BLOCKS=5|6: occupancy experiment (CTA-level end only)
-    static bool carveout_set = false;
-    if (!carveout_set) {
-      carveout_set = true;
-      if (min_blocks == 5) cudaFuncSetAttribute(env_step_fast_kernel<true, 5>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-      if (min_blocks == 6) cudaFuncSetAttribute(env_step_fast_kernel<true, 6>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    }
-    const dim3 fgrid((num_envs + WPB - 1) / WPB), fblock(WPB * 32);
-    if (!cta_tail) env_step_fast_kernel<false, 0><<<fgrid, fblock, fsm, (cudaStream_t)stream>>>(p);
-    else if (min_blocks == 5) env_step_fast_kernel<true, 5><<<fgrid, fblock, fsm, (cudaStream_t)stream>>>(p);
-    else if (min_blocks == 6) env_step_fast_kernel<true, 6><<<fgrid, fblock, fsm, (cudaStream_t)stream>>>(p);
-    else env_step_fast_kernel<true, 0><<<fgrid, fblock, fsm, (cudaStream_t)stream>>>(p);
+    env_step_fast_kernel<<<(num_envs + WPB - 1) / WPB, WPB * 32, fsm, (cudaStream_t)stream>>>(p);
   } else {
     env_step_kernel<false><<<(num_envs + WPB - 1) / WPB, WPB * 32, smem, (cudaStream_t)stream>>>(p);
   }

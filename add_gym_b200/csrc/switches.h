@@ -5,7 +5,6 @@
 struct AddkSwitches {
   int tc_pair;            // ADDK_TC_PAIR         (legacy tf32x3) CTA-pair kernel on / off                      default 1
   int tc_pair_flags;      // ADDK_TC_PAIR_FLAGS   (legacy tf32x3) bit0 cluster-scope waits, bit1 relaxed arrives default 2
-  int h3_flags;           // ADDK_H3_FLAGS        f16x3 persistent kernel experiments: bit0 no stores, bit1 no drains   0
   int h3_persistent;      // ADDK_H3_PERSISTENT   persistent f16x3 kernel for 256-wide layers                    default 1
   int h3_pair;            // ADDK_H3_PAIR         cta_group::2 CTA pairs for the persistent f16x3 / bf16 kernel          default 1
   int h3_chunk_kb;        // ADDK_H3_CHUNK_KB     k-blocks per accumulator drain                                 default 8
@@ -17,8 +16,6 @@ struct AddkSwitches {
   int h3_fused_planes;    // ADDK_H3_FUSED_PLANES dense-layer epilogue writes the fp16 planes of its output      default 0
   int h3_colpart;         // ADDK_H3_COLPART      split pass leaves bias-gradient column sums behind             default 1
   int h3_relu_bits;       // ADDK_H3_RELU_BITS    optimizer step: ReLU masks travel as bit planes (arena_bits)  default 1
-  int step_cta_tail;      // ADDK_STEP_CTA_TAIL   reward / done tail of the step kernel run per CTA              default 1
   int fused_tail;         // ADDK_FUSED_TAIL      optimizer step: slab reduction + AdamW + diagnostics row in one launch      default 1
-  int step_min_blocks;    // ADDK_STEP_MIN_BLOCKS occupancy experiment of the step kernel (0 | 5 | 6)            default 0
 };
 const AddkSwitches& addk_switches();
