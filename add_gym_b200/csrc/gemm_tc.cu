@@ -1118,7 +1118,10 @@ gemm_tc_h3p_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
       for (int t = unit; t < pp.total_tiles; t += units) {
         const int z = t / tiles_mn, r = t - z * tiles_mn;
         const int m0 = (r / pp.tiles_n) * TM + (int)rank * BM;                 // this CTA's 128 rows of A
-        const int n0 = (r % pp.tiles_n) * BN + (int)rank * C::B_ROWS * (PAIR ? 1 : 0);     // this CTA's (half of the) B rows
+        // this CTA's (half of the) B rows; a ragged last n-tile is contracted at its effective width (see the MMA issuer)
+        const int nt0 = (r % pp.tiles_n) * BN;
+        const int n_eff = min(BN, ((p.N - nt0 + 31) >> 5) << 5);
+        const int n0 = nt0 + (PAIR ? (int)rank * (n_eff >> 1) : 0);
         const int kb_begin = z * p.kb_per_split;
         const int num_kb = min(kb_total, kb_begin + p.kb_per_split) - kb_begin;
         for (int i = 0; i < num_kb; ++i, ++it) {
@@ -1153,8 +1156,12 @@ gemm_tc_h3p_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
   } else if (warp == 1 && (!PAIR || leader)) {
     // ===================== MMA issuer (PAIR: the leader CTA's, for both) =====================
     const uint32_t fmt = (SINGLE && pp.bf16) ? ((1u << 7) | (1u << 10)) : 0u;      // A / B format: 0 = fp16, 1 = bf16
-    const uint32_t idesc = (1u << 4) | fmt | ((uint32_t)(p.a_mn ? 1 : 0) << 15) | ((uint32_t)(p.b_mn ? 1 : 0) << 16) |
-                           ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+    // (N field per tile: a ragged last n-tile -- the 264-column first-layer weight gradient has 8 valid columns in its
+    //  second tile -- is contracted with N = the valid width rounded up to 32, not 256: an eighth of the tensor-core work
+    //  and energy for that tile.  cta_group::2 takes N/2 columns from each CTA, so the producer loads CTA 1's B rows from
+    //  n0 + N/2; accumulator column j is output column n0 + j either way.)
+    const uint32_t idesc0 = (1u << 4) | fmt | ((uint32_t)(p.a_mn ? 1 : 0) << 15) | ((uint32_t)(p.b_mn ? 1 : 0) << 16) |
+                            ((uint32_t)(TM >> 4) << 24);
     const uint32_t a_lbo = p.a_mn ? C::MN_BOX_BYTES : 16u, b_lbo = p.b_mn ? C::MN_BOX_BYTES : 16u;
     const uint32_t a_sbo = p.a_mn ? 1024u : C::K_SBO, b_sbo = p.b_mn ? 1024u : C::K_SBO;
     constexpr uint32_t K_LAY = BK == 64 ? 2u : 4u;            // K-major tiles: SWIZZLE_128B (128-byte rows) | SWIZZLE_64B
@@ -1172,6 +1179,8 @@ gemm_tc_h3p_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
       const int z = t / tiles_mn;
       const int kb_begin = z * p.kb_per_split;
       const int num_kb = min(kb_total, kb_begin + p.kb_per_split) - kb_begin;
+      const int nt0 = ((t - z * tiles_mn) % pp.tiles_n) * BN;
+      const uint32_t idesc = idesc0 | ((uint32_t)(min(BN, ((p.N - nt0 + 31) >> 5) << 5) >> 3) << 17);
       for (int kb = 0; kb < num_kb; ++g) {
         const uint32_t b = g & 1u;
         const long long c0 = dbg ? clock64() : 0;

@@ -318,6 +318,12 @@ H3P_CASES = [
     ("weight gradient 512x1024 split-K 9, 16385 rows", 512, 1024, MB + 1, 1, 0, "split9"),
     ("weight gradient first layer N=272 split-K 9", 1024, 272, MB, 1, 0, "split9"),
     ("A^T.B^T (both operands transposed)", 8192, 1024, 1024, 1, 1, None),
+    # ragged last n-tile: contracted at its effective width (N = 32 .. 224 instead of 256; each CTA of the pair then
+    # stages its half of THAT width)
+    ("weight gradient first layer N=264 split-K 9", 1024, 264, MB, 1, 0, "split9"),
+    ("forward ragged N=400 (K-major B, second tile 160 wide)", MB, 400, 512, 0, 1, "bias_relu"),
+    ("input gradient ragged N=456 (MN-major B, second tile 224 wide)", MB, 456, 512, 0, 0, None),
+    ("forward ragged N=296 (second tile 64 wide)", MB, 296, 256, 0, 1, None),
 ]
 
 
