@@ -321,6 +321,46 @@ def test_full_size_update_tensor_core_vs_cuda_core_gradients(tc_mode):
     assert max(errs.values()) <= 5e-3, "beyond a few ReLU boundary flips (1/sqrt(8M active units) = 3.5e-4 each)"
 
 
+def test_fused_optimizer_tail_is_bit_identical_to_reduce_then_adamw():
+    """One GPU runs the tail of an optimizer step as ONE launch (reduce_slabs_adamw_kernel: split-K slab reduction +
+    AdamW + diagnostics row); the multi-rank path runs reduce_slabs_kernel + finalize_info_kernel inside
+    addk_update_minibatch(do_optim=0) and addk_adamw afterwards.  Same arithmetic element by element: parameters, both
+    moment vectors, the summed gradient and the diagnostics row must come out bit-identical over several steps."""
+    from add_gym_b200 import _lib
+    from add_gym_b200.add_agent import ADDAgent
+
+    def make():
+        cfg = b200_config.default_config(num_envs=96)
+        cfg["engine"].update(seed=11, noise_device="device", fall_prob=0.02)
+        torch.manual_seed(3)
+        torch.cuda.manual_seed(3)
+        a = ADDAgent(cfg, device="cuda:0")
+        a._curr_obs, a._curr_info = a._reset_envs()
+        a._exp_buffer.clear()
+        a._rollout_train(a._steps_per_iter)
+        a._build_train_data()
+        return a
+
+    fused, split = make(), make()
+    assert torch.equal(fused._model.flat, split._model.flat)
+    L = _lib.lib()
+    g = torch.Generator(device="cuda").manual_seed(5)
+    for step in range(4):
+        idx = torch.randint(0, 96 * fused._steps_per_iter, (fused._mb_rows,), device="cuda", generator=g)
+        _lib.check(L.addk_update_minibatch(_lib.stream(), fused._ctx.buf, _lib.ptr(idx), C.c_int(step), C.c_int(step + 1)), "fused")
+        _lib.check(L.addk_update_minibatch(_lib.stream(), split._ctx.buf, _lib.ptr(idx), C.c_int(step), C.c_int(0)), "split")
+        opt = split._optimizer
+        _lib.check(L.addk_adamw(_lib.stream(), _lib.ptr(split._model.flat), _lib.ptr(split._model.flat_grad), _lib.ptr(opt.exp_avg),
+                                _lib.ptr(opt.exp_avg_sq), C.c_longlong(split._model.num_params), C.c_int(step + 1),
+                                C.c_double(opt.lr), C.c_double(opt.betas[0]), C.c_double(opt.betas[1]), C.c_double(opt.eps),
+                                C.c_double(opt.weight_decay), C.c_double(1.0)), "addk_adamw")
+        assert torch.equal(fused._model.flat_grad, split._model.flat_grad), step
+        assert torch.equal(fused._model.flat, split._model.flat), step
+        assert torch.equal(fused._optimizer.exp_avg, opt.exp_avg) and torch.equal(fused._optimizer.exp_avg_sq, opt.exp_avg_sq), step
+        assert torch.equal(fused._ws["info"][step], split._ws["info"][step]), step
+    assert float(fused._model.flat.abs().max()) > 0 and bool(torch.isfinite(fused._model.flat).all())
+
+
 def test_empty_and_ragged_requests():
     from add_gym_b200.add_motion import ADDMotion
     from add_gym_b200.env import ImitationEnvironment
