@@ -603,22 +603,6 @@ __global__ void scale_by_coef_kernel(float* __restrict__ g, long long n, const f
   if (blockIdx.x == 0 && threadIdx.x < (n & 3)) g[4 * n4 + threadIdx.x] *= c;
 }
 
-struct Seg { long long begin, end; int nslabs; float l2; };
-struct SegTable { Seg s[24]; int n; long long P; };
-
-// grads[i] = sum over the split-K slabs of segment(i) + l2 * param[i]
-__global__ void reduce_slabs_kernel(const __grid_constant__ SegTable t, const float* __restrict__ slabs,
-                                    const float* __restrict__ params, float* __restrict__ grads) {
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= t.P) return;
-  int ns = 0; float l2 = 0.f;
-  for (int k = 0; k < t.n; ++k) if (i >= t.s[k].begin && i < t.s[k].end) { ns = t.s[k].nslabs; l2 = t.s[k].l2; break; }
-  float g = 0.f;
-  for (int s = 0; s < ns; ++s) g += slabs[(size_t)s * t.P + i];
-  if (l2 != 0.f) g += l2 * params[i];
-  grads[i] = g;
-}
-
 struct InfoArgs { const double* st; const int* cnt; int M; float bound_w, critic_w, disc_w, logit_reg, gp, wd; float* info; };
 __device__ __forceinline__ void finalize_info(const InfoArgs& a) {
   const double* st = a.st;
@@ -647,11 +631,27 @@ __device__ __forceinline__ void finalize_info(const InfoArgs& a) {
   info[13] = (float)n;
   info[14] = 0.f; info[15] = 0.f;
 }
-__global__ void finalize_info_kernel(const InfoArgs a) { finalize_info(a); }
+struct Seg { long long begin, end; int nslabs; float l2; };
+struct SegTable { Seg s[24]; int n; long long P; };
+
+// grads[i] = sum over the split-K slabs of segment(i) + l2 * param[i]
+__global__ void reduce_slabs_kernel(const __grid_constant__ SegTable t, const float* __restrict__ slabs,
+                                    const float* __restrict__ params, float* __restrict__ grads, const InfoArgs ia) {
+  if (blockIdx.x == 0 && threadIdx.x == 0 && ia.info) finalize_info(ia);      // the diagnostics row of the step
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= t.P) return;
+  int ns = 0; float l2 = 0.f;
+  for (int k = 0; k < t.n; ++k) if (i >= t.s[k].begin && i < t.s[k].end) { ns = t.s[k].nslabs; l2 = t.s[k].l2; break; }
+  float g = 0.f;
+  for (int s = 0; s < ns; ++s) g += slabs[(size_t)s * t.P + i];
+  if (l2 != 0.f) g += l2 * params[i];
+  grads[i] = g;
+}
+
 
 // The tail of an optimizer step as ONE launch (single GPU, no gradient clipping): slab reduction + AdamW + the
-// diagnostics row.  Same arithmetic, element by element, as reduce_slabs_kernel -> adamw_vec4_kernel (adam1) and
-// finalize_info_kernel; the summed gradient is still written (diagnostics / tests read it).  As three launches behind
+// diagnostics row.  Same arithmetic, element by element, as reduce_slabs_kernel (slab sums + diagnostics row) followed by
+// adamw_vec4_kernel (adam1); the summed gradient is still written (diagnostics / tests read it).  As three launches behind
 // the join of the chains the tail ran alone on the GPU for ~80 us of a 1.7 ms step; fused it reads the slabs once and
 // never re-reads the gradient vector.
 __global__ void __launch_bounds__(256) reduce_slabs_adamw_kernel(const __grid_constant__ SegTable t, const float* __restrict__ slabs,
@@ -1457,9 +1457,7 @@ extern "C" int addk_update_minibatch(void* stream, void* ctx_host, const long lo
     ADDK_CHECK_LAUNCH();
     return ADDK_OK;
   }
-  reduce_slabs_kernel<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(t, F(c.slabs), W, F(c.grads));
-  ADDK_CHECK_LAUNCH();
-  finalize_info_kernel<<<1, 1, 0, st>>>(ia);
+  reduce_slabs_kernel<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(t, F(c.slabs), W, F(c.grads), ia);
   ADDK_CHECK_LAUNCH();
   if (do_optim) {
     if (c.grad_clip > 0.0)      // the coefficient lands in info[14] of this step (0 = clipping off)

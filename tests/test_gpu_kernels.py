@@ -323,7 +323,7 @@ def test_full_size_update_tensor_core_vs_cuda_core_gradients(tc_mode):
 
 def test_fused_optimizer_tail_is_bit_identical_to_reduce_then_adamw():
     """One GPU runs the tail of an optimizer step as ONE launch (reduce_slabs_adamw_kernel: split-K slab reduction +
-    AdamW + diagnostics row); the multi-rank path runs reduce_slabs_kernel + finalize_info_kernel inside
+    AdamW + diagnostics row); the multi-rank path runs reduce_slabs_kernel (slab sums + diagnostics row) inside
     addk_update_minibatch(do_optim=0) and addk_adamw afterwards.  Same arithmetic element by element: parameters, both
     moment vectors, the summed gradient and the diagnostics row must come out bit-identical over several steps."""
     from add_gym_b200 import _lib
