@@ -717,9 +717,10 @@ __global__ void sample_action_kernel(const float* __restrict__ mean, int act_ld,
 // Normalizer.normalize for a block of rows (normalizer.py:107-110): out = (x - mean) / std, 128-bit when dim % 4 == 0
 __global__ void obs_normalize_kernel(const float* __restrict__ x, const float* __restrict__ mean,
                                      const float* __restrict__ sd, long long rows, int dim, int ld_out, float* __restrict__ out,
-                                     uint16_t* __restrict__ out16) {
+                                     uint16_t* __restrict__ out16, uint32_t* slot) {
   const int q = ld_out / 4;                          // float4 slots per output row; slots >= dim / 4 are zero padding
   const long long n4 = rows * q;
+  float vm = 0.f;                                    // max|out| of what this thread writes (f16x3: left in `slot`)
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     const long long r = i / q;
     const int c = (int)(i - r * q) * 4;
@@ -730,8 +731,10 @@ __global__ void obs_normalize_kernel(const float* __restrict__ x, const float* _
       o = make_float4(sub_rn(v.x, m.x) / s.x, sub_rn(v.y, m.y) / s.y, sub_rn(v.z, m.z) / s.z, sub_rn(v.w, m.w) / s.w);
     }
     stg4(out + 4 * i, o);
+    vm = fmaxf(fmaxf(vm, fmaxf(fabsf(o.x), fabsf(o.y))), fmaxf(fabsf(o.z), fabsf(o.w)));
     if (out16) { out16[4 * i] = to_bf16(o.x); out16[4 * i + 1] = to_bf16(o.y); out16[4 * i + 2] = to_bf16(o.z); out16[4 * i + 3] = to_bf16(o.w); }
   }
+  amax_commit(vm, slot);
 }
 
 // wd0_pad[r, c] = c < dim ? W[r, c] : 0 : the discriminator's first-layer weight with 16-byte aligned rows, so that
@@ -1191,7 +1194,8 @@ static int trunk_forward(cudaStream_t st, const Ctx& c, const ChainWs& ws, const
     // tensor-core modes: normalise into the minibatch scratch first (TMA cannot apply it on load), then the TC tile
     const long long n4 = (long long)rows * OL / 4;
     int bl = (int)((n4 + 255) / 256); if (bl > 148 * 8) bl = 148 * 8;
-    obs_normalize_kernel<<<bl, 256, 0, st>>>(X, nmean, nstd, rows, in_dim, OL, F(c.xn), twin16(c.xn));
+    uint16_t* const xn16 = twin16(c.xn);
+    obs_normalize_kernel<<<bl, 256, 0, st>>>(X, nmean, nstd, rows, in_dim, OL, F(c.xn), xn16, amax_hook(st, c.xn, rows, OL, OL));
     ADDK_CHECK_LAUNCH();
     X = F(c.xn); ldx = OL; nmean = nullptr; nstd = nullptr;
   }
