@@ -258,10 +258,11 @@ def test_sampler_update_errors_matches_oracle():
 # ---------------------------------------------------------------------------------------------------------------
 # full-size checks (BASELINE configs[1] / configs[4] shapes)
 # ---------------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("num_envs", [4096])
+@pytest.mark.parametrize("num_envs", [4096, 32768])
 def test_full_size_rollout_steps_match_oracle(num_envs):
-    """Four env steps at 4096 envs through the lean fused kernel + masked reset, against the oracle on the same synthetic
-    physics stream: flags / ids bit-exact, rows 1e-5."""
+    """Four env steps at 4096 envs (BASELINE configs[1]) and at 32768 envs (configs[4], the largest configuration) through
+    the lean fused kernel + masked reset, against the oracle on the same synthetic physics stream: flags / ids bit-exact,
+    rows 1e-5."""
     import parity_helpers as helpers
     import test_gpu_parity as T
     oracle, agent, rec = T._pair(num_envs, None, fall_prob=0.01)
