@@ -515,6 +515,12 @@ def test_full_size_iteration_parity_bf16_4096_envs():
     _iteration_parity(4096, None, steps_synced=2, precision="bf16", tol=2e-2)
 
 
+def test_full_size_iteration_parity_bf16_8192_envs():
+    """BASELINE configs[3] at its own size: 8192 envs, bf16 dense layers, one optimizer step at the 32768-row minibatch
+    (the rollout and build_train_data over 262144 rows included), same bars as the 4096-env case."""
+    _iteration_parity(8192, None, steps_synced=1, precision="bf16", tol=2e-2)
+
+
 def test_iteration_parity_local_obs_golden():
     """Golden case 3 of the executed reference: local-frame observations with velocity and phase features
     (global_obs=False, enable_vel_obs=True, enable_phase_obs=True) on the three-clip library."""
